@@ -1,0 +1,103 @@
+"""ctypes binding of libdfvit.so (C ABI declared in include/dfvit.h).
+
+There is no fallback: if the shared library is missing, importing this module raises, and
+every launch entry point refuses non-sm_100 devices (DFV_ERR_DEVICE) -- the product has no
+CPU or stock-PyTorch code path.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdfvit.so")
+
+DFV_F32, DFV_BF16 = 0, 1
+DFV_ACT_NONE, DFV_ACT_SILU = 0, 1
+(W_STEM, W_STEM_BIAS, W_EXPAND, W_EXPAND_BIAS, W_DW, W_DW_BIAS, W_SE_REDUCE, W_SE_REDUCE_BIAS,
+ W_SE_EXPAND, W_SE_EXPAND_BIAS, W_PROJECT, W_PROJECT_BIAS, W_HEAD, W_HEAD_BIAS) = range(14)
+
+
+class DfvError(RuntimeError):
+    pass
+
+
+class BlockInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "c_in", "c_mid", "c_out", "kernel", "stride", "pad_lo", "pad_hi", "se_squeeze", "has_expand", "has_skip")]
+
+
+class InferArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("use_attention", C.c_int32), ("use_landmark", C.c_int32), ("use_channel", C.c_int32),
+        ("use_spatial", C.c_int32), ("heat_group", C.c_int32), ("landmark_ref_size", C.c_float),
+        ("blob", C.c_void_p), ("images_nchw", C.c_void_p), ("landmarks", C.c_void_p),
+        ("lm_weights", C.c_void_p), ("ca_w1", C.c_void_p), ("ca_w2_t", C.c_void_p),
+        ("ca_hidden", C.c_int32), ("sa_w", C.c_void_p),
+        ("head_w_t", C.POINTER(C.c_void_p)), ("head_b", C.POINTER(C.c_void_p)),
+        ("head_dims", C.POINTER(C.c_int32)), ("head_layers", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("logits", C.c_void_p), ("features", C.c_void_p), ("heat", C.c_void_p),
+        ("taps", C.POINTER(C.c_void_p)),
+    ]
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C deepfake_vit_b200/csrc`). deepfake_vit_b200 has no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+    sigs = {
+        "dfv_version": (C.c_int, []),
+        "dfv_last_error": (C.c_char_p, []),
+        "dfv_device_check": (C.c_int, []),
+        "dfv_debug_force_simt_gemm": (None, [i32]),
+        "dfv_launch_count": (i64, [i32]),
+        "dfv_b4_num_blocks": (C.c_int, []),
+        "dfv_b4_block": (C.c_int, [i32, C.POINTER(BlockInfo)]),
+        "dfv_b4_stem_channels": (C.c_int, []),
+        "dfv_b4_head_channels": (C.c_int, []),
+        "dfv_b4_output_hw": (C.c_int, [i32, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "dfv_blob_bytes": (sz, [i32]),
+        "dfv_blob_slot": (C.c_int, [i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]),
+        "dfv_stem_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "dfv_dwconv_pool_parts": (C.c_int, [i32] * 8),
+        "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
+        "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "dfv_pw_gemm_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, vp]),
+        "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
+        "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 8 + [i32] * 8 + [vp]),
+        "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, i32, vp]),
+        "dfv_combined_loss_fwd_bwd": (C.c_int, [vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, i32, i32, i32,
+                                                C.POINTER(C.c_int), vp]),
+        "dfv_infer_workspace_bytes": (sz, [i32, i32, i32, i32]),
+        "dfv_infer_fwd": (C.c_int, [C.POINTER(InferArgs), vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)          # AttributeError if the header and library disagree
+        fn.restype, fn.argtypes = res, args
+    return lib, tuple(sigs)
+
+
+lib, EXPORTS = _load()
+
+
+def check(rc: int):
+    if rc != 0:
+        raise DfvError(f"libdfvit error {rc}: {lib.dfv_last_error().decode(errors='replace')}")
+
+
+def b4_blocks():
+    out = []
+    for i in range(lib.dfv_b4_num_blocks()):
+        bi = BlockInfo()
+        check(lib.dfv_b4_block(i, C.byref(bi)))
+        out.append(bi)
+    return out
+
+
+def blob_slot(dtype: int, block: int, kind: int):
+    off, n = C.c_size_t(), C.c_size_t()
+    check(lib.dfv_blob_slot(dtype, block, kind, C.byref(off), C.byref(n)))
+    return off.value, n.value

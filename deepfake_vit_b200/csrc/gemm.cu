@@ -1,0 +1,406 @@
+// Pointwise (1x1) convolution as a GEMM with fused epilogue:
+//   out[M][N] = act((a[M][K] * gate[image][K]) . w[N][K]^T + bias[N]) + residual[M][N]
+//
+// bf16 path (pw_gemm_tc_kernel): persistent, warp-specialised tcgen05 kernel
+//   warp 0      TMA producer: A tile 128 x 64 and B tile BN x 64 per k-block, 128B-swizzled
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16, fp32 accumulators
+//               in TMEM (2 stages x 256 columns), owns TMEM alloc/dealloc
+//   warps 2-5   SE-gate transform (project GEMMs only): multiply the landed A tile in shared
+//               memory by the per-image channel gate, fence.proxy.async, hand to the MMA warp.
+//               (x (.) s) . W is thereby applied on the operand path; the gated tensor is
+//               never written to HBM.
+//   warps 6-13  epilogue: tcgen05.ld -> +bias -> swish -> +residual -> bf16 -> global
+// Most of these GEMMs are HBM-bound (K/N of 24..960: AI < 218 flop/B); only the 12x12-stage
+// layers (K or N >= 1632, head 448x1792) are tensor-bound.
+//
+// fp32 path / debug (pw_gemm_simt_kernel): plain tiled FFMA kernel, exact fp32 arithmetic for
+// the 1e-4 parity mode.
+#include "common.cuh"
+
+namespace dfv {
+
+// ------------------------------------------------------------------------------------
+// SIMT kernel
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f(float& d, float v) { d = v; }
+__device__ __forceinline__ void from_f(__nv_bfloat16& d, float v) { d = __float2bfloat16_rn(v); }
+
+template <typename T, bool kFast>
+__global__ void __launch_bounds__(256) pw_gemm_simt_kernel(const T* __restrict__ a, const T* __restrict__ w,
+                                                          const float* __restrict__ bias,
+                                                          const float* __restrict__ a_scale, int rows_per_image,
+                                                          const T* __restrict__ residual, T* __restrict__ out,
+                                                          long long M, int K, int N, int act) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Ws[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const long long m0 = (long long)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    // 64 rows x 16 k = 1024 elements per operand, 4 per thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx / TK, kk = idx % TK;
+      const long long m = m0 + r;
+      const int k = k0 + kk;
+      float va = 0.f, vw = 0.f;
+      if (m < M && k < K) {
+        va = to_f(a[(size_t)m * K + k]);
+        if (a_scale) {
+          va *= a_scale[(size_t)(m / rows_per_image) * K + k];
+          if constexpr (sizeof(T) == 2) va = __bfloat162float(__float2bfloat16_rn(va));  // as the tc path rounds
+        }
+      }
+      if (n0 + r < N && k < K) vw = to_f(w[(size_t)(n0 + r) * K + k]);
+      As[kk][r] = va;
+      Ws[kk][r] = vw;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float av[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + bias[n];
+      if (act == DFV_ACT_SILU) v = silu<kFast>(v);
+      if (residual) v += to_f(residual[(size_t)m * N + n]);
+      from_f(out[(size_t)m * N + n], v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------
+constexpr int kBM = 128;        // UMMA M (cta_group::1)
+constexpr int kBK = 64;         // one 128-byte swizzle atom of bf16 along K
+constexpr int kMaxStages = 8;
+constexpr int kTcThreads = 448; // 14 warps
+constexpr int kFirstXformWarp = 2, kFirstEpiWarp = 6, kNumEpiWarps = 8;
+constexpr uint32_t kTmemCols = 512;
+
+struct TcParams {
+  long long M;
+  int K, N;
+  int BN;             // N tile (multiple of 16, <= 256)
+  int n_tiles_n;
+  long long n_tiles;  // total tiles
+  int k_blocks;
+  int stages;
+  int rows_per_image;
+  int act;
+};
+
+struct __align__(8) TcBarriers {
+  uint64_t full[kMaxStages];    // TMA landed
+  uint64_t ready[kMaxStages];   // SE transform done
+  uint64_t empty[kMaxStages];   // MMAs that read the stage completed
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B: 8-row core-matrix groups are 1024 B apart (SBO); LBO unused.
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+template <bool kHasScale>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                      const float* __restrict__ bias, const float* __restrict__ a_scale,
+                      const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the dynamic-smem base
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t a_bytes = kBM * kBK * 2;
+  const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  unsigned char* tiles = smem;
+  float* bias_sm = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  const int n_pad = p.n_tiles_n * p.BN;
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(reinterpret_cast<unsigned char*>(bias_sm) + (size_t)((n_pad * 4 + 15) / 16) * 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) bias_sm[i] = i < p.N ? bias[i] : 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->ready[s], 128);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->tmem_full[s], 1);
+      mbar_init(&bars->tmem_empty[s], kNumEpiWarps);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const long long mt = t / p.n_tiles_n;
+        const int nt = (int)(t % p.n_tiles_n);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          unsigned char* sa = tiles + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&bars->full[stage], stage_bytes);
+          tma_load_2d(sa, &tm_a, &bars->full[stage], kb * kBK, (int)(mt * kBM));
+          tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(kHasScale ? &bars->ready[stage] : &bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
+          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + a_bytes);
+          const int k_left = p.K - kb * kBK;
+          const int ksteps = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&bars->empty[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->tmem_full[as]);
+      }
+    }
+  } else if (warp < kFirstEpiWarp) {
+    // ------------------------------------------------------------- SE-gate transform
+    if constexpr (kHasScale) {
+      const int row = (warp - kFirstXformWarp) * 32 + lane;   // 0..127, one tile row per thread
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const long long m = (t / p.n_tiles_n) * kBM + row;
+        const bool valid = m < p.M;
+        const float* srow = a_scale + (size_t)(valid ? m / p.rows_per_image : 0) * p.K;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          if (valid) {
+            unsigned char* arow = tiles + (size_t)stage * stage_bytes + (size_t)row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int k0 = kb * kBK + c * 8;
+              if (k0 < p.K) {
+                uint4* ptr = reinterpret_cast<uint4*>(arow + ((c ^ (row & 7)) << 4));
+                uint4 u = *ptr;
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(srow + k0));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(srow + k0 + 4));
+                u.x = pack_bf16(bf16_lo(u.x) * s0.x, bf16_hi(u.x) * s0.y);
+                u.y = pack_bf16(bf16_lo(u.y) * s0.z, bf16_hi(u.y) * s0.w);
+                u.z = pack_bf16(bf16_lo(u.z) * s1.x, bf16_hi(u.z) * s1.y);
+                u.w = pack_bf16(bf16_lo(u.w) * s1.z, bf16_hi(u.w) * s1.w);
+                *ptr = u;
+              }
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(&bars->ready[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int half = (warp - kFirstEpiWarp) >> 2;    // column half
+    const int chunks = p.BN >> 4;
+    const int c_begin = half == 0 ? 0 : (chunks + 1) / 2;
+    const int c_end = half == 0 ? (chunks + 1) / 2 : chunks;
+    int it = 0;
+    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const long long m = (t / p.n_tiles_n) * kBM + q * 32 + lane;
+      const int nt = (int)(t % p.n_tiles_n);
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
+      for (int cc = c_begin; cc < c_end; ++cc) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tbase + (uint32_t)cc * 16, v);
+        tmem_ld_wait();
+        const int n0 = nt * p.BN + cc * 16;
+        if (m < p.M) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = n0 + h * 8;
+            if (n < p.N) {
+              float o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x = __uint_as_float(v[h * 8 + j]) + bias_sm[n + j];
+                o[j] = p.act == DFV_ACT_SILU ? silu<true>(x) : x;
+              }
+              if (residual != nullptr) {
+                float r[8];
+                load8(residual + (size_t)m * p.N + n, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] += r[j];
+              }
+              store8(out + (size_t)m * p.N + n, o);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+static int launch_tc(const void* a, const void* w, const float* bias, const float* a_scale, int rows_per_image,
+                     const void* residual, void* out, long long M, int K, int N, int act, cudaStream_t st) {
+  TcParams p;
+  p.M = M;
+  p.K = K;
+  p.N = N;
+  p.n_tiles_n = (N + 255) / 256;
+  p.BN = (((N + p.n_tiles_n - 1) / p.n_tiles_n) + 15) / 16 * 16;
+  p.n_tiles = ((M + kBM - 1) / kBM) * p.n_tiles_n;
+  p.k_blocks = (K + kBK - 1) / kBK;
+  p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
+  p.act = act;
+  const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;
+  const size_t tail = align_up((size_t)p.n_tiles_n * p.BN * 4, 16) + sizeof(TcBarriers) + 64 + 1024;
+  const size_t budget = 220 * 1024;
+  int stages = (int)((budget - tail) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  DFV_REQUIRE(stages >= 2, "dfv_pw_gemm_fwd: tile does not fit shared memory (N=%d)", N);
+  p.stages = stages;
+  // keep one CTA per SM (each allocates all 512 TMEM columns): ask for > half of the SM's smem
+  size_t smem = (size_t)stages * stage_bytes + tail;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+
+  CUtensorMap tm_a, tm_b;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kBM};
+    DFV_TRY(make_tensor_map(&tm_a, DFV_BF16, 2, a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)p.BN};
+    DFV_TRY(make_tensor_map(&tm_b, DFV_BF16, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  long long grid = p.n_tiles < (long long)num_sms() ? p.n_tiles : (long long)num_sms();
+  static thread_local bool configured[2] = {false, false};
+  if (a_scale) {
+    if (!configured[1]) {
+      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured[1] = true;
+    }
+    pw_gemm_tc_kernel<true><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, bias, a_scale, (const __nv_bfloat16*)residual,
+                                                                    (__nv_bfloat16*)out, p);
+  } else {
+    if (!configured[0]) {
+      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      configured[0] = true;
+    }
+    pw_gemm_tc_kernel<false><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, bias, a_scale, (const __nv_bfloat16*)residual,
+                                                                     (__nv_bfloat16*)out, p);
+  }
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+}  // namespace dfv
+
+using namespace dfv;
+
+extern "C" int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, const float* a_scale, int rows_per_image,
+                               const void* residual, void* out, int dtype, long long M, int K, int N, int act,
+                               dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(a && w && bias && out, "dfv_pw_gemm_fwd: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype), "dfv_pw_gemm_fwd: bad dtype %d", dtype);
+  DFV_REQUIRE(M > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0, "dfv_pw_gemm_fwd: need K %% 8 == 0 and N %% 8 == 0 (M=%lld K=%d N=%d)", M, K, N);
+  DFV_REQUIRE(!a_scale || (rows_per_image > 0 && M % rows_per_image == 0), "dfv_pw_gemm_fwd: a_scale needs rows_per_image dividing M");
+  DFV_REQUIRE(act == DFV_ACT_NONE || act == DFV_ACT_SILU, "dfv_pw_gemm_fwd: bad act %d", act);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == DFV_BF16 && !force_simt_gemm())
+    return launch_tc(a, w, bias, a_scale, rows_per_image, residual, out, M, K, N, act, st);
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+  if (dtype == DFV_BF16)
+    pw_gemm_simt_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)w, bias, a_scale,
+                                                               rows_per_image, (const __nv_bfloat16*)residual,
+                                                               (__nv_bfloat16*)out, M, K, N, act);
+  else
+    pw_gemm_simt_kernel<float, false><<<grid, 256, 0, st>>>((const float*)a, (const float*)w, bias, a_scale, rows_per_image,
+                                                         (const float*)residual, (float*)out, M, K, N, act);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}

@@ -1,0 +1,383 @@
+"""Drop-in for the reference's model classes, computed by libdfvit (sm_100a CUDA kernels).
+
+Mirrors the reference's nn.Module API for the hot path:
+  DeepfakeDetectionModel      src/feature_extraction/feature_extractor.py:184-299
+  DeepfakeFeatureExtractor    src/feature_extraction/feature_extractor.py:16-178
+  EfficientNetB4Backbone      src/feature_extraction/efficientnet.py:13-170
+  HybridAttention & friends   src/feature_extraction/landmark_attention.py:13-310
+Same constructor arguments (the YAML `model:` mapping, config/model_config.yaml:4-19), same
+`forward(images, landmarks=None, return_features=False) -> (logits, features|None)`, same
+module tree and therefore the same state_dict keys, so
+`best_model.pth`-style checkpoints load with strict=True in either direction.
+
+The sub-modules below only HOLD parameters (they are torch modules so that registration
+order, default initialisation and state_dict layout are exactly the reference's); none of
+their `forward`s is ever used.  All arithmetic happens in libdfvit through one C call.
+"""
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import check, lib
+
+BN_EPS, BN_MOM = 1e-3, 0.01   # efficientnet-pytorch global params for B4
+
+
+def _holder(cls):
+    class Holder(cls):
+        def forward(self, *a, **k):   # pragma: no cover
+            raise RuntimeError(f"{cls.__name__} here is a parameter holder; libdfvit computes this layer")
+    Holder.__name__ = Holder.__qualname__ = cls.__name__
+    return Holder
+
+
+_Conv2d, _BN2d, _BN1d, _Linear = (_holder(c) for c in (nn.Conv2d, nn.BatchNorm2d, nn.BatchNorm1d, nn.Linear))
+
+
+class _MBConvParams(nn.Module):
+    """Parameters of one MBConvBlock of efficientnet-pytorch 0.7.1 (names as upstream)."""
+
+    def __init__(self, info: _lib.BlockInfo):
+        super().__init__()
+        self.info = {f[0]: getattr(info, f[0]) for f in info._fields_}
+        cin, cmid, cout, k, sq = info.c_in, info.c_mid, info.c_out, info.kernel, info.se_squeeze
+        if info.has_expand:
+            self._expand_conv = _Conv2d(cin, cmid, 1, bias=False)
+            self._bn0 = _BN2d(cmid, eps=BN_EPS, momentum=BN_MOM)
+        self._depthwise_conv = _Conv2d(cmid, cmid, k, stride=info.stride, groups=cmid, bias=False)
+        self._bn1 = _BN2d(cmid, eps=BN_EPS, momentum=BN_MOM)
+        self._se_reduce = _Conv2d(cmid, sq, 1)
+        self._se_expand = _Conv2d(sq, cmid, 1)
+        self._project_conv = _Conv2d(cmid, cout, 1, bias=False)
+        self._bn2 = _BN2d(cout, eps=BN_EPS, momentum=BN_MOM)
+
+
+class _EfficientNetB4Params(nn.Module):
+    """Parameter tree of `EfficientNet.from_name('efficientnet-b4')` with `_fc = Identity`."""
+
+    def __init__(self):
+        super().__init__()
+        stem_c, head_c = lib.dfv_b4_stem_channels(), lib.dfv_b4_head_channels()
+        self._conv_stem = _Conv2d(3, stem_c, 3, stride=2, bias=False)
+        self._bn0 = _BN2d(stem_c, eps=BN_EPS, momentum=BN_MOM)
+        blocks = _lib.b4_blocks()
+        self._blocks = nn.ModuleList(_MBConvParams(b) for b in blocks)
+        self._conv_head = _Conv2d(blocks[-1].c_out, head_c, 1, bias=False)
+        self._bn1 = _BN2d(head_c, eps=BN_EPS, momentum=BN_MOM)
+        # upstream builds Linear(1792, 1000) here and the reference replaces it with Identity
+        # (efficientnet.py:68); build-and-drop keeps seeded initialisation identical.
+        nn.Linear(head_c, 1000)
+        self._fc = nn.Identity()
+        self.head_channels = head_c
+
+
+class EfficientNetB4Backbone(nn.Module):
+    def __init__(self, pretrained=True, freeze_bn=False, dropout_rate=0.4, extract_features=True):
+        super().__init__()
+        # `pretrained` only matters if ./model/efficientnet-b4-6ed6700e.pth exists in the
+        # reference (efficientnet.py:48-54); offline it never does -> random init, never raises.
+        self.backbone = _EfficientNetB4Params()
+        self.extract_features = extract_features
+        self.freeze_bn = freeze_bn
+        self.feature_dim = self.backbone.head_channels
+        self.dropout = nn.Dropout(p=dropout_rate)
+        self.intermediate_features: Dict[str, torch.Tensor] = {}
+        if freeze_bn:
+            self._freeze_bn_layers()
+
+    def _freeze_bn_layers(self):
+        for m in self.backbone.modules():
+            if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                m.eval()
+                for p in m.parameters():
+                    p.requires_grad = False
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        if self.freeze_bn:
+            self._freeze_bn_layers()
+        return self
+
+
+class LandmarkAttention(nn.Module):
+    def __init__(self, feature_size=(7, 7), sigma=1.5, learnable=True):
+        super().__init__()
+        self.feature_size, self.sigma, self.learnable = feature_size, sigma, learnable
+        if learnable:
+            self.attention_weights = nn.Parameter(torch.ones(5))
+        else:
+            self.register_buffer("attention_weights", torch.ones(5))
+
+    def _create_attention_map(self, landmarks, feature_size, device=None, group=0):
+        """(B,1,H,W) heat-map, landmark_attention.py:76-130, computed by dfv_landmark_heatmap_fwd."""
+        H, W = feature_size
+        lm = landmarks.detach().to(self.attention_weights.device, torch.float32).contiguous()
+        heat = ops.landmark_heatmap(lm, self.attention_weights.detach().float().contiguous(), H, W, 224.0,
+                                    self.sigma, group)
+        return heat.unsqueeze(1)
+
+
+class SpatialAttention(nn.Module):
+    def __init__(self, kernel_size=7):
+        super().__init__()
+        self.conv = _Conv2d(2, 1, kernel_size, padding=kernel_size // 2, bias=False)
+        self.sigmoid = nn.Sigmoid()
+
+
+class ChannelAttention(nn.Module):
+    def __init__(self, channels, reduction=16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.max_pool = nn.AdaptiveMaxPool2d(1)
+        self.fc = nn.Sequential(_Linear(channels, channels // reduction, bias=False), nn.ReLU(inplace=True),
+                                _Linear(channels // reduction, channels, bias=False))
+        self.sigmoid = nn.Sigmoid()
+
+
+class HybridAttention(nn.Module):
+    def __init__(self, channels, feature_size=(7, 7), use_landmark=True, use_spatial=True, use_channel=True):
+        super().__init__()
+        self.use_landmark, self.use_spatial, self.use_channel = use_landmark, use_spatial, use_channel
+        if use_landmark:
+            self.landmark_attn = LandmarkAttention(feature_size=feature_size, learnable=True)
+        if use_spatial:
+            self.spatial_attn = SpatialAttention()
+        if use_channel:
+            self.channel_attn = ChannelAttention(channels)
+
+
+class DeepfakeFeatureExtractor(nn.Module):
+    def __init__(self, pretrained=True, freeze_bn=False, dropout_rate=0.4, use_attention=True,
+                 attention_config: Optional[Dict] = None):
+        super().__init__()
+        self.backbone = EfficientNetB4Backbone(pretrained=pretrained, freeze_bn=freeze_bn,
+                                               dropout_rate=dropout_rate, extract_features=True)
+        self.use_attention = use_attention
+        self.feature_dim = self.backbone.feature_dim
+        if use_attention:
+            if attention_config is None:
+                attention_config = {"use_landmark": True, "use_spatial": True, "use_channel": True}
+            self.attention = HybridAttention(channels=self.feature_dim, feature_size=(7, 7), **attention_config)
+        else:
+            self.attention = None
+
+
+class _Packed:
+    """Folded, device-resident weights for one (dtype, device) pair."""
+
+    def __init__(self):
+        self.key = None
+        self.blob = None
+        self.head: Optional[ops.HeadPack] = None
+        self.lm_w = self.ca_w1 = self.ca_w2_t = self.sa_w = None
+
+
+class DeepfakeDetectionModel(nn.Module):
+    """Reference-compatible module whose forward is one libdfvit call."""
+
+    def __init__(self, num_classes: int = 2, pretrained: bool = True,
+                 feature_extractor_config: Optional[Dict] = None,
+                 classifier_hidden_dims: List[int] = [512, 128, 32], dropout_rate: float = 0.4):
+        super().__init__()
+        if feature_extractor_config is None:   # top-level `pretrained` ignored otherwise (:210-218)
+            feature_extractor_config = {"pretrained": pretrained, "use_attention": True}
+        self.feature_extractor = DeepfakeFeatureExtractor(**feature_extractor_config)
+        layers, d = [], self.feature_extractor.feature_dim
+        for h in classifier_hidden_dims:
+            layers += [_Linear(d, h), _BN1d(h), nn.ReLU(inplace=True), nn.Dropout(dropout_rate)]
+            d = h
+        layers.append(_Linear(d, num_classes))
+        self.classifier = nn.Sequential(*layers)
+        self.num_classes = num_classes
+        # ---- knobs that are not part of the reference API
+        self.compute_dtype = torch.bfloat16     # or torch.float32 (parity mode)
+        self.landmark_max_group = 0             # images per heat-map max group; 0 = whole call (reference)
+        self._packed: Dict[Tuple, _Packed] = {}
+        self._workspace: Dict[Tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ packing
+    def _version_key(self):
+        return sum(t._version for t in self.state_dict(keep_vars=True).values())
+
+    @staticmethod
+    def _fold(bn):
+        scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+        return scale, bn.bias.float() - bn.running_mean.float() * scale
+
+    @torch.no_grad()
+    def _pack(self, dtype: torch.dtype, device) -> _Packed:
+        key = (dtype, str(device))
+        pk = self._packed.setdefault(key, _Packed())
+        ver = self._version_key()
+        if pk.key == ver:
+            return pk
+        code = ops.dtype_code(dtype)
+        blob = torch.zeros(lib.dfv_blob_bytes(code), dtype=torch.uint8, device=device)
+
+        def put(block, kind, t, as_dtype=torch.float32):
+            off, n = _lib.blob_slot(code, block, kind)
+            t = t.to(device=device, dtype=as_dtype).contiguous()
+            assert t.numel() == n, (block, kind, t.shape, n)
+            blob[off:off + n * t.element_size()].copy_(t.view(-1).view(torch.uint8))
+
+        bb = self.feature_extractor.backbone.backbone
+        s, b = self._fold(bb._bn0)
+        put(-1, _lib.W_STEM, bb._conv_stem.weight.float().permute(2, 3, 1, 0) * s)     # [kh][kw][ci][co]
+        put(-1, _lib.W_STEM_BIAS, b)
+        for i, blk in enumerate(bb._blocks):
+            info = blk.info
+            cmid = info["c_mid"]
+            if info["has_expand"]:
+                s, b = self._fold(blk._bn0)
+                put(i, _lib.W_EXPAND, blk._expand_conv.weight.float().view(cmid, -1) * s[:, None], dtype)
+                put(i, _lib.W_EXPAND_BIAS, b)
+            s, b = self._fold(blk._bn1)
+            kk = info["kernel"] ** 2
+            put(i, _lib.W_DW, (blk._depthwise_conv.weight.float().view(cmid, kk) * s[:, None]).t())   # [k*k][C]
+            put(i, _lib.W_DW_BIAS, b)
+            put(i, _lib.W_SE_REDUCE, blk._se_reduce.weight.float().view(-1, cmid))                   # [sq][C]
+            put(i, _lib.W_SE_REDUCE_BIAS, blk._se_reduce.bias.float())
+            put(i, _lib.W_SE_EXPAND, blk._se_expand.weight.float().view(cmid, -1).t())               # [sq][C]
+            put(i, _lib.W_SE_EXPAND_BIAS, blk._se_expand.bias.float())
+            s, b = self._fold(blk._bn2)
+            put(i, _lib.W_PROJECT, blk._project_conv.weight.float().view(info["c_out"], cmid) * s[:, None], dtype)
+            put(i, _lib.W_PROJECT_BIAS, b)
+        s, b = self._fold(bb._bn1)
+        put(-1, _lib.W_HEAD, bb._conv_head.weight.float().view(bb.head_channels, -1) * s[:, None], dtype)
+        put(-1, _lib.W_HEAD_BIAS, b)
+        pk.blob = blob
+
+        att = self.feature_extractor.attention
+        f32 = dict(device=device, dtype=torch.float32)
+        if att is not None and att.use_landmark:
+            pk.lm_w = att.landmark_attn.attention_weights.detach().to(**f32).contiguous()
+        if att is not None and att.use_channel:
+            pk.ca_w1 = att.channel_attn.fc[0].weight.detach().to(**f32).contiguous()
+            pk.ca_w2_t = att.channel_attn.fc[2].weight.detach().to(**f32).t().contiguous()
+        if att is not None and att.use_spatial:
+            pk.sa_w = att.spatial_attn.conv.weight.detach().to(**f32).reshape(-1).contiguous()
+
+        w_t, bs = [], []
+        mods = list(self.classifier)
+        i = 0
+        while i < len(mods):
+            lin = mods[i]
+            w, bias = lin.weight.float(), lin.bias.float()
+            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
+                s, sh = self._fold(mods[i + 1])
+                w, bias = w * s[:, None], bias * s + sh
+                i += 4          # Linear, BN, ReLU, Dropout
+            else:
+                i += 1
+            w_t.append(w.t().to(**f32).contiguous())
+            bs.append(bias.to(**f32).contiguous())
+        pk.head = ops.HeadPack(w_t, bs)
+        pk.key = ver
+        return pk
+
+    def _ws(self, code, B, H, W, device):
+        key = (code, B, H, W, str(device))
+        ws = self._workspace.get(key)
+        if ws is None:
+            n = lib.dfv_infer_workspace_bytes(code, B, H, W)
+            if n == 0:
+                check(-1)
+            self._workspace = {key: torch.empty(n, dtype=torch.uint8, device=device)}   # keep one shape resident
+            ws = self._workspace[key]
+        return ws
+
+    # ------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def _infer(self, images, landmarks, want_heat=False, taps=False):
+        if not images.is_cuda:
+            raise RuntimeError("deepfake_vit_b200 runs on sm_100 CUDA devices only (no CPU path); move the "
+                               "model and inputs to cuda")
+        check(lib.dfv_device_check())
+        dev = images.device
+        images = images.detach().to(torch.float32).contiguous()
+        B, Cin, H, W = images.shape
+        assert Cin == 3, "images must be (B, 3, H, W)"
+        dtype = self.compute_dtype
+        code = ops.dtype_code(dtype)
+        pk = self._pack(dtype, dev)
+        ws = self._ws(code, B, H, W, dev)
+        att = self.feature_extractor.attention
+        use_att = bool(self.feature_extractor.use_attention and att is not None)
+        ho, wo = C.c_int(), C.c_int()
+        check(lib.dfv_b4_output_hw(H, W, C.byref(ho), C.byref(wo)))
+        Hf, Wf = ho.value, wo.value
+        logits = torch.empty(B, self.num_classes, device=dev, dtype=torch.float32)
+        feats = torch.empty(B, self.feature_extractor.feature_dim, device=dev, dtype=torch.float32)
+        lm = None
+        if landmarks is not None and use_att and att.use_landmark:
+            lm = landmarks.detach().to(device=dev, dtype=torch.float32).contiguous()
+            assert lm.shape == (B, 5, 2), "landmarks must be (B, 5, 2)"
+        heat = torch.empty(B, Hf, Wf, device=dev, dtype=torch.float32) if (want_heat and lm is not None) else None
+
+        tap_tensors, tap_ptrs = None, None
+        if taps:
+            bb = self.feature_extractor.backbone.backbone
+            shapes = [(B, (H - 2) // 2 + 1, (W - 2) // 2 + 1, lib.dfv_b4_stem_channels())]
+            h, w = shapes[0][1], shapes[0][2]
+            for blk in bb._blocks:
+                i = blk.info
+                h = (h + i["pad_lo"] + i["pad_hi"] - i["kernel"]) // i["stride"] + 1
+                w = (w + i["pad_lo"] + i["pad_hi"] - i["kernel"]) // i["stride"] + 1
+                shapes.append((B, h, w, i["c_out"]))
+            shapes.append((B, h, w, bb.head_channels))
+            tap_tensors = [torch.empty(s, device=dev, dtype=dtype) for s in shapes]
+            tap_ptrs = (C.c_void_p * len(shapes))(*[t.data_ptr() for t in tap_tensors])
+
+        a = _lib.InferArgs()
+        a.dtype, a.B, a.H, a.W = code, B, H, W
+        a.use_attention = int(use_att)
+        a.use_landmark = int(use_att and att.use_landmark)
+        a.use_channel = int(use_att and att.use_channel)
+        a.use_spatial = int(use_att and att.use_spatial)
+        a.heat_group = int(self.landmark_max_group)
+        a.landmark_ref_size = 224.0
+        a.blob = pk.blob.data_ptr()
+        a.images_nchw = images.data_ptr()
+        a.landmarks = lm.data_ptr() if lm is not None else None
+        a.lm_weights = pk.lm_w.data_ptr() if pk.lm_w is not None else None
+        a.ca_w1 = pk.ca_w1.data_ptr() if pk.ca_w1 is not None else None
+        a.ca_w2_t = pk.ca_w2_t.data_ptr() if pk.ca_w2_t is not None else None
+        a.ca_hidden = pk.ca_w1.shape[0] if pk.ca_w1 is not None else 0
+        a.sa_w = pk.sa_w.data_ptr() if pk.sa_w is not None else None
+        a.head_w_t, a.head_b = pk.head.wp, pk.head.bp
+        a.head_dims, a.head_layers = C.cast(pk.head.dims, C.POINTER(C.c_int32)), pk.head.n
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.logits, a.features = logits.data_ptr(), feats.data_ptr()
+        a.heat = heat.data_ptr() if heat is not None else None
+        a.taps = tap_ptrs if tap_ptrs is not None else None
+        check(lib.dfv_infer_fwd(C.byref(a), torch.cuda.current_stream().cuda_stream))
+        return logits, feats, heat, tap_tensors
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, images: torch.Tensor, landmarks: Optional[torch.Tensor] = None,
+                return_features: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        if self.training:
+            raise NotImplementedError(
+                "the training path (batch-stat BN, dropout, backward kernels) is not built yet; "
+                "call model.eval() for inference")
+        logits, feats, _, _ = self._infer(images, landmarks)
+        return (logits, feats) if return_features else (logits, None)
+
+    def predict(self, images, landmarks=None, return_probs=True):
+        logits, _ = self.forward(images, landmarks)
+        return torch.softmax(logits, dim=1) if return_probs else logits
+
+    @torch.no_grad()
+    def forward_with_taps(self, images, landmarks=None):
+        """Debug/parity: (logits, features, heat (B,1,h,w)|None, [stem, block0..31, head] NHWC tensors)."""
+        logits, feats, heat, taps = self._infer(images, landmarks, want_heat=True, taps=True)
+        return logits, feats, (heat.unsqueeze(1) if heat is not None else None), taps
+
+    def set_compute_dtype(self, dtype):
+        dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}.get(dtype, dtype)
+        ops.dtype_code(dtype)
+        self.compute_dtype = dtype
+        return self
