@@ -10,5 +10,19 @@ from .losses import CombinedLoss
 from .model import (ChannelAttention, DeepfakeDetectionModel, DeepfakeFeatureExtractor, EfficientNetB4Backbone,
                     HybridAttention, LandmarkAttention, SpatialAttention)
 
-__all__ = ["DeepfakeDetectionModel", "DeepfakeFeatureExtractor", "EfficientNetB4Backbone", "HybridAttention",
+# The `model:` section of the reference's config/model_config.yaml:4-19 as constructor kwargs
+# (`pretrained` is moot offline: the ImageNet file is absent and the reference falls back to
+# random init, efficientnet.py:48-54).
+DEFAULT_MODEL_CONFIG = {
+    "num_classes": 2,
+    "pretrained": False,
+    "feature_extractor_config": {
+        "pretrained": False, "freeze_bn": False, "dropout_rate": 0.4, "use_attention": True,
+        "attention_config": {"use_landmark": True, "use_spatial": True, "use_channel": True},
+    },
+    "classifier_hidden_dims": [512, 128, 32],
+    "dropout_rate": 0.4,
+}
+
+__all__ = ["DEFAULT_MODEL_CONFIG", "DeepfakeDetectionModel", "DeepfakeFeatureExtractor", "EfficientNetB4Backbone", "HybridAttention",
            "LandmarkAttention", "SpatialAttention", "ChannelAttention", "CombinedLoss", "ops"]

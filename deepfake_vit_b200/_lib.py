@@ -54,6 +54,10 @@ def _load():
         "dfv_device_check": (C.c_int, []),
         "dfv_debug_force_simt_gemm": (None, [i32]),
         "dfv_launch_count": (i64, [i32]),
+        "dfv_profile_enable": (C.c_int, [i32]),
+        "dfv_profile_count": (C.c_int, []),
+        "dfv_profile_get": (C.c_int, [i32, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_float)]),
         "dfv_b4_num_blocks": (C.c_int, []),
         "dfv_b4_block": (C.c_int, [i32, C.POINTER(BlockInfo)]),
         "dfv_b4_stem_channels": (C.c_int, []),
@@ -86,6 +90,20 @@ lib, EXPORTS = _load()
 def check(rc: int):
     if rc != 0:
         raise DfvError(f"libdfvit error {rc}: {lib.dfv_last_error().decode(errors='replace')}")
+
+
+PROFILE_KINDS = ("stem", "expand_gemm", "dwconv", "se_gate", "project_gemm", "heatmap", "attention", "mlp_head",
+                 "loss", "gemm_simt")
+
+
+def profile_records():
+    """[(kind_name, algorithmic_bytes, flops, ms)] for every launch recorded since dfv_profile_enable(1)."""
+    out = []
+    k, b, f, ms = C.c_int(), C.c_double(), C.c_double(), C.c_float()
+    for i in range(lib.dfv_profile_count()):
+        check(lib.dfv_profile_get(i, C.byref(k), C.byref(b), C.byref(f), C.byref(ms)))
+        out.append((PROFILE_KINDS[k.value], b.value, f.value, ms.value))
+    return out
 
 
 def b4_blocks():

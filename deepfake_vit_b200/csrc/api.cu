@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace dfv {
@@ -20,6 +22,29 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 bool force_simt_gemm() { return g_force_simt != 0; }
+
+struct ProfRec {
+  cudaEvent_t a, b;
+  int kind;
+  double bytes, flops;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(int kind, double bytes, double flops, cudaStream_t s) : idx(-1), st(s) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.kind = kind;
+  r.bytes = bytes;
+  r.flops = flops;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+  idx = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(g_prof[idx].b, st);
+}
 
 int check_device() {
   static thread_local int cached_dev = -1;
@@ -229,6 +254,27 @@ long long dfv_launch_count(int reset) {
   long long v = g_launches;
   if (reset) g_launches = 0;
   return v;
+}
+
+int dfv_profile_enable(int on) {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return DFV_OK;
+}
+int dfv_profile_count(void) { return (int)g_prof.size(); }
+int dfv_profile_get(int i, int* kind, double* bytes, double* flops, float* ms) {
+  DFV_REQUIRE(i >= 0 && i < (int)g_prof.size() && kind && bytes && flops && ms, "dfv_profile_get: bad index %d", i);
+  const ProfRec& r = g_prof[i];
+  DFV_CUDA(cudaEventSynchronize(r.b));
+  DFV_CUDA(cudaEventElapsedTime(ms, r.a, r.b));
+  *kind = r.kind;
+  *bytes = r.bytes;
+  *flops = r.flops;
+  return DFV_OK;
 }
 
 int dfv_b4_num_blocks(void) { return topology().n; }

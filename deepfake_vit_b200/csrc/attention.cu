@@ -207,6 +207,7 @@ extern "C" int dfv_landmark_heatmap_fwd(const float* landmarks, const float* wei
   const float sx = (float)((double)W / (double)ref_size), sy = (float)((double)H / (double)ref_size);
   const float denom = (float)(2.0 * (double)sigma * (double)sigma);
   const int total = B * H * W;
+  ProfScope prof(PK_HEATMAP, 4.0 * (B * 10.0 + 3.0 * total), 60.0 * total, st);
   heat_raw_kernel<<<(total + 255) / 256, 256, 0, st>>>(landmarks, weights5, raw_ws, max_ws, scaled_xy, B, H, W, sx, sy,
                                                       denom, group);
   DFV_LAUNCH_CHECK();
@@ -228,6 +229,9 @@ extern "C" int dfv_hybrid_attention_fwd(const void* fmap, const float* heat, con
   const size_t smem = sizeof(float) * ((size_t)4 * H * W + 3 * (size_t)C + (size_t)(hidden > 0 ? hidden : 0));
   DFV_REQUIRE(smem <= 200 * 1024, "dfv_hybrid_attention_fwd: map too large for one CTA (H*W=%d C=%d)", H * W, C);
   cudaStream_t st = as_stream(stream);
+  // algorithmic minimum: channel stats need all positions, spatial stats need all channels after the
+  // channel gate -> 2 reads of the map; this kernel does 3 (L2-resident)
+  ProfScope prof(PK_ATTENTION, 2.0 * (double)B * H * W * C * dtype_size(dtype) + 4.0 * B * C, 8.0 * (double)B * H * W * C, st);
   if (dtype == DFV_BF16) {
     auto k = hybrid_attention_kernel<__nv_bfloat16>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -50,6 +50,18 @@ bool force_simt_gemm();
     if (rc_ != DFV_OK) return rc_; \
   } while (0)
 
+// Optional per-launch CUDA-event profiler (bench.py's roofline leg): every operator entry
+// declares its kind and ALGORITHMIC bytes / flops; when enabled, start/stop events are recorded
+// on the launching stream around the launch.
+enum ProfKind { PK_STEM = 0, PK_EXPAND_GEMM, PK_DWCONV, PK_SE_GATE, PK_PROJECT_GEMM, PK_HEATMAP, PK_ATTENTION,
+                PK_MLP_HEAD, PK_LOSS, PK_GEMM_SIMT, PK_NUM };
+struct ProfScope {
+  ProfScope(int kind, double bytes, double flops, cudaStream_t st);
+  ~ProfScope();
+  int idx;
+  cudaStream_t st;
+};
+
 inline cudaStream_t as_stream(dfv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t dtype_size(int dtype) { return dtype == DFV_BF16 ? 2 : 4; }
 inline bool valid_dtype(int dtype) { return dtype == DFV_F32 || dtype == DFV_BF16; }

@@ -270,6 +270,8 @@ extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, 
   uint64_t strides[3] = {(uint64_t)C * es, (uint64_t)W * C * es, (uint64_t)H * W * C * es};
   uint32_t box[4] = {(uint32_t)pl.p.CB, (uint32_t)pl.p.TWI, (uint32_t)pl.p.THI, 1};
   DFV_TRY(make_tensor_map(&tm, dtype, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+  ProfScope prof(PK_DWCONV, ((double)B * H * W * C + (double)B * pl.p.Ho * pl.p.Wo * C) * es,
+                 2.0 * kernel * kernel * (double)B * pl.p.Ho * pl.p.Wo * C, as_stream(stream));
   if (dtype == DFV_BF16)
     return dispatch<__nv_bfloat16, true>(kernel, stride, pl.L, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));
   return dispatch<float, false>(kernel, stride, pl.L, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));

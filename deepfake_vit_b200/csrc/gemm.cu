@@ -391,6 +391,11 @@ extern "C" int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, 
   DFV_REQUIRE(!a_scale || (rows_per_image > 0 && M % rows_per_image == 0), "dfv_pw_gemm_fwd: a_scale needs rows_per_image dividing M");
   DFV_REQUIRE(act == DFV_ACT_NONE || act == DFV_ACT_SILU, "dfv_pw_gemm_fwd: bad act %d", act);
   cudaStream_t st = as_stream(stream);
+  const bool tc = dtype == DFV_BF16 && !force_simt_gemm();
+  // algorithmic bytes: A read once, out written once, residual read once, weights once
+  const double es = (double)dtype_size(dtype);
+  ProfScope prof(tc ? (a_scale ? PK_PROJECT_GEMM : PK_EXPAND_GEMM) : PK_GEMM_SIMT,
+                 es * ((double)M * K + (double)M * N + (residual ? (double)M * N : 0.0) + (double)N * K), 2.0 * (double)M * K * N, st);
   if (dtype == DFV_BF16 && !force_simt_gemm())
     return launch_tc(a, w, bias, a_scale, rows_per_image, residual, out, M, K, N, act, st);
   dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));

@@ -85,6 +85,9 @@ extern "C" int dfv_mlp_head_fwd(const float* features, const float* const* w_t, 
   const size_t smem = sizeof(float) * 2 * kHeadRows * hp.max_dim;
   DFV_REQUIRE(smem <= 160 * 1024, "dfv_mlp_head_fwd: layer too wide (%d)", hp.max_dim);
   if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(mlp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  double wbytes = 0;
+  for (int l = 0; l < n_layers; ++l) wbytes += 4.0 * dims[l] * dims[l + 1];
+  ProfScope prof(PK_MLP_HEAD, wbytes + 4.0 * B * (dims[0] + dims[n_layers]), 2.0 * B * wbytes / 4.0, as_stream(stream));
   mlp_head_kernel<<<(B + kHeadRows - 1) / kHeadRows, 256, smem, as_stream(stream)>>>(features, logits, hp, B);
   DFV_LAUNCH_CHECK();
   return DFV_OK;

@@ -132,6 +132,7 @@ extern "C" int dfv_combined_loss_fwd_bwd(const float* logits, const int64_t* tar
   const bool con = features != nullptr && B >= 2 && w_contrastive > 0.f;
   if (has_contrastive) *has_contrastive = con ? 1 : 0;
   // weights <= 0 switch a term off exactly as `self.weights[k] > 0` does (losses.py:216,222,228)
+  ProfScope prof(PK_LOSS, 4.0 * B * (2.0 * C + 2.0 * D), 10.0 * B * (C + D), as_stream(stream));
   combined_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, (const long long*)targets, con ? features : nullptr,
                                                         class_weights, w_ce > 0.f ? w_ce : 0.f,
                                                         w_focal > 0.f ? w_focal : 0.f, con ? w_contrastive : 0.f, losses,

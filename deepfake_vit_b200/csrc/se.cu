@@ -51,6 +51,8 @@ extern "C" int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_h
   DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && parts > 0, "dfv_se_gate_fwd: bad shape");
   const size_t smem = (size_t)(C + squeeze) * sizeof(float);
   DFV_REQUIRE(smem <= 48 * 1024, "dfv_se_gate_fwd: C + squeeze too large (%d + %d)", C, squeeze);
+  ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * parts * C + (double)B * C + 2.0 * C * squeeze), 4.0 * B * (double)C * squeeze,
+                 as_stream(stream));
   se_gate_kernel<<<B, 256, smem, as_stream(stream)>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand_t,
                                                       b_expand, gate, C, squeeze);
   DFV_LAUNCH_CHECK();

@@ -76,6 +76,8 @@ extern "C" int dfv_stem_conv_fwd(const float* x, const float* w, const float* bi
   const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
   const long long total = (long long)B * Ho * Wo;
   const unsigned grid = (unsigned)((total + 127) / 128);
+  ProfScope prof(PK_STEM, (double)B * 3 * H * W * 4 + (double)total * kStemC * dtype_size(dtype),
+                 2.0 * 27 * kStemC * (double)total, as_stream(stream));
   if (dtype == DFV_BF16)
     stem_kernel<__nv_bfloat16, true><<<grid, 128, 0, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo);
   else

@@ -57,6 +57,15 @@ void dfv_debug_force_simt_gemm(int on);
 /* Number of kernels launched by this thread since the last reset (bench.py's gpu_launches). */
 long long dfv_launch_count(int reset);
 
+/* Per-launch profiler (CUDA events on the launching stream around every operator launch), used
+ * by bench.py for the roofline leg.  enable(1) clears and starts recording, enable(0) stops.
+ * get(): kind (0 stem, 1 expand/head GEMM, 2 depthwise, 3 SE gate, 4 project GEMM, 5 heat-map,
+ * 6 attention, 7 MLP head, 8 loss, 9 SIMT GEMM), the launch's ALGORITHMIC bytes and flops, and
+ * its duration in ms (synchronises on the launch's stop event). */
+int dfv_profile_enable(int on);
+int dfv_profile_count(void);
+int dfv_profile_get(int idx, int* kind, double* bytes, double* flops, float* ms);
+
 /* ------------------------------------------------------------------------------------
  * EfficientNet-B4 topology (efficientnet-pytorch 0.7.1 `from_name('efficientnet-b4')`,
  * called at src/feature_extraction/efficientnet.py:42-45).

@@ -11,8 +11,7 @@ run() {
 run stem tests/test_gpu_ops.py -k "stem"
 run dwconv tests/test_gpu_ops.py -k "dwconv"
 run se tests/test_gpu_ops.py -k "se_gate"
-run gemm_fp32 tests/test_gpu_ops.py -k "pw_gemm_all and float32"
-run gemm_bf16 tests/test_gpu_ops.py -k "pw_gemm_all and bfloat16"
+run gemm_all tests/test_gpu_ops.py -k "pw_gemm_all"
 run gemm_big tests/test_gpu_ops.py -k "tcgen05_matches or rejects"
 run attention tests/test_gpu_ops.py -k "heatmap or hybrid or mlp_head"
 run loss tests/test_gpu_ops.py -k "combined_loss"
