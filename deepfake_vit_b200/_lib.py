@@ -54,6 +54,7 @@ def _load():
         "dfv_device_check": (C.c_int, []),
         "dfv_debug_force_simt_gemm": (None, [i32]),
         "dfv_launch_count": (i64, [i32]),
+        "dfv_debug_last_timeout": (C.c_uint, []),
         "dfv_profile_enable": (C.c_int, [i32]),
         "dfv_profile_count": (C.c_int, []),
         "dfv_profile_get": (C.c_int, [i32, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -68,7 +69,7 @@ def _load():
         "dfv_stem_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "dfv_dwconv_pool_parts": (C.c_int, [i32] * 8),
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
-        "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "dfv_pw_gemm_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, vp]),
         "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
         "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 8 + [i32] * 8 + [vp]),
@@ -89,7 +90,8 @@ lib, EXPORTS = _load()
 
 def check(rc: int):
     if rc != 0:
-        raise DfvError(f"libdfvit error {rc}: {lib.dfv_last_error().decode(errors='replace')}")
+        raise DfvError(f"libdfvit error {rc}: {lib.dfv_last_error().decode(errors='replace')} "
+                       f"[timeout word 0x{lib.dfv_debug_last_timeout():08x}]")
 
 
 PROFILE_KINDS = ("stem", "expand_gemm", "dwconv", "se_gate", "project_gemm", "heatmap", "attention", "mlp_head",

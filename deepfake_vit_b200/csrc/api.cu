@@ -2,6 +2,7 @@
 // folded-weight blob layout.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -22,6 +23,31 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches += n; }
 bool force_simt_gemm() { return g_force_simt != 0; }
+int debug_flags() {
+  static int flags = -1;
+  if (flags < 0) {
+    const char* e = getenv("DFV_DEBUG_FLAGS");
+    flags = e ? atoi(e) : 0;
+  }
+  return flags;
+}
+
+static unsigned int* g_timeout_host = nullptr;
+static unsigned int* g_timeout_dev = nullptr;
+
+// A host-mapped word the device writes to when a bounded mbarrier wait starves (readable even
+// after the context is lost).
+unsigned int* timeout_device_ptr() {
+  if (g_timeout_dev) return g_timeout_dev;
+  unsigned int* h = nullptr;
+  if (cudaHostAlloc((void**)&h, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+  *h = 0;
+  unsigned int* d = nullptr;
+  if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) return nullptr;
+  g_timeout_host = h;
+  g_timeout_dev = d;
+  return d;
+}
 
 struct ProfRec {
   cudaEvent_t a, b;
@@ -255,6 +281,8 @@ long long dfv_launch_count(int reset) {
   if (reset) g_launches = 0;
   return v;
 }
+
+unsigned int dfv_debug_last_timeout(void) { return g_timeout_host ? *g_timeout_host : 0; }
 
 int dfv_profile_enable(int on) {
   for (auto& r : g_prof) {

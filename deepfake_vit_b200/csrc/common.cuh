@@ -16,6 +16,7 @@ int check_device();                       // DFV_OK or DFV_ERR_DEVICE (cached pe
 int num_sms();
 void count_launch(int n = 1);
 bool force_simt_gemm();
+int debug_flags();   // DFV_DEBUG_FLAGS env: bisecting aid (1 skip dwconv, 2 skip se, 4 skip stem, 8 simt project, 16 simt expand)
 
 #define DFV_REQUIRE(cond, ...)                    \
   do {                                            \
@@ -67,6 +68,8 @@ inline size_t dtype_size(int dtype) { return dtype == DFV_BF16 ? 2 : 4; }
 inline bool valid_dtype(int dtype) { return dtype == DFV_F32 || dtype == DFV_BF16; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+unsigned int* timeout_device_ptr();      // host-mapped debug word (device address), api.cu
+
 // ---------------------------------------------------------------- host: topology / blob (api.cu)
 const dfv_block_info* topo_blocks(int* n);
 int topo_stem_c();
@@ -87,6 +90,12 @@ __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__device__ __forceinline__ uint32_t hmul2_bf16(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
 }
 
 // 8 consecutive channels <-> 8 fp32 registers.
@@ -167,12 +176,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) after ~2 s instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a protocol bug traps (launch error) after ~2 s instead of hanging the GPU, after
+// leaving a tag in host-mapped memory (dfv_debug_last_timeout()) that says which wait starved.
+static __device__ unsigned int* g_timeout_word = nullptr;   // one copy per translation unit (no -rdc)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) {
+      if (g_timeout_word) {
+        *reinterpret_cast<volatile unsigned int*>(g_timeout_word) = 0x80000000u | (tag << 24) | (blockIdx.x & 0xffffff);
+        __threadfence_system();
+      }
+      __trap();
+    }
   }
 }
 
@@ -230,6 +247,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Point this translation unit's g_timeout_word at the process-wide host-mapped word.
+static inline int init_timeout_word_tu() {
+  static bool done = false;
+  if (done) return DFV_OK;
+  unsigned int* d = timeout_device_ptr();
+  if (d) DFV_CUDA(cudaMemcpyToSymbol(g_timeout_word, &d, sizeof(d)));
+  done = true;
+  return DFV_OK;
+}
 
 #endif  // __CUDACC__
 }  // namespace dfv

@@ -21,41 +21,80 @@ struct DwParams {
   int TH, TW;      // output tile
   int THI, TWI;    // input tile = (T-1)*S + K
   int tiles_w, tiles_h;
+  int chunks;      // channel chunks; gridDim.x is a multiple of it, so a CTA's chunk is fixed
+  long long total; // B * tiles * chunks work items
   int pad;         // pad_lo (top == left)
   int act;
   int nthreads;
 };
 
-template <typename T>
-struct WVec;  // 8 weights of type T in shared memory -> 8 floats
+// 8 channels of activations / weights as they sit in shared memory.
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> { uint4 r; };
+template <> struct Vec8<float> { float v[8]; };
 
+__device__ __forceinline__ void ldvec(const __nv_bfloat16* p, Vec8<__nv_bfloat16>& o) { o.r = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void ldvec(const float* p, Vec8<float>& o) { load8(p, o.v); }
+
+// acc[0..1] += x.{lo,hi} * w.{lo,hi}: sm_100 mixed-precision FMA (SASS FHFMA.BF16) -- bf16 operands are
+// taken straight from the packed registers (half selectors), fp32 accumulate; the product of two
+// bf16 values is exact in fp32, so this equals convert-then-FFMA bit for bit without the 2 unpack
+// instructions per pair.
+__device__ __forceinline__ void fma_pair(uint32_t x, uint32_t w, float& a0, float& a1) {
+  asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\t"
+      "mov.b32 {xl, xh}, %2;\n\t"
+      "mov.b32 {wl, wh}, %3;\n\t"
+      "fma.rn.f32.bf16 %0, xl, wl, %0;\n\t"
+      "fma.rn.f32.bf16 %1, xh, wh, %1;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "r"(x), "r"(w));
+}
+__device__ __forceinline__ void fma8(const Vec8<__nv_bfloat16>& x, const Vec8<__nv_bfloat16>& w, float acc[8]) {
+  fma_pair(x.r.x, w.r.x, acc[0], acc[1]);
+  fma_pair(x.r.y, w.r.y, acc[2], acc[3]);
+  fma_pair(x.r.z, w.r.z, acc[4], acc[5]);
+  fma_pair(x.r.w, w.r.w, acc[6], acc[7]);
+}
+__device__ __forceinline__ void fma8(const Vec8<float>& x, const Vec8<float>& w, float acc[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(x.v[e], w.v[e], acc[e]);
+}
+
+// Persistent CTA: loops over work items (image, tile) of ONE channel chunk with a 2-deep TMA
+// pipeline: the tile for item i+1 is in flight while item i is computed.
 template <typename T, int K, int S, int L, bool kFast>
-__global__ void __launch_bounds__(384) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                    const float* __restrict__ w, const float* __restrict__ bias,
-                                                    T* __restrict__ y, float* __restrict__ pool_partial, DwParams p) {
+__global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       T* __restrict__ y, float* __restrict__ pool_partial, DwParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // [tile: THI*TWI*CB T][weights: K*K*CB T][bias: CB f32][red: nthreads*8 f32][mbar]
-  T* tile = reinterpret_cast<T*>(smem_raw);
+  // [tile0][tile1][weights: K*K*CB T][bias: CB f32][red: 2 x nthreads*8 f32][mbar x2]
   const size_t tile_bytes = (size_t)p.THI * p.TWI * p.CB * sizeof(T);
-  T* wsm = reinterpret_cast<T*>(smem_raw + ((tile_bytes + 127) / 128) * 128);
+  const size_t tile_stride = ((tile_bytes + 127) / 128) * 128;
+  T* wsm = reinterpret_cast<T*>(smem_raw + 2 * tile_stride);
   float* bsm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wsm) + (((size_t)K * K * p.CB * sizeof(T) + 15) / 16) * 16);
   float* red = bsm + p.CB;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + (size_t)p.nthreads * 8);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + (size_t)p.nthreads * 16);
 
   const int tid = threadIdx.x;
-  const int tile_id = blockIdx.x;
-  const int tw_i = tile_id % p.tiles_w, th_i = tile_id / p.tiles_w;
-  const int c0 = blockIdx.y * p.CB;
-  const int b = blockIdx.z;
-  const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+  const int chunk = blockIdx.x % p.chunks;
+  const int c0 = chunk * p.CB;
+  const int n_tiles = p.tiles_w * p.tiles_h;
+
+  auto issue = [&](long long wi, int buf) {
+    const long long rest = wi / p.chunks;
+    const int tile_id = (int)(rest % n_tiles), b = (int)(rest / n_tiles);
+    const int tw_i = tile_id % p.tiles_w, th_i = tile_id / p.tiles_w;
+    mbar_expect_tx(&mbar[buf], (uint32_t)tile_bytes);
+    tma_load_4d(smem_raw + buf * tile_stride, &tmap, &mbar[buf], c0, tw_i * p.TW * S - p.pad, th_i * p.TH * S - p.pad, b);
+  };
 
   if (tid == 0) {
-    mbar_init(mbar, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
     fence_mbar_init();
-    mbar_expect_tx(mbar, (uint32_t)tile_bytes);
-    tma_load_4d(tile, &tmap, mbar, c0, w0 * S - p.pad, h0 * S - p.pad, b);
+    issue(blockIdx.x, 0);
   }
-  // Stage this chunk's weights (BN scale already folded in) and bias while the tile lands.
+  // Stage this chunk's weights (BN scale already folded in) and bias while the first tile lands.
   for (int i = tid; i < K * K * p.CB; i += blockDim.x) {
     const int c = c0 + i % p.CB;
     const float v = (c < p.C) ? w[(size_t)(i / p.CB) * p.C + c] : 0.f;
@@ -63,83 +102,95 @@ __global__ void __launch_bounds__(384) dwconv_kernel(const __grid_constant__ CUt
   }
   for (int i = tid; i < p.CB; i += blockDim.x) bsm[i] = (c0 + i < p.C) ? bias[c0 + i] : 0.f;
   __syncthreads();
-  mbar_wait(mbar, 0);
 
   const int G = p.CB >> 3;
-  const int strips = (p.TW + L - 1) / L;
+  const int strips = p.TW / L;             // the host picks TW as a multiple of L
   const int n_items = p.TH * strips * G;
   const int g = tid % G;  // blockDim is a multiple of G: the channel group is fixed per thread
   const int c = c0 + g * 8;
-  float psum[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) psum[e] = 0.f;
   float bv[8];
   load8(bsm + g * 8, bv);
-
   constexpr int NI = (L - 1) * S + K;  // input window per kernel row
-  if (c < p.C) {
-    for (int item = tid; item < n_items; item += blockDim.x) {
-      const int rest = item / G;
-      const int j = rest % strips, r = rest / strips;
-      const int ho = h0 + r, wo0 = w0 + j * L;
-      if (ho >= p.Ho || wo0 >= p.Wo) continue;
-      float acc[L][8];
-#pragma unroll
-      for (int l = 0; l < L; ++l)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[l][e] = 0.f;
+  const int nth = blockDim.x;
+  float* red0 = red;
+  float* red1 = red + (size_t)p.nthreads * 8;
 
+  int it = 0;
+  for (long long wi = blockIdx.x; wi < p.total; wi += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (tid == 0 && wi + gridDim.x < p.total) issue(wi + gridDim.x, buf ^ 1);   // prefetch the next tile
+    const long long rest = wi / p.chunks;
+    const int tile_id = (int)(rest % n_tiles), b = (int)(rest / n_tiles);
+    const int h0 = (tile_id / p.tiles_w) * p.TH, w0 = (tile_id % p.tiles_w) * p.TW;
+    const T* tile = reinterpret_cast<const T*>(smem_raw + buf * tile_stride);
+    mbar_wait(&mbar[buf], (it >> 1) & 1, 6);
+
+    float psum[8];
 #pragma unroll
-      for (int kh = 0; kh < K; ++kh) {
-        float wk[K][8];
+    for (int e = 0; e < 8; ++e) psum[e] = 0.f;
+
+    if (c < p.C) {
+      for (int item = tid; item < n_items; item += nth) {
+        const int r_ = item / G;
+        const int j = r_ % strips, r = r_ / strips;
+        const int ho = h0 + r, wo0 = w0 + j * L;
+        if (ho >= p.Ho || wo0 >= p.Wo) continue;
+        float acc[L][8];
 #pragma unroll
-        for (int kw = 0; kw < K; ++kw) load8(wsm + (kh * K + kw) * p.CB + g * 8, wk[kw]);
-        const T* row = tile + ((size_t)(r * S + kh) * p.TWI + j * L * S) * p.CB + g * 8;
+        for (int l = 0; l < L; ++l)
 #pragma unroll
-        for (int iw = 0; iw < NI; ++iw) {
-          // the last strip of a tile may overhang TWI; those outputs are masked below
-          if (j * L * S + iw < p.TWI) {
-            float v[8];
-            load8(row + (size_t)iw * p.CB, v);
+          for (int e = 0; e < 8; ++e) acc[l][e] = bv[e];
+
+        const T* in = tile + ((size_t)(r * S) * p.TWI + j * L * S) * p.CB + g * 8;
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+          Vec8<T> wk[K];
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) ldvec(wsm + (kh * K + kw) * p.CB + g * 8, wk[kw]);
+          const T* row = in + (size_t)kh * p.TWI * p.CB;
+#pragma unroll
+          for (int iw = 0; iw < NI; ++iw) {
+            Vec8<T> v;
+            ldvec(row + iw * p.CB, v);
 #pragma unroll
             for (int l = 0; l < L; ++l) {
               const int kw = iw - l * S;
-              if (kw >= 0 && kw < K) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[l][e] = fmaf(v[e], wk[kw][e], acc[l][e]);
-              }
+              if (kw >= 0 && kw < K) fma8(v, wk[kw], acc[l]);
             }
           }
         }
-      }
+        T* out = y + (((size_t)b * p.Ho + ho) * p.Wo + wo0) * p.C + c;
+        const int nvalid = min(L, p.Wo - wo0);
 #pragma unroll
-      for (int l = 0; l < L; ++l) {
-        const int wo = wo0 + l;
-        if (wo < p.Wo && j * L + l < p.TW) {
-          float o[8];
+        for (int l = 0; l < L; ++l) {
+          if (l < nvalid) {
+            float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float t = acc[l][e] + bv[e];
-            o[e] = p.act ? silu<kFast>(t) : t;
-            psum[e] += o[e];
+            for (int e = 0; e < 8; ++e) {
+              o[e] = p.act ? silu<kFast>(acc[l][e]) : acc[l][e];
+              psum[e] += o[e];
+            }
+            store8(out + (size_t)l * p.C, o);
           }
-          store8(y + (((size_t)b * p.Ho + ho) * p.Wo + wo) * p.C + c, o);
         }
       }
     }
-  }
 
-  if (pool_partial != nullptr) {
-    // deterministic CTA reduction: threads sharing a channel group are tid = g + G*i
+    if (pool_partial != nullptr) {
+      // deterministic CTA reduction: threads sharing a channel group are tid = g + G*i.  The
+      // scratch is double buffered so one barrier per tile suffices.
+      float* rbuf = buf ? red1 : red0;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) red[tid * 8 + e] = psum[e];
-    __syncthreads();
-    if (tid < p.CB && c0 + tid < p.C) {
-      const int gg = tid >> 3, e = tid & 7;
-      float s = 0.f;
-      for (int t = gg; t < (int)blockDim.x; t += G) s += red[t * 8 + e];
-      const int parts = p.tiles_w * p.tiles_h;
-      pool_partial[((size_t)b * parts + tile_id) * p.C + c0 + tid] = s;
+      for (int e = 0; e < 8; ++e) rbuf[tid * 8 + e] = psum[e];
+      __syncthreads();   // also: everyone is done with tile[buf] before it is refilled
+      if (tid < p.CB && c0 + tid < p.C) {
+        const int gg = tid >> 3, e = tid & 7;
+        float s = 0.f;
+        for (int t = gg; t < nth; t += G) s += rbuf[t * 8 + e];
+        pool_partial[((size_t)b * n_tiles + tile_id) * p.C + c0 + tid] = s;
+      }
+    } else {
+      __syncthreads();
     }
   }
 }
@@ -168,24 +219,20 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
   if (p.Ho <= 0 || p.Wo <= 0) return DFV_ERR_INVALID;
   p.CB = pick_cb(C, dtype);
   p.pad = pad_lo;
-  int L, TW, TH;
+  // strip length: 8 for 3x3 (weights + 64 accumulators fit 128 registers), 4 for 5x5 and stride 2
+  int L = (S == 1) ? 8 : 4;
+  if (p.Wo <= 12 && L == 8) L = p.Wo > 8 ? 6 : 4;
+  int TW, TH;
   if (S == 2) {
-    L = 4;
-    TW = p.Wo >= 16 ? 16 : ((p.Wo + 3) / 4) * 4;
+    TW = p.Wo >= 16 ? 16 : ((p.Wo + L - 1) / L) * L;
     TH = p.Ho >= 8 ? 8 : p.Ho;
   } else if (p.Wo > 24) {
-    L = 8;
     TW = p.Wo >= 32 ? 32 : 24;
     if (p.Wo > 32 && p.Wo <= 48) TW = 24;
     TH = 8;
-  } else if (p.Wo > 12) {
-    L = 8;
-    TW = ((p.Wo + 7) / 8) * 8;
-    TH = p.Ho >= 12 ? 12 : p.Ho;
   } else {
-    L = p.Wo > 8 ? 6 : 4;
     TW = ((p.Wo + L - 1) / L) * L;
-    TH = p.Ho;
+    TH = p.Ho > 12 ? 8 : p.Ho;
   }
   pl->L = L;
   p.TW = TW;
@@ -194,32 +241,41 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
   p.THI = (TH - 1) * S + K;
   p.tiles_w = (p.Wo + TW - 1) / TW;
   p.tiles_h = (p.Ho + TH - 1) / TH;
-  pl->chunks = (C + p.CB - 1) / p.CB;
+  p.chunks = pl->chunks = (C + p.CB - 1) / p.CB;
   const int G = p.CB / 8;
-  const int items = TH * (TW / L) * G;
-  const int rounds = (items + 319) / 320;  // aim for <= 320 threads, balanced rounds
+  const int items = TH * ((TW + L - 1) / L) * G;
+  const int rounds = (items + 255) / 256;
   int nt = (items + rounds - 1) / rounds;
   nt = ((nt + G - 1) / G) * G;
-  if (nt > 384) nt = (384 / G) * G;
+  if (nt > 256) nt = (256 / G) * G;
   if (nt < G) nt = G;
   p.nthreads = nt;
   const size_t ts = dtype_size(dtype);
   size_t tile_bytes = (size_t)p.THI * p.TWI * p.CB * ts;
-  pl->smem = align_up(tile_bytes, 128) + align_up((size_t)K * K * p.CB * ts, 16) + (size_t)p.CB * 4 + (size_t)nt * 32 + 16;
-  if (p.TWI > 256 || p.THI > 256 || p.CB > 256 || pl->smem > 200 * 1024) return DFV_ERR_INVALID;
+  pl->smem = 2 * align_up(tile_bytes, 128) + align_up((size_t)K * K * p.CB * ts, 16) + (size_t)p.CB * 4 + (size_t)nt * 64 + 32;
+  if (p.TWI > 256 || p.THI > 256 || p.CB > 256 || pl->smem > 220 * 1024) return DFV_ERR_INVALID;
   return DFV_OK;
 }
 
 template <typename T, int K, int S, int L, bool kFast>
-static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, const DwPlan& pl, int B,
+static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, DwPlan& pl, int B,
                   cudaStream_t st) {
   auto kern = dwconv_kernel<T, K, S, L, kFast>;
-  static thread_local size_t configured = 0;
-  if (pl.smem > 48 * 1024 && pl.smem > configured) {
-    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
+  static thread_local bool configured = false;
+  if (!configured) {
+    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
   }
-  dim3 grid(pl.p.tiles_w * pl.p.tiles_h, pl.chunks, B);
+  DFV_TRY(init_timeout_word_tu());
+  const long long per_chunk = (long long)B * pl.p.tiles_w * pl.p.tiles_h;
+  pl.p.total = per_chunk * pl.chunks;
+  // persistent grid: a multiple of `chunks` (fixed chunk per CTA), about two CTAs per SM
+  const int occ = pl.smem <= 110 * 1024 ? 2 : 1;
+  long long ctas_per_chunk = (long long)num_sms() * occ / pl.chunks;
+  if (ctas_per_chunk < 1) ctas_per_chunk = 1;
+  if (ctas_per_chunk > per_chunk) ctas_per_chunk = per_chunk;
+  const unsigned grid = (unsigned)(ctas_per_chunk * pl.chunks);
   kern<<<grid, pl.p.nthreads, pl.smem, st>>>(tm, w, bias, (T*)y, pool, pl.p);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
@@ -227,7 +283,7 @@ static int launch(const CUtensorMap& tm, const float* w, const float* bias, void
 
 template <typename T, bool kFast>
 static int dispatch(int K, int S, int L, const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool,
-                    const DwPlan& pl, int B, cudaStream_t st) {
+                    DwPlan& pl, int B, cudaStream_t st) {
 #define DW_CASE(k, s, l) \
   if (K == k && S == s && L == l) return launch<T, k, s, l, kFast>(tm, w, bias, y, pool, pl, B, st);
   DW_CASE(3, 1, 8) DW_CASE(3, 1, 6) DW_CASE(3, 1, 4) DW_CASE(5, 1, 8) DW_CASE(5, 1, 6) DW_CASE(5, 1, 4)
@@ -258,8 +314,9 @@ extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, 
   DFV_REQUIRE(valid_dtype(dtype), "dfv_dwconv_fwd: bad dtype %d", dtype);
   DFV_REQUIRE((kernel == 3 || kernel == 5) && (stride == 1 || stride == 2), "dfv_dwconv_fwd: k=%d s=%d unsupported",
               kernel, stride);
-  DFV_REQUIRE(B > 0 && B <= 65535 && C > 0 && C % 8 == 0, "dfv_dwconv_fwd: need 0 < B <= 65535 and C %% 8 == 0 (B=%d C=%d)", B, C);
+  DFV_REQUIRE(B > 0 && C > 0 && C % 8 == 0, "dfv_dwconv_fwd: need B > 0 and C %% 8 == 0 (B=%d C=%d)", B, C);
   DFV_REQUIRE(pad_lo >= 0 && pad_hi >= 0 && pad_lo < kernel && pad_hi < kernel, "dfv_dwconv_fwd: bad pad");
+  if (debug_flags() & 1) return DFV_OK;
   DwPlan pl;
   DFV_REQUIRE(make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) == DFV_OK,
               "dfv_dwconv_fwd: cannot tile H=%d W=%d C=%d k=%d s=%d", H, W, C, kernel, stride);

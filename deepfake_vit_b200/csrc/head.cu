@@ -5,7 +5,7 @@
 
 namespace dfv {
 
-constexpr int kHeadRows = 4;
+constexpr int kHeadRows = 2;
 constexpr int kHeadMaxLayers = 8;
 
 struct HeadParams {
@@ -39,8 +39,9 @@ __global__ void __launch_bounds__(256) mlp_head_kernel(const float* __restrict__
       float acc[kHeadRows];
 #pragma unroll
       for (int r = 0; r < kHeadRows; ++r) acc[r] = 0.f;
+#pragma unroll 16
       for (int k = 0; k < din; ++k) {
-        const float wv = wt[(size_t)k * dout + n];
+        const float wv = __ldg(wt + (size_t)k * dout + n);
 #pragma unroll
         for (int r = 0; r < kHeadRows; ++r) acc[r] = fmaf(in[r * hp.max_dim + k], wv, acc[r]);
       }

@@ -58,7 +58,7 @@ struct Workspace {
   char* expand;
   char* dw;
   float* pool;
-  float* gate;
+  void* gate;
   float* heat;
   float* heat_raw;
   uint32_t* heat_max;
@@ -78,7 +78,7 @@ static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) 
   ws->expand = take((size_t)B * s.exp_elems * es);
   ws->dw = take((size_t)B * s.dw_elems * es);
   ws->pool = (float*)take((size_t)B * s.pool_floats * 4);
-  ws->gate = (float*)take((size_t)B * s.max_cmid * 4);
+  ws->gate = take((size_t)B * s.max_cmid * 4);
   ws->heat = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_raw = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_max = (uint32_t*)take((size_t)B * 4);
@@ -147,7 +147,7 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
                            w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, DFV_ACT_SILU, stream));
     DFV_TRY(dfv_se_gate_fwd(ws.pool, parts, 1.0f / (float)(ho * wo), (const float*)W_(i, DFV_W_SE_REDUCE),
                             (const float*)W_(i, DFV_W_SE_REDUCE_BIAS), (const float*)W_(i, DFV_W_SE_EXPAND),
-                            (const float*)W_(i, DFV_W_SE_EXPAND_BIAS), ws.gate, B, b.c_mid, b.se_squeeze, stream));
+                            (const float*)W_(i, DFV_W_SE_EXPAND_BIAS), ws.gate, dtype, B, b.c_mid, b.se_squeeze, stream));
     DFV_TRY(dfv_pw_gemm_fwd(ws.dw, W_(i, DFV_W_PROJECT), (const float*)W_(i, DFV_W_PROJECT_BIAS), ws.gate, ho * wo,
                             b.has_skip ? x : nullptr, ws.act[cur ^ 1], dtype, (long long)B * ho * wo, b.c_mid, b.c_out,
                             DFV_ACT_NONE, stream));

@@ -8,8 +8,24 @@ namespace dfv {
 
 constexpr int kStemC = 48;
 
+// Register blocking: each thread computes 4 adjacent output pixels x 12 channels, so every
+// 16-byte weight read from shared memory feeds 16 FMAs (the 1 pixel x 48 channel version was
+// bound by shared-memory weight broadcasts).  Four threads (channel quarters) share each pixel quad.
+__device__ __forceinline__ void stem_store12(__nv_bfloat16* p, const float o[12]) {
+  uint2* q = reinterpret_cast<uint2*>(p);   // 24 bytes, 8-byte aligned
+  q[0] = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+  q[1] = make_uint2(pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+  q[2] = make_uint2(pack_bf16(o[8], o[9]), pack_bf16(o[10], o[11]));
+}
+__device__ __forceinline__ void stem_store12(float* p, const float o[12]) {
+  float4* q = reinterpret_cast<float4*>(p);
+  q[0] = make_float4(o[0], o[1], o[2], o[3]);
+  q[1] = make_float4(o[4], o[5], o[6], o[7]);
+  q[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+
 template <typename T, bool kFast>
-__global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 3) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                   const float* __restrict__ bias, T* __restrict__ y, int B, int H,
                                                   int W, int Ho, int Wo) {
   __shared__ __align__(16) float ws[27 * kStemC];
@@ -18,47 +34,55 @@ __global__ void __launch_bounds__(128) stem_kernel(const float* __restrict__ x, 
   if (threadIdx.x < kStemC) bs[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
 
-  const long long total = (long long)B * Ho * Wo;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  const int wo = (int)(p % Wo);
-  const int ho = (int)((p / Wo) % Ho);
-  const int b = (int)(p / ((long long)Wo * Ho));
+  const int quads_w = (Wo + 3) / 4;
+  const long long total = (long long)B * Ho * quads_w * 4;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int cq = (int)(gid & 3);                 // channel quarter: channels 12*cq .. 12*cq+11
+  const long long pq = gid >> 2;
+  const int wq = (int)(pq % quads_w);
+  const int ho = (int)((pq / quads_w) % Ho);
+  const int b = (int)(pq / ((long long)quads_w * Ho));
+  const int wo0 = wq * 4;
 
-  float acc[kStemC];
+  float acc[4][12];
 #pragma unroll
-  for (int i = 0; i < kStemC; ++i) acc[i] = 0.f;
+  for (int pxl = 0; pxl < 4; ++pxl)
+#pragma unroll
+    for (int i = 0; i < 12; ++i) acc[pxl][i] = 0.f;
 
   const float* xb = x + (size_t)b * 3 * H * W;
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int hi = 2 * ho + kh;
 #pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int wi = 2 * wo + kw;
-      const bool ok = (hi < H) && (wi < W);
+    for (int ci = 0; ci < 3; ++ci) {
+      float in[9];
+      const float* xr = xb + ((size_t)ci * H + hi) * W + 2 * wo0;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float v = ok ? __ldg(xb + ((size_t)ci * H + hi) * W + wi) : 0.f;
-        const float4* wr = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * 3 + ci) * kStemC);
+      for (int i = 0; i < 9; ++i) in[i] = (hi < H && 2 * wo0 + i < W) ? __ldg(xr + i) : 0.f;
 #pragma unroll
-        for (int q = 0; q < kStemC / 4; ++q) {
-          const float4 w4 = wr[q];
-          acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * 3 + ci) * kStemC + cq * 12);
+        const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2];
+        const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+        for (int pxl = 0; pxl < 4; ++pxl) {
+          const float v = in[2 * pxl + kw];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) acc[pxl][i] = fmaf(v, wv[i], acc[pxl][i]);
         }
       }
     }
   }
-  T* yo = y + (size_t)p * kStemC;
 #pragma unroll
-  for (int q = 0; q < kStemC / 8; ++q) {
-    float o[8];
+  for (int pxl = 0; pxl < 4; ++pxl) {
+    if (wo0 + pxl < Wo) {
+      float o[12];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = silu<kFast>(acc[8 * q + j] + bs[8 * q + j]);
-    store8(yo + 8 * q, o);
+      for (int i = 0; i < 12; ++i) o[i] = silu<kFast>(acc[pxl][i] + bs[cq * 12 + i]);
+      stem_store12(y + (((size_t)b * Ho + ho) * Wo + wo0 + pxl) * kStemC + cq * 12, o);
+    }
   }
 }
 
@@ -73,15 +97,17 @@ extern "C" int dfv_stem_conv_fwd(const float* x, const float* w, const float* bi
   DFV_REQUIRE(valid_dtype(dtype), "dfv_stem_conv_fwd: bad dtype %d", dtype);
   DFV_REQUIRE(C == kStemC, "dfv_stem_conv_fwd: C must be %d (EfficientNet-B4 stem), got %d", kStemC, C);
   DFV_REQUIRE(B > 0 && H >= 3 && W >= 3, "dfv_stem_conv_fwd: bad shape B=%d H=%d W=%d", B, H, W);
+  if (debug_flags() & 4) return DFV_OK;
   const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
   const long long total = (long long)B * Ho * Wo;
-  const unsigned grid = (unsigned)((total + 127) / 128);
+  const long long threads = (long long)B * Ho * ((Wo + 3) / 4) * 4;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
   ProfScope prof(PK_STEM, (double)B * 3 * H * W * 4 + (double)total * kStemC * dtype_size(dtype),
                  2.0 * 27 * kStemC * (double)total, as_stream(stream));
   if (dtype == DFV_BF16)
-    stem_kernel<__nv_bfloat16, true><<<grid, 128, 0, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo);
+    stem_kernel<__nv_bfloat16, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo);
   else
-    stem_kernel<float, false><<<grid, 128, 0, as_stream(stream)>>>(x, w, bias, (float*)y, B, H, W, Ho, Wo);
+    stem_kernel<float, false><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (float*)y, B, H, W, Ho, Wo);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

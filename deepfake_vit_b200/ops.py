@@ -62,12 +62,12 @@ def dwconv(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, act=DFV_ACT_SILU, wan
     return y, pool
 
 
-def se_gate(pool_partial, hw, w_reduce, b_reduce, w_expand_t, b_expand):
+def se_gate(pool_partial, hw, w_reduce, b_reduce, w_expand_t, b_expand, gate_dtype=torch.float32):
     B, parts, C_ = pool_partial.shape
     sq = b_reduce.numel()
-    gate = torch.empty(B, C_, device=pool_partial.device, dtype=torch.float32)
+    gate = torch.empty(B, C_, device=pool_partial.device, dtype=gate_dtype)
     check(lib.dfv_se_gate_fwd(_f32(pool_partial), parts, 1.0 / hw, _f32(w_reduce), _f32(b_reduce), _f32(w_expand_t),
-                              _f32(b_expand), _f32(gate), B, C_, sq, _stream()))
+                              _f32(b_expand), _ptr(gate), dtype_code(gate_dtype), B, C_, sq, _stream()))
     return gate
 
 
@@ -77,6 +77,7 @@ def pw_gemm(a, w, bias, act=DFV_ACT_NONE, a_scale=None, rows_per_image=0, residu
     N = w.shape[0]
     M = a.numel() // K
     assert w.shape[1] == K and w.dtype == a.dtype
+    assert a_scale is None or a_scale.dtype == a.dtype, "the SE gate has the activation dtype"
     out = torch.empty(*a.shape[:-1], N, device=a.device, dtype=a.dtype)
     check(lib.dfv_pw_gemm_fwd(_ptr(a), _ptr(w), _f32(bias), _ptr(a_scale), rows_per_image, _ptr(residual), _ptr(out),
                               dtype_code(a.dtype), M, K, N, act, _stream()))

@@ -54,6 +54,9 @@ int dfv_device_check(void);
 /* Debug/localisation switch: route bf16 1x1 convolutions through the SIMT kernel that the
  * fp32 mode uses instead of tcgen05.  Tests only; default 0. */
 void dfv_debug_force_simt_gemm(int on);
+/* Debug: nonzero if a bounded in-kernel barrier wait starved (the kernel then traps): bit 31 set,
+ * bits 24-30 = which wait, bits 0-23 = block index.  Readable after a launch failure. */
+unsigned int dfv_debug_last_timeout(void);
 /* Number of kernels launched by this thread since the last reset (bench.py's gpu_launches). */
 long long dfv_launch_count(int reset);
 
@@ -136,19 +139,22 @@ int dfv_dwconv_fwd(const void* x, const float* w_kkc, const float* bias, void* y
 
 /* Squeeze-excite gate: mean over H*W (finishing the partial sums) -> 1x1 conv + bias ->
  * swish -> 1x1 conv + bias -> sigmoid.  Replaces `_se_expand(_swish(_se_reduce(pool)))`
- * and `torch.sigmoid` of MBConvBlock.forward.  gate: fp32 [B][C].  The channel rescale
- * itself is fused into the project GEMM's A-operand path (dfv_pw_gemm_fwd a_scale). */
+ * and `torch.sigmoid` of MBConvBlock.forward.  gate: [B][C] of type gate_dtype (fp32 in
+ * parity mode; bf16 in bf16 mode, where the autocast reference's sigmoid output is a bf16
+ * tensor too).  The channel rescale itself is fused into the project GEMM's A-operand path
+ * (dfv_pw_gemm_fwd a_scale). */
 int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce,
-                    const float* b_reduce, const float* w_expand_t, const float* b_expand, float* gate,
-                    int B, int C, int squeeze, dfv_stream_t stream);
+                    const float* b_reduce, const float* w_expand_t, const float* b_expand, void* gate,
+                    int gate_dtype, int B, int C, int squeeze, dfv_stream_t stream);
 
 /* Pointwise (1x1) convolution as a GEMM  out[M][N] = act((a[M][K] * a_scale) . w[N][K]^T + bias) + residual.
- * M = B*H*W rows.  a_scale: fp32 [M / rows_per_image][K] per-image channel scale (SE gate) or
- * NULL; residual: [M][N] or NULL (the MBConv identity skip).  Replaces `_expand_conv+_bn0+_swish`,
- * `sigmoid(se) * x` + `_project_conv+_bn2` + `x + inputs`, and `_conv_head+_bn1+_swish`.
- * bf16: TMA -> smem -> tcgen05.mma (fp32 accumulators in TMEM) -> tcgen05.ld epilogue.
- * K % 8 == 0 and N % 8 == 0 required. */
-int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, const float* a_scale, int rows_per_image,
+ * M = B*H*W rows.  a_scale: [M / rows_per_image][K] per-image channel scale (SE gate) of the
+ * activation dtype, or NULL; residual: [M][N] or NULL (the MBConv identity skip).  Replaces
+ * `_expand_conv+_bn0+_swish`, `sigmoid(se) * x` + `_project_conv+_bn2` + `x + inputs`, and
+ * `_conv_head+_bn1+_swish`.
+ * bf16: TMA -> smem -> tcgen05.mma (fp32 accumulators in TMEM) -> tcgen05.ld epilogue -> swizzled
+ * smem staging -> TMA store.  K % 8 == 0 and N % 8 == 0 required. */
+int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
                     const void* residual, void* out, int dtype, long long M, int K, int N, int act,
                     dfv_stream_t stream);
 

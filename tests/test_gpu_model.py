@@ -165,7 +165,7 @@ def test_bf16_block_by_block_identical_inputs():
                            slot(i, d._lib.W_SE_REDUCE, torch.float32, (inf["se_squeeze"], inf["c_mid"])),
                            slot(i, d._lib.W_SE_REDUCE_BIAS, torch.float32, (inf["se_squeeze"],)),
                            slot(i, d._lib.W_SE_EXPAND, torch.float32, (inf["se_squeeze"], inf["c_mid"])),
-                           slot(i, d._lib.W_SE_EXPAND_BIAS, torch.float32, (inf["c_mid"],)))
+                           slot(i, d._lib.W_SE_EXPAND_BIAS, torch.float32, (inf["c_mid"],)), torch.bfloat16)
         out = ops.pw_gemm(y, slot(i, d._lib.W_PROJECT, torch.bfloat16, (inf["c_out"], inf["c_mid"])),
                           slot(i, d._lib.W_PROJECT_BIAS, torch.float32, (inf["c_out"],)), 0, gate,
                           y.shape[1] * y.shape[2], xin if inf["has_skip"] else None)

@@ -119,6 +119,9 @@ def test_se_gate(ops):
         ref = torch.sigmoid(silu(m @ w1.t() + b1) @ w2.t() + b2)
         out = ops.se_gate(pool.to(DEV), hw, w1.to(DEV), b1.to(DEV), w2.t().contiguous().to(DEV), b2.to(DEV))
         assert rel(out, ref) < 1e-5
+        out16 = ops.se_gate(pool.to(DEV), hw, w1.to(DEV), b1.to(DEV), w2.t().contiguous().to(DEV), b2.to(DEV),
+                            torch.bfloat16)
+        assert out16.dtype == torch.bfloat16 and rel(out16.float(), ref) < 3e-3
 
 
 # ------------------------------------------------------------------------------- pointwise GEMM
@@ -135,7 +138,7 @@ def _gemm_cases():
 def _gemm_ref(a, w, bias, act, scale, rpi, res):
     a = a.float()
     if scale is not None:
-        a = a * scale.repeat_interleave(rpi, 0)
+        a = a * scale.float().repeat_interleave(rpi, 0)
         if w.dtype == torch.bfloat16:
             a = a.bfloat16().float()      # the kernel rounds the gated operand to bf16
     y = a @ w.float().t() + bias
@@ -157,7 +160,7 @@ def test_pw_gemm_all_b4_shapes(ops, dtype):
         a = torch.randn(M, K, generator=g).to(dtype)
         w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dtype)
         bias = torch.randn(N, generator=g) * 0.1
-        scale = torch.rand(M // rpi, K, generator=g)
+        scale = torch.rand(M // rpi, K, generator=g).to(dtype)
         res = torch.randn(M, N, generator=g).to(dtype)
         for act, use_scale, use_res in ((1, False, False), (0, True, True), (0, True, False)):
             ref = _gemm_ref(a, w, bias, act, scale if use_scale else None, rpi, res if use_res else None)
