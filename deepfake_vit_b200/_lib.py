@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdfvit.so")
 
 DFV_F32, DFV_BF16 = 0, 1
-DFV_ACT_NONE, DFV_ACT_SILU = 0, 1
+DFV_ACT_NONE, DFV_ACT_SILU, DFV_ACT_RELU = 0, 1, 2
 (W_STEM, W_STEM_BIAS, W_EXPAND, W_EXPAND_BIAS, W_DW, W_DW_BIAS, W_SE_REDUCE, W_SE_REDUCE_BIAS,
  W_SE_EXPAND, W_SE_EXPAND_BIAS, W_PROJECT, W_PROJECT_BIAS, W_HEAD, W_HEAD_BIAS) = range(14)
 
@@ -41,6 +41,30 @@ class InferArgs(C.Structure):
     ]
 
 
+class TrainArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("use_attention", C.c_int32), ("use_landmark", C.c_int32), ("use_channel", C.c_int32),
+        ("use_spatial", C.c_int32), ("heat_group", C.c_int32), ("landmark_ref_size", C.c_float),
+        ("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("cls_bn_eps", C.c_float), ("cls_bn_momentum", C.c_float),
+        ("drop_connect_rate", C.c_float), ("feat_dropout", C.c_float), ("cls_dropout", C.c_float),
+        ("seed", C.c_uint64),
+        ("params", C.POINTER(C.c_void_p)), ("grads", C.POINTER(C.c_void_p)),
+        ("images_nchw", C.c_void_p), ("landmarks", C.c_void_p),
+        ("ca_hidden", C.c_int32), ("head_dims", C.POINTER(C.c_int32)), ("head_layers", C.c_int32),
+        ("arena", C.c_void_p), ("arena_bytes", C.c_size_t), ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
+        ("logits", C.c_void_p), ("features", C.c_void_p), ("dlogits", C.c_void_p), ("dfeatures", C.c_void_p),
+        ("taps", C.POINTER(C.c_void_p)),
+    ]
+
+
+# per-block / global tensor kinds of the training parameter table (include/dfvit.h DFV_T_*, DFV_TG_*)
+(T_EXPAND_W, T_BN0_G, T_BN0_B, T_BN0_RM, T_BN0_RV, T_DW_W, T_BN1_G, T_BN1_B, T_BN1_RM, T_BN1_RV,
+ T_SE_R_W, T_SE_R_B, T_SE_E_W, T_SE_E_B, T_PROJ_W, T_BN2_G, T_BN2_B, T_BN2_RM, T_BN2_RV) = range(19)
+(TG_STEM_W, TG_STEM_G, TG_STEM_B, TG_STEM_RM, TG_STEM_RV, TG_HEAD_W, TG_HEAD_G, TG_HEAD_B, TG_HEAD_RM, TG_HEAD_RV,
+ TG_LM_W, TG_SA_W, TG_CA_W1, TG_CA_W2) = range(14)
+
+
 def _load():
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
@@ -66,7 +90,7 @@ def _load():
         "dfv_b4_output_hw": (C.c_int, [i32, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "dfv_blob_bytes": (sz, [i32]),
         "dfv_blob_slot": (C.c_int, [i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]),
-        "dfv_stem_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "dfv_stem_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "dfv_dwconv_pool_parts": (C.c_int, [i32] * 8),
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
         "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
@@ -76,6 +100,38 @@ def _load():
         "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, i32, vp]),
         "dfv_combined_loss_fwd_bwd": (C.c_int, [vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, i32, i32, i32,
                                                 C.POINTER(C.c_int), vp]),
+        "dfv_rows_chunks": (C.c_int, [i32, i64]),
+        "dfv_bn_ws_floats": (sz, [i32, i64, i32]),
+        "dfv_bn_stats_fwd": (C.c_int, [vp, i32, i32, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp]),
+        "dfv_bn_act_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i64, i32, vp]),
+        "dfv_act_bn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64,
+                                     i32, vp]),
+        "dfv_bn_bwd_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]),
+        "dfv_se_train_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp]),
+        "dfv_se_bwd_ws_floats": (sz, [i32, i64, i32, i32]),
+        "dfv_se_bwd": (C.c_int, [vp, vp, i32] + [vp] * 11 + [i32, i64, i32, i32, vp]),
+        "dfv_pw_wgrad": (C.c_int, [vp, vp, vp, i32, vp, i32, i64, i32, i32, vp]),
+        "dfv_dwconv_dgrad": (C.c_int, [vp, vp, vp] + [i32] * 9 + [vp]),
+        "dfv_dwconv_wgrad": (C.c_int, [vp, vp, vp] + [i32] * 9 + [vp]),
+        "dfv_stem_wgrad": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp]),
+        "dfv_attention_saved_floats": (sz, [i32] * 5),
+        "dfv_hybrid_attention_train_fwd": (C.c_int, [vp] * 7 + [i32] * 8 + [vp]),
+        "dfv_hybrid_attention_bwd": (C.c_int, [vp] * 13 + [i32] * 8 + [vp]),
+        "dfv_landmark_heatmap_bwd": (C.c_int, [vp] * 6 + [i32, i32, i32, f32, f32, i32, vp]),
+        "dfv_cast_weight": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+        "dfv_dw_weight_pack": (C.c_int, [vp, vp, i32, i32, i32, vp]),
+        "dfv_dw_weight_unpack": (C.c_int, [vp, vp, i32, i32, vp]),
+        "dfv_dropout_mask": (C.c_int, [vp, i64, f32, C.c_uint64, vp]),
+        "dfv_colsum": (C.c_int, [vp, i32, i32, vp, vp]),
+        "dfv_add_mul": (C.c_int, [vp, vp, vp, vp, i64, vp]),
+        "dfv_convert": (C.c_int, [vp, i32, vp, i32, i64, vp]),
+        "dfv_train_table_size": (C.c_int, []),
+        "dfv_train_index": (C.c_int, [i32, i32]),
+        "dfv_train_cls_index": (C.c_int, [i32, i32]),
+        "dfv_train_arena_bytes": (sz, [i32, i32, i32, i32, C.POINTER(C.c_int32), i32, i32]),
+        "dfv_train_scratch_bytes": (sz, [i32, i32, i32, i32, C.POINTER(C.c_int32), i32, i32]),
+        "dfv_train_fwd": (C.c_int, [C.POINTER(TrainArgs), vp]),
+        "dfv_train_bwd": (C.c_int, [C.POINTER(TrainArgs), vp]),
         "dfv_infer_workspace_bytes": (sz, [i32, i32, i32, i32]),
         "dfv_infer_fwd": (C.c_int, [C.POINTER(InferArgs), vp]),
     }
@@ -95,7 +151,7 @@ def check(rc: int):
 
 
 PROFILE_KINDS = ("stem", "expand_gemm", "dwconv", "se_gate", "project_gemm", "heatmap", "attention", "mlp_head",
-                 "loss", "gemm_simt")
+                 "loss", "gemm_simt", "bn_act", "pw_wgrad", "dwconv_bwd")
 
 
 def profile_records():

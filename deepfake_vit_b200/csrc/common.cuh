@@ -55,7 +55,7 @@ int debug_flags();   // DFV_DEBUG_FLAGS env: bisecting aid (1 skip dwconv, 2 ski
 // declares its kind and ALGORITHMIC bytes / flops; when enabled, start/stop events are recorded
 // on the launching stream around the launch.
 enum ProfKind { PK_STEM = 0, PK_EXPAND_GEMM, PK_DWCONV, PK_SE_GATE, PK_PROJECT_GEMM, PK_HEATMAP, PK_ATTENTION,
-                PK_MLP_HEAD, PK_LOSS, PK_GEMM_SIMT, PK_NUM };
+                PK_MLP_HEAD, PK_LOSS, PK_GEMM_SIMT, PK_BN, PK_WGRAD, PK_DWCONV_BWD, PK_NUM };
 struct ProfScope {
   ProfScope(int kind, double bytes, double flops, cudaStream_t st);
   ~ProfScope();

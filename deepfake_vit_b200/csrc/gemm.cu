@@ -479,7 +479,8 @@ extern "C" int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, 
   DFV_TRY(check_device());
   DFV_REQUIRE(a && w && bias && out, "dfv_pw_gemm_fwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype), "dfv_pw_gemm_fwd: bad dtype %d", dtype);
-  DFV_REQUIRE(M > 0 && K > 0 && N > 0 && K % 8 == 0 && N % 8 == 0, "dfv_pw_gemm_fwd: need K %% 8 == 0 and N %% 8 == 0 (M=%lld K=%d N=%d)", M, K, N);
+  DFV_REQUIRE(M > 0 && K > 0 && N > 0, "dfv_pw_gemm_fwd: bad shape (M=%lld K=%d N=%d)", M, K, N);
+  DFV_REQUIRE(dtype == DFV_F32 || (K % 8 == 0 && N % 8 == 0), "dfv_pw_gemm_fwd: bf16 needs K %% 8 == 0 and N %% 8 == 0 (K=%d N=%d)", K, N);
   DFV_REQUIRE(!a_scale || (rows_per_image > 0 && M % rows_per_image == 0), "dfv_pw_gemm_fwd: a_scale needs rows_per_image dividing M");
   DFV_REQUIRE(act == DFV_ACT_NONE || act == DFV_ACT_SILU, "dfv_pw_gemm_fwd: bad act %d", act);
   cudaStream_t st = as_stream(stream);

@@ -129,7 +129,7 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
 
   int cur = 0;
   DFV_TRY(dfv_stem_conv_fwd(a->images_nchw, (const float*)W_(-1, DFV_W_STEM), (const float*)W_(-1, DFV_W_STEM_BIAS),
-                            ws.act[cur], dtype, B, a->H, a->W, stem_c, stream));
+                            ws.act[cur], dtype, B, a->H, a->W, stem_c, DFV_ACT_SILU, stream));
   DFV_TRY(tap(0, ws.act[cur], (size_t)B * s.Hs * s.Ws * stem_c));
 
   for (int i = 0; i < n; ++i) {

@@ -27,7 +27,7 @@ __device__ __forceinline__ void stem_store12(float* p, const float o[12]) {
 template <typename T, bool kFast>
 __global__ void __launch_bounds__(256, 3) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                   const float* __restrict__ bias, T* __restrict__ y, int B, int H,
-                                                  int W, int Ho, int Wo) {
+                                                  int W, int Ho, int Wo, int act) {
   __shared__ __align__(16) float ws[27 * kStemC];
   __shared__ __align__(16) float bs[kStemC];
   for (int i = threadIdx.x; i < 27 * kStemC; i += blockDim.x) ws[i] = w[i];
@@ -80,7 +80,10 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const float* __restrict__ 
     if (wo0 + pxl < Wo) {
       float o[12];
 #pragma unroll
-      for (int i = 0; i < 12; ++i) o[i] = silu<kFast>(acc[pxl][i] + bs[cq * 12 + i]);
+      for (int i = 0; i < 12; ++i) {
+        const float v = acc[pxl][i] + bs[cq * 12 + i];
+        o[i] = act ? silu<kFast>(v) : v;
+      }
       stem_store12(y + (((size_t)b * Ho + ho) * Wo + wo0 + pxl) * kStemC + cq * 12, o);
     }
   }
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const float* __restrict__ 
 using namespace dfv;
 
 extern "C" int dfv_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int dtype, int B, int H,
-                                 int W, int C, dfv_stream_t stream) {
+                                 int W, int C, int act, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(x && w && bias && y, "dfv_stem_conv_fwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype), "dfv_stem_conv_fwd: bad dtype %d", dtype);
@@ -105,9 +108,9 @@ extern "C" int dfv_stem_conv_fwd(const float* x, const float* w, const float* bi
   ProfScope prof(PK_STEM, (double)B * 3 * H * W * 4 + (double)total * kStemC * dtype_size(dtype),
                  2.0 * 27 * kStemC * (double)total, as_stream(stream));
   if (dtype == DFV_BF16)
-    stem_kernel<__nv_bfloat16, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo);
+    stem_kernel<__nv_bfloat16, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, act);
   else
-    stem_kernel<float, false><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (float*)y, B, H, W, Ho, Wo);
+    stem_kernel<float, false><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (float*)y, B, H, W, Ho, Wo, act);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

@@ -1,0 +1,764 @@
+// Training-path building blocks over channels-last [M][C] tensors (M = B * rows_per_image):
+//   bn_stats        per-channel batch mean / inverse std (+ running-stat update)      nn.BatchNorm2d/1d, train mode
+//   bn_act          y = act(bn(raw)) [* mask] [* rowscale[b]] [+ residual], optional SE pool partials
+//   act_bn_bwd      du = dy' * act'(u), per-channel sum(du), sum(du * xhat) -> dgamma, dbeta
+//   bn_bwd_apply    d raw = gamma * invstd * (du - mean(du) - xhat * mean(du * xhat))
+//   se_*            squeeze-excite forward (saving what backward needs) and backward
+//   small helpers   weight cast / transpose, depthwise tap flip, dropout masks, column sums
+// All HBM-bound streaming kernels: 16-byte vectors of 8 channels, fixed channel group per thread,
+// fp32 accumulation, per-CTA partials finished by a tiny second kernel (deterministic).
+#include "common.cuh"
+
+namespace dfv {
+
+constexpr int kNT = 256;
+
+// Thread -> (column vector, row lane) mapping shared by the streaming kernels.
+struct ColMap {
+  int CV, cpp, rpp, col_l, row_l;
+  __device__ __forceinline__ ColMap(int C) {
+    CV = C >> 3;
+    cpp = CV < kNT ? CV : kNT;
+    rpp = kNT / cpp;
+    col_l = threadIdx.x % cpp;
+    row_l = threadIdx.x / cpp;
+  }
+};
+
+template <bool kFast>
+__device__ __forceinline__ float act_fwd(float u, int act) {
+  if (act == DFV_ACT_SILU) return silu<kFast>(u);
+  if (act == DFV_ACT_RELU) return fmaxf(u, 0.f);
+  return u;
+}
+// d act(u) / du.  swish: sigma * (1 + u * (1 - sigma))  (SwishImplementation.backward of efficientnet-pytorch)
+__device__ __forceinline__ float act_grad(float u, int act) {
+  if (act == DFV_ACT_SILU) {
+    const float s = sigmoid_exact(u);
+    return s * (1.f + u * (1.f - s));
+  }
+  if (act == DFV_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// Reduce 16 (or 8) per-thread floats across the row lanes of a column; result valid for row_l == 0.
+template <int N>
+__device__ __forceinline__ void reduce_rows(float* sm, const ColMap& m, float v[N]) {
+  if (m.rpp > 1) {
+#pragma unroll
+    for (int e = 0; e < N; ++e) sm[threadIdx.x * N + e] = v[e];
+    __syncthreads();
+    if (m.row_l == 0) {
+      for (int rl = 1; rl < m.rpp; ++rl)
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] += sm[(rl * m.cpp + m.col_l) * N + e];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------ bn_stats
+template <typename T>
+__global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw, long long rows_per_image, int C,
+                                                      long long rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float sm[kNT * 16];
+  const ColMap m(C);
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
+  const T* base = raw + (size_t)blockIdx.y * rows_per_image * C;
+  float* pout = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
+  for (int cb = 0; cb < m.CV; cb += m.cpp) {
+    const int cv = cb + m.col_l;
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    if (cv < m.CV && m.row_l < m.rpp) {
+      for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
+        float v[8];
+        load8(base + (size_t)r * C + cv * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[e] += v[e];
+          acc[8 + e] = fmaf(v[e], v[e], acc[8 + e]);
+        }
+      }
+    }
+    reduce_rows<16>(sm, m, acc);
+    if (m.row_l == 0 && cv < m.CV) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        pout[cv * 8 + e] = acc[e];
+        pout[C + cv * 8 + e] = acc[8 + e];
+      }
+    }
+  }
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int n_partial, int C, double count, float eps,
+                                         float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < n_partial; ++i) {
+    s += (double)partial[(size_t)i * 2 * C + c];
+    q += (double)partial[(size_t)i * 2 * C + C + c];
+  }
+  const double mu = s / count;
+  double var = q / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  invstd[c] = 1.0f / sqrtf((float)var + eps);
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ------------------------------------------------------------------------------------ bn_act
+template <typename T, bool kFast>
+__global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, const float* __restrict__ mean,
+                                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, int act,
+                                                    const float* __restrict__ rowscale, const T* __restrict__ residual,
+                                                    const float* __restrict__ mask, T* __restrict__ out,
+                                                    float* __restrict__ pool_partial, long long rows_per_image, int C,
+                                                    long long rows_per_chunk) {
+  __shared__ float sm[kNT * 8];
+  const ColMap m(C);
+  const int b = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
+  const size_t img = (size_t)b * rows_per_image * C;
+  const float rs = rowscale ? rowscale[b] : 1.f;
+  for (int cb = 0; cb < m.CV; cb += m.cpp) {
+    const int cv = cb + m.col_l;
+    float ps[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ps[e] = 0.f;
+    if (cv < m.CV && m.row_l < m.rpp) {
+      float sc[8], sh[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = cv * 8 + e;
+        const float is = invstd ? invstd[c] : 1.f;
+        sc[e] = gamma ? gamma[c] * is : is;
+        sh[e] = (beta ? beta[c] : 0.f) - (mean ? mean[c] : 0.f) * sc[e];
+      }
+      for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
+        const size_t off = img + (size_t)r * C + cv * 8;
+        float v[8];
+        load8(raw + off, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = act_fwd<kFast>(fmaf(v[e], sc[e], sh[e]), act);
+        if (mask) {
+          float mk[8];
+          load8(mask + off, mk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= mk[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ps[e] += v[e];
+        if (rowscale) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= rs;
+        }
+        if (residual) {
+          float rr[8];
+          load8(residual + off, rr);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += rr[e];
+        }
+        store8(out + off, v);
+      }
+    }
+    if (pool_partial) {
+      reduce_rows<8>(sm, m, ps);
+      if (m.row_l == 0 && cv < m.CV) {
+        float* po = pool_partial + ((size_t)b * gridDim.x + blockIdx.x) * C + cv * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) po[e] = ps[e];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ act_bn_bwd
+template <typename T>
+__global__ void __launch_bounds__(kNT) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
+                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int act, const T* __restrict__ gate, const float* __restrict__ dpool,
+                                                        float inv_hw, const float* __restrict__ rowscale,
+                                                        const float* __restrict__ mask, T* __restrict__ du,
+                                                        float* __restrict__ partial, long long rows_per_image, int C,
+                                                        long long rows_per_chunk) {
+  __shared__ float sm[kNT * 16];
+  const ColMap m(C);
+  const int b = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
+  const size_t img = (size_t)b * rows_per_image * C;
+  const float rs = rowscale ? rowscale[b] : 1.f;
+  float* pout = partial + ((size_t)b * gridDim.x + blockIdx.x) * 2 * C;
+  for (int cb = 0; cb < m.CV; cb += m.cpp) {
+    const int cv = cb + m.col_l;
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    if (cv < m.CV && m.row_l < m.rpp) {
+      float sc[8], sh[8], mu[8], is[8], gt[8], dp[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = cv * 8 + e;
+        is[e] = invstd ? invstd[c] : 1.f;
+        mu[e] = mean ? mean[c] : 0.f;
+        sc[e] = gamma ? gamma[c] * is[e] : is[e];
+        sh[e] = (beta ? beta[c] : 0.f) - mu[e] * sc[e];
+        dp[e] = dpool ? dpool[(size_t)b * C + c] * inv_hw : 0.f;
+      }
+      if (gate) load8(gate + (size_t)b * C + cv * 8, gt);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gt[e] = 1.f;
+      }
+      for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
+        const size_t off = img + (size_t)r * C + cv * 8;
+        float gv[8], x[8], mk[8];
+        load8(g + off, gv);
+        load8(raw + off, x);
+        if (mask) load8(mask + off, mk);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float gi = fmaf(gv[e], gt[e], dp[e]) * rs;
+          if (mask) gi *= mk[e];
+          const float u = fmaf(x[e], sc[e], sh[e]);
+          const float d = gi * act_grad(u, act);
+          gv[e] = d;
+          acc[e] += d;
+          acc[8 + e] = fmaf(d, (x[e] - mu[e]) * is[e], acc[8 + e]);
+        }
+        store8(du + off, gv);
+      }
+    }
+    reduce_rows<16>(sm, m, acc);
+    if (m.row_l == 0 && cv < m.CV) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        pout[cv * 8 + e] = acc[e];
+        pout[C + cv * 8 + e] = acc[8 + e];
+      }
+    }
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int n_partial, int C, double count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < n_partial; ++i) {
+    s1 += (double)partial[(size_t)i * 2 * C + c];
+    s2 += (double)partial[(size_t)i * 2 * C + C + c];
+  }
+  if (dbeta) dbeta[c] = (float)s1;
+  if (dgamma) dgamma[c] = (float)s2;
+  coef[c] = (float)(s1 / count);
+  coef[C + c] = (float)(s2 / count);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__ du, const T* __restrict__ raw,
+                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ coef,
+                                                          T* __restrict__ draw, long long M, int C) {
+  const int CV = C >> 3;
+  const long long total = M * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const size_t off = (size_t)(i / CV) * C + cv * 8;
+    float d[8], x[8];
+    load8(du + off, d);
+    load8(raw + off, x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cv * 8 + e;
+      const float is = invstd[c];
+      const float xh = (x[e] - mean[c]) * is;
+      d[e] = (gamma ? gamma[c] : 1.f) * is * (d[e] - coef[c] - xh * coef[C + c]);
+    }
+    store8(draw + off, d);
+  }
+}
+
+// ------------------------------------------------------------------------------------ SE (train)
+// One CTA per image.  Native torch layouts: w1 = _se_reduce.weight [sq][C], w2 = _se_expand.weight [C][sq].
+template <typename GT>
+__global__ void __launch_bounds__(512) se_train_fwd_kernel(const float* __restrict__ partial, int parts, float inv_hw,
+                                                          const float* __restrict__ w1, const float* __restrict__ b1,
+                                                          const float* __restrict__ w2, const float* __restrict__ b2,
+                                                          GT* __restrict__ gate, float* __restrict__ pooled_out,
+                                                          float* __restrict__ h1_out, float* __restrict__ gate_f32, int C,
+                                                          int sq) {
+  extern __shared__ float sm[];
+  float* pooled = sm;         // [C]
+  float* hidden = sm + C;     // [sq]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float* pb = partial + (size_t)b * parts * C + c;
+    float s = 0.f;
+    for (int t = 0; t < parts; ++t) s += pb[(size_t)t * C];
+    s *= inv_hw;
+    pooled[c] = s;
+    pooled_out[(size_t)b * C + c] = s;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < sq; j += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(w1[(size_t)j * C + c], pooled[c], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      s += b1[j];
+      h1_out[(size_t)b * sq + j] = s;
+      hidden[j] = s * sigmoid_exact(s);
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = b2[c];
+    for (int j = 0; j < sq; ++j) s = fmaf(w2[(size_t)c * sq + j], hidden[j], s);
+    const float gv = sigmoid_exact(s);
+    gate_f32[(size_t)b * C + c] = gv;
+    if constexpr (sizeof(GT) == 2) gate[(size_t)b * C + c] = __float2bfloat16_rn(gv);
+    else gate[(size_t)b * C + c] = gv;
+  }
+}
+
+// dgate partials: sum over positions of dA[pos][c] * d[pos][c]
+template <typename T>
+__global__ void __launch_bounds__(kNT) dot_rows_kernel(const T* __restrict__ a, const T* __restrict__ d,
+                                                      long long rows_per_image, int C, long long rows_per_chunk,
+                                                      float* __restrict__ partial) {
+  __shared__ float sm[kNT * 8];
+  const ColMap m(C);
+  const int b = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
+  const size_t img = (size_t)b * rows_per_image * C;
+  for (int cb = 0; cb < m.CV; cb += m.cpp) {
+    const int cv = cb + m.col_l;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (cv < m.CV && m.row_l < m.rpp) {
+      for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
+        const size_t off = img + (size_t)r * C + cv * 8;
+        float x[8], y[8];
+        load8(a + off, x);
+        load8(d + off, y);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(x[e], y[e], acc[e]);
+      }
+    }
+    reduce_rows<8>(sm, m, acc);
+    if (m.row_l == 0 && cv < m.CV) {
+      float* po = partial + ((size_t)b * gridDim.x + blockIdx.x) * C + cv * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) po[e] = acc[e];
+    }
+  }
+}
+
+// Per image: dgate (finish partials) -> dz -> dh1 -> dpool.
+__global__ void __launch_bounds__(512) se_bwd_image_kernel(const float* __restrict__ dgate_partial, int parts,
+                                                          const float* __restrict__ gate_f32, const float* __restrict__ h1,
+                                                          const float* __restrict__ w1, const float* __restrict__ w2,
+                                                          float* __restrict__ dz_out, float* __restrict__ dh1_out,
+                                                          float* __restrict__ dpool, int C, int sq) {
+  extern __shared__ float sm[];
+  float* dz = sm;          // [C]
+  float* dh1 = sm + C;     // [sq]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float* pb = dgate_partial + (size_t)b * parts * C + c;
+    float s = 0.f;
+    for (int t = 0; t < parts; ++t) s += pb[(size_t)t * C];
+    const float gv = gate_f32[(size_t)b * C + c];
+    const float v = s * gv * (1.f - gv);
+    dz[c] = v;
+    dz_out[(size_t)b * C + c] = v;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < sq; j += nwarps) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(dz[c], w2[(size_t)c * sq + j], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+      const float v = s * act_grad(h1[(size_t)b * sq + j], DFV_ACT_SILU);
+      dh1[j] = v;
+      dh1_out[(size_t)b * sq + j] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < sq; ++j) s = fmaf(dh1[j], w1[(size_t)j * C + c], s);
+    dpool[(size_t)b * C + c] = s;
+  }
+}
+
+// Weight gradients, reduced over the batch.  grid = ceil(C / 128), 128 threads: thread = channel.
+__global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __restrict__ dz, const float* __restrict__ dh1,
+                                                            const float* __restrict__ pooled, const float* __restrict__ h1,
+                                                            float* __restrict__ dw1, float* __restrict__ db1,
+                                                            float* __restrict__ dw2, float* __restrict__ db2, int B, int C,
+                                                            int sq) {
+  extern __shared__ float sm[];   // hidden [B][sq], dh1 [B][sq]
+  float* hid = sm;
+  float* dh = sm + (size_t)B * sq;
+  for (int i = threadIdx.x; i < B * sq; i += blockDim.x) {
+    const float v = h1[i];
+    hid[i] = v * sigmoid_exact(v);
+    dh[i] = dh1[i];
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float sb = 0.f;
+    for (int b = 0; b < B; ++b) sb += dz[(size_t)b * C + c];
+    db2[c] = sb;
+    for (int j = 0; j < sq; ++j) {
+      float s2 = 0.f, s1 = 0.f;
+      for (int b = 0; b < B; ++b) {
+        s2 = fmaf(dz[(size_t)b * C + c], hid[b * sq + j], s2);
+        s1 = fmaf(dh[b * sq + j], pooled[(size_t)b * C + c], s1);
+      }
+      dw2[(size_t)c * sq + j] = s2;
+      dw1[(size_t)j * C + c] = s1;
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int j = threadIdx.x; j < sq; j += blockDim.x) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += dh[b * sq + j];
+      db1[j] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ helpers
+// dst[r][c] (T) = src (fp32): same layout, or transposed (src is [cols][rows]).
+template <typename T>
+__global__ void cast_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int rows, int cols, int transpose) {
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    const float v = transpose ? src[(size_t)c * rows + r] : src[i];
+    if constexpr (sizeof(T) == 2) dst[i] = __float2bfloat16_rn(v); else dst[i] = v;
+  }
+}
+
+// Depthwise weights: torch [C][1][k][k] -> [k*k][C] fp32, optionally with the taps flipped (dgrad of a stride-1 conv).
+__global__ void dw_weight_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int kk, int flip) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * kk) return;
+  const int t = i / C, c = i % C;
+  dst[i] = src[(size_t)c * kk + (flip ? kk - 1 - t : t)];
+}
+// and back: gradient [k*k][C] -> torch layout [C][k*k]
+__global__ void dw_weight_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int kk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * kk) return;
+  const int c = i / kk, t = i % kk;
+  dst[i] = src[(size_t)t * C + c];
+}
+
+// Counter-based uniform hash (splitmix64 finaliser): out[i] = u(seed, i) >= p ? 1 / (1 - p) : 0.
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float p, unsigned long long seed) {
+  const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    out[i] = u >= p ? scale : 0.f;
+  }
+}
+
+// out[c] = sum over rows of a[r][c]  (any C; small matrices: classifier bias gradients)
+__global__ void colsum_kernel(const float* __restrict__ a, int rows, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += a[(size_t)r * C + c];
+  out[c] = s;
+}
+
+// out = (a + b) * mask   (fp32; b / mask optional)
+__global__ void add_mul_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mask,
+                               float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = a[i];
+    if (b) v += b[i];
+    if (mask) v *= mask[i];
+    out[i] = v;
+  }
+}
+
+// fp32 [M][C] -> T [M][C] (and back): gradient hand-over between the fp32 attention block and the bf16 backbone.
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v;
+    if constexpr (sizeof(S) == 2) v = __bfloat162float(src[i]); else v = src[i];
+    if constexpr (sizeof(D) == 2) dst[i] = __float2bfloat16_rn(v); else dst[i] = v;
+  }
+}
+
+static inline long long chunks_for(int B, long long rows_per_image) {
+  long long chunks = (4LL * num_sms() + B - 1) / B;
+  if (chunks < 1) chunks = 1;
+  if (chunks > rows_per_image) chunks = rows_per_image;
+  return chunks;
+}
+
+}  // namespace dfv
+
+using namespace dfv;
+
+extern "C" {
+
+int dfv_rows_chunks(int B, long long rows_per_image) {
+  if (B <= 0 || rows_per_image <= 0) return DFV_ERR_INVALID;
+  return (int)chunks_for(B, rows_per_image);
+}
+
+size_t dfv_bn_ws_floats(int B, long long rows_per_image, int C) {
+  if (B <= 0 || rows_per_image <= 0 || C <= 0) return 0;
+  return (size_t)B * chunks_for(B, rows_per_image) * 2 * C;
+}
+
+int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image, int C, float eps, float momentum,
+                     float* mean, float* invstd, float* running_mean, float* running_var, float* ws,
+                     dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(raw && mean && invstd && ws, "dfv_bn_stats_fwd: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0, "dfv_bn_stats_fwd: bad shape (C %% 8)");
+  cudaStream_t st = as_stream(stream);
+  const long long chunks = chunks_for(B, rows_per_image);
+  const long long rpc = (rows_per_image + chunks - 1) / chunks;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(PK_BN, (double)B * rows_per_image * C * dtype_size(dtype), 3.0 * B * rows_per_image * C, st);
+  if (dtype == DFV_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, rows_per_image, C, rpc, ws);
+  else bn_stats_kernel<float><<<grid, kNT, 0, st>>>((const float*)raw, rows_per_image, C, rpc, ws);
+  DFV_LAUNCH_CHECK();
+  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, eps,
+                                                         momentum, mean, invstd, running_mean, running_var);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_bn_act_fwd(const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                   const float* rowscale, const void* residual, const float* mask, void* out, float* pool_partial,
+                   int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(raw && out, "dfv_bn_act_fwd: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0, "dfv_bn_act_fwd: bad shape (C %% 8)");
+  DFV_REQUIRE(act >= DFV_ACT_NONE && act <= DFV_ACT_RELU, "dfv_bn_act_fwd: bad act %d", act);
+  cudaStream_t st = as_stream(stream);
+  const long long chunks = chunks_for(B, rows_per_image);
+  const long long rpc = (rows_per_image + chunks - 1) / chunks;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(PK_BN, (double)B * rows_per_image * C * dtype_size(dtype) * (residual ? 3.0 : 2.0), 8.0 * B * rows_per_image * C, st);
+  if (dtype == DFV_BF16)
+    bn_act_kernel<__nv_bfloat16, true><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act, rowscale,
+                                                           (const __nv_bfloat16*)residual, mask, (__nv_bfloat16*)out,
+                                                           pool_partial, rows_per_image, C, rpc);
+  else
+    bn_act_kernel<float, false><<<grid, kNT, 0, st>>>((const float*)raw, mean, invstd, gamma, beta, act, rowscale,
+                                                    (const float*)residual, mask, (float*)out, pool_partial, rows_per_image, C, rpc);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma,
+                   const float* beta, int act, const void* gate, const float* dpool, float inv_hw, const float* rowscale,
+                   const float* mask, void* du, float* dgamma, float* dbeta, float* coef, float* ws, int dtype, int B,
+                   long long rows_per_image, int C, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(g && raw && du && coef && ws, "dfv_act_bn_bwd: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0, "dfv_act_bn_bwd: bad shape (C %% 8)");
+  cudaStream_t st = as_stream(stream);
+  const long long chunks = chunks_for(B, rows_per_image);
+  const long long rpc = (rows_per_image + chunks - 1) / chunks;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 12.0 * B * rows_per_image * C, st);
+  if (dtype == DFV_BF16)
+    act_bn_bwd_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)raw, mean, invstd, gamma, beta,
+                                                        act, (const __nv_bfloat16*)gate, dpool, inv_hw, rowscale, mask,
+                                                        (__nv_bfloat16*)du, ws, rows_per_image, C, rpc);
+  else
+    act_bn_bwd_kernel<float><<<grid, kNT, 0, st>>>((const float*)g, (const float*)raw, mean, invstd, gamma, beta, act,
+                                                (const float*)gate, dpool, inv_hw, rowscale, mask, (float*)du, ws, rows_per_image, C, rpc);
+  DFV_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const float* invstd, const float* gamma,
+                     const float* coef, void* draw, int dtype, long long M, int C, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(du && raw && mean && invstd && coef && draw, "dfv_bn_bwd_apply: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype) && M > 0 && C > 0 && C % 8 == 0, "dfv_bn_bwd_apply: bad shape (C %% 8)");
+  cudaStream_t st = as_stream(stream);
+  const long long total = M * (C / 8);
+  long long blocks = (total + kNT - 1) / kNT;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  ProfScope prof(PK_BN, 3.0 * M * C * dtype_size(dtype), 6.0 * M * C, st);
+  if (dtype == DFV_BF16)
+    bn_bwd_apply_kernel<__nv_bfloat16><<<(unsigned)blocks, kNT, 0, st>>>((const __nv_bfloat16*)du, (const __nv_bfloat16*)raw, mean, invstd,
+                                                                        gamma, coef, (__nv_bfloat16*)draw, M, C);
+  else
+    bn_bwd_apply_kernel<float><<<(unsigned)blocks, kNT, 0, st>>>((const float*)du, (const float*)raw, mean, invstd, gamma, coef, (float*)draw, M, C);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_se_train_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce, const float* b_reduce,
+                     const float* w_expand, const float* b_expand, void* gate, int gate_dtype, float* pooled, float* h1,
+                     float* gate_f32, int B, int C, int squeeze, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(pool_partial && w_reduce && b_reduce && w_expand && b_expand && gate && pooled && h1 && gate_f32,
+              "dfv_se_train_fwd: null pointer");
+  DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && parts > 0 && valid_dtype(gate_dtype), "dfv_se_train_fwd: bad shape / dtype");
+  const size_t smem = (size_t)(C + squeeze) * sizeof(float);
+  DFV_REQUIRE(smem <= 48 * 1024, "dfv_se_train_fwd: C + squeeze too large");
+  cudaStream_t st = as_stream(stream);
+  ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * parts * C + 3.0 * B * C + 2.0 * C * squeeze), 4.0 * B * (double)C * squeeze, st);
+  if (gate_dtype == DFV_BF16)
+    se_train_fwd_kernel<__nv_bfloat16><<<B, 512, smem, st>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand,
+                                                          (__nv_bfloat16*)gate, pooled, h1, gate_f32, C, squeeze);
+  else
+    se_train_fwd_kernel<float><<<B, 512, smem, st>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand,
+                                                  (float*)gate, pooled, h1, gate_f32, C, squeeze);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+/* SE backward.  da: gradient wrt the gated tensor (d (.) gate), d: the activated depthwise output; both [B][rows][C].
+ * Outputs: dpool [B][C] (to be folded into the depthwise-activation gradient: + dpool / HW) and the four
+ * parameter gradients in torch layout.  ws: fp32, dfv_se_bwd_ws_floats(). */
+size_t dfv_se_bwd_ws_floats(int B, long long rows_per_image, int C, int squeeze) {
+  if (B <= 0 || rows_per_image <= 0 || C <= 0 || squeeze <= 0) return 0;
+  return (size_t)B * chunks_for(B, rows_per_image) * C + (size_t)B * C + (size_t)B * squeeze;
+}
+
+int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, const float* pooled, const float* h1,
+               const float* w_reduce, const float* w_expand, float* dpool, float* dw_reduce, float* db_reduce,
+               float* dw_expand, float* db_expand, float* ws, int B, long long rows_per_image, int C, int squeeze,
+               dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(da && d && gate_f32 && pooled && h1 && w_reduce && w_expand && dpool && dw_reduce && db_reduce && dw_expand &&
+                  db_expand && ws, "dfv_se_bwd: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0 && squeeze > 0, "dfv_se_bwd: bad shape");
+  cudaStream_t st = as_stream(stream);
+  const long long chunks = chunks_for(B, rows_per_image);
+  const long long rpc = (rows_per_image + chunks - 1) / chunks;
+  float* partial = ws;
+  float* dz = partial + (size_t)B * chunks * C;
+  float* dh1 = dz + (size_t)B * C;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(PK_SE_GATE, 2.0 * B * rows_per_image * C * dtype_size(dtype), 2.0 * B * rows_per_image * C, st);
+  if (dtype == DFV_BF16)
+    dot_rows_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)d, rows_per_image, C, rpc, partial);
+  else
+    dot_rows_kernel<float><<<grid, kNT, 0, st>>>((const float*)da, (const float*)d, rows_per_image, C, rpc, partial);
+  DFV_LAUNCH_CHECK();
+  const size_t smem = (size_t)(C + squeeze) * sizeof(float);
+  DFV_REQUIRE(smem <= 48 * 1024, "dfv_se_bwd: C + squeeze too large");
+  se_bwd_image_kernel<<<B, 512, smem, st>>>(partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, C, squeeze);
+  DFV_LAUNCH_CHECK();
+  const size_t smem2 = (size_t)2 * B * squeeze * sizeof(float);
+  DFV_REQUIRE(smem2 <= 160 * 1024, "dfv_se_bwd: batch too large for the weight-gradient kernel (B * squeeze = %d)", B * squeeze);
+  if (smem2 > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(se_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  se_bwd_weights_kernel<<<(C + 127) / 128, 128, smem2, st>>>(dz, dh1, pooled, h1, dw_reduce, db_reduce, dw_expand, db_expand, B, C, squeeze);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_cast_weight(const float* src, void* dst, int dtype, int rows, int cols, int transpose, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(src && dst && valid_dtype(dtype) && rows > 0 && cols > 0, "dfv_cast_weight: bad arguments");
+  const long long n = (long long)rows * cols;
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * num_sms());
+  if (dtype == DFV_BF16) cast_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, rows, cols, transpose);
+  else cast_weight_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(src, (float*)dst, rows, cols, transpose);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_dw_weight_pack(const float* src_ckk, float* dst_kkc, int C, int kernel, int flip, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(src_ckk && dst_kkc && C > 0 && kernel > 0, "dfv_dw_weight_pack: bad arguments");
+  const int n = C * kernel * kernel;
+  dw_weight_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(src_ckk, dst_kkc, C, kernel * kernel, flip);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_dw_weight_unpack(const float* src_kkc, float* dst_ckk, int C, int kernel, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(src_kkc && dst_ckk && C > 0 && kernel > 0, "dfv_dw_weight_unpack: bad arguments");
+  const int n = C * kernel * kernel;
+  dw_weight_unpack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(src_kkc, dst_ckk, C, kernel * kernel);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_dropout_mask(float* out, long long n, float p, unsigned long long seed, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(out && n > 0 && p >= 0.f && p <= 1.f, "dfv_dropout_mask: bad arguments");
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * num_sms());
+  dropout_mask_kernel<<<blocks, 256, 0, as_stream(stream)>>>(out, n, p, seed);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_colsum(const float* a, int rows, int C, float* out, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(a && out && rows > 0 && C > 0, "dfv_colsum: bad arguments");
+  colsum_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(a, rows, C, out);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_add_mul(const float* a, const float* b, const float* mask, float* out, long long n, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(a && out && n > 0, "dfv_add_mul: bad arguments");
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * num_sms());
+  add_mul_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, b, mask, out, n);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(src && dst && n > 0 && valid_dtype(src_dtype) && valid_dtype(dst_dtype), "dfv_convert: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 8LL * num_sms());
+  if (src_dtype == dst_dtype) {
+    DFV_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * dtype_size(src_dtype), cudaMemcpyDeviceToDevice, st));
+    return DFV_OK;
+  }
+  if (src_dtype == DFV_F32) convert_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else convert_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+}  // extern "C"

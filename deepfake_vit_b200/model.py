@@ -72,6 +72,7 @@ class _EfficientNetB4Params(nn.Module):
         nn.Linear(head_c, 1000)
         self._fc = nn.Identity()
         self.head_channels = head_c
+        self.drop_connect_rate = 0.2      # efficientnet-pytorch global params for B4
 
 
 class EfficientNetB4Backbone(nn.Module):
@@ -165,6 +166,48 @@ class DeepfakeFeatureExtractor(nn.Module):
             self.attention = None
 
 
+class _TrainState:
+    """What one train-mode forward leaves behind for its backward (arena = saved activations)."""
+
+    def __init__(self):
+        self.arena = None
+        self.key = None
+        self.in_flight = False
+
+
+def allreduce_gradients(flat: torch.Tensor, group=None):
+    """Data-parallel gradient exchange: ONE all-reduce over the flat fp32 gradient buffer,
+    averaged over ranks.  NCCL averages in the collective; gloo (CPU tests) sums then divides."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    return flat
+
+
+class _TrainFn(torch.autograd.Function):
+    """forward = dfv_train_fwd, backward = dfv_train_bwd (+ the data-parallel all-reduce)."""
+
+    @staticmethod
+    def forward(ctx, model, images, landmarks, *params):
+        logits, feats, run = model._train_fwd(images, landmarks)
+        ctx.model, ctx.run = model, run
+        ctx.n_params = len(params)
+        return logits, feats
+
+    @staticmethod
+    def backward(ctx, dlogits, dfeats):
+        grads = ctx.model._train_bwd(ctx.run, dlogits, dfeats)
+        return (None, None, None) + tuple(grads)
+
+
 class _Packed:
     """Folded, device-resident weights for one (dtype, device) pair."""
 
@@ -195,8 +238,14 @@ class DeepfakeDetectionModel(nn.Module):
         # ---- knobs that are not part of the reference API
         self.compute_dtype = torch.bfloat16     # or torch.float32 (parity mode)
         self.landmark_max_group = 0             # images per heat-map max group; 0 = whole call (reference)
+        self.ddp_allreduce = True               # average gradients over torch.distributed ranks inside backward
         self._packed: Dict[Tuple, _Packed] = {}
         self._workspace: Dict[Tuple, torch.Tensor] = {}
+        self._train_state = _TrainState()
+        self._train_scratch = None
+        self._want_taps = False                 # debug: keep NHWC copies of every stage output of a train forward
+        self._last_taps = None
+        self._last_flat_grad = None
 
     # ------------------------------------------------------------------ packing
     def _version_key(self):
@@ -319,17 +368,8 @@ class DeepfakeDetectionModel(nn.Module):
 
         tap_tensors, tap_ptrs = None, None
         if taps:
-            bb = self.feature_extractor.backbone.backbone
-            shapes = [(B, (H - 2) // 2 + 1, (W - 2) // 2 + 1, lib.dfv_b4_stem_channels())]
-            h, w = shapes[0][1], shapes[0][2]
-            for blk in bb._blocks:
-                i = blk.info
-                h = (h + i["pad_lo"] + i["pad_hi"] - i["kernel"]) // i["stride"] + 1
-                w = (w + i["pad_lo"] + i["pad_hi"] - i["kernel"]) // i["stride"] + 1
-                shapes.append((B, h, w, i["c_out"]))
-            shapes.append((B, h, w, bb.head_channels))
-            tap_tensors = [torch.empty(s, device=dev, dtype=dtype) for s in shapes]
-            tap_ptrs = (C.c_void_p * len(shapes))(*[t.data_ptr() for t in tap_tensors])
+            tap_tensors = self._tap_tensors(B, H, W, dev, dtype)
+            tap_ptrs = (C.c_void_p * len(tap_tensors))(*[t.data_ptr() for t in tap_tensors])
 
         a = _lib.InferArgs()
         a.dtype, a.B, a.H, a.W = code, B, H, W
@@ -356,13 +396,187 @@ class DeepfakeDetectionModel(nn.Module):
         check(lib.dfv_infer_fwd(C.byref(a), torch.cuda.current_stream().cuda_stream))
         return logits, feats, heat, tap_tensors
 
+    # ------------------------------------------------------------------ training
+    def _train_tensors(self):
+        """The module's own parameter / buffer tensors in the C ABI's table order (dfv_train_index)."""
+        T = [None] * lib.dfv_train_table_size()
+        ix, cx = lib.dfv_train_index, lib.dfv_train_cls_index
+
+        def bn(block, base, m):
+            T[ix(block, base)], T[ix(block, base + 1)] = m.weight, m.bias
+            T[ix(block, base + 2)], T[ix(block, base + 3)] = m.running_mean, m.running_var
+
+        bb = self.feature_extractor.backbone.backbone
+        T[ix(-1, _lib.TG_STEM_W)] = bb._conv_stem.weight
+        bn(-1, _lib.TG_STEM_G, bb._bn0)
+        for i, blk in enumerate(bb._blocks):
+            if blk.info["has_expand"]:
+                T[ix(i, _lib.T_EXPAND_W)] = blk._expand_conv.weight
+                bn(i, _lib.T_BN0_G, blk._bn0)
+            T[ix(i, _lib.T_DW_W)] = blk._depthwise_conv.weight
+            bn(i, _lib.T_BN1_G, blk._bn1)
+            T[ix(i, _lib.T_SE_R_W)], T[ix(i, _lib.T_SE_R_B)] = blk._se_reduce.weight, blk._se_reduce.bias
+            T[ix(i, _lib.T_SE_E_W)], T[ix(i, _lib.T_SE_E_B)] = blk._se_expand.weight, blk._se_expand.bias
+            T[ix(i, _lib.T_PROJ_W)] = blk._project_conv.weight
+            bn(i, _lib.T_BN2_G, blk._bn2)
+        T[ix(-1, _lib.TG_HEAD_W)] = bb._conv_head.weight
+        bn(-1, _lib.TG_HEAD_G, bb._bn1)
+        att = self.feature_extractor.attention
+        if att is not None and self.feature_extractor.use_attention:
+            if att.use_landmark:
+                T[ix(-1, _lib.TG_LM_W)] = att.landmark_attn.attention_weights
+            if att.use_spatial:
+                T[ix(-1, _lib.TG_SA_W)] = att.spatial_attn.conv.weight
+            if att.use_channel:
+                T[ix(-1, _lib.TG_CA_W1)] = att.channel_attn.fc[0].weight
+                T[ix(-1, _lib.TG_CA_W2)] = att.channel_attn.fc[2].weight
+        mods, layer, dims, i = list(self.classifier), 0, [self.feature_extractor.feature_dim], 0
+        p_drop = 0.0
+        while i < len(mods):
+            lin = mods[i]
+            T[cx(layer, 0)], T[cx(layer, 1)] = lin.weight, lin.bias
+            dims.append(lin.out_features)
+            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
+                b1 = mods[i + 1]
+                T[cx(layer, 2)], T[cx(layer, 3)], T[cx(layer, 4)], T[cx(layer, 5)] = b1.weight, b1.bias, b1.running_mean, b1.running_var
+                p_drop = mods[i + 3].p
+                i += 4
+            else:
+                i += 1
+            layer += 1
+        return T, dims, p_drop
+
+    def _train_args(self, images, landmarks, T, dims, p_drop):
+        dev = images.device
+        att = self.feature_extractor.attention
+        use_att = bool(self.feature_extractor.use_attention and att is not None)
+        a = _lib.TrainArgs()
+        a.dtype = ops.dtype_code(self.compute_dtype)
+        a.B, _, a.H, a.W = images.shape
+        a.use_attention = int(use_att)
+        a.use_landmark = int(use_att and att.use_landmark)
+        a.use_channel = int(use_att and att.use_channel)
+        a.use_spatial = int(use_att and att.use_spatial)
+        a.heat_group = int(self.landmark_max_group)
+        a.landmark_ref_size = 224.0
+        bb = self.feature_extractor.backbone.backbone
+        a.bn_eps, a.bn_momentum = bb._bn0.eps, bb._bn0.momentum
+        bn1d = [m for m in self.classifier if isinstance(m, nn.BatchNorm1d)]
+        a.cls_bn_eps, a.cls_bn_momentum = (bn1d[0].eps, bn1d[0].momentum) if bn1d else (1e-5, 0.1)
+        a.drop_connect_rate = float(bb.drop_connect_rate)
+        a.feat_dropout = float(self.feature_extractor.backbone.dropout.p)
+        a.cls_dropout = float(p_drop)
+        for t in T:
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "parameters must be contiguous fp32 CUDA tensors"
+        a.params = (C.c_void_p * len(T))(*[t.data_ptr() if t is not None else None for t in T])
+        a.images_nchw = images.data_ptr()
+        a.landmarks = landmarks.data_ptr() if landmarks is not None else None
+        a.ca_hidden = att.channel_attn.fc[0].out_features if (use_att and att.use_channel) else 0
+        hd = (C.c_int32 * len(dims))(*dims)
+        a.head_dims, a.head_layers = hd, len(dims) - 1
+        return a, hd
+
+    def _train_fwd(self, images, landmarks):
+        if not images.is_cuda:
+            raise RuntimeError("deepfake_vit_b200 runs on sm_100 CUDA devices only (no CPU path)")
+        if self.feature_extractor.backbone.freeze_bn:
+            raise NotImplementedError("freeze_bn=True training (eval-mode backbone BatchNorm inside train mode) is not built")
+        check(lib.dfv_device_check())
+        dev = images.device
+        images = images.detach().to(torch.float32).contiguous()
+        B, Cin, H, W = images.shape
+        assert Cin == 3, "images must be (B, 3, H, W)"
+        att = self.feature_extractor.attention
+        lm = None
+        if landmarks is not None and self.feature_extractor.use_attention and att is not None and att.use_landmark:
+            lm = landmarks.detach().to(device=dev, dtype=torch.float32).contiguous()
+            assert lm.shape == (B, 5, 2), "landmarks must be (B, 5, 2)"
+        T, dims, p_drop = self._train_tensors()
+        a, hd = self._train_args(images, lm, T, dims, p_drop)
+        key = (a.dtype, B, H, W, str(dev))
+        st = self._train_state
+        if st.in_flight or st.key != key or st.arena is None:
+            n = lib.dfv_train_arena_bytes(a.dtype, B, H, W, hd, a.head_layers, a.ca_hidden)
+            if n == 0:
+                check(-1)
+            if st.in_flight:          # an earlier forward still awaits its backward: do not reuse its arena
+                st = _TrainState()
+            else:
+                self._train_state = st
+            st.arena, st.key = torch.empty(n, dtype=torch.uint8, device=dev), key
+        st.in_flight = torch.is_grad_enabled()
+        a.arena, a.arena_bytes = st.arena.data_ptr(), st.arena.numel()
+        logits = torch.empty(B, dims[-1], device=dev, dtype=torch.float32)
+        feats = torch.empty(B, dims[0], device=dev, dtype=torch.float32)
+        a.logits, a.features = logits.data_ptr(), feats.data_ptr()
+        a.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        taps = None
+        if self._want_taps:
+            taps = self._tap_tensors(B, H, W, dev, self.compute_dtype)
+            a.taps = (C.c_void_p * len(taps))(*[t.data_ptr() for t in taps])
+        check(lib.dfv_train_fwd(C.byref(a), torch.cuda.current_stream().cuda_stream))
+        nbt = [m.num_batches_tracked for m in self.modules() if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d))]
+        torch._foreach_add_(nbt, 1)
+        run = dict(args=a, keep=(hd, images, lm, T, st, feats), taps=taps, state=st)
+        self._last_taps = taps
+        return logits, feats, run
+
+    def _train_bwd(self, run, dlogits, dfeats):
+        a, st = run["args"], run["state"]
+        hd, images, lm, T, _, feats = run["keep"]
+        dev = images.device
+        params = [p for _, p in self.named_parameters()]
+        offs, total = {}, 0
+        for p in params:
+            offs[id(p)] = total
+            total += p.numel()
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        gp = []
+        for t in T:
+            if t is not None and id(t) in offs:
+                gp.append(flat.data_ptr() + 4 * offs[id(t)])
+            else:
+                gp.append(None)
+        a.grads = (C.c_void_p * len(T))(*gp)
+        key = (a.dtype, a.B, a.H, a.W, str(dev))
+        if self._train_scratch is None or self._train_scratch[0] != key:
+            n = lib.dfv_train_scratch_bytes(a.dtype, a.B, a.H, a.W, hd, a.head_layers, a.ca_hidden)
+            if n == 0:
+                check(-1)
+            self._train_scratch = (key, torch.empty(n, dtype=torch.uint8, device=dev))
+        sc = self._train_scratch[1]
+        a.scratch, a.scratch_bytes = sc.data_ptr(), sc.numel()
+        dl = dlogits.detach().to(torch.float32).contiguous() if dlogits is not None else torch.zeros(a.B, self.num_classes, device=dev)
+        df = dfeats.detach().to(torch.float32).contiguous() if dfeats is not None else None
+        a.dlogits = dl.data_ptr()
+        a.dfeatures = df.data_ptr() if df is not None else None
+        check(lib.dfv_train_bwd(C.byref(a), torch.cuda.current_stream().cuda_stream))
+        st.in_flight = False
+        if self.ddp_allreduce:
+            allreduce_gradients(flat)
+        self._last_flat_grad = flat
+        return [flat[offs[id(p)]:offs[id(p)] + p.numel()].view_as(p) if p.requires_grad else None for p in params]
+
+    def _tap_tensors(self, B, H, W, dev, dtype):
+        bb = self.feature_extractor.backbone.backbone
+        shapes = [(B, (H - 2) // 2 + 1, (W - 2) // 2 + 1, lib.dfv_b4_stem_channels())]
+        h, w = shapes[0][1], shapes[0][2]
+        for blk in bb._blocks:
+            i = blk.info
+            h = (h + i["pad_lo"] + i["pad_hi"] - i["kernel"]) // i["stride"] + 1
+            w = (w + i["pad_lo"] + i["pad_hi"] - i["kernel"]) // i["stride"] + 1
+            shapes.append((B, h, w, i["c_out"]))
+        shapes.append((B, h, w, bb.head_channels))
+        return [torch.empty(s, device=dev, dtype=dtype) for s in shapes]
+
     # ------------------------------------------------------------------ reference API
     def forward(self, images: torch.Tensor, landmarks: Optional[torch.Tensor] = None,
                 return_features: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         if self.training:
-            raise NotImplementedError(
-                "the training path (batch-stat BN, dropout, backward kernels) is not built yet; "
-                "call model.eval() for inference")
+            params = [p for _, p in self.named_parameters()]
+            logits, feats = _TrainFn.apply(self, images, landmarks, *params)
+            return (logits, feats) if return_features else (logits, None)
         logits, feats, _, _ = self._infer(images, landmarks)
         return (logits, feats) if return_features else (logits, None)
 

@@ -35,12 +35,12 @@ def _f32(t):
     return _ptr(t)
 
 
-def stem_conv(x_nchw, w_khwc, bias, out_dtype):
+def stem_conv(x_nchw, w_khwc, bias, out_dtype, act=DFV_ACT_SILU):
     B, _, H, W = x_nchw.shape
     C_ = bias.numel()
     Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
     y = torch.empty(B, Ho, Wo, C_, device=x_nchw.device, dtype=out_dtype)
-    check(lib.dfv_stem_conv_fwd(_f32(x_nchw), _f32(w_khwc), _f32(bias), _ptr(y), dtype_code(out_dtype), B, H, W, C_, _stream()))
+    check(lib.dfv_stem_conv_fwd(_f32(x_nchw), _f32(w_khwc), _f32(bias), _ptr(y), dtype_code(out_dtype), B, H, W, C_, act, _stream()))
     return y
 
 
@@ -144,3 +144,164 @@ def combined_loss(logits, targets, features, class_weights, w_ce, w_focal, w_con
                                         w_con, _f32(losses), _ptr(dlogits), _ptr(dfeat), B, Cn, D, C.byref(has),
                                         _stream()))
     return losses, bool(has.value), dlogits, dfeat
+
+
+# --------------------------------------------------------------------------------------------------
+# Training-path operators (train_ops.cu, conv_bwd.cu, attention_train.cu).  Channels-last [B, rows.., C].
+# --------------------------------------------------------------------------------------------------
+def _rows(x):
+    B, C_ = x.shape[0], x.shape[-1]
+    return B, x.numel() // (B * C_), C_
+
+
+def _f32buf(n, dev):
+    return torch.empty(max(int(n), 1), device=dev, dtype=torch.float32)
+
+
+def bn_stats(raw, eps, momentum=0.0, running_mean=None, running_var=None):
+    """Batch statistics of raw [B, ..., C] -> (mean, invstd); running stats updated in place if given."""
+    B, rows, C_ = _rows(raw)
+    mean, invstd = _f32buf(C_, raw.device), _f32buf(C_, raw.device)
+    ws = _f32buf(lib.dfv_bn_ws_floats(B, rows, C_), raw.device)
+    check(lib.dfv_bn_stats_fwd(_ptr(raw), dtype_code(raw.dtype), B, rows, C_, eps, momentum, _f32(mean), _f32(invstd),
+                               _ptr(running_mean), _ptr(running_var), _f32(ws), _stream()))
+    return mean, invstd
+
+
+def bn_act(raw, mean, invstd, gamma, beta, act=DFV_ACT_NONE, rowscale=None, residual=None, mask=None, want_pool=False):
+    B, rows, C_ = _rows(raw)
+    out = torch.empty_like(raw)
+    pool = None
+    if want_pool:
+        pool = torch.empty(B, lib.dfv_rows_chunks(B, rows), C_, device=raw.device, dtype=torch.float32)
+    check(lib.dfv_bn_act_fwd(_ptr(raw), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), act, _ptr(rowscale), _ptr(residual),
+                             _ptr(mask), _ptr(out), _ptr(pool), dtype_code(raw.dtype), B, rows, C_, _stream()))
+    return (out, pool) if want_pool else out
+
+
+def act_bn_bwd(g, raw, mean, invstd, gamma, beta, act=DFV_ACT_NONE, gate=None, dpool=None, inv_hw=0.0, rowscale=None,
+               mask=None):
+    """Returns (d raw, dgamma, dbeta)."""
+    B, rows, C_ = _rows(raw)
+    dev = raw.device
+    du = torch.empty_like(raw)
+    dgamma, dbeta, coef = _f32buf(C_, dev), _f32buf(C_, dev), _f32buf(2 * C_, dev)
+    ws = _f32buf(lib.dfv_bn_ws_floats(B, rows, C_), dev)
+    code = dtype_code(raw.dtype)
+    check(lib.dfv_act_bn_bwd(_ptr(g), _ptr(raw), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), act, _ptr(gate), _ptr(dpool),
+                             inv_hw, _ptr(rowscale), _ptr(mask), _ptr(du), _f32(dgamma), _f32(dbeta), _f32(coef), _f32(ws), code,
+                             B, rows, C_, _stream()))
+    check(lib.dfv_bn_bwd_apply(_ptr(du), _ptr(raw), _f32(mean), _f32(invstd), _ptr(gamma), _f32(coef), _ptr(du), code, B * rows,
+                               C_, _stream()))
+    return du, dgamma, dbeta
+
+
+def pw_wgrad(g, a, a_scale=None, rows_per_image=0):
+    """dW [N, K] fp32 = sum_m g[m, n] * a[m, k] * a_scale[m // rows_per_image, k]."""
+    N, K = g.shape[-1], a.shape[-1]
+    M = a.numel() // K
+    dw = torch.zeros(N, K, device=g.device, dtype=torch.float32)
+    check(lib.dfv_pw_wgrad(_ptr(g), _ptr(a), _ptr(a_scale), rows_per_image, _f32(dw), dtype_code(g.dtype), M, K, N, _stream()))
+    return dw
+
+
+def dwconv_dgrad(g, w_kkc, H, W, kernel, stride, pad_lo, pad_hi):
+    B, _, _, C_ = g.shape
+    dx = torch.empty(B, H, W, C_, device=g.device, dtype=g.dtype)
+    check(lib.dfv_dwconv_dgrad(_ptr(g), _f32(w_kkc), _ptr(dx), dtype_code(g.dtype), B, H, W, C_, kernel, stride, pad_lo, pad_hi,
+                               _stream()))
+    return dx
+
+
+def dwconv_wgrad(g, x, kernel, stride, pad_lo, pad_hi):
+    B, H, W, C_ = x.shape
+    dw = torch.zeros(kernel * kernel, C_, device=g.device, dtype=torch.float32)
+    check(lib.dfv_dwconv_wgrad(_ptr(g), _ptr(x), _f32(dw), dtype_code(g.dtype), B, H, W, C_, kernel, stride, pad_lo, pad_hi,
+                               _stream()))
+    return dw
+
+
+def stem_wgrad(g, x_nchw):
+    B, _, H, W = x_nchw.shape
+    dw = torch.zeros(48, 3, 3, 3, device=g.device, dtype=torch.float32)
+    check(lib.dfv_stem_wgrad(_ptr(g), _f32(x_nchw), _f32(dw), dtype_code(g.dtype), B, H, W, _stream()))
+    return dw
+
+
+def se_train_fwd(pool_partial, hw, w_reduce, b_reduce, w_expand, b_expand, gate_dtype=torch.float32):
+    """Torch layouts: w_reduce [sq, C], w_expand [C, sq].  Returns (gate, pooled, h1, gate_f32)."""
+    B, parts, C_ = pool_partial.shape
+    sq, dev = b_reduce.numel(), pool_partial.device
+    gate = torch.empty(B, C_, device=dev, dtype=gate_dtype)
+    pooled, h1, g32 = _f32buf(B * C_, dev).view(B, C_), _f32buf(B * sq, dev).view(B, sq), _f32buf(B * C_, dev).view(B, C_)
+    check(lib.dfv_se_train_fwd(_f32(pool_partial), parts, 1.0 / hw, _f32(w_reduce), _f32(b_reduce), _f32(w_expand), _f32(b_expand),
+                               _ptr(gate), dtype_code(gate_dtype), _f32(pooled), _f32(h1), _f32(g32), B, C_, sq, _stream()))
+    return gate, pooled, h1, g32
+
+
+def se_bwd(da, d, gate_f32, pooled, h1, w_reduce, w_expand):
+    """Returns (dpool [B, C], dw_reduce, db_reduce, dw_expand, db_expand)."""
+    B, rows, C_ = _rows(d)
+    sq, dev = h1.shape[1], d.device
+    dpool = _f32buf(B * C_, dev).view(B, C_)
+    dw1, db1 = torch.zeros_like(w_reduce), _f32buf(sq, dev)
+    dw2, db2 = torch.zeros_like(w_expand), _f32buf(C_, dev)
+    ws = _f32buf(lib.dfv_se_bwd_ws_floats(B, rows, C_, sq), dev)
+    check(lib.dfv_se_bwd(_ptr(da), _ptr(d), dtype_code(d.dtype), _f32(gate_f32), _f32(pooled), _f32(h1), _f32(w_reduce),
+                         _f32(w_expand), _f32(dpool), _f32(dw1), _f32(db1), _f32(dw2), _f32(db2), _f32(ws), B, rows, C_, sq,
+                         _stream()))
+    return dpool, dw1, db1, dw2, db2
+
+
+def hybrid_attention_train(fmap, heat, ca_w1, ca_w2, sa_w, use_channel=True, use_spatial=True):
+    """Torch layouts (ca_w2 = fc.2.weight [C, hidden]).  Returns (features, saved)."""
+    B, H, W, C_ = fmap.shape
+    hidden = ca_w1.shape[0] if use_channel else 0
+    feats = torch.empty(B, C_, device=fmap.device, dtype=torch.float32)
+    saved = _f32buf(lib.dfv_attention_saved_floats(B, H, W, C_, hidden), fmap.device)
+    check(lib.dfv_hybrid_attention_train_fwd(_ptr(fmap), _ptr(heat), _ptr(ca_w1), _ptr(ca_w2), _ptr(sa_w), _f32(feats), _f32(saved),
+                                             dtype_code(fmap.dtype), B, H, W, C_, hidden, int(use_channel), int(use_spatial),
+                                             _stream()))
+    return feats, saved
+
+
+def hybrid_attention_bwd(fmap, heat, ca_w1, ca_w2, sa_w, dfeatures, saved, use_channel=True, use_spatial=True):
+    """Returns (dfmap, dheat | None, dca_w1, dca_w2, dsa_w)."""
+    B, H, W, C_ = fmap.shape
+    dev = fmap.device
+    hidden = ca_w1.shape[0] if use_channel else 0
+    dfmap = torch.empty_like(fmap)
+    dheat = torch.empty(B, H, W, device=dev, dtype=torch.float32) if heat is not None else None
+    dw1 = torch.zeros_like(ca_w1) if use_channel else None
+    dw2 = torch.zeros_like(ca_w2) if use_channel else None
+    dsa = torch.zeros(98, device=dev, dtype=torch.float32) if use_spatial else None
+    ws = _f32buf(B * C_ + 2 * B * max(hidden, 1), dev)
+    check(lib.dfv_hybrid_attention_bwd(_ptr(fmap), _ptr(heat), _ptr(ca_w1), _ptr(ca_w2), _ptr(sa_w), _f32(dfeatures), _f32(saved),
+                                       _ptr(dfmap), _ptr(dheat), _ptr(dw1), _ptr(dw2), _ptr(dsa), _f32(ws), dtype_code(fmap.dtype),
+                                       B, H, W, C_, hidden, int(use_channel), int(use_spatial), _stream()))
+    return dfmap, dheat, dw1, dw2, dsa
+
+
+def landmark_heatmap_train(landmarks, weights5, H, W, ref_size=224.0, sigma=1.5, group=0):
+    """Returns (heat, raw, max_ws) -- the scratch buffers are what landmark_heatmap_bwd needs."""
+    B, dev = landmarks.shape[0], landmarks.device
+    heat = torch.empty(B, H, W, device=dev, dtype=torch.float32)
+    raw = torch.empty(B * H * W, device=dev, dtype=torch.float32)
+    mx = torch.empty(B, device=dev, dtype=torch.int32)
+    check(lib.dfv_landmark_heatmap_fwd(_f32(landmarks), _f32(weights5), _f32(heat), _f32(raw), _ptr(mx), None, B, H, W, ref_size,
+                                       sigma, group, _stream()))
+    return heat, raw, mx
+
+
+def landmark_heatmap_bwd(landmarks, weights5, raw, mx, dheat, H, W, ref_size=224.0, sigma=1.5, group=0):
+    B = landmarks.shape[0]
+    dw = torch.empty(5, device=landmarks.device, dtype=torch.float32)
+    check(lib.dfv_landmark_heatmap_bwd(_f32(landmarks), _f32(weights5), _f32(raw), _ptr(mx), _f32(dheat), _f32(dw), B, H, W,
+                                       ref_size, sigma, group, _stream()))
+    return dw
+
+
+def dropout_mask(shape, p, seed, device):
+    out = torch.empty(shape, device=device, dtype=torch.float32)
+    check(lib.dfv_dropout_mask(_f32(out), out.numel(), p, seed, _stream()))
+    return out

@@ -37,7 +37,7 @@ extern "C" {
 typedef void* dfv_stream_t; /* cudaStream_t */
 
 enum { DFV_F32 = 0, DFV_BF16 = 1 };
-enum { DFV_ACT_NONE = 0, DFV_ACT_SILU = 1 };
+enum { DFV_ACT_NONE = 0, DFV_ACT_SILU = 1, DFV_ACT_RELU = 2 };
 
 enum {
   DFV_OK = 0,
@@ -63,8 +63,9 @@ long long dfv_launch_count(int reset);
 /* Per-launch profiler (CUDA events on the launching stream around every operator launch), used
  * by bench.py for the roofline leg.  enable(1) clears and starts recording, enable(0) stops.
  * get(): kind (0 stem, 1 expand/head GEMM, 2 depthwise, 3 SE gate, 4 project GEMM, 5 heat-map,
- * 6 attention, 7 MLP head, 8 loss, 9 SIMT GEMM), the launch's ALGORITHMIC bytes and flops, and
- * its duration in ms (synchronises on the launch's stop event). */
+ * 6 attention, 7 MLP head, 8 loss, 9 SIMT GEMM, 10 BatchNorm/activation pass, 11 1x1 weight gradient,
+ * 12 depthwise backward), the launch's ALGORITHMIC bytes and flops, and its duration in ms
+ * (synchronises on the launch's stop event). */
 int dfv_profile_enable(int on);
 int dfv_profile_count(void);
 int dfv_profile_get(int idx, int* kind, double* bytes, double* flops, float* ms);
@@ -124,7 +125,7 @@ int dfv_blob_slot(int dtype, int block, int kind, size_t* offset, size_t* elems)
  * 0.7.1, reached from efficientnet.py:163).  x is the reference's input contract
  * (src/data/dataset.py:82-116): NCHW fp32.  y: NHWC [B][Ho][Wo][C]. */
 int dfv_stem_conv_fwd(const float* x_nchw, const float* w_khwc, const float* bias, void* y, int dtype,
-                      int B, int H, int W, int C, dfv_stream_t stream);
+                      int B, int H, int W, int C, int act, dfv_stream_t stream);
 
 /* Depthwise k x k conv (k in {3,5}, stride in {1,2}) with the static asymmetric pad
  * applied by TMA out-of-bounds zero fill (no padded copy), folded BN, swish, and the SE
@@ -238,6 +239,149 @@ typedef struct {
 
 size_t dfv_infer_workspace_bytes(int dtype, int B, int H, int W);
 int dfv_infer_fwd(const dfv_infer_args* args, dfv_stream_t stream);
+
+
+/* ====================================================================================
+ * Training path: train-mode forward (batch-statistics BatchNorm,
+ * dropout, drop-connect) and the backward pass that `loss.backward()` runs in the reference
+ * (src/training/trainer.py:140-153).  Building blocks first, then the whole-path sequencer.
+ * Tensors are channels-last [B][rows_per_image][C]; C % 8 == 0.
+ * ==================================================================================== */
+
+/* Number of row chunks per image the streaming kernels use (= SE pool `parts` of dfv_bn_act_fwd). */
+int dfv_rows_chunks(int B, long long rows_per_image);
+/* fp32 scratch the BatchNorm statistics / backward-reduce kernels need. */
+size_t dfv_bn_ws_floats(int B, long long rows_per_image, int C);
+
+/* nn.BatchNorm2d / BatchNorm1d in train mode, statistics half: per-channel mean and 1/sqrt(biased var + eps)
+ * of raw; running_mean / running_var (may be NULL) updated with `momentum` and the UNBIASED variance. */
+int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image, int C, float eps, float momentum,
+                     float* mean, float* invstd, float* running_mean, float* running_var, float* ws, dfv_stream_t stream);
+/* out = act(gamma * (raw - mean) * invstd + beta) [* mask] [* rowscale[image]] [+ residual].
+ * mean/invstd/gamma/beta may be NULL (identity).  mask: fp32 [B][rows][C] (dropout keep-scale) or NULL.
+ * rowscale: fp32 [B] (drop-connect) or NULL.  pool_partial: fp32 [B][dfv_rows_chunks()][C] per-chunk sums of the
+ * activated values (SE squeeze) or NULL.  `_swish(_bnX(conv))`, `_bn2(..)` + drop_connect + skip of MBConvBlock.forward. */
+int dfv_bn_act_fwd(const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                   const float* rowscale, const void* residual, const float* mask, void* out, float* pool_partial,
+                   int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream);
+/* Backward through [mask, rowscale, SE gate] -> activation -> BatchNorm, reduction half:
+ *   gin = (g * gate[image][c] + dpool[image][c] * inv_hw) * rowscale[image] * mask;  du = gin * act'(u)
+ * writes du (may alias g), dgamma = sum du * xhat, dbeta = sum du (may be NULL), coef [2][C] = the two means. */
+int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma,
+                   const float* beta, int act, const void* gate, const float* dpool, float inv_hw, const float* rowscale,
+                   const float* mask, void* du, float* dgamma, float* dbeta, float* coef, float* ws, int dtype, int B,
+                   long long rows_per_image, int C, dfv_stream_t stream);
+/* d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])   (draw may alias du) */
+int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const float* invstd, const float* gamma,
+                     const float* coef, void* draw, int dtype, long long M, int C, dfv_stream_t stream);
+
+/* Squeeze-excite forward that also saves pooled [B][C], h1 [B][sq] (pre-swish) and the fp32 gate; weights in
+ * torch layout: w_reduce [sq][C], w_expand [C][sq]. */
+int dfv_se_train_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce, const float* b_reduce,
+                     const float* w_expand, const float* b_expand, void* gate, int gate_dtype, float* pooled, float* h1,
+                     float* gate_f32, int B, int C, int squeeze, dfv_stream_t stream);
+size_t dfv_se_bwd_ws_floats(int B, long long rows_per_image, int C, int squeeze);
+int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, const float* pooled, const float* h1,
+               const float* w_reduce, const float* w_expand, float* dpool, float* dw_reduce, float* db_reduce,
+               float* dw_expand, float* db_expand, float* ws, int B, long long rows_per_image, int C, int squeeze,
+               dfv_stream_t stream);
+
+/* 1x1 conv weight gradient: dw[N][K] (fp32, torch layout, caller zeroes) += sum_m g[m][n] a[m][k] a_scale[m/rpi][k]. */
+int dfv_pw_wgrad(const void* g, const void* a, const void* a_scale, int rows_per_image, float* dw, int dtype, long long M,
+                 int K, int N, dfv_stream_t stream);
+/* Depthwise conv gradients (H, W = INPUT size of the forward conv; w / dw are fp32 [k*k][C]). */
+int dfv_dwconv_dgrad(const void* g, const float* w_kkc, void* dx, int dtype, int B, int H, int W, int C, int kernel,
+                     int stride, int pad_lo, int pad_hi, dfv_stream_t stream);
+int dfv_dwconv_wgrad(const void* g, const void* x, float* dw_kkc, int dtype, int B, int H, int W, int C, int kernel,
+                     int stride, int pad_lo, int pad_hi, dfv_stream_t stream);
+int dfv_stem_wgrad(const void* g, const float* x_nchw, float* dw, int dtype, int B, int H, int W, dfv_stream_t stream);
+
+/* HybridAttention train forward / backward and the heat-map backward (attention_train.cu). */
+size_t dfv_attention_saved_floats(int B, int H, int W, int C, int hidden);
+int dfv_hybrid_attention_train_fwd(const void* fmap, const float* heat, const float* ca_w1, const float* ca_w2,
+                                   const float* sa_w, float* features, float* saved, int dtype, int B, int H, int W, int C,
+                                   int hidden, int use_channel, int use_spatial, dfv_stream_t stream);
+int dfv_hybrid_attention_bwd(const void* fmap, const float* heat, const float* ca_w1, const float* ca_w2,
+                             const float* sa_w, const float* dfeatures, const float* saved, void* dfmap, float* dheat,
+                             float* dca_w1, float* dca_w2, float* dsa_w, float* ws, int dtype, int B, int H, int W, int C,
+                             int hidden, int use_channel, int use_spatial, dfv_stream_t stream);
+int dfv_landmark_heatmap_bwd(const float* landmarks, const float* weights5, const float* raw_ws, const uint32_t* max_ws,
+                             const float* dheat, float* dweights5, int B, int H, int W, float ref_size, float sigma,
+                             int group, dfv_stream_t stream);
+
+/* Small helpers. */
+int dfv_cast_weight(const float* src, void* dst, int dtype, int rows, int cols, int transpose, dfv_stream_t stream);
+int dfv_dw_weight_pack(const float* src_ckk, float* dst_kkc, int C, int kernel, int flip, dfv_stream_t stream);
+int dfv_dw_weight_unpack(const float* src_kkc, float* dst_ckk, int C, int kernel, dfv_stream_t stream);
+int dfv_dropout_mask(float* out, long long n, float p, unsigned long long seed, dfv_stream_t stream);
+int dfv_colsum(const float* a, int rows, int C, float* out, dfv_stream_t stream);
+int dfv_add_mul(const float* a, const float* b, const float* mask, float* out, long long n, dfv_stream_t stream);
+int dfv_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, dfv_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole-path training step.  `params` / `grads` are host arrays of dfv_train_table_size() device
+ * pointers to fp32 tensors in torch layout (the module's own parameter / buffer storage):
+ *   block tensors   index = dfv_train_index(block 0..31, DFV_T_*)
+ *   global tensors  index = dfv_train_index(-1, DFV_TG_*)
+ *   classifier      index = dfv_train_cls_index(layer, 0 weight | 1 bias | 2 bn.weight | 3 bn.bias |
+ *                                                      4 bn.running_mean | 5 bn.running_var)
+ * Entries of tensors a configuration lacks are NULL.  dfv_train_fwd updates the BatchNorm running
+ * statistics in place (num_batches_tracked is the host's to bump).  dfv_train_bwd ADDS every parameter
+ * gradient into grads[] (the caller zeroes the buffer); entries for running statistics are ignored.
+ * arena: saved activations, written by fwd and read by bwd; scratch: backward temporaries.
+ * ---------------------------------------------------------------------------------- */
+enum {
+  DFV_T_EXPAND_W = 0, DFV_T_BN0_G, DFV_T_BN0_B, DFV_T_BN0_RM, DFV_T_BN0_RV,
+  DFV_T_DW_W, DFV_T_BN1_G, DFV_T_BN1_B, DFV_T_BN1_RM, DFV_T_BN1_RV,
+  DFV_T_SE_R_W, DFV_T_SE_R_B, DFV_T_SE_E_W, DFV_T_SE_E_B,
+  DFV_T_PROJ_W, DFV_T_BN2_G, DFV_T_BN2_B, DFV_T_BN2_RM, DFV_T_BN2_RV,
+  DFV_T_PER_BLOCK
+};
+enum {
+  DFV_TG_STEM_W = 0, DFV_TG_STEM_G, DFV_TG_STEM_B, DFV_TG_STEM_RM, DFV_TG_STEM_RV,
+  DFV_TG_HEAD_W, DFV_TG_HEAD_G, DFV_TG_HEAD_B, DFV_TG_HEAD_RM, DFV_TG_HEAD_RV,
+  DFV_TG_LM_W, DFV_TG_SA_W, DFV_TG_CA_W1, DFV_TG_CA_W2,
+  DFV_TG_COUNT
+};
+#define DFV_MAX_CLS_LAYERS 8
+int dfv_train_table_size(void);
+int dfv_train_index(int block, int kind);
+int dfv_train_cls_index(int layer, int kind);
+
+typedef struct {
+  int32_t dtype;
+  int32_t B, H, W;
+  int32_t use_attention, use_landmark, use_channel, use_spatial;
+  int32_t heat_group;              /* images per heat-map max group; 0 = whole batch */
+  float landmark_ref_size;         /* 224.0 */
+  float bn_eps, bn_momentum;       /* backbone BatchNorm2d: 1e-3, 0.01 (efficientnet-pytorch B4 global params) */
+  float cls_bn_eps, cls_bn_momentum; /* classifier BatchNorm1d: torch defaults 1e-5, 0.1 */
+  float drop_connect_rate;         /* 0.2; block i uses rate * i / 32 (EfficientNet.extract_features) */
+  float feat_dropout, cls_dropout; /* feature_extractor.backbone.dropout p, classifier Dropout p */
+  uint64_t seed;                   /* dropout / drop-connect masks are a function of (seed, position) */
+  const float* const* params;
+  float* const* grads;             /* bwd only */
+  const float* images_nchw;        /* [B][3][H][W] fp32 */
+  const float* landmarks;          /* [B][5][2] fp32 or NULL */
+  int32_t ca_hidden;
+  const int32_t* head_dims;        /* host int[head_layers + 1] */
+  int32_t head_layers;
+  void* arena;
+  size_t arena_bytes;
+  void* scratch;
+  size_t scratch_bytes;
+  float* logits;                   /* fwd out [B][num_classes] */
+  float* features;                 /* fwd out [B][1792]: post-dropout pooled features (what CombinedLoss receives) */
+  const float* dlogits;            /* bwd in  [B][num_classes] */
+  const float* dfeatures;          /* bwd in  [B][1792] or NULL */
+  void* const* taps;               /* optional debug: host array of 34 device pointers (stem, block0..31, head)
+                                      receiving NHWC copies of each stage output (fwd) */
+} dfv_train_args;
+
+size_t dfv_train_arena_bytes(int dtype, int B, int H, int W, const int32_t* head_dims, int head_layers, int ca_hidden);
+size_t dfv_train_scratch_bytes(int dtype, int B, int H, int W, const int32_t* head_dims, int head_layers, int ca_hidden);
+int dfv_train_fwd(const dfv_train_args* args, dfv_stream_t stream);
+int dfv_train_bwd(const dfv_train_args* args, dfv_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,186 @@
+"""Whole-path training parity (B200 only): train-mode forward + CombinedLoss + backward of the drop-in
+module against the oracle (the reference's modules over the restated backbone, fp32 autograd on CPU),
+same weights, same synthetic inputs.  Stochastic parts (Dropout x4, drop-connect) are switched off on
+both sides for the exact comparison and tested separately for their statistics.
+
+Tolerances: fp32 mode -- logits / features / loss 1e-4 relative, every parameter gradient 5e-3 relative
+L2 (||g|| > 1e-7), BatchNorm running statistics 1e-4; bf16 mode -- loss 3e-2, flat-gradient cosine > 0.9.
+"""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+LOSS_W = {"ce": 1.0, "focal": 0.5, "contrastive": 0.2}
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _no_stochastic(model, oracle_side):
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    bb = model.feature_extractor.backbone.backbone
+    if oracle_side:
+        bb._global_params = bb._global_params._replace(drop_connect_rate=0.0)
+    else:
+        bb.drop_connect_rate = 0.0
+
+
+def _pair(size, stochastic=False):
+    import deepfake_vit_b200 as d
+    from oracle import calibrate, refmodel
+    om = calibrate.build(refmodel.get_oracle(), "calibrated", calib_size=size, calib_batches=2)
+    m = d.DeepfakeDetectionModel(**refmodel.MODEL_CONFIG)
+    m.load_state_dict(om.state_dict(), strict=True)
+    m = m.to(DEV)
+    if not stochastic:
+        _no_stochastic(om, True)
+        _no_stochastic(m, False)
+    return om.train(), m.train(), d, refmodel
+
+
+@pytest.fixture(scope="module")
+def step96():
+    """One training step on both sides: B = 4, 96 x 96, class-weighted CombinedLoss."""
+    from oracle import calibrate
+    om, m, d, refmodel = _pair(96)
+    x, lm, y = calibrate.synthetic_batch(4, 96)
+    y = torch.tensor([0, 1, 1, 1])
+    cw = torch.tensor([1.0, 1.5])
+    lo, fe = om(x, lm, return_features=True)
+    ref_loss = refmodel.CombinedLoss(LOSS_W, cw)(lo, y, fe)
+    ref_loss["total"].backward()
+    m.set_compute_dtype(torch.float32)
+    lo2, fe2 = m(x.to(DEV), lm.to(DEV), return_features=True)
+    loss = d.CombinedLoss(LOSS_W, cw.to(DEV))(lo2, y.to(DEV), fe2)
+    loss["total"].backward()
+    torch.cuda.synchronize()
+    return om, m, (lo, fe, ref_loss), (lo2, fe2, loss)
+
+
+def test_train_forward_fp32(step96):
+    om, m, (lo, fe, ref_loss), (lo2, fe2, loss) = step96
+    assert rel(fe2, fe) < 1e-4
+    assert rel(lo2, lo) < 1e-4
+    for k in ("ce", "focal", "contrastive", "total"):
+        assert abs(loss[k].item() - ref_loss[k].item()) < 1e-4 * max(1.0, abs(ref_loss[k].item())), k
+
+
+def test_train_gradients_fp32(step96):
+    om, m, _, _ = step96
+    ref = dict(om.named_parameters())
+    norms = sorted(float(p.grad.norm()) for p in ref.values())
+    typical = norms[len(norms) // 2]
+    # Some gradients vanish analytically (a BatchNorm bias feeding a conv + batch-stat BatchNorm is a no-op
+    # shift): they are rounding noise on both sides, so the error is measured against max(||ref||, 1e-3 * median norm).
+    worst, bad = 0.0, []
+    for name, p in m.named_parameters():
+        g, r = p.grad, ref[name].grad
+        assert g is not None, name
+        assert r is not None, name
+        e = float((g.double().cpu() - r.double()).norm()) / max(float(r.norm()), 1e-3 * typical)
+        worst = max(worst, e)
+        if e > 5e-3:
+            bad.append((name, e, r.norm().item()))
+    print("median gradient norm", typical, "worst parameter-gradient relative error", worst)
+    assert not bad, f"{len(bad)} gradients off, worst first: {sorted(bad, key=lambda t: -t[1])[:8]}"
+
+
+def test_train_running_stats_fp32(step96):
+    om, m, _, _ = step96
+    sd, ref = m.state_dict(), om.state_dict()
+    for k, v in ref.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert rel(sd[k], v) < 1e-4, k
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+
+
+def test_train_step_bf16_close_to_fp32_oracle(step96):
+    from oracle import calibrate
+    om, m, (lo, fe, ref_loss), _ = step96
+    import deepfake_vit_b200 as d
+    x, lm, _ = calibrate.synthetic_batch(4, 96)
+    y = torch.tensor([0, 1, 1, 1])
+    m.zero_grad(set_to_none=True)
+    m.set_compute_dtype(torch.bfloat16)
+    lo2, fe2 = m(x.to(DEV), lm.to(DEV), return_features=True)
+    loss = d.CombinedLoss(LOSS_W, torch.tensor([1.0, 1.5], device=DEV))(lo2, y.to(DEV), fe2)
+    loss["total"].backward()
+    m.set_compute_dtype(torch.float32)
+    assert abs(loss["total"].item() - ref_loss["total"].item()) < 3e-2 * max(1.0, abs(ref_loss["total"].item()))
+    ref = dict(om.named_parameters())
+    a = torch.cat([p.grad.flatten().cpu().double() for _, p in m.named_parameters()])
+    b = torch.cat([ref[n].grad.flatten().double() for n, _ in m.named_parameters()])
+    cos = (a @ b / (a.norm() * b.norm())).item()
+    print("bf16 flat-gradient cosine vs fp32 oracle", cos, "norm ratio", (a.norm() / b.norm()).item())
+    assert cos > 0.9
+
+
+def test_train_without_landmarks_and_partial_attention():
+    """landmarks=None skips the landmark stage (landmark_attention.py:299); odd batch drops the last contrastive sample."""
+    from oracle import calibrate
+    om, m, d, refmodel = _pair(64)
+    x, _, _ = calibrate.synthetic_batch(3, 64)
+    y = torch.tensor([1, 0, 1])
+    lo, fe = om(x, None, return_features=True)
+    refmodel.CombinedLoss(LOSS_W, None)(lo, y, fe)["total"].backward()
+    m.set_compute_dtype(torch.float32)
+    lo2, fe2 = m(x.to(DEV), None, return_features=True)
+    d.CombinedLoss(LOSS_W, None)(lo2, y.to(DEV), fe2)["total"].backward()
+    assert rel(lo2, lo) < 1e-4
+    ref = dict(om.named_parameters())
+    for name in ("feature_extractor.backbone.backbone._conv_stem.weight", "feature_extractor.attention.channel_attn.fc.0.weight",
+                 "feature_extractor.attention.spatial_attn.conv.weight", "classifier.0.weight",
+                 "feature_extractor.backbone.backbone._blocks.16._depthwise_conv.weight"):
+        assert rel(dict(m.named_parameters())[name].grad, ref[name].grad) < 5e-3, name
+    lmw = m.feature_extractor.attention.landmark_attn.attention_weights
+    assert lmw.grad is None or float(lmw.grad.abs().max()) == 0.0
+
+
+def test_optimizer_steps_reduce_loss():
+    """The drop-in trains with the stock optimizer exactly as Trainer.train_epoch drives it (trainer.py:140-167)."""
+    from oracle import calibrate
+    _, m, d, _ = _pair(64, stochastic=True)
+    m.set_compute_dtype(torch.bfloat16)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-4)
+    crit = d.CombinedLoss(LOSS_W, None)
+    x, lm, y = calibrate.synthetic_batch(8, 64)
+    x, lm, y = x.to(DEV), lm.to(DEV), y.to(DEV)
+    torch.manual_seed(0)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        lo, fe = m(x, lm, return_features=True)
+        loss = crit(lo, y, fe)["total"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        losses.append(loss.item())
+    assert all(map(lambda v: v == v and abs(v) < 1e4, losses)), losses
+    assert min(losses[3:]) < losses[0], losses
+
+
+def test_stochastic_paths_are_seeded():
+    from oracle import calibrate
+    _, m, d, _ = _pair(64, stochastic=True)
+    m.set_compute_dtype(torch.float32)
+    x, lm, _ = calibrate.synthetic_batch(4, 64)
+    x, lm = x.to(DEV), lm.to(DEV)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    outs = []
+    for seed in (5, 5, 6):
+        m.load_state_dict(sd)
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            outs.append(m(x, lm, return_features=True)[1].clone())
+    assert torch.equal(outs[0], outs[1])
+    assert not torch.equal(outs[0], outs[2])
+    zero_frac = (outs[0] == 0).float().mean().item()          # feature dropout p = 0.4
+    assert 0.3 < zero_frac < 0.5, zero_frac
