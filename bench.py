@@ -103,6 +103,116 @@ def cpu_reference_run(steps, warmup, batch=8):
             "ms_per_step": 1e3 * total / steps}
 
 
+def train_bench(args, d, _lib, dev, rank, world, local, warmup):
+    """BASELINE.json configs[2]: training step = train-mode forward + CombinedLoss + backward + NCCL gradient
+    all-reduce (inside backward), batch 64 per GPU, bf16 activations / fp32 master weights and gradients."""
+    import torch
+    import torch.distributed as dist
+    B = args.batch if args.batch != 256 else 64
+    torch.manual_seed(42)
+    model = d.DeepfakeDetectionModel(**d.DEFAULT_MODEL_CONFIG).to(dev).train().set_compute_dtype(torch.bfloat16)
+    if world > 1:
+        d.parallel.broadcast_parameters(model)
+    crit = d.CombinedLoss({"ce": 1.0, "focal": 0.5, "contrastive": 0.2}, torch.tensor([1.0, 1.5], device=dev))
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_x = torch.randn(B, 3, SIZE, SIZE, generator=g).pin_memory()
+    host_lm = (torch.rand(B, 5, 2, generator=g) * SIZE).pin_memory()
+    host_y = torch.randint(0, 2, (B,), generator=g).pin_memory()
+    x, lm, y = host_x.to(dev), host_lm.to(dev), host_y.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(xx, ll, yy):
+        model.zero_grad(set_to_none=True)
+        lo, fe = model(xx, ll, return_features=True)
+        loss = crit(lo, yy, fe)["total"]
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step(x, lm, y)
+    barrier()
+    _lib.lib.dfv_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step(x, lm, y)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = int(_lib.lib.dfv_launch_count(0))
+
+    _lib.lib.dfv_profile_enable(1)
+    prof_steps = min(args.steps, 3)
+    for _ in range(prof_steps):
+        step(x, lm, y)
+    torch.cuda.synchronize()
+    recs = _lib.profile_records()
+    _lib.lib.dfv_profile_enable(0)
+    agg = {}
+    for kind, nbytes, flops, kms in recs:
+        a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
+        a[0] += nbytes; a[1] += flops; a[2] += kms; a[3] += 1
+    pk = peaks()
+    kernels = {k: {"launches_per_step": n // prof_steps, "ms_per_step": kms / prof_steps,
+                   "gbs": nb / (kms * 1e-3) / 1e9 if kms > 0 else None, "tflops": fl / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                   "hbm_frac": nb / (kms * 1e-3) / 1e9 / pk["hbm_gbs"] if kms > 0 else None}
+               for k, (nb, fl, kms, n) in agg.items()}
+    top = max(agg, key=lambda k: agg[k][2])
+    tb, tf, tms, tn = agg[top]
+    roofline = {"kernel": top, "bound": "hbm", "achieved": tb / (tms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "launches": tn // prof_steps, "avg_launch_ms": tms / tn, "algorithmic_bytes_per_launch": tb / tn, "kernels": kernels}
+
+    # end to end: pinned host batch -> device every step, loss read back every step
+    dx, dl, dy = torch.empty_like(x), torch.empty_like(lm), torch.empty_like(y)
+
+    def e2e_step():
+        dx.copy_(host_x, non_blocking=True)
+        dl.copy_(host_lm, non_blocking=True)
+        dy.copy_(host_y, non_blocking=True)
+        return step(dx, dl, dy).item()
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t[0].item(), t[1].item()
+    n_gpus = max(world, 1)
+    if rank == 0:
+        line = {"metric": "images/sec @380x380 train-step (bf16)", "value": B * n_gpus * args.steps / (ms * 1e-3), "unit": "images/s",
+                "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"training step fwd + CombinedLoss(CE+Focal+Contrastive, class weights) + bwd + gradient all-reduce, "
+                                       f"batch {B}/GPU @ {SIZE}x{SIZE} (BASELINE.json configs[2]); optimizer step not included",
+                           "per_gpu_batch": B, "global_batch": B * n_gpus, "image_size": SIZE,
+                           "parallelism": f"dp{n_gpus} (batch sharded, one NCCL all-reduce of the flat fp32 gradient buffer per step)",
+                           "l2_policy": "activations exceed the 126 MB L2; no flush needed"},
+                "roofline": roofline, "cpu_baseline": None,
+                "e2e": {"value": B * n_gpus * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
+                        "h2d_bytes_per_step": (x.numel() * 4 + lm.numel() * 4 + y.numel() * 8) * n_gpus, "d2h_bytes_per_step": 4 * n_gpus,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "clocks": clk.summary(),
+                "memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -110,6 +220,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE.json configs[1] (the headline line); train = configs[2], fwd + CombinedLoss + bwd + "
+                         "gradient all-reduce at batch 64/GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -148,6 +261,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.mode == "train":
+        return train_bench(args, d, _lib, dev, rank, world, local, warmup)
 
     torch.manual_seed(42)
     model = d.DeepfakeDetectionModel(**MODEL_CONFIG).to(dev).eval().set_compute_dtype(torch.bfloat16)

@@ -5,7 +5,7 @@ A drop-in for `src.feature_extraction.DeepfakeDetectionModel` and
 forward signatures, same state_dict layout; all arithmetic runs in hand-written CUDA kernels
 (libdfvit.so, C ABI in include/dfvit.h).  No CPU path, no stock-PyTorch compute path.
 """
-from . import _lib, ops  # noqa: F401  (raises if libdfvit.so is missing)
+from . import _lib, ops, parallel  # noqa: F401  (raises if libdfvit.so is missing)
 from .losses import CombinedLoss
 from .model import (ChannelAttention, DeepfakeDetectionModel, DeepfakeFeatureExtractor, EfficientNetB4Backbone,
                     HybridAttention, LandmarkAttention, SpatialAttention)

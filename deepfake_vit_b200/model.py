@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
+from .parallel import allreduce_gradients
 from ._lib import check, lib
 
 BN_EPS, BN_MOM = 1e-3, 0.01   # efficientnet-pytorch global params for B4
@@ -173,23 +174,6 @@ class _TrainState:
         self.arena = None
         self.key = None
         self.in_flight = False
-
-
-def allreduce_gradients(flat: torch.Tensor, group=None):
-    """Data-parallel gradient exchange: ONE all-reduce over the flat fp32 gradient buffer,
-    averaged over ranks.  NCCL averages in the collective; gloo (CPU tests) sums then divides."""
-    import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()):
-        return flat
-    world = dist.get_world_size(group)
-    if world == 1:
-        return flat
-    if dist.get_backend(group) == "nccl":
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
-    else:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world)
-    return flat
 
 
 class _TrainFn(torch.autograd.Function):

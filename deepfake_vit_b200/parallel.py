@@ -1,0 +1,69 @@
+"""Data-parallel host logic: one process per GPU, the batch sharded over images.
+
+Inference needs no collective.  Training exchanges gradients with ONE all-reduce over the flat fp32
+gradient buffer that dfv_train_bwd fills (BatchNorm statistics stay rank-local, as DDP over the
+single-GPU reference would leave them).  Nothing here computes on tensors beyond the collective itself.
+"""
+from typing import List, Tuple
+
+import torch
+
+
+def shard_bounds(n_items: int, world: int, rank: int, multiple: int = 2) -> Tuple[int, int]:
+    """Contiguous shard [start, end) of n_items for `rank`.  Shard sizes are multiples of `multiple`
+    (CombinedLoss pairs consecutive samples (2i, 2i+1), losses.py:233-238, so a pair never straddles two
+    ranks); the remainder goes to the last rank."""
+    assert 0 <= rank < world and n_items >= 0 and multiple >= 1
+    units = n_items // multiple
+    base, extra = divmod(units, world)
+    start = (rank * base + min(rank, extra)) * multiple
+    end = start + (base + (1 if rank < extra else 0)) * multiple
+    if rank == world - 1:
+        end = n_items
+    return start, end
+
+
+def clip_shards(n_clips: int, frames_per_clip: int, world: int, rank: int) -> Tuple[int, int]:
+    """Video scoring (BASELINE.json configs[3]): whole clips per rank, so the per-clip heat-map normaliser
+    group and the per-clip mean never cross ranks.  Returns the image range [start, end)."""
+    c0, c1 = shard_bounds(n_clips, world, rank, 1)
+    return c0 * frames_per_clip, c1 * frames_per_clip
+
+
+def allreduce_gradients(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Average the flat gradient buffer over ranks in place.  NCCL averages inside the collective; gloo
+    (the CPU tests) sums, then divides."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    return flat
+
+
+def flat_layout(named_shapes: List[Tuple[str, torch.Size]]):
+    """Offsets of every parameter gradient inside the flat buffer (registration order, no padding):
+    {name: (offset, numel)}, total."""
+    offs, total = {}, 0
+    for name, shape in named_shapes:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        offs[name] = (total, n)
+        total += n
+    return offs, total
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
+    """Make every rank start from rank `src`'s parameters and buffers (what DDP does at construction)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)

@@ -1,0 +1,92 @@
+"""N > 1 host logic on CPU: world_size-2 gloo process group.  Covers the batch / clip
+sharding rules and the flat-gradient all-reduce the training backward runs (no CUDA involved)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deepfake_vit_b200 import parallel
+        # 1. flat gradient all-reduce = mean over ranks
+        torch.manual_seed(100 + rank)
+        flat = torch.randn(18_939_345 // 64)
+        mine = flat.clone()
+        parallel.allreduce_gradients(flat)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        want = torch.stack(gathered).mean(0)
+        ok_mean = bool(torch.allclose(flat, want, atol=1e-6))
+        # 2. sharding: contiguous, even, covers the batch exactly once
+        bounds = [parallel.shard_bounds(130, world, r) for r in range(world)]
+        ok_shard = bounds[0][0] == 0 and bounds[-1][1] == 130 and all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+        ok_even = all((e - s) % 2 == 0 for s, e in bounds[:-1])
+        # 3. parameters broadcast from rank 0
+        lin = torch.nn.Linear(8, 4)
+        bn = torch.nn.BatchNorm1d(4)
+        with torch.no_grad():
+            bn.running_mean.fill_(float(rank))
+        mod = torch.nn.Sequential(lin, bn)
+        parallel.broadcast_parameters(mod)
+        w = [torch.empty_like(lin.weight) for _ in range(world)]
+        dist.all_gather(w, lin.weight.data)
+        ok_bcast = all(torch.equal(w[0], t) for t in w) and float(bn.running_mean[0]) == 0.0
+        # 4. a data-parallel step of a toy loss: averaged per-rank gradients == gradient of the mean of rank losses
+        torch.manual_seed(7)
+        wgt = torch.randn(6, requires_grad=True)
+        x = torch.arange(24, dtype=torch.float32).view(4, 6) / 10.0
+        s, e = parallel.shard_bounds(4, world, rank)
+        (x[s:e] @ wgt).pow(2).mean().backward()
+        g = wgt.grad.clone()
+        parallel.allreduce_gradients(g)
+        wg2 = wgt.detach().clone().requires_grad_(True)
+        sum((x[a:b] @ wg2).pow(2).mean() for a, b in [parallel.shard_bounds(4, world, r) for r in range(world)]).div(world).backward()
+        ok_ddp = bool(torch.allclose(g, wg2.grad, atol=1e-6))
+        out[rank] = (ok_mean, ok_shard, ok_even, ok_bcast, ok_ddp)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo():
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        res = dict(out)
+    assert set(res) == {0, 1}
+    for r, flags in res.items():
+        assert all(flags), (r, flags)
+
+
+@pytest.mark.parametrize("n,world", [(256, 8), (64, 8), (130, 4), (6, 4), (2, 2), (0, 2)])
+def test_shard_bounds_cover(n, world):
+    from deepfake_vit_b200.parallel import shard_bounds
+    b = [shard_bounds(n, world, r) for r in range(world)]
+    assert b[0][0] == 0 and b[-1][1] == n
+    assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+    assert all((e - s) % 2 == 0 for s, e in b[:-1])
+
+
+def test_clip_shards_whole_clips():
+    from deepfake_vit_b200.parallel import clip_shards
+    spans = [clip_shards(64, 32, 8, r) for r in range(8)]       # BASELINE.json configs[3]: 64 clips x 32 frames on 8 GPUs
+    assert spans[0] == (0, 256) and spans[-1] == (1792, 2048)
+    assert all((e - s) % 32 == 0 for s, e in spans)
+
+
+def test_flat_layout_matches_registration_order():
+    from deepfake_vit_b200.parallel import flat_layout
+    offs, total = flat_layout([("a", torch.Size([3, 4])), ("b", torch.Size([5])), ("c", torch.Size([]))])
+    assert offs == {"a": (0, 12), "b": (12, 5), "c": (17, 1)} and total == 18
