@@ -11,6 +11,8 @@
 // vector is read once per kernel row.  fp32 accumulation.
 // Bound: HBM (read C*H*W + write C*Ho*Wo elements per image), with the 5x5 layers close to
 // the FP32-FMA limit (25 FMA per output).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dfv {
@@ -21,11 +23,17 @@ struct DwParams {
   int TH, TW;      // output tile
   int THI, TWI;    // input tile = (T-1)*S + K
   int tiles_w, tiles_h;
-  int chunks;      // channel chunks; gridDim.x is a multiple of it, so a CTA's chunk is fixed
-  long long total; // B * tiles * chunks work items
+  int chunks;      // channel chunks; gridDim.x = chunks * ctas_per_chunk, so a CTA's chunk is fixed
+  long long per_chunk;   // B * tiles_w * tiles_h tiles per channel chunk
+  int ctas_per_chunk;
+  int d_tw, d_th, d_b;   // tile-coordinate increments of a step of ctas_per_chunk tiles
   int pad;         // pad_lo (top == left)
   int act;
-  int nthreads;
+  int nthreads;    // = G * strips * rpr: thread -> (channel group, strip, row) is fixed for the whole kernel
+  int strips;      // TW / L
+  int rpr;         // tile rows per round
+  int rounds;      // ceil(TH / rpr)
+  int red_parts;   // second-stage partials of the pool reduction
 };
 
 // 8 channels of activations / weights as they sit in shared memory.
@@ -60,39 +68,49 @@ __device__ __forceinline__ void fma8(const Vec8<float>& x, const Vec8<float>& w,
   for (int e = 0; e < 8; ++e) acc[e] = fmaf(x.v[e], w.v[e], acc[e]);
 }
 
-// Persistent CTA: loops over work items (image, tile) of ONE channel chunk with a 2-deep TMA
-// pipeline: the tile for item i+1 is in flight while item i is computed.
+// Persistent CTA: loops over the tiles (image, tile row, tile column) of ONE channel chunk with a 2-deep
+// TMA pipeline: the tile for step i+1 is in flight while step i is computed.  All index arithmetic that
+// does not depend on the tile is hoisted: a thread keeps its (channel group, strip, first row) for the
+// whole kernel and tile coordinates advance by precomputed increments (no divisions in the loops).
 template <typename T, int K, int S, int L, bool kFast>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        T* __restrict__ y, float* __restrict__ pool_partial, DwParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // [tile0][tile1][weights: K*K*CB T][bias: CB f32][red: 2 x nthreads*8 f32][mbar x2]
+  // [tile0][tile1][weights: K*K*CB T][bias: CB f32][red: nthreads*8 f32][red2: 4*CB f32][mbar x2]
   const size_t tile_bytes = (size_t)p.THI * p.TWI * p.CB * sizeof(T);
   const size_t tile_stride = ((tile_bytes + 127) / 128) * 128;
   T* wsm = reinterpret_cast<T*>(smem_raw + 2 * tile_stride);
   float* bsm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wsm) + (((size_t)K * K * p.CB * sizeof(T) + 15) / 16) * 16);
   float* red = bsm + p.CB;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + (size_t)p.nthreads * 16);
+  float* red2 = red + (size_t)p.nthreads * 8;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red2 + 4 * p.CB);
 
   const int tid = threadIdx.x;
-  const int chunk = blockIdx.x % p.chunks;
+  const int chunk = blockIdx.x % p.chunks, slot = blockIdx.x / p.chunks;
   const int c0 = chunk * p.CB;
   const int n_tiles = p.tiles_w * p.tiles_h;
 
-  auto issue = [&](long long wi, int buf) {
-    const long long rest = wi / p.chunks;
-    const int tile_id = (int)(rest % n_tiles), b = (int)(rest / n_tiles);
-    const int tw_i = tile_id % p.tiles_w, th_i = tile_id / p.tiles_w;
+  // tile coordinates of this CTA's current and next tile
+  long long t = slot;
+  int tw_i = (int)(t % p.tiles_w), th_i = (int)((t / p.tiles_w) % p.tiles_h), b = (int)(t / n_tiles);
+  auto advance = [&](int& tw, int& th, int& bb) {
+    tw += p.d_tw;
+    if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
+    th += p.d_th;
+    if (th >= p.tiles_h) { th -= p.tiles_h; ++bb; }
+    bb += p.d_b;
+  };
+  auto issue = [&](int tw, int th, int bb, int buf) {
     mbar_expect_tx(&mbar[buf], (uint32_t)tile_bytes);
-    tma_load_4d(smem_raw + buf * tile_stride, &tmap, &mbar[buf], c0, tw_i * p.TW * S - p.pad, th_i * p.TH * S - p.pad, b);
+    tma_load_4d(smem_raw + buf * tile_stride, &tmap, &mbar[buf], c0, tw * p.TW * S - p.pad, th * p.TH * S - p.pad, bb);
   };
 
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     fence_mbar_init();
-    issue(blockIdx.x, 0);
+    if (t < p.per_chunk) issue(tw_i, th_i, b, 0);
   }
   // Stage this chunk's weights (BN scale already folded in) and bias while the first tile lands.
   for (int i = tid; i < K * K * p.CB; i += blockDim.x) {
@@ -103,51 +121,58 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   for (int i = tid; i < p.CB; i += blockDim.x) bsm[i] = (c0 + i < p.C) ? bias[c0 + i] : 0.f;
   __syncthreads();
 
+  // fixed per-thread role
   const int G = p.CB >> 3;
-  const int strips = p.TW / L;             // the host picks TW as a multiple of L
-  const int n_items = p.TH * strips * G;
-  const int g = tid % G;  // blockDim is a multiple of G: the channel group is fixed per thread
+  const int g = tid % G;
+  const int j = (tid / G) % p.strips;
+  const int r0 = tid / (G * p.strips);
   const int c = c0 + g * 8;
+  const bool chan_ok = c < p.C;
+  const int in_off0 = ((r0 * S) * p.TWI + j * L * S) * p.CB + g * 8;
+  const int in_step = p.rpr * S * p.TWI * p.CB;
+  const int out_off0 = (r0 * p.Wo + j * L) * p.C + g * 8;
+  const int out_step = p.rpr * p.Wo * p.C;
+  const int row_stride = p.TWI * p.CB;
+  const T* wbase = wsm + g * 8;
   float bv[8];
   load8(bsm + g * 8, bv);
   constexpr int NI = (L - 1) * S + K;  // input window per kernel row
   const int nth = blockDim.x;
-  float* red0 = red;
-  float* red1 = red + (size_t)p.nthreads * 8;
 
   int it = 0;
-  for (long long wi = blockIdx.x; wi < p.total; wi += gridDim.x, ++it) {
+  for (; t < p.per_chunk; t += p.ctas_per_chunk, ++it) {
     const int buf = it & 1;
-    if (tid == 0 && wi + gridDim.x < p.total) issue(wi + gridDim.x, buf ^ 1);   // prefetch the next tile
-    const long long rest = wi / p.chunks;
-    const int tile_id = (int)(rest % n_tiles), b = (int)(rest / n_tiles);
-    const int h0 = (tile_id / p.tiles_w) * p.TH, w0 = (tile_id % p.tiles_w) * p.TW;
+    int ntw = tw_i, nth_i = th_i, nb = b;
+    advance(ntw, nth_i, nb);
+    if (tid == 0 && t + p.ctas_per_chunk < p.per_chunk) issue(ntw, nth_i, nb, buf ^ 1);   // prefetch the next tile
+    const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
+    const int hrem = p.Ho - h0;                    // valid rows in this tile
+    const int wrem = p.Wo - (w0 + j * L);          // valid pixels from this thread's strip start
     const T* tile = reinterpret_cast<const T*>(smem_raw + buf * tile_stride);
+    T* out_tile = y + (((size_t)b * p.Ho + h0) * p.Wo + w0) * p.C + c0;
     mbar_wait(&mbar[buf], (it >> 1) & 1, 6);
 
     float psum[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) psum[e] = 0.f;
 
-    if (c < p.C) {
-      for (int item = tid; item < n_items; item += nth) {
-        const int r_ = item / G;
-        const int j = r_ % strips, r = r_ / strips;
-        const int ho = h0 + r, wo0 = w0 + j * L;
-        if (ho >= p.Ho || wo0 >= p.Wo) continue;
+    if (chan_ok && wrem > 0) {
+      int r = r0, in_off = in_off0, out_off = out_off0;
+      for (int rr = 0; rr < p.rounds; ++rr, r += p.rpr, in_off += in_step, out_off += out_step) {
+        if (r >= p.TH || r >= hrem) break;
         float acc[L][8];
 #pragma unroll
         for (int l = 0; l < L; ++l)
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[l][e] = bv[e];
 
-        const T* in = tile + ((size_t)(r * S) * p.TWI + j * L * S) * p.CB + g * 8;
+        const T* in = tile + in_off;
 #pragma unroll
         for (int kh = 0; kh < K; ++kh) {
           Vec8<T> wk[K];
 #pragma unroll
-          for (int kw = 0; kw < K; ++kw) ldvec(wsm + (kh * K + kw) * p.CB + g * 8, wk[kw]);
-          const T* row = in + (size_t)kh * p.TWI * p.CB;
+          for (int kw = 0; kw < K; ++kw) ldvec(wbase + (kh * K + kw) * p.CB, wk[kw]);
+          const T* row = in + kh * row_stride;
 #pragma unroll
           for (int iw = 0; iw < NI; ++iw) {
             Vec8<T> v;
@@ -159,11 +184,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
             }
           }
         }
-        T* out = y + (((size_t)b * p.Ho + ho) * p.Wo + wo0) * p.C + c;
-        const int nvalid = min(L, p.Wo - wo0);
+        T* out = out_tile + out_off;
+        if (wrem >= L) {
 #pragma unroll
-        for (int l = 0; l < L; ++l) {
-          if (l < nvalid) {
+          for (int l = 0; l < L; ++l) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -172,26 +196,50 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
             }
             store8(out + (size_t)l * p.C, o);
           }
+        } else {
+#pragma unroll
+          for (int l = 0; l < L; ++l) {
+            if (l < wrem) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                o[e] = p.act ? silu<kFast>(acc[l][e]) : acc[l][e];
+                psum[e] += o[e];
+              }
+              store8(out + (size_t)l * p.C, o);
+            }
+          }
         }
       }
     }
 
     if (pool_partial != nullptr) {
-      // deterministic CTA reduction: threads sharing a channel group are tid = g + G*i.  The
-      // scratch is double buffered so one barrier per tile suffices.
-      float* rbuf = buf ? red1 : red0;
+      // deterministic two-stage CTA reduction over the threads that share a channel group (tid = g + G*i)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) rbuf[tid * 8 + e] = psum[e];
+      for (int e = 0; e < 8; ++e) red[tid * 8 + e] = psum[e];
       __syncthreads();   // also: everyone is done with tile[buf] before it is refilled
-      if (tid < p.CB && c0 + tid < p.C) {
-        const int gg = tid >> 3, e = tid & 7;
+      const int R = p.red_parts;
+      for (int idx = tid; idx < p.CB * R; idx += nth) {
+        const int o = idx % p.CB, q = idx / p.CB;
+        const int gg = o >> 3, e = o & 7;
         float s = 0.f;
-        for (int t = gg; t < nth; t += G) s += rbuf[t * 8 + e];
-        pool_partial[((size_t)b * n_tiles + tile_id) * p.C + c0 + tid] = s;
+        for (int u = gg + G * q; u < nth; u += G * R) s += red[u * 8 + e];
+        red2[idx] = s;
+      }
+      __syncthreads();
+      for (int o = tid; o < p.CB; o += nth) {
+        if (c0 + o < p.C) {
+          float s = 0.f;
+          for (int q = 0; q < R; ++q) s += red2[q * p.CB + o];
+          pool_partial[((size_t)b * n_tiles + th_i * p.tiles_w + tw_i) * p.C + c0 + o] = s;
+        }
       }
     } else {
       __syncthreads();
     }
+    tw_i = ntw;
+    th_i = nth_i;
+    b = nb;
   }
 }
 
@@ -243,16 +291,18 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
   p.tiles_h = (p.Ho + TH - 1) / TH;
   p.chunks = pl->chunks = (C + p.CB - 1) / p.CB;
   const int G = p.CB / 8;
-  const int items = TH * ((TW + L - 1) / L) * G;
-  const int rounds = (items + 255) / 256;
-  int nt = (items + rounds - 1) / rounds;
-  nt = ((nt + G - 1) / G) * G;
-  if (nt > 256) nt = (256 / G) * G;
-  if (nt < G) nt = G;
+  p.strips = TW / L;
+  const int per_row = G * p.strips;               // threads per tile row (<= 64)
+  const int rpr_max = std::max(1, 256 / per_row);
+  p.rounds = (TH + rpr_max - 1) / rpr_max;
+  p.rpr = (TH + p.rounds - 1) / p.rounds;
+  const int nt = per_row * p.rpr;
   p.nthreads = nt;
+  p.red_parts = std::max(1, std::min(4, nt / p.CB));
   const size_t ts = dtype_size(dtype);
   size_t tile_bytes = (size_t)p.THI * p.TWI * p.CB * ts;
-  pl->smem = 2 * align_up(tile_bytes, 128) + align_up((size_t)K * K * p.CB * ts, 16) + (size_t)p.CB * 4 + (size_t)nt * 64 + 32;
+  pl->smem = 2 * align_up(tile_bytes, 128) + align_up((size_t)K * K * p.CB * ts, 16) + (size_t)p.CB * 4 + (size_t)nt * 32 +
+             (size_t)p.CB * 16 + 32;
   if (p.TWI > 256 || p.THI > 256 || p.CB > 256 || pl->smem > 220 * 1024) return DFV_ERR_INVALID;
   return DFV_OK;
 }
@@ -269,12 +319,16 @@ static int launch(const CUtensorMap& tm, const float* w, const float* bias, void
   }
   DFV_TRY(init_timeout_word_tu());
   const long long per_chunk = (long long)B * pl.p.tiles_w * pl.p.tiles_h;
-  pl.p.total = per_chunk * pl.chunks;
+  pl.p.per_chunk = per_chunk;
   // persistent grid: a multiple of `chunks` (fixed chunk per CTA), about two CTAs per SM
   const int occ = pl.smem <= 110 * 1024 ? 2 : 1;
   long long ctas_per_chunk = (long long)num_sms() * occ / pl.chunks;
   if (ctas_per_chunk < 1) ctas_per_chunk = 1;
   if (ctas_per_chunk > per_chunk) ctas_per_chunk = per_chunk;
+  pl.p.ctas_per_chunk = (int)ctas_per_chunk;
+  pl.p.d_tw = (int)(ctas_per_chunk % pl.p.tiles_w);
+  pl.p.d_th = (int)((ctas_per_chunk / pl.p.tiles_w) % pl.p.tiles_h);
+  pl.p.d_b = (int)(ctas_per_chunk / ((long long)pl.p.tiles_w * pl.p.tiles_h));
   const unsigned grid = (unsigned)(ctas_per_chunk * pl.chunks);
   kern<<<grid, pl.p.nthreads, pl.smem, st>>>(tm, w, bias, (T*)y, pool, pl.p);
   DFV_LAUNCH_CHECK();

@@ -7,6 +7,8 @@
 //   small helpers   weight cast / transpose, depthwise tap flip, dropout masks, column sums
 // All HBM-bound streaming kernels: 16-byte vectors of 8 channels, fixed channel group per thread,
 // fp32 accumulation, per-CTA partials finished by a tiny second kernel (deterministic).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dfv {
@@ -32,9 +34,18 @@ __device__ __forceinline__ float act_fwd(float u, int act) {
   return u;
 }
 // d act(u) / du.  swish: sigma * (1 + u * (1 - sigma))  (SwishImplementation.backward of efficientnet-pytorch)
+// kFast (bf16 tensors): sigma = 0.5 tanh(u / 2) + 0.5 with one MUFU.TANH.
+template <bool kFast = false>
 __device__ __forceinline__ float act_grad(float u, int act) {
   if (act == DFV_ACT_SILU) {
-    const float s = sigmoid_exact(u);
+    float s;
+    if constexpr (kFast) {
+      float t;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+      s = fmaf(0.5f, t, 0.5f);
+    } else {
+      s = sigmoid_exact(u);
+    }
     return s * (1.f + u * (1.f - s));
   }
   if (act == DFV_ACT_RELU) return u > 0.f ? 1.f : 0.f;
@@ -94,16 +105,27 @@ __global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw
   }
 }
 
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partial, int n_partial, int C, double count, float eps,
-                                         float momentum, float* __restrict__ mean, float* __restrict__ invstd,
-                                         float* __restrict__ running_mean, float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// 32 channels x 8 partial lanes per CTA: coalesced partial reads, 8-way split of the partial loop.
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
+                                                               double count, float eps, float momentum,
+                                                               float* __restrict__ mean, float* __restrict__ invstd,
+                                                               float* __restrict__ running_mean,
+                                                               float* __restrict__ running_var) {
+  __shared__ double sh[2][8][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < n_partial; ++i) {
-    s += (double)partial[(size_t)i * 2 * C + c];
-    q += (double)partial[(size_t)i * 2 * C + C + c];
+  if (c < C) {
+    for (int i = lane; i < n_partial; i += 8) {
+      s += (double)partial[(size_t)i * 2 * C + c];
+      q += (double)partial[(size_t)i * 2 * C + C + c];
+    }
   }
+  sh[0][lane][cl] = s;
+  sh[1][lane][cl] = q;
+  __syncthreads();
+  if (lane != 0 || c >= C) return;
+  for (int l = 1; l < 8; ++l) { s += sh[0][l][cl]; q += sh[1][l][cl]; }
   const double mu = s / count;
   double var = q / count - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -234,7 +256,7 @@ __global__ void __launch_bounds__(kNT) act_bn_bwd_kernel(const T* __restrict__ g
           float gi = fmaf(gv[e], gt[e], dp[e]) * rs;
           if (mask) gi *= mk[e];
           const float u = fmaf(x[e], sc[e], sh[e]);
-          const float d = gi * act_grad(u, act);
+          const float d = gi * act_grad<sizeof(T) == 2>(u, act);
           gv[e] = d;
           acc[e] += d;
           acc[8 + e] = fmaf(d, (x[e] - mu[e]) * is[e], acc[8 + e]);
@@ -253,15 +275,24 @@ __global__ void __launch_bounds__(kNT) act_bn_bwd_kernel(const T* __restrict__ g
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int n_partial, int C, double count,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
+                                                             double count, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, float* __restrict__ coef) {
+  __shared__ double sh[2][8][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < n_partial; ++i) {
-    s1 += (double)partial[(size_t)i * 2 * C + c];
-    s2 += (double)partial[(size_t)i * 2 * C + C + c];
+  if (c < C) {
+    for (int i = lane; i < n_partial; i += 8) {
+      s1 += (double)partial[(size_t)i * 2 * C + c];
+      s2 += (double)partial[(size_t)i * 2 * C + C + c];
+    }
   }
+  sh[0][lane][cl] = s1;
+  sh[1][lane][cl] = s2;
+  __syncthreads();
+  if (lane != 0 || c >= C) return;
+  for (int l = 1; l < 8; ++l) { s1 += sh[0][l][cl]; s2 += sh[1][l][cl]; }
   if (dbeta) dbeta[c] = (float)s1;
   if (dgamma) dgamma[c] = (float)s2;
   coef[c] = (float)(s1 / count);
@@ -272,23 +303,33 @@ template <typename T>
 __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__ du, const T* __restrict__ raw,
                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ coef,
-                                                          T* __restrict__ draw, long long M, int C) {
-  const int CV = C >> 3;
-  const long long total = M * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    const size_t off = (size_t)(i / CV) * C + cv * 8;
-    float d[8], x[8];
-    load8(du + off, d);
-    load8(raw + off, x);
+                                                          T* __restrict__ draw, long long M, int C, long long rows_per_chunk) {
+  const ColMap m(C);
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(r0 + rows_per_chunk, M);
+  if (m.row_l >= m.rpp) return;
+  for (int cb = 0; cb < m.CV; cb += m.cpp) {
+    const int cv = cb + m.col_l;
+    if (cv >= m.CV) continue;
+    float gi[8], mu[8], c1[8], k2[8];   // d raw = gi * (du - c1 - (x - mu) * k2),  k2 = invstd * coef[1]
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = cv * 8 + e;
       const float is = invstd[c];
-      const float xh = (x[e] - mean[c]) * is;
-      d[e] = (gamma ? gamma[c] : 1.f) * is * (d[e] - coef[c] - xh * coef[C + c]);
+      gi[e] = (gamma ? gamma[c] : 1.f) * is;
+      mu[e] = mean[c];
+      c1[e] = coef[c];
+      k2[e] = is * coef[C + c];
     }
-    store8(draw + off, d);
+    for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
+      const size_t off = (size_t)r * C + cv * 8;
+      float d[8], x[8];
+      load8(du + off, d);
+      load8(raw + off, x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = gi[e] * (d[e] - c1[e] - (x[e] - mu[e]) * k2[e]);
+      store8(draw + off, d);
+    }
   }
 }
 
@@ -410,41 +451,57 @@ __global__ void __launch_bounds__(512) se_bwd_image_kernel(const float* __restri
   }
 }
 
-// Weight gradients, reduced over the batch.  grid = ceil(C / 128), 128 threads: thread = channel.
+// Weight gradients, reduced over the batch.  grid = (ceil(C / 128), squeeze slices), thread = channel.
 __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __restrict__ dz, const float* __restrict__ dh1,
                                                             const float* __restrict__ pooled, const float* __restrict__ h1,
                                                             float* __restrict__ dw1, float* __restrict__ db1,
                                                             float* __restrict__ dw2, float* __restrict__ db2, int B, int C,
                                                             int sq) {
-  extern __shared__ float sm[];   // hidden [B][sq], dh1 [B][sq]
+  extern __shared__ float sm[];   // hidden [B][jn], dh1 [B][jn] of this slice
+  const int j0 = (int)((long long)sq * blockIdx.y / gridDim.y), j1 = (int)((long long)sq * (blockIdx.y + 1) / gridDim.y);
+  const int jn = j1 - j0;
   float* hid = sm;
-  float* dh = sm + (size_t)B * sq;
-  for (int i = threadIdx.x; i < B * sq; i += blockDim.x) {
-    const float v = h1[i];
+  float* dh = sm + (size_t)B * jn;
+  for (int i = threadIdx.x; i < B * jn; i += blockDim.x) {
+    const int b = i / jn, j = j0 + i % jn;
+    const float v = h1[(size_t)b * sq + j];
     hid[i] = v * sigmoid_exact(v);
-    dh[i] = dh1[i];
+    dh[i] = dh1[(size_t)b * sq + j];
   }
   __syncthreads();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    float sb = 0.f;
-    for (int b = 0; b < B; ++b) sb += dz[(size_t)b * C + c];
-    db2[c] = sb;
-    for (int j = 0; j < sq; ++j) {
-      float s2 = 0.f, s1 = 0.f;
+    if (blockIdx.y == 0) {
+      float sb = 0.f;
+      for (int b = 0; b < B; ++b) sb += dz[(size_t)b * C + c];
+      db2[c] = sb;
+    }
+    for (int jj = 0; jj < jn; jj += 4) {
+      float s2[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
       for (int b = 0; b < B; ++b) {
-        s2 = fmaf(dz[(size_t)b * C + c], hid[b * sq + j], s2);
-        s1 = fmaf(dh[b * sq + j], pooled[(size_t)b * C + c], s1);
+        const float z = dz[(size_t)b * C + c], pv = pooled[(size_t)b * C + c];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (jj + u < jn) {
+            s2[u] = fmaf(z, hid[b * jn + jj + u], s2[u]);
+            s1[u] = fmaf(dh[b * jn + jj + u], pv, s1[u]);
+          }
+        }
       }
-      dw2[(size_t)c * sq + j] = s2;
-      dw1[(size_t)j * C + c] = s1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (jj + u < jn) {
+          dw2[(size_t)c * sq + j0 + jj + u] = s2[u];
+          dw1[(size_t)(j0 + jj + u) * C + c] = s1[u];
+        }
+      }
     }
   }
   if (blockIdx.x == 0) {
-    for (int j = threadIdx.x; j < sq; j += blockDim.x) {
+    for (int j = threadIdx.x; j < jn; j += blockDim.x) {
       float s = 0.f;
-      for (int b = 0; b < B; ++b) s += dh[b * sq + j];
-      db1[j] = s;
+      for (int b = 0; b < B; ++b) s += dh[b * jn + j];
+      db1[j0 + j] = s;
     }
   }
 }
@@ -556,7 +613,7 @@ int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image
   if (dtype == DFV_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, rows_per_image, C, rpc, ws);
   else bn_stats_kernel<float><<<grid, kNT, 0, st>>>((const float*)raw, rows_per_image, C, rpc, ws);
   DFV_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, eps,
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, eps,
                                                          momentum, mean, invstd, running_mean, running_var);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
@@ -605,7 +662,7 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
     act_bn_bwd_kernel<float><<<grid, kNT, 0, st>>>((const float*)g, (const float*)raw, mean, invstd, gamma, beta, act,
                                                 (const float*)gate, dpool, inv_hw, rowscale, mask, (float*)du, ws, rows_per_image, C, rpc);
   DFV_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -616,15 +673,15 @@ int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const f
   DFV_REQUIRE(du && raw && mean && invstd && coef && draw, "dfv_bn_bwd_apply: null pointer");
   DFV_REQUIRE(valid_dtype(dtype) && M > 0 && C > 0 && C % 8 == 0, "dfv_bn_bwd_apply: bad shape (C %% 8)");
   cudaStream_t st = as_stream(stream);
-  const long long total = M * (C / 8);
-  long long blocks = (total + kNT - 1) / kNT;
-  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  long long blocks = std::min<long long>(M, 8LL * num_sms());
+  const long long rpc = (M + blocks - 1) / blocks;
+  blocks = (M + rpc - 1) / rpc;
   ProfScope prof(PK_BN, 3.0 * M * C * dtype_size(dtype), 6.0 * M * C, st);
   if (dtype == DFV_BF16)
     bn_bwd_apply_kernel<__nv_bfloat16><<<(unsigned)blocks, kNT, 0, st>>>((const __nv_bfloat16*)du, (const __nv_bfloat16*)raw, mean, invstd,
-                                                                        gamma, coef, (__nv_bfloat16*)draw, M, C);
+                                                                        gamma, coef, (__nv_bfloat16*)draw, M, C, rpc);
   else
-    bn_bwd_apply_kernel<float><<<(unsigned)blocks, kNT, 0, st>>>((const float*)du, (const float*)raw, mean, invstd, gamma, coef, (float*)draw, M, C);
+    bn_bwd_apply_kernel<float><<<(unsigned)blocks, kNT, 0, st>>>((const float*)du, (const float*)raw, mean, invstd, gamma, coef, (float*)draw, M, C, rpc);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -683,10 +740,12 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
   DFV_REQUIRE(smem <= 48 * 1024, "dfv_se_bwd: C + squeeze too large");
   se_bwd_image_kernel<<<B, 512, smem, st>>>(partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, C, squeeze);
   DFV_LAUNCH_CHECK();
-  const size_t smem2 = (size_t)2 * B * squeeze * sizeof(float);
-  DFV_REQUIRE(smem2 <= 160 * 1024, "dfv_se_bwd: batch too large for the weight-gradient kernel (B * squeeze = %d)", B * squeeze);
+  const int slices = std::max(1, std::min(squeeze / 4, (2 * num_sms() * 128 + C - 1) / C));
+  const int jn_max = (squeeze + slices - 1) / slices + 1;
+  const size_t smem2 = (size_t)2 * B * jn_max * sizeof(float);
+  DFV_REQUIRE(smem2 <= 160 * 1024, "dfv_se_bwd: batch too large for the weight-gradient kernel (B * squeeze slice = %d)", B * jn_max);
   if (smem2 > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(se_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  se_bwd_weights_kernel<<<(C + 127) / 128, 128, smem2, st>>>(dz, dh1, pooled, h1, dw_reduce, db_reduce, dw_expand, db_expand, B, C, squeeze);
+  se_bwd_weights_kernel<<<dim3((C + 127) / 128, slices), 128, smem2, st>>>(dz, dh1, pooled, h1, dw_reduce, db_reduce, dw_expand, db_expand, B, C, squeeze);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

@@ -190,10 +190,12 @@ def test_pw_gemm_tcgen05_matches_simt_large(ops):
 
 def test_pw_gemm_rejects_bad_shapes(ops):
     import deepfake_vit_b200 as d
-    a = torch.zeros(16, 12, device=DEV)
-    w = torch.zeros(8, 12, device=DEV)
+    a = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)
+    w = torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16)
     with pytest.raises(d._lib.DfvError):
-        ops.pw_gemm(a, w, torch.zeros(8, device=DEV))      # K % 8 != 0
+        ops.pw_gemm(a, w, torch.zeros(8, device=DEV))      # bf16 (TMA / tcgen05) needs K % 8 == 0
+    out = ops.pw_gemm(a.float() + 1, w.float() + 1, torch.zeros(8, device=DEV))   # the fp32 SIMT path takes any K, N
+    assert torch.allclose(out, torch.full((16, 8), 12.0, device=DEV))
 
 
 # ------------------------------------------------------------------------------- attention
