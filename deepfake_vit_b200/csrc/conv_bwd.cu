@@ -121,59 +121,149 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const T* __restrict__ g, 
 }
 
 // ------------------------------------------------------------------------------------ dw_wgrad
-// block = 8 channel groups x K kernel rows x LANES pixel lanes; every thread keeps K x 8 accumulators.
-template <typename T, int K>
-__global__ void __launch_bounds__(256) dw_wgrad_kernel(const T* __restrict__ g, const T* __restrict__ x,
-                                                      float* __restrict__ dw, int B, int H, int W, int C, int Ho, int Wo,
-                                                      int S, int pad, long long pix_per_cta) {
-  constexpr int G = 8, LANES = 256 / (G * K);
-  __shared__ float sm[LANES * K * G * K * 8];
+// dw[kh][kw][c] = sum over (b, ho, wo) of g[b,ho,wo,c] * x[b, ho*S - pad + kh, wo*S - pad + kw, c]
+// Persistent CTAs over (image, tile) for ONE channel chunk, 2-deep TMA pipeline of an x tile (with halo;
+// out-of-bounds zero fill is the static pad) and the matching g tile (zero fill beyond Ho / Wo removes
+// every bounds check).  thread = (8-channel group, kernel row kh, tile row, strip): it slides a K-wide
+// register window along its strip and keeps K x 8 fp32 accumulators for the whole kernel; one shared-memory
+// reduction and one set of atomic adds per CTA at the end.
+struct DwWgParams {
+  int C, CB, G;
+  int TH, TW, THI, TWI, SL, NS;
+  int tiles_w, tiles_h;
+  int chunks, ctas_per_chunk;
+  long long per_chunk;
+  int pad;
+  int units;     // TH * NS
+};
+
+__device__ __forceinline__ void wg_fma8(const uint4& x, const uint4& g, float acc[8]) {
+  auto pair = [](uint32_t a, uint32_t b, float& a0, float& a1) {
+    asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\t"
+        "mov.b32 {xl, xh}, %2;\n\t"
+        "mov.b32 {wl, wh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, xl, wl, %0;\n\t"
+        "fma.rn.f32.bf16 %1, xh, wh, %1;\n\t}"
+        : "+f"(a0), "+f"(a1)
+        : "r"(a), "r"(b));
+  };
+  pair(x.x, g.x, acc[0], acc[1]);
+  pair(x.y, g.y, acc[2], acc[3]);
+  pair(x.z, g.z, acc[4], acc[5]);
+  pair(x.w, g.w, acc[6], acc[7]);
+}
+struct F8 { float v[8]; };
+__device__ __forceinline__ void wg_fma8(const F8& x, const F8& g, float acc[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = fmaf(x.v[e], g.v[e], acc[e]);
+}
+__device__ __forceinline__ void wg_ld(const __nv_bfloat16* p, uint4& o) { o = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void wg_ld(const float* p, F8& o) { load8(p, o.v); }
+template <typename T> struct WgVec;
+template <> struct WgVec<__nv_bfloat16> { using type = uint4; };
+template <> struct WgVec<float> { using type = F8; };
+
+template <typename T, int K, int S>
+__global__ void __launch_bounds__(256, 2) dw_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                             const __grid_constant__ CUtensorMap tm_g,
+                                                             float* __restrict__ dw, DwWgParams p) {
+  using V = typename WgVec<T>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t x_bytes = (size_t)p.THI * p.TWI * p.CB * sizeof(T);
+  const size_t g_bytes = (size_t)p.TH * p.TW * p.CB * sizeof(T);
+  const size_t x_stride = (x_bytes + 127) / 128 * 128, g_stride = (g_bytes + 127) / 128 * 128;
+  const size_t buf_stride = x_stride + g_stride;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + 2 * buf_stride);
+
   const int tid = threadIdx.x;
-  const int gi = tid % G, kh = (tid / G) % K, lane = tid / (G * K);
-  const int c = blockIdx.x * (G * 8) + gi * 8;
-  const long long npix = (long long)B * Ho * Wo;
-  const long long p0 = (long long)blockIdx.y * pix_per_cta, p1 = min(p0 + pix_per_cta, npix);
+  const int chunk = blockIdx.x % p.chunks, slot = blockIdx.x / p.chunks;
+  const int c0 = chunk * p.CB;
+  const int n_tiles = p.tiles_w * p.tiles_h;
+
+  auto issue = [&](long long t, int buf) {
+    const int tw = (int)(t % p.tiles_w), th = (int)((t / p.tiles_w) % p.tiles_h), b = (int)(t / n_tiles);
+    unsigned char* base = smem_raw + buf * buf_stride;
+    mbar_expect_tx(&mbar[buf], (uint32_t)(x_bytes + g_bytes));
+    tma_load_4d(base, &tm_x, &mbar[buf], c0, tw * p.TW * S - p.pad, th * p.TH * S - p.pad, b);
+    tma_load_4d(base + x_stride, &tm_g, &mbar[buf], c0, tw * p.TW, th * p.TH, b);
+  };
+  long long t = slot;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+    if (t < p.per_chunk) issue(t, 0);
+  }
+  __syncthreads();
+
+  const int G = p.G;
+  const int g = tid % G, kh = (tid / G) % K, unit = tid / (G * K);
+  const bool active = unit < p.units && c0 + g * 8 < p.C;
+  const int r = unit / p.NS, j = unit % p.NS;
+  const int x_off = ((r * S + kh) * p.TWI + j * p.SL * S) * p.CB + g * 8;
+  const int g_off = (r * p.TW + j * p.SL) * p.CB + g * 8;
   float acc[K][8];
 #pragma unroll
   for (int kw = 0; kw < K; ++kw)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[kw][e] = 0.f;
-  if (lane < LANES && c < C) {
-    for (long long p = p0 + lane; p < p1; p += LANES) {
-      const int wo = (int)(p % Wo);
-      const long long r = p / Wo;
-      const int ho = (int)(r % Ho), b = (int)(r / Ho);
-      const int hi = ho * S - pad + kh;
-      if (hi < 0 || hi >= H) continue;
-      float gv[8];
-      load8(g + (size_t)p * C + c, gv);
-      const T* xr = x + (((size_t)b * H + hi) * W) * C + c;
+
+  int it = 0;
+  for (; t < p.per_chunk; t += p.ctas_per_chunk, ++it) {
+    const int buf = it & 1;
+    if (tid == 0 && t + p.ctas_per_chunk < p.per_chunk) issue(t + p.ctas_per_chunk, buf ^ 1);
+    mbar_wait(&mbar[buf], (it >> 1) & 1, 21);
+    if (active) {
+      const T* xrow = reinterpret_cast<const T*>(smem_raw + buf * buf_stride) + x_off;
+      const T* grow = reinterpret_cast<const T*>(smem_raw + buf * buf_stride + x_stride) + g_off;
+      if constexpr (S == 1) {
+        V xw[K];
 #pragma unroll
-      for (int kw = 0; kw < K; ++kw) {
-        const int wi = wo * S - pad + kw;
-        if (wi < 0 || wi >= W) continue;
-        float xv[8];
-        load8(xr + (size_t)wi * C, xv);
+        for (int u = 0; u < K - 1; ++u) wg_ld(xrow + u * p.CB, xw[u]);
+        for (int wo0 = 0; wo0 < p.SL; wo0 += K) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[kw][e] = fmaf(gv[e], xv[e], acc[kw][e]);
+          for (int u = 0; u < K; ++u) {
+            const int wo = wo0 + u;
+            V gv;
+            wg_ld(grow + wo * p.CB, gv);
+            wg_ld(xrow + (wo + K - 1) * p.CB, xw[(u + K - 1) % K]);
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) wg_fma8(xw[(u + kw) % K], gv, acc[kw]);
+          }
+        }
+      } else {
+        for (int wo = 0; wo < p.SL; ++wo) {
+          V gv;
+          wg_ld(grow + wo * p.CB, gv);
+#pragma unroll
+          for (int kw = 0; kw < K; ++kw) {
+            V xv;
+            wg_ld(xrow + (wo * S + kw) * p.CB, xv);
+            wg_fma8(xv, gv, acc[kw]);
+          }
+        }
       }
     }
+    __syncthreads();   // everyone is done with tile[buf] before it is refilled
   }
-  if (lane < LANES) {
-    float* s = sm + ((size_t)(lane * K + kh) * G + gi) * K * 8;
+
+  // CTA reduction over units (the tile buffers are free now), then one atomic per (tap, channel)
+  float* red = reinterpret_cast<float*>(smem_raw);
+  const int per_unit = K * G * K * 8;
+  if (unit < p.units) {
+    float* s = red + (size_t)unit * per_unit + ((size_t)kh * G + g) * K * 8;
 #pragma unroll
     for (int kw = 0; kw < K; ++kw)
 #pragma unroll
       for (int e = 0; e < 8; ++e) s[kw * 8 + e] = acc[kw][e];
   }
   __syncthreads();
-  // K * G * K * 8 outputs per CTA
-  for (int o = tid; o < K * G * K * 8; o += blockDim.x) {
+  for (int o = tid; o < per_unit; o += blockDim.x) {
     float s = 0.f;
-    for (int l = 0; l < LANES; ++l) s += sm[(size_t)l * K * G * K * 8 + o];
+    for (int u = 0; u < p.units; ++u) s += red[(size_t)u * per_unit + o];
     const int e = o % 8, kw = (o / 8) % K, g2 = (o / (8 * K)) % G, kh2 = o / (8 * K * G);
-    const int cc = blockIdx.x * (G * 8) + g2 * 8 + e;
-    if (cc < C) atomicAdd(dw + (size_t)(kh2 * K + kw) * C + cc, s);
+    const int cc = c0 + g2 * 8 + e;
+    if (cc < p.C) atomicAdd(dw + (size_t)(kh2 * K + kw) * p.C + cc, s);
   }
 }
 
@@ -215,6 +305,24 @@ __global__ void __launch_bounds__(192) stem_wgrad_kernel(const T* __restrict__ g
   }
 }
 
+}  // namespace dfv
+
+namespace dfv {
+template <typename T, int K, int S>
+static int launch_dw_wgrad(const CUtensorMap& tmx, const CUtensorMap& tmg, float* dw, const DwWgParams& p, size_t smem, unsigned grid,
+                           cudaStream_t st) {
+  auto kern = dw_wgrad_tma_kernel<T, K, S>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  DFV_TRY(init_timeout_word_tu());
+  kern<<<grid, 256, smem, st>>>(tmx, tmg, dw, p);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
 }  // namespace dfv
 
 using namespace dfv;
@@ -282,28 +390,80 @@ int dfv_dwconv_wgrad(const void* g, const void* x, float* dw_kkc, int dtype, int
                      int stride, int pad_lo, int pad_hi, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(g && x && dw_kkc, "dfv_dwconv_wgrad: null pointer");
-  DFV_REQUIRE(valid_dtype(dtype) && B > 0 && C > 0 && C % 8 == 0 && (kernel == 3 || kernel == 5), "dfv_dwconv_wgrad: bad shape");
+  DFV_REQUIRE(valid_dtype(dtype) && B > 0 && C > 0 && C % 8 == 0 && (kernel == 3 || kernel == 5) && (stride == 1 || stride == 2),
+              "dfv_dwconv_wgrad: bad shape");
   const int Ho = (H + pad_lo + pad_hi - kernel) / stride + 1, Wo = (W + pad_lo + pad_hi - kernel) / stride + 1;
   DFV_REQUIRE(Ho > 0 && Wo > 0, "dfv_dwconv_wgrad: bad shape");
   cudaStream_t st = as_stream(stream);
-  const int chunks = (C + 63) / 64;
-  const long long npix = (long long)B * Ho * Wo;
-  long long splits = std::max<long long>(1, 4LL * num_sms() / chunks);
-  splits = std::min<long long>(splits, std::min<long long>(npix, 65535));
-  const long long ppc = (npix + splits - 1) / splits;
-  dim3 grid((unsigned)chunks, (unsigned)((npix + ppc - 1) / ppc));
-  const double es = (double)dtype_size(dtype);
-  ProfScope prof(PK_DWCONV_BWD, es * ((double)B * H * W * C + (double)B * Ho * Wo * C), 2.0 * kernel * kernel * (double)B * Ho * Wo * C, st);
-#define DWW(T_, K_)                                                                                                       \
-  dw_wgrad_kernel<T_, K_><<<grid, 256, 0, st>>>((const T_*)g, (const T_*)x, dw_kkc, B, H, W, C, Ho, Wo, stride, pad_lo, ppc)
-  if (dtype == DFV_BF16) {
-    if (kernel == 3) DWW(__nv_bfloat16, 3); else DWW(__nv_bfloat16, 5);
+  const int K = kernel, S = stride;
+  const size_t es = dtype_size(dtype);
+  DwWgParams p;
+  p.C = C;
+  p.pad = pad_lo;
+  const int cap = dtype == DFV_BF16 ? 32 : 16;
+  p.CB = 8;
+  for (int cb = 8; cb <= cap; cb += 8)
+    if (C % cb == 0) p.CB = cb;
+  p.G = p.CB / 8;
+  const int units_max = 256 / (p.G * K);
+  if (S == 1) {
+    p.SL = K == 3 ? 12 : (Wo <= 15 ? 15 : 25);
+    p.NS = (K == 3 && Wo > 12) ? 2 : 1;
   } else {
-    if (kernel == 3) DWW(float, 3); else DWW(float, 5);
+    p.SL = 8;
+    p.NS = Wo > 8 ? 2 : 1;
+  }
+  p.TW = p.SL * p.NS;
+  p.TH = std::min(std::min(units_max / p.NS, S == 1 ? 16 : 8), Ho);
+  auto smem_of = [&](int th) {
+    const size_t xb = align_up((size_t)((th - 1) * S + K) * ((p.TW - 1) * S + K) * p.CB * es, 128);
+    const size_t gb = align_up((size_t)th * p.TW * p.CB * es, 128);
+    return 2 * (xb + gb) + 64;
+  };
+  while (p.TH > 1 && smem_of(p.TH) > 100 * 1024) --p.TH;
+  p.THI = (p.TH - 1) * S + K;
+  p.TWI = (p.TW - 1) * S + K;
+  p.units = p.TH * p.NS;
+  p.tiles_w = (Wo + p.TW - 1) / p.TW;
+  p.tiles_h = (Ho + p.TH - 1) / p.TH;
+  p.chunks = (C + p.CB - 1) / p.CB;
+  p.per_chunk = (long long)B * p.tiles_w * p.tiles_h;
+  const size_t red_bytes = (size_t)p.units * K * p.G * K * 8 * sizeof(float);
+  const size_t smem = std::max(smem_of(p.TH), red_bytes + 64);
+  DFV_REQUIRE(smem <= 200 * 1024 && p.TWI <= 256 && p.THI <= 256, "dfv_dwconv_wgrad: cannot tile H=%d W=%d C=%d k=%d s=%d", H, W, C, K, S);
+  long long cpc = (long long)num_sms() * 2 / p.chunks;
+  if (cpc < 1) cpc = 1;
+  if (cpc > p.per_chunk) cpc = p.per_chunk;
+  p.ctas_per_chunk = (int)cpc;
+  const unsigned grid = (unsigned)(cpc * p.chunks);
+
+  CUtensorMap tmx, tmg;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)C * es, (uint64_t)W * C * es, (uint64_t)H * W * C * es};
+    uint32_t box[4] = {(uint32_t)p.CB, (uint32_t)p.TWI, (uint32_t)p.THI, 1};
+    DFV_TRY(make_tensor_map(&tmx, dtype, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)C * es, (uint64_t)Wo * C * es, (uint64_t)Ho * Wo * C * es};
+    uint32_t box[4] = {(uint32_t)p.CB, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    DFV_TRY(make_tensor_map(&tmg, dtype, 4, g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+  }
+  ProfScope prof(PK_DWCONV_BWD, es * ((double)B * H * W * C + (double)B * Ho * Wo * C), 2.0 * kernel * kernel * (double)B * Ho * Wo * C, st);
+#define DWW(T_, K_, S_) return launch_dw_wgrad<T_, K_, S_>(tmx, tmg, dw_kkc, p, smem, grid, st)
+  if (dtype == DFV_BF16) {
+    if (K == 3 && S == 1) DWW(__nv_bfloat16, 3, 1);
+    if (K == 3 && S == 2) DWW(__nv_bfloat16, 3, 2);
+    if (K == 5 && S == 1) DWW(__nv_bfloat16, 5, 1);
+    DWW(__nv_bfloat16, 5, 2);
+  } else {
+    if (K == 3 && S == 1) DWW(float, 3, 1);
+    if (K == 3 && S == 2) DWW(float, 3, 2);
+    if (K == 5 && S == 1) DWW(float, 5, 1);
+    DWW(float, 5, 2);
   }
 #undef DWW
-  DFV_LAUNCH_CHECK();
-  return DFV_OK;
 }
 
 /* Stem weight gradient, accumulated into dw fp32 [48][3][3][3] (torch layout), which the caller zeroes.

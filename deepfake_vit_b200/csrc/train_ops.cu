@@ -68,29 +68,67 @@ __device__ __forceinline__ void reduce_rows(float* sm, const ColMap& m, float v[
   }
 }
 
+// ------------------------------------------------------------------------------------ streaming helpers
+// Raw 16-byte (bf16) / 32-byte (fp32) vector of 8 channels: loads are issued for several rows before any
+// of them is unpacked, so every thread keeps U independent requests in flight (these kernels are pure
+// HBM streams; with one request per thread they ran at ~35% of the copy bandwidth).
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { r = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void unpack(float v[8]) const {
+    v[0] = bf16_lo(r.x); v[1] = bf16_hi(r.x); v[2] = bf16_lo(r.y); v[3] = bf16_hi(r.y);
+    v[4] = bf16_lo(r.z); v[5] = bf16_hi(r.z); v[6] = bf16_lo(r.w); v[7] = bf16_hi(r.w);
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float v[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <typename T> struct Unroll { static constexpr int U = sizeof(T) == 2 ? 4 : 2; };
+
 // ------------------------------------------------------------------------------------ bn_stats
+// Per-CTA column sums -> double atomics into acc[2C] (zeroed by the entry point): the finalize kernel then
+// reads 2C doubles instead of hundreds of per-CTA partial rows.
 template <typename T>
 __global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw, long long rows_per_image, int C,
-                                                      long long rows_per_chunk, float* __restrict__ partial) {
+                                                      long long rows_per_chunk, double* __restrict__ acc_out) {
+  constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 16];
   const ColMap m(C);
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
   const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
   const T* base = raw + (size_t)blockIdx.y * rows_per_image * C;
-  float* pout = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
   for (int cb = 0; cb < m.CV; cb += m.cpp) {
     const int cv = cb + m.col_l;
     float acc[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     if (cv < m.CV && m.row_l < m.rpp) {
-      for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
-        float v[8];
-        load8(base + (size_t)r * C + cv * 8, v);
+      for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
+        Raw8<T> x[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc[e] += v[e];
-          acc[8 + e] = fmaf(v[e], v[e], acc[8 + e]);
+        for (int i = 0; i < U; ++i) {
+          const long long ri = r + (long long)i * m.rpp;
+          if (ri < r1) x[i].load(base + (size_t)ri * C + cv * 8); else x[i].zero();
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          float v[8];
+          x[i].unpack(v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[e] += v[e];
+            acc[8 + e] = fmaf(v[e], v[e], acc[8 + e]);
+          }
         }
       }
     }
@@ -98,36 +136,21 @@ __global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw
     if (m.row_l == 0 && cv < m.CV) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        pout[cv * 8 + e] = acc[e];
-        pout[C + cv * 8 + e] = acc[8 + e];
+        atomicAdd(acc_out + cv * 8 + e, (double)acc[e]);
+        atomicAdd(acc_out + C + cv * 8 + e, (double)acc[8 + e]);
       }
     }
   }
 }
 
-// 32 channels x 8 partial lanes per CTA: coalesced partial reads, 8-way split of the partial loop.
-__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
-                                                               double count, float eps, float momentum,
-                                                               float* __restrict__ mean, float* __restrict__ invstd,
-                                                               float* __restrict__ running_mean,
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const double* __restrict__ acc, int C, double count, float eps,
+                                                               float momentum, float* __restrict__ mean,
+                                                               float* __restrict__ invstd, float* __restrict__ running_mean,
                                                                float* __restrict__ running_var) {
-  __shared__ double sh[2][8][32];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  double s = 0.0, q = 0.0;
-  if (c < C) {
-    for (int i = lane; i < n_partial; i += 8) {
-      s += (double)partial[(size_t)i * 2 * C + c];
-      q += (double)partial[(size_t)i * 2 * C + C + c];
-    }
-  }
-  sh[0][lane][cl] = s;
-  sh[1][lane][cl] = q;
-  __syncthreads();
-  if (lane != 0 || c >= C) return;
-  for (int l = 1; l < 8; ++l) { s += sh[0][l][cl]; q += sh[1][l][cl]; }
-  const double mu = s / count;
-  double var = q / count - mu * mu;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = acc[c] / count;
+  double var = acc[C + c] / count - mu * mu;
   if (var < 0.0) var = 0.0;
   mean[c] = (float)mu;
   invstd[c] = 1.0f / sqrtf((float)var + eps);
@@ -147,6 +170,7 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
                                                     const float* __restrict__ mask, T* __restrict__ out,
                                                     float* __restrict__ pool_partial, long long rows_per_image, int C,
                                                     long long rows_per_chunk) {
+  constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 8];
   const ColMap m(C);
   const int b = blockIdx.y;
@@ -168,31 +192,47 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
         sc[e] = gamma ? gamma[c] * is : is;
         sh[e] = (beta ? beta[c] : 0.f) - (mean ? mean[c] : 0.f) * sc[e];
       }
-      for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
-        const size_t off = img + (size_t)r * C + cv * 8;
-        float v[8];
-        load8(raw + off, v);
+      for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
+        Raw8<T> x[U], rr[U];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = act_fwd<kFast>(fmaf(v[e], sc[e], sh[e]), act);
-        if (mask) {
-          float mk[8];
-          load8(mask + off, mk);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= mk[e];
+        for (int i = 0; i < U; ++i) {
+          const long long ri = r + (long long)i * m.rpp;
+          if (ri < r1) {
+            const size_t off = img + (size_t)ri * C + cv * 8;
+            x[i].load(raw + off);
+            if (residual) rr[i].load(residual + off);
+          }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) ps[e] += v[e];
-        if (rowscale) {
+        for (int i = 0; i < U; ++i) {
+          const long long ri = r + (long long)i * m.rpp;
+          if (ri < r1) {
+            const size_t off = img + (size_t)ri * C + cv * 8;
+            float v[8];
+            x[i].unpack(v);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= rs;
-        }
-        if (residual) {
-          float rr[8];
-          load8(residual + off, rr);
+            for (int e = 0; e < 8; ++e) v[e] = act_fwd<kFast>(fmaf(v[e], sc[e], sh[e]), act);
+            if (mask) {
+              float mk[8];
+              load8(mask + off, mk);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += rr[e];
+              for (int e = 0; e < 8; ++e) v[e] *= mk[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ps[e] += v[e];
+            if (rowscale) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] *= rs;
+            }
+            if (residual) {
+              float q[8];
+              rr[i].unpack(q);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] += q[e];
+            }
+            store8(out + off, v);
+          }
         }
-        store8(out + off, v);
       }
     }
     if (pool_partial) {
@@ -207,15 +247,16 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
 }
 
 // ------------------------------------------------------------------------------------ act_bn_bwd
-template <typename T>
-__global__ void __launch_bounds__(kNT) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
-                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        int act, const T* __restrict__ gate, const float* __restrict__ dpool,
-                                                        float inv_hw, const float* __restrict__ rowscale,
-                                                        const float* __restrict__ mask, T* __restrict__ du,
-                                                        float* __restrict__ partial, long long rows_per_image, int C,
-                                                        long long rows_per_chunk) {
+template <typename T, bool kGate>
+__global__ void __launch_bounds__(kNT, 2) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           int act, const T* __restrict__ gate, const float* __restrict__ dpool,
+                                                           float inv_hw, const float* __restrict__ rowscale,
+                                                           const float* __restrict__ mask, T* __restrict__ du,
+                                                           double* __restrict__ acc_out, long long rows_per_image, int C,
+                                                           long long rows_per_chunk) {
+  constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 16];
   const ColMap m(C);
   const int b = blockIdx.y;
@@ -223,76 +264,88 @@ __global__ void __launch_bounds__(kNT) act_bn_bwd_kernel(const T* __restrict__ g
   const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
   const size_t img = (size_t)b * rows_per_image * C;
   const float rs = rowscale ? rowscale[b] : 1.f;
-  float* pout = partial + ((size_t)b * gridDim.x + blockIdx.x) * 2 * C;
   for (int cb = 0; cb < m.CV; cb += m.cpp) {
     const int cv = cb + m.col_l;
     float acc[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     if (cv < m.CV && m.row_l < m.rpp) {
-      float sc[8], sh[8], mu[8], is[8], gt[8], dp[8];
+      // xhat = x * is + nm,  u = xhat * ga + be
+      float is[8], nm[8], ga[8], be[8], gt[8], dp[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = cv * 8 + e;
         is[e] = invstd ? invstd[c] : 1.f;
-        mu[e] = mean ? mean[c] : 0.f;
-        sc[e] = gamma ? gamma[c] * is[e] : is[e];
-        sh[e] = (beta ? beta[c] : 0.f) - mu[e] * sc[e];
-        dp[e] = dpool ? dpool[(size_t)b * C + c] * inv_hw : 0.f;
+        nm[e] = -(mean ? mean[c] : 0.f) * is[e];
+        ga[e] = gamma ? gamma[c] : 1.f;
+        be[e] = beta ? beta[c] : 0.f;
+        if constexpr (kGate) dp[e] = dpool ? dpool[(size_t)b * C + c] * inv_hw * rs : 0.f;
       }
-      if (gate) load8(gate + (size_t)b * C + cv * 8, gt);
-      else {
+      if constexpr (kGate) {
+        if (gate) load8(gate + (size_t)b * C + cv * 8, gt);
+        else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gt[e] = 1.f;
-      }
-      for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
-        const size_t off = img + (size_t)r * C + cv * 8;
-        float gv[8], x[8], mk[8];
-        load8(g + off, gv);
-        load8(raw + off, x);
-        if (mask) load8(mask + off, mk);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float gi = fmaf(gv[e], gt[e], dp[e]) * rs;
-          if (mask) gi *= mk[e];
-          const float u = fmaf(x[e], sc[e], sh[e]);
-          const float d = gi * act_grad<sizeof(T) == 2>(u, act);
-          gv[e] = d;
-          acc[e] += d;
-          acc[8 + e] = fmaf(d, (x[e] - mu[e]) * is[e], acc[8 + e]);
+          for (int e = 0; e < 8; ++e) gt[e] = 1.f;
         }
-        store8(du + off, gv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gt[e] *= rs;
+      }
+      for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
+        Raw8<T> gx[U], xx[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const long long ri = r + (long long)i * m.rpp;
+          if (ri < r1) {
+            const size_t off = img + (size_t)ri * C + cv * 8;
+            gx[i].load(g + off);
+            xx[i].load(raw + off);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const long long ri = r + (long long)i * m.rpp;
+          if (ri < r1) {
+            const size_t off = img + (size_t)ri * C + cv * 8;
+            float gv[8], x[8];
+            gx[i].unpack(gv);
+            xx[i].unpack(x);
+            float mk[8];
+            if (mask) load8(mask + off, mk);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float gi;
+              if constexpr (kGate) gi = fmaf(gv[e], gt[e], dp[e]);
+              else gi = gv[e] * rs;
+              if (mask) gi *= mk[e];
+              const float xh = fmaf(x[e], is[e], nm[e]);
+              const float u = fmaf(xh, ga[e], be[e]);
+              const float d = gi * act_grad<sizeof(T) == 2>(u, act);
+              gv[e] = d;
+              acc[e] += d;
+              acc[8 + e] = fmaf(d, xh, acc[8 + e]);
+            }
+            store8(du + off, gv);
+          }
+        }
       }
     }
     reduce_rows<16>(sm, m, acc);
     if (m.row_l == 0 && cv < m.CV) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        pout[cv * 8 + e] = acc[e];
-        pout[C + cv * 8 + e] = acc[8 + e];
+        atomicAdd(acc_out + cv * 8 + e, (double)acc[e]);
+        atomicAdd(acc_out + C + cv * 8 + e, (double)acc[8 + e]);
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
-                                                             double count, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, float* __restrict__ coef) {
-  __shared__ double sh[2][8][32];
-  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  double s1 = 0.0, s2 = 0.0;
-  if (c < C) {
-    for (int i = lane; i < n_partial; i += 8) {
-      s1 += (double)partial[(size_t)i * 2 * C + c];
-      s2 += (double)partial[(size_t)i * 2 * C + C + c];
-    }
-  }
-  sh[0][lane][cl] = s1;
-  sh[1][lane][cl] = s2;
-  __syncthreads();
-  if (lane != 0 || c >= C) return;
-  for (int l = 1; l < 8; ++l) { s1 += sh[0][l][cl]; s2 += sh[1][l][cl]; }
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ acc, int C, double count,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = acc[c], s2 = acc[C + c];
   if (dbeta) dbeta[c] = (float)s1;
   if (dgamma) dgamma[c] = (float)s2;
   coef[c] = (float)(s1 / count);
@@ -304,6 +357,7 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__
                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ coef,
                                                           T* __restrict__ draw, long long M, int C, long long rows_per_chunk) {
+  constexpr int U = Unroll<T>::U;
   const ColMap m(C);
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
   const long long r1 = min(r0 + rows_per_chunk, M);
@@ -311,24 +365,40 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__
   for (int cb = 0; cb < m.CV; cb += m.cpp) {
     const int cv = cb + m.col_l;
     if (cv >= m.CV) continue;
-    float gi[8], mu[8], c1[8], k2[8];   // d raw = gi * (du - c1 - (x - mu) * k2),  k2 = invstd * coef[1]
+    // d raw = gi * du - gk * x - k0:   gi = gamma * is,  gk = gi * is * coef2,  k0 = gi * (coef1 - mu * is * coef2)
+    float gi[8], gk[8], k0[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = cv * 8 + e;
       const float is = invstd[c];
       gi[e] = (gamma ? gamma[c] : 1.f) * is;
-      mu[e] = mean[c];
-      c1[e] = coef[c];
-      k2[e] = is * coef[C + c];
+      const float k2 = is * coef[C + c];
+      gk[e] = gi[e] * k2;
+      k0[e] = gi[e] * (coef[c] - mean[c] * k2);
     }
-    for (long long r = r0 + m.row_l; r < r1; r += m.rpp) {
-      const size_t off = (size_t)r * C + cv * 8;
-      float d[8], x[8];
-      load8(du + off, d);
-      load8(raw + off, x);
+    for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
+      Raw8<T> dd[U], xx[U];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) d[e] = gi[e] * (d[e] - c1[e] - (x[e] - mu[e]) * k2[e]);
-      store8(draw + off, d);
+      for (int i = 0; i < U; ++i) {
+        const long long ri = r + (long long)i * m.rpp;
+        if (ri < r1) {
+          const size_t off = (size_t)ri * C + cv * 8;
+          dd[i].load(du + off);
+          xx[i].load(raw + off);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const long long ri = r + (long long)i * m.rpp;
+        if (ri < r1) {
+          float d[8], x[8];
+          dd[i].unpack(d);
+          xx[i].unpack(x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] = fmaf(gi[e], d[e], -fmaf(gk[e], x[e], k0[e]));
+          store8(draw + (size_t)ri * C + cv * 8, d);
+        }
+      }
     }
   }
 }
@@ -596,7 +666,8 @@ int dfv_rows_chunks(int B, long long rows_per_image) {
 
 size_t dfv_bn_ws_floats(int B, long long rows_per_image, int C) {
   if (B <= 0 || rows_per_image <= 0 || C <= 0) return 0;
-  return (size_t)B * chunks_for(B, rows_per_image) * 2 * C;
+  /* >= 2C doubles (the per-channel sum / sum-of-squares accumulators) */
+  return std::max<size_t>((size_t)B * chunks_for(B, rows_per_image) * 2 * C, 4 * (size_t)C + 16);
 }
 
 int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image, int C, float eps, float momentum,
@@ -610,11 +681,13 @@ int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, (double)B * rows_per_image * C * dtype_size(dtype), 3.0 * B * rows_per_image * C, st);
-  if (dtype == DFV_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, rows_per_image, C, rpc, ws);
-  else bn_stats_kernel<float><<<grid, kNT, 0, st>>>((const float*)raw, rows_per_image, C, rpc, ws);
+  double* acc = reinterpret_cast<double*>(ws);
+  DFV_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)C, st));
+  if (dtype == DFV_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, rows_per_image, C, rpc, acc);
+  else bn_stats_kernel<float><<<grid, kNT, 0, st>>>((const float*)raw, rows_per_image, C, rpc, acc);
   DFV_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, eps,
-                                                         momentum, mean, invstd, running_mean, running_var);
+  bn_stats_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(acc, C, (double)B * (double)rows_per_image, eps, momentum, mean, invstd,
+                                                           running_mean, running_var);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -654,15 +727,20 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 12.0 * B * rows_per_image * C, st);
-  if (dtype == DFV_BF16)
-    act_bn_bwd_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)raw, mean, invstd, gamma, beta,
-                                                        act, (const __nv_bfloat16*)gate, dpool, inv_hw, rowscale, mask,
-                                                        (__nv_bfloat16*)du, ws, rows_per_image, C, rpc);
-  else
-    act_bn_bwd_kernel<float><<<grid, kNT, 0, st>>>((const float*)g, (const float*)raw, mean, invstd, gamma, beta, act,
-                                                (const float*)gate, dpool, inv_hw, rowscale, mask, (float*)du, ws, rows_per_image, C, rpc);
+  double* acc = reinterpret_cast<double*>(ws);
+  DFV_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)C, st));
+  const bool gated = gate != nullptr || dpool != nullptr;
+#define ABB(T_, G_)                                                                                                                 \
+  act_bn_bwd_kernel<T_, G_><<<grid, kNT, 0, st>>>((const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act, (const T_*)gate, dpool, \
+                                                 inv_hw, rowscale, mask, (T_*)du, acc, rows_per_image, C, rpc)
+  if (dtype == DFV_BF16) {
+    if (gated) ABB(__nv_bfloat16, true); else ABB(__nv_bfloat16, false);
+  } else {
+    if (gated) ABB(float, true); else ABB(float, false);
+  }
+#undef ABB
   DFV_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(acc, C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
