@@ -91,13 +91,14 @@ def _load():
         "dfv_blob_bytes": (sz, [i32]),
         "dfv_blob_slot": (C.c_int, [i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]),
         "dfv_stem_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
-        "dfv_dwconv_pool_parts": (C.c_int, [i32] * 8),
+        "dfv_dwconv_pool_parts": (C.c_int, [i32] * 9),
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
         "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "dfv_pw_gemm_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, vp]),
         "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
         "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 8 + [i32] * 8 + [vp]),
-        "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, i32, vp]),
+        "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, vp, i32, vp]),
+        "dfv_mlp_head_scratch_floats": (sz, [C.POINTER(C.c_int), i32, i32]),
         "dfv_combined_loss_fwd_bwd": (C.c_int, [vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, i32, i32, i32,
                                                 C.POINTER(C.c_int), vp]),
         "dfv_rows_chunks": (C.c_int, [i32, i64]),

@@ -26,7 +26,8 @@ struct DwParams {
   int chunks;      // channel chunks; gridDim.x = chunks * ctas_per_chunk, so a CTA's chunk is fixed
   long long per_chunk;   // B * tiles_w * tiles_h tiles per channel chunk
   int ctas_per_chunk;
-  int d_tw, d_th, d_b;   // tile-coordinate increments of a step of ctas_per_chunk tiles
+  long long tiles_per_cta;   // contiguous tile range per CTA
+  int parts;                 // pool-partial slots per image
   int pad;         // pad_lo (top == left)
   int act;
   int nthreads;    // = G * strips * rpr: thread -> (channel group, strip, row) is fixed for the whole kernel
@@ -68,14 +69,68 @@ __device__ __forceinline__ void fma8(const Vec8<float>& x, const Vec8<float>& w,
   for (int e = 0; e < 8; ++e) acc[e] = fmaf(x.v[e], w.v[e], acc[e]);
 }
 
-// Persistent CTA: loops over the tiles (image, tile row, tile column) of ONE channel chunk with a 2-deep
-// TMA pipeline: the tile for step i+1 is in flight while step i is computed.  All index arithmetic that
-// does not depend on the tile is hoisted: a thread keeps its (channel group, strip, first row) for the
-// whole kernel and tile coordinates advance by precomputed increments (no divisions in the loops).
-template <typename T, int K, int S, int L, bool kFast>
+// packed fp32 pair helpers (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+
+// Activation + pool sum + store of one output pixel (8 channels).  kHalf: the accumulators hold x / 2 (the 1/2
+// of swish(x) = h * tanh(h) + h, h = x / 2, is folded into the staged weights and bias).
+template <typename T, bool kAct, bool kHalf>
+__device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4], T* out) {
+  if constexpr (kAct && kHalf) {
+    uint4 pk;
+    uint32_t* pw = &pk.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 h = make_float2(acc[2 * j], acc[2 * j + 1]);
+      const float2 t = make_float2(tanh_fast(h.x), tanh_fast(h.y));
+      const float2 o = ffma2(h, t, h);
+      psum[j] = fadd2(psum[j], o);
+      pw[j] = pack_bf16(o.x, o.y);
+    }
+    if constexpr (sizeof(T) == 2) *reinterpret_cast<uint4*>(out) = pk;
+  } else {
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = kAct ? silu<false>(acc[e]) : acc[e];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      psum[j].x += o[2 * j];
+      psum[j].y += o[2 * j + 1];
+    }
+    store8(out, o);
+  }
+}
+
+// Persistent CTA: a CONTIGUOUS range of the (image, tile row, tile column) tiles of ONE channel chunk, with a
+// 2-deep TMA pipeline: the tile for step i+1 is in flight while step i is computed.  A thread keeps its
+// (channel group, strip, first row) for the whole kernel; consecutive tiles belong to the same image for long
+// runs, so the SE pool sums stay in registers across tiles and are reduced (shared memory, deterministic)
+// only when the image changes.  Image b's partial sums land in slot (cta - first cta touching b); the
+// last CTA of an image zero-fills the unused slots, so the SE-gate kernel simply sums `parts` rows.
+template <typename T, int K, int S, int L, bool kFast, bool kAct>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        T* __restrict__ y, float* __restrict__ pool_partial, DwParams p) {
+  constexpr bool kHalf = kFast && kAct && sizeof(T) == 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [tile0][tile1][weights: K*K*CB T][bias: CB f32][red: nthreads*8 f32][red2: 4*CB f32][mbar x2]
   const size_t tile_bytes = (size_t)p.THI * p.TWI * p.CB * sizeof(T);
@@ -90,17 +145,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   const int chunk = blockIdx.x % p.chunks, slot = blockIdx.x / p.chunks;
   const int c0 = chunk * p.CB;
   const int n_tiles = p.tiles_w * p.tiles_h;
+  const long long t_begin = (long long)slot * p.tiles_per_cta;
+  const long long t_end = min(t_begin + p.tiles_per_cta, p.per_chunk);
 
-  // tile coordinates of this CTA's current and next tile
-  long long t = slot;
-  int tw_i = (int)(t % p.tiles_w), th_i = (int)((t / p.tiles_w) % p.tiles_h), b = (int)(t / n_tiles);
-  auto advance = [&](int& tw, int& th, int& bb) {
-    tw += p.d_tw;
-    if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
-    th += p.d_th;
-    if (th >= p.tiles_h) { th -= p.tiles_h; ++bb; }
-    bb += p.d_b;
-  };
+  // tile coordinates of this CTA's current tile
+  int b = (int)(t_begin / n_tiles);
+  int th_i = (int)((t_begin % n_tiles) / p.tiles_w), tw_i = (int)(t_begin % p.tiles_w);
   auto issue = [&](int tw, int th, int bb, int buf) {
     mbar_expect_tx(&mbar[buf], (uint32_t)tile_bytes);
     tma_load_4d(smem_raw + buf * tile_stride, &tmap, &mbar[buf], c0, tw * p.TW * S - p.pad, th * p.TH * S - p.pad, bb);
@@ -110,15 +160,16 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     fence_mbar_init();
-    if (t < p.per_chunk) issue(tw_i, th_i, b, 0);
+    if (t_begin < t_end) issue(tw_i, th_i, b, 0);
   }
   // Stage this chunk's weights (BN scale already folded in) and bias while the first tile lands.
+  const float fold = kHalf ? 0.5f : 1.0f;
   for (int i = tid; i < K * K * p.CB; i += blockDim.x) {
     const int c = c0 + i % p.CB;
-    const float v = (c < p.C) ? w[(size_t)(i / p.CB) * p.C + c] : 0.f;
+    const float v = (c < p.C) ? fold * w[(size_t)(i / p.CB) * p.C + c] : 0.f;
     if constexpr (sizeof(T) == 2) wsm[i] = __float2bfloat16_rn(v); else wsm[i] = v;
   }
-  for (int i = tid; i < p.CB; i += blockDim.x) bsm[i] = (c0 + i < p.C) ? bias[c0 + i] : 0.f;
+  for (int i = tid; i < p.CB; i += blockDim.x) bsm[i] = (c0 + i < p.C) ? fold * bias[c0 + i] : 0.f;
   __syncthreads();
 
   // fixed per-thread role
@@ -139,22 +190,23 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   constexpr int NI = (L - 1) * S + K;  // input window per kernel row
   const int nth = blockDim.x;
 
+  float2 psum[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) psum[e] = make_float2(0.f, 0.f);
+
   int it = 0;
-  for (; t < p.per_chunk; t += p.ctas_per_chunk, ++it) {
+  for (long long t = t_begin; t < t_end; ++t, ++it) {
     const int buf = it & 1;
-    int ntw = tw_i, nth_i = th_i, nb = b;
-    advance(ntw, nth_i, nb);
-    if (tid == 0 && t + p.ctas_per_chunk < p.per_chunk) issue(ntw, nth_i, nb, buf ^ 1);   // prefetch the next tile
+    int ntw = tw_i + 1, nth_i = th_i, nb = b;
+    if (ntw == p.tiles_w) { ntw = 0; ++nth_i; }
+    if (nth_i == p.tiles_h) { nth_i = 0; ++nb; }
+    if (tid == 0 && t + 1 < t_end) issue(ntw, nth_i, nb, buf ^ 1);   // prefetch the next tile
     const int h0 = th_i * p.TH, w0 = tw_i * p.TW;
     const int hrem = p.Ho - h0;                    // valid rows in this tile
     const int wrem = p.Wo - (w0 + j * L);          // valid pixels from this thread's strip start
     const T* tile = reinterpret_cast<const T*>(smem_raw + buf * tile_stride);
     T* out_tile = y + (((size_t)b * p.Ho + h0) * p.Wo + w0) * p.C + c0;
     mbar_wait(&mbar[buf], (it >> 1) & 1, 6);
-
-    float psum[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) psum[e] = 0.f;
 
     if (chan_ok && wrem > 0) {
       int r = r0, in_off = in_off0, out_off = out_off0;
@@ -187,36 +239,24 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
         T* out = out_tile + out_off;
         if (wrem >= L) {
 #pragma unroll
-          for (int l = 0; l < L; ++l) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              o[e] = p.act ? silu<kFast>(acc[l][e]) : acc[l][e];
-              psum[e] += o[e];
-            }
-            store8(out + (size_t)l * p.C, o);
-          }
+          for (int l = 0; l < L; ++l) finish_pixel<T, kAct, kHalf>(acc[l], psum, out + (size_t)l * p.C);
         } else {
 #pragma unroll
-          for (int l = 0; l < L; ++l) {
-            if (l < wrem) {
-              float o[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                o[e] = p.act ? silu<kFast>(acc[l][e]) : acc[l][e];
-                psum[e] += o[e];
-              }
-              store8(out + (size_t)l * p.C, o);
-            }
-          }
+          for (int l = 0; l < L; ++l)
+            if (l < wrem) finish_pixel<T, kAct, kHalf>(acc[l], psum, out + (size_t)l * p.C);
         }
       }
     }
 
-    if (pool_partial != nullptr) {
+    const bool flush = pool_partial != nullptr && (nb != b || t + 1 == t_end);
+    if (flush) {
       // deterministic two-stage CTA reduction over the threads that share a channel group (tid = g + G*i)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) red[tid * 8 + e] = psum[e];
+      for (int e = 0; e < 4; ++e) {
+        red[tid * 8 + 2 * e] = psum[e].x;
+        red[tid * 8 + 2 * e + 1] = psum[e].y;
+        psum[e] = make_float2(0.f, 0.f);
+      }
       __syncthreads();   // also: everyone is done with tile[buf] before it is refilled
       const int R = p.red_parts;
       for (int idx = tid; idx < p.CB * R; idx += nth) {
@@ -227,11 +267,17 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
         red2[idx] = s;
       }
       __syncthreads();
+      const long long first_cta = ((long long)b * n_tiles) / p.tiles_per_cta;
+      const long long last_cta = ((long long)(b + 1) * n_tiles - 1) / p.tiles_per_cta;
+      const int my_slot = (int)(slot - first_cta);
       for (int o = tid; o < p.CB; o += nth) {
         if (c0 + o < p.C) {
           float s = 0.f;
           for (int q = 0; q < R; ++q) s += red2[q * p.CB + o];
-          pool_partial[((size_t)b * n_tiles + th_i * p.tiles_w + tw_i) * p.C + c0 + o] = s;
+          float* dst = pool_partial + (size_t)b * p.parts * p.C + c0 + o;
+          dst[(size_t)my_slot * p.C] = s;
+          if (slot == last_cta)
+            for (int z = my_slot + 1; z < p.parts; ++z) dst[(size_t)z * p.C] = 0.f;
         }
       }
     } else {
@@ -251,73 +297,85 @@ struct DwPlan {
   int chunks;
 };
 
-static int pick_cb(int C, int dtype) {
-  const int cap = dtype == DFV_BF16 ? 64 : 32;
-  int best = 8;
-  for (int cb = 8; cb <= cap; cb += 8)
-    if (C % cb == 0) best = cb;
-  return best;
-}
-
+// Tile plan: search (channel chunk, strip length, tile width / height) for the configuration that keeps the most
+// threads busy (<= 256 per CTA, two CTAs per SM), wastes the fewest tile cells on the image edge and re-reads the
+// smallest halo.  Every candidate is a valid launch; the score only ranks them.
 static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, int pad_lo, int pad_hi) {
   DwParams& p = pl->p;
   p.C = C;
   p.Ho = (H + pad_lo + pad_hi - K) / S + 1;
   p.Wo = (W + pad_lo + pad_hi - K) / S + 1;
   if (p.Ho <= 0 || p.Wo <= 0) return DFV_ERR_INVALID;
-  p.CB = pick_cb(C, dtype);
   p.pad = pad_lo;
-  // strip length: 8 for 3x3 (weights + 64 accumulators fit 128 registers), 4 for 5x5 and stride 2
-  int L = (S == 1) ? 8 : 4;
-  if (p.Wo <= 12 && L == 8) L = p.Wo > 8 ? 6 : 4;
-  int TW, TH;
-  if (S == 2) {
-    TW = p.Wo >= 16 ? 16 : ((p.Wo + L - 1) / L) * L;
-    TH = p.Ho >= 8 ? 8 : p.Ho;
-  } else if (p.Wo > 24) {
-    TW = p.Wo >= 32 ? 32 : 24;
-    if (p.Wo > 32 && p.Wo <= 48) TW = 24;
-    TH = 8;
-  } else {
-    TW = ((p.Wo + L - 1) / L) * L;
-    TH = p.Ho > 12 ? 8 : p.Ho;
-  }
-  pl->L = L;
-  p.TW = TW;
-  p.TH = TH;
-  p.TWI = (TW - 1) * S + K;
-  p.THI = (TH - 1) * S + K;
-  p.tiles_w = (p.Wo + TW - 1) / TW;
-  p.tiles_h = (p.Ho + TH - 1) / TH;
-  p.chunks = pl->chunks = (C + p.CB - 1) / p.CB;
-  const int G = p.CB / 8;
-  p.strips = TW / L;
-  const int per_row = G * p.strips;               // threads per tile row (<= 64)
-  const int rpr_max = std::max(1, 256 / per_row);
-  p.rounds = (TH + rpr_max - 1) / rpr_max;
-  p.rpr = (TH + p.rounds - 1) / p.rounds;
-  const int nt = per_row * p.rpr;
-  p.nthreads = nt;
-  p.red_parts = std::max(1, std::min(4, nt / p.CB));
   const size_t ts = dtype_size(dtype);
-  size_t tile_bytes = (size_t)p.THI * p.TWI * p.CB * ts;
-  pl->smem = 2 * align_up(tile_bytes, 128) + align_up((size_t)K * K * p.CB * ts, 16) + (size_t)p.CB * 4 + (size_t)nt * 32 +
-             (size_t)p.CB * 16 + 32;
-  if (p.TWI > 256 || p.THI > 256 || p.CB > 256 || pl->smem > 220 * 1024) return DFV_ERR_INVALID;
+  const int cb_cap = dtype == DFV_BF16 ? 64 : 32;
+  const int Ls1[3] = {8, 6, 4}, Ls2[1] = {4};
+  const int* Ls = S == 1 ? Ls1 : Ls2;
+  const int nL = S == 1 ? 3 : 1;
+  double best = -1.0;
+  for (int cb = 8; cb <= cb_cap; cb += 8) {
+    if (C % cb) continue;
+    const int G = cb / 8;
+    for (int li = 0; li < nL; ++li) {
+      const int L = Ls[li];
+      for (int strips = 1; strips * L <= 48; ++strips) {
+        const int TW = strips * L;
+        if (TW - L >= p.Wo) break;                 // a whole strip beyond the image: never better
+        const int per_row = G * strips;
+        if (per_row > 256) break;
+        for (int TH = 1; TH <= 16 && TH - 1 < p.Ho; ++TH) {
+          if (S == 2) {   // stride-2 layers (four of them): the hand-picked 16 x 8 tile with the widest channel chunk measured 4.5-4.9 TB/s
+            int cbw = 8;
+            for (int q = 8; q <= cb_cap; q += 8) if (C % q == 0) cbw = q;
+            const int tw2 = p.Wo >= 16 ? 16 : ((p.Wo + L - 1) / L) * L, th2 = p.Ho >= 8 ? 8 : p.Ho;
+            if (cb != cbw || TW != tw2 || TH != th2) continue;
+          }
+          const int rpr_max = std::max(1, 256 / per_row);
+          const int rounds = (TH + rpr_max - 1) / rpr_max;
+          const int rpr = (TH + rounds - 1) / rounds;
+          const int nt = per_row * rpr;
+          const int TWI = (TW - 1) * S + K, THI = (TH - 1) * S + K;
+          const size_t tile_bytes = (size_t)THI * TWI * cb * ts;
+          const size_t smem = 2 * align_up(tile_bytes, 128) + align_up((size_t)K * K * cb * ts, 16) + (size_t)cb * 4 + (size_t)nt * 32 +
+                              (size_t)cb * 16 + 32;
+          if (TWI > 256 || THI > 256 || smem > (size_t)(S == 2 ? 220 : 110) * 1024) continue;
+          const int tiles_w = (p.Wo + TW - 1) / TW, tiles_h = (p.Ho + TH - 1) / TH;
+          const double cover = (double)p.Ho * p.Wo / ((double)tiles_w * TW * tiles_h * TH);
+          const double busy = (double)TH / (rounds * rpr);              // rows actually computed per round slot
+          const double threads = std::min(1.0, nt / 256.0) * ((nt % 32 == 0) ? 1.0 : (double)nt / ((nt + 31) / 32 * 32));
+          const double halo = (double)(TH * S) * (TW * S) / ((double)THI * TWI);
+          const double regs = (K == 5 && L == 8) ? 0.9 : 1.0;          // 64 accumulators + 5 weight vectors: spills
+          const double per_tile = (double)TH * TW / (TH * TW + 24.0);  // fixed per-tile cost (barrier, TMA issue)
+          const double seg = std::min(1.0, (double)cb * ts / 128.0);   // contiguous bytes per pixel the TMA box fetches
+          const double score = cover * busy * threads * (0.6 + 0.4 * halo) * regs * per_tile * (0.3 + 0.7 * seg);
+          if (score > best) {
+            best = score;
+            p.CB = cb;
+            pl->L = L;
+            p.TW = TW;
+            p.TH = TH;
+            p.TWI = TWI;
+            p.THI = THI;
+            p.tiles_w = tiles_w;
+            p.tiles_h = tiles_h;
+            p.strips = strips;
+            p.rounds = rounds;
+            p.rpr = rpr;
+            p.nthreads = nt;
+            pl->smem = smem;
+          }
+        }
+      }
+    }
+  }
+  if (best < 0.0) return DFV_ERR_INVALID;
+  p.chunks = pl->chunks = (C + p.CB - 1) / p.CB;
+  p.red_parts = std::max(1, std::min(4, p.nthreads / p.CB));
   return DFV_OK;
 }
 
-template <typename T, int K, int S, int L, bool kFast>
-static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, DwPlan& pl, int B,
-                  cudaStream_t st) {
-  auto kern = dwconv_kernel<T, K, S, L, kFast>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured = true;
-  }
-  DFV_TRY(init_timeout_word_tu());
+// Grid plan shared by the launcher and dfv_dwconv_pool_parts (the SE-gate kernel must sum the same slot count).
+static void plan_grid(DwPlan& pl, int B) {
   const long long per_chunk = (long long)B * pl.p.tiles_w * pl.p.tiles_h;
   pl.p.per_chunk = per_chunk;
   // persistent grid: a multiple of `chunks` (fixed chunk per CTA), about two CTAs per SM
@@ -325,21 +383,40 @@ static int launch(const CUtensorMap& tm, const float* w, const float* bias, void
   long long ctas_per_chunk = (long long)num_sms() * occ / pl.chunks;
   if (ctas_per_chunk < 1) ctas_per_chunk = 1;
   if (ctas_per_chunk > per_chunk) ctas_per_chunk = per_chunk;
+  const long long tpc = (per_chunk + ctas_per_chunk - 1) / ctas_per_chunk;
+  ctas_per_chunk = (per_chunk + tpc - 1) / tpc;
   pl.p.ctas_per_chunk = (int)ctas_per_chunk;
-  pl.p.d_tw = (int)(ctas_per_chunk % pl.p.tiles_w);
-  pl.p.d_th = (int)((ctas_per_chunk / pl.p.tiles_w) % pl.p.tiles_h);
-  pl.p.d_b = (int)(ctas_per_chunk / ((long long)pl.p.tiles_w * pl.p.tiles_h));
-  const unsigned grid = (unsigned)(ctas_per_chunk * pl.chunks);
+  pl.p.tiles_per_cta = tpc;
+  const long long n = (long long)pl.p.tiles_w * pl.p.tiles_h;
+  pl.p.parts = (int)((n + tpc - 2) / tpc + 1);
+}
+
+template <typename T, int K, int S, int L, bool kFast, bool kAct>
+static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, DwPlan& pl, int B,
+                  cudaStream_t st) {
+  auto kern = dwconv_kernel<T, K, S, L, kFast, kAct>;
+  static thread_local bool configured = false;
+  if (!configured) {
+    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  DFV_TRY(init_timeout_word_tu());
+  plan_grid(pl, B);
+  const unsigned grid = (unsigned)((long long)pl.p.ctas_per_chunk * pl.chunks);
   kern<<<grid, pl.p.nthreads, pl.smem, st>>>(tm, w, bias, (T*)y, pool, pl.p);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
 
 template <typename T, bool kFast>
-static int dispatch(int K, int S, int L, const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool,
+static int dispatch(int K, int S, int L, int act, const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool,
                     DwPlan& pl, int B, cudaStream_t st) {
-#define DW_CASE(k, s, l) \
-  if (K == k && S == s && L == l) return launch<T, k, s, l, kFast>(tm, w, bias, y, pool, pl, B, st);
+#define DW_CASE(k, s, l)                                                                          \
+  if (K == k && S == s && L == l) {                                                               \
+    if (act) return launch<T, k, s, l, kFast, true>(tm, w, bias, y, pool, pl, B, st);             \
+    return launch<T, k, s, l, kFast, false>(tm, w, bias, y, pool, pl, B, st);                     \
+  }
   DW_CASE(3, 1, 8) DW_CASE(3, 1, 6) DW_CASE(3, 1, 4) DW_CASE(5, 1, 8) DW_CASE(5, 1, 6) DW_CASE(5, 1, 4)
   DW_CASE(3, 2, 4) DW_CASE(5, 2, 4)
 #undef DW_CASE
@@ -351,13 +428,28 @@ static int dispatch(int K, int S, int L, const CUtensorMap& tm, const float* w, 
 
 using namespace dfv;
 
-extern "C" int dfv_dwconv_pool_parts(int dtype, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi) {
+extern "C" int dfv_dwconv_pool_parts(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi) {
   DwPlan pl;
-  if (!valid_dtype(dtype) || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) {
+  if (!valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) {
     set_error("dfv_dwconv_pool_parts: bad shape");
     return DFV_ERR_INVALID;
   }
-  return pl.p.tiles_w * pl.p.tiles_h;
+  plan_grid(pl, B);
+  return pl.p.parts;
+}
+
+/* Debug / documentation aid (host only): the tile plan chosen for a layer.
+ * out[0..9] = CB, L, TW, TH, threads, smem bytes, tiles_w, tiles_h, parts, grid. */
+extern "C" int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out) {
+  DwPlan pl;
+  if (!out || !valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) {
+    set_error("dfv_debug_dwconv_plan: bad shape");
+    return DFV_ERR_INVALID;
+  }
+  plan_grid(pl, B);
+  out[0] = pl.p.CB; out[1] = pl.L; out[2] = pl.p.TW; out[3] = pl.p.TH; out[4] = pl.p.nthreads; out[5] = (int)pl.smem;
+  out[6] = pl.p.tiles_w; out[7] = pl.p.tiles_h; out[8] = pl.p.parts; out[9] = pl.p.ctas_per_chunk * pl.chunks;
+  return DFV_OK;
 }
 
 extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, int dtype,
@@ -384,6 +476,6 @@ extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, 
   ProfScope prof(PK_DWCONV, ((double)B * H * W * C + (double)B * pl.p.Ho * pl.p.Wo * C) * es,
                  2.0 * kernel * kernel * (double)B * pl.p.Ho * pl.p.Wo * C, as_stream(stream));
   if (dtype == DFV_BF16)
-    return dispatch<__nv_bfloat16, true>(kernel, stride, pl.L, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));
-  return dispatch<float, false>(kernel, stride, pl.L, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));
+    return dispatch<__nv_bfloat16, true>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));
+  return dispatch<float, false>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));
 }

@@ -117,6 +117,7 @@ struct TcParams {
   int BN;             // N tile (multiple of 16, <= 256)
   int n_tiles_n;
   long long n_tiles;  // total tiles
+  long long tiles_per_cta;   // contiguous tile range per CTA
   int k_blocks;
   int stages;
   int rows_per_image;
@@ -146,7 +147,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // Worker warps 2..17.  With an SE gate (project GEMMs) warps 2..9 are the operand transform
 // (two groups of four alternating k-block stages) and warps 10..17 the epilogue; without one
 // (expand / head GEMMs) all sixteen are epilogue warps.
-template <bool kHasScale>
+template <bool kHasScale, int kAct, bool kRes>
 __global__ void __launch_bounds__(kTcThreads, 1)
     pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out_tail,
@@ -163,13 +164,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t staging_bytes = (uint32_t)p.nbox * (kBM * 128);
   float* bias_sm = reinterpret_cast<float*>(staging + (size_t)p.nbuf * staging_bytes);
   const int n_pad = p.n_tiles_n * p.BN;
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(reinterpret_cast<unsigned char*>(bias_sm) + (size_t)((n_pad * 4 + 15) / 16) * 16);
+  __nv_bfloat16* gate_sm = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(bias_sm) + (size_t)((n_pad * 4 + 15) / 16) * 16);
+  const int k_pad = p.k_blocks * kBK;      // gate rows of the (at most two) images a tile touches: [2][k_pad]
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(reinterpret_cast<unsigned char*>(gate_sm) + (kHasScale ? (size_t)2 * k_pad * 2 : 0));
+  // contiguous tile range per CTA (m-major): consecutive tiles stay inside one image for rows_per_image / 128 tiles
+  const long long t_begin = (long long)blockIdx.x * p.tiles_per_cta;
+  const long long t_end = min(t_begin + p.tiles_per_cta, p.n_tiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kNumXform = kHasScale ? 8 : 0;
   constexpr int kNumEpi = kNumWorkers - kNumXform;
 
-  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) bias_sm[i] = i < p.N ? bias[i] : 0.f;
+  // swish epilogue works on h = x / 2: keep bias / 2
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) bias_sm[i] = i < p.N ? (kAct == DFV_ACT_SILU ? 0.5f * bias[i] : bias[i]) : 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      for (long long t = t_begin; t < t_end; ++t) {
         const long long mt = t / p.n_tiles_n;
         const int nt = (int)(t % p.n_tiles_n);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+      for (long long t = t_begin; t < t_end; ++t, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1, 2);
@@ -246,12 +253,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int tx = (warp - kFirstWorker) * 32 + lane;    // 0..255
     const int row = tx & 127;
     const int cbase = (tx >> 7) * 4;                      // chunks cbase .. cbase+3
+    const bool smem_gate = p.rows_per_image >= kBM;       // a tile then touches at most two images
+    const long long n_images = p.M / p.rows_per_image;
+    long long cached_img = -1;
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const long long m = (t / p.n_tiles_n) * kBM + row;
+    for (long long t = t_begin; t < t_end; ++t) {
+      const long long m0 = (t / p.n_tiles_n) * kBM;
+      const long long m = m0 + row;
       const bool valid = m < p.M;
-      const __nv_bfloat16* srow = a_scale + (size_t)(valid ? m / p.rows_per_image : 0) * p.K;
+      const long long img_lo = m0 / p.rows_per_image;
+      const long long img = valid ? m / p.rows_per_image : img_lo;
+      if (smem_gate && img_lo != cached_img) {
+        // stage the gate rows of images img_lo, img_lo + 1 (bf16 [2][k_pad]); the barrier before keeps
+        // slower transform threads of the previous tile from reading rows that are being replaced
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        for (int i = tx; i < 2 * (p.K >> 3); i += 256) {
+          const int r = i / (p.K >> 3), c = i % (p.K >> 3);
+          if (img_lo + r < n_images)
+            *reinterpret_cast<uint4*>(gate_sm + (size_t)r * k_pad + c * 8) =
+                __ldg(reinterpret_cast<const uint4*>(a_scale + (size_t)(img_lo + r) * p.K + c * 8));
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        cached_img = img_lo;
+      }
+      const __nv_bfloat16* srow = smem_gate ? gate_sm + (size_t)(img - img_lo) * k_pad : a_scale + (size_t)img * p.K;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(&bars->full[stage], phase, 4);
         if (valid) {
@@ -267,7 +293,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const int c = cbase + i;
             if (c < nchunk) {
               u[i] = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
-              gt[i] = __ldg(reinterpret_cast<const uint4*>(srow + k0 + c * 8));
+              gt[i] = *reinterpret_cast<const uint4*>(srow + k0 + c * 8);
             }
           }
 #pragma unroll
@@ -302,8 +328,44 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int c_begin = min(chunks, part * per), c_end = min(chunks, (part + 1) * per);
     const bool leader = (ew == 0 && lane == 0);
     const int row = q * 32 + lane;
+    const uint32_t row_off = (uint32_t)row * 128, r7 = (uint32_t)(row & 7);
+    const bool tail_box = p.tail_w != 64;
+    // one 8-column group: +bias, swish, +residual, bf16, swizzled 16-byte store into the staging tile
+    auto emit8 = [&](const uint32_t* v, int col, int n, unsigned char* stg, const uint4& rres, bool res_ok) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + n);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + n + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if constexpr (kAct == DFV_ACT_SILU) {
+          const float h = fmaf(__uint_as_float(v[j]), 0.5f, bb[j]);
+          float th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+          o[j] = fmaf(h, th, h);
+        } else {
+          o[j] = __uint_as_float(v[j]) + bb[j];
+        }
+      }
+      if constexpr (kRes) {
+        if (res_ok) {
+          o[0] += bf16_lo(rres.x); o[1] += bf16_hi(rres.x); o[2] += bf16_lo(rres.y); o[3] += bf16_hi(rres.y);
+          o[4] += bf16_lo(rres.z); o[5] += bf16_hi(rres.z); o[6] += bf16_lo(rres.w); o[7] += bf16_hi(rres.w);
+        }
+      }
+      const uint32_t box = (uint32_t)col >> 6, c8 = ((uint32_t)col >> 3) & 7;
+      unsigned char* dst;
+      if (tail_box && (int)box == p.nbox - 1)
+        dst = stg + (size_t)box * (kBM * 128) + (size_t)row * (p.tail_w * 2) + (col & 63) * 2;      // unswizzled tail
+      else
+        dst = stg + (size_t)box * (kBM * 128) + row_off + ((c8 ^ r7) << 4);
+      uint4 pk;
+      pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
+      pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dst) = pk;
+    };
     int it = 0;
-    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const long long m0 = (t / p.n_tiles_n) * kBM;
@@ -320,44 +382,30 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       mbar_wait(&bars->tmem_full[as], aphase, 5);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
+      const __nv_bfloat16* rrow = kRes ? residual + (size_t)m * p.N : nullptr;
       for (int cc = c_begin; cc < c_end; cc += 2) {
-        // two 16-column chunks per iteration: both TMEM loads in flight before the wait
-        uint32_t v[2][16];
+        // two 16-column chunks per iteration: both TMEM loads (and the residual loads) in flight before the wait
+        uint32_t v0[16], v1[16];
+        uint4 rr[4];
+        bool rok[4] = {false, false, false, false};
         const bool two = cc + 1 < c_end;
+        const int col0 = cc * 16, n0 = nt * p.BN + col0;
         __syncwarp();
-        tmem_ld16(tbase + (uint32_t)cc * 16, v[0]);
-        if (two) tmem_ld16(tbase + (uint32_t)(cc + 1) * 16, v[1]);
+        tmem_ld16(tbase + (uint32_t)col0, v0);
+        if (two) tmem_ld16(tbase + (uint32_t)col0 + 16, v1);
+        if constexpr (kRes) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            rok[g] = m < p.M && n0 + g * 8 < p.N && (g < 2 || two);
+            if (rok[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + g * 8));
+          }
+        }
         tmem_ld_wait();
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          if (h >= 2 && !two) break;
-          const int col = (cc + (h >> 1)) * 16 + (h & 1) * 8;     // column within the tile
-          const int n = nt * p.BN + col;
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + n);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + n + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = __uint_as_float(v[h >> 1][(h & 1) * 8 + j]) + bb[j];
-            o[j] = p.act == DFV_ACT_SILU ? silu<true>(x) : x;
-          }
-          if (residual != nullptr && m < p.M && n < p.N) {
-            float r[8];
-            load8(residual + (size_t)m * p.N + n, r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] += r[j];
-          }
-          const int box = col >> 6, cib = col & 63;            // 64-column box, column inside it
-          unsigned char* dst;
-          if (box == p.nbox - 1 && p.tail_w != 64)
-            dst = stg + (size_t)box * (kBM * 128) + (size_t)row * (p.tail_w * 2) + cib * 2;      // unswizzled tail
-          else
-            dst = stg + (size_t)box * (kBM * 128) + (size_t)row * 128 + ((((cib >> 3) ^ (row & 7))) << 4);
-          uint4 pk;
-          pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
-          pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
-          *reinterpret_cast<uint4*>(dst) = pk;
+        emit8(v0, col0, n0, stg, rr[0], rok[0]);
+        emit8(v0 + 8, col0 + 8, n0 + 8, stg, rr[1], rok[1]);
+        if (two) {
+          emit8(v1, col0 + 16, n0 + 16, stg, rr[2], rok[2]);
+          emit8(v1 + 8, col0 + 24, n0 + 24, stg, rr[3], rok[3]);
         }
       }
       tc_fence_before();
@@ -406,7 +454,7 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   p.tail_w = p.BN - (p.nbox - 1) * 64;
   const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;
   const size_t staging = (size_t)p.nbox * kBM * 128;
-  const size_t tail = align_up((size_t)p.n_tiles_n * p.BN * 4, 16) + sizeof(TcBarriers) + 64 + 1024;
+  const size_t tail = align_up((size_t)p.n_tiles_n * p.BN * 4, 16) + (a_scale ? (size_t)4 * p.k_blocks * kBK : 0) + sizeof(TcBarriers) + 64 + 1024;
   const size_t budget = 222 * 1024;
   p.nbuf = (2 * staging + 3 * stage_bytes + tail <= budget) ? 2 : 1;
   int stages = (int)((budget - tail - p.nbuf * staging) / stage_bytes);
@@ -439,23 +487,29 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
     DFV_TRY(make_tensor_map(&tm_tail, DFV_BF16, 2, out, dims, strides, tbox, CU_TENSOR_MAP_SWIZZLE_NONE));
   }
   long long grid = p.n_tiles < (long long)num_sms() ? p.n_tiles : (long long)num_sms();
+  p.tiles_per_cta = (p.n_tiles + grid - 1) / grid;
+  grid = (p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   DFV_TRY(init_timeout_word_tu());
-  static thread_local bool configured[2] = {false, false};
+#define TC_LAUNCH(S_, A_, R_)                                                                                                   \
+  do {                                                                                                                          \
+    static thread_local bool configured = false;                                                                                \
+    if (!configured) {                                                                                                          \
+      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
+      configured = true;                                                                                                        \
+    }                                                                                                                           \
+    pw_gemm_tc_kernel<S_, A_, R_><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, tm_out, tm_tail, bias,                  \
+                                                                          (const __nv_bfloat16*)a_scale,                       \
+                                                                          (const __nv_bfloat16*)residual, p);                  \
+  } while (0)
+  const bool silu_act = act == DFV_ACT_SILU;
   if (a_scale) {
-    if (!configured[1]) {
-      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured[1] = true;
-    }
-    pw_gemm_tc_kernel<true><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, tm_out, tm_tail, bias, (const __nv_bfloat16*)a_scale,
-                                                                    (const __nv_bfloat16*)residual, p);
+    if (residual) { if (silu_act) TC_LAUNCH(true, DFV_ACT_SILU, true); else TC_LAUNCH(true, DFV_ACT_NONE, true); }
+    else { if (silu_act) TC_LAUNCH(true, DFV_ACT_SILU, false); else TC_LAUNCH(true, DFV_ACT_NONE, false); }
   } else {
-    if (!configured[0]) {
-      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured[0] = true;
-    }
-    pw_gemm_tc_kernel<false><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, tm_out, tm_tail, bias, (const __nv_bfloat16*)a_scale,
-                                                                     (const __nv_bfloat16*)residual, p);
+    if (residual) { if (silu_act) TC_LAUNCH(false, DFV_ACT_SILU, true); else TC_LAUNCH(false, DFV_ACT_NONE, true); }
+    else { if (silu_act) TC_LAUNCH(false, DFV_ACT_SILU, false); else TC_LAUNCH(false, DFV_ACT_NONE, false); }
   }
+#undef TC_LAUNCH
   DFV_LAUNCH_CHECK();
   if (debug_flags() & 32) {   // bisecting aid: attribute an asynchronous fault to this launch
     cudaError_t e = cudaStreamSynchronize(st);

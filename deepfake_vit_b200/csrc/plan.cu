@@ -19,7 +19,7 @@ struct Shapes {
   int max_cmid;
 };
 
-static int compute_shapes(Shapes* s, int dtype, int H, int W) {
+static int compute_shapes(Shapes* s, int dtype, int B, int H, int W) {
   int n;
   const dfv_block_info* blk = topo_blocks(&n);
   s->Hs = (H + 1 - 3) / 2 + 1;
@@ -39,7 +39,7 @@ static int compute_shapes(Shapes* s, int dtype, int H, int W) {
     s->Wout[i] = wo;
     if (b.has_expand) s->exp_elems = std::max(s->exp_elems, (size_t)h * w * b.c_mid);
     s->dw_elems = std::max(s->dw_elems, (size_t)ho * wo * b.c_mid);
-    const int parts = dfv_dwconv_pool_parts(dtype, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi);
+    const int parts = dfv_dwconv_pool_parts(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi);
     if (parts <= 0) return DFV_ERR_INVALID;
     s->pool_floats = std::max(s->pool_floats, (size_t)parts * b.c_mid);
     s->act_elems = std::max(s->act_elems, (size_t)ho * wo * b.c_out);
@@ -62,8 +62,10 @@ struct Workspace {
   float* heat;
   float* heat_raw;
   uint32_t* heat_max;
+  float* head_scratch;     // classifier hidden activations: 2 x B x kHeadHiddenMax
   size_t bytes;
 };
+constexpr int kHeadHiddenMax = 2048;
 
 static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) {
   const size_t es = dtype_size(dtype);
@@ -82,6 +84,7 @@ static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) 
   ws->heat = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_raw = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_max = (uint32_t*)take((size_t)B * 4);
+  ws->head_scratch = (float*)take((size_t)2 * B * kHeadHiddenMax * 4);
   ws->bytes = off;
 }
 
@@ -91,7 +94,7 @@ using namespace dfv;
 
 extern "C" size_t dfv_infer_workspace_bytes(int dtype, int B, int H, int W) {
   Shapes s;
-  if (!valid_dtype(dtype) || B <= 0 || H < 32 || W < 32 || compute_shapes(&s, dtype, H, W) != DFV_OK) {
+  if (!valid_dtype(dtype) || B <= 0 || H < 32 || W < 32 || compute_shapes(&s, dtype, B, H, W) != DFV_OK) {
     set_error("dfv_infer_workspace_bytes: bad arguments");
     return 0;
   }
@@ -109,7 +112,7 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
   DFV_REQUIRE(a->head_w_t && a->head_b && a->head_dims && a->head_layers >= 1, "dfv_infer_fwd: classifier head missing");
   const int dtype = a->dtype, B = a->B;
   Shapes s;
-  DFV_REQUIRE(compute_shapes(&s, dtype, a->H, a->W) == DFV_OK, "dfv_infer_fwd: input %dx%d too small for the backbone", a->H, a->W);
+  DFV_REQUIRE(compute_shapes(&s, dtype, a->B, a->H, a->W) == DFV_OK, "dfv_infer_fwd: input %dx%d too small for the backbone", a->H, a->W);
   Workspace ws;
   carve(&ws, (char*)a->workspace, s, dtype, B);
   if (ws.bytes > a->workspace_bytes) {
@@ -142,7 +145,7 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
                               dtype, (long long)B * h * w, b.c_in, b.c_mid, DFV_ACT_SILU, stream));
       dw_in = ws.expand;
     }
-    const int parts = dfv_dwconv_pool_parts(dtype, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi);
+    const int parts = dfv_dwconv_pool_parts(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi);
     DFV_TRY(dfv_dwconv_fwd(dw_in, (const float*)W_(i, DFV_W_DW), (const float*)W_(i, DFV_W_DW_BIAS), ws.dw, ws.pool, dtype, B, h,
                            w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, DFV_ACT_SILU, stream));
     DFV_TRY(dfv_se_gate_fwd(ws.pool, parts, 1.0f / (float)(ho * wo), (const float*)W_(i, DFV_W_SE_REDUCE),
@@ -171,6 +174,8 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
   const int use_c = a->use_attention && a->use_channel, use_s = a->use_attention && a->use_spatial;
   DFV_TRY(dfv_hybrid_attention_fwd(ws.act[cur], heat, a->ca_w1, a->ca_w2_t, a->sa_w, a->features, nullptr, nullptr, dtype, B,
                                    s.Hf, s.Wf, head_c, use_c ? a->ca_hidden : 0, use_c, use_s, stream));
-  DFV_TRY(dfv_mlp_head_fwd(a->features, a->head_w_t, a->head_b, a->head_dims, a->head_layers, a->logits, B, stream));
+  for (int l = 1; l < a->head_layers; ++l)
+    DFV_REQUIRE(a->head_dims[l] <= kHeadHiddenMax, "dfv_infer_fwd: classifier hidden width %d > %d", a->head_dims[l], kHeadHiddenMax);
+  DFV_TRY(dfv_mlp_head_fwd(a->features, a->head_w_t, a->head_b, a->head_dims, a->head_layers, a->logits, ws.head_scratch, B, stream));
   return DFV_OK;
 }

@@ -1,48 +1,54 @@
 // Squeeze-excite gate: finishes the depthwise kernel's pool partial sums, then
 // C -> squeeze (bias, swish) -> C (bias, sigmoid).  One CTA per image; all fp32.
 // Negligible bytes (pool partials + the two small FC matrices, L2-resident).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace dfv {
 
-// IMG images per CTA share every weight load (the two FC matrices are the only real traffic).
+// One thread-block CLUSTER of 8 CTAs per group of IMG images.  Phase 1 splits the squeeze rows over the cluster's
+// CTAs (each weight row is read once per image group and reused for IMG images), the hidden vector is exchanged
+// through distributed shared memory, phase 2 splits the channels.  The one-CTA-per-image version spent 80-170 us
+// per late layer walking both FC matrices from L2 with a single CTA's worth of loads in flight.
+constexpr int kSeCluster = 8;
+
 template <int IMG, typename GT>
-__global__ void __launch_bounds__(512) se_gate_kernel(const float* __restrict__ partial, int parts, float inv_hw,
-                                                     const float* __restrict__ w1, const float* __restrict__ b1,
-                                                     const float* __restrict__ w2t, const float* __restrict__ b2,
-                                                     GT* __restrict__ gate, int B, int C, int sq) {
+__global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256)
+    se_gate_kernel(const float* __restrict__ partial, int parts, float inv_hw, const float* __restrict__ w1,
+                   const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+                   GT* __restrict__ gate, int B, int C, int sq) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float sm[];
-  float* pooled = sm;               // [IMG][C]
-  float* hidden = sm + IMG * C;     // [IMG][sq]
-  const int b0 = blockIdx.x * IMG, tid = threadIdx.x;
+  float* pooled = sm;                         // [IMG][C]
+  float* hidden = sm + (size_t)IMG * C;       // [IMG][sq]   (all squeeze rows, gathered)
+  float* mine = hidden + (size_t)IMG * sq;    // [IMG][jn]   (this CTA's slice)
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / kSeCluster) * IMG, tid = threadIdx.x;
+  const int jper = (sq + kSeCluster - 1) / kSeCluster;
+  const int j0 = min(sq, rank * jper), j1 = min(sq, j0 + jper);
+
   for (int i = tid; i < IMG * C; i += blockDim.x) {
     const int im = i / C, c = i % C;
     float s = 0.f;
     if (b0 + im < B) {
       const float* pb = partial + (size_t)(b0 + im) * parts * C + c;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int t = 0;
-      for (; t + 4 <= parts; t += 4) {
-        s0 += pb[(size_t)t * C];
-        s1 += pb[(size_t)(t + 1) * C];
-        s2 += pb[(size_t)(t + 2) * C];
-        s3 += pb[(size_t)(t + 3) * C];
-      }
-      for (; t < parts; ++t) s0 += pb[(size_t)t * C];
-      s = (s0 + s1) + (s2 + s3);
+      for (int t = 0; t < parts; ++t) s += pb[(size_t)t * C];
     }
     pooled[i] = s * inv_hw;
   }
   __syncthreads();
+
   const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < sq; j += nwarps) {
+  for (int j = j0 + warp; j < j1; j += nwarps) {
     const float* wr = w1 + (size_t)j * C;
     float s[IMG];
 #pragma unroll
     for (int im = 0; im < IMG; ++im) s[im] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int c = lane; c < C; c += 32) {
-      const float wv = wr[c];
+      const float wv = __ldg(wr + c);
 #pragma unroll
       for (int im = 0; im < IMG; ++im) s[im] = fmaf(wv, pooled[im * C + c], s[im]);
     }
@@ -51,19 +57,30 @@ __global__ void __launch_bounds__(512) se_gate_kernel(const float* __restrict__ 
       float v = warp_sum(s[im]);
       if (lane == 0) {
         v += b1[j];
-        hidden[im * sq + j] = v * sigmoid_exact(v);
+        mine[im * jper + (j - j0)] = v * sigmoid_exact(v);
       }
     }
   }
-  __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
+  cluster.sync();
+  // gather every CTA's slice of the hidden vector through distributed shared memory
+  for (int i = tid; i < IMG * sq; i += blockDim.x) {
+    const int im = i / sq, j = i % sq;
+    const int r = j / jper;
+    const float* remote = cluster.map_shared_rank(mine, r);
+    hidden[i] = remote[im * jper + (j - r * jper)];
+  }
+  cluster.sync();   // also keeps every CTA's shared memory alive until all peers have read it
+
+  const int cper = (C + kSeCluster - 1) / kSeCluster;
+  const int c0 = rank * cper, c1 = min(C, c0 + cper);
+  for (int c = c0 + tid; c < c1; c += blockDim.x) {
     float s[IMG];
     const float bv = b2[c];
 #pragma unroll
     for (int im = 0; im < IMG; ++im) s[im] = bv;
 #pragma unroll 8
     for (int j = 0; j < sq; ++j) {
-      const float wv = w2t[(size_t)j * C + c];
+      const float wv = __ldg(w2t + (size_t)j * C + c);
 #pragma unroll
       for (int im = 0; im < IMG; ++im) s[im] = fmaf(wv, hidden[im * sq + j], s[im]);
     }
@@ -88,18 +105,27 @@ extern "C" int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_h
   DFV_REQUIRE(pool_partial && w_reduce && b_reduce && w_expand_t && b_expand && gate, "dfv_se_gate_fwd: null pointer");
   DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && parts > 0 && valid_dtype(gate_dtype), "dfv_se_gate_fwd: bad shape / dtype");
   if (debug_flags() & 2) return DFV_OK;
-  const int img = B >= 2 * num_sms() ? 2 : 1;
-  const size_t smem = (size_t)img * (C + squeeze) * sizeof(float);
-  DFV_REQUIRE(smem <= 48 * 1024, "dfv_se_gate_fwd: C + squeeze too large (%d + %d)", C, squeeze);
+  const int img = B >= 32 ? 8 : 1;
+  const int jper = (squeeze + kSeCluster - 1) / kSeCluster;
+  const size_t smem = (size_t)img * ((size_t)C + squeeze + jper) * sizeof(float);
+  DFV_REQUIRE(smem <= 160 * 1024, "dfv_se_gate_fwd: C + squeeze too large (%d + %d)", C, squeeze);
   ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * parts * C + (double)B * C + 2.0 * C * squeeze), 4.0 * B * (double)C * squeeze,
                  as_stream(stream));
-#define SE_LAUNCH(IMG_, GT_)                                                                                     \
-  se_gate_kernel<IMG_, GT_><<<(B + IMG_ - 1) / IMG_, 512, smem, as_stream(stream)>>>(                            \
-      pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand_t, b_expand, (GT_*)gate, B, C, squeeze)
+  const unsigned grid = (unsigned)((B + img - 1) / img) * kSeCluster;
+#define SE_LAUNCH(IMG_, GT_)                                                                                          \
+  do {                                                                                                                \
+    static thread_local bool configured = false;                                                                      \
+    if (!configured) {                                                                                                \
+      DFV_CUDA(cudaFuncSetAttribute(se_gate_kernel<IMG_, GT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+      configured = true;                                                                                              \
+    }                                                                                                                 \
+    se_gate_kernel<IMG_, GT_><<<grid, 256, smem, as_stream(stream)>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, \
+                                                                     w_expand_t, b_expand, (GT_*)gate, B, C, squeeze); \
+  } while (0)
   if (gate_dtype == DFV_BF16) {
-    if (img == 2) SE_LAUNCH(2, __nv_bfloat16); else SE_LAUNCH(1, __nv_bfloat16);
+    if (img == 8) SE_LAUNCH(8, __nv_bfloat16); else SE_LAUNCH(1, __nv_bfloat16);
   } else {
-    if (img == 2) SE_LAUNCH(2, float); else SE_LAUNCH(1, float);
+    if (img == 8) SE_LAUNCH(8, float); else SE_LAUNCH(1, float);
   }
 #undef SE_LAUNCH
   DFV_LAUNCH_CHECK();

@@ -96,17 +96,17 @@ template <> struct Raw8<float> {
 template <typename T> struct Unroll { static constexpr int U = sizeof(T) == 2 ? 4 : 2; };
 
 // ------------------------------------------------------------------------------------ bn_stats
-// Per-CTA column sums -> double atomics into acc[2C] (zeroed by the entry point): the finalize kernel then
-// reads 2C doubles instead of hundreds of per-CTA partial rows.
+// Per-CTA column sums -> one partial row [2C] per CTA, finished (in double) by bn_stats_finalize_kernel.
 template <typename T>
 __global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw, long long rows_per_image, int C,
-                                                      long long rows_per_chunk, double* __restrict__ acc_out) {
+                                                      long long rows_per_chunk, float* __restrict__ partial) {
   constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 16];
   const ColMap m(C);
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
   const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
   const T* base = raw + (size_t)blockIdx.y * rows_per_image * C;
+  float* pout = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
   for (int cb = 0; cb < m.CV; cb += m.cpp) {
     const int cv = cb + m.col_l;
     float acc[16];
@@ -134,23 +134,58 @@ __global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw
     }
     reduce_rows<16>(sm, m, acc);
     if (m.row_l == 0 && cv < m.CV) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(acc_out + cv * 8 + e, (double)acc[e]);
-        atomicAdd(acc_out + C + cv * 8 + e, (double)acc[8 + e]);
-      }
+      *reinterpret_cast<float4*>(pout + cv * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(pout + cv * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      *reinterpret_cast<float4*>(pout + C + cv * 8) = make_float4(acc[8], acc[9], acc[10], acc[11]);
+      *reinterpret_cast<float4*>(pout + C + cv * 8 + 4) = make_float4(acc[12], acc[13], acc[14], acc[15]);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const double* __restrict__ acc, int C, double count, float eps,
-                                                               float momentum, float* __restrict__ mean,
-                                                               float* __restrict__ invstd, float* __restrict__ running_mean,
+// Sum of the per-CTA partial rows: 32 channels x 8 row lanes per CTA, 4 independent loads per thread in flight,
+// double accumulation.  Result in sh[0][0][cl] (sum) and sh[1][0][cl] (second moment) for lane 0 threads.
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int n_partial, int C, int c, int lane,
+                                                int cl, double (*sh)[8][32], double& s, double& q) {
+  s = 0.0;
+  q = 0.0;
+  if (c < C) {
+    int i = lane;
+    for (; i + 24 < n_partial; i += 32) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = partial[(size_t)(i + 8 * u) * 2 * C + c];
+        b[u] = partial[(size_t)(i + 8 * u) * 2 * C + C + c];
+      }
+      s += ((double)a[0] + (double)a[1]) + ((double)a[2] + (double)a[3]);
+      q += ((double)b[0] + (double)b[1]) + ((double)b[2] + (double)b[3]);
+    }
+    for (; i < n_partial; i += 8) {
+      s += (double)partial[(size_t)i * 2 * C + c];
+      q += (double)partial[(size_t)i * 2 * C + C + c];
+    }
+  }
+  sh[0][lane][cl] = s;
+  sh[1][lane][cl] = q;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < 8; ++l) { s += sh[0][l][cl]; q += sh[1][l][cl]; }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
+                                                               double count, float eps, float momentum,
+                                                               float* __restrict__ mean, float* __restrict__ invstd,
+                                                               float* __restrict__ running_mean,
                                                                float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double mu = acc[c] / count;
-  double var = acc[C + c] / count - mu * mu;
+  __shared__ double sh[2][8][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s, q;
+  reduce_partials(partial, n_partial, C, c, lane, cl, sh, s, q);
+  if (lane != 0 || c >= C) return;
+  const double mu = s / count;
+  double var = q / count - mu * mu;
   if (var < 0.0) var = 0.0;
   mean[c] = (float)mu;
   invstd[c] = 1.0f / sqrtf((float)var + eps);
@@ -254,7 +289,7 @@ __global__ void __launch_bounds__(kNT, 2) act_bn_bwd_kernel(const T* __restrict_
                                                            int act, const T* __restrict__ gate, const float* __restrict__ dpool,
                                                            float inv_hw, const float* __restrict__ rowscale,
                                                            const float* __restrict__ mask, T* __restrict__ du,
-                                                           double* __restrict__ acc_out, long long rows_per_image, int C,
+                                                           float* __restrict__ partial, long long rows_per_image, int C,
                                                            long long rows_per_chunk) {
   constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 16];
@@ -264,6 +299,7 @@ __global__ void __launch_bounds__(kNT, 2) act_bn_bwd_kernel(const T* __restrict_
   const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
   const size_t img = (size_t)b * rows_per_image * C;
   const float rs = rowscale ? rowscale[b] : 1.f;
+  float* pout = partial + ((size_t)b * gridDim.x + blockIdx.x) * 2 * C;
   for (int cb = 0; cb < m.CV; cb += m.cpp) {
     const int cv = cb + m.col_l;
     float acc[16];
@@ -331,21 +367,23 @@ __global__ void __launch_bounds__(kNT, 2) act_bn_bwd_kernel(const T* __restrict_
     }
     reduce_rows<16>(sm, m, acc);
     if (m.row_l == 0 && cv < m.CV) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(acc_out + cv * 8 + e, (double)acc[e]);
-        atomicAdd(acc_out + C + cv * 8 + e, (double)acc[8 + e]);
-      }
+      *reinterpret_cast<float4*>(pout + cv * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(pout + cv * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      *reinterpret_cast<float4*>(pout + C + cv * 8) = make_float4(acc[8], acc[9], acc[10], acc[11]);
+      *reinterpret_cast<float4*>(pout + C + cv * 8 + 4) = make_float4(acc[12], acc[13], acc[14], acc[15]);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const double* __restrict__ acc, int C, double count,
-                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double s1 = acc[c], s2 = acc[C + c];
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
+                                                             double count, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, float* __restrict__ coef) {
+  __shared__ double sh[2][8][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s1, s2;
+  reduce_partials(partial, n_partial, C, c, lane, cl, sh, s1, s2);
+  if (lane != 0 || c >= C) return;
   if (dbeta) dbeta[c] = (float)s1;
   if (dgamma) dgamma[c] = (float)s2;
   coef[c] = (float)(s1 / count);
@@ -646,10 +684,12 @@ __global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, l
   }
 }
 
+// Row chunks per image: B * chunks CTAs fill two waves of a 2-CTA/SM grid without a ragged third wave, and a CTA
+// keeps at least 32 rows (small late-layer tensors: fewer, fatter CTAs and fewer partial rows to finish).
 static inline long long chunks_for(int B, long long rows_per_image) {
-  long long chunks = (4LL * num_sms() + B - 1) / B;
+  long long chunks = (4LL * num_sms()) / B;
+  if (chunks > rows_per_image / 32) chunks = rows_per_image / 32;
   if (chunks < 1) chunks = 1;
-  if (chunks > rows_per_image) chunks = rows_per_image;
   return chunks;
 }
 
@@ -681,13 +721,11 @@ int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, (double)B * rows_per_image * C * dtype_size(dtype), 3.0 * B * rows_per_image * C, st);
-  double* acc = reinterpret_cast<double*>(ws);
-  DFV_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)C, st));
-  if (dtype == DFV_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, rows_per_image, C, rpc, acc);
-  else bn_stats_kernel<float><<<grid, kNT, 0, st>>>((const float*)raw, rows_per_image, C, rpc, acc);
+  if (dtype == DFV_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, rows_per_image, C, rpc, ws);
+  else bn_stats_kernel<float><<<grid, kNT, 0, st>>>((const float*)raw, rows_per_image, C, rpc, ws);
   DFV_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(acc, C, (double)B * (double)rows_per_image, eps, momentum, mean, invstd,
-                                                           running_mean, running_var);
+  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, eps,
+                                                         momentum, mean, invstd, running_mean, running_var);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -727,12 +765,10 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 12.0 * B * rows_per_image * C, st);
-  double* acc = reinterpret_cast<double*>(ws);
-  DFV_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)C, st));
   const bool gated = gate != nullptr || dpool != nullptr;
 #define ABB(T_, G_)                                                                                                                 \
   act_bn_bwd_kernel<T_, G_><<<grid, kNT, 0, st>>>((const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act, (const T_*)gate, dpool, \
-                                                 inv_hw, rowscale, mask, (T_*)du, acc, rows_per_image, C, rpc)
+                                                 inv_hw, rowscale, mask, (T_*)du, ws, rows_per_image, C, rpc)
   if (dtype == DFV_BF16) {
     if (gated) ABB(__nv_bfloat16, true); else ABB(__nv_bfloat16, false);
   } else {
@@ -740,7 +776,7 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
   }
 #undef ABB
   DFV_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 255) / 256, 256, 0, st>>>(acc, C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

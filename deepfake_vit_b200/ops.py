@@ -53,7 +53,7 @@ def dwconv(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, act=DFV_ACT_SILU, wan
     y = torch.empty(B, Ho, Wo, C_, device=x.device, dtype=x.dtype)
     pool = None
     if want_pool:
-        parts = lib.dfv_dwconv_pool_parts(dt, H, W, C_, kernel, stride, pad_lo, pad_hi)
+        parts = lib.dfv_dwconv_pool_parts(dt, B, H, W, C_, kernel, stride, pad_lo, pad_hi)
         if parts <= 0:
             check(parts)
         pool = torch.empty(B, parts, C_, device=x.device, dtype=torch.float32)
@@ -125,8 +125,9 @@ class HeadPack:
 def mlp_head(features, pack: HeadPack):
     B = features.shape[0]
     logits = torch.empty(B, pack.dims[pack.n], device=features.device, dtype=torch.float32)
-    check(lib.dfv_mlp_head_fwd(_f32(features), pack.wp, pack.bp, C.cast(pack.dims, C.POINTER(C.c_int)), pack.n,
-                               _f32(logits), B, _stream()))
+    dims = C.cast(pack.dims, C.POINTER(C.c_int))
+    scratch = _f32buf(lib.dfv_mlp_head_scratch_floats(dims, pack.n, B), features.device)
+    check(lib.dfv_mlp_head_fwd(_f32(features), pack.wp, pack.bp, dims, pack.n, _f32(logits), _f32(scratch), B, _stream()))
     return logits
 
 

@@ -132,8 +132,8 @@ int dfv_stem_conv_fwd(const float* x_nchw, const float* w_khwc, const float* bia
  * global-average-pool partial sums emitted by the same kernel.
  * Replaces `_swish(_bn1(_depthwise_conv(x)))` + `F.adaptive_avg_pool2d(x, 1)` of
  * MBConvBlock.forward.  pool_partial: fp32 [B][parts][C] (may be NULL), parts =
- * dfv_dwconv_pool_parts(...).  x: [B][H][W][C], y: [B][Ho][Wo][C]. */
-int dfv_dwconv_pool_parts(int dtype, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi);
+ * dfv_dwconv_pool_parts(...) (depends on B: one slot per persistent CTA that touches an image).  x: [B][H][W][C], y: [B][Ho][Wo][C]. */
+int dfv_dwconv_pool_parts(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi);
 int dfv_dwconv_fwd(const void* x, const float* w_kkc, const float* bias, void* y, float* pool_partial,
                    int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi,
                    int act, dfv_stream_t stream);
@@ -188,9 +188,12 @@ int dfv_hybrid_attention_fwd(const void* fmap, const float* heat, const float* c
  * (feature_extractor.py:223-238), eval mode: n_layers Linear layers, BatchNorm1d folded
  * into each hidden Linear, ReLU after every layer but the last; Dropout is identity.
  * dims: host int[n_layers + 1]; w_t[l]: fp32 [dims[l]][dims[l+1]] (transposed), b[l]: fp32
- * [dims[l+1]].  w_t / b are HOST arrays of n_layers DEVICE pointers.  n_layers <= 8. */
+ * [dims[l+1]].  w_t / b are HOST arrays of n_layers DEVICE pointers.  n_layers <= 8.
+ * One split-K kernel per layer; the hidden activations ping-pong through `scratch` (fp32 device buffer of
+ * dfv_mlp_head_scratch_floats(...) floats; may be NULL when n_layers == 1). */
+size_t dfv_mlp_head_scratch_floats(const int* dims, int n_layers, int B);
 int dfv_mlp_head_fwd(const float* features, const float* const* w_t, const float* const* b, const int* dims,
-                     int n_layers, float* logits, int B, dfv_stream_t stream);
+                     int n_layers, float* logits, float* scratch, int B, dfv_stream_t stream);
 
 /* CombinedLoss.forward (src/training/losses.py:192-247) and its gradient in one pass:
  * weighted-mean CE + focal(gamma=2, alpha=class weights) + contrastive (consecutive pairs,

@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python scripts/profile_train.py 64 2 > gpurun_out/plain_train.log 2>&1 || { echo plain failed; tail -5 gpurun_out/plain_train.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/train_launches.csv python scripts/profile_train.py 64 2 > gpurun_out/ncu_train.log 2>&1
+echo "ncu exit=$?"
+python - <<'PY'
+import csv, collections
+rows=[r for r in csv.reader(open('gpurun_out/train_launches.csv')) if len(r)>10 and r[0].isdigit()]
+half=len(rows)//2
+agg=collections.defaultdict(lambda:[0,0.0])
+for r in rows[half:]:
+    name=r[4].split('(')[0].replace('void ','').replace('dfv::','')
+    agg[name][0]+=1; agg[name][1]+=float(r[-1])/1e6
+tot=sum(v[1] for v in agg.values())
+print('second step: total %.2f ms over %d launches'%(tot, sum(v[0] for v in agg.values())))
+for k,v in sorted(agg.items(), key=lambda kv:-kv[1][1])[:24]: print('%8.3f ms %5d  %s'%(v[1],v[0],k[:110]))
+PY
+# full capture: the block-3..5 BN kernels of the backward pass (second step)
+ncu --set full --import-source on --clock-control none -k 'regex:^(act_bn_bwd_kernel|bn_bwd_apply_kernel|bn_act_kernel|bn_stats_kernel|dw_wgrad_tma_kernel)' -s 560 -c 12 -o gpurun_out/full_bn -f python scripts/profile_train.py 64 2 > gpurun_out/ncu_full_bn.log 2>&1
+echo "full exit=$?"
