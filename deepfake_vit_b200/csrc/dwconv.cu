@@ -314,8 +314,13 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
   const int nL = S == 1 ? 3 : 1;
   double best = -1.0;
   for (int cb = 8; cb <= cb_cap; cb += 8) {
-    if (C % cb) continue;
+    // a chunk width that does not divide C is allowed for the full-width chunk only (TMA zero-fills the missing
+    // channels of the last chunk; its threads are masked): 8 channel groups = one 128-byte shared-memory row per
+    // pixel, the only width whose quarter-warp vector loads never collide on a bank
+    if (C % cb && !(cb == cb_cap && C > cb)) continue;
     const int G = cb / 8;
+    const double waste = (double)C / ((double)((C + cb - 1) / cb) * cb);
+    const double banks = (cb * ts == 128) ? 1.0 : (cb * ts > 64 ? 0.8 : 0.65);
     for (int li = 0; li < nL; ++li) {
       const int L = Ls[li];
       for (int strips = 1; strips * L <= 48; ++strips) {
@@ -347,7 +352,7 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
           const double regs = (K == 5 && L == 8) ? 0.9 : 1.0;          // 64 accumulators + 5 weight vectors: spills
           const double per_tile = (double)TH * TW / (TH * TW + 24.0);  // fixed per-tile cost (barrier, TMA issue)
           const double seg = std::min(1.0, (double)cb * ts / 128.0);   // contiguous bytes per pixel the TMA box fetches
-          const double score = cover * busy * threads * (0.6 + 0.4 * halo) * regs * per_tile * (0.3 + 0.7 * seg);
+          const double score = cover * busy * threads * (0.6 + 0.4 * halo) * regs * per_tile * (0.3 + 0.7 * seg) * waste * banks;
           if (score > best) {
             best = score;
             p.CB = cb;

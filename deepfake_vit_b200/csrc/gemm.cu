@@ -111,9 +111,10 @@ constexpr uint32_t kTmemCols = 512;
 struct TcParams {
   long long M;
   int K, N;
-  int nbox;           // 64-column output boxes per tile (last one may be narrower: tail_w)
-  int tail_w;         // width of the last box (== 64 when BN % 64 == 0)
-  int nbuf;           // output staging buffers (1 or 2)
+  int cw;             // output columns per epilogue warp (= BN / column parts), = nb * bw
+  int nb, bw;         // TMA-store boxes per warp and their width (16 / 32 / 48 / 64 columns)
+  int swz;            // XOR mask source of the staging swizzle: 3 = 128B, 2 = 64B, 1 = 32B, 0 = none
+  int nbuf;           // output staging buffers per warp (1 or 2)
   int BN;             // N tile (multiple of 16, <= 256)
   int n_tiles_n;
   long long n_tiles;  // total tiles
@@ -160,9 +161,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   unsigned char* tiles = smem;
-  unsigned char* staging = smem + (size_t)p.stages * stage_bytes;            // [nbuf][nbox][128 x 128 B]
-  const uint32_t staging_bytes = (uint32_t)p.nbox * (kBM * 128);
-  float* bias_sm = reinterpret_cast<float*>(staging + (size_t)p.nbuf * staging_bytes);
+  constexpr int kNumEpiW = kNumWorkers - (kHasScale ? 8 : 0);
+  unsigned char* staging = smem + (size_t)p.stages * stage_bytes;            // [epilogue warp][nbuf][nb][32 rows x bw]
+  const uint32_t warp_stage_bytes = (uint32_t)p.cw * 64;                     // 32 rows x cw columns x 2 B
+  float* bias_sm = reinterpret_cast<float*>(staging + (size_t)kNumEpiW * p.nbuf * warp_stage_bytes);
   const int n_pad = p.n_tiles_n * p.BN;
   __nv_bfloat16* gate_sm = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(bias_sm) + (size_t)((n_pad * 4 + 15) / 16) * 16);
   const int k_pad = p.k_blocks * kBK;      // gate rows of the (at most two) images a tile touches: [2][k_pad]
@@ -318,20 +320,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ------------------------------------------------------------- epilogue
     // TMEM -> registers -> (+bias, swish, +residual, bf16) -> swizzled staging tile in shared memory
     // -> TMA store (clips the M / N tails; full-line writes instead of 32 strided 16-byte stores).
+    // Every epilogue warp is autonomous: it owns 32 rows (its TMEM lane quarter) x cw columns of the tile, stages
+    // them in its own shared-memory slice and issues its own TMA stores -- no CTA-wide barrier per tile (the
+    // all-warps barrier + single-leader store version spent half its samples waiting at the barrier on the
+    // large-M / small-N layers).
     const int ew = warp - kFirstWorker - kNumXform;  // 0 .. kNumEpi-1
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    constexpr int kParts = kNumEpi / 4;              // column parts (2 or 4)
-    constexpr int kEpiThreads = kNumEpi * 32;
-    const int part = ew >> 2;
-    const int chunks = p.BN >> 4;
-    const int per = (chunks + kParts - 1) / kParts;
-    const int c_begin = min(chunks, part * per), c_end = min(chunks, (part + 1) * per);
-    const bool leader = (ew == 0 && lane == 0);
-    const int row = q * 32 + lane;
-    const uint32_t row_off = (uint32_t)row * 128, r7 = (uint32_t)(row & 7);
-    const bool tail_box = p.tail_w != 64;
-    // one 8-column group: +bias, swish, +residual, bf16, swizzled 16-byte store into the staging tile
-    auto emit8 = [&](const uint32_t* v, int col, int n, unsigned char* stg, const uint4& rres, bool res_ok) {
+    const int part = ew >> 2;                        // column part
+    const int col_lo = part * p.cw;                  // first tile column of this warp
+    const int nchunk = p.cw >> 4;                    // 16-column chunks per warp (<= 8)
+    const uint32_t pitch = (uint32_t)p.bw * 2;
+    const uint32_t row_off = (uint32_t)lane * pitch;
+    const uint32_t xr = p.swz == 3 ? (uint32_t)(lane & 7) : (p.swz == 2 ? (uint32_t)((lane >> 1) & 3) : (p.swz == 1 ? (uint32_t)((lane >> 2) & 1) : 0u));
+    const uint32_t box_bytes = 32u * pitch;
+    unsigned char* my_stage = staging + (size_t)ew * p.nbuf * warp_stage_bytes;
+    // one 8-column group: +bias, swish, +residual, bf16, swizzled 16-byte store into the warp's staging slice
+    auto emit8 = [&](const uint32_t* v, int wcol, int n, unsigned char* stg, const uint4& rres, bool res_ok) {
       const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + n);
       const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + n + 4);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -353,12 +357,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           o[4] += bf16_lo(rres.z); o[5] += bf16_hi(rres.z); o[6] += bf16_lo(rres.w); o[7] += bf16_hi(rres.w);
         }
       }
-      const uint32_t box = (uint32_t)col >> 6, c8 = ((uint32_t)col >> 3) & 7;
-      unsigned char* dst;
-      if (tail_box && (int)box == p.nbox - 1)
-        dst = stg + (size_t)box * (kBM * 128) + (size_t)row * (p.tail_w * 2) + (col & 63) * 2;      // unswizzled tail
-      else
-        dst = stg + (size_t)box * (kBM * 128) + row_off + ((c8 ^ r7) << 4);
+      const uint32_t box = (uint32_t)wcol / (uint32_t)p.bw, c8 = ((uint32_t)wcol % (uint32_t)p.bw) >> 3;
+      unsigned char* dst = stg + box * box_bytes + row_off + ((c8 ^ xr) << 4);
       uint4 pk;
       pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
       pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
@@ -368,44 +368,63 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const long long m0 = (t / p.n_tiles_n) * kBM;
-      const long long m = m0 + row;
+      const long long m0 = (t / p.n_tiles_n) * kBM + q * 32;   // first row of this warp
+      const long long m = m0 + lane;
       const int nt = (int)(t % p.n_tiles_n);
-      unsigned char* stg = staging + (size_t)(p.nbuf == 2 ? (it & 1) : 0) * staging_bytes;
-      // the staging buffer we are about to overwrite must have been fully read by its TMA store
-      if (leader) {
+      const int n_lo = nt * p.BN + col_lo;                     // first output column of this warp
+      const bool active = col_lo < p.BN && n_lo < p.N && m0 < p.M;
+      unsigned char* stg = my_stage + (size_t)(p.nbuf == 2 ? (it & 1) : 0) * warp_stage_bytes;
+      const __nv_bfloat16* rrow = kRes ? residual + (size_t)m * p.N : nullptr;
+      // residual of the first two chunks: requested before anything else so its latency hides behind the waits
+      uint4 rr[4];
+      bool rok[4] = {false, false, false, false};
+      if constexpr (kRes) {
+        if (active) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            rok[g] = m < p.M && n_lo + g * 8 < p.N && g * 8 < p.cw;
+            if (rok[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(rrow + n_lo + g * 8));
+          }
+        }
+      }
+      // the staging slice we are about to overwrite must have been read by this warp's earlier TMA stores
+      if (lane == 0) {
         if (p.nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
-      __syncwarp();   // the leader lane may have diverged in the wait above; named barriers are warp-aligned
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      __syncwarp();
       mbar_wait(&bars->tmem_full[as], aphase, 5);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
-      const __nv_bfloat16* rrow = kRes ? residual + (size_t)m * p.N : nullptr;
-      for (int cc = c_begin; cc < c_end; cc += 2) {
-        // two 16-column chunks per iteration: both TMEM loads (and the residual loads) in flight before the wait
-        uint32_t v0[16], v1[16];
-        uint4 rr[4];
-        bool rok[4] = {false, false, false, false};
-        const bool two = cc + 1 < c_end;
-        const int col0 = cc * 16, n0 = nt * p.BN + col0;
-        __syncwarp();
-        tmem_ld16(tbase + (uint32_t)col0, v0);
-        if (two) tmem_ld16(tbase + (uint32_t)col0 + 16, v1);
-        if constexpr (kRes) {
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256 + (uint32_t)col_lo;
+      if (active) {
+        for (int cc = 0; cc < nchunk; cc += 2) {
+          const int wcol = cc * 16, n0 = n_lo + wcol;
+          if (n0 >= p.N) break;
+          uint32_t v0[16], v1[16];
+          const bool two = cc + 1 < nchunk && n0 + 16 < p.N;
+          __syncwarp();
+          tmem_ld16(tbase + (uint32_t)wcol, v0);
+          if (two) tmem_ld16(tbase + (uint32_t)wcol + 16, v1);
+          uint4 rn[4];
+          bool rnok[4] = {false, false, false, false};
+          if constexpr (kRes) {      // prefetch the next pair's residual while this pair is processed
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            rok[g] = m < p.M && n0 + g * 8 < p.N && (g < 2 || two);
-            if (rok[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + g * 8));
+            for (int g = 0; g < 4; ++g) {
+              rnok[g] = cc + 2 < nchunk && m < p.M && n0 + 32 + g * 8 < p.N && wcol + 32 + g * 8 < p.cw;
+              if (rnok[g]) rn[g] = __ldg(reinterpret_cast<const uint4*>(rrow + n0 + 32 + g * 8));
+            }
           }
-        }
-        tmem_ld_wait();
-        emit8(v0, col0, n0, stg, rr[0], rok[0]);
-        emit8(v0 + 8, col0 + 8, n0 + 8, stg, rr[1], rok[1]);
-        if (two) {
-          emit8(v1, col0 + 16, n0 + 16, stg, rr[2], rok[2]);
-          emit8(v1 + 8, col0 + 24, n0 + 24, stg, rr[3], rok[3]);
+          tmem_ld_wait();
+          emit8(v0, wcol, n0, stg, rr[0], rok[0]);
+          emit8(v0 + 8, wcol + 8, n0 + 8, stg, rr[1], rok[1]);
+          if (two) {
+            emit8(v1, wcol + 16, n0 + 16, stg, rr[2], rok[2]);
+            emit8(v1 + 8, wcol + 24, n0 + 24, stg, rr[3], rok[3]);
+          }
+          if constexpr (kRes) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { rr[g] = rn[g]; rok[g] = rnok[g]; }
+          }
         }
       }
       tc_fence_before();
@@ -413,20 +432,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);     // TMEM stage drained
       fence_proxy_async();                                   // staging writes -> visible to the TMA engine
       __syncwarp();
-      asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
-      if (leader) {
-        for (int bx = 0; bx < p.nbox; ++bx) {
-          const CUtensorMap* tm = (bx == p.nbox - 1 && p.tail_w != 64) ? &tm_out_tail : &tm_out;
+      if (lane == 0 && active) {
+        for (int bx = 0; bx < p.nb; ++bx) {
+          const int n = n_lo + bx * p.bw;
+          if (n >= p.N) break;
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                       ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(stg + (size_t)bx * (kBM * 128))),
-                       "r"(nt * p.BN + bx * 64), "r"((int)m0)
+                       ::"l"(reinterpret_cast<uint64_t>(&tm_out)), "r"(smem_u32(stg + (size_t)bx * box_bytes)), "r"(n), "r"((int)m0)
                        : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       __syncwarp();
     }
-    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
   }
 
   tc_fence_before();
@@ -444,16 +462,33 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   p.M = M;
   p.K = K;
   p.N = N;
-  p.n_tiles_n = (N + 255) / 256;
-  p.BN = (((N + p.n_tiles_n - 1) / p.n_tiles_n) + 15) / 16 * 16;
+  // N tile: BN = (column parts) x cw, cw in {16, 32, 48, 64, 96, 128} so that every epilogue warp owns whole
+  // TMA-store boxes.  Cost model: padded columns plus a fixed per-tile charge (A is re-fetched per N tile).
+  const int parts = a_scale ? 2 : 4;
+  static const int cws[6] = {16, 32, 48, 64, 96, 128};
+  long long best_cost = -1, best_pad = 0;
+  p.BN = 0;
+  for (int ci = 0; ci < 6; ++ci) {
+    const int bn = parts * cws[ci];
+    if (bn > 256) continue;
+    const long long nt = (N + bn - 1) / bn, cost = nt * (bn + 96), pad = nt * bn;
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && pad < best_pad)) {
+      best_cost = cost;
+      best_pad = pad;
+      p.BN = bn;
+      p.cw = cws[ci];
+    }
+  }
+  p.n_tiles_n = (N + p.BN - 1) / p.BN;
+  p.nb = p.cw > 64 ? 2 : 1;
+  p.bw = p.cw / p.nb;
+  p.swz = p.bw == 64 ? 3 : (p.bw == 32 ? 2 : (p.bw == 16 ? 1 : 0));
   p.n_tiles = ((M + kBM - 1) / kBM) * p.n_tiles_n;
   p.k_blocks = (K + kBK - 1) / kBK;
   p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
   p.act = act;
-  p.nbox = (p.BN + 63) / 64;
-  p.tail_w = p.BN - (p.nbox - 1) * 64;
   const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;
-  const size_t staging = (size_t)p.nbox * kBM * 128;
+  const size_t staging = (size_t)p.BN * 256;            // all epilogue warps, one buffer each
   const size_t tail = align_up((size_t)p.n_tiles_n * p.BN * 4, 16) + (a_scale ? (size_t)4 * p.k_blocks * kBK : 0) + sizeof(TcBarriers) + 64 + 1024;
   const size_t budget = 222 * 1024;
   p.nbuf = (2 * staging + 3 * stage_bytes + tail <= budget) ? 2 : 1;
@@ -481,10 +516,11 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   {
     uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)N * 2};
-    uint32_t box[2] = {64, (uint32_t)kBM};
-    DFV_TRY(make_tensor_map(&tm_out, DFV_BF16, 2, out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
-    uint32_t tbox[2] = {(uint32_t)p.tail_w, (uint32_t)kBM};
-    DFV_TRY(make_tensor_map(&tm_tail, DFV_BF16, 2, out, dims, strides, tbox, CU_TENSOR_MAP_SWIZZLE_NONE));
+    uint32_t box[2] = {(uint32_t)p.bw, 32};
+    const CUtensorMapSwizzle sw = p.swz == 3 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : (p.swz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : (p.swz == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
+    DFV_TRY(make_tensor_map(&tm_out, DFV_BF16, 2, out, dims, strides, box, sw));
+    tm_tail = tm_out;
   }
   long long grid = p.n_tiles < (long long)num_sms() ? p.n_tiles : (long long)num_sms();
   p.tiles_per_cta = (p.n_tiles + grid - 1) / grid;
@@ -514,8 +550,8 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   if (debug_flags() & 32) {   // bisecting aid: attribute an asynchronous fault to this launch
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
-      set_error("tc GEMM faulted: %s M=%lld K=%d N=%d BN=%d stages=%d nbuf=%d nbox=%d tail=%d scale=%d res=%d act=%d grid=%lld smem=%zu",
-                cudaGetErrorString(e), M, K, N, p.BN, p.stages, p.nbuf, p.nbox, p.tail_w, a_scale != nullptr,
+      set_error("tc GEMM faulted: %s M=%lld K=%d N=%d BN=%d stages=%d nbuf=%d cw=%d bw=%d scale=%d res=%d act=%d grid=%lld smem=%zu",
+                cudaGetErrorString(e), M, K, N, p.BN, p.stages, p.nbuf, p.cw, p.bw, a_scale != nullptr,
                 residual != nullptr, act, grid, smem);
       return DFV_ERR_CUDA;
     }

@@ -2,6 +2,8 @@
 // Reads the reference's NCHW fp32 input contract directly and writes NHWC.
 // HBM-bound by bytes (1.7 MB in / 3.5 MB out per image at 380 in bf16) but carries
 // 1296 FMA per output pixel, so it sits near the FP32-pipe / HBM crossover.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dfv {
@@ -89,6 +91,232 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------ tcgen05 stem (bf16)
+// The stem is the network's first dense contraction: out[pixel][48] = im2col(x)[pixel][27] . W[27][48].
+//   warps 0-3  build the im2col A tile (128 output pixels x 32 taps, bf16, 128-byte-swizzled K-major rows) straight
+//              from the NCHW fp32 images (static pad (0,1,0,1) = bounds checks), two stages
+//   warp  8    issues two tcgen05.mma (M 128, N 48, K 16) per tile, fp32 accumulators in TMEM (two stages)
+//   warps 4-7  epilogue: tcgen05.ld -> bias -> swish -> bf16 -> shared staging -> one 12 KB bulk copy per tile
+//              (128 consecutive NHWC pixels are contiguous in global memory)
+// The SIMT kernel above needs 1296 FFMA per pixel (0.33 ms of FP32 pipe at batch 256 before any memory traffic).
+constexpr int kStemTcThreads = 288;
+constexpr int kStemTile = 128;
+constexpr uint32_t kStemTmemCols = 128;
+
+struct __align__(8) StemBars {
+  uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint64_t stem_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <bool kAct>
+__global__ void __launch_bounds__(kStemTcThreads, 2)
+    stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, long long tiles_per_cta) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* a_tiles = smem;                           // 2 x 16 KB
+  unsigned char* b_tile = smem + 2 * 16384;                // 48 rows x 128 B (padded to 8 KB)
+  unsigned char* staging = b_tile + 8192;                  // 2 x 12 KB
+  float* bias_sm = reinterpret_cast<float*>(staging + 2 * 12288);
+  StemBars* bars = reinterpret_cast<StemBars*>(bias_sm + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long total = (long long)B * Ho * Wo;
+  const long long n_tiles = (total + kStemTile - 1) / kStemTile;
+  const long long t_begin = (long long)blockIdx.x * tiles_per_cta;
+  const long long t_end = min(t_begin + tiles_per_cta, n_tiles);
+
+  // B operand: W^T [48][32] bf16 (k = (kh*3 + kw)*3 + ci, as the weight blob is laid out), taps 27..31 zero
+  for (int i = tid; i < kStemC * 4; i += blockDim.x) {
+    const int n = i >> 2, c = i & 3;
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k0 = c * 8 + 2 * j;
+      const float lo = k0 < 27 ? w[k0 * kStemC + n] : 0.f, hi = k0 + 1 < 27 ? w[(k0 + 1) * kStemC + n] : 0.f;
+      pk[j] = pack_bf16(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(b_tile + n * 128 + ((c ^ (n & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (tid < kStemC) bias_sm[tid] = kAct ? 0.5f * bias[tid] : bias[tid];
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->a_full[s], 128);
+      mbar_init(&bars->a_empty[s], 1);
+      mbar_init(&bars->t_full[s], 1);
+      mbar_init(&bars->t_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(&bars->tmem_base, kStemTmemCols);
+  fence_proxy_async();      // the weight tile was written with ordinary stores; the tensor core reads it through the async proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------- im2col builders
+    int it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const long long p = t * kStemTile + tid;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      if (p < total) {
+        const int wo = (int)(p % Wo);
+        const long long r = p / Wo;
+        const int ho = (int)(r % Ho), b = (int)(r / Ho);
+        const float* xb = x + (size_t)b * 3 * H * W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+            const int hi = 2 * ho + kh;
+            const float* xr = xb + ((size_t)ci * H + hi) * W + 2 * wo;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw)
+              if (hi < H && 2 * wo + kw < W) v[(kh * 3 + kw) * 3 + ci] = __ldg(xr + kw);
+          }
+      }
+      mbar_wait(&bars->a_empty[s], ph ^ 1, 31);
+      unsigned char* arow = a_tiles + s * 16384 + tid * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 pk;
+        pk.x = pack_bf16(v[c * 8 + 0], v[c * 8 + 1]);
+        pk.y = pack_bf16(v[c * 8 + 2], v[c * 8 + 3]);
+        pk.z = pack_bf16(v[c * 8 + 4], v[c * 8 + 5]);
+        pk.w = pack_bf16(v[c * 8 + 6], v[c * 8 + 7]);
+        *reinterpret_cast<uint4*>(arow + ((c ^ (tid & 7)) << 4)) = pk;
+      }
+      fence_proxy_async();
+      mbar_arrive(&bars->a_full[s]);
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kStemC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t db = stem_sw128_desc(smem_u32(b_tile));
+      int it = 0;
+      for (long long t = t_begin; t < t_end; ++t, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&bars->t_empty[s], ph ^ 1, 32);
+        mbar_wait(&bars->a_full[s], ph, 33);
+        tc_fence_after();
+        const uint64_t da = stem_sw128_desc(smem_u32(a_tiles + s * 16384));
+        const uint32_t d_tmem = tmem_base + (uint32_t)s * 64;
+        umma_bf16(d_tmem, da, db, idesc, 0);
+        umma_bf16(d_tmem, da + 2, db + 2, idesc, 1);
+        umma_commit(&bars->a_empty[s]);
+        umma_commit(&bars->t_full[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue (warps 4..7 <-> TMEM lane quarters 0..3)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool leader = (warp == 4 && lane == 0);
+    int it = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      unsigned char* stg = staging + s * 12288;
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // staging[s]'s previous copy has been read
+      __syncwarp();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&bars->t_full[s], ph, 34);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * 64;
+      uint32_t v[3][16];
+      tmem_ld16(tbase, v[0]);
+      tmem_ld16(tbase + 16, v[1]);
+      tmem_ld16(tbase + 32, v[2]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->t_empty[s]);
+#pragma unroll
+      for (int g = 0; g < 6; ++g) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = __uint_as_float(v[g >> 1][(g & 1) * 8 + j]);
+          if constexpr (kAct) {
+            const float h = fmaf(a, 0.5f, bias_sm[g * 8 + j]);
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+            o[j] = fmaf(h, th, h);
+          } else {
+            o[j] = a + bias_sm[g * 8 + j];
+          }
+        }
+        uint4 pk;
+        pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
+        pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(stg + row * 96 + g * 16) = pk;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (leader) {
+        const long long p0 = t * kStemTile;
+        const long long npx = min((long long)kStemTile, total - p0);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(reinterpret_cast<uint64_t>(y + (size_t)p0 * kStemC)), "r"(smem_u32(stg)), "r"((uint32_t)(npx * kStemC * 2))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      __syncwarp();
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kStemTmemCols);
+  }
+}
+
+static int launch_stem_tc(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Ho, int Wo, int act,
+                          cudaStream_t st) {
+  const long long total = (long long)B * Ho * Wo;
+  const long long n_tiles = (total + kStemTile - 1) / kStemTile;
+  long long grid = std::min<long long>(n_tiles, 2LL * num_sms());
+  const long long tpc = (n_tiles + grid - 1) / grid;
+  grid = (n_tiles + tpc - 1) / tpc;
+  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 1024;
+  DFV_TRY(init_timeout_word_tu());
+  static thread_local bool configured = false;
+  if (!configured) {
+    DFV_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  if (act)
+    stem_tc_kernel<true><<<(unsigned)grid, kStemTcThreads, smem, st>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, tpc);
+  else
+    stem_tc_kernel<false><<<(unsigned)grid, kStemTcThreads, smem, st>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, tpc);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
 }  // namespace dfv
 
 using namespace dfv;
@@ -107,6 +335,7 @@ extern "C" int dfv_stem_conv_fwd(const float* x, const float* w, const float* bi
   const unsigned grid = (unsigned)((threads + 255) / 256);
   ProfScope prof(PK_STEM, (double)B * 3 * H * W * 4 + (double)total * kStemC * dtype_size(dtype),
                  2.0 * 27 * kStemC * (double)total, as_stream(stream));
+  if (dtype == DFV_BF16 && !force_simt_gemm()) return launch_stem_tc(x, w, bias, y, B, H, W, Ho, Wo, act, as_stream(stream));
   if (dtype == DFV_BF16)
     stem_kernel<__nv_bfloat16, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, act);
   else

@@ -48,7 +48,7 @@ def test_stem(ops, shape, dtype):
     y = ops.stem_conv(x.to(DEV), w.permute(2, 3, 1, 0).contiguous().to(DEV), bias.to(DEV), dtype)
     assert y.shape == (B, ref.shape[2], ref.shape[3], 48)
     r = rel(y.float().permute(0, 3, 1, 2), ref)
-    assert r < (2e-6 if dtype == torch.float32 else 5e-3), r
+    assert r < (2e-6 if dtype == torch.float32 else 8e-3), r   # bf16: images and weights are bf16 tensor-core operands, as under autocast
 
 
 # ------------------------------------------------------------------------------- depthwise
