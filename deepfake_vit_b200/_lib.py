@@ -95,6 +95,8 @@ def _load():
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
         "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "dfv_pw_gemm_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, vp]),
+        "dfv_pw_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, vp, vp]),
+        "dfv_pw_fold_ws_bytes": (sz, [i32]),
         "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
         "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 8 + [i32] * 8 + [vp]),
         "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, vp, i32, vp]),

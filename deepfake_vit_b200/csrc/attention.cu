@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(256) hybrid_attention_kernel(
       float s[8], m[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { s[e] = 0.f; m[e] = -INFINITY; }
-      for (int p = 0; p < HW; ++p) {
+#pragma unroll 8
+      for (int p = 0; p < HW; ++p) {      // unrolled: eight independent 16-byte loads in flight per thread
         float v[8];
         load8(fb + (size_t)p * C + cv * 8, v);
         const float a = a_lm[p];
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_kernel(
     for (int j = warp; j < hidden; j += nwarps) {
       const float* wr = w1 + (size_t)j * C;
       float sa = 0.f, sx = 0.f;
+#pragma unroll 8
       for (int c = lane; c < C; c += 32) {
         const float wv = wr[c];
         sa = fmaf(wv, avg_c[c], sa);
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_kernel(
     __syncthreads();
     for (int c = tid; c < C; c += blockDim.x) {
       float s = 0.f;
+#pragma unroll 16
       for (int j = 0; j < hidden; ++j) s = fmaf(w2t[(size_t)j * C + c], hid[j], s);
       const float g = sigmoid_exact(s);
       gate_c[c] = g;
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_kernel(
     for (int p = warp; p < HW; p += nwarps) {
       const float a = a_lm[p];
       float s = 0.f, m = -INFINITY;
+#pragma unroll 8
       for (int cv = lane; cv < CV; cv += 32) {
         float v[8];
         load8(fb + (size_t)p * C + cv * 8, v);
@@ -177,6 +181,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_kernel(
     float s[8], gc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; gc[e] = gate_c[cv * 8 + e]; }
+#pragma unroll 8
     for (int p = 0; p < HW; ++p) {
       float v[8];
       load8(fb + (size_t)p * C + cv * 8, v);

@@ -126,24 +126,25 @@ __device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4],
 // runs, so the SE pool sums stay in registers across tiles and are reduced (shared memory, deterministic)
 // only when the image changes.  Image b's partial sums land in slot (cta - first cta touching b); the
 // last CTA of an image zero-fills the unused slots, so the SE-gate kernel simply sums `parts` rows.
-template <typename T, int K, int S, int L, bool kFast, bool kAct>
+template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        T* __restrict__ y, float* __restrict__ pool_partial, DwParams p) {
   constexpr bool kHalf = kFast && kAct && sizeof(T) == 2;
+  const int CB = kCB ? kCB : p.CB;     // compile-time for the full-width chunk: shared-memory offsets become immediates
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [tile0][tile1][weights: K*K*CB T][bias: CB f32][red: nthreads*8 f32][red2: 4*CB f32][mbar x2]
-  const size_t tile_bytes = (size_t)p.THI * p.TWI * p.CB * sizeof(T);
+  const size_t tile_bytes = (size_t)p.THI * p.TWI * CB * sizeof(T);
   const size_t tile_stride = ((tile_bytes + 127) / 128) * 128;
   T* wsm = reinterpret_cast<T*>(smem_raw + 2 * tile_stride);
-  float* bsm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wsm) + (((size_t)K * K * p.CB * sizeof(T) + 15) / 16) * 16);
-  float* red = bsm + p.CB;
+  float* bsm = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(wsm) + (((size_t)K * K * CB * sizeof(T) + 15) / 16) * 16);
+  float* red = bsm + CB;
   float* red2 = red + (size_t)p.nthreads * 8;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red2 + 4 * p.CB);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red2 + 4 * CB);
 
   const int tid = threadIdx.x;
   const int chunk = blockIdx.x % p.chunks, slot = blockIdx.x / p.chunks;
-  const int c0 = chunk * p.CB;
+  const int c0 = chunk * CB;
   const int n_tiles = p.tiles_w * p.tiles_h;
   const long long t_begin = (long long)slot * p.tiles_per_cta;
   const long long t_end = min(t_begin + p.tiles_per_cta, p.per_chunk);
@@ -164,26 +165,26 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   }
   // Stage this chunk's weights (BN scale already folded in) and bias while the first tile lands.
   const float fold = kHalf ? 0.5f : 1.0f;
-  for (int i = tid; i < K * K * p.CB; i += blockDim.x) {
-    const int c = c0 + i % p.CB;
-    const float v = (c < p.C) ? fold * w[(size_t)(i / p.CB) * p.C + c] : 0.f;
+  for (int i = tid; i < K * K * CB; i += blockDim.x) {
+    const int c = c0 + i % CB;
+    const float v = (c < p.C) ? fold * w[(size_t)(i / CB) * p.C + c] : 0.f;
     if constexpr (sizeof(T) == 2) wsm[i] = __float2bfloat16_rn(v); else wsm[i] = v;
   }
-  for (int i = tid; i < p.CB; i += blockDim.x) bsm[i] = (c0 + i < p.C) ? fold * bias[c0 + i] : 0.f;
+  for (int i = tid; i < CB; i += blockDim.x) bsm[i] = (c0 + i < p.C) ? fold * bias[c0 + i] : 0.f;
   __syncthreads();
 
   // fixed per-thread role
-  const int G = p.CB >> 3;
+  const int G = CB >> 3;
   const int g = tid % G;
   const int j = (tid / G) % p.strips;
   const int r0 = tid / (G * p.strips);
   const int c = c0 + g * 8;
   const bool chan_ok = c < p.C;
-  const int in_off0 = ((r0 * S) * p.TWI + j * L * S) * p.CB + g * 8;
-  const int in_step = p.rpr * S * p.TWI * p.CB;
+  const int in_off0 = ((r0 * S) * p.TWI + j * L * S) * CB + g * 8;
+  const int in_step = p.rpr * S * p.TWI * CB;
   const int out_off0 = (r0 * p.Wo + j * L) * p.C + g * 8;
   const int out_step = p.rpr * p.Wo * p.C;
-  const int row_stride = p.TWI * p.CB;
+  const int row_stride = p.TWI * CB;
   const T* wbase = wsm + g * 8;
   float bv[8];
   load8(bsm + g * 8, bv);
@@ -223,12 +224,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
         for (int kh = 0; kh < K; ++kh) {
           Vec8<T> wk[K];
 #pragma unroll
-          for (int kw = 0; kw < K; ++kw) ldvec(wbase + (kh * K + kw) * p.CB, wk[kw]);
+          for (int kw = 0; kw < K; ++kw) ldvec(wbase + (kh * K + kw) * CB, wk[kw]);
           const T* row = in + kh * row_stride;
 #pragma unroll
           for (int iw = 0; iw < NI; ++iw) {
             Vec8<T> v;
-            ldvec(row + iw * p.CB, v);
+            ldvec(row + iw * CB, v);
 #pragma unroll
             for (int l = 0; l < L; ++l) {
               const int kw = iw - l * S;
@@ -259,8 +260,8 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
       }
       __syncthreads();   // also: everyone is done with tile[buf] before it is refilled
       const int R = p.red_parts;
-      for (int idx = tid; idx < p.CB * R; idx += nth) {
-        const int o = idx % p.CB, q = idx / p.CB;
+      for (int idx = tid; idx < CB * R; idx += nth) {
+        const int o = idx % CB, q = idx / CB;
         const int gg = o >> 3, e = o & 7;
         float s = 0.f;
         for (int u = gg + G * q; u < nth; u += G * R) s += red[u * 8 + e];
@@ -270,10 +271,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
       const long long first_cta = ((long long)b * n_tiles) / p.tiles_per_cta;
       const long long last_cta = ((long long)(b + 1) * n_tiles - 1) / p.tiles_per_cta;
       const int my_slot = (int)(slot - first_cta);
-      for (int o = tid; o < p.CB; o += nth) {
+      for (int o = tid; o < CB; o += nth) {
         if (c0 + o < p.C) {
           float s = 0.f;
-          for (int q = 0; q < R; ++q) s += red2[q * p.CB + o];
+          for (int q = 0; q < R; ++q) s += red2[q * CB + o];
           float* dst = pool_partial + (size_t)b * p.parts * p.C + c0 + o;
           dst[(size_t)my_slot * p.C] = s;
           if (slot == last_cta)
@@ -396,10 +397,10 @@ static void plan_grid(DwPlan& pl, int B) {
   pl.p.parts = (int)((n + tpc - 2) / tpc + 1);
 }
 
-template <typename T, int K, int S, int L, bool kFast, bool kAct>
+template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB>
 static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, DwPlan& pl, int B,
                   cudaStream_t st) {
-  auto kern = dwconv_kernel<T, K, S, L, kFast, kAct>;
+  auto kern = dwconv_kernel<T, K, S, L, kFast, kAct, kCB>;
   static thread_local bool configured = false;
   if (!configured) {
     DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -419,8 +420,12 @@ static int dispatch(int K, int S, int L, int act, const CUtensorMap& tm, const f
                     DwPlan& pl, int B, cudaStream_t st) {
 #define DW_CASE(k, s, l)                                                                          \
   if (K == k && S == s && L == l) {                                                               \
-    if (act) return launch<T, k, s, l, kFast, true>(tm, w, bias, y, pool, pl, B, st);             \
-    return launch<T, k, s, l, kFast, false>(tm, w, bias, y, pool, pl, B, st);                     \
+    if (sizeof(T) == 2 && pl.p.CB == 64) {                                                        \
+      if (act) return launch<T, k, s, l, kFast, true, 64>(tm, w, bias, y, pool, pl, B, st);       \
+      return launch<T, k, s, l, kFast, false, 64>(tm, w, bias, y, pool, pl, B, st);               \
+    }                                                                                             \
+    if (act) return launch<T, k, s, l, kFast, true, 0>(tm, w, bias, y, pool, pl, B, st);          \
+    return launch<T, k, s, l, kFast, false, 0>(tm, w, bias, y, pool, pl, B, st);                  \
   }
   DW_CASE(3, 1, 8) DW_CASE(3, 1, 6) DW_CASE(3, 1, 4) DW_CASE(5, 1, 8) DW_CASE(5, 1, 6) DW_CASE(5, 1, 4)
   DW_CASE(3, 2, 4) DW_CASE(5, 2, 4)

@@ -63,13 +63,11 @@ struct Workspace {
   float* heat_raw;
   uint32_t* heat_max;
   float* head_scratch;     // classifier hidden activations: 2 x B x kHeadHiddenMax
-  char* fold_w;            // block-diagonal weights of a row-folded 1x1 convolution
-  float* fold_bias;
-  char* fold_gate;
+  char* fold_ws;           // scratch of dfv_pw_conv_fwd (row-folded thin 1x1 convolutions)
   size_t bytes;
 };
 constexpr int kHeadHiddenMax = 2048;
-constexpr int kFoldWElems = 64 * 1024, kFoldBias = 1024, kFoldGate = 256;
+
 
 static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) {
   const size_t es = dtype_size(dtype);
@@ -89,64 +87,8 @@ static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) 
   ws->heat_raw = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_max = (uint32_t*)take((size_t)B * 4);
   ws->head_scratch = (float*)take((size_t)2 * B * kHeadHiddenMax * 4);
-  ws->fold_w = take((size_t)kFoldWElems * 4);
-  ws->fold_bias = (float*)take((size_t)kFoldBias * 4);
-  ws->fold_gate = take((size_t)B * kFoldGate * 4);
+  ws->fold_ws = take(dfv_pw_fold_ws_bytes(B));
   ws->bytes = off;
-}
-
-// ---- row folding of thin 1x1 convolutions --------------------------------------------------------------
-// A [M][K] activation with K <= 48 channels is a poor tensor-core / TMA operand: 128-row tiles carry 6-12 KB and the
-// per-tile pipeline latency, not HBM, sets the pace (measured 1.4-2.7 TB/s on the 190x190 layers).  The SAME memory
-// read as [M/f][f*K] times the block-diagonal weight diag(W, ..., W) gives the SAME output memory [M/f][f*N]:
-// f x fewer, f x fatter tiles for f x the (idle) tensor FLOPs.  The SE gate and bias are tiled f times.
-template <typename T>
-__global__ void fold_weight_kernel(const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ wf,
-                                   float* __restrict__ bf, int N, int K, int f) {
-  const int total = f * N * f * K;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int col = i % (f * K), row = i / (f * K);
-    const int a = row / N, n = row % N, b = col / K, k = col % K;
-    T v = w[(size_t)n * K + k];
-    if (a != b) v = T(0.f);
-    wf[i] = v;
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f * N; i += gridDim.x * blockDim.x) bf[i] = bias[i % N];
-}
-template <typename T>
-__global__ void tile_gate_kernel(const T* __restrict__ g, T* __restrict__ gf, int B, int K, int f) {
-  const int total = B * f * K;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int b = i / (f * K), k = (i % (f * K)) % K;
-    gf[i] = g[(size_t)b * K + k];
-  }
-}
-
-static int pick_fold(int dtype, long long M, int K, int N, int rows_per_image, bool gated, int B) {
-  if (dtype != DFV_BF16 || K > 48 || force_simt_gemm()) return 1;
-  for (int f = 4; f >= 2; f >>= 1) {
-    if (M % f || (gated && rows_per_image % f)) continue;
-    if (f * N > (f == 4 ? 256 : 512)) continue;
-    if ((size_t)f * N * f * K > (size_t)kFoldWElems || f * N > kFoldBias || (gated && f * K > kFoldGate)) continue;
-    return f;
-  }
-  return 1;
-}
-
-// 1x1 convolution through the (possibly row-folded) tcgen05 GEMM.
-static int pw_conv(const Workspace& ws, const void* x, const void* w, const float* bias, const void* gate, int rows_per_image,
-                   const void* residual, void* out, int dtype, int B, long long M, int K, int N, int act, dfv_stream_t stream) {
-  const int f = pick_fold(dtype, M, K, N, rows_per_image, gate != nullptr, B);
-  if (f == 1) return dfv_pw_gemm_fwd(x, w, bias, gate, rows_per_image, residual, out, dtype, M, K, N, act, stream);
-  cudaStream_t st = as_stream(stream);
-  fold_weight_kernel<__nv_bfloat16><<<16, 256, 0, st>>>((const __nv_bfloat16*)w, bias, (__nv_bfloat16*)ws.fold_w, ws.fold_bias, N, K, f);
-  DFV_LAUNCH_CHECK();
-  if (gate) {
-    tile_gate_kernel<__nv_bfloat16><<<32, 256, 0, st>>>((const __nv_bfloat16*)gate, (__nv_bfloat16*)ws.fold_gate, B, K, f);
-    DFV_LAUNCH_CHECK();
-  }
-  return dfv_pw_gemm_fwd(x, ws.fold_w, ws.fold_bias, gate ? ws.fold_gate : nullptr, rows_per_image / f, residual, out, dtype, M / f,
-                         f * K, f * N, act, stream);
 }
 
 }  // namespace dfv
@@ -202,8 +144,8 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
     const void* x = ws.act[cur];
     const void* dw_in = x;
     if (b.has_expand) {
-      DFV_TRY(pw_conv(ws, x, W_(i, DFV_W_EXPAND), (const float*)W_(i, DFV_W_EXPAND_BIAS), nullptr, h * w, nullptr, ws.expand,
-                      dtype, B, (long long)B * h * w, b.c_in, b.c_mid, DFV_ACT_SILU, stream));
+      DFV_TRY(dfv_pw_conv_fwd(x, W_(i, DFV_W_EXPAND), (const float*)W_(i, DFV_W_EXPAND_BIAS), nullptr, h * w, nullptr, ws.expand,
+                              dtype, B, (long long)B * h * w, b.c_in, b.c_mid, DFV_ACT_SILU, ws.fold_ws, stream));
       dw_in = ws.expand;
     }
     const int parts = dfv_dwconv_pool_parts(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi);
@@ -212,9 +154,9 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_se_gate_fwd(ws.pool, parts, 1.0f / (float)(ho * wo), (const float*)W_(i, DFV_W_SE_REDUCE),
                             (const float*)W_(i, DFV_W_SE_REDUCE_BIAS), (const float*)W_(i, DFV_W_SE_EXPAND),
                             (const float*)W_(i, DFV_W_SE_EXPAND_BIAS), ws.gate, dtype, B, b.c_mid, b.se_squeeze, stream));
-    DFV_TRY(pw_conv(ws, ws.dw, W_(i, DFV_W_PROJECT), (const float*)W_(i, DFV_W_PROJECT_BIAS), ws.gate, ho * wo,
-                    b.has_skip ? x : nullptr, ws.act[cur ^ 1], dtype, B, (long long)B * ho * wo, b.c_mid, b.c_out, DFV_ACT_NONE,
-                    stream));
+    DFV_TRY(dfv_pw_conv_fwd(ws.dw, W_(i, DFV_W_PROJECT), (const float*)W_(i, DFV_W_PROJECT_BIAS), ws.gate, ho * wo,
+                            b.has_skip ? x : nullptr, ws.act[cur ^ 1], dtype, B, (long long)B * ho * wo, b.c_mid, b.c_out,
+                            DFV_ACT_NONE, ws.fold_ws, stream));
     cur ^= 1;
     DFV_TRY(tap(1 + i, ws.act[cur], (size_t)B * ho * wo * b.c_out));
   }

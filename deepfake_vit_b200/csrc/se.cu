@@ -14,7 +14,7 @@ namespace dfv {
 constexpr int kSeCluster = 8;
 
 template <int IMG, typename GT>
-__global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256)
+__global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
     se_gate_kernel(const float* __restrict__ partial, int parts, float inv_hw, const float* __restrict__ w1,
                    const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
                    GT* __restrict__ gate, int B, int C, int sq) {
@@ -29,14 +29,28 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256)
   const int jper = (sq + kSeCluster - 1) / kSeCluster;
   const int j0 = min(sq, rank * jper), j1 = min(sq, j0 + jper);
 
-  for (int i = tid; i < IMG * C; i += blockDim.x) {
-    const int im = i / C, c = i % C;
-    float s = 0.f;
-    if (b0 + im < B) {
-      const float* pb = partial + (size_t)(b0 + im) * parts * C + c;
-      for (int t = 0; t < parts; ++t) s += pb[(size_t)t * C];
+  // pooled[im][c]: four (image, channel) cells per thread per round so that 4 x parts loads are in flight
+  constexpr int PU = 16;     // cells per thread per round: 16 x parts independent loads in flight
+  for (int i0 = tid; i0 < IMG * C; i0 += PU * blockDim.x) {
+    float s[PU];
+    const float* pb[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      s[u] = 0.f;
+      const int i = i0 + u * blockDim.x;
+      const int im = i / C, c = i % C;
+      pb[u] = (i < IMG * C && b0 + im < B) ? partial + (size_t)(b0 + im) * parts * C + c : nullptr;
     }
-    pooled[i] = s * inv_hw;
+    for (int t = 0; t < parts; ++t) {
+#pragma unroll
+      for (int u = 0; u < PU; ++u)
+        if (pb[u]) s[u] += __ldg(pb[u] + (size_t)t * C);
+    }
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < IMG * C) pooled[i] = s[u] * inv_hw;
+    }
   }
   __syncthreads();
 
@@ -46,11 +60,32 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256)
     float s[IMG];
 #pragma unroll
     for (int im = 0; im < IMG; ++im) s[im] = 0.f;
-#pragma unroll 8
-    for (int c = lane; c < C; c += 32) {
-      const float wv = __ldg(wr + c);
+    if ((C & 3) == 0) {
+      // 16-byte weight loads, the whole row slice of a lane (up to 12 loads = 1536 channels) requested before use
+      for (int cb = lane * 4; cb < C; cb += 12 * 128) {
+        float4 wv[12];
 #pragma unroll
-      for (int im = 0; im < IMG; ++im) s[im] = fmaf(wv, pooled[im * C + c], s[im]);
+        for (int u = 0; u < 12; ++u)
+          wv[u] = cb + u * 128 < C ? __ldg(reinterpret_cast<const float4*>(wr + cb + u * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+          const int c = cb + u * 128;
+          if (c < C) {
+#pragma unroll
+            for (int im = 0; im < IMG; ++im) {
+              const float4 pv = *reinterpret_cast<const float4*>(pooled + im * C + c);
+              s[im] = fmaf(wv[u].x, pv.x, fmaf(wv[u].y, pv.y, fmaf(wv[u].z, pv.z, fmaf(wv[u].w, pv.w, s[im]))));
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int c = lane; c < C; c += 32) {
+        const float wv = __ldg(wr + c);
+#pragma unroll
+        for (int im = 0; im < IMG; ++im) s[im] = fmaf(wv, pooled[im * C + c], s[im]);
+      }
     }
 #pragma unroll
     for (int im = 0; im < IMG; ++im) {
@@ -78,11 +113,17 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256)
     const float bv = b2[c];
 #pragma unroll
     for (int im = 0; im < IMG; ++im) s[im] = bv;
-#pragma unroll 8
-    for (int j = 0; j < sq; ++j) {
-      const float wv = __ldg(w2t + (size_t)j * C + c);
+    for (int jb = 0; jb < sq; jb += 32) {     // 32 weight loads in flight per thread
+      float wv[32];
 #pragma unroll
-      for (int im = 0; im < IMG; ++im) s[im] = fmaf(wv, hidden[im * sq + j], s[im]);
+      for (int u = 0; u < 32; ++u) wv[u] = jb + u < sq ? __ldg(w2t + (size_t)(jb + u) * C + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        if (jb + u < sq) {
+#pragma unroll
+          for (int im = 0; im < IMG; ++im) s[im] = fmaf(wv[u], hidden[im * sq + jb + u], s[im]);
+        }
+      }
     }
 #pragma unroll
     for (int im = 0; im < IMG; ++im)

@@ -71,6 +71,7 @@ struct Arena {
   float* mask_f;
   float* pool_ws;
   float* bn_ws;
+  char* fold_ws;
   ClsArena cls[DFV_MAX_CLS_LAYERS];
   size_t bytes;
 };
@@ -82,6 +83,7 @@ struct Scratch {
   float* gcls[2];
   float* wT;
   float* dfeat;
+  char* fold_ws;
   size_t bytes;
 };
 
@@ -175,6 +177,7 @@ void carve_arena(Arena* a, void* base, const TShapes& s, int dtype, int B, const
   a->mask_f = c.takef((size_t)B * topo_head_c());
   a->pool_ws = c.takef(pool_max);
   a->bn_ws = c.takef(max_bn_ws(s, B, dims, layers));
+  a->fold_ws = c.take(dfv_pw_fold_ws_bytes(B));
   for (int l = 0; l < layers && l < DFV_MAX_CLS_LAYERS; ++l) {
     const size_t d = dims[l + 1];
     a->cls[l].lin = c.takef((size_t)B * d);
@@ -223,6 +226,7 @@ void carve_scratch(Scratch* sc, void* base, const TShapes& s, int dtype, int B, 
   sc->gcls[1] = c.takef((size_t)B * dmax);
   sc->wT = c.takef(wmax);
   sc->dfeat = c.takef((size_t)B * topo_head_c());
+  sc->fold_ws = c.take(dfv_pw_fold_ws_bytes(B));
   sc->bytes = c.off;
 }
 
@@ -343,7 +347,8 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
     if (b.has_expand) {
       DFV_TRY(dfv_cast_weight(P(i, DFV_T_EXPAND_W), ba.wE, dtype, b.c_mid, b.c_in, 0, stream));
       DFV_TRY(dfv_cast_weight(P(i, DFV_T_EXPAND_W), ba.wEt, dtype, b.c_in, b.c_mid, 1, stream));
-      DFV_TRY(dfv_pw_gemm_fwd(x, ba.wE, ar.zero_bias, nullptr, 0, nullptr, ba.e_raw, dtype, B * hw_in, b.c_in, b.c_mid, DFV_ACT_NONE, stream));
+      DFV_TRY(dfv_pw_conv_fwd(x, ba.wE, ar.zero_bias, nullptr, (int)hw_in, nullptr, ba.e_raw, dtype, B, B * hw_in, b.c_in, b.c_mid, DFV_ACT_NONE,
+                              ar.fold_ws, stream));
       DFV_TRY(dfv_bn_stats_fwd(ba.e_raw, dtype, B, hw_in, b.c_mid, eps, mom, ba.m0, ba.i0, PW(i, DFV_T_BN0_RM), PW(i, DFV_T_BN0_RV), ar.bn_ws, stream));
       DFV_TRY(dfv_bn_act_fwd(ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ba.e,
                              nullptr, dtype, B, hw_in, b.c_mid, stream));
@@ -360,7 +365,8 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
                              P(i, DFV_T_SE_E_W), P(i, DFV_T_SE_E_B), ba.gate, dtype, ba.pooled, ba.h1, ba.gate_f32, B, b.c_mid, b.se_squeeze, stream));
     DFV_TRY(dfv_cast_weight(P(i, DFV_T_PROJ_W), ba.wP, dtype, b.c_out, b.c_mid, 0, stream));
     DFV_TRY(dfv_cast_weight(P(i, DFV_T_PROJ_W), ba.wPt, dtype, b.c_mid, b.c_out, 1, stream));
-    DFV_TRY(dfv_pw_gemm_fwd(ba.d, ba.wP, ar.zero_bias, ba.gate, (int)hw_out, nullptr, ba.p_raw, dtype, B * hw_out, b.c_mid, b.c_out, DFV_ACT_NONE, stream));
+    DFV_TRY(dfv_pw_conv_fwd(ba.d, ba.wP, ar.zero_bias, ba.gate, (int)hw_out, nullptr, ba.p_raw, dtype, B, B * hw_out, b.c_mid, b.c_out, DFV_ACT_NONE,
+                            ar.fold_ws, stream));
     DFV_TRY(dfv_bn_stats_fwd(ba.p_raw, dtype, B, hw_out, b.c_out, eps, mom, ba.m2, ba.i2, PW(i, DFV_T_BN2_RM), PW(i, DFV_T_BN2_RV), ar.bn_ws, stream));
     const float rate = a->drop_connect_rate * (float)i / (float)n;
     const float* rowscale = nullptr;
@@ -515,7 +521,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_bn_bwd_apply(sc.gP, ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), sc.coef, sc.gP, dtype, B * hw_out, b.c_out, stream));
     // project conv
     DFV_TRY(dfv_pw_wgrad(sc.gP, ba.d, ba.gate, (int)hw_out, G(i, DFV_T_PROJ_W), dtype, B * hw_out, b.c_mid, b.c_out, stream));
-    DFV_TRY(dfv_pw_gemm_fwd(sc.gP, ba.wPt, ar.zero_bias, nullptr, 0, nullptr, sc.gA, dtype, B * hw_out, b.c_out, b.c_mid, DFV_ACT_NONE, stream));
+    DFV_TRY(dfv_pw_conv_fwd(sc.gP, ba.wPt, ar.zero_bias, nullptr, (int)hw_out, nullptr, sc.gA, dtype, B, B * hw_out, b.c_out, b.c_mid, DFV_ACT_NONE,
+                            sc.fold_ws, stream));
     // squeeze-excite
     DFV_TRY(dfv_se_bwd(sc.gA, ba.d, dtype, ba.gate_f32, ba.pooled, ba.h1, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_E_W), sc.dpool, G(i, DFV_T_SE_R_W),
                        G(i, DFV_T_SE_R_B), G(i, DFV_T_SE_E_W), G(i, DFV_T_SE_E_B), sc.se_ws, B, hw_out, b.c_mid, b.se_squeeze, stream));
@@ -541,8 +548,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
                              sc.gE, G(i, DFV_T_BN0_G), G(i, DFV_T_BN0_B), sc.coef, sc.bn_ws, dtype, B, hw_in, b.c_mid, stream));
       DFV_TRY(dfv_bn_bwd_apply(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), sc.coef, sc.gE, dtype, B * hw_in, b.c_mid, stream));
       DFV_TRY(dfv_pw_wgrad(sc.gE, x, nullptr, 0, G(i, DFV_T_EXPAND_W), dtype, B * hw_in, b.c_in, b.c_mid, stream));
-      DFV_TRY(dfv_pw_gemm_fwd(sc.gE, ba.wEt, ar.zero_bias, nullptr, 0, b.has_skip ? gy : nullptr, gx, dtype, B * hw_in, b.c_mid, b.c_in,
-                              DFV_ACT_NONE, stream));
+      DFV_TRY(dfv_pw_conv_fwd(sc.gE, ba.wEt, ar.zero_bias, nullptr, (int)hw_in, b.has_skip ? gy : nullptr, gx, dtype, B, B * hw_in, b.c_mid, b.c_in,
+                              DFV_ACT_NONE, sc.fold_ws, stream));
     } else {
       // no expand conv: gE is already the gradient wrt the block input (c_mid == c_in); add the skip gradient
       DFV_TRY(dfv_bn_act_fwd(sc.gE, nullptr, nullptr, nullptr, nullptr, DFV_ACT_NONE, nullptr, b.has_skip ? gy : nullptr, nullptr, gx, nullptr, dtype,

@@ -282,8 +282,8 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
 }
 
 // ------------------------------------------------------------------------------------ act_bn_bwd
-template <typename T, bool kGate>
-__global__ void __launch_bounds__(kNT, 2) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
+template <typename T, bool kGate, int U, int MINB>
+__global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int act, const T* __restrict__ gate, const float* __restrict__ dpool,
@@ -291,7 +291,6 @@ __global__ void __launch_bounds__(kNT, 2) act_bn_bwd_kernel(const T* __restrict_
                                                            const float* __restrict__ mask, T* __restrict__ du,
                                                            float* __restrict__ partial, long long rows_per_image, int C,
                                                            long long rows_per_chunk) {
-  constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 16];
   const ColMap m(C);
   const int b = blockIdx.y;
@@ -766,13 +765,16 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 12.0 * B * rows_per_image * C, st);
   const bool gated = gate != nullptr || dpool != nullptr;
-#define ABB(T_, G_)                                                                                                                 \
-  act_bn_bwd_kernel<T_, G_><<<grid, kNT, 0, st>>>((const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act, (const T_*)gate, dpool, \
-                                                 inv_hw, rowscale, mask, (T_*)du, ws, rows_per_image, C, rpc)
+#define ABB(T_, G_, U_, M_)                                                                                                         \
+  act_bn_bwd_kernel<T_, G_, U_, M_><<<grid, kNT, 0, st>>>((const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act, (const T_*)gate, \
+                                                         dpool, inv_hw, rowscale, mask, (T_*)du, ws, rows_per_image, C, rpc)
+  const int variant = (debug_flags() >> 8) & 3;   // tuning aid: DFV_DEBUG_FLAGS bits 8-9
   if (dtype == DFV_BF16) {
-    if (gated) ABB(__nv_bfloat16, true); else ABB(__nv_bfloat16, false);
+    if (variant == 1) { if (gated) ABB(__nv_bfloat16, true, 2, 3); else ABB(__nv_bfloat16, false, 2, 3); }
+    else if (variant == 2) { if (gated) ABB(__nv_bfloat16, true, 8, 1); else ABB(__nv_bfloat16, false, 8, 1); }
+    else { if (gated) ABB(__nv_bfloat16, true, 4, 2); else ABB(__nv_bfloat16, false, 4, 2); }
   } else {
-    if (gated) ABB(float, true); else ABB(float, false);
+    if (gated) ABB(float, true, 2, 2); else ABB(float, false, 2, 2);
   }
 #undef ABB
   DFV_LAUNCH_CHECK();

@@ -159,6 +159,15 @@ int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, const void*
                     const void* residual, void* out, int dtype, long long M, int K, int N, int act,
                     dfv_stream_t stream);
 
+/* The same 1x1 convolution, with thin bf16 layers (K <= 48 channels: the 190x190-stage project / expand convs) run
+ * ROW-FOLDED: [M][K] read as [M/f][f*K] against the block-diagonal weight diag(W,...,W) gives the same output memory
+ * [M/f][f*N] with f x fewer, f x fatter tensor-core tiles.  fold_ws: dfv_pw_fold_ws_bytes(B) bytes of device scratch
+ * (NULL = never fold); B = number of images (rows of a_scale). */
+size_t dfv_pw_fold_ws_bytes(int B);
+int dfv_pw_conv_fwd(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
+                    const void* residual, void* out, int dtype, int B, long long M, int K, int N, int act,
+                    void* fold_ws, dfv_stream_t stream);
+
 /* Landmark heat-map of LandmarkAttention._create_attention_map
  * (src/feature_extraction/landmark_attention.py:76-130), op order of SURVEY.md B.2:
  * coordinates scaled by W/ref_size (ref_size = 224.0 hard-coded at :97-98), five weighted
