@@ -97,6 +97,11 @@ def _load():
         "dfv_pw_gemm_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, vp]),
         "dfv_pw_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, vp, vp]),
         "dfv_pw_fold_ws_bytes": (sz, [i32]),
+        "dfv_debug_dwconv_plan": (C.c_int, [i32] * 9 + [C.POINTER(C.c_int)]),
+        "dfv_clip_aggregate": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, f32, vp]),
+        "dfv_global_avg_pool": (C.c_int, [vp, i32, vp, i32, i64, i32, vp]),
+        "dfv_l2_normalize": (C.c_int, [vp, vp, i32, i32, f32, vp]),
+        "dfv_clip_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, vp] + [C.c_double] * 7 + [i64, vp, vp]),
         "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
         "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 8 + [i32] * 8 + [vp]),
         "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, vp, i32, vp]),

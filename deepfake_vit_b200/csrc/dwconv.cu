@@ -12,6 +12,7 @@
 // Bound: HBM (read C*H*W + write C*Ho*Wo elements per image), with the 5x5 layers close to
 // the FP32-FMA limit (25 FMA per output).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -314,7 +315,12 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
   const int* Ls = S == 1 ? Ls1 : Ls2;
   const int nL = S == 1 ? 3 : 1;
   double best = -1.0;
+  // tuning aid: DFV_DW_FORCE="L,TW,TH,CB" (0 = free) restricts the search for stride-1 layers
+  int fL = 0, fTW = 0, fTH = 0, fCB = 0;
+  if (const char* e = getenv("DFV_DW_FORCE")) sscanf(e, "%d,%d,%d,%d", &fL, &fTW, &fTH, &fCB);
+  if (S != 1) fL = fTW = fTH = fCB = 0;
   for (int cb = 8; cb <= cb_cap; cb += 8) {
+    if (fCB && cb != fCB) continue;
     // a chunk width that does not divide C is allowed for the full-width chunk only (TMA zero-fills the missing
     // channels of the last chunk; its threads are masked): 8 channel groups = one 128-byte shared-memory row per
     // pixel, the only width whose quarter-warp vector loads never collide on a bank
@@ -324,12 +330,15 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
     const double banks = (cb * ts == 128) ? 1.0 : (cb * ts > 64 ? 0.8 : 0.65);
     for (int li = 0; li < nL; ++li) {
       const int L = Ls[li];
+      if (fL && L != fL) continue;
       for (int strips = 1; strips * L <= 48; ++strips) {
         const int TW = strips * L;
+        if (fTW && TW != fTW) continue;
         if (TW - L >= p.Wo) break;                 // a whole strip beyond the image: never better
         const int per_row = G * strips;
         if (per_row > 256) break;
         for (int TH = 1; TH <= 16 && TH - 1 < p.Ho; ++TH) {
+          if (fTH && TH != fTH) continue;
           if (S == 2) {   // stride-2 layers (four of them): the hand-picked 16 x 8 tile with the widest channel chunk measured 4.5-4.9 TB/s
             int cbw = 8;
             for (int q = 8; q <= cb_cap; q += 8) if (C % q == 0) cbw = q;

@@ -95,6 +95,17 @@ template <> struct Raw8<float> {
 };
 template <typename T> struct Unroll { static constexpr int U = sizeof(T) == 2 ? 4 : 2; };
 
+// cp.async (LDGSTS) staging for the compute-heavy streams: every thread owns private 16-byte shared-memory slots
+// that it fills for the NEXT round while it computes the current one, so the memory system always has
+// U x (tensors) requests per thread in flight (plain loads drained during the ~17-instruction-per-element math
+// and the kernels sat at ~45% of the copy bandwidth).  No block barrier: a thread only reads its own slots.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+constexpr int kPipeU = 4;
+
 // ------------------------------------------------------------------------------------ bn_stats
 // Per-CTA column sums -> one partial row [2C] per CTA, finished (in double) by bn_stats_finalize_kernel.
 template <typename T>
@@ -227,45 +238,79 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
         sc[e] = gamma ? gamma[c] * is : is;
         sh[e] = (beta ? beta[c] : 0.f) - (mean ? mean[c] : 0.f) * sc[e];
       }
-      for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
-        Raw8<T> x[U], rr[U];
+      auto body = [&](const Raw8<T>& xi, const Raw8<T>& ri, size_t off) {
+        float v[8];
+        xi.unpack(v);
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-          const long long ri = r + (long long)i * m.rpp;
-          if (ri < r1) {
-            const size_t off = img + (size_t)ri * C + cv * 8;
-            x[i].load(raw + off);
-            if (residual) rr[i].load(residual + off);
-          }
+        for (int e = 0; e < 8; ++e) v[e] = act_fwd<kFast>(fmaf(v[e], sc[e], sh[e]), act);
+        if (mask) {
+          float mk[8];
+          load8(mask + off, mk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= mk[e];
         }
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-          const long long ri = r + (long long)i * m.rpp;
-          if (ri < r1) {
-            const size_t off = img + (size_t)ri * C + cv * 8;
-            float v[8];
-            x[i].unpack(v);
+        for (int e = 0; e < 8; ++e) ps[e] += v[e];
+        if (rowscale) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = act_fwd<kFast>(fmaf(v[e], sc[e], sh[e]), act);
-            if (mask) {
-              float mk[8];
-              load8(mask + off, mk);
+          for (int e = 0; e < 8; ++e) v[e] *= rs;
+        }
+        if (residual) {
+          float q[8];
+          ri.unpack(q);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] *= mk[e];
+          for (int e = 0; e < 8; ++e) v[e] += q[e];
+        }
+        store8(out + off, v);
+      };
+      if constexpr (sizeof(T) == 2) {
+        extern __shared__ uint4 stage[];   // [2 buffers][kPipeU rows][2 tensors][kNT threads]
+        auto slot = [&](int buf, int i, int t) { return stage + ((buf * kPipeU + i) * 2 + t) * kNT + threadIdx.x; };
+        auto prefetch = [&](long long r, int buf) {
+#pragma unroll
+          for (int i = 0; i < kPipeU; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) {
+              const size_t off = img + (size_t)ri * C + cv * 8;
+              cp_async16(slot(buf, i, 0), raw + off);
+              if (residual) cp_async16(slot(buf, i, 1), residual + off);
             }
+          }
+          cp_async_commit();
+        };
+        long long r = r0 + m.row_l;
+        int buf = 0;
+        prefetch(r, 0);
+        for (; r < r1; r += (long long)kPipeU * m.rpp, buf ^= 1) {
+          prefetch(r + (long long)kPipeU * m.rpp, buf ^ 1);
+          cp_async_wait1();
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ps[e] += v[e];
-            if (rowscale) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] *= rs;
+          for (int i = 0; i < kPipeU; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) {
+              Raw8<T> xi, qi;
+              xi.r = *slot(buf, i, 0);
+              if (residual) qi.r = *slot(buf, i, 1); else qi.zero();
+              body(xi, qi, img + (size_t)ri * C + cv * 8);
             }
-            if (residual) {
-              float q[8];
-              rr[i].unpack(q);
+          }
+        }
+      } else {
+        for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
+          Raw8<T> x[U], rr[U];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] += q[e];
+          for (int i = 0; i < U; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) {
+              const size_t off = img + (size_t)ri * C + cv * 8;
+              x[i].load(raw + off);
+              if (residual) rr[i].load(residual + off); else rr[i].zero();
             }
-            store8(out + off, v);
+          }
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) body(x[i], rr[i], img + (size_t)ri * C + cv * 8);
           }
         }
       }
@@ -325,41 +370,75 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
 #pragma unroll
         for (int e = 0; e < 8; ++e) gt[e] *= rs;
       }
-      for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
-        Raw8<T> gx[U], xx[U];
+      auto body = [&](const Raw8<T>& gxi, const Raw8<T>& xxi, size_t off) {
+        float gv[8], x[8];
+        gxi.unpack(gv);
+        xxi.unpack(x);
+        float mk[8];
+        if (mask) load8(mask + off, mk);
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-          const long long ri = r + (long long)i * m.rpp;
-          if (ri < r1) {
-            const size_t off = img + (size_t)ri * C + cv * 8;
-            gx[i].load(g + off);
-            xx[i].load(raw + off);
+        for (int e = 0; e < 8; ++e) {
+          float gi;
+          if constexpr (kGate) gi = fmaf(gv[e], gt[e], dp[e]);
+          else gi = gv[e] * rs;
+          if (mask) gi *= mk[e];
+          const float xh = fmaf(x[e], is[e], nm[e]);
+          const float u = fmaf(xh, ga[e], be[e]);
+          const float d = gi * act_grad<sizeof(T) == 2>(u, act);
+          gv[e] = d;
+          acc[e] += d;
+          acc[8 + e] = fmaf(d, xh, acc[8 + e]);
+        }
+        store8(du + off, gv);
+      };
+      if constexpr (sizeof(T) == 2) {
+        extern __shared__ uint4 stage[];   // [2 buffers][kPipeU rows][2 tensors][kNT threads]
+        auto slot = [&](int buf, int i, int t) { return stage + ((buf * kPipeU + i) * 2 + t) * kNT + threadIdx.x; };
+        auto prefetch = [&](long long r, int buf) {
+#pragma unroll
+          for (int i = 0; i < kPipeU; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) {
+              const size_t off = img + (size_t)ri * C + cv * 8;
+              cp_async16(slot(buf, i, 0), g + off);
+              cp_async16(slot(buf, i, 1), raw + off);
+            }
+          }
+          cp_async_commit();
+        };
+        long long r = r0 + m.row_l;
+        int buf = 0;
+        prefetch(r, 0);
+        for (; r < r1; r += (long long)kPipeU * m.rpp, buf ^= 1) {
+          prefetch(r + (long long)kPipeU * m.rpp, buf ^ 1);   // rows >= r1 are skipped inside; the (empty) group is still committed
+          cp_async_wait1();
+#pragma unroll
+          for (int i = 0; i < kPipeU; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) {
+              Raw8<T> gxi, xxi;
+              gxi.r = *slot(buf, i, 0);
+              xxi.r = *slot(buf, i, 1);
+              body(gxi, xxi, img + (size_t)ri * C + cv * 8);
+            }
           }
         }
+      } else {
+        for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
+          Raw8<T> gx[U], xx[U];
 #pragma unroll
-        for (int i = 0; i < U; ++i) {
-          const long long ri = r + (long long)i * m.rpp;
-          if (ri < r1) {
-            const size_t off = img + (size_t)ri * C + cv * 8;
-            float gv[8], x[8];
-            gx[i].unpack(gv);
-            xx[i].unpack(x);
-            float mk[8];
-            if (mask) load8(mask + off, mk);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float gi;
-              if constexpr (kGate) gi = fmaf(gv[e], gt[e], dp[e]);
-              else gi = gv[e] * rs;
-              if (mask) gi *= mk[e];
-              const float xh = fmaf(x[e], is[e], nm[e]);
-              const float u = fmaf(xh, ga[e], be[e]);
-              const float d = gi * act_grad<sizeof(T) == 2>(u, act);
-              gv[e] = d;
-              acc[e] += d;
-              acc[8 + e] = fmaf(d, xh, acc[8 + e]);
+          for (int i = 0; i < U; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) {
+              const size_t off = img + (size_t)ri * C + cv * 8;
+              gx[i].load(g + off);
+              xx[i].load(raw + off);
             }
-            store8(du + off, gv);
+          }
+#pragma unroll
+          for (int i = 0; i < U; ++i) {
+            const long long ri = r + (long long)i * m.rpp;
+            if (ri < r1) body(gx[i], xx[i], img + (size_t)ri * C + cv * 8);
           }
         }
       }
@@ -741,13 +820,20 @@ int dfv_bn_act_fwd(const void* raw, const float* mean, const float* invstd, cons
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, (double)B * rows_per_image * C * dtype_size(dtype) * (residual ? 3.0 : 2.0), 8.0 * B * rows_per_image * C, st);
-  if (dtype == DFV_BF16)
-    bn_act_kernel<__nv_bfloat16, true><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act, rowscale,
-                                                           (const __nv_bfloat16*)residual, mask, (__nv_bfloat16*)out,
-                                                           pool_partial, rows_per_image, C, rpc);
-  else
+  if (dtype == DFV_BF16) {
+    constexpr int kStage = 2 * kPipeU * 2 * kNT * 16;
+    static thread_local bool configured = false;
+    if (!configured) {
+      DFV_CUDA(cudaFuncSetAttribute(bn_act_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStage));
+      configured = true;
+    }
+    bn_act_kernel<__nv_bfloat16, true><<<grid, kNT, kStage, st>>>((const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act, rowscale,
+                                                                (const __nv_bfloat16*)residual, mask, (__nv_bfloat16*)out,
+                                                                pool_partial, rows_per_image, C, rpc);
+  } else {
     bn_act_kernel<float, false><<<grid, kNT, 0, st>>>((const float*)raw, mean, invstd, gamma, beta, act, rowscale,
                                                     (const float*)residual, mask, (float*)out, pool_partial, rows_per_image, C, rpc);
+  }
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -765,16 +851,22 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 12.0 * B * rows_per_image * C, st);
   const bool gated = gate != nullptr || dpool != nullptr;
-#define ABB(T_, G_, U_, M_)                                                                                                         \
-  act_bn_bwd_kernel<T_, G_, U_, M_><<<grid, kNT, 0, st>>>((const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act, (const T_*)gate, \
-                                                         dpool, inv_hw, rowscale, mask, (T_*)du, ws, rows_per_image, C, rpc)
-  const int variant = (debug_flags() >> 8) & 3;   // tuning aid: DFV_DEBUG_FLAGS bits 8-9
+#define ABB(T_, G_, U_, M_, SMEM_)                                                                                                   \
+  do {                                                                                                                              \
+    static thread_local bool configured = false;                                                                                    \
+    if (SMEM_ > 0 && !configured) {                                                                                                 \
+      DFV_CUDA(cudaFuncSetAttribute(act_bn_bwd_kernel<T_, G_, U_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_));        \
+      configured = true;                                                                                                            \
+    }                                                                                                                               \
+    act_bn_bwd_kernel<T_, G_, U_, M_><<<grid, kNT, SMEM_, st>>>((const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act,       \
+                                                               (const T_*)gate, dpool, inv_hw, rowscale, mask, (T_*)du, ws,        \
+                                                               rows_per_image, C, rpc);                                            \
+  } while (0)
+  constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;   // cp.async staging of the bf16 kernels
   if (dtype == DFV_BF16) {
-    if (variant == 1) { if (gated) ABB(__nv_bfloat16, true, 2, 3); else ABB(__nv_bfloat16, false, 2, 3); }
-    else if (variant == 2) { if (gated) ABB(__nv_bfloat16, true, 8, 1); else ABB(__nv_bfloat16, false, 8, 1); }
-    else { if (gated) ABB(__nv_bfloat16, true, 4, 2); else ABB(__nv_bfloat16, false, 4, 2); }
+    if (gated) ABB(__nv_bfloat16, true, 4, 2, kStageBytes); else ABB(__nv_bfloat16, false, 4, 2, kStageBytes);
   } else {
-    if (gated) ABB(float, true, 2, 2); else ABB(float, false, 2, 2);
+    if (gated) ABB(float, true, 2, 2, 0); else ABB(float, false, 2, 2, 0);
   }
 #undef ABB
   DFV_LAUNCH_CHECK();

@@ -15,6 +15,7 @@ order, default initialisation and state_dict layout are exactly the reference's)
 their `forward`s is ever used.  All arithmetic happens in libdfvit through one C call.
 """
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -166,6 +167,43 @@ class DeepfakeFeatureExtractor(nn.Module):
         else:
             self.attention = None
 
+    # ---- the reference's public side APIs (feature_extractor.py:74-178), eval mode, computed by the owning model's
+    # ---- libdfvit forward (this module itself only holds parameters)
+    def _model(self):
+        owner = getattr(self, "_owner", None)
+        m = owner() if owner is not None else None
+        if m is None:
+            raise RuntimeError("DeepfakeFeatureExtractor is a parameter holder; use it through DeepfakeDetectionModel")
+        return m
+
+    def forward(self, images, landmarks=None, return_attention=False):
+        """-> (features (B, 1792), attention_map (B, 1, 7, 7) | None)  (feature_extractor.py:74-117; the reference
+        renders the returned map on a hard-coded 7x7 grid whatever the real feature size is, :100-103)."""
+        m = self._model()
+        assert not m.training, "feature_extractor(...) is the eval-mode side API; train through DeepfakeDetectionModel.forward"
+        _, feats, _, _ = m._infer(images, landmarks)
+        amap = None
+        if return_attention and landmarks is not None and self.use_attention and self.attention is not None \
+                and getattr(self.attention, "use_landmark", False):
+            amap = self.attention.landmark_attn._create_attention_map(landmarks, (7, 7), images.device,
+                                                                      group=int(m.landmark_max_group))
+        return feats, amap
+
+    def extract_multi_scale_features(self, images, landmarks=None):
+        """{'reduction_2', 'reduction_4', 'reduction_5'}: pooled outputs of blocks 5 / 10 / 21 (efficientnet.py:110-118),
+        'final': the attended features (feature_extractor.py:119-154)."""
+        m = self._model()
+        assert not m.training
+        _, feats, _, taps = m._infer(images, landmarks, taps=True)
+        out = {name: ops.global_avg_pool(taps[1 + blk]) for name, blk in (("reduction_2", 5), ("reduction_4", 10), ("reduction_5", 21))}
+        out["final"] = feats
+        return out
+
+    def get_embedding(self, images, landmarks=None, normalize=True):
+        """L2-normalised features (feature_extractor.py:156-178)."""
+        feats, _ = self.forward(images, landmarks)
+        return ops.l2_normalize(feats.contiguous()) if normalize else feats
+
 
 class _TrainState:
     """What one train-mode forward leaves behind for its backward (arena = saved activations)."""
@@ -212,6 +250,7 @@ class DeepfakeDetectionModel(nn.Module):
         if feature_extractor_config is None:   # top-level `pretrained` ignored otherwise (:210-218)
             feature_extractor_config = {"pretrained": pretrained, "use_attention": True}
         self.feature_extractor = DeepfakeFeatureExtractor(**feature_extractor_config)
+        object.__setattr__(self.feature_extractor, "_owner", weakref.ref(self))   # side APIs run this model's forward
         layers, d = [], self.feature_extractor.feature_dim
         for h in classifier_hidden_dims:
             layers += [_Linear(d, h), _BN1d(h), nn.ReLU(inplace=True), nn.Dropout(dropout_rate)]
@@ -567,6 +606,22 @@ class DeepfakeDetectionModel(nn.Module):
     def predict(self, images, landmarks=None, return_probs=True):
         logits, _ = self.forward(images, landmarks)
         return torch.softmax(logits, dim=1) if return_probs else logits
+
+    @torch.no_grad()
+    def score_clips(self, images, landmarks=None, frames_per_clip: int = 32, threshold: float = 0.5):
+        """Video-frame scoring (BASELINE.json configs[3]; task.ipynb:434-442 calls the model once per file): the batch
+        holds whole clips of `frames_per_clip` consecutive frames; the landmark heat-map normaliser group is the clip
+        (== one reference call per clip).  Returns {'mean_logits' (n_clips, 2), 'fake_prob' (n_clips,) = mean
+        softmax[:, 1], 'labels' (n_clips,) = fake_prob >= threshold}."""
+        assert not self.training and images.shape[0] % frames_per_clip == 0
+        prev = self.landmark_max_group
+        self.landmark_max_group = frames_per_clip
+        try:
+            logits, _, _, _ = self._infer(images, landmarks)
+        finally:
+            self.landmark_max_group = prev
+        mean_logits, prob, labels = ops.clip_aggregate(logits.contiguous(), frames_per_clip, threshold)
+        return {"mean_logits": mean_logits, "fake_prob": prob, "labels": labels}
 
     @torch.no_grad()
     def forward_with_taps(self, images, landmarks=None):

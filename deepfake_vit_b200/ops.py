@@ -306,3 +306,32 @@ def dropout_mask(shape, p, seed, device):
     out = torch.empty(shape, device=device, dtype=torch.float32)
     check(lib.dfv_dropout_mask(_f32(out), out.numel(), p, seed, _stream()))
     return out
+
+
+# ------------------------------------------------------------------ side operators
+def clip_aggregate(logits, frames_per_clip, threshold=0.5):
+    """Video scoring rule of task.ipynb:434-442 over consecutive groups of `frames_per_clip` frames:
+    returns (mean_logits [n_clips, n_classes], fake_prob [n_clips] = mean softmax[:, 1], labels [n_clips] int32)."""
+    B, nc = logits.shape
+    assert B % frames_per_clip == 0, "batch must hold whole clips"
+    n = B // frames_per_clip
+    dev = logits.device
+    mean_logits = torch.empty(n, nc, device=dev, dtype=torch.float32)
+    prob = torch.empty(n, device=dev, dtype=torch.float32)
+    labels = torch.empty(n, device=dev, dtype=torch.int32)
+    check(lib.dfv_clip_aggregate(_f32(logits), n, frames_per_clip, nc, _f32(mean_logits), _f32(prob), _ptr(labels), threshold, _stream()))
+    return mean_logits, prob, labels
+
+
+def global_avg_pool(x_nhwc):
+    """[B, H, W, C] (fp32 / bf16) -> [B, C] fp32 mean over positions."""
+    B, H, W, C_ = x_nhwc.shape
+    out = torch.empty(B, C_, device=x_nhwc.device, dtype=torch.float32)
+    check(lib.dfv_global_avg_pool(_ptr(x_nhwc), dtype_code(x_nhwc.dtype), _f32(out), B, H * W, C_, _stream()))
+    return out
+
+
+def l2_normalize(x, eps=1e-12):
+    y = torch.empty_like(x)
+    check(lib.dfv_l2_normalize(_f32(x), _f32(y), x.shape[0], x.shape[1], eps, _stream()))
+    return y

@@ -395,6 +395,36 @@ size_t dfv_train_scratch_bytes(int dtype, int B, int H, int W, const int32_t* he
 int dfv_train_fwd(const dfv_train_args* args, dfv_stream_t stream);
 int dfv_train_bwd(const dfv_train_args* args, dfv_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Operators either side of the hot path.
+ * ---------------------------------------------------------------------------------- */
+
+/* Video-frame scoring rule of the competition notebook (task.ipynb:434-442): the batch holds n_clips groups of
+ * frames_per_clip consecutive frames; per clip: mean logit [n_clips][n_classes], mean softmax(logits)[:, 1]
+ * (fake_prob) and label = fake_prob >= threshold.  All fp32 / int32 device buffers. */
+int dfv_clip_aggregate(const float* logits, int n_clips, int frames_per_clip, int n_classes, float* mean_logits,
+                       float* fake_prob, int* labels, float threshold, dfv_stream_t stream);
+
+/* F.adaptive_avg_pool2d(x, 1).flatten(1) of an NHWC map -> fp32 [B][C]
+ * (DeepfakeFeatureExtractor.extract_multi_scale_features, feature_extractor.py:119-154). */
+int dfv_global_avg_pool(const void* x, int dtype, float* out, int B, long long rows_per_image, int C, dfv_stream_t stream);
+
+/* F.normalize(x, p=2, dim=1) (DeepfakeFeatureExtractor.get_embedding, feature_extractor.py:156-178). */
+int dfv_l2_normalize(const float* x, float* y, int B, int D, float eps, dfv_stream_t stream);
+
+/* The optimizer step of the reference training loop (trainer.py:158-167; scripts/train.py:96-102):
+ * torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.AdamW, over FLAT fp32 buffers of n
+ * elements (parameters, gradients, exp_avg, exp_avg_sq).  grad_scale multiplies the gradients first (1/N of a
+ * summed all-reduce, or a loss-scale inverse); max_norm <= 0 disables clipping; step is 1-based.
+ * sqnorm_ws: one double of device scratch; total_norm_out: optional device float (pre-clip global norm). */
+int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                        double* sqnorm_ws, double max_norm, double grad_scale, double lr, double beta1, double beta2,
+                        double eps, double weight_decay, long long step, float* total_norm_out, dfv_stream_t stream);
+
+/* Debug / documentation aid (host only): the depthwise tile plan chosen for a layer.
+ * out[0..9] = CB, L, TW, TH, threads, smem bytes, tiles_w, tiles_h, pool parts, grid. */
+int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out);
+
 #ifdef __cplusplus
 }
 #endif
