@@ -79,24 +79,24 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restri
 
 // sum of squares of the flat gradient buffer: per-CTA partial -> one double atomic
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
-  __shared__ float red[8];
-  float s = 0.f;
+  __shared__ double red[8];
+  double s = 0.0;       // double accumulation: the clip coefficient inherits this sum's relative error
   const long long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = g4[i];
-    s = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s))));
+    s += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
   }
   if (blockIdx.x == 0)
-    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
-  s = warp_sum(s);
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += (double)(g[i] * g[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float t = red[threadIdx.x];
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
-    if (threadIdx.x == 0) atomicAdd(out, (double)t);
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
   }
 }
 

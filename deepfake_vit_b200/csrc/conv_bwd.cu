@@ -120,6 +120,114 @@ __global__ void __launch_bounds__(256) dw_dgrad_kernel(const T* __restrict__ g, 
   }
 }
 
+// ------------------------------------------------------------------------------------ dw_dgrad, stride 2 (TMA-tiled)
+// dx[b][hi][wi][c] = sum over (kh, kw) with (hi + pad - kh) and (wi + pad - kw) even of
+//                    g[b][(hi + pad - kh) / 2][(wi + pad - kw) / 2][c] * w[kh][kw][c]
+// Persistent CTAs over contiguous (image, tile) ranges of one channel chunk; the g tile that a TH x TW tile of dx
+// needs ((TH + K - 1) / 2 + 1 rows) arrives by a double-buffered 4-D TMA load whose out-of-bounds zero fill supplies
+// the "no contribution" border.  thread = (8-channel group, strip of 4 dx pixels, row); only the parity-matching
+// taps are visited.  Replaces the per-pixel gather kernel for the four stride-2 layers.
+struct DwDgParams {
+  int C, CB, G;
+  int H, W, Ho, Wo;
+  int TH, TW, THg, TWg;
+  int tiles_w, tiles_h;
+  int chunks, ctas_per_chunk;
+  long long per_chunk, tiles_per_cta;
+  int pad;
+};
+
+template <typename T, int K>
+__global__ void __launch_bounds__(256, 2) dw_dgrad_s2_kernel(const __grid_constant__ CUtensorMap tm_g, const float* __restrict__ w,
+                                                            T* __restrict__ dx, DwDgParams p) {
+  constexpr int L = 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t g_bytes = (size_t)p.THg * p.TWg * p.CB * sizeof(T);
+  const size_t g_stride = (g_bytes + 127) / 128 * 128;
+  float* wsm = reinterpret_cast<float*>(smem_raw + 2 * g_stride);            // [K*K][CB] fp32
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wsm + (size_t)K * K * p.CB);
+
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % p.chunks, slot = blockIdx.x / p.chunks;
+  const int c0 = chunk * p.CB;
+  const int n_tiles = p.tiles_w * p.tiles_h;
+  const long long t_begin = (long long)slot * p.tiles_per_cta;
+  const long long t_end = min(t_begin + p.tiles_per_cta, p.per_chunk);
+
+  // first g row / column a tile starting at dx row h0 / column w0 can touch (floor division, may be negative)
+  auto g_lo = [&](int x0) { const int a = x0 + p.pad - (K - 1); return a >= 0 ? a / 2 : -((1 - a) / 2); };
+  auto issue = [&](long long t, int buf) {
+    const int tw = (int)(t % p.tiles_w), th = (int)((t / p.tiles_w) % p.tiles_h), b = (int)(t / n_tiles);
+    mbar_expect_tx(&mbar[buf], (uint32_t)g_bytes);
+    tma_load_4d(smem_raw + buf * g_stride, &tm_g, &mbar[buf], c0, g_lo(tw * p.TW), g_lo(th * p.TH), b);
+  };
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+    if (t_begin < t_end) issue(t_begin, 0);
+  }
+  for (int i = tid; i < K * K * p.CB; i += blockDim.x) {
+    const int c = c0 + i % p.CB;
+    wsm[i] = c < p.C ? w[(size_t)(i / p.CB) * p.C + c] : 0.f;
+  }
+  __syncthreads();
+
+  const int G = p.G, strips = p.TW / L;
+  const int g = tid % G, j = (tid / G) % strips, r = tid / (G * strips);
+  const bool active = r < p.TH && c0 + g * 8 < p.C;
+
+  int it = 0;
+  for (long long t = t_begin; t < t_end; ++t, ++it) {
+    const int buf = it & 1;
+    if (tid == 0 && t + 1 < t_end) issue(t + 1, buf ^ 1);
+    const int tw = (int)(t % p.tiles_w), th = (int)((t / p.tiles_w) % p.tiles_h), b = (int)(t / n_tiles);
+    const int h0 = th * p.TH, w0 = tw * p.TW;
+    const int hi = h0 + r, wi0 = w0 + j * L;
+    mbar_wait(&mbar[buf], (it >> 1) & 1, 22);
+    if (active && hi < p.H && wi0 < p.W) {
+      const T* gt = reinterpret_cast<const T*>(smem_raw + buf * g_stride) + g * 8;
+      const int glo_h = g_lo(h0), glo_w = g_lo(w0);
+      float acc[L][8];
+#pragma unroll
+      for (int l = 0; l < L; ++l)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[l][e] = 0.f;
+      const int kh0 = (hi + p.pad) & 1;          // taps with (hi + pad - kh) even
+#pragma unroll
+      for (int th2 = 0; th2 < (K + 1) / 2; ++th2) {
+        const int kh = kh0 + 2 * th2;
+        if (kh < K) {
+          const int ho_t = ((hi + p.pad - kh) >> 1) - glo_h;       // tile-local g row (the numerator is even)
+          const T* grow = gt + (size_t)ho_t * p.TWg * p.CB;
+#pragma unroll
+          for (int l = 0; l < L; ++l) {
+            const int wi = wi0 + l;
+            const int kw0 = (wi + p.pad) & 1;
+#pragma unroll
+            for (int tw2 = 0; tw2 < (K + 1) / 2; ++tw2) {
+              const int kw = kw0 + 2 * tw2;
+              if (kw < K) {
+                const int wo_t = ((wi + p.pad - kw) >> 1) - glo_w;
+                float gv[8], wv[8];
+                load8(grow + (size_t)wo_t * p.CB, gv);
+                load8(wsm + (size_t)(kh * K + kw) * p.CB + g * 8, wv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[l][e] = fmaf(gv[e], wv[e], acc[l][e]);
+              }
+            }
+          }
+        }
+      }
+      T* out = dx + (((size_t)b * p.H + hi) * p.W + wi0) * p.C + c0 + g * 8;
+#pragma unroll
+      for (int l = 0; l < L; ++l)
+        if (wi0 + l < p.W) store8(out + (size_t)l * p.C, acc[l]);
+    }
+    __syncthreads();   // everyone is done with tile[buf] before it is refilled
+  }
+}
+
 // ------------------------------------------------------------------------------------ dw_wgrad
 // dw[kh][kw][c] = sum over (b, ho, wo) of g[b,ho,wo,c] * x[b, ho*S - pad + kh, wo*S - pad + kw, c]
 // Persistent CTAs over (image, tile) for ONE channel chunk, 2-deep TMA pipeline of an x tile (with halo;
@@ -373,10 +481,55 @@ int dfv_dwconv_dgrad(const void* g, const float* w_kkc, void* dx, int dtype, int
   const int Ho = (H + pad_lo + pad_hi - kernel) / stride + 1, Wo = (W + pad_lo + pad_hi - kernel) / stride + 1;
   DFV_REQUIRE(Ho > 0 && Wo > 0, "dfv_dwconv_dgrad: bad shape");
   cudaStream_t st = as_stream(stream);
-  const long long total = (long long)B * H * W * (C / 8);
-  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms());
   const double es = (double)dtype_size(dtype);
   ProfScope prof(PK_DWCONV_BWD, es * ((double)B * H * W * C + (double)B * Ho * Wo * C), 2.0 * kernel * kernel * (double)B * Ho * Wo * C, st);
+  if (stride == 2 && (kernel == 3 || kernel == 5)) {
+    DwDgParams p;
+    p.C = C; p.H = H; p.W = W; p.Ho = Ho; p.Wo = Wo; p.pad = pad_lo;
+    const int cap = dtype == DFV_BF16 ? 64 : 32;
+    p.CB = 8;
+    for (int cb = 8; cb <= cap; cb += 8)
+      if (C % cb == 0) p.CB = cb;
+    p.G = p.CB / 8;
+    p.TW = 16;
+    p.TH = std::max(1, std::min(256 / (p.G * (p.TW / 4)), 16));
+    p.THg = (p.TH + kernel - 1) / 2 + 1;
+    p.TWg = (p.TW + kernel - 1) / 2 + 1;
+    p.tiles_w = (W + p.TW - 1) / p.TW;
+    p.tiles_h = (H + p.TH - 1) / p.TH;
+    p.chunks = (C + p.CB - 1) / p.CB;
+    p.per_chunk = (long long)B * p.tiles_w * p.tiles_h;
+    long long cpc = std::max<long long>(1, (long long)num_sms() * 2 / p.chunks);
+    cpc = std::min(cpc, p.per_chunk);
+    p.tiles_per_cta = (p.per_chunk + cpc - 1) / cpc;
+    cpc = (p.per_chunk + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    p.ctas_per_chunk = (int)cpc;
+    const size_t g_stride = align_up((size_t)p.THg * p.TWg * p.CB * dtype_size(dtype), 128);
+    const size_t smem = 2 * g_stride + (size_t)kernel * kernel * p.CB * 4 + 64;
+    CUtensorMap tmg;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)C * dtype_size(dtype), (uint64_t)Wo * C * dtype_size(dtype), (uint64_t)Ho * Wo * C * dtype_size(dtype)};
+    uint32_t box[4] = {(uint32_t)p.CB, (uint32_t)p.TWg, (uint32_t)p.THg, 1};
+    DFV_TRY(make_tensor_map(&tmg, dtype, 4, g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+    DFV_TRY(init_timeout_word_tu());
+    const unsigned grid = (unsigned)(cpc * p.chunks);
+#define DGL(T_, K_)                                                                                                              \
+  do {                                                                                                                           \
+    static thread_local bool configured = false;                                                                                 \
+    if (!configured) {                                                                                                           \
+      DFV_CUDA(cudaFuncSetAttribute(dw_dgrad_s2_kernel<T_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));       \
+      configured = true;                                                                                                         \
+    }                                                                                                                            \
+    dw_dgrad_s2_kernel<T_, K_><<<grid, 256, smem, st>>>(tmg, w_kkc, (T_*)dx, p);                                                 \
+  } while (0)
+    if (dtype == DFV_BF16) { if (kernel == 3) DGL(__nv_bfloat16, 3); else DGL(__nv_bfloat16, 5); }
+    else { if (kernel == 3) DGL(float, 3); else DGL(float, 5); }
+#undef DGL
+    DFV_LAUNCH_CHECK();
+    return DFV_OK;
+  }
+  const long long total = (long long)B * H * W * (C / 8);
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms());
   if (dtype == DFV_BF16)
     dw_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, w_kkc, (__nv_bfloat16*)dx, B, H, W, C, Ho, Wo, kernel, stride, pad_lo);
   else

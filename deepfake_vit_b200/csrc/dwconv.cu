@@ -359,7 +359,7 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
           const double busy = (double)TH / (rounds * rpr);              // rows actually computed per round slot
           const double threads = std::min(1.0, nt / 256.0) * ((nt % 32 == 0) ? 1.0 : (double)nt / ((nt + 31) / 32 * 32));
           const double halo = (double)(TH * S) * (TW * S) / ((double)THI * TWI);
-          const double regs = (K == 5 && L == 8) ? 0.9 : 1.0;          // 64 accumulators + 5 weight vectors: spills
+          const double regs = L == 8 ? 0.9 : 1.0;                      // 64 accumulators + a row of weight vectors: 128 registers, spills
           const double per_tile = (double)TH * TW / (TH * TW + 24.0);  // fixed per-tile cost (barrier, TMA issue)
           const double seg = std::min(1.0, (double)cb * ts / 128.0);   // contiguous bytes per pixel the TMA box fetches
           const double score = cover * busy * threads * (0.6 + 0.4 * halo) * regs * per_tile * (0.3 + 0.7 * seg) * waste * banks;

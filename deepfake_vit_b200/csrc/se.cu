@@ -13,11 +13,14 @@ namespace dfv {
 // per late layer walking both FC matrices from L2 with a single CTA's worth of loads in flight.
 constexpr int kSeCluster = 8;
 
-template <int IMG, typename GT>
+// kTrain: the expand weight arrives in torch layout [C][sq] (not transposed) and the kernel also saves what the
+// backward pass needs: pooled [B][C], h1 [B][sq] (pre-swish) and the fp32 gate.
+template <int IMG, typename GT, bool kTrain>
 __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
     se_gate_kernel(const float* __restrict__ partial, int parts, float inv_hw, const float* __restrict__ w1,
                    const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
-                   GT* __restrict__ gate, int B, int C, int sq) {
+                   GT* __restrict__ gate, int B, int C, int sq, float* __restrict__ pooled_out,
+                   float* __restrict__ h1_out, float* __restrict__ gate_f32) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float sm[];
@@ -49,7 +52,12 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
 #pragma unroll
     for (int u = 0; u < PU; ++u) {
       const int i = i0 + u * blockDim.x;
-      if (i < IMG * C) pooled[i] = s[u] * inv_hw;
+      if (i < IMG * C) {
+        pooled[i] = s[u] * inv_hw;
+        if constexpr (kTrain) {
+          if (rank == 0 && b0 + i / C < B) pooled_out[(size_t)(b0 + i / C) * C + i % C] = s[u] * inv_hw;
+        }
+      }
     }
   }
   __syncthreads();
@@ -93,6 +101,9 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
       if (lane == 0) {
         v += b1[j];
         mine[im * jper + (j - j0)] = v * sigmoid_exact(v);
+        if constexpr (kTrain) {
+          if (b0 + im < B) h1_out[(size_t)(b0 + im) * sq + j] = v;
+        }
       }
     }
   }
@@ -116,7 +127,10 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
     for (int jb = 0; jb < sq; jb += 32) {     // 32 weight loads in flight per thread
       float wv[32];
 #pragma unroll
-      for (int u = 0; u < 32; ++u) wv[u] = jb + u < sq ? __ldg(w2t + (size_t)(jb + u) * C + c) : 0.f;
+      for (int u = 0; u < 32; ++u) {
+        if constexpr (kTrain) wv[u] = jb + u < sq ? __ldg(w2t + (size_t)c * sq + jb + u) : 0.f;   // torch layout [C][sq]
+        else wv[u] = jb + u < sq ? __ldg(w2t + (size_t)(jb + u) * C + c) : 0.f;
+      }
 #pragma unroll
       for (int u = 0; u < 32; ++u) {
         if (jb + u < sq) {
@@ -131,8 +145,39 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
         const float gv = sigmoid_exact(s[im]);
         if constexpr (sizeof(GT) == 2) gate[(size_t)(b0 + im) * C + c] = __float2bfloat16_rn(gv);
         else gate[(size_t)(b0 + im) * C + c] = gv;
+        if constexpr (kTrain) gate_f32[(size_t)(b0 + im) * C + c] = gv;
       }
   }
+}
+
+// shared launcher of the inference and training entry points
+template <bool kTrain>
+static int launch_se(const float* pool_partial, int parts, float inv_hw, const float* w_reduce, const float* b_reduce,
+                     const float* w_expand, const float* b_expand, void* gate, int gate_dtype, int B, int C, int squeeze,
+                     float* pooled, float* h1, float* gate_f32, cudaStream_t st) {
+  const int img = B >= 128 ? 8 : (B >= 16 ? 4 : 1);
+  const int jper = (squeeze + kSeCluster - 1) / kSeCluster;
+  const size_t smem = (size_t)img * ((size_t)C + squeeze + jper) * sizeof(float);
+  DFV_REQUIRE(smem <= 160 * 1024, "squeeze-excite: C + squeeze too large (%d + %d)", C, squeeze);
+  const unsigned grid = (unsigned)((B + img - 1) / img) * kSeCluster;
+#define SE_LAUNCH(IMG_, GT_)                                                                                                  \
+  do {                                                                                                                        \
+    static thread_local bool configured = false;                                                                              \
+    if (!configured) {                                                                                                        \
+      DFV_CUDA(cudaFuncSetAttribute(se_gate_kernel<IMG_, GT_, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+      configured = true;                                                                                                      \
+    }                                                                                                                         \
+    se_gate_kernel<IMG_, GT_, kTrain><<<grid, 256, smem, st>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand, \
+                                                              (GT_*)gate, B, C, squeeze, pooled, h1, gate_f32);               \
+  } while (0)
+  if (gate_dtype == DFV_BF16) {
+    if (img == 8) SE_LAUNCH(8, __nv_bfloat16); else if (img == 4) SE_LAUNCH(4, __nv_bfloat16); else SE_LAUNCH(1, __nv_bfloat16);
+  } else {
+    if (img == 8) SE_LAUNCH(8, float); else if (img == 4) SE_LAUNCH(4, float); else SE_LAUNCH(1, float);
+  }
+#undef SE_LAUNCH
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
 }
 
 }  // namespace dfv
@@ -146,29 +191,24 @@ extern "C" int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_h
   DFV_REQUIRE(pool_partial && w_reduce && b_reduce && w_expand_t && b_expand && gate, "dfv_se_gate_fwd: null pointer");
   DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && parts > 0 && valid_dtype(gate_dtype), "dfv_se_gate_fwd: bad shape / dtype");
   if (debug_flags() & 2) return DFV_OK;
-  const int img = B >= 32 ? 8 : 1;
-  const int jper = (squeeze + kSeCluster - 1) / kSeCluster;
-  const size_t smem = (size_t)img * ((size_t)C + squeeze + jper) * sizeof(float);
-  DFV_REQUIRE(smem <= 160 * 1024, "dfv_se_gate_fwd: C + squeeze too large (%d + %d)", C, squeeze);
   ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * parts * C + (double)B * C + 2.0 * C * squeeze), 4.0 * B * (double)C * squeeze,
                  as_stream(stream));
-  const unsigned grid = (unsigned)((B + img - 1) / img) * kSeCluster;
-#define SE_LAUNCH(IMG_, GT_)                                                                                          \
-  do {                                                                                                                \
-    static thread_local bool configured = false;                                                                      \
-    if (!configured) {                                                                                                \
-      DFV_CUDA(cudaFuncSetAttribute(se_gate_kernel<IMG_, GT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-      configured = true;                                                                                              \
-    }                                                                                                                 \
-    se_gate_kernel<IMG_, GT_><<<grid, 256, smem, as_stream(stream)>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, \
-                                                                     w_expand_t, b_expand, (GT_*)gate, B, C, squeeze); \
-  } while (0)
-  if (gate_dtype == DFV_BF16) {
-    if (img == 8) SE_LAUNCH(8, __nv_bfloat16); else SE_LAUNCH(1, __nv_bfloat16);
-  } else {
-    if (img == 8) SE_LAUNCH(8, float); else SE_LAUNCH(1, float);
-  }
-#undef SE_LAUNCH
-  DFV_LAUNCH_CHECK();
-  return DFV_OK;
+  return launch_se<false>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand_t, b_expand, gate, gate_dtype, B, C, squeeze,
+                          nullptr, nullptr, nullptr, as_stream(stream));
 }
+
+/* Training variant (declared in dfvit.h next to the other training entry points): torch-layout weights, saves pooled / h1 /
+ * fp32 gate for dfv_se_bwd. */
+extern "C" int dfv_se_train_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce, const float* b_reduce,
+                                const float* w_expand, const float* b_expand, void* gate, int gate_dtype, float* pooled, float* h1,
+                                float* gate_f32, int B, int C, int squeeze, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(pool_partial && w_reduce && b_reduce && w_expand && b_expand && gate && pooled && h1 && gate_f32,
+              "dfv_se_train_fwd: null pointer");
+  DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && parts > 0 && valid_dtype(gate_dtype), "dfv_se_train_fwd: bad shape / dtype");
+  ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * parts * C + 3.0 * B * C + 2.0 * C * squeeze), 4.0 * B * (double)C * squeeze,
+                 as_stream(stream));
+  return launch_se<true>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand, gate, gate_dtype, B, C, squeeze, pooled,
+                         h1, gate_f32, as_stream(stream));
+}
+

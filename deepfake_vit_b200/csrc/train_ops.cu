@@ -894,27 +894,6 @@ int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const f
   return DFV_OK;
 }
 
-int dfv_se_train_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce, const float* b_reduce,
-                     const float* w_expand, const float* b_expand, void* gate, int gate_dtype, float* pooled, float* h1,
-                     float* gate_f32, int B, int C, int squeeze, dfv_stream_t stream) {
-  DFV_TRY(check_device());
-  DFV_REQUIRE(pool_partial && w_reduce && b_reduce && w_expand && b_expand && gate && pooled && h1 && gate_f32,
-              "dfv_se_train_fwd: null pointer");
-  DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && parts > 0 && valid_dtype(gate_dtype), "dfv_se_train_fwd: bad shape / dtype");
-  const size_t smem = (size_t)(C + squeeze) * sizeof(float);
-  DFV_REQUIRE(smem <= 48 * 1024, "dfv_se_train_fwd: C + squeeze too large");
-  cudaStream_t st = as_stream(stream);
-  ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * parts * C + 3.0 * B * C + 2.0 * C * squeeze), 4.0 * B * (double)C * squeeze, st);
-  if (gate_dtype == DFV_BF16)
-    se_train_fwd_kernel<__nv_bfloat16><<<B, 512, smem, st>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand,
-                                                          (__nv_bfloat16*)gate, pooled, h1, gate_f32, C, squeeze);
-  else
-    se_train_fwd_kernel<float><<<B, 512, smem, st>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand,
-                                                  (float*)gate, pooled, h1, gate_f32, C, squeeze);
-  DFV_LAUNCH_CHECK();
-  return DFV_OK;
-}
-
 /* SE backward.  da: gradient wrt the gated tensor (d (.) gate), d: the activated depthwise output; both [B][rows][C].
  * Outputs: dpool [B][C] (to be folded into the depthwise-activation gradient: + dpool / HW) and the four
  * parameter gradients in torch layout.  ws: fp32, dfv_se_bwd_ws_floats(). */

@@ -93,14 +93,16 @@ def test_fused_clip_adamw_matches_torch(max_norm):
         assert abs(norm.item() - float(norm_ref)) < 1e-4 * float(norm_ref)
         for p, q in zip(ref_p, our_p):
             assert rel(q.detach(), p.detach()) < 2e-6
+            # moments scale with the clip coefficient, i.e. with each side's fp32 norm reduction order
+            assert rel(our_opt.state[q]["exp_avg"], ref_opt.state[p]["exp_avg"]) < (2e-5 if max_norm else 2e-6)
     # stock-format state_dict: loads into torch.optim.AdamW and back
     sd = our_opt.state_dict()
     ref2_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
     ref2 = torch.optim.AdamW(ref2_p, lr=1e-3, weight_decay=1e-2)
     ref2.load_state_dict(copy.deepcopy(sd))
     for (p, q) in zip(ref_p, ref2_p):
-        assert rel(ref2.state[q]["exp_avg"], ref_opt.state[p]["exp_avg"]) < 2e-6
-        assert rel(ref2.state[q]["exp_avg_sq"], ref_opt.state[p]["exp_avg_sq"]) < 2e-6
+        assert rel(ref2.state[q]["exp_avg"], ref_opt.state[p]["exp_avg"]) < (2e-5 if max_norm else 2e-6)
+        assert rel(ref2.state[q]["exp_avg_sq"], ref_opt.state[p]["exp_avg_sq"]) < (4e-5 if max_norm else 2e-6)
         assert int(ref2.state[q]["step"]) == 4
     our2_p = [torch.nn.Parameter(p.detach().clone().to(DEV)) for p in ref_p]
     our2 = d.FusedAdamW(our2_p, lr=5e-4, weight_decay=0.0, max_grad_norm=max_norm)
