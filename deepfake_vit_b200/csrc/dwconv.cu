@@ -94,8 +94,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
 
 // Activation + pool sum + store of one output pixel (8 channels).  kHalf: the accumulators hold x / 2 (the 1/2
 // of swish(x) = h * tanh(h) + h, h = x / 2, is folded into the staged weights and bias).
-template <typename T, bool kAct, bool kHalf>
-__device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4], T* out) {
+template <typename T, bool kAct, bool kHalf, bool kStats>
+__device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4], float2 psq[4], T* out) {
   if constexpr (kAct && kHalf) {
     uint4 pk;
     uint32_t* pw = &pk.x;
@@ -116,6 +116,10 @@ __device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4],
     for (int j = 0; j < 4; ++j) {
       psum[j].x += o[2 * j];
       psum[j].y += o[2 * j + 1];
+      if constexpr (kStats) {
+        psq[j].x = fmaf(o[2 * j], o[2 * j], psq[j].x);
+        psq[j].y = fmaf(o[2 * j + 1], o[2 * j + 1], psq[j].y);
+      }
     }
     store8(out, o);
   }
@@ -127,10 +131,14 @@ __device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4],
 // runs, so the SE pool sums stay in registers across tiles and are reduced (shared memory, deterministic)
 // only when the image changes.  Image b's partial sums land in slot (cta - first cta touching b); the
 // last CTA of an image zero-fills the unused slots, so the SE-gate kernel simply sums `parts` rows.
-template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB>
+// kStats (training, kAct = false): per-channel sum / sum of squares of the raw conv output, accumulated in registers
+// over the whole kernel and added (double atomics, one per channel per CTA) into stats[2C] -- the BatchNorm
+// batch statistics without a separate pass over the output.
+template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                       T* __restrict__ y, float* __restrict__ pool_partial, DwParams p) {
+                                                       T* __restrict__ y, float* __restrict__ pool_partial,
+                                                       double* __restrict__ stats, DwParams p) {
   constexpr bool kHalf = kFast && kAct && sizeof(T) == 2;
   const int CB = kCB ? kCB : p.CB;     // compile-time for the full-width chunk: shared-memory offsets become immediates
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -192,9 +200,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   constexpr int NI = (L - 1) * S + K;  // input window per kernel row
   const int nth = blockDim.x;
 
-  float2 psum[4];
+  float2 psum[4], psq[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) psum[e] = make_float2(0.f, 0.f);
+  for (int e = 0; e < 4; ++e) psum[e] = psq[e] = make_float2(0.f, 0.f);
 
   int it = 0;
   for (long long t = t_begin; t < t_end; ++t, ++it) {
@@ -241,11 +249,11 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
         T* out = out_tile + out_off;
         if (wrem >= L) {
 #pragma unroll
-          for (int l = 0; l < L; ++l) finish_pixel<T, kAct, kHalf>(acc[l], psum, out + (size_t)l * p.C);
+          for (int l = 0; l < L; ++l) finish_pixel<T, kAct, kHalf, kStats>(acc[l], psum, psq, out + (size_t)l * p.C);
         } else {
 #pragma unroll
           for (int l = 0; l < L; ++l)
-            if (l < wrem) finish_pixel<T, kAct, kHalf>(acc[l], psum, out + (size_t)l * p.C);
+            if (l < wrem) finish_pixel<T, kAct, kHalf, kStats>(acc[l], psum, psq, out + (size_t)l * p.C);
         }
       }
     }
@@ -288,6 +296,35 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
     tw_i = ntw;
     th_i = nth_i;
     b = nb;
+  }
+  if constexpr (kStats) {
+    // CTA reduction of the two statistics (same two-stage scheme as the pool flush), one double atomic per channel
+    const int R = p.red_parts;
+    for (int pass = 0; pass < 2; ++pass) {
+      const float2* v = pass == 0 ? psum : psq;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        red[tid * 8 + 2 * e] = v[e].x;
+        red[tid * 8 + 2 * e + 1] = v[e].y;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < CB * R; idx += nth) {
+        const int o = idx % CB, q = idx / CB;
+        const int gg = o >> 3, e = o & 7;
+        float s = 0.f;
+        for (int u = gg + G * q; u < nth; u += G * R) s += red[u * 8 + e];
+        red2[idx] = s;
+      }
+      __syncthreads();
+      for (int o = tid; o < CB; o += nth) {
+        if (c0 + o < p.C) {
+          float s = 0.f;
+          for (int q = 0; q < R; ++q) s += red2[q * CB + o];
+          atomicAdd(stats + (size_t)pass * p.C + c0 + o, (double)s);
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -406,10 +443,10 @@ static void plan_grid(DwPlan& pl, int B) {
   pl.p.parts = (int)((n + tpc - 2) / tpc + 1);
 }
 
-template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB>
-static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, DwPlan& pl, int B,
+template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats>
+static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, double* stats, DwPlan& pl, int B,
                   cudaStream_t st) {
-  auto kern = dwconv_kernel<T, K, S, L, kFast, kAct, kCB>;
+  auto kern = dwconv_kernel<T, K, S, L, kFast, kAct, kCB, kStats>;
   static thread_local bool configured = false;
   if (!configured) {
     DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -419,22 +456,23 @@ static int launch(const CUtensorMap& tm, const float* w, const float* bias, void
   DFV_TRY(init_timeout_word_tu());
   plan_grid(pl, B);
   const unsigned grid = (unsigned)((long long)pl.p.ctas_per_chunk * pl.chunks);
-  kern<<<grid, pl.p.nthreads, pl.smem, st>>>(tm, w, bias, (T*)y, pool, pl.p);
+  kern<<<grid, pl.p.nthreads, pl.smem, st>>>(tm, w, bias, (T*)y, pool, stats, pl.p);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
 
 template <typename T, bool kFast>
 static int dispatch(int K, int S, int L, int act, const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool,
-                    DwPlan& pl, int B, cudaStream_t st) {
+                    double* stats, DwPlan& pl, int B, cudaStream_t st) {
 #define DW_CASE(k, s, l)                                                                          \
   if (K == k && S == s && L == l) {                                                               \
-    if (sizeof(T) == 2 && pl.p.CB == 64) {                                                        \
-      if (act) return launch<T, k, s, l, kFast, true, 64>(tm, w, bias, y, pool, pl, B, st);       \
-      return launch<T, k, s, l, kFast, false, 64>(tm, w, bias, y, pool, pl, B, st);               \
-    }                                                                                             \
-    if (act) return launch<T, k, s, l, kFast, true, 0>(tm, w, bias, y, pool, pl, B, st);          \
-    return launch<T, k, s, l, kFast, false, 0>(tm, w, bias, y, pool, pl, B, st);                  \
+    if (stats) return launch<T, k, s, l, kFast, false, 0, true>(tm, w, bias, y, pool, stats, pl, B, st);    \
+    if (sizeof(T) == 2 && pl.p.CB == 64) {                                                                  \
+      if (act) return launch<T, k, s, l, kFast, true, 64, false>(tm, w, bias, y, pool, stats, pl, B, st);   \
+      return launch<T, k, s, l, kFast, false, 64, false>(tm, w, bias, y, pool, stats, pl, B, st);           \
+    }                                                                                                       \
+    if (act) return launch<T, k, s, l, kFast, true, 0, false>(tm, w, bias, y, pool, stats, pl, B, st);      \
+    return launch<T, k, s, l, kFast, false, 0, false>(tm, w, bias, y, pool, stats, pl, B, st);              \
   }
   DW_CASE(3, 1, 8) DW_CASE(3, 1, 6) DW_CASE(3, 1, 4) DW_CASE(5, 1, 8) DW_CASE(5, 1, 6) DW_CASE(5, 1, 4)
   DW_CASE(3, 2, 4) DW_CASE(5, 2, 4)
@@ -471,9 +509,8 @@ extern "C" int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int 
   return DFV_OK;
 }
 
-extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, int dtype,
-                              int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act,
-                              dfv_stream_t stream) {
+static int dwconv_entry(const void* x, const float* w, const float* bias, void* y, float* pool_partial, double* stats, int dtype,
+                        int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(x && w && bias && y, "dfv_dwconv_fwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype), "dfv_dwconv_fwd: bad dtype %d", dtype);
@@ -495,6 +532,21 @@ extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, 
   ProfScope prof(PK_DWCONV, ((double)B * H * W * C + (double)B * pl.p.Ho * pl.p.Wo * C) * es,
                  2.0 * kernel * kernel * (double)B * pl.p.Ho * pl.p.Wo * C, as_stream(stream));
   if (dtype == DFV_BF16)
-    return dispatch<__nv_bfloat16, true>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));
-  return dispatch<float, false>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, pl, B, as_stream(stream));
+    return dispatch<__nv_bfloat16, true>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, stats, pl, B, as_stream(stream));
+  return dispatch<float, false>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, stats, pl, B, as_stream(stream));
+}
+
+extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, int dtype,
+                              int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act,
+                              dfv_stream_t stream) {
+  return dwconv_entry(x, w, bias, y, pool_partial, nullptr, dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, act, stream);
+}
+
+/* Training forward: raw depthwise conv (no activation) that also ADDS the per-channel sum and sum of squares of its
+ * output into stats[2C] (double, zeroed by the caller): train-mode BatchNorm statistics without a second pass
+ * (finish with dfv_bn_stats_from_sums). */
+extern "C" int dfv_dwconv_stats_fwd(const void* x, const float* w, const float* bias, void* y, double* stats, int dtype, int B,
+                                    int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream) {
+  DFV_REQUIRE(stats != nullptr, "dfv_dwconv_stats_fwd: null stats");
+  return dwconv_entry(x, w, bias, y, nullptr, stats, dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, DFV_ACT_NONE, stream);
 }

@@ -71,6 +71,7 @@ struct Arena {
   float* mask_f;
   float* pool_ws;
   float* bn_ws;
+  double* bn_acc;      // per-channel sum / sum of squares a producer kernel accumulates (fused BatchNorm statistics)
   char* fold_ws;
   ClsArena cls[DFV_MAX_CLS_LAYERS];
   size_t bytes;
@@ -178,6 +179,7 @@ void carve_arena(Arena* a, void* base, const TShapes& s, int dtype, int B, const
   a->pool_ws = c.takef(pool_max);
   a->bn_ws = c.takef(max_bn_ws(s, B, dims, layers));
   a->fold_ws = c.take(dfv_pw_fold_ws_bytes(B));
+  a->bn_acc = reinterpret_cast<double*>(c.take(sizeof(double) * 2 * 4096));
   for (int l = 0; l < layers && l < DFV_MAX_CLS_LAYERS; ++l) {
     const size_t d = dims[l + 1];
     a->cls[l].lin = c.takef((size_t)B * d);
@@ -356,9 +358,13 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
     }
     DFV_TRY(dfv_dw_weight_pack(P(i, DFV_T_DW_W), ba.wD, b.c_mid, b.kernel, 0, stream));
     DFV_TRY(dfv_dw_weight_pack(P(i, DFV_T_DW_W), ba.wDf, b.c_mid, b.kernel, 1, stream));
-    DFV_TRY(dfv_dwconv_fwd(dw_in, ba.wD, ar.zero_bias, ba.d_raw, nullptr, dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi,
-                           DFV_ACT_NONE, stream));
-    DFV_TRY(dfv_bn_stats_fwd(ba.d_raw, dtype, B, hw_out, b.c_mid, eps, mom, ba.m1, ba.i1, PW(i, DFV_T_BN1_RM), PW(i, DFV_T_BN1_RV), ar.bn_ws, stream));
+    // depthwise conv with the BatchNorm batch statistics accumulated in its epilogue (no separate pass over d_raw)
+    DFV_REQUIRE(b.c_mid <= 4096, "dfv_train_fwd: c_mid %d > 4096", b.c_mid);
+    DFV_CUDA(cudaMemsetAsync(ar.bn_acc, 0, sizeof(double) * 2 * (size_t)b.c_mid, st));
+    DFV_TRY(dfv_dwconv_stats_fwd(dw_in, ba.wD, ar.zero_bias, ba.d_raw, ar.bn_acc, dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo,
+                                 b.pad_hi, stream));
+    DFV_TRY(dfv_bn_stats_from_sums(ar.bn_acc, b.c_mid, (double)B * (double)hw_out, eps, mom, ba.m1, ba.i1, PW(i, DFV_T_BN1_RM),
+                                   PW(i, DFV_T_BN1_RV), stream));
     DFV_TRY(dfv_bn_act_fwd(ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ba.d,
                            ar.pool_ws, dtype, B, hw_out, b.c_mid, stream));
     DFV_TRY(dfv_se_train_fwd(ar.pool_ws, dfv_rows_chunks(B, hw_out), 1.0f / (float)hw_out, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_R_B),

@@ -9,6 +9,8 @@
 // fp32 accumulation, per-CTA partials finished by a tiny second kernel (deterministic).
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace dfv {
@@ -197,6 +199,25 @@ __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __r
   if (lane != 0 || c >= C) return;
   const double mu = s / count;
   double var = q / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  invstd[c] = 1.0f / sqrtf((float)var + eps);
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// Finish statistics that a producer kernel accumulated as per-channel double sums (dfv_dwconv_stats_fwd).
+__global__ void __launch_bounds__(256) bn_stats_from_sums_kernel(const double* __restrict__ acc, int C, double count, float eps,
+                                                                float momentum, float* __restrict__ mean,
+                                                                float* __restrict__ invstd, float* __restrict__ running_mean,
+                                                                float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = acc[c] / count;
+  double var = acc[C + c] / count - mu * mu;
   if (var < 0.0) var = 0.0;
   mean[c] = (float)mu;
   invstd[c] = 1.0f / sqrtf((float)var + eps);
@@ -520,49 +541,6 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------ SE (train)
-// One CTA per image.  Native torch layouts: w1 = _se_reduce.weight [sq][C], w2 = _se_expand.weight [C][sq].
-template <typename GT>
-__global__ void __launch_bounds__(512) se_train_fwd_kernel(const float* __restrict__ partial, int parts, float inv_hw,
-                                                          const float* __restrict__ w1, const float* __restrict__ b1,
-                                                          const float* __restrict__ w2, const float* __restrict__ b2,
-                                                          GT* __restrict__ gate, float* __restrict__ pooled_out,
-                                                          float* __restrict__ h1_out, float* __restrict__ gate_f32, int C,
-                                                          int sq) {
-  extern __shared__ float sm[];
-  float* pooled = sm;         // [C]
-  float* hidden = sm + C;     // [sq]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int c = tid; c < C; c += blockDim.x) {
-    const float* pb = partial + (size_t)b * parts * C + c;
-    float s = 0.f;
-    for (int t = 0; t < parts; ++t) s += pb[(size_t)t * C];
-    s *= inv_hw;
-    pooled[c] = s;
-    pooled_out[(size_t)b * C + c] = s;
-  }
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < sq; j += nwarps) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(w1[(size_t)j * C + c], pooled[c], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      s += b1[j];
-      h1_out[(size_t)b * sq + j] = s;
-      hidden[j] = s * sigmoid_exact(s);
-    }
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
-    float s = b2[c];
-    for (int j = 0; j < sq; ++j) s = fmaf(w2[(size_t)c * sq + j], hidden[j], s);
-    const float gv = sigmoid_exact(s);
-    gate_f32[(size_t)b * C + c] = gv;
-    if constexpr (sizeof(GT) == 2) gate[(size_t)b * C + c] = __float2bfloat16_rn(gv);
-    else gate[(size_t)b * C + c] = gv;
-  }
-}
-
 // dgate partials: sum over positions of dA[pos][c] * d[pos][c]
 template <typename T>
 __global__ void __launch_bounds__(kNT) dot_rows_kernel(const T* __restrict__ a, const T* __restrict__ d,
@@ -598,42 +576,109 @@ __global__ void __launch_bounds__(kNT) dot_rows_kernel(const T* __restrict__ a, 
   }
 }
 
-// Per image: dgate (finish partials) -> dz -> dh1 -> dpool.
-__global__ void __launch_bounds__(512) se_bwd_image_kernel(const float* __restrict__ dgate_partial, int parts,
-                                                          const float* __restrict__ gate_f32, const float* __restrict__ h1,
-                                                          const float* __restrict__ w1, const float* __restrict__ w2,
-                                                          float* __restrict__ dz_out, float* __restrict__ dh1_out,
-                                                          float* __restrict__ dpool, int C, int sq) {
+// Per image group: dgate (finish partials) -> dz -> dh1 -> dpool, on a CLUSTER of 8 CTAs (same scheme as the forward
+// gate kernel in se.cu): every CTA owns a channel slice; the squeeze-wide dh1 vector is reduced across the cluster
+// through distributed shared memory.  The one-CTA-per-image version walked w2 with a 272-byte lane stride and took
+// ~36 us per layer at batch 64.
+constexpr int kSeBwdCluster = 8;
+
+template <int IMG>
+__global__ void __cluster_dims__(kSeBwdCluster, 1, 1) __launch_bounds__(256, 2)
+    se_bwd_image_kernel(const float* __restrict__ dgate_partial, int parts, const float* __restrict__ gate_f32,
+                        const float* __restrict__ h1, const float* __restrict__ w1, const float* __restrict__ w2,
+                        float* __restrict__ dz_out, float* __restrict__ dh1_out, float* __restrict__ dpool, int B, int C, int sq) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float sm[];
-  float* dz = sm;          // [C]
-  float* dh1 = sm + C;     // [sq]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int c = tid; c < C; c += blockDim.x) {
-    const float* pb = dgate_partial + (size_t)b * parts * C + c;
-    float s = 0.f;
-    for (int t = 0; t < parts; ++t) s += pb[(size_t)t * C];
-    const float gv = gate_f32[(size_t)b * C + c];
-    const float v = s * gv * (1.f - gv);
-    dz[c] = v;
-    dz_out[(size_t)b * C + c] = v;
-  }
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < sq; j += nwarps) {
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s = fmaf(dz[c], w2[(size_t)c * sq + j], s);
-    s = warp_sum(s);
-    if (lane == 0) {
-      const float v = s * act_grad(h1[(size_t)b * sq + j], DFV_ACT_SILU);
-      dh1[j] = v;
-      dh1_out[(size_t)b * sq + j] = v;
+  const int cper = (C + kSeBwdCluster - 1) / kSeBwdCluster;
+  float* dz = sm;                                   // [IMG][cper]      this CTA's channel slice
+  float* part = dz + (size_t)IMG * cper;            // [IMG][sq]        partial dh1 of the slice (read by peers)
+  float* dh1 = part + (size_t)IMG * sq;             // [IMG][sq]        full dh1
+  float* red = dh1 + (size_t)IMG * sq;              // [8 warps][IMG][sq]
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / kSeBwdCluster) * IMG, tid = threadIdx.x;
+  const int c0 = min(C, rank * cper), c1 = min(C, c0 + cper), cn = c1 - c0;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < IMG * cper; i += blockDim.x) {
+    const int im = i / cper, cl = i % cper;
+    float v = 0.f;
+    if (cl < cn && b0 + im < B) {
+      const size_t bc = (size_t)(b0 + im) * C + c0 + cl;
+      const float* pb = dgate_partial + (size_t)(b0 + im) * parts * C + c0 + cl;
+      float s = 0.f;
+      for (int t = 0; t < parts; ++t) s += __ldg(pb + (size_t)t * C);
+      const float gv = gate_f32[bc];
+      v = s * gv * (1.f - gv);
+      dz_out[bc] = v;
     }
+    dz[i] = v;
   }
   __syncthreads();
-  for (int c = tid; c < C; c += blockDim.x) {
+  // partial dh1[im][j] over this slice: warp -> channels (stride 8), lane -> j (coalesced rows of w2 [C][sq])
+  {
+    float acc[4][IMG];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int im = 0; im < IMG; ++im) acc[u][im] = 0.f;
+#pragma unroll 4
+    for (int cl = warp; cl < cn; cl += 8) {
+      const float* wr = w2 + (size_t)(c0 + cl) * sq;
+      float wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wv[u] = lane + 32 * u < sq ? __ldg(wr + lane + 32 * u) : 0.f;
+#pragma unroll
+      for (int im = 0; im < IMG; ++im) {
+        const float z = dz[im * cper + cl];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u][im] = fmaf(z, wv[u], acc[u][im]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (lane + 32 * u < sq)
+#pragma unroll
+        for (int im = 0; im < IMG; ++im) red[((size_t)warp * IMG + im) * sq + lane + 32 * u] = acc[u][im];
+  }
+  __syncthreads();
+  for (int i = tid; i < IMG * sq; i += blockDim.x) {
     float s = 0.f;
-    for (int j = 0; j < sq; ++j) s = fmaf(dh1[j], w1[(size_t)j * C + c], s);
-    dpool[(size_t)b * C + c] = s;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[(size_t)w * IMG * sq + i];
+    part[i] = s;
+  }
+  cluster.sync();
+  for (int i = tid; i < IMG * sq; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kSeBwdCluster; ++r) s += cluster.map_shared_rank(part, r)[i];
+    const int im = i / sq, j = i % sq;
+    float v = 0.f;
+    if (b0 + im < B) {
+      v = s * act_grad(h1[(size_t)(b0 + im) * sq + j], DFV_ACT_SILU);
+      if (rank == 0) dh1_out[(size_t)(b0 + im) * sq + j] = v;
+    }
+    dh1[i] = v;
+  }
+  cluster.sync();   // peers have finished reading `part`; dh1 complete in every CTA
+  for (int cl = tid; cl < cn; cl += blockDim.x) {
+    float s[IMG];
+#pragma unroll
+    for (int im = 0; im < IMG; ++im) s[im] = 0.f;
+    for (int jb = 0; jb < sq; jb += 32) {
+      float wv[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) wv[u] = jb + u < sq ? __ldg(w1 + (size_t)(jb + u) * C + c0 + cl) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 32; ++u)
+        if (jb + u < sq)
+#pragma unroll
+          for (int im = 0; im < IMG; ++im) s[im] = fmaf(dh1[im * sq + jb + u], wv[u], s[im]);
+    }
+#pragma unroll
+    for (int im = 0; im < IMG; ++im)
+      if (b0 + im < B) dpool[(size_t)(b0 + im) * C + c0 + cl] = s[im];
   }
 }
 
@@ -808,6 +853,17 @@ int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image
   return DFV_OK;
 }
 
+/* mean / invstd (+ running-stat update) from per-channel double sums acc[0..C) = sum x, acc[C..2C) = sum x^2. */
+int dfv_bn_stats_from_sums(const double* acc, int C, double count, float eps, float momentum, float* mean, float* invstd,
+                           float* running_mean, float* running_var, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(acc && mean && invstd && C > 0 && count > 0, "dfv_bn_stats_from_sums: bad arguments");
+  bn_stats_from_sums_kernel<<<(C + 255) / 256, 256, 0, as_stream(stream)>>>(acc, C, count, eps, momentum, mean, invstd, running_mean,
+                                                                          running_var);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
 int dfv_bn_act_fwd(const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
                    const float* rowscale, const void* residual, const float* mask, void* out, float* pool_partial,
                    int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream) {
@@ -923,10 +979,18 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
   else
     dot_rows_kernel<float><<<grid, kNT, 0, st>>>((const float*)da, (const float*)d, rows_per_image, C, rpc, partial);
   DFV_LAUNCH_CHECK();
-  const size_t smem = (size_t)(C + squeeze) * sizeof(float);
-  DFV_REQUIRE(smem <= 48 * 1024, "dfv_se_bwd: C + squeeze too large");
-  se_bwd_image_kernel<<<B, 512, smem, st>>>(partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, C, squeeze);
-  DFV_LAUNCH_CHECK();
+  DFV_REQUIRE(squeeze <= 128, "dfv_se_bwd: squeeze width %d > 128", squeeze);
+  {
+    const int img = B >= 16 ? 4 : 1;
+    const int cper = (C + kSeBwdCluster - 1) / kSeBwdCluster;
+    const size_t smem = sizeof(float) * ((size_t)img * cper + (size_t)2 * img * squeeze + (size_t)8 * img * squeeze);
+    const unsigned grid_i = (unsigned)((B + img - 1) / img) * kSeBwdCluster;
+    if (img == 4)
+      se_bwd_image_kernel<4><<<grid_i, 256, smem, st>>>(partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, B, C, squeeze);
+    else
+      se_bwd_image_kernel<1><<<grid_i, 256, smem, st>>>(partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, B, C, squeeze);
+    DFV_LAUNCH_CHECK();
+  }
   const int slices = std::max(1, std::min(squeeze / 4, (2 * num_sms() * 128 + C - 1) / C));
   const int jn_max = (squeeze + slices - 1) / slices + 1;
   const size_t smem2 = (size_t)2 * B * jn_max * sizeof(float);

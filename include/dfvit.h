@@ -395,6 +395,14 @@ size_t dfv_train_scratch_bytes(int dtype, int B, int H, int W, const int32_t* he
 int dfv_train_fwd(const dfv_train_args* args, dfv_stream_t stream);
 int dfv_train_bwd(const dfv_train_args* args, dfv_stream_t stream);
 
+/* Training forward of the depthwise conv with the train-mode BatchNorm statistics fused in: raw conv output (no
+ * activation) plus per-channel sum / sum of squares ADDED into stats[2C] (double; the caller zeroes it), finished by
+ * dfv_bn_stats_from_sums (mean, 1/sqrt(var + eps), running statistics with momentum and the unbiased variance). */
+int dfv_dwconv_stats_fwd(const void* x, const float* w_kkc, const float* bias, void* y, double* stats, int dtype, int B,
+                         int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream);
+int dfv_bn_stats_from_sums(const double* acc, int C, double count, float eps, float momentum, float* mean, float* invstd,
+                           float* running_mean, float* running_var, dfv_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Operators either side of the hot path.
  * ---------------------------------------------------------------------------------- */
