@@ -32,31 +32,24 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
   const int jper = (sq + kSeCluster - 1) / kSeCluster;
   const int j0 = min(sq, rank * jper), j1 = min(sq, j0 + jper);
 
-  // pooled[im][c]: four (image, channel) cells per thread per round so that 4 x parts loads are in flight
-  constexpr int PU = 16;     // cells per thread per round: 16 x parts independent loads in flight
-  for (int i0 = tid; i0 < IMG * C; i0 += PU * blockDim.x) {
-    float s[PU];
-    const float* pb[PU];
+  // pooled[im][c] = mean over positions (finishing the producer's partial sums).  No integer division in the
+  // loops (the first version spent half its instructions on i / C and i % C): channels advance by blockDim,
+  // images are a compile-time inner dimension, IMG x parts independent loads in flight per thread.
+  for (int c = tid; c < C; c += blockDim.x) {
+    float s[IMG];
 #pragma unroll
-    for (int u = 0; u < PU; ++u) {
-      s[u] = 0.f;
-      const int i = i0 + u * blockDim.x;
-      const int im = i / C, c = i % C;
-      pb[u] = (i < IMG * C && b0 + im < B) ? partial + (size_t)(b0 + im) * parts * C + c : nullptr;
-    }
+    for (int im = 0; im < IMG; ++im) s[im] = 0.f;
     for (int t = 0; t < parts; ++t) {
 #pragma unroll
-      for (int u = 0; u < PU; ++u)
-        if (pb[u]) s[u] += __ldg(pb[u] + (size_t)t * C);
+      for (int im = 0; im < IMG; ++im)
+        if (b0 + im < B) s[im] += __ldg(partial + ((size_t)(b0 + im) * parts + t) * C + c);
     }
 #pragma unroll
-    for (int u = 0; u < PU; ++u) {
-      const int i = i0 + u * blockDim.x;
-      if (i < IMG * C) {
-        pooled[i] = s[u] * inv_hw;
-        if constexpr (kTrain) {
-          if (rank == 0 && b0 + i / C < B) pooled_out[(size_t)(b0 + i / C) * C + i % C] = s[u] * inv_hw;
-        }
+    for (int im = 0; im < IMG; ++im) {
+      const float v = s[im] * inv_hw;
+      pooled[im * C + c] = v;
+      if constexpr (kTrain) {
+        if (rank == 0 && b0 + im < B) pooled_out[(size_t)(b0 + im) * C + c] = v;
       }
     }
   }
@@ -109,11 +102,12 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
   }
   cluster.sync();
   // gather every CTA's slice of the hidden vector through distributed shared memory
-  for (int i = tid; i < IMG * sq; i += blockDim.x) {
-    const int im = i / sq, j = i % sq;
-    const int r = j / jper;
+  for (int r = 0; r < kSeCluster; ++r) {
     const float* remote = cluster.map_shared_rank(mine, r);
-    hidden[i] = remote[im * jper + (j - r * jper)];
+    const int jr0 = r * jper, jn = min(sq, jr0 + jper) - jr0;
+    for (int jj = tid; jj < jn; jj += blockDim.x)
+#pragma unroll
+      for (int im = 0; im < IMG; ++im) hidden[im * sq + jr0 + jj] = remote[im * jper + jj];
   }
   cluster.sync();   // also keeps every CTA's shared memory alive until all peers have read it
 

@@ -600,19 +600,21 @@ __global__ void __cluster_dims__(kSeBwdCluster, 1, 1) __launch_bounds__(256, 2)
   const int c0 = min(C, rank * cper), c1 = min(C, c0 + cper), cn = c1 - c0;
   const int warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < IMG * cper; i += blockDim.x) {
-    const int im = i / cper, cl = i % cper;
-    float v = 0.f;
-    if (cl < cn && b0 + im < B) {
-      const size_t bc = (size_t)(b0 + im) * C + c0 + cl;
-      const float* pb = dgate_partial + (size_t)(b0 + im) * parts * C + c0 + cl;
-      float s = 0.f;
-      for (int t = 0; t < parts; ++t) s += __ldg(pb + (size_t)t * C);
-      const float gv = gate_f32[bc];
-      v = s * gv * (1.f - gv);
-      dz_out[bc] = v;
+  for (int cl = tid; cl < cper; cl += blockDim.x) {
+#pragma unroll
+    for (int im = 0; im < IMG; ++im) {
+      float v = 0.f;
+      if (cl < cn && b0 + im < B) {
+        const size_t bc = (size_t)(b0 + im) * C + c0 + cl;
+        const float* pb = dgate_partial + (size_t)(b0 + im) * parts * C + c0 + cl;
+        float s = 0.f;
+        for (int t = 0; t < parts; ++t) s += __ldg(pb + (size_t)t * C);
+        const float gv = gate_f32[bc];
+        v = s * gv * (1.f - gv);
+        dz_out[bc] = v;
+      }
+      dz[im * cper + cl] = v;
     }
-    dz[i] = v;
   }
   __syncthreads();
   // partial dh1[im][j] over this slice: warp -> channels (stride 8), lane -> j (coalesced rows of w2 [C][sq])
@@ -649,17 +651,20 @@ __global__ void __cluster_dims__(kSeBwdCluster, 1, 1) __launch_bounds__(256, 2)
     part[i] = s;
   }
   cluster.sync();
-  for (int i = tid; i < IMG * sq; i += blockDim.x) {
-    float s = 0.f;
+  for (int j = tid; j < sq; j += blockDim.x) {
 #pragma unroll
-    for (int r = 0; r < kSeBwdCluster; ++r) s += cluster.map_shared_rank(part, r)[i];
-    const int im = i / sq, j = i % sq;
-    float v = 0.f;
-    if (b0 + im < B) {
-      v = s * act_grad(h1[(size_t)(b0 + im) * sq + j], DFV_ACT_SILU);
-      if (rank == 0) dh1_out[(size_t)(b0 + im) * sq + j] = v;
+    for (int im = 0; im < IMG; ++im) {
+      const int i = im * sq + j;
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < kSeBwdCluster; ++r) s += cluster.map_shared_rank(part, r)[i];
+      float v = 0.f;
+      if (b0 + im < B) {
+        v = s * act_grad(h1[(size_t)(b0 + im) * sq + j], DFV_ACT_SILU);
+        if (rank == 0) dh1_out[(size_t)(b0 + im) * sq + j] = v;
+      }
+      dh1[i] = v;
     }
-    dh1[i] = v;
   }
   cluster.sync();   // peers have finished reading `part`; dh1 complete in every CTA
   for (int cl = tid; cl < cn; cl += blockDim.x) {
