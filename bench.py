@@ -77,6 +77,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over this kernel's launches of one
+    step) from the committed ncu pass profiles/r01_traffic.json (scripts/gpu_final_profile.sh); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def cpu_reference_run(steps, warmup, batch=8):
     """The reference's own CPU implementation of the path (reference wrapper code over the
     efficientnet-pytorch restatement; the real import when /root/reference is mounted, else its
@@ -167,7 +177,7 @@ def train_bench(args, d, _lib, dev, rank, world, local, warmup):
     top = max(agg, key=lambda k: agg[k][2])
     tb, tf, tms, tn = agg[top]
     roofline = {"kernel": top, "bound": "hbm", "achieved": tb / (tms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": measured_traffic(top), "peak_source": pk["source"],
                 "launches": tn // prof_steps, "avg_launch_ms": tms / tn, "algorithmic_bytes_per_launch": tb / tn, "kernels": kernels}
 
     # end to end: pinned host batch -> device every step, loss read back every step
@@ -321,7 +331,7 @@ def main():
     top = max(agg, key=lambda k: agg[k][2])
     tb, tf, tms, tn = agg[top]
     roofline = {"kernel": top, "bound": "hbm", "achieved": tb / (tms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": measured_traffic(top), "peak_source": pk["source"],
                 "launches": tn // prof_steps, "avg_launch_ms": tms / tn,
                 "algorithmic_bytes_per_launch": tb / tn, "kernels": kernels,
                 "note": "achieved = sum of algorithmic bytes of this kernel's launches / sum of their CUDA-event "

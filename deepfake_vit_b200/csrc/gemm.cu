@@ -592,7 +592,9 @@ static int pick_fold(int dtype, long long M, int K, int N, int rows_per_image, b
   if (dtype != DFV_BF16 || K > 48 || force_simt_gemm()) return 1;
   for (int f = 4; f >= 2; f >>= 1) {
     if (M % f || (gated && rows_per_image % f)) continue;
-    if (f * N > (f == 4 ? 256 : 512)) continue;
+    // folded width: one N tile, or (f = 4) an exact multiple of the 192-column tile (e.g. 24 -> 144: 576 = 3 x 192)
+    const bool exact4 = f == 4 && !gated && f * N <= 768 && (f * N) % 192 == 0 && N % 48 == 0 && N < 192;
+    if (f * N > (f == 4 ? 256 : 512) && !exact4) continue;
     if ((size_t)f * N * f * K > (size_t)kFoldWElems || f * N > kFoldBias || (gated && f * K > kFoldGate)) continue;
     return f;
   }

@@ -61,7 +61,7 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
     float s[IMG];
 #pragma unroll
     for (int im = 0; im < IMG; ++im) s[im] = 0.f;
-    if ((C & 3) == 0) {
+    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(w1) & 15) == 0) {
       // 16-byte weight loads, the whole row slice of a lane (up to 12 loads = 1536 channels) requested before use
       for (int cb = lane * 4; cb < C; cb += 12 * 128) {
         float4 wv[12];

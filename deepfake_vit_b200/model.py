@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .parallel import allreduce_gradients
+from .parallel import allreduce_gradients, flat_offsets
 from ._lib import check, lib
 
 BN_EPS, BN_MOM = 1e-3, 0.01   # efficientnet-pytorch global params for B4
@@ -550,10 +550,8 @@ class DeepfakeDetectionModel(nn.Module):
         hd, images, lm, T, _, feats = run["keep"]
         dev = images.device
         params = [p for _, p in self.named_parameters()]
-        offs, total = {}, 0
-        for p in params:
-            offs[id(p)] = total
-            total += p.numel()
+        starts, total = flat_offsets([p.numel() for p in params])
+        offs = {id(p): o for p, o in zip(params, starts)}
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
         gp = []
         for t in T:

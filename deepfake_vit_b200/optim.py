@@ -12,6 +12,7 @@ from typing import Iterable, Optional
 import torch
 
 from ._lib import check, lib
+from .parallel import flat_offsets
 
 
 class FusedAdamW(torch.optim.Optimizer):
@@ -29,22 +30,20 @@ class FusedAdamW(torch.optim.Optimizer):
         self._params = [p for p in self.param_groups[0]["params"]]
         assert all(p.dtype == torch.float32 for p in self._params), "master parameters are fp32"
         dev = self._params[0].device
-        n = sum(p.numel() for p in self._params)
+        self._offsets, n = flat_offsets([p.numel() for p in self._params])   # same layout as the model's flat gradient buffer
         self._n = n
         # parameters become views of one flat buffer (values preserved)
-        self._flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self._flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self._flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
         self._flat_v = torch.zeros(n, dtype=torch.float32, device=dev)
         self._norm_ws = torch.zeros(1, dtype=torch.float64, device=dev)
         self._total_norm = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._offsets, off = [], 0
         with torch.no_grad():
-            for p in self._params:
+            self._flat_p.zero_()
+            for p, off in zip(self._params, self._offsets):
                 k = p.numel()
                 self._flat_p[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self._flat_p[off:off + k].view_as(p)
-                self._offsets.append(off)
-                off += k
         self._step = 0
         self._bind_state()
 

@@ -47,17 +47,32 @@ def allreduce_gradients(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+FLAT_ALIGN = 64   # floats: every tensor starts on a 256-byte boundary inside a flat buffer, like a torch allocation
+                  # (the kernels read parameters with 16-byte vector loads)
+
+
+def flat_offsets(numels, align: int = FLAT_ALIGN):
+    """Start offset of every tensor inside a flat buffer (given order, each start rounded up to `align` elements)
+    and the buffer's total length.  Shared by the model's flat gradient buffer and FusedAdamW's flat parameter /
+    moment buffers, so the optimizer reads the gradient buffer the backward pass filled without gathering."""
+    offs, total = [], 0
+    for n in numels:
+        offs.append(total)
+        total += (int(n) + align - 1) // align * align
+    return offs, total
+
+
 def flat_layout(named_shapes: List[Tuple[str, torch.Size]]):
-    """Offsets of every parameter gradient inside the flat buffer (registration order, no padding):
+    """Offsets of every parameter gradient inside the flat buffer (registration order, FLAT_ALIGN-aligned starts):
     {name: (offset, numel)}, total."""
-    offs, total = {}, 0
-    for name, shape in named_shapes:
+    numels = []
+    for _, shape in named_shapes:
         n = 1
         for s in shape:
             n *= int(s)
-        offs[name] = (total, n)
-        total += n
-    return offs, total
+        numels.append(n)
+    offs, total = flat_offsets(numels)
+    return {name: (o, n) for (name, _), o, n in zip(named_shapes, offs, numels)}, total
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):

@@ -89,4 +89,12 @@ def test_clip_shards_whole_clips():
 def test_flat_layout_matches_registration_order():
     from deepfake_vit_b200.parallel import flat_layout
     offs, total = flat_layout([("a", torch.Size([3, 4])), ("b", torch.Size([5])), ("c", torch.Size([]))])
-    assert offs == {"a": (0, 12), "b": (12, 5), "c": (17, 1)} and total == 18
+    # registration order, every tensor on a 64-float (256-byte) boundary: the kernels read parameters with vector loads
+    assert offs == {"a": (0, 12), "b": (64, 5), "c": (128, 1)} and total == 192
+
+
+def test_flat_offsets_shared_by_gradient_buffer_and_optimizer():
+    from deepfake_vit_b200.parallel import FLAT_ALIGN, flat_offsets
+    offs, total = flat_offsets([1296, 48, 7, 64, 65])
+    assert offs == [0, 1344, 1408, 1472, 1536] and total == 1664
+    assert all(o % FLAT_ALIGN == 0 for o in offs)
