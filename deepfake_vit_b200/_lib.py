@@ -99,9 +99,6 @@ def _load():
         "dfv_pw_fold_ws_bytes": (sz, [i32]),
         "dfv_dwconv_stats_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 9 + [vp]),
         "dfv_bn_stats_from_sums": (C.c_int, [vp, i32, C.c_double, f32, f32, vp, vp, vp, vp, vp]),
-        "dfv_bn_fused_applicable": (C.c_int, [i32, i64, i32]),
-        "dfv_bn_fused_fwd": (C.c_int, [vp, vp, vp, i32, f32, f32, vp, vp, vp, vp, vp, i64, i32, vp]),
-        "dfv_bn_fused_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, vp, vp, vp, i64, i64, i32, vp]),
         "dfv_debug_dwconv_plan": (C.c_int, [i32] * 9 + [C.POINTER(C.c_int)]),
         "dfv_clip_aggregate": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, f32, vp]),
         "dfv_global_avg_pool": (C.c_int, [vp, i32, vp, i32, i64, i32, vp]),

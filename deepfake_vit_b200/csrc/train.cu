@@ -351,14 +351,9 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
       DFV_TRY(dfv_cast_weight(P(i, DFV_T_EXPAND_W), ba.wEt, dtype, b.c_in, b.c_mid, 1, stream));
       DFV_TRY(dfv_pw_conv_fwd(x, ba.wE, ar.zero_bias, nullptr, (int)hw_in, nullptr, ba.e_raw, dtype, B, B * hw_in, b.c_in, b.c_mid, DFV_ACT_NONE,
                               ar.fold_ws, stream));
-      if (dfv_bn_fused_applicable(dtype, B * hw_in, b.c_mid)) {   // small L2-resident tensor: statistics + normalise + swish in one cluster kernel
-        DFV_TRY(dfv_bn_fused_fwd(ba.e_raw, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, eps, mom, ba.m0, ba.i0, PW(i, DFV_T_BN0_RM),
-                                 PW(i, DFV_T_BN0_RV), ba.e, B * hw_in, b.c_mid, stream));
-      } else {
-        DFV_TRY(dfv_bn_stats_fwd(ba.e_raw, dtype, B, hw_in, b.c_mid, eps, mom, ba.m0, ba.i0, PW(i, DFV_T_BN0_RM), PW(i, DFV_T_BN0_RV), ar.bn_ws, stream));
-        DFV_TRY(dfv_bn_act_fwd(ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ba.e,
-                               nullptr, dtype, B, hw_in, b.c_mid, stream));
-      }
+      DFV_TRY(dfv_bn_stats_fwd(ba.e_raw, dtype, B, hw_in, b.c_mid, eps, mom, ba.m0, ba.i0, PW(i, DFV_T_BN0_RM), PW(i, DFV_T_BN0_RV), ar.bn_ws, stream));
+      DFV_TRY(dfv_bn_act_fwd(ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ba.e,
+                             nullptr, dtype, B, hw_in, b.c_mid, stream));
       dw_in = ba.e;
     }
     DFV_TRY(dfv_dw_weight_pack(P(i, DFV_T_DW_W), ba.wD, b.c_mid, b.kernel, 0, stream));
@@ -398,14 +393,9 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
   DFV_TRY(dfv_cast_weight(P(-1, DFV_TG_HEAD_W), ar.wH, dtype, head_c, c_last, 0, stream));
   DFV_TRY(dfv_cast_weight(P(-1, DFV_TG_HEAD_W), ar.wHt, dtype, c_last, head_c, 1, stream));
   DFV_TRY(dfv_pw_gemm_fwd(x, ar.wH, ar.zero_bias, nullptr, 0, nullptr, ar.h_raw, dtype, B * hw_f, c_last, head_c, DFV_ACT_NONE, stream));
-  if (dfv_bn_fused_applicable(dtype, B * hw_f, head_c)) {
-    DFV_TRY(dfv_bn_fused_fwd(ar.h_raw, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, eps, mom, ar.hm, ar.hi, PW(-1, DFV_TG_HEAD_RM),
-                             PW(-1, DFV_TG_HEAD_RV), ar.h, B * hw_f, head_c, stream));
-  } else {
-    DFV_TRY(dfv_bn_stats_fwd(ar.h_raw, dtype, B, hw_f, head_c, eps, mom, ar.hm, ar.hi, PW(-1, DFV_TG_HEAD_RM), PW(-1, DFV_TG_HEAD_RV), ar.bn_ws, stream));
-    DFV_TRY(dfv_bn_act_fwd(ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ar.h, nullptr,
-                           dtype, B, hw_f, head_c, stream));
-  }
+  DFV_TRY(dfv_bn_stats_fwd(ar.h_raw, dtype, B, hw_f, head_c, eps, mom, ar.hm, ar.hi, PW(-1, DFV_TG_HEAD_RM), PW(-1, DFV_TG_HEAD_RV), ar.bn_ws, stream));
+  DFV_TRY(dfv_bn_act_fwd(ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ar.h, nullptr,
+                         dtype, B, hw_f, head_c, stream));
   DFV_TRY(tap(1 + n, ar.h, (size_t)B * hw_f * head_c));
 
   // ---- attention + pool
@@ -514,14 +504,9 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
   if (has_heat && G(-1, DFV_TG_LM_W))
     DFV_TRY(dfv_landmark_heatmap_bwd(a->landmarks, P(-1, DFV_TG_LM_W), ar.heat_raw, ar.heat_max, sc.dheat, G(-1, DFV_TG_LM_W), B, s.Hf, s.Wf,
                                      a->landmark_ref_size > 0.f ? a->landmark_ref_size : 224.0f, 1.5f, a->heat_group, stream));
-  if (dfv_bn_fused_applicable(dtype, B * hw_f, head_c)) {
-    DFV_TRY(dfv_bn_fused_bwd(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, sc.gE,
-                             G(-1, DFV_TG_HEAD_G), G(-1, DFV_TG_HEAD_B), B * hw_f, hw_f, head_c, stream));
-  } else {
-    DFV_TRY(dfv_act_bn_bwd(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr,
-                           nullptr, sc.gE, G(-1, DFV_TG_HEAD_G), G(-1, DFV_TG_HEAD_B), sc.coef, sc.bn_ws, dtype, B, hw_f, head_c, stream));
-    DFV_TRY(dfv_bn_bwd_apply(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), sc.coef, sc.gE, dtype, B * hw_f, head_c, stream));
-  }
+  DFV_TRY(dfv_act_bn_bwd(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr,
+                         nullptr, sc.gE, G(-1, DFV_TG_HEAD_G), G(-1, DFV_TG_HEAD_B), sc.coef, sc.bn_ws, dtype, B, hw_f, head_c, stream));
+  DFV_TRY(dfv_bn_bwd_apply(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), sc.coef, sc.gE, dtype, B * hw_f, head_c, stream));
   DFV_TRY(dfv_pw_wgrad(sc.gE, ar.blk[n - 1].out, nullptr, 0, G(-1, DFV_TG_HEAD_W), dtype, B * hw_f, c_last, head_c, stream));
   int gc = 0;
   DFV_TRY(dfv_pw_gemm_fwd(sc.gE, ar.wHt, ar.zero_bias, nullptr, 0, nullptr, sc.gout[gc], dtype, B * hw_f, head_c, c_last, DFV_ACT_NONE, stream));
@@ -548,14 +533,9 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_se_bwd(sc.gA, ba.d, dtype, ba.gate_f32, ba.pooled, ba.h1, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_E_W), sc.dpool, G(i, DFV_T_SE_R_W),
                        G(i, DFV_T_SE_R_B), G(i, DFV_T_SE_E_W), G(i, DFV_T_SE_E_B), sc.se_ws, B, hw_out, b.c_mid, b.se_squeeze, stream));
     // gate, swish, bn1
-    if (dfv_bn_fused_applicable(dtype, B * hw_out, b.c_mid)) {
-      DFV_TRY(dfv_bn_fused_bwd(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool,
-                               1.0f / (float)hw_out, sc.gA, G(i, DFV_T_BN1_G), G(i, DFV_T_BN1_B), B * hw_out, hw_out, b.c_mid, stream));
-    } else {
-      DFV_TRY(dfv_act_bn_bwd(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool, 1.0f / (float)hw_out,
-                             nullptr, nullptr, sc.gA, G(i, DFV_T_BN1_G), G(i, DFV_T_BN1_B), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_mid, stream));
-      DFV_TRY(dfv_bn_bwd_apply(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), sc.coef, sc.gA, dtype, B * hw_out, b.c_mid, stream));
-    }
+    DFV_TRY(dfv_act_bn_bwd(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool, 1.0f / (float)hw_out,
+                           nullptr, nullptr, sc.gA, G(i, DFV_T_BN1_G), G(i, DFV_T_BN1_B), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_mid, stream));
+    DFV_TRY(dfv_bn_bwd_apply(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), sc.coef, sc.gA, dtype, B * hw_out, b.c_mid, stream));
     // depthwise conv
     const void* dw_in = b.has_expand ? (const void*)ba.e : x;
     const int kk = b.kernel * b.kernel;
@@ -570,14 +550,9 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     }
     void* gx = sc.gout[gc ^ 1];
     if (b.has_expand) {
-      if (dfv_bn_fused_applicable(dtype, B * hw_in, b.c_mid)) {
-        DFV_TRY(dfv_bn_fused_bwd(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, sc.gE,
-                                 G(i, DFV_T_BN0_G), G(i, DFV_T_BN0_B), B * hw_in, hw_in, b.c_mid, stream));
-      } else {
-        DFV_TRY(dfv_act_bn_bwd(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr, nullptr,
-                               sc.gE, G(i, DFV_T_BN0_G), G(i, DFV_T_BN0_B), sc.coef, sc.bn_ws, dtype, B, hw_in, b.c_mid, stream));
-        DFV_TRY(dfv_bn_bwd_apply(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), sc.coef, sc.gE, dtype, B * hw_in, b.c_mid, stream));
-      }
+      DFV_TRY(dfv_act_bn_bwd(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr, nullptr,
+                             sc.gE, G(i, DFV_T_BN0_G), G(i, DFV_T_BN0_B), sc.coef, sc.bn_ws, dtype, B, hw_in, b.c_mid, stream));
+      DFV_TRY(dfv_bn_bwd_apply(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), sc.coef, sc.gE, dtype, B * hw_in, b.c_mid, stream));
       DFV_TRY(dfv_pw_wgrad(sc.gE, x, nullptr, 0, G(i, DFV_T_EXPAND_W), dtype, B * hw_in, b.c_in, b.c_mid, stream));
       DFV_TRY(dfv_pw_conv_fwd(sc.gE, ba.wEt, ar.zero_bias, nullptr, (int)hw_in, b.has_skip ? gy : nullptr, gx, dtype, B, B * hw_in, b.c_mid, b.c_in,
                               DFV_ACT_NONE, sc.fold_ws, stream));

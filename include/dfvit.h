@@ -403,17 +403,6 @@ int dfv_dwconv_stats_fwd(const void* x, const float* w_kkc, const float* bias, v
 int dfv_bn_stats_from_sums(const double* acc, int C, double count, float eps, float momentum, float* mean, float* invstd,
                            float* running_mean, float* running_var, dfv_stream_t stream);
 
-/* Cluster-fused train-mode BatchNorm for small (L2-resident) bf16 tensors [M][C], C % 32 == 0: one launch computes the
- * batch statistics over a 32-channel slice on a cluster of 8 CTAs (distributed shared memory reduction), then normalises
- * (+ activation) / applies the BatchNorm backward from L2.  dfv_bn_fused_applicable() says when the training sequencer
- * uses them instead of the streaming pairs (dfv_bn_stats_fwd + dfv_bn_act_fwd, dfv_act_bn_bwd + dfv_bn_bwd_apply). */
-int dfv_bn_fused_applicable(int dtype, long long M, int C);
-int dfv_bn_fused_fwd(const void* raw, const float* gamma, const float* beta, int act, float eps, float momentum, float* mean,
-                     float* invstd, float* running_mean, float* running_var, void* out, long long M, int C, dfv_stream_t stream);
-int dfv_bn_fused_bwd(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma,
-                     const float* beta, int act, const void* gate, const float* dpool, float inv_hw, void* draw,
-                     float* dgamma, float* dbeta, long long M, long long rows_per_image, int C, dfv_stream_t stream);
-
 /* ------------------------------------------------------------------------------------
  * Operators either side of the hot path.
  * ---------------------------------------------------------------------------------- */
