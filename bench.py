@@ -165,6 +165,10 @@ def train_bench(args, d, _lib, dev, rank, world, local, warmup):
     torch.cuda.synchronize()
     recs = _lib.profile_records()
     _lib.lib.dfv_profile_enable(0)
+    if os.environ.get("DFV_BENCH_DUMP"):          # per-launch list of the last profiled step
+        per = len(recs) // prof_steps
+        with open(os.environ["DFV_BENCH_DUMP"], "w") as f:
+            json.dump([{"kind": k, "bytes": b, "flops": fl, "ms": m} for k, b, fl, m in recs[-per:]], f)
     agg = {}
     for kind, nbytes, flops, kms in recs:
         a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])

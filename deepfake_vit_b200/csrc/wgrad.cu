@@ -188,13 +188,24 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       tmem_ld16(tbase + (uint32_t)c0, v);
       tmem_ld_wait();
       if (pidx < p.Pdim) {
+        const int q0 = qt * p.QT + half * cols_half + c0;
+        if (p.p_is_g) {
+          // a lane owns 16 consecutive k of one weight row: four 16-byte vector reductions (K % 8 == 0 keeps them
+          // aligned) instead of 16 scalar ones -- the split-M epilogue is bound by L2 atomic operations on the
+          // late layers (7 splits x 444k weights)
+          float* dst = dw + (size_t)pidx * p.K + q0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int qidx = qt * p.QT + half * cols_half + c0 + j;
-          if (qidx < p.Qdim) {
-            float* dst = p.p_is_g ? dw + (size_t)pidx * p.K + qidx : dw + (size_t)qidx * p.K + pidx;
-            atomicAdd(dst, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; j += 4) {
+            if (q0 + j < p.Qdim)      // Qdim % 8 == 0: a group of 4 is either entirely valid or entirely out of range
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
           }
+        } else {
+          // lanes = consecutive k of the same weight row: every scalar reduction of the warp is one coalesced line
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (q0 + j < p.Qdim) atomicAdd(dw + (size_t)(q0 + j) * p.K + pidx, __uint_as_float(v[j]));
         }
       }
     }
@@ -219,7 +230,7 @@ int launch_wgrad_tc(const void* g, const void* a, const void* a_scale, int rows_
   WgParams p;
   p.M = M;
   p.K = K;
-  p.p_is_g = cost(N, K) <= cost(K, N) ? 1 : 0;
+  p.p_is_g = cost(N, K) < cost(K, N) ? 1 : 0;   // tie: lanes over k (coalesced reductions)
   p.Pdim = p.p_is_g ? N : K;
   p.Qdim = p.p_is_g ? K : N;
   p.p_tiles = (p.Pdim + 127) / 128;
