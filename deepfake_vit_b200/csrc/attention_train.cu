@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
       int mi[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { s[e] = 0.f; m[e] = -INFINITY; mi[e] = 0; }
+      #pragma unroll 8
       for (int p = 0; p < HW; ++p) {
         float v[8];
         load8(fb + (size_t)p * C + cv * 8, v);
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
     for (int j = warp; j < hidden; j += nwarps) {
       const float* wr = w1 + (size_t)j * C;
       float sa = 0.f, sx = 0.f;
+      #pragma unroll 8
       for (int c = lane; c < C; c += 32) {
         const float wv = wr[c];
         sa = fmaf(wv, avg_c[c], sa);
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
     __syncthreads();
     for (int c = tid; c < C; c += blockDim.x) {
       float s = 0.f;
+      #pragma unroll 8
       for (int j = 0; j < hidden; ++j) s = fmaf(w2[(size_t)c * hidden + j], hid[j], s);
       const float g = sigmoid_exact(s);
       gate_c[c] = g;
@@ -109,6 +112,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
       const float a = a_lm[p];
       float s = 0.f, m = -INFINITY;
       int mi = 0;
+      #pragma unroll 8
       for (int cv = lane; cv < CV; cv += 32) {
         float v[8];
         load8(fb + (size_t)p * C + cv * 8, v);
@@ -161,6 +165,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
     float s[8], gc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; gc[e] = gate_c[cv * 8 + e]; }
+    #pragma unroll 8
     for (int p = 0; p < HW; ++p) {
       float v[8];
       load8(fb + (size_t)p * C + cv * 8, v);
@@ -229,6 +234,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
     for (int p = warp; p < HW; p += nwarps) {
       const float a = a_lm[p];
       float s = 0.f;
+      #pragma unroll 8
       for (int cv = lane; cv < CV; cv += 32) {
         float v[8];
         load8(fb + (size_t)p * C + cv * 8, v);
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
       const int ch = tid / 49, ky = (tid % 49) / 7, kx = tid % 7;
       const float* in = ch ? spx : spm;
       float s = 0.f;
+      #pragma unroll 8
       for (int p = 0; p < HW; ++p) {
         const int yy = p / W + ky - 3, xx = p % W + kx - 3;
         if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
       float s[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) s[e] = 0.f;
+      #pragma unroll 8
       for (int p = 0; p < HW; ++p) {
         float v[8];
         load8(fb + (size_t)p * C + cv * 8, v);
@@ -308,6 +316,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
       const int j = tid % hidden, qd = tid / hidden;
       const int c0 = (int)((long long)C * qd / nq), c1 = (int)((long long)C * (qd + 1) / nq);
       float s = 0.f;
+      #pragma unroll 8
       for (int c = c0; c < c1; ++c) s = fmaf(dzs[c], w2[(size_t)c * hidden + j], s);
       part[qd * hidden + j] = s;
     }
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
     // S5: d avg[c], d max[c]
     for (int c = tid; c < C; c += blockDim.x) {
       float sa = 0.f, sx = 0.f;
+      #pragma unroll 8
       for (int j = 0; j < hidden; ++j) {
         const float wv = w1[(size_t)j * C + c];
         sa = fmaf(dh[j], wv, sa);
@@ -342,6 +352,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
     const float a = a_lm[p], g = gate_p[p], dm = dsm[p] * inv_c, dxv = dsx[p];
     const int si = sp_idx[p];
     float sA = 0.f;
+    #pragma unroll 8
     for (int cv = lane; cv < CV; cv += 32) {
       float v[8], o[8];
       const size_t off = (size_t)p * C + cv * 8;
@@ -369,6 +380,7 @@ __global__ void __launch_bounds__(128) ca_wgrad_kernel(const float* __restrict__
                                                       float* __restrict__ dw2, int B, int C, int hidden) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  #pragma unroll 8
   for (int j = 0; j < hidden; ++j) {
     float s1 = 0.f, s2 = 0.f;
     for (int b = 0; b < B; ++b) {
