@@ -248,6 +248,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A training step is ~3000 mostly small launches; stream-ordered launches pay the full launch latency and the previous
+// grid's tail at every boundary.  Kernels launched with launch_pdl() may be SCHEDULED while their predecessor still
+// runs: pdl_prologue() first lets this grid's own successor do the same, then blocks until every prerequisite grid has
+// completed and flushed its memory (griddepcontrol.wait), so data dependencies are exactly those of plain stream order.
+// (Without the launch attribute both instructions are no-ops.)
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Point this translation unit's g_timeout_word at the process-wide host-mapped word.
 static inline int init_timeout_word_tu() {
   static bool done = false;
@@ -256,6 +267,21 @@ static inline int init_timeout_word_tu() {
   if (d) DFV_CUDA(cudaMemcpyToSymbol(g_timeout_word, &d, sizeof(d)));
   done = true;
   return DFV_OK;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 #endif  // __CUDACC__

@@ -15,6 +15,16 @@
 
 namespace dfv {
 
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute (common.cuh)
+#define DFV_PDL(kern, grid, block, smem, st, ...)                                                        \
+  do {                                                                                                   \
+    cudaError_t pe_ = ::dfv::launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__); \
+    if (pe_ != cudaSuccess) {                                                                            \
+      ::dfv::set_error("launch failed: %s (%s:%d)", cudaGetErrorString(pe_), __FILE__, __LINE__);        \
+      return DFV_ERR_CUDA;                                                                               \
+    }                                                                                                    \
+  } while (0)
+
 constexpr int kNT = 256;
 
 // Thread -> (column vector, row lane) mapping shared by the streaming kernels.
@@ -113,6 +123,7 @@ constexpr int kPipeU = 4;
 template <typename T>
 __global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw, long long rows_per_image, int C,
                                                       long long rows_per_chunk, float* __restrict__ partial) {
+  pdl_prologue();
   constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 16];
   const ColMap m(C);
@@ -191,6 +202,7 @@ __global__ void __launch_bounds__(256) bn_stats_finalize_kernel(const float* __r
                                                                float* __restrict__ mean, float* __restrict__ invstd,
                                                                float* __restrict__ running_mean,
                                                                float* __restrict__ running_var) {
+  pdl_prologue();
   __shared__ double sh[2][8][32];
   const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -214,6 +226,7 @@ __global__ void __launch_bounds__(256) bn_stats_from_sums_kernel(const double* _
                                                                 float momentum, float* __restrict__ mean,
                                                                 float* __restrict__ invstd, float* __restrict__ running_mean,
                                                                 float* __restrict__ running_var) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mu = acc[c] / count;
@@ -237,6 +250,7 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
                                                     const float* __restrict__ mask, T* __restrict__ out,
                                                     float* __restrict__ pool_partial, long long rows_per_image, int C,
                                                     long long rows_per_chunk) {
+  pdl_prologue();
   constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 8];
   const ColMap m(C);
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
                                                            const float* __restrict__ mask, T* __restrict__ du,
                                                            float* __restrict__ partial, long long rows_per_image, int C,
                                                            long long rows_per_chunk) {
+  pdl_prologue();
   __shared__ float sm[kNT * 16];
   const ColMap m(C);
   const int b = blockIdx.y;
@@ -477,6 +492,7 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
                                                              double count, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, float* __restrict__ coef) {
+  pdl_prologue();
   __shared__ double sh[2][8][32];
   const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
@@ -494,6 +510,7 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__
                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ coef,
                                                           T* __restrict__ draw, long long M, int C, long long rows_per_chunk) {
+  pdl_prologue();
   constexpr int U = Unroll<T>::U;
   const ColMap m(C);
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
@@ -546,6 +563,7 @@ template <typename T>
 __global__ void __launch_bounds__(kNT) dot_rows_kernel(const T* __restrict__ a, const T* __restrict__ d,
                                                       long long rows_per_image, int C, long long rows_per_chunk,
                                                       float* __restrict__ partial) {
+  pdl_prologue();
   __shared__ float sm[kNT * 8];
   const ColMap m(C);
   const int b = blockIdx.y;
@@ -587,6 +605,7 @@ __global__ void __cluster_dims__(kSeBwdCluster, 1, 1) __launch_bounds__(256, 2)
     se_bwd_image_kernel(const float* __restrict__ dgate_partial, int parts, const float* __restrict__ gate_f32,
                         const float* __restrict__ h1, const float* __restrict__ w1, const float* __restrict__ w2,
                         float* __restrict__ dz_out, float* __restrict__ dh1_out, float* __restrict__ dpool, int B, int C, int sq) {
+  pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float sm[];
@@ -693,6 +712,7 @@ __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __rest
                                                             float* __restrict__ dw1, float* __restrict__ db1,
                                                             float* __restrict__ dw2, float* __restrict__ db2, int B, int C,
                                                             int sq) {
+  pdl_prologue();
   extern __shared__ float sm[];   // hidden [B][jn], dh1 [B][jn] of this slice
   const int j0 = (int)((long long)sq * blockIdx.y / gridDim.y), j1 = (int)((long long)sq * (blockIdx.y + 1) / gridDim.y);
   const int jn = j1 - j0;
@@ -746,6 +766,7 @@ __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __rest
 // dst[r][c] (T) = src (fp32): same layout, or transposed (src is [cols][rows]).
 template <typename T>
 __global__ void cast_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int rows, int cols, int transpose) {
+  pdl_prologue();
   const long long n = (long long)rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -756,6 +777,7 @@ __global__ void cast_weight_kernel(const float* __restrict__ src, T* __restrict_
 
 // Depthwise weights: torch [C][1][k][k] -> [k*k][C] fp32, optionally with the taps flipped (dgrad of a stride-1 conv).
 __global__ void dw_weight_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int kk, int flip) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * kk) return;
   const int t = i / C, c = i % C;
@@ -763,6 +785,7 @@ __global__ void dw_weight_pack_kernel(const float* __restrict__ src, float* __re
 }
 // and back: gradient [k*k][C] -> torch layout [C][k*k]
 __global__ void dw_weight_unpack_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int kk) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * kk) return;
   const int c = i / kk, t = i % kk;
@@ -771,6 +794,7 @@ __global__ void dw_weight_unpack_kernel(const float* __restrict__ src, float* __
 
 // Counter-based uniform hash (splitmix64 finaliser): out[i] = u(seed, i) >= p ? 1 / (1 - p) : 0.
 __global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float p, unsigned long long seed) {
+  pdl_prologue();
   const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
@@ -784,6 +808,7 @@ __global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float 
 
 // out[c] = sum over rows of a[r][c]  (any C; small matrices: classifier bias gradients)
 __global__ void colsum_kernel(const float* __restrict__ a, int rows, int C, float* __restrict__ out) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
@@ -794,6 +819,7 @@ __global__ void colsum_kernel(const float* __restrict__ a, int rows, int C, floa
 // out = (a + b) * mask   (fp32; b / mask optional)
 __global__ void add_mul_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mask,
                                float* __restrict__ out, long long n) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = a[i];
     if (b) v += b[i];
@@ -805,6 +831,7 @@ __global__ void add_mul_kernel(const float* __restrict__ a, const float* __restr
 // fp32 [M][C] -> T [M][C] (and back): gradient hand-over between the fp32 attention block and the bf16 backbone.
 template <typename S, typename D>
 __global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, long long n) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v;
     if constexpr (sizeof(S) == 2) v = __bfloat162float(src[i]); else v = src[i];
@@ -849,10 +876,10 @@ int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, (double)B * rows_per_image * C * dtype_size(dtype), 3.0 * B * rows_per_image * C, st);
-  if (dtype == DFV_BF16) bn_stats_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)raw, rows_per_image, C, rpc, ws);
-  else bn_stats_kernel<float><<<grid, kNT, 0, st>>>((const float*)raw, rows_per_image, C, rpc, ws);
+  if (dtype == DFV_BF16) DFV_PDL((bn_stats_kernel<__nv_bfloat16>), grid, kNT, 0, st, (const __nv_bfloat16*)raw, rows_per_image, C, rpc, ws);
+  else DFV_PDL((bn_stats_kernel<float>), grid, kNT, 0, st, (const float*)raw, rows_per_image, C, rpc, ws);
   DFV_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, eps,
+  DFV_PDL(bn_stats_finalize_kernel, (C + 31) / 32, 256, 0, st, ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, eps,
                                                          momentum, mean, invstd, running_mean, running_var);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
@@ -863,7 +890,7 @@ int dfv_bn_stats_from_sums(const double* acc, int C, double count, float eps, fl
                            float* running_mean, float* running_var, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(acc && mean && invstd && C > 0 && count > 0, "dfv_bn_stats_from_sums: bad arguments");
-  bn_stats_from_sums_kernel<<<(C + 255) / 256, 256, 0, as_stream(stream)>>>(acc, C, count, eps, momentum, mean, invstd, running_mean,
+  DFV_PDL(bn_stats_from_sums_kernel, (C + 255) / 256, 256, 0, as_stream(stream), acc, C, count, eps, momentum, mean, invstd, running_mean,
                                                                           running_var);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
@@ -888,11 +915,11 @@ int dfv_bn_act_fwd(const void* raw, const float* mean, const float* invstd, cons
       DFV_CUDA(cudaFuncSetAttribute(bn_act_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStage));
       configured = true;
     }
-    bn_act_kernel<__nv_bfloat16, true><<<grid, kNT, kStage, st>>>((const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act, rowscale,
+    DFV_PDL((bn_act_kernel<__nv_bfloat16, true>), grid, kNT, kStage, st, (const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act, rowscale,
                                                                 (const __nv_bfloat16*)residual, mask, (__nv_bfloat16*)out,
                                                                 pool_partial, rows_per_image, C, rpc);
   } else {
-    bn_act_kernel<float, false><<<grid, kNT, 0, st>>>((const float*)raw, mean, invstd, gamma, beta, act, rowscale,
+    DFV_PDL((bn_act_kernel<float, false>), grid, kNT, 0, st, (const float*)raw, mean, invstd, gamma, beta, act, rowscale,
                                                     (const float*)residual, mask, (float*)out, pool_partial, rows_per_image, C, rpc);
   }
   DFV_LAUNCH_CHECK();
@@ -919,7 +946,7 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
       DFV_CUDA(cudaFuncSetAttribute(act_bn_bwd_kernel<T_, G_, U_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_));        \
       configured = true;                                                                                                            \
     }                                                                                                                               \
-    act_bn_bwd_kernel<T_, G_, U_, M_><<<grid, kNT, SMEM_, st>>>((const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act,       \
+    DFV_PDL((act_bn_bwd_kernel<T_, G_, U_, M_>), grid, kNT, SMEM_, st, (const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act,       \
                                                                (const T_*)gate, dpool, inv_hw, rowscale, mask, (T_*)du, ws,        \
                                                                rows_per_image, C, rpc);                                            \
   } while (0)
@@ -931,7 +958,7 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
   }
 #undef ABB
   DFV_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, st>>>(ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
+  DFV_PDL(bn_bwd_finalize_kernel, (C + 31) / 32, 256, 0, st, ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -947,10 +974,10 @@ int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const f
   blocks = (M + rpc - 1) / rpc;
   ProfScope prof(PK_BN, 3.0 * M * C * dtype_size(dtype), 6.0 * M * C, st);
   if (dtype == DFV_BF16)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<(unsigned)blocks, kNT, 0, st>>>((const __nv_bfloat16*)du, (const __nv_bfloat16*)raw, mean, invstd,
+    DFV_PDL((bn_bwd_apply_kernel<__nv_bfloat16>), (unsigned)blocks, kNT, 0, st, (const __nv_bfloat16*)du, (const __nv_bfloat16*)raw, mean, invstd,
                                                                         gamma, coef, (__nv_bfloat16*)draw, M, C, rpc);
   else
-    bn_bwd_apply_kernel<float><<<(unsigned)blocks, kNT, 0, st>>>((const float*)du, (const float*)raw, mean, invstd, gamma, coef, (float*)draw, M, C, rpc);
+    DFV_PDL((bn_bwd_apply_kernel<float>), (unsigned)blocks, kNT, 0, st, (const float*)du, (const float*)raw, mean, invstd, gamma, coef, (float*)draw, M, C, rpc);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -980,9 +1007,9 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_SE_GATE, 2.0 * B * rows_per_image * C * dtype_size(dtype), 2.0 * B * rows_per_image * C, st);
   if (dtype == DFV_BF16)
-    dot_rows_kernel<__nv_bfloat16><<<grid, kNT, 0, st>>>((const __nv_bfloat16*)da, (const __nv_bfloat16*)d, rows_per_image, C, rpc, partial);
+    DFV_PDL((dot_rows_kernel<__nv_bfloat16>), grid, kNT, 0, st, (const __nv_bfloat16*)da, (const __nv_bfloat16*)d, rows_per_image, C, rpc, partial);
   else
-    dot_rows_kernel<float><<<grid, kNT, 0, st>>>((const float*)da, (const float*)d, rows_per_image, C, rpc, partial);
+    DFV_PDL((dot_rows_kernel<float>), grid, kNT, 0, st, (const float*)da, (const float*)d, rows_per_image, C, rpc, partial);
   DFV_LAUNCH_CHECK();
   DFV_REQUIRE(squeeze <= 128, "dfv_se_bwd: squeeze width %d > 128", squeeze);
   {
@@ -991,9 +1018,9 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
     const size_t smem = sizeof(float) * ((size_t)img * cper + (size_t)2 * img * squeeze + (size_t)8 * img * squeeze);
     const unsigned grid_i = (unsigned)((B + img - 1) / img) * kSeBwdCluster;
     if (img == 4)
-      se_bwd_image_kernel<4><<<grid_i, 256, smem, st>>>(partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, B, C, squeeze);
+      DFV_PDL((se_bwd_image_kernel<4>), grid_i, 256, smem, st, partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, B, C, squeeze);
     else
-      se_bwd_image_kernel<1><<<grid_i, 256, smem, st>>>(partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, B, C, squeeze);
+      DFV_PDL((se_bwd_image_kernel<1>), grid_i, 256, smem, st, partial, (int)chunks, gate_f32, h1, w_reduce, w_expand, dz, dh1, dpool, B, C, squeeze);
     DFV_LAUNCH_CHECK();
   }
   const int slices = std::max(1, std::min(squeeze / 4, (2 * num_sms() * 128 + C - 1) / C));
@@ -1001,7 +1028,7 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
   const size_t smem2 = (size_t)2 * B * jn_max * sizeof(float);
   DFV_REQUIRE(smem2 <= 160 * 1024, "dfv_se_bwd: batch too large for the weight-gradient kernel (B * squeeze slice = %d)", B * jn_max);
   if (smem2 > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(se_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  se_bwd_weights_kernel<<<dim3((C + 127) / 128, slices), 128, smem2, st>>>(dz, dh1, pooled, h1, dw_reduce, db_reduce, dw_expand, db_expand, B, C, squeeze);
+  DFV_PDL(se_bwd_weights_kernel, dim3((C + 127) / 128, slices), 128, smem2, st, dz, dh1, pooled, h1, dw_reduce, db_reduce, dw_expand, db_expand, B, C, squeeze);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1011,8 +1038,8 @@ int dfv_cast_weight(const float* src, void* dst, int dtype, int rows, int cols, 
   DFV_REQUIRE(src && dst && valid_dtype(dtype) && rows > 0 && cols > 0, "dfv_cast_weight: bad arguments");
   const long long n = (long long)rows * cols;
   const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * num_sms());
-  if (dtype == DFV_BF16) cast_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst, rows, cols, transpose);
-  else cast_weight_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(src, (float*)dst, rows, cols, transpose);
+  if (dtype == DFV_BF16) DFV_PDL((cast_weight_kernel<__nv_bfloat16>), blocks, 256, 0, as_stream(stream), src, (__nv_bfloat16*)dst, rows, cols, transpose);
+  else DFV_PDL((cast_weight_kernel<float>), blocks, 256, 0, as_stream(stream), src, (float*)dst, rows, cols, transpose);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1021,7 +1048,7 @@ int dfv_dw_weight_pack(const float* src_ckk, float* dst_kkc, int C, int kernel, 
   DFV_TRY(check_device());
   DFV_REQUIRE(src_ckk && dst_kkc && C > 0 && kernel > 0, "dfv_dw_weight_pack: bad arguments");
   const int n = C * kernel * kernel;
-  dw_weight_pack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(src_ckk, dst_kkc, C, kernel * kernel, flip);
+  DFV_PDL(dw_weight_pack_kernel, (n + 255) / 256, 256, 0, as_stream(stream), src_ckk, dst_kkc, C, kernel * kernel, flip);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1030,7 +1057,7 @@ int dfv_dw_weight_unpack(const float* src_kkc, float* dst_ckk, int C, int kernel
   DFV_TRY(check_device());
   DFV_REQUIRE(src_kkc && dst_ckk && C > 0 && kernel > 0, "dfv_dw_weight_unpack: bad arguments");
   const int n = C * kernel * kernel;
-  dw_weight_unpack_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(src_kkc, dst_ckk, C, kernel * kernel);
+  DFV_PDL(dw_weight_unpack_kernel, (n + 255) / 256, 256, 0, as_stream(stream), src_kkc, dst_ckk, C, kernel * kernel);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1039,7 +1066,7 @@ int dfv_dropout_mask(float* out, long long n, float p, unsigned long long seed, 
   DFV_TRY(check_device());
   DFV_REQUIRE(out && n > 0 && p >= 0.f && p <= 1.f, "dfv_dropout_mask: bad arguments");
   const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * num_sms());
-  dropout_mask_kernel<<<blocks, 256, 0, as_stream(stream)>>>(out, n, p, seed);
+  DFV_PDL(dropout_mask_kernel, blocks, 256, 0, as_stream(stream), out, n, p, seed);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1047,7 +1074,7 @@ int dfv_dropout_mask(float* out, long long n, float p, unsigned long long seed, 
 int dfv_colsum(const float* a, int rows, int C, float* out, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(a && out && rows > 0 && C > 0, "dfv_colsum: bad arguments");
-  colsum_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(a, rows, C, out);
+  DFV_PDL(colsum_kernel, (C + 127) / 128, 128, 0, as_stream(stream), a, rows, C, out);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1056,7 +1083,7 @@ int dfv_add_mul(const float* a, const float* b, const float* mask, float* out, l
   DFV_TRY(check_device());
   DFV_REQUIRE(a && out && n > 0, "dfv_add_mul: bad arguments");
   const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * num_sms());
-  add_mul_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, b, mask, out, n);
+  DFV_PDL(add_mul_kernel, blocks, 256, 0, as_stream(stream), a, b, mask, out, n);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1070,8 +1097,8 @@ int dfv_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long l
     DFV_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * dtype_size(src_dtype), cudaMemcpyDeviceToDevice, st));
     return DFV_OK;
   }
-  if (src_dtype == DFV_F32) convert_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
-  else convert_kernel<__nv_bfloat16, float><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  if (src_dtype == DFV_F32) DFV_PDL((convert_kernel<float, __nv_bfloat16>), blocks, 256, 0, st, (const float*)src, (__nv_bfloat16*)dst, n);
+  else DFV_PDL((convert_kernel<__nv_bfloat16, float>), blocks, 256, 0, st, (const __nv_bfloat16*)src, (float*)dst, n);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
