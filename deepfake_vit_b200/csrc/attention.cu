@@ -17,6 +17,7 @@ namespace dfv {
 __global__ void heat_raw_kernel(const float* __restrict__ lm, const float* __restrict__ w5, float* __restrict__ raw,
                                 uint32_t* __restrict__ gmax, float* __restrict__ scaled_xy, int B, int H, int W,
                                 float sx, float sy, float denom, int group) {
+  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = H * W;
   if (idx >= B * HW) return;
@@ -46,6 +47,7 @@ __global__ void heat_raw_kernel(const float* __restrict__ lm, const float* __res
 
 __global__ void heat_norm_kernel(const float* __restrict__ raw, const uint32_t* __restrict__ gmax,
                                  float* __restrict__ heat, int B, int HW, int group) {
+  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * HW) return;
   uint32_t key = gmax[(idx / HW) / group];
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_kernel(
     const float* __restrict__ w2t, const float* __restrict__ sa_w, float* __restrict__ features,
     float* __restrict__ channel_gate, float* __restrict__ spatial_gate, int H, int W, int C, int hidden,
     int use_channel, int use_spatial) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int HW = H * W;
   float* a_lm = sm;                 // [HW]   landmark gate (1 if absent)
@@ -213,10 +216,10 @@ extern "C" int dfv_landmark_heatmap_fwd(const float* landmarks, const float* wei
   const float denom = (float)(2.0 * (double)sigma * (double)sigma);
   const int total = B * H * W;
   ProfScope prof(PK_HEATMAP, 4.0 * (B * 10.0 + 3.0 * total), 60.0 * total, st);
-  heat_raw_kernel<<<(total + 255) / 256, 256, 0, st>>>(landmarks, weights5, raw_ws, max_ws, scaled_xy, B, H, W, sx, sy,
+  DFV_PDL((heat_raw_kernel), (total + 255) / 256, 256, 0, st, landmarks, weights5, raw_ws, max_ws, scaled_xy, B, H, W, sx, sy,
                                                       denom, group);
   DFV_LAUNCH_CHECK();
-  heat_norm_kernel<<<(total + 255) / 256, 256, 0, st>>>(raw_ws, max_ws, heat, B, H * W, group);
+  DFV_PDL((heat_norm_kernel), (total + 255) / 256, 256, 0, st, raw_ws, max_ws, heat, B, H * W, group);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -240,12 +243,12 @@ extern "C" int dfv_hybrid_attention_fwd(const void* fmap, const float* heat, con
   if (dtype == DFV_BF16) {
     auto k = hybrid_attention_kernel<__nv_bfloat16>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k<<<B, 256, smem, st>>>((const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2_t, sa_w, features, channel_gate, spatial_gate, H, W,
+    DFV_PDL((k), B, 256, smem, st, (const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2_t, sa_w, features, channel_gate, spatial_gate, H, W,
                             C, hidden, use_channel, use_spatial);
   } else {
     auto k = hybrid_attention_kernel<float>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k<<<B, 256, smem, st>>>((const float*)fmap, heat, ca_w1, ca_w2_t, sa_w, features, channel_gate, spatial_gate, H, W, C,
+    DFV_PDL((k), B, 256, smem, st, (const float*)fmap, heat, ca_w1, ca_w2_t, sa_w, features, channel_gate, spatial_gate, H, W, C,
                             hidden, use_channel, use_spatial);
   }
   DFV_LAUNCH_CHECK();

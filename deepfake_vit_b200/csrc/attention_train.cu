@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
     const T* __restrict__ fmap, const float* __restrict__ heat, const float* __restrict__ w1,
     const float* __restrict__ w2, const float* __restrict__ sa_w, float* __restrict__ features, AttnSaved sv, int H,
     int W, int C, int hidden, int use_channel, int use_spatial) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int HW = H * W;
   float* a_lm = sm;
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
     const float* __restrict__ w2, const float* __restrict__ sa_w, const float* __restrict__ df, AttnSaved sv,
     T* __restrict__ dx, float* __restrict__ dA, float* __restrict__ dz_out, float* __restrict__ dhpre_out,
     float* __restrict__ dsa_w, int H, int W, int C, int hidden, int use_channel, int use_spatial) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int HW = H * W;
   float* a_lm = sm;                 // [HW]
@@ -378,6 +380,7 @@ __global__ void __launch_bounds__(128) ca_wgrad_kernel(const float* __restrict__
                                                       const float* __restrict__ hpre, const float* __restrict__ avg,
                                                       const float* __restrict__ mx, float* __restrict__ dw1,
                                                       float* __restrict__ dw2, int B, int C, int hidden) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   #pragma unroll 8
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(256) heat_bwd_kernel(const float* __restrict__
                                                       const float* __restrict__ raw, const uint32_t* __restrict__ gmax,
                                                       const float* __restrict__ dA, float* __restrict__ dw5, int B, int H,
                                                       int W, float sx, float sy, float denom, int group) {
+  pdl_prologue();
   __shared__ float red[8][6];
   __shared__ float s_dmax, s_ties;
   const int HW = H * W, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -512,11 +516,11 @@ int dfv_hybrid_attention_train_fwd(const void* fmap, const float* heat, const fl
   if (dtype == DFV_BF16) {
     auto k = hybrid_attention_train_fwd_kernel<__nv_bfloat16>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k<<<B, 256, smem, st>>>((const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
+    DFV_PDL((k), B, 256, smem, st, (const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
   } else {
     auto k = hybrid_attention_train_fwd_kernel<float>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k<<<B, 256, smem, st>>>((const float*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
+    DFV_PDL((k), B, 256, smem, st, (const float*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
   }
   DFV_LAUNCH_CHECK();
   return DFV_OK;
@@ -551,17 +555,17 @@ int dfv_hybrid_attention_bwd(const void* fmap, const float* heat, const float* c
   if (dtype == DFV_BF16) {
     auto k = hybrid_attention_bwd_kernel<__nv_bfloat16>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k<<<B, 512, smem, st>>>((const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2, sa_w, dfeatures, sv, (__nv_bfloat16*)dfmap, dheat, dz, dhpre,
+    DFV_PDL((k), B, 512, smem, st, (const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2, sa_w, dfeatures, sv, (__nv_bfloat16*)dfmap, dheat, dz, dhpre,
                             dsa_w, H, W, C, hidden, use_channel, use_spatial);
   } else {
     auto k = hybrid_attention_bwd_kernel<float>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k<<<B, 512, smem, st>>>((const float*)fmap, heat, ca_w1, ca_w2, sa_w, dfeatures, sv, (float*)dfmap, dheat, dz, dhpre, dsa_w, H, W, C,
+    DFV_PDL((k), B, 512, smem, st, (const float*)fmap, heat, ca_w1, ca_w2, sa_w, dfeatures, sv, (float*)dfmap, dheat, dz, dhpre, dsa_w, H, W, C,
                             hidden, use_channel, use_spatial);
   }
   DFV_LAUNCH_CHECK();
   if (use_channel) {
-    ca_wgrad_kernel<<<(C + 127) / 128, 128, 0, st>>>(dz, dhpre, sv.hpre, sv.avg, sv.mx, dca_w1, dca_w2, B, C, hidden);
+    DFV_PDL((ca_wgrad_kernel), (C + 127) / 128, 128, 0, st, dz, dhpre, sv.hpre, sv.avg, sv.mx, dca_w1, dca_w2, B, C, hidden);
     DFV_LAUNCH_CHECK();
   }
   return DFV_OK;
@@ -578,7 +582,7 @@ int dfv_landmark_heatmap_bwd(const float* landmarks, const float* weights5, cons
   if (group <= 0 || group > B) group = B;
   const float sx = (float)((double)W / (double)ref_size), sy = (float)((double)H / (double)ref_size);
   const float denom = (float)(2.0 * (double)sigma * (double)sigma);
-  heat_bwd_kernel<<<1, 256, 0, as_stream(stream)>>>(landmarks, weights5, raw_ws, max_ws, dheat, dweights5, B, H, W, sx, sy, denom, group);
+  DFV_PDL((heat_bwd_kernel), 1, 256, 0, as_stream(stream), landmarks, weights5, raw_ws, max_ws, dheat, dweights5, B, H, W, sx, sy, denom, group);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

@@ -15,6 +15,7 @@ namespace dfv {
 __global__ void clip_aggregate_kernel(const float* __restrict__ logits, int n_clips, int frames, int n_classes,
                                       float* __restrict__ mean_logits, float* __restrict__ fake_prob,
                                       int* __restrict__ labels, float threshold) {
+  pdl_prologue();
   const int clip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (clip >= n_clips) return;
   const float* l = logits + (size_t)clip * frames * n_classes;
@@ -43,6 +44,7 @@ __global__ void clip_aggregate_kernel(const float* __restrict__ logits, int n_cl
 // thread = 8 channels of one image; rows are walked with 4 loads in flight
 template <typename T>
 __global__ void global_avg_pool_kernel(const T* __restrict__ x, float* __restrict__ out, int B, long long rows, int C) {
+  pdl_prologue();
   const int CV = C >> 3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * CV) return;
@@ -65,6 +67,7 @@ __global__ void global_avg_pool_kernel(const T* __restrict__ x, float* __restric
 
 // one warp per row: x / max(||x||_2, eps)
 __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int D, float eps) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= B) return;
   float s = 0.f;
@@ -79,6 +82,7 @@ __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restri
 
 // sum of squares of the flat gradient buffer: per-CTA partial -> one double atomic
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  pdl_prologue();
   __shared__ double red[8];
   double s = 0.0;       // double accumulation: the clip coefficient inherits this sum's relative error
   const long long n4 = n >> 2;
@@ -107,6 +111,7 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
                                                         float max_norm, float grad_scale, float decay, float beta1, float omb1,
                                                         float beta2, float omb2, float eps, float step_size, float bc2_sqrt,
                                                         float* __restrict__ total_norm_out) {
+  pdl_prologue();
   const float total = sqrtf((float)*sqnorm) * grad_scale;
   float coef = grad_scale;
   if (max_norm > 0.f) coef *= fminf(max_norm / (total + 1e-6f), 1.0f);
@@ -135,7 +140,7 @@ int dfv_clip_aggregate(const float* logits, int n_clips, int frames_per_clip, in
   DFV_TRY(check_device());
   DFV_REQUIRE(logits && mean_logits && fake_prob && labels, "dfv_clip_aggregate: null pointer");
   DFV_REQUIRE(n_clips > 0 && frames_per_clip > 0 && n_classes >= 2, "dfv_clip_aggregate: bad shape");
-  clip_aggregate_kernel<<<(n_clips + 3) / 4, 128, 0, as_stream(stream)>>>(logits, n_clips, frames_per_clip, n_classes, mean_logits,
+  DFV_PDL((clip_aggregate_kernel), (n_clips + 3) / 4, 128, 0, as_stream(stream), logits, n_clips, frames_per_clip, n_classes, mean_logits,
                                                                         fake_prob, labels, threshold);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
@@ -146,9 +151,9 @@ int dfv_global_avg_pool(const void* x, int dtype, float* out, int B, long long r
   DFV_REQUIRE(x && out && valid_dtype(dtype) && B > 0 && rows > 0 && C > 0 && C % 8 == 0, "dfv_global_avg_pool: bad arguments");
   const long long n = (long long)B * (C / 8);
   if (dtype == DFV_BF16)
-    global_avg_pool_kernel<__nv_bfloat16><<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, out, B, rows, C);
+    DFV_PDL((global_avg_pool_kernel<__nv_bfloat16>), (unsigned)((n + 127) / 128), 128, 0, as_stream(stream), (const __nv_bfloat16*)x, out, B, rows, C);
   else
-    global_avg_pool_kernel<float><<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>((const float*)x, out, B, rows, C);
+    DFV_PDL((global_avg_pool_kernel<float>), (unsigned)((n + 127) / 128), 128, 0, as_stream(stream), (const float*)x, out, B, rows, C);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -156,7 +161,7 @@ int dfv_global_avg_pool(const void* x, int dtype, float* out, int B, long long r
 int dfv_l2_normalize(const float* x, float* y, int B, int D, float eps, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(x && y && B > 0 && D > 0, "dfv_l2_normalize: bad arguments");
-  l2_normalize_kernel<<<(B + 3) / 4, 128, 0, as_stream(stream)>>>(x, y, B, D, eps);
+  DFV_PDL((l2_normalize_kernel), (B + 3) / 4, 128, 0, as_stream(stream), x, y, B, D, eps);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -172,11 +177,11 @@ int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float
   cudaStream_t st = as_stream(stream);
   DFV_CUDA(cudaMemsetAsync(sqnorm_ws, 0, sizeof(double), st));
   const unsigned blocks = (unsigned)std::min<long long>((n / 4 + 255) / 256 + 1, 4LL * num_sms());
-  grad_sqnorm_kernel<<<blocks, 256, 0, st>>>(grads, n, sqnorm_ws);
+  DFV_PDL((grad_sqnorm_kernel), blocks, 256, 0, st, grads, n, sqnorm_ws);
   DFV_LAUNCH_CHECK();
   // hyper-parameter arithmetic in double on the host, as the Python optimizer does it
   const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
-  clip_adamw_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, sqnorm_ws, (float)max_norm, (float)grad_scale,
+  DFV_PDL((clip_adamw_kernel), blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, sqnorm_ws, (float)max_norm, (float)grad_scale,
                                            (float)(1.0 - lr * weight_decay), (float)beta1, (float)(1.0 - beta1), (float)beta2,
                                            (float)(1.0 - beta2), (float)eps, (float)(lr / bc1), (float)std::sqrt(bc2), total_norm_out);
   DFV_LAUNCH_CHECK();

@@ -286,3 +286,15 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
 
 #endif  // __CUDACC__
 }  // namespace dfv
+
+#ifdef __CUDACC__
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute (common.cuh)
+#define DFV_PDL(kern, grid, block, smem, st, ...)                                                        \
+  do {                                                                                                   \
+    cudaError_t pe_ = ::dfv::launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__); \
+    if (pe_ != cudaSuccess) {                                                                            \
+      ::dfv::set_error("launch failed: %s (%s:%d)", cudaGetErrorString(pe_), __FILE__, __LINE__);        \
+      return DFV_ERR_CUDA;                                                                               \
+    }                                                                                                    \
+  } while (0)
+#endif

@@ -567,6 +567,7 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
 template <typename T>
 __global__ void fold_weight_kernel(const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ wf,
                                    float* __restrict__ bf, int N, int K, int f) {
+  pdl_prologue();
   const int total = f * N * f * K;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int col = i % (f * K), row = i / (f * K);
@@ -579,6 +580,7 @@ __global__ void fold_weight_kernel(const T* __restrict__ w, const float* __restr
 }
 template <typename T>
 __global__ void tile_gate_kernel(const T* __restrict__ g, T* __restrict__ gf, int B, int K, int f) {
+  pdl_prologue();
   const int total = B * f * K;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int b = i / (f * K), k = (i % (f * K)) % K;
@@ -655,10 +657,10 @@ extern "C" int dfv_pw_conv_fwd(const void* x, const void* w, const float* bias, 
   float* fb = reinterpret_cast<float*>(base + align_up((size_t)kFoldWElems * 2, 1024));
   __nv_bfloat16* fg = reinterpret_cast<__nv_bfloat16*>(base + align_up((size_t)kFoldWElems * 2, 1024) + align_up((size_t)kFoldBias * 4, 1024));
   cudaStream_t st = as_stream(stream);
-  fold_weight_kernel<__nv_bfloat16><<<16, 256, 0, st>>>((const __nv_bfloat16*)w, bias, fw, fb, N, K, f);
+  DFV_PDL((fold_weight_kernel<__nv_bfloat16>), 16, 256, 0, st, (const __nv_bfloat16*)w, bias, fw, fb, N, K, f);
   DFV_LAUNCH_CHECK();
   if (gate) {
-    tile_gate_kernel<__nv_bfloat16><<<32, 256, 0, st>>>((const __nv_bfloat16*)gate, fg, B, K, f);
+    DFV_PDL((tile_gate_kernel<__nv_bfloat16>), 32, 256, 0, st, (const __nv_bfloat16*)gate, fg, B, K, f);
     DFV_LAUNCH_CHECK();
   }
   return dfv_pw_gemm_fwd(x, fw, fb, gate ? fg : nullptr, rows_per_image / f, residual, out, dtype, M / f, f * K, f * N, act, stream);

@@ -16,6 +16,7 @@ constexpr int kLinCols = 128;   // output columns per CTA (4 per lane)
 __global__ void __launch_bounds__(256) linear_splitk_kernel(const float* __restrict__ in, const float* __restrict__ w_t,
                                                            const float* __restrict__ bias, float* __restrict__ out, int B,
                                                            int din, int dout, int relu) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float* xin = sm;                                  // [kLinRows][din]
   float* red = sm + (size_t)kLinRows * din;         // [8 warps][kLinRows][kLinCols]
@@ -100,7 +101,7 @@ extern "C" int dfv_mlp_head_fwd(const float* features, const float* const* w_t, 
     const size_t smem = sizeof(float) * ((size_t)kLinRows * dims[l] + (size_t)8 * kLinRows * kLinCols);
     DFV_REQUIRE(smem <= 160 * 1024, "dfv_mlp_head_fwd: layer too wide (%d)", dims[l]);
     dim3 grid((unsigned)((B + kLinRows - 1) / kLinRows), (unsigned)((dims[l + 1] + kLinCols - 1) / kLinCols));
-    linear_splitk_kernel<<<grid, 256, smem, as_stream(stream)>>>(in, w_t[l], b[l], out, B, dims[l], dims[l + 1], last ? 0 : 1);
+    DFV_PDL((linear_splitk_kernel), grid, 256, smem, as_stream(stream), in, w_t[l], b[l], out, B, dims[l], dims[l + 1], last ? 0 : 1);
     DFV_LAUNCH_CHECK();
     in = out;
   }

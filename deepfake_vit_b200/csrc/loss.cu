@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) combined_loss_kernel(const float* __restr
                                                            float w_con, float* __restrict__ losses,
                                                            float* __restrict__ dlogits, float* __restrict__ dfeat,
                                                            int B, int C, int D) {
+  pdl_prologue();
   __shared__ float red[3][8];
   __shared__ float s_wsum, s_ce_num, s_focal;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -133,7 +134,7 @@ extern "C" int dfv_combined_loss_fwd_bwd(const float* logits, const int64_t* tar
   if (has_contrastive) *has_contrastive = con ? 1 : 0;
   // weights <= 0 switch a term off exactly as `self.weights[k] > 0` does (losses.py:216,222,228)
   ProfScope prof(PK_LOSS, 4.0 * B * (2.0 * C + 2.0 * D), 10.0 * B * (C + D), as_stream(stream));
-  combined_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, (const long long*)targets, con ? features : nullptr,
+  DFV_PDL((combined_loss_kernel), 1, 256, 0, as_stream(stream), logits, (const long long*)targets, con ? features : nullptr,
                                                         class_weights, w_ce > 0.f ? w_ce : 0.f,
                                                         w_focal > 0.f ? w_focal : 0.f, con ? w_contrastive : 0.f, losses,
                                                         dlogits, con ? dfeatures : nullptr, B, C, D);

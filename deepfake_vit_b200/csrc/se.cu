@@ -21,6 +21,7 @@ __global__ void __cluster_dims__(kSeCluster, 1, 1) __launch_bounds__(256, 2)
                    const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
                    GT* __restrict__ gate, int B, int C, int sq, float* __restrict__ pooled_out,
                    float* __restrict__ h1_out, float* __restrict__ gate_f32) {
+  pdl_prologue();
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float sm[];
@@ -161,7 +162,7 @@ static int launch_se(const float* pool_partial, int parts, float inv_hw, const f
       DFV_CUDA(cudaFuncSetAttribute(se_gate_kernel<IMG_, GT_, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
       configured = true;                                                                                                      \
     }                                                                                                                         \
-    se_gate_kernel<IMG_, GT_, kTrain><<<grid, 256, smem, st>>>(pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand, \
+    DFV_PDL((se_gate_kernel<IMG_, GT_, kTrain>), grid, 256, smem, st, pool_partial, parts, inv_hw, w_reduce, b_reduce, w_expand, b_expand, \
                                                               (GT_*)gate, B, C, squeeze, pooled, h1, gate_f32);               \
   } while (0)
   if (gate_dtype == DFV_BF16) {

@@ -249,6 +249,7 @@ int validate(const dfv_train_args* a, bool bwd) {
 
 // torch [48][3][3][3] -> stem kernel layout [kh][kw][ci][co]
 __global__ void stem_weight_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int CO) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 27 * CO) return;
   const int co = i % CO, t = i / CO;           // t = (kh * 3 + kw) * 3 + ci
@@ -328,7 +329,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
 
   // ---- stem
   DFV_REQUIRE(P(-1, DFV_TG_STEM_W) && P(-1, DFV_TG_STEM_G) && P(-1, DFV_TG_STEM_B), "dfv_train_fwd: stem parameters missing");
-  stem_weight_pack_kernel<<<(27 * stem_c + 255) / 256, 256, 0, st>>>(P(-1, DFV_TG_STEM_W), ar.stem_w, stem_c);
+  DFV_PDL((stem_weight_pack_kernel), (27 * stem_c + 255) / 256, 256, 0, st, P(-1, DFV_TG_STEM_W), ar.stem_w, stem_c);
   DFV_LAUNCH_CHECK();
   DFV_TRY(dfv_stem_conv_fwd(a->images_nchw, ar.stem_w, ar.zero_bias, ar.s_raw, dtype, B, a->H, a->W, stem_c, DFV_ACT_NONE, stream));
   DFV_TRY(dfv_bn_stats_fwd(ar.s_raw, dtype, B, (long long)s.Hs * s.Ws, stem_c, eps, mom, ar.sm, ar.si, PW(-1, DFV_TG_STEM_RM),
