@@ -119,6 +119,9 @@ struct TcParams {
   int n_tiles_n;
   long long n_tiles;  // total tiles
   long long tiles_per_cta;   // contiguous tile range per CTA
+  int b_res;          // 1: weight-stationary -- the CTA keeps ONE N tile of the weight (all of K) in shared memory
+  int m_splits;       //    and walks tiles_per_cta consecutive M tiles; blockIdx = n_tile * m_splits + m_split
+  long long n_tiles_m;
   int k_blocks;
   int stages;
   int rows_per_image;
@@ -131,6 +134,7 @@ struct __align__(8) TcBarriers {
   uint64_t empty[kMaxStages];   // MMAs that read the stage completed
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t b_full;              // weight-stationary mode: the resident weight tile landed
   uint32_t tmem_base;
 };
 
@@ -157,21 +161,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the dynamic-smem base
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // weight-stationary plans are made for ungated GEMMs only: the gated variants (at the register cap) compile without it
+  const bool b_res = !kHasScale && p.b_res != 0;
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = b_res ? a_bytes : a_bytes + b_bytes;        // weight-stationary: stages carry A only
   unsigned char* tiles = smem;
   constexpr int kNumEpiW = kNumWorkers - (kHasScale ? 8 : 0);
-  unsigned char* staging = smem + (size_t)p.stages * stage_bytes;            // [epilogue warp][nbuf][nb][32 rows x bw]
+  unsigned char* bres = smem + (size_t)p.stages * stage_bytes;               // [k_blocks][BN x 64] resident weight tile
+  unsigned char* staging = bres + (b_res ? (size_t)p.k_blocks * b_bytes : 0);   // [epilogue warp][nbuf][nb][32 rows x bw]
   const uint32_t warp_stage_bytes = (uint32_t)p.cw * 64;                     // 32 rows x cw columns x 2 B
   float* bias_sm = reinterpret_cast<float*>(staging + (size_t)kNumEpiW * p.nbuf * warp_stage_bytes);
   const int n_pad = p.n_tiles_n * p.BN;
   __nv_bfloat16* gate_sm = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(bias_sm) + (size_t)((n_pad * 4 + 15) / 16) * 16);
   const int k_pad = p.k_blocks * kBK;      // gate rows of the (at most two) images a tile touches: [2][k_pad]
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(reinterpret_cast<unsigned char*>(gate_sm) + (kHasScale ? (size_t)2 * k_pad * 2 : 0));
-  // contiguous tile range per CTA (m-major): consecutive tiles stay inside one image for rows_per_image / 128 tiles
-  const long long t_begin = (long long)blockIdx.x * p.tiles_per_cta;
-  const long long t_end = min(t_begin + p.tiles_per_cta, p.n_tiles);
+  // contiguous tile range per CTA (m-major): consecutive tiles stay inside one image for rows_per_image / 128 tiles.
+  // Weight-stationary mode: one N tile, tiles_per_cta consecutive M tiles.
+  const long long t_begin = b_res ? (long long)(blockIdx.x % p.m_splits) * p.tiles_per_cta : (long long)blockIdx.x * p.tiles_per_cta;
+  const long long t_end = min(t_begin + p.tiles_per_cta, b_res ? p.n_tiles_m : p.n_tiles);
+  const int nt_res = b_res ? (int)(blockIdx.x / p.m_splits) : 0;
+  auto tile_m = [&](long long t) -> long long { return b_res ? t : t / p.n_tiles_n; };
+  auto tile_n = [&](long long t) -> int { return b_res ? nt_res : (int)(t % p.n_tiles_n); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kNumXform = kHasScale ? 8 : 0;
@@ -189,6 +200,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       mbar_init(&bars->tmem_full[s], 1);
       mbar_init(&bars->tmem_empty[s], kNumEpi);
     }
+    mbar_init(&bars->b_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -205,15 +217,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (b_res && t_begin < t_end) {
+        mbar_expect_tx(&bars->b_full, (uint32_t)p.k_blocks * b_bytes);
+        for (int kb = 0; kb < p.k_blocks; ++kb) tma_load_2d(bres + (size_t)kb * b_bytes, &tm_b, &bars->b_full, kb * kBK, nt_res * p.BN);
+      }
       for (long long t = t_begin; t < t_end; ++t) {
-        const long long mt = t / p.n_tiles_n;
-        const int nt = (int)(t % p.n_tiles_n);
+        const long long mt = tile_m(t);
+        const int nt = tile_n(t);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1, 1);
           unsigned char* sa = tiles + (size_t)stage * stage_bytes;
           mbar_expect_tx(&bars->full[stage], stage_bytes);
           tma_load_2d(sa, &tm_a, &bars->full[stage], kb * kBK, (int)(mt * kBM));
-          tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
+          if (!b_res) tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -226,6 +242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (b_res && t_begin < t_end) mbar_wait(&bars->b_full, 0, 6);
       for (long long t = t_begin; t < t_end; ++t, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -236,7 +253,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           mbar_wait(kHasScale ? &bars->ready[stage] : &bars->full[stage], phase, 3);
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
-          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + a_bytes);
+          const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(b_res ? smem_u32(bres + (size_t)kb * b_bytes) : sa + a_bytes);
           const int k_left = p.K - kb * kBK;
           const int ksteps = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
           for (int k = 0; k < ksteps; ++k)
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (long long t = t_begin; t < t_end; ++t) {
-      const long long m0 = (t / p.n_tiles_n) * kBM;
+      const long long m0 = tile_m(t) * kBM;
       const long long m = m0 + row;
       const bool valid = m < p.M;
       const long long img_lo = m0 / p.rows_per_image;
@@ -365,15 +382,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       *reinterpret_cast<uint4*>(dst) = pk;
     };
     int it = 0;
+    int n_stores = 0;     // tiles THIS warp stored: picks the staging buffer (a warp whose column part lies beyond N on
+                          // some N tiles skips those, so the tile counter's parity would reuse a buffer still being read)
     for (long long t = t_begin; t < t_end; ++t, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const long long m0 = (t / p.n_tiles_n) * kBM + q * 32;   // first row of this warp
+      const long long m0 = tile_m(t) * kBM + q * 32;           // first row of this warp
       const long long m = m0 + lane;
-      const int nt = (int)(t % p.n_tiles_n);
+      const int nt = tile_n(t);
       const int n_lo = nt * p.BN + col_lo;                     // first output column of this warp
       const bool active = col_lo < p.BN && n_lo < p.N && m0 < p.M;
-      unsigned char* stg = my_stage + (size_t)(p.nbuf == 2 ? (it & 1) : 0) * warp_stage_bytes;
+      unsigned char* stg = my_stage + (size_t)(p.nbuf == 2 ? (n_stores & 1) : 0) * warp_stage_bytes;
       const __nv_bfloat16* rrow = kRes ? residual + (size_t)m * p.N : nullptr;
       // residual of the first two chunks: requested before anything else so its latency hides behind the waits
       uint4 rr[4];
@@ -442,6 +461,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      if (active) ++n_stores;
       __syncwarp();
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before exit
@@ -456,15 +476,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
 }
 
-static int launch_tc(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
-                     const void* residual, void* out, long long M, int K, int N, int act, cudaStream_t st) {
-  TcParams p;
+// Tile plan of one GEMM: N tile, streaming vs weight-stationary, pipeline depth, grid.
+static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int K, int N, bool scaled, int rows_per_image, int act) {
   p.M = M;
   p.K = K;
   p.N = N;
   // N tile: BN = (column parts) x cw, cw in {16, 32, 48, 64, 96, 128} so that every epilogue warp owns whole
-  // TMA-store boxes.  Cost model: padded columns plus a fixed per-tile charge (A is re-fetched per N tile).
-  const int parts = a_scale ? 2 : 4;
+  // TMA-store boxes.  Streaming cost model: padded columns plus a fixed per-tile charge (A is re-fetched per N tile).
+  const int parts = scaled ? 2 : 4;
   static const int cws[6] = {16, 32, 48, 64, 96, 128};
   long long best_cost = -1, best_pad = 0;
   p.BN = 0;
@@ -472,33 +491,122 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
     const int bn = parts * cws[ci];
     if (bn > 256) continue;
     const long long nt = (N + bn - 1) / bn, cost = nt * (bn + 96), pad = nt * bn;
-    if (best_cost < 0 || cost < best_cost || (cost == best_cost && pad < best_pad)) {
+    // ties: a gated GEMM repeats the SE transform of A per N tile -> fewer, wider tiles (1632 -> 272: 2 x 192 beats
+    // 3 x 96 by 17%); otherwise fewer padded columns
+    if (best_cost < 0 || cost < best_cost || (cost == best_cost && (scaled || pad < best_pad))) {
       best_cost = cost;
       best_pad = pad;
       p.BN = bn;
       p.cw = cws[ci];
     }
   }
+  // Weight-stationary candidates: the CTA keeps one N tile of the weight (all of K) in shared memory and streams A
+  // only.  The streaming scheme re-fetches the weight tile for every 128 rows, and on many of these layers that
+  // L2 -> SM traffic (not HBM) sets the pace: e.g. 272 -> 1632 at 12x12 moved 496 MB through the crossbar for 21 MB of
+  // A and 0.9 MB of weight.  Estimated crossbar bytes decide; DFV_GEMM_FORCE="b_res,BN" overrides (tuning aid).
+  const long long n_tm = (M + kBM - 1) / kBM;
+  const int k_blocks = (K + kBK - 1) / kBK;
+  const size_t budget = 222 * 1024;
+  auto tail_bytes = [&](int bn) {
+    const int ntn = (N + bn - 1) / bn;
+    return align_up((size_t)ntn * bn * 4, 16) + (scaled ? (size_t)4 * k_blocks * kBK : 0) + sizeof(TcBarriers) + 64 + 1024;
+  };
+  p.b_res = 0;
+  p.m_splits = 1;
+  p.tiles_per_cta = 1;
+  {
+    int force_res = -1, force_bn = 0;
+    if (const char* f = getenv("DFV_GEMM_FORCE")) sscanf(f, "%d,%d", &force_res, &force_bn);
+    if (force_res == 0 && force_bn > 0) {
+      for (int ci = 0; ci < 6; ++ci)
+        if (parts * cws[ci] == force_bn) { p.BN = force_bn; p.cw = cws[ci]; }
+    }
+    const int ntn0 = (N + p.BN - 1) / p.BN;
+    const double stream_bytes = (double)n_tm * ((double)ntn0 * kBM * K * 2 + (double)N * K * 2);
+    double best = force_res == 1 ? 1e300 : stream_bytes * 0.8;      // must be clearly better than streaming
+    for (int ci = 0; ci < 6 && force_res != 0 && !scaled; ++ci) {
+      const int bn = parts * cws[ci];
+      if (bn > 256) continue;
+      if (force_res == 1 && force_bn > 0 && bn != force_bn) continue;
+      const size_t fixed = (size_t)k_blocks * bn * kBK * 2 + (size_t)bn * 256 + tail_bytes(bn);
+      // A alone is 16 KB per k-block: the pipeline needs depth (>= 5 stages) to cover the L2 latency, and a narrow tile
+      // (BN = 128: one k-block per 256 MMA cycles = 64 B/clk) asks more of the SM's L2 port than it delivers
+      if (fixed + (force_res == 1 ? 2 : 5) * (size_t)kBM * kBK * 2 > budget) continue;
+      const int ntn = (N + bn - 1) / bn;
+      if (ntn > num_sms()) continue;
+      if (bn < 192 && ntn > 1 && force_res != 1) continue;
+      long long ms = num_sms() / ntn;
+      if (ms > n_tm) ms = n_tm;
+      const long long tpc = (n_tm + ms - 1) / ms;
+      if (tpc < 4 && force_res != 1) continue;                       // too few tiles to amortise the weight load
+      ms = (n_tm + tpc - 1) / tpc;
+      const double quant = (double)(n_tm * ntn) / (double)(tpc * num_sms());          // SM-time actually used
+      const double pad = (double)ntn * bn / N;                                        // padded output columns
+      const double bytes = ((double)ntn * M * K * 2 + (double)ms * ntn * bn * K * 2) * pad / quant;
+      if (bytes < best) {
+        best = bytes;
+        p.b_res = 1;
+        p.BN = bn;
+        p.cw = cws[ci];
+        p.m_splits = (int)ms;
+        p.tiles_per_cta = tpc;
+      }
+    }
+  }
   p.n_tiles_n = (N + p.BN - 1) / p.BN;
   p.nb = p.cw > 64 ? 2 : 1;
   p.bw = p.cw / p.nb;
   p.swz = p.bw == 64 ? 3 : (p.bw == 32 ? 2 : (p.bw == 16 ? 1 : 0));
-  p.n_tiles = ((M + kBM - 1) / kBM) * p.n_tiles_n;
-  p.k_blocks = (K + kBK - 1) / kBK;
+  p.n_tiles_m = n_tm;
+  p.n_tiles = n_tm * p.n_tiles_n;
+  p.k_blocks = k_blocks;
   p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
   p.act = act;
-  const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;
+  const size_t a_stage = (size_t)kBM * kBK * 2;
+  const size_t stage_bytes = p.b_res ? a_stage : a_stage + (size_t)p.BN * kBK * 2;
+  const size_t resident = p.b_res ? (size_t)k_blocks * p.BN * kBK * 2 : 0;
   const size_t staging = (size_t)p.BN * 256;            // all epilogue warps, one buffer each
-  const size_t tail = align_up((size_t)p.n_tiles_n * p.BN * 4, 16) + (a_scale ? (size_t)4 * p.k_blocks * kBK : 0) + sizeof(TcBarriers) + 64 + 1024;
-  const size_t budget = 222 * 1024;
-  p.nbuf = (2 * staging + 3 * stage_bytes + tail <= budget) ? 2 : 1;
+  const size_t tail = tail_bytes(p.BN) + resident;
+  p.nbuf = (2 * staging + (p.b_res ? 5 : 3) * stage_bytes + tail <= budget) ? 2 : 1;
   int stages = (int)((budget - tail - p.nbuf * staging) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   DFV_REQUIRE(stages >= 2, "dfv_pw_gemm_fwd: tile does not fit shared memory (N=%d)", N);
   p.stages = stages;
   // keep one CTA per SM (each allocates all 512 TMEM columns): ask for > half of the SM's smem
-  size_t smem = (size_t)stages * stage_bytes + p.nbuf * staging + tail;
+  smem = (size_t)stages * stage_bytes + p.nbuf * staging + tail;
   if (smem < 120 * 1024) smem = 120 * 1024;
+  if (p.b_res) {
+    grid = (long long)p.m_splits * p.n_tiles_n;
+  } else {
+    grid = p.n_tiles < (long long)num_sms() ? p.n_tiles : (long long)num_sms();
+    p.tiles_per_cta = (p.n_tiles + grid - 1) / grid;
+    grid = (p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  }
+  return DFV_OK;
+}
+
+/* Debug / documentation aid (host only): the tile plan of a bf16 tensor-core GEMM.
+ * out[0..7] = BN, weight-stationary flag, pipeline stages, staging buffers, grid, tiles per CTA, smem bytes, N tiles. */
+extern "C" int dfv_debug_gemm_plan(long long M, int K, int N, int scaled, int* out) {
+  TcParams p;
+  size_t smem = 0;
+  long long grid = 0;
+  if (!out || M <= 0 || K <= 0 || N <= 0 || K % 8 || N % 8) {
+    set_error("dfv_debug_gemm_plan: bad shape");
+    return DFV_ERR_INVALID;
+  }
+  DFV_TRY(plan_tc(p, smem, grid, M, K, N, scaled != 0, 1, 0));
+  out[0] = p.BN; out[1] = p.b_res; out[2] = p.stages; out[3] = p.nbuf; out[4] = (int)grid; out[5] = (int)p.tiles_per_cta;
+  out[6] = (int)smem; out[7] = p.n_tiles_n;
+  return DFV_OK;
+}
+
+static int launch_tc(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
+                     const void* residual, void* out, long long M, int K, int N, int act, cudaStream_t st) {
+  TcParams p;
+  size_t smem = 0;
+  long long grid = 0;
+  DFV_TRY(plan_tc(p, smem, grid, M, K, N, a_scale != nullptr, rows_per_image, act));
 
   CUtensorMap tm_a, tm_b, tm_out, tm_tail;
   {
@@ -522,9 +630,6 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
     DFV_TRY(make_tensor_map(&tm_out, DFV_BF16, 2, out, dims, strides, box, sw));
     tm_tail = tm_out;
   }
-  long long grid = p.n_tiles < (long long)num_sms() ? p.n_tiles : (long long)num_sms();
-  p.tiles_per_cta = (p.n_tiles + grid - 1) / grid;
-  grid = (p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   DFV_TRY(init_timeout_word_tu());
 #define TC_LAUNCH(S_, A_, R_)                                                                                                   \
   do {                                                                                                                          \
@@ -550,8 +655,8 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   if (debug_flags() & 32) {   // bisecting aid: attribute an asynchronous fault to this launch
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
-      set_error("tc GEMM faulted: %s M=%lld K=%d N=%d BN=%d stages=%d nbuf=%d cw=%d bw=%d scale=%d res=%d act=%d grid=%lld smem=%zu",
-                cudaGetErrorString(e), M, K, N, p.BN, p.stages, p.nbuf, p.cw, p.bw, a_scale != nullptr,
+      set_error("tc GEMM faulted: %s M=%lld K=%d N=%d BN=%d b_res=%d stages=%d nbuf=%d cw=%d bw=%d scale=%d res=%d act=%d grid=%lld smem=%zu",
+                cudaGetErrorString(e), M, K, N, p.BN, p.b_res, p.stages, p.nbuf, p.cw, p.bw, a_scale != nullptr,
                 residual != nullptr, act, grid, smem);
       return DFV_ERR_CUDA;
     }

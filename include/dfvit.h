@@ -432,6 +432,9 @@ int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float
 /* Debug / documentation aid (host only): the depthwise tile plan chosen for a layer.
  * out[0..9] = CB, L, TW, TH, threads, smem bytes, tiles_w, tiles_h, pool parts, grid. */
 int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out);
+/* Tile plan of a bf16 tensor-core 1x1-conv GEMM (host only): out[0..7] = N tile, weight-stationary flag, pipeline
+ * stages, staging buffers, grid, tiles per CTA, shared-memory bytes, N tiles. */
+int dfv_debug_gemm_plan(long long M, int K, int N, int scaled, int* out);
 
 #ifdef __cplusplus
 }

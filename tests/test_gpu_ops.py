@@ -188,6 +188,39 @@ def test_pw_gemm_tcgen05_matches_simt_large(ops):
         assert rel(out_tc.float(), out_simt.float()) < 3e-3, (M, K, N)
 
 
+def test_pw_gemm_full_size_every_element(ops):
+    """Benchmark-size launches (batch 256) checked element by element, three times each.  Regression: with N = 336 and
+    192-column tiles the last column part of every second tile lies beyond N; its epilogue warps skipped those tiles but
+    picked their staging buffer by tile parity, so a TMA store still reading the buffer could be overwritten -- a few
+    thousand wrong values per launch in the first tiles of some CTAs, invisible to sampled / norm-based checks.
+    Also covers the weight-stationary plan (small K, several N tiles) and the streaming plan (large K) at full size."""
+    import os
+    g = torch.Generator(device=DEV).manual_seed(61)
+    for (M, K, N, act, gated, rpi) in ((589824, 56, 336, 1, False, 0), (147456, 160, 960, 1, False, 0),
+                                       (36864, 1632, 272, 0, True, 144), (2310400 // 4, 96, 576, 1, False, 0)):
+        a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+        w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device=DEV, generator=g) * 0.1
+        sc = torch.rand(M // rpi, K, device=DEV, generator=g).bfloat16() if gated else None
+        ref = torch.empty(M, N, device=DEV)
+        for i in range(0, M, 65536):
+            av = a[i:i + 65536]
+            if gated:
+                av = av * sc[torch.arange(i, min(i + 65536, M), device=DEV) // rpi]
+            r = av.float() @ w.float().t() + bias
+            ref[i:i + 65536] = r * torch.sigmoid(r) if act else r
+        for forced in (None, "0,192", "0,128"):
+            if forced:
+                os.environ["DFV_GEMM_FORCE"] = forced
+            try:
+                for rep in range(3):
+                    y = ops.pw_gemm(a, w, bias, act, sc, rpi)
+                    bad = ((y.float() - ref).abs() > 0.03 * (ref.abs() + 1.0)).sum().item()
+                    assert bad == 0, (M, K, N, forced, rep, bad)
+            finally:
+                os.environ.pop("DFV_GEMM_FORCE", None)
+
+
 def test_pw_gemm_rejects_bad_shapes(ops):
     import deepfake_vit_b200 as d
     a = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)
