@@ -107,6 +107,36 @@ def test_dwconv_ragged_shapes(ops, case):
     assert rel(pool.sum(1), ref.sum((2, 3))) < 1e-5
 
 
+def test_dwconv_and_stem_full_size_every_element(ops):
+    """Benchmark-size (batch 256) launches compared element by element with torch on the GPU, twice each: the
+    persistent tile loops, pipeline wrap-around and pool-slot flushes only run long at this size, and a sporadic
+    race there is invisible to a norm-based check (see test_pw_gemm_full_size_every_element)."""
+    g = torch.Generator(device=DEV).manual_seed(62)
+    B = 256
+    for (k, s, C, H, plo, phi) in ((3, 1, 192, 95, 1, 1), (5, 1, 336, 48, 2, 2), (3, 2, 336, 48, 0, 1), (5, 2, 960, 24, 1, 2),
+                                   (5, 1, 1632, 12, 2, 2), (3, 1, 2688, 12, 1, 1)):
+        x = torch.randn(B, H, H, C, device=DEV, generator=g).bfloat16()
+        w = (torch.randn(C, k * k, device=DEV, generator=g) * 0.2).bfloat16().float()
+        bias = torch.randn(C, device=DEV, generator=g) * 0.1
+        ref = _dw_ref(x.float(), w, bias, k, s, plo, phi).permute(0, 2, 3, 1)
+        for rep in range(2):
+            y, pool = ops.dwconv(x, w.t().contiguous(), bias, k, s, plo, phi)
+            bad = ((y.float() - ref).abs() > 0.03 * (ref.abs() + 1.0)).sum().item()
+            assert bad == 0, (k, s, C, H, rep, bad)
+            ps = pool.sum(1)
+            rs = ref.sum((1, 2))
+            assert ((ps - rs).abs() <= 0.02 * (rs.abs() + ref.abs().sum((1, 2)) * 0.01 + 1.0)).all(), (k, s, C, H, rep)
+        del ref, x
+    x = torch.randn(B, 3, 380, 380, device=DEV, generator=g)
+    w = torch.randn(48, 3, 3, 3, device=DEV, generator=g) * 0.3
+    bias = torch.randn(48, device=DEV, generator=g) * 0.1
+    ref = silu(F.conv2d(F.pad(x.bfloat16().float(), (0, 1, 0, 1)), w.bfloat16().float(), bias, stride=2)).permute(0, 2, 3, 1)
+    for rep in range(2):
+        y = ops.stem_conv(x, w.permute(2, 3, 1, 0).contiguous(), bias, torch.bfloat16)
+        bad = ((y.float() - ref).abs() > 0.03 * (ref.abs() + 1.0)).sum().item()
+        assert bad == 0, ("stem", rep, bad)
+
+
 # ------------------------------------------------------------------------------- SE gate
 def test_se_gate(ops):
     g = torch.Generator().manual_seed(4)
