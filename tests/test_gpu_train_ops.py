@@ -316,3 +316,68 @@ def test_dropout_mask_statistics(ops):
     m3 = ops.dropout_mask((n,), p, 1235, DEV)
     assert (m != m3).float().mean().item() > 0.3
     assert torch.all(ops.dropout_mask((1000,), 0.0, 7, DEV) == 1.0)
+
+
+# ------------------------------------------------------------------------------- full-size, every element
+def test_train_streams_full_size_every_element(ops):
+    """Training-batch (64) launches of the streaming kernels checked element by element against torch on the GPU, twice
+    each: multi-wave grids, the cp.async slot pipeline's wrap-around and the TMA tile loops only run long at this size,
+    and a sporadic race is invisible to a norm (the GEMM epilogue had one, see tests/test_gpu_ops.py)."""
+    dt = torch.bfloat16
+    g = torch.Generator(device=DEV).manual_seed(71)
+
+    def bad_count(y, ref, t=0.03):
+        return ((y.float() - ref).abs() > t * (ref.abs() + 1.0)).sum().item()
+
+    for (B, H, W, C) in ((64, 95, 95, 192), (64, 12, 12, 1632), (64, 48, 48, 56)):
+        x = (torch.randn(B, H, W, C, device=DEV, generator=g) * 1.3 + 0.2).to(dt)
+        gy = torch.randn(B, H, W, C, device=DEV, generator=g).to(dt)
+        gamma = torch.randn(C, device=DEV, generator=g) * 0.3 + 1.0
+        beta = torch.randn(C, device=DEV, generator=g) * 0.3
+        xf = x.float().requires_grad_(True)
+        gm, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        ref = silu(F.batch_norm(xf.permute(0, 3, 1, 2), None, None, gm, bt, True, 0.0, 1e-3)).permute(0, 2, 3, 1)
+        ref.backward(gy.float())
+        for rep in range(2):
+            mean, invstd = ops.bn_stats(x, 1e-3)
+            y, pool = ops.bn_act(x, mean, invstd, gamma, beta, act=1, want_pool=True)
+            assert bad_count(y, ref.detach()) == 0, ("bn_act", B, H, W, C, rep)
+            dx, dgamma, dbeta = ops.act_bn_bwd(gy, x, mean, invstd, gamma, beta, act=1)
+            assert bad_count(dx, xf.grad) == 0, ("act_bn_bwd", B, H, W, C, rep)
+            assert rel(dgamma, gm.grad) < 1e-2 and rel(dbeta, bt.grad) < 1e-2
+        del ref, xf
+    for (k, s, pl, ph, C, H) in ((5, 2, 1, 2, 192, 95), (3, 2, 0, 1, 336, 48), (5, 1, 2, 2, 960, 24), (3, 2, 0, 1, 144, 190)):
+        B = 64
+        x = torch.randn(B, C, H, H, device=DEV, generator=g).to(dt).float().requires_grad_(True)
+        w = (torch.randn(C, 1, k, k, device=DEV, generator=g) * 0.3).requires_grad_(True)
+        y = F.conv2d(F.pad(x, (pl, ph, pl, ph)), w, None, stride=s, groups=C)
+        gy = torch.randn(*y.shape, device=DEV, generator=g).to(dt)
+        y.backward(gy.float())
+        gd = gy.permute(0, 2, 3, 1).contiguous()
+        xd = x.detach().permute(0, 2, 3, 1).contiguous().to(dt)
+        w_kkc = w.detach().view(C, k * k).t().contiguous()
+        for rep in range(2):
+            dx = ops.dwconv_dgrad(gd, w_kkc, H, H, k, s, pl, ph)
+            assert bad_count(dx.permute(0, 3, 1, 2), x.grad) == 0, ("dw dgrad", k, s, C, H, rep)
+            dw = ops.dwconv_wgrad(gd, xd, k, s, pl, ph)
+            assert rel(dw.t().reshape(C, 1, k, k), w.grad) < 2e-3, ("dw wgrad", k, s, C, H, rep)
+        del x, y
+
+
+def test_pw_wgrad_full_size_every_element(ops):
+    """Training-batch weight gradients of the tensor-core kernel, every dW element, three launches each (the sum over
+    147k..578k rows runs the TMA / transform / MMA pipeline through hundreds of stages per CTA)."""
+    dt = torch.bfloat16
+    g_ = torch.Generator(device=DEV).manual_seed(72)
+    for (B, HW, K, N, gated) in ((64, 2304, 336, 56, True), (64, 9025, 32, 192, False), (64, 144, 1632, 272, True),
+                                 (64, 576, 160, 960, False), (64, 144, 448, 1792, False)):
+        a = torch.randn(B, HW, K, device=DEV, generator=g_).to(dt)
+        g = torch.randn(B, HW, N, device=DEV, generator=g_).to(dt)
+        gate = torch.sigmoid(torch.randn(B, K, device=DEV, generator=g_)).to(dt) if gated else None
+        ag = (a * gate.view(B, 1, K)).to(dt).float() if gated else a.float()
+        ref = (g.float().reshape(-1, N).double().t() @ ag.reshape(-1, K).double()).float()
+        scale = ref.abs().mean().item()
+        for rep in range(3):
+            dw = ops.pw_wgrad(g, a, gate, HW if gated else 0)
+            bad = ((dw - ref).abs() > 2e-3 * (ref.abs() + scale)).sum().item()
+            assert bad == 0, (B, HW, K, N, gated, rep, bad)
