@@ -93,7 +93,8 @@ def _load():
         "dfv_stem_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
         "dfv_dwconv_pool_parts": (C.c_int, [i32] * 9),
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
-        "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+        "dfv_se_scratch_floats": (sz, [i32, i32, i32]),
+        "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]),
         "dfv_pw_gemm_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, vp]),
         "dfv_pw_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, vp, vp]),
         "dfv_pw_fold_ws_bytes": (sz, [i32]),
@@ -118,7 +119,7 @@ def _load():
         "dfv_act_bn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64,
                                      i32, vp]),
         "dfv_bn_bwd_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]),
-        "dfv_se_train_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, i32, i32, vp]),
+        "dfv_se_train_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
         "dfv_se_bwd_ws_floats": (sz, [i32, i64, i32, i32]),
         "dfv_se_bwd": (C.c_int, [vp, vp, i32] + [vp] * 11 + [i32, i64, i32, i32, vp]),
         "dfv_pw_wgrad": (C.c_int, [vp, vp, vp, i32, vp, i32, i64, i32, i32, vp]),

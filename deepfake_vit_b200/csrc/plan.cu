@@ -17,6 +17,7 @@ struct Shapes {
   size_t dw_elems;            // per image: max depthwise output
   size_t pool_floats;         // per image: max parts * c_mid
   int max_cmid;
+  size_t se_scratch_floats;   // whole batch: max over blocks of dfv_se_scratch_floats
 };
 
 static int compute_shapes(Shapes* s, int dtype, int B, int H, int W) {
@@ -28,6 +29,7 @@ static int compute_shapes(Shapes* s, int dtype, int B, int H, int W) {
   s->act_elems = (size_t)h * w * topo_stem_c();
   s->exp_elems = s->dw_elems = s->pool_floats = 0;
   s->max_cmid = 0;
+  s->se_scratch_floats = 0;
   for (int i = 0; i < n; ++i) {
     const dfv_block_info& b = blk[i];
     s->Hin[i] = h;
@@ -44,6 +46,7 @@ static int compute_shapes(Shapes* s, int dtype, int B, int H, int W) {
     s->pool_floats = std::max(s->pool_floats, (size_t)parts * b.c_mid);
     s->act_elems = std::max(s->act_elems, (size_t)ho * wo * b.c_out);
     s->max_cmid = std::max(s->max_cmid, b.c_mid);
+    s->se_scratch_floats = std::max(s->se_scratch_floats, dfv_se_scratch_floats(B, b.c_mid, b.se_squeeze));
     h = ho;
     w = wo;
   }
@@ -59,6 +62,7 @@ struct Workspace {
   char* dw;
   float* pool;
   void* gate;
+  float* se_scratch;       // squeeze partial sums between the two SE kernels
   float* heat;
   float* heat_raw;
   uint32_t* heat_max;
@@ -83,6 +87,7 @@ static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) 
   ws->dw = take((size_t)B * s.dw_elems * es);
   ws->pool = (float*)take((size_t)B * s.pool_floats * 4);
   ws->gate = take((size_t)B * s.max_cmid * 4);
+  ws->se_scratch = (float*)take(s.se_scratch_floats * 4);
   ws->heat = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_raw = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_max = (uint32_t*)take((size_t)B * 4);
@@ -153,7 +158,7 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
                            w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, DFV_ACT_SILU, stream));
     DFV_TRY(dfv_se_gate_fwd(ws.pool, parts, 1.0f / (float)(ho * wo), (const float*)W_(i, DFV_W_SE_REDUCE),
                             (const float*)W_(i, DFV_W_SE_REDUCE_BIAS), (const float*)W_(i, DFV_W_SE_EXPAND),
-                            (const float*)W_(i, DFV_W_SE_EXPAND_BIAS), ws.gate, dtype, B, b.c_mid, b.se_squeeze, stream));
+                            (const float*)W_(i, DFV_W_SE_EXPAND_BIAS), ws.gate, dtype, ws.se_scratch, B, b.c_mid, b.se_squeeze, stream));
     DFV_TRY(dfv_pw_conv_fwd(ws.dw, W_(i, DFV_W_PROJECT), (const float*)W_(i, DFV_W_PROJECT_BIAS), ws.gate, ho * wo,
                             b.has_skip ? x : nullptr, ws.act[cur ^ 1], dtype, B, (long long)B * ho * wo, b.c_mid, b.c_out,
                             DFV_ACT_NONE, ws.fold_ws, stream));

@@ -70,6 +70,7 @@ struct Arena {
   float* feat_pre;
   float* mask_f;
   float* pool_ws;
+  float* se_scratch;   // squeeze partial sums between the two SE kernels
   float* bn_ws;
   double* bn_acc;      // per-channel sum / sum of squares a producer kernel accumulates (fused BatchNorm statistics)
   char* fold_ws;
@@ -128,7 +129,7 @@ void carve_arena(Arena* a, void* base, const TShapes& s, int dtype, int B, const
   a->a0 = c.take(stem_elems * es);
   a->sm = c.takef(topo_stem_c());
   a->si = c.takef(topo_stem_c());
-  size_t pool_max = 0;
+  size_t pool_max = 0, se_max = 0;
   for (int i = 0; i < n; ++i) {
     const dfv_block_info& b = blk[i];
     BlockArena& ba = a->blk[i];
@@ -162,6 +163,7 @@ void carve_arena(Arena* a, void* base, const TShapes& s, int dtype, int B, const
     ba.wD = c.takef((size_t)b.kernel * b.kernel * b.c_mid);
     ba.wDf = c.takef((size_t)b.kernel * b.kernel * b.c_mid);
     pool_max = std::max(pool_max, (size_t)B * dfv_rows_chunks(B, (long long)s.Hout[i] * s.Wout[i]) * b.c_mid);
+    se_max = std::max(se_max, dfv_se_scratch_floats(B, b.c_mid, b.se_squeeze));
   }
   const size_t head_elems = (size_t)B * s.Hf * s.Wf * topo_head_c();
   a->h_raw = c.take(head_elems * es);
@@ -177,6 +179,7 @@ void carve_arena(Arena* a, void* base, const TShapes& s, int dtype, int B, const
   a->feat_pre = c.takef((size_t)B * topo_head_c());
   a->mask_f = c.takef((size_t)B * topo_head_c());
   a->pool_ws = c.takef(pool_max);
+  a->se_scratch = c.takef(se_max);
   a->bn_ws = c.takef(max_bn_ws(s, B, dims, layers));
   a->fold_ws = c.take(dfv_pw_fold_ws_bytes(B));
   a->bn_acc = reinterpret_cast<double*>(c.take(sizeof(double) * 2 * 4096));
@@ -369,7 +372,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_bn_act_fwd(ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ba.d,
                            ar.pool_ws, dtype, B, hw_out, b.c_mid, stream));
     DFV_TRY(dfv_se_train_fwd(ar.pool_ws, dfv_rows_chunks(B, hw_out), 1.0f / (float)hw_out, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_R_B),
-                             P(i, DFV_T_SE_E_W), P(i, DFV_T_SE_E_B), ba.gate, dtype, ba.pooled, ba.h1, ba.gate_f32, B, b.c_mid, b.se_squeeze, stream));
+                             P(i, DFV_T_SE_E_W), P(i, DFV_T_SE_E_B), ba.gate, dtype, ba.pooled, ba.h1, ba.gate_f32, ar.se_scratch, B, b.c_mid, b.se_squeeze, stream));
     DFV_TRY(dfv_cast_weight(P(i, DFV_T_PROJ_W), ba.wP, dtype, b.c_out, b.c_mid, 0, stream));
     DFV_TRY(dfv_cast_weight(P(i, DFV_T_PROJ_W), ba.wPt, dtype, b.c_mid, b.c_out, 1, stream));
     DFV_TRY(dfv_pw_conv_fwd(ba.d, ba.wP, ar.zero_bias, ba.gate, (int)hw_out, nullptr, ba.p_raw, dtype, B, B * hw_out, b.c_mid, b.c_out, DFV_ACT_NONE,

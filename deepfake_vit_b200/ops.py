@@ -66,8 +66,9 @@ def se_gate(pool_partial, hw, w_reduce, b_reduce, w_expand_t, b_expand, gate_dty
     B, parts, C_ = pool_partial.shape
     sq = b_reduce.numel()
     gate = torch.empty(B, C_, device=pool_partial.device, dtype=gate_dtype)
+    scratch = _f32buf(lib.dfv_se_scratch_floats(B, C_, sq), pool_partial.device)
     check(lib.dfv_se_gate_fwd(_f32(pool_partial), parts, 1.0 / hw, _f32(w_reduce), _f32(b_reduce), _f32(w_expand_t),
-                              _f32(b_expand), _ptr(gate), dtype_code(gate_dtype), B, C_, sq, _stream()))
+                              _f32(b_expand), _ptr(gate), dtype_code(gate_dtype), _f32(scratch), B, C_, sq, _stream()))
     return gate
 
 
@@ -235,8 +236,9 @@ def se_train_fwd(pool_partial, hw, w_reduce, b_reduce, w_expand, b_expand, gate_
     sq, dev = b_reduce.numel(), pool_partial.device
     gate = torch.empty(B, C_, device=dev, dtype=gate_dtype)
     pooled, h1, g32 = _f32buf(B * C_, dev).view(B, C_), _f32buf(B * sq, dev).view(B, sq), _f32buf(B * C_, dev).view(B, C_)
+    scratch = _f32buf(lib.dfv_se_scratch_floats(B, C_, sq), dev)
     check(lib.dfv_se_train_fwd(_f32(pool_partial), parts, 1.0 / hw, _f32(w_reduce), _f32(b_reduce), _f32(w_expand), _f32(b_expand),
-                               _ptr(gate), dtype_code(gate_dtype), _f32(pooled), _f32(h1), _f32(g32), B, C_, sq, _stream()))
+                               _ptr(gate), dtype_code(gate_dtype), _f32(pooled), _f32(h1), _f32(g32), _f32(scratch), B, C_, sq, _stream()))
     return gate, pooled, h1, g32
 
 

@@ -143,10 +143,12 @@ int dfv_dwconv_fwd(const void* x, const float* w_kkc, const float* bias, void* y
  * and `torch.sigmoid` of MBConvBlock.forward.  gate: [B][C] of type gate_dtype (fp32 in
  * parity mode; bf16 in bf16 mode, where the autocast reference's sigmoid output is a bf16
  * tensor too).  The channel rescale itself is fused into the project GEMM's A-operand path
- * (dfv_pw_gemm_fwd a_scale). */
+ * (dfv_pw_gemm_fwd a_scale).  scratch: dfv_se_scratch_floats(B, C, squeeze) floats of device memory (the squeeze
+ * layer's per-channel-slice partial sums, handed from the squeeze kernel to the excite kernel). */
+size_t dfv_se_scratch_floats(int B, int C, int squeeze);
 int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce,
                     const float* b_reduce, const float* w_expand_t, const float* b_expand, void* gate,
-                    int gate_dtype, int B, int C, int squeeze, dfv_stream_t stream);
+                    int gate_dtype, float* scratch, int B, int C, int squeeze, dfv_stream_t stream);
 
 /* Pointwise (1x1) convolution as a GEMM  out[M][N] = act((a[M][K] * a_scale) . w[N][K]^T + bias) + residual.
  * M = B*H*W rows.  a_scale: [M / rows_per_image][K] per-image channel scale (SE gate) of the
@@ -288,10 +290,10 @@ int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const f
                      const float* coef, void* draw, int dtype, long long M, int C, dfv_stream_t stream);
 
 /* Squeeze-excite forward that also saves pooled [B][C], h1 [B][sq] (pre-swish) and the fp32 gate; weights in
- * torch layout: w_reduce [sq][C], w_expand [C][sq]. */
+ * torch layout: w_reduce [sq][C], w_expand [C][sq].  scratch: dfv_se_scratch_floats(B, C, squeeze) floats. */
 int dfv_se_train_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce, const float* b_reduce,
                      const float* w_expand, const float* b_expand, void* gate, int gate_dtype, float* pooled, float* h1,
-                     float* gate_f32, int B, int C, int squeeze, dfv_stream_t stream);
+                     float* gate_f32, float* scratch, int B, int C, int squeeze, dfv_stream_t stream);
 size_t dfv_se_bwd_ws_floats(int B, long long rows_per_image, int C, int squeeze);
 int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, const float* pooled, const float* h1,
                const float* w_reduce, const float* w_expand, float* dpool, float* dw_reduce, float* db_reduce,
