@@ -66,11 +66,12 @@ struct Workspace {
   float* heat;
   float* heat_raw;
   uint32_t* heat_max;
-  float* head_scratch;     // classifier hidden activations: 2 x B x kHeadHiddenMax
+  float* head_scratch;     // classifier scratch: kHeadScratchPerRow floats per image (dfv_mlp_head_scratch_floats must fit)
   char* fold_ws;           // scratch of dfv_pw_conv_fwd (row-folded thin 1x1 convolutions)
   size_t bytes;
 };
 constexpr int kHeadHiddenMax = 2048;
+constexpr size_t kHeadScratchPerRow = (size_t)10 * kHeadHiddenMax;   // two activation buffers + K-slice partial sums
 
 
 static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) {
@@ -91,7 +92,7 @@ static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) 
   ws->heat = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_raw = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_max = (uint32_t*)take((size_t)B * 4);
-  ws->head_scratch = (float*)take((size_t)2 * B * kHeadHiddenMax * 4);
+  ws->head_scratch = (float*)take((size_t)B * kHeadScratchPerRow * 4);
   ws->fold_ws = take(dfv_pw_fold_ws_bytes(B));
   ws->bytes = off;
 }
@@ -184,6 +185,8 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
                                    s.Hf, s.Wf, head_c, use_c ? a->ca_hidden : 0, use_c, use_s, stream));
   for (int l = 1; l < a->head_layers; ++l)
     DFV_REQUIRE(a->head_dims[l] <= kHeadHiddenMax, "dfv_infer_fwd: classifier hidden width %d > %d", a->head_dims[l], kHeadHiddenMax);
+  DFV_REQUIRE(dfv_mlp_head_scratch_floats(a->head_dims, a->head_layers, B) <= (size_t)B * kHeadScratchPerRow,
+              "dfv_infer_fwd: classifier head too wide for the workspace");
   DFV_TRY(dfv_mlp_head_fwd(a->features, a->head_w_t, a->head_b, a->head_dims, a->head_layers, a->logits, ws.head_scratch, B, stream));
   return DFV_OK;
 }
