@@ -107,7 +107,8 @@ def _load():
         "dfv_l2_normalize": (C.c_int, [vp, vp, i32, i32, f32, vp]),
         "dfv_clip_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, vp] + [C.c_double] * 7 + [i64, vp, vp]),
         "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
-        "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 8 + [i32] * 8 + [vp]),
+        "dfv_attention_scratch_floats": (sz, [i32] * 5),
+        "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 9 + [i32] * 8 + [vp]),
         "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, vp, i32, vp]),
         "dfv_mlp_head_scratch_floats": (sz, [C.POINTER(C.c_int), i32, i32]),
         "dfv_combined_loss_fwd_bwd": (C.c_int, [vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, i32, i32, i32,

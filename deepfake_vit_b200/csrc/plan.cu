@@ -66,11 +66,13 @@ struct Workspace {
   float* heat;
   float* heat_raw;
   uint32_t* heat_max;
+  float* attn_scratch;     // HybridAttention scratch (dfv_attention_scratch_floats at hidden = kAttnHiddenMax)
   float* head_scratch;     // classifier scratch: kHeadScratchPerRow floats per image (dfv_mlp_head_scratch_floats must fit)
   char* fold_ws;           // scratch of dfv_pw_conv_fwd (row-folded thin 1x1 convolutions)
   size_t bytes;
 };
 constexpr int kHeadHiddenMax = 2048;
+constexpr int kAttnHiddenMax = 288;    // channel-attention MLP width the workspace (and the small-linear kernels' shared memory) allow
 constexpr size_t kHeadScratchPerRow = (size_t)10 * kHeadHiddenMax;   // two activation buffers + K-slice partial sums
 
 
@@ -92,6 +94,7 @@ static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) 
   ws->heat = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_raw = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_max = (uint32_t*)take((size_t)B * 4);
+  ws->attn_scratch = (float*)take(dfv_attention_scratch_floats(B, s.Hf, s.Wf, topo_head_c(), kAttnHiddenMax) * 4);
   ws->head_scratch = (float*)take((size_t)B * kHeadScratchPerRow * 4);
   ws->fold_ws = take(dfv_pw_fold_ws_bytes(B));
   ws->bytes = off;
@@ -181,7 +184,8 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
     if (a->heat) DFV_CUDA(cudaMemcpyAsync(a->heat, ws.heat, sizeof(float) * (size_t)B * s.Hf * s.Wf, cudaMemcpyDeviceToDevice, st));
   }
   const int use_c = a->use_attention && a->use_channel, use_s = a->use_attention && a->use_spatial;
-  DFV_TRY(dfv_hybrid_attention_fwd(ws.act[cur], heat, a->ca_w1, a->ca_w2_t, a->sa_w, a->features, nullptr, nullptr, dtype, B,
+  DFV_REQUIRE(!use_c || a->ca_hidden <= kAttnHiddenMax, "dfv_infer_fwd: channel-attention hidden width %d > %d", a->ca_hidden, kAttnHiddenMax);
+  DFV_TRY(dfv_hybrid_attention_fwd(ws.act[cur], heat, a->ca_w1, a->ca_w2_t, a->sa_w, a->features, nullptr, nullptr, ws.attn_scratch, dtype, B,
                                    s.Hf, s.Wf, head_c, use_c ? a->ca_hidden : 0, use_c, use_s, stream));
   for (int l = 1; l < a->head_layers; ++l)
     DFV_REQUIRE(a->head_dims[l] <= kHeadHiddenMax, "dfv_infer_fwd: classifier hidden width %d > %d", a->head_dims[l], kHeadHiddenMax);

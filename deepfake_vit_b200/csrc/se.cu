@@ -36,7 +36,8 @@ static int launch_se(const float* pool_partial, int parts, float inv_hw, const f
     configured = true;
   }
   float* hid = h1 ? h1 : scratch + (size_t)ksplit * B * squeeze;      // training keeps h1 for the backward pass
-  DFV_PDL((sl_rowmajor_partial_kernel<kTrain>), grid_a, kSlThreads, smem_a, st, pool_partial, parts, inv_hw, w_reduce, scratch, pooled, B, C, squeeze);
+  DFV_PDL((sl_rowmajor_partial_kernel<kTrain>), grid_a, kSlThreads, smem_a, st, pool_partial, parts, inv_hw, w_reduce, scratch, pooled, B, C, squeeze,
+          (size_t)0, (size_t)0);
   DFV_PDL(sl_combine_kernel, (unsigned)(((size_t)B * squeeze + kSlThreads - 1) / kSlThreads), kSlThreads, 0, st, (const float*)scratch,
           (const float*)nullptr, ksplit, b_reduce, hid, B, squeeze, 0);
   if (gate_dtype == DFV_BF16)

@@ -30,8 +30,11 @@ constexpr int kSlThreads = 256;
 template <bool kTrain>
 __global__ void __launch_bounds__(kSlThreads)
     sl_rowmajor_partial_kernel(const float* __restrict__ partial, int parts, float inv_hw, const float* __restrict__ w1,
-                      float* __restrict__ part, float* __restrict__ pooled_out, int B, int C, int sq) {
+                      float* __restrict__ part, float* __restrict__ pooled_out, int B, int C, int sq, size_t x_zstride,
+                      size_t part_zstride) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  partial += blockIdx.z * x_zstride;      // gridDim.z independent input sets against the same weights
+  part += blockIdx.z * part_zstride;
   extern __shared__ __align__(16) float sm[];
   float* ps = sm;                                  // [kSlKSlice][kSlRows]   pooled, image-minor
   float* ws = sm + kSlKSlice * kSlRows;            // [sq][kSlKSlice + 4]    weight slice (padded rows: conflict-free float4 reads)

@@ -105,8 +105,9 @@ def hybrid_attention(fmap, heat, ca_w1, ca_w2_t, sa_w, use_channel=True, use_spa
     cg = torch.empty(B, C_, device=dev, dtype=torch.float32) if return_gates and use_channel else None
     sg = torch.empty(B, H * W, device=dev, dtype=torch.float32) if return_gates and use_spatial else None
     hidden = ca_w1.shape[0] if use_channel else 0
+    scratch = _f32buf(lib.dfv_attention_scratch_floats(B, H, W, C_, hidden), dev)
     check(lib.dfv_hybrid_attention_fwd(_ptr(fmap), _ptr(heat), _ptr(ca_w1), _ptr(ca_w2_t), _ptr(sa_w), _f32(feats),
-                                       _ptr(cg), _ptr(sg), dtype_code(fmap.dtype), B, H, W, C_, hidden,
+                                       _ptr(cg), _ptr(sg), _f32(scratch), dtype_code(fmap.dtype), B, H, W, C_, hidden,
                                        int(use_channel), int(use_spatial), _stream()))
     return (feats, cg, sg) if return_gates else feats
 

@@ -189,10 +189,12 @@ int dfv_landmark_heatmap_fwd(const float* landmarks, const float* weights5, floa
  * fp32 [hidden][C] (fc.2.weight transposed); sa_w: fp32 [2][7][7] (spatial_attn.conv.weight).
  * use_channel / use_spatial mirror attention_config.  features: fp32 [B][C].  The attended
  * map is never written.  Optional debug outputs (may be NULL): channel_gate fp32 [B][C],
- * spatial_gate fp32 [B][H*W]. */
+ * spatial_gate fp32 [B][H*W].  scratch: dfv_attention_scratch_floats(B, H, W, C, hidden) floats of device memory
+ * (channel statistics, the channel-attention MLP's intermediates, spatial statistics). */
+size_t dfv_attention_scratch_floats(int B, int H, int W, int C, int hidden);
 int dfv_hybrid_attention_fwd(const void* fmap, const float* heat, const float* ca_w1, const float* ca_w2_t,
                              const float* sa_w, float* features, float* channel_gate, float* spatial_gate,
-                             int dtype, int B, int H, int W, int C, int hidden, int use_channel,
+                             float* scratch, int dtype, int B, int H, int W, int C, int hidden, int use_channel,
                              int use_spatial, dfv_stream_t stream);
 
 /* Classifier head `nn.Sequential` of DeepfakeDetectionModel.__init__
