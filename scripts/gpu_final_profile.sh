@@ -21,3 +21,5 @@ ncu --set full --import-source on --clock-control none -k 'regex:^dwconv_kernel'
 echo "full dw7 exit=$?"
 ncu --set full --import-source on --clock-control none -k 'regex:^pw_gemm_tc_kernel' -s 67 -c 2 -o gpurun_out/full_gemm_b3 -f python scripts/profile_fwd.py 256 2 > gpurun_out/ncu_full_gemm.log 2>&1
 echo "full gemm exit=$?"
+ncu --set full --import-source on --clock-control none -k 'regex:^pw_gemm_tc_kernel' -s 109 -c 2 -o gpurun_out/full_gemm_b24 -f python scripts/profile_fwd.py 256 2 > gpurun_out/ncu_full_gemm24.log 2>&1
+echo "full gemm b24 exit=$?"
