@@ -227,24 +227,27 @@ def test_pw_gemm_full_size_every_element(ops):
     import os
     g = torch.Generator(device=DEV).manual_seed(61)
     for (M, K, N, act, gated, rpi) in ((589824, 56, 336, 1, False, 0), (147456, 160, 960, 1, False, 0),
-                                       (36864, 1632, 272, 0, True, 144), (2310400 // 4, 96, 576, 1, False, 0)):
+                                       (36864, 1632, 272, 0, True, 144), (2310400 // 4, 96, 576, 1, False, 0),
+                                       (577600, 96, 96, 0, True, 9025 // 1), (147461, 672, 112, 0, True, 147461)):
         a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
         w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
         bias = torch.randn(N, device=DEV, generator=g) * 0.1
         sc = torch.rand(M // rpi, K, device=DEV, generator=g).bfloat16() if gated else None
+        res = torch.randn(M, N, device=DEV, generator=g).bfloat16() if gated else None     # project GEMMs carry the skip
         ref = torch.empty(M, N, device=DEV)
         for i in range(0, M, 65536):
             av = a[i:i + 65536]
             if gated:
                 av = av * sc[torch.arange(i, min(i + 65536, M), device=DEV) // rpi]
             r = av.float() @ w.float().t() + bias
-            ref[i:i + 65536] = r * torch.sigmoid(r) if act else r
+            r = r * torch.sigmoid(r) if act else r
+            ref[i:i + 65536] = r + res[i:i + 65536].float() if gated else r
         for forced in (None, "0,192", "0,128"):
             if forced:
                 os.environ["DFV_GEMM_FORCE"] = forced
             try:
                 for rep in range(3):
-                    y = ops.pw_gemm(a, w, bias, act, sc, rpi)
+                    y = ops.pw_gemm(a, w, bias, act, sc, rpi, res)
                     bad = ((y.float() - ref).abs() > 0.03 * (ref.abs() + 1.0)).sum().item()
                     assert bad == 0, (M, K, N, forced, rep, bad)
             finally:
