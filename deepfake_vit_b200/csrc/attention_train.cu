@@ -374,27 +374,41 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
   }
 }
 
-// Channel-attention weight gradients, reduced over the batch.  thread = channel.
+// Channel-attention weight gradients, reduced over the batch.  thread = (channel, group of kCaJ hidden units);
+// grid = (C / 128, hidden / kCaJ).  (One thread per channel walking all hidden x B terms took 577 us.)
 //   dW1[j][c] = sum_b dha[b][j] avg[b][c] + dhm[b][j] max[b][c];   dW2[c][j] = sum_b dz[b][c] (relu(ha) + relu(hm))[b][j]
+constexpr int kCaJ = 4;
 __global__ void __launch_bounds__(128) ca_wgrad_kernel(const float* __restrict__ dz, const float* __restrict__ dhpre,
                                                       const float* __restrict__ hpre, const float* __restrict__ avg,
                                                       const float* __restrict__ mx, float* __restrict__ dw1,
                                                       float* __restrict__ dw2, int B, int C, int hidden) {
   pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j0 = blockIdx.y * kCaJ;
   if (c >= C) return;
-  #pragma unroll 8
-  for (int j = 0; j < hidden; ++j) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int b = 0; b < B; ++b) {
+  float s1[kCaJ], s2[kCaJ];
+#pragma unroll
+  for (int u = 0; u < kCaJ; ++u) { s1[u] = 0.f; s2[u] = 0.f; }
+#pragma unroll 4
+  for (int b = 0; b < B; ++b) {
+    const float av = avg[(size_t)b * C + c], mv = mx[(size_t)b * C + c], zv = dz[(size_t)b * C + c];
+#pragma unroll
+    for (int u = 0; u < kCaJ; ++u) {
+      const int j = min(j0 + u, hidden - 1);
       const float ha = __ldg(hpre + ((size_t)b * 2 + 0) * hidden + j), hm = __ldg(hpre + ((size_t)b * 2 + 1) * hidden + j);
       const float da = __ldg(dhpre + ((size_t)b * 2 + 0) * hidden + j), dm = __ldg(dhpre + ((size_t)b * 2 + 1) * hidden + j);
-      s1 = fmaf(da, avg[(size_t)b * C + c], s1);
-      s1 = fmaf(dm, mx[(size_t)b * C + c], s1);
-      s2 = fmaf(dz[(size_t)b * C + c], fmaxf(ha, 0.f) + fmaxf(hm, 0.f), s2);
+      s1[u] = fmaf(da, av, s1[u]);
+      s1[u] = fmaf(dm, mv, s1[u]);
+      s2[u] = fmaf(zv, fmaxf(ha, 0.f) + fmaxf(hm, 0.f), s2[u]);
     }
-    dw1[(size_t)j * C + c] = s1;
-    dw2[(size_t)c * hidden + j] = s2;
+  }
+#pragma unroll
+  for (int u = 0; u < kCaJ; ++u) {
+    const int j = j0 + u;
+    if (j < hidden) {
+      dw1[(size_t)j * C + c] = s1[u];
+      dw2[(size_t)c * hidden + j] = s2[u];
+    }
   }
 }
 
@@ -565,7 +579,8 @@ int dfv_hybrid_attention_bwd(const void* fmap, const float* heat, const float* c
   }
   DFV_LAUNCH_CHECK();
   if (use_channel) {
-    DFV_PDL((ca_wgrad_kernel), (C + 127) / 128, 128, 0, st, dz, dhpre, sv.hpre, sv.avg, sv.mx, dca_w1, dca_w2, B, C, hidden);
+    DFV_PDL((ca_wgrad_kernel), dim3((unsigned)((C + 127) / 128), (unsigned)((hidden + kCaJ - 1) / kCaJ)), 128, 0, st, dz, dhpre, sv.hpre, sv.avg, sv.mx,
+            dca_w1, dca_w2, B, C, hidden);
     DFV_LAUNCH_CHECK();
   }
   return DFV_OK;
