@@ -111,3 +111,33 @@ def test_no_cpu_fallback_and_no_oracle_in_product(d):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
                 assert "efficientnet_pytorch" not in src or f == "model.py" and "import efficientnet_pytorch" not in src
+
+
+def test_tile_planners_stay_within_the_sm(d):
+    """Host-side planners (no launch): every 1x1-conv GEMM and depthwise layer of B4, at the benchmark batches and a few
+    odd ones, gets a plan that fits one SM -- <= 227 KB of shared memory, >= 2 pipeline stages, a grid of at most a
+    few CTAs per SM -- and the weight-stationary GEMM plan appears only where its weight tile fits."""
+    lib = d._lib.lib
+    out = (ctypes.c_int * 8)()
+    dw = (ctypes.c_int * 10)()
+    for B in (1, 3, 64, 256):
+        size = 190
+        for b in d._lib.b4_blocks():
+            hw_in = size * size
+            size_out = (size + b.stride - 1) // b.stride
+            hw_out = size_out * size_out
+            shapes = []
+            if b.has_expand:
+                shapes.append((B * hw_in, b.c_in, b.c_mid, 0))
+            shapes.append((B * hw_out, b.c_mid, b.c_out, 1))
+            for (M, K, N, gated) in shapes:
+                assert lib.dfv_debug_gemm_plan(ctypes.c_longlong(M), K, N, gated, out) == 0, (B, M, K, N)
+                bn, res, stages, nbuf, grid, tpc, smem, ntn = list(out)
+                assert 16 <= bn <= 256 and bn % 16 == 0 and ntn * bn >= N
+                assert stages >= 2 and nbuf in (1, 2) and 0 < smem <= 227 * 1024
+                assert 1 <= grid <= 148 and tpc >= 1 and grid * tpc * (1 if res else 1) >= 1
+                if res:
+                    assert not gated and ((K + 63) // 64) * 64 * bn * 2 <= 160 * 1024
+            assert lib.dfv_debug_dwconv_plan(1, B, size, size, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, dw) == 0
+            assert 0 < dw[5] <= 227 * 1024 and dw[4] <= 256 and dw[8] >= 1 and 1 <= dw[9] <= 148 * 4
+            size = size_out
