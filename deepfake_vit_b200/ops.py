@@ -157,8 +157,31 @@ def _rows(x):
     return B, x.numel() // (B * C_), C_
 
 
+_GUARD = None          # test aid: a list collects (buffer, n, band) while guard mode is on
+_GUARD_VALUE = 12345.678
+
+
 def _f32buf(n, dev):
-    return torch.empty(max(int(n), 1), device=dev, dtype=torch.float32)
+    """fp32 scratch / output buffer of n floats.  In guard mode (tests) it sits between two sentinel bands so that a
+    kernel writing outside the size its *_scratch_floats() function published is caught (guards_intact())."""
+    n = max(int(n), 1)
+    if _GUARD is None:
+        return torch.empty(n, device=dev, dtype=torch.float32)
+    band = 1024
+    full = torch.full((n + 2 * band,), _GUARD_VALUE, device=dev, dtype=torch.float32)
+    _GUARD.append((full, n, band))
+    return full[band:band + n]
+
+
+def guard_mode(on: bool):
+    global _GUARD
+    _GUARD = [] if on else None
+
+
+def guards_intact() -> bool:
+    torch.cuda.synchronize()
+    ref = torch.tensor(_GUARD_VALUE, dtype=torch.float32).item()
+    return all(bool((full[:band] == ref).all()) and bool((full[band + n:] == ref).all()) for full, n, band in (_GUARD or []))
 
 
 def bn_stats(raw, eps, momentum=0.0, running_mean=None, running_var=None):

@@ -366,3 +366,35 @@ def test_combined_loss_values_and_grads(B, cw):
     ref2 = refmodel.CombinedLoss(weights, cwt)(logits.detach(), y)
     assert set(out2) == set(ref2) == {"ce", "focal", "total"}
     assert abs(out2["total"].item() - float(ref2["total"])) < 2e-6
+
+
+# ------------------------------------------------------------------------------- scratch sizes
+def test_scratch_buffers_are_not_overrun(ops):
+    """Every wrapper that hands a kernel a scratch / fp32 output buffer sized by a dfv_*_scratch_floats() function runs
+    with sentinel bands around the buffer (ops.guard_mode): odd batches, K-split and single-slice layers, with and without
+    the optional stages.  (compute-sanitizer is not available on the pool; this is the bounds check of our own.)"""
+    g = torch.Generator(device=DEV).manual_seed(81)
+    rn = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    ops.guard_mode(True)
+    try:
+        for (B, C, sq, parts) in ((1, 48, 12, 3), (5, 336, 14, 2), (17, 1632, 68, 1), (64, 2688, 112, 1), (33, 200, 9, 4)):
+            pool = rn(B, parts, C)
+            w1, b1, w2t, b2 = rn(sq, C) * 0.1, rn(sq) * 0.1, rn(sq, C) * 0.1, rn(C) * 0.1
+            gate = ops.se_gate(pool, 144, w1, b1, w2t, b2, torch.float32)
+            pooled = pool.sum(1) / 144
+            h = pooled @ w1.t() + b1
+            ref = torch.sigmoid((h * torch.sigmoid(h)) @ w2t + b2)
+            assert rel(gate, ref) < 1e-5, (B, C, sq, parts)
+            gate_t, pooled_t, h1_t, g32 = ops.se_train_fwd(pool, 144, w1, b1, w2t.t().contiguous(), b2, torch.float32)
+            assert rel(gate_t, ref) < 1e-5 and rel(pooled_t, pooled) < 1e-6 and rel(h1_t, h) < 1e-5 and torch.equal(gate_t, g32)
+        for (B, H, W, C, hid, uc, us) in ((1, 12, 12, 1792, 112, True, True), (7, 5, 7, 256, 16, True, False), (19, 12, 12, 1792, 112, False, True),
+                                          (4, 3, 3, 64, 8, True, True)):
+            fmap = rn(B, H, W, C).bfloat16()
+            heat = torch.rand(B, H, W, device=DEV, generator=g)
+            ops.hybrid_attention(fmap, heat, rn(hid, C) * 0.1, rn(hid, C) * 0.1, rn(98) * 0.1, uc, us)
+        for (B, dims) in ((1, (1792, 512, 256, 2)), (37, (1792, 512, 256, 2)), (9, (300, 2)), (64, (2048, 1000, 7))):
+            pack = ops.HeadPack([rn(dims[i], dims[i + 1]) * 0.05 for i in range(len(dims) - 1)], [rn(dims[i + 1]) * 0.1 for i in range(len(dims) - 1)])
+            ops.mlp_head(rn(B, dims[0]), pack)
+        assert ops.guards_intact()
+    finally:
+        ops.guard_mode(False)
