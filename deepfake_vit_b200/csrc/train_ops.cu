@@ -616,7 +616,13 @@ __global__ void __cluster_dims__(kSeBwdCluster, 1, 1) __launch_bounds__(256, 2)
         const size_t bc = (size_t)(b0 + im) * C + c0 + cl;
         const float* pb = dgate_partial + (size_t)(b0 + im) * parts * C + c0 + cl;
         float s = 0.f;
-        for (int t = 0; t < parts; ++t) s += __ldg(pb + (size_t)t * C);
+        for (int t0 = 0; t0 < parts; t0 += 8) {      // eight partial rows per round trip (a plain loop chained them)
+          float tv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) tv[u] = t0 + u < parts ? __ldg(pb + (size_t)(t0 + u) * C) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) s += tv[u];
+        }
         const float gv = gate_f32[bc];
         v = s * gv * (1.f - gv);
         dz_out[bc] = v;
@@ -718,11 +724,13 @@ __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __rest
   if (c < C) {
     if (blockIdx.y == 0) {
       float sb = 0.f;
+#pragma unroll 16
       for (int b = 0; b < B; ++b) sb += dz[(size_t)b * C + c];
       db2[c] = sb;
     }
     for (int jj = 0; jj < jn; jj += 4) {
       float s2[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 16      // sixteen batch rows' loads in flight (the plain loop was a chain of 64 dependent load pairs: 17 us)
       for (int b = 0; b < B; ++b) {
         const float z = dz[(size_t)b * C + c], pv = pooled[(size_t)b * C + c];
 #pragma unroll
@@ -745,6 +753,7 @@ __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __rest
   if (blockIdx.x == 0) {
     for (int j = threadIdx.x; j < jn; j += blockDim.x) {
       float s = 0.f;
+#pragma unroll 8
       for (int b = 0; b < B; ++b) s += dh[b * jn + j];
       db1[j0 + j] = s;
     }
