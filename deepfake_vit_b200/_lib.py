@@ -102,6 +102,7 @@ def _load():
         "dfv_bn_stats_from_sums": (C.c_int, [vp, i32, C.c_double, f32, f32, vp, vp, vp, vp, vp]),
         "dfv_debug_dwconv_plan": (C.c_int, [i32] * 9 + [C.POINTER(C.c_int)]),
         "dfv_debug_gemm_plan": (C.c_int, [C.c_longlong, i32, i32, i32, C.POINTER(C.c_int)]),
+        "dfv_debug_dwconv_tc_probe": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp]),
         "dfv_clip_aggregate": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, f32, vp]),
         "dfv_global_avg_pool": (C.c_int, [vp, i32, vp, i32, i64, i32, vp]),
         "dfv_l2_normalize": (C.c_int, [vp, vp, i32, i32, f32, vp]),

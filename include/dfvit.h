@@ -439,6 +439,12 @@ int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int kernel, int
 /* Tile plan of a bf16 tensor-core 1x1-conv GEMM (host only): out[0..7] = N tile, weight-stationary flag, pipeline
  * stages, staging buffers, grid, tiles per CTA, shared-memory bytes, N tiles. */
 int dfv_debug_gemm_plan(long long M, int K, int N, int scaled, int* out);
+/* Probe for the planned tensor-core depthwise kernel (csrc/dw_tc_probe.cu; not on the product path):
+ * out[p][c] = sum_t x[p + offs[t]][c] * w[t][c] for 128 pixels x 64 channels with tcgen05.mma on a TMA-written SWIZZLE_128B
+ * tile viewed from arbitrary pixel-row offsets.  x [P][64] bf16, w [taps][64] bf16, offs DEVICE int[taps], out [128][64] fp32;
+ * mode 0 / 1 = A descriptor without / with the matrix-base-offset field. */
+int dfv_debug_dwconv_tc_probe(const void* x, const void* w, const int* offs, int taps, int P, int mode, float* out,
+                              dfv_stream_t stream);
 
 #ifdef __cplusplus
 }
