@@ -446,6 +446,7 @@ int dfv_debug_gemm_plan(long long M, int K, int N, int scaled, int* out);
 int dfv_debug_dwconv_tc_probe(const void* x, const void* w, const int* offs, int taps, int P, int mode, float* out,
                               dfv_stream_t stream);
 
+
 #ifdef __cplusplus
 }
 #endif
