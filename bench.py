@@ -11,6 +11,7 @@ device->host read of the logits inside the timed region.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -54,6 +55,7 @@ class ClockSampler:
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             self.nvml = pynvml
+            self.sample_nvml()      # first-call costs of the queries are paid here, outside the timed region
         except Exception:
             self.nvml = None
 
@@ -75,7 +77,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.05 if self.nvml is not None else 0.2)
+            self.stop.wait(0.1 if self.nvml is not None else 0.2)
 
     def __enter__(self):
         self.t.start()
@@ -172,6 +174,8 @@ def train_bench(args, d, _lib, dev, rank, world, local, warmup):
     barrier()
     _lib.lib.dfv_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect()
+    gc.disable()        # a collector pause inside a 3475-launch step drains the launch queue (seen as sporadic 33-38 ms steps)
     with ClockSampler(local) as clk:
         barrier()
         ev0.record()
@@ -179,6 +183,7 @@ def train_bench(args, d, _lib, dev, rank, world, local, warmup):
             step(x, lm, y)
         ev1.record()
         barrier()
+    gc.enable()
     ms = ev0.elapsed_time(ev1)
     launches = int(_lib.lib.dfv_launch_count(0))
 
@@ -323,6 +328,8 @@ def main():
     barrier()
     _lib.lib.dfv_launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect()
+    gc.disable()        # no collector pause inside the timed region
     with ClockSampler(local) as clk:
         barrier()
         ev0.record()
@@ -330,6 +337,7 @@ def main():
             logits, _ = model(x, lm)
         ev1.record()
         barrier()
+    gc.enable()
     ms = ev0.elapsed_time(ev1)
     launches = int(_lib.lib.dfv_launch_count(0))
 
