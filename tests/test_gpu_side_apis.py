@@ -138,3 +138,25 @@ def test_train_step_with_fused_optimizer_reads_the_flat_gradient():
     assert changed > 0.9 * len(before)
     lo2, _ = m(x.to(DEV), lm.to(DEV))          # the packed / cast weights follow the in-place update
     assert torch.isfinite(lo2).all()
+
+
+def test_graphed_inference_replays_the_eager_forward_bit_for_bit():
+    """GraphedInference (one CUDA-graph replay per batch) returns exactly what the eager forward returns, follows new
+    inputs copied into its static buffers, and rejects a different shape."""
+    import deepfake_vit_b200 as d
+    torch.manual_seed(3)
+    m = d.DeepfakeDetectionModel(**d.DEFAULT_MODEL_CONFIG).cuda().eval().set_compute_dtype(torch.bfloat16)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(8, 3, 224, 224, device="cuda", generator=g)
+    lm = torch.rand(8, 5, 2, device="cuda", generator=g) * 224
+    gi = d.GraphedInference(m, x, lm, return_features=True)
+    for trial in range(2):
+        x2 = torch.randn(8, 3, 224, 224, device="cuda", generator=g)
+        lm2 = torch.rand(8, 5, 2, device="cuda", generator=g) * 224
+        with torch.no_grad():
+            ref_lo, ref_fe = m(x2, lm2, return_features=True)
+        lo, fe = gi(x2, lm2)
+        torch.cuda.synchronize()
+        assert torch.equal(lo, ref_lo) and torch.equal(fe, ref_fe), trial
+    with pytest.raises(ValueError):
+        gi(x[:4], lm[:4])
