@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
                       const float* __restrict__ bias, const __nv_bfloat16* __restrict__ a_scale,
-                      const __nv_bfloat16* __restrict__ residual, TcParams p) {
+                      TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the dynamic-smem base
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -594,7 +594,7 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   long long grid = 0;
   DFV_TRY(plan_tc(p, smem, grid, M, K, N, a_scale != nullptr, rows_per_image, act));
 
-  CUtensorMap tm_a, tm_b, tm_out, tm_tail;
+  CUtensorMap tm_a, tm_b, tm_out, tm_res;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)K * 2};
@@ -614,8 +614,8 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
     const CUtensorMapSwizzle sw = p.swz == 3 ? CU_TENSOR_MAP_SWIZZLE_128B
                                              : (p.swz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : (p.swz == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
     DFV_TRY(make_tensor_map(&tm_out, DFV_BF16, 2, out, dims, strides, box, sw));
-    tm_tail = tm_out;
-    if (residual) DFV_TRY(make_tensor_map(&tm_tail, DFV_BF16, 2, residual, dims, strides, box, sw));   // the residual: same geometry
+    tm_res = tm_out;      // unused without a residual
+    if (residual) DFV_TRY(make_tensor_map(&tm_res, DFV_BF16, 2, residual, dims, strides, box, sw));   // the residual: same geometry as the output
   }
   DFV_TRY(init_timeout_word_tu());
 #define TC_LAUNCH(S_, A_, R_)                                                                                                   \
@@ -625,9 +625,9 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
       DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
       configured = true;                                                                                                        \
     }                                                                                                                           \
-    pw_gemm_tc_kernel<S_, A_, R_><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, tm_out, tm_tail, bias,                  \
+    pw_gemm_tc_kernel<S_, A_, R_><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, tm_out, tm_res, bias,                   \
                                                                           (const __nv_bfloat16*)a_scale,                       \
-                                                                          (const __nv_bfloat16*)residual, p);                  \
+                                                                          p);                                                  \
   } while (0)
   const bool silu_act = act == DFV_ACT_SILU;
   if (a_scale) {
