@@ -4,11 +4,16 @@
 A "step" is one eval-mode forward pass of DeepfakeDetectionModel over one batch of synthetic
 380x380 face crops + 5-point landmarks.  At every N the per-GPU workload is BASELINE.json
 configs[1] (batch 256, bf16, folded BN) -- weak scaling, no data-path collective (inference needs
-none).  `value` is images/s with inputs resident in HBM; `e2e` is the same metric
-through the public nn.Module call with HOST (pinned) inputs, host->device copies and the
-device->host read of the logits inside the timed region.
+none).  `value` is images/s with inputs resident in HBM (the reference's fp32 NCHW
+contract, forward replayed from a CUDA graph); `e2e` is the same metric through the public
+nn.Module call with HOST (pinned) inputs -- raw uint8 crops, normalised inside the stem kernel --
+host->device copies and the device->host read of the logits inside the timed region.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+The same JSON line carries, under "train_step", BASELINE.json configs[2]: fwd + CombinedLoss + bwd +
+the bucketed NCCL gradient all-reduce (overlapped with the backward) at batch 64 per GPU -- the
+only path with a collective -- so that the driver's 1/2/4/8-GPU runs measure it too.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference] [--mode both|infer|train]
 """
 import argparse
 import gc
@@ -105,12 +110,53 @@ class ClockSampler:
 
 def measured_traffic(kernel):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over this kernel's launches of one
-    step) from the committed ncu pass profiles/r01_traffic.json (scripts/gpu_final_profile.sh); None if absent."""
+    step) from the committed ncu pass (profiles/r02_traffic.json, else round 1's); None if absent."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+            if v is not None:
+                return v
+        except Exception:
+            continue
+    return None
+
+
+def synthetic_inputs(batch, rank, n_buffers=1):
+    """The bench's synthetic batch: for rank 0 the first buffer is exactly oracle.calibrate.synthetic_batch(batch, 380)
+    (the inputs of tests/golden/fwd_bench_b256_380_*.npz and train_bench_b64_380.npz)."""
+    import torch
+    out = []
+    for i in range(n_buffers):
+        g = torch.Generator().manual_seed(1234 + rank + 1000 * i)
+        x = torch.randn(batch, 3, SIZE, SIZE, generator=g)
+        lm = torch.rand(batch, 5, 2, generator=g) * SIZE
+        y = torch.randint(0, 2, (batch,), generator=g)
+        out.append((x, lm, y))
+    return out
+
+
+def to_uint8_crops(x):
+    """Synthetic RAW crops for the uint8 front end: the fp32 N(0,1) image mapped back through the reference's
+    normalisation (u8 = clamp(round((x * std + mean) * 255))), HWC."""
+    import torch
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    return ((x * std + mean) * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this process on the CPUs NVML names for the GPU, so that pinned host buffers (first touch) land
+    on the GPU's NUMA node."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return True
     except Exception:
-        return None
+        return False
 
 
 def cpu_reference_run(steps, warmup, batch=8):
@@ -139,21 +185,88 @@ def cpu_reference_run(steps, warmup, batch=8):
             "ms_per_step": 1e3 * total / steps}
 
 
-def train_bench(args, d, _lib, dev, rank, world, local, warmup):
-    """BASELINE.json configs[2]: training step = train-mode forward + CombinedLoss + backward + NCCL gradient
-    all-reduce (inside backward), batch 64 per GPU, bf16 activations / fp32 master weights and gradients."""
+def gpu_stock_baseline(dev):
+    """SURVEY 8(d) / BASELINE.md 3 "also reported": the oracle module (stock PyTorch ops: cuDNN / cuBLAS / ATen) on the
+    SAME B200, eager fp32 (TF32 off) and torch.autocast(bf16), batch 8 and 256 -- the comparator for the new kernels
+    that is not a CPU.  Baseline leg only: never on the product path."""
+    import torch
+    from oracle import calibrate, refmodel
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    out = {}
+    try:
+        model = calibrate.build(refmodel.get_oracle(), "default").to(dev).eval()
+        for batch in (8, 256):
+            x, lm, _ = calibrate.synthetic_batch(batch, SIZE)
+            x, lm = x.to(dev), lm.to(dev)
+            for tag, ctx in (("fp32", None), ("autocast_bf16", torch.bfloat16)):
+                def fwd():
+                    with torch.no_grad():
+                        if ctx is None:
+                            return model(x, lm)
+                        with torch.autocast("cuda", dtype=ctx):
+                            return model(x, lm)
+                for _ in range(3):
+                    fwd()
+                torch.cuda.synchronize()
+                n = 10 if batch == 8 else 5
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(n):
+                    fwd()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / n
+                out[f"batch{batch}_{tag}"] = {"images_per_s": batch / (ms * 1e-3), "ms_per_step": ms}
+        del model
+        torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["what"] = "reference module (stock PyTorch eager) on this B200, eval forward @380x380, CUDA events"
+    return out
+
+
+def kernel_table(recs, prof_steps, pk):
+    agg = {}
+    for kind, nbytes, flops, kms in recs:
+        a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
+        a[0] += nbytes; a[1] += flops; a[2] += kms; a[3] += 1
+    kernels = {}
+    for kind, (nbytes, flops, kms, n) in agg.items():
+        kernels[kind] = {"launches_per_step": n // prof_steps, "ms_per_step": kms / prof_steps,
+                         "gbs": nbytes / (kms * 1e-3) / 1e9 if kms > 0 else None,
+                         "tflops": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
+                         "hbm_frac": nbytes / (kms * 1e-3) / 1e9 / pk["hbm_gbs"] if kms > 0 else None}
+    top = max(agg, key=lambda k: agg[k][2])
+    tb, tf, tms, tn = agg[top]
+    roofline = {"kernel": top, "bound": "hbm", "achieved": tb / (tms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": measured_traffic(top), "peak_source": pk["source"],
+                "launches": tn // prof_steps, "avg_launch_ms": tms / tn, "algorithmic_bytes_per_launch": tb / tn, "kernels": kernels,
+                "note": "achieved = sum of algorithmic bytes of this kernel's launches / sum of their CUDA-event "
+                        "durations, measured on the launch stream in a profiled pass right after the timed region"}
+    return roofline
+
+
+class Ctx:
+    pass
+
+
+def train_leg(c, steps, warmup):
+    """BASELINE.json configs[2]: training step = train-mode forward + CombinedLoss + backward + NCCL gradient all-reduce
+    (bucketed, issued on a side stream behind per-bucket events of the backward), batch 64 per GPU, bf16 activations /
+    fp32 master weights and gradients.  Returns the dict that goes under "train_step" (or is the line in --mode train)."""
     import torch
     import torch.distributed as dist
-    B = args.batch if args.batch != 256 else 64
+    d, _lib, dev, rank, world, local = c.d, c._lib, c.dev, c.rank, c.world, c.local
+    B = c.train_batch
     torch.manual_seed(42)
     model = d.DeepfakeDetectionModel(**d.DEFAULT_MODEL_CONFIG).to(dev).train().set_compute_dtype(torch.bfloat16)
     if world > 1:
         d.parallel.broadcast_parameters(model)
     crit = d.CombinedLoss({"ce": 1.0, "focal": 0.5, "contrastive": 0.2}, torch.tensor([1.0, 1.5], device=dev))
-    g = torch.Generator().manual_seed(1234 + rank)
-    host_x = torch.randn(B, 3, SIZE, SIZE, generator=g).pin_memory()
-    host_lm = (torch.rand(B, 5, 2, generator=g) * SIZE).pin_memory()
-    host_y = torch.randint(0, 2, (B,), generator=g).pin_memory()
+    hx, hlm, hy = synthetic_inputs(B, rank)[0]
+    host_x, host_lm, host_y = hx.pin_memory(), hlm.pin_memory(), hy.pin_memory()
+    host_u8 = to_uint8_crops(hx).pin_memory()
     x, lm, y = host_x.to(dev), host_lm.to(dev), host_y.to(dev)
 
     def barrier():
@@ -169,26 +282,38 @@ def train_bench(args, d, _lib, dev, rank, world, local, warmup):
         loss.backward()
         return loss
 
+    def timed(n, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
     for _ in range(warmup):
         step(x, lm, y)
     barrier()
     _lib.lib.dfv_launch_count(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gc.collect()
-    gc.disable()        # a collector pause inside a 3475-launch step drains the launch queue (seen as sporadic 33-38 ms steps)
+    gc.disable()        # a collector pause inside a ~3000-launch step drains the launch queue (seen as sporadic 33-38 ms steps)
     with ClockSampler(local) as clk:
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            step(x, lm, y)
-        ev1.record()
-        barrier()
-    gc.enable()
-    ms = ev0.elapsed_time(ev1)
+        ms = timed(steps, lambda: step(x, lm, y))
     launches = int(_lib.lib.dfv_launch_count(0))
+    # the collective's cost: the same loop with it switched off, and the all-reduce alone
+    ms_off, ar_ms = None, None
+    if world > 1:
+        model.ddp_allreduce = False
+        step(x, lm, y)
+        ms_off = timed(steps, lambda: step(x, lm, y))
+        model.ddp_allreduce = True
+        flat = model._last_flat_grad
+        ar_ms = timed(5, lambda: d.parallel.allreduce_gradients(flat)) / 5
+    gc.enable()
 
     _lib.lib.dfv_profile_enable(1)
-    prof_steps = min(args.steps, 3)
+    prof_steps = min(steps, 3)
     for _ in range(prof_steps):
         step(x, lm, y)
     torch.cuda.synchronize()
@@ -196,125 +321,65 @@ def train_bench(args, d, _lib, dev, rank, world, local, warmup):
     _lib.lib.dfv_profile_enable(0)
     if os.environ.get("DFV_BENCH_DUMP"):          # per-launch list of the last profiled step
         per = len(recs) // prof_steps
-        with open(os.environ["DFV_BENCH_DUMP"], "w") as f:
+        with open(os.environ["DFV_BENCH_DUMP"] + ".train", "w") as f:
             json.dump([{"kind": k, "bytes": b, "flops": fl, "ms": m} for k, b, fl, m in recs[-per:]], f)
-    agg = {}
-    for kind, nbytes, flops, kms in recs:
-        a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
-        a[0] += nbytes; a[1] += flops; a[2] += kms; a[3] += 1
     pk = peaks()
-    kernels = {k: {"launches_per_step": n // prof_steps, "ms_per_step": kms / prof_steps,
-                   "gbs": nb / (kms * 1e-3) / 1e9 if kms > 0 else None, "tflops": fl / (kms * 1e-3) / 1e12 if kms > 0 else None,
-                   "hbm_frac": nb / (kms * 1e-3) / 1e9 / pk["hbm_gbs"] if kms > 0 else None}
-               for k, (nb, fl, kms, n) in agg.items()}
-    top = max(agg, key=lambda k: agg[k][2])
-    tb, tf, tms, tn = agg[top]
-    roofline = {"kernel": top, "bound": "hbm", "achieved": tb / (tms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": measured_traffic(top), "peak_source": pk["source"],
-                "launches": tn // prof_steps, "avg_launch_ms": tms / tn, "algorithmic_bytes_per_launch": tb / tn, "kernels": kernels}
+    roofline = kernel_table(recs, prof_steps, pk)
 
-    # end to end: pinned host batch -> device every step, loss read back every step
-    dx, dl, dy = torch.empty_like(x), torch.empty_like(lm), torch.empty_like(y)
+    # end to end: pinned host batch (raw uint8 crops) -> device every step, loss read back every step
+    du8, dl, dy = torch.empty_like(host_u8, device=dev), torch.empty_like(lm), torch.empty_like(y)
 
     def e2e_step():
-        dx.copy_(host_x, non_blocking=True)
+        du8.copy_(host_u8, non_blocking=True)
         dl.copy_(host_lm, non_blocking=True)
         dy.copy_(host_y, non_blocking=True)
-        return step(dx, dl, dy).item()
+        return step(du8, dl, dy).item()
 
     e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = timed(steps, e2e_step)
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, ms_off], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t[0].item(), t[1].item()
+        ms, e2e_ms, ms_off = t[0].item(), t[1].item(), t[2].item()
     n_gpus = max(world, 1)
-    if rank == 0:
-        line = {"metric": "images/sec @380x380 train-step (bf16)", "value": B * n_gpus * args.steps / (ms * 1e-3), "unit": "images/s",
-                "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"training step fwd + CombinedLoss(CE+Focal+Contrastive, class weights) + bwd + gradient all-reduce, "
-                                       f"batch {B}/GPU @ {SIZE}x{SIZE} (BASELINE.json configs[2]); optimizer step not included",
-                           "per_gpu_batch": B, "global_batch": B * n_gpus, "image_size": SIZE,
-                           "parallelism": f"dp{n_gpus} (batch sharded, one NCCL all-reduce of the flat fp32 gradient buffer per step)",
-                           "l2_policy": "activations exceed the 126 MB L2; no flush needed"},
-                "roofline": roofline, "cpu_baseline": None,
-                "e2e": {"value": B * n_gpus * args.steps / (e2e_ms * 1e-3), "unit": "images/s",
-                        "h2d_bytes_per_step": (x.numel() * 4 + lm.numel() * 4 + y.numel() * 8) * n_gpus, "d2h_bytes_per_step": 4 * n_gpus,
-                        "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "clocks": clk.summary(),
-                "memory_gb": torch.cuda.max_memory_allocated() / 1e9}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    out = {"metric": "images/sec @380x380 train-step (bf16)", "value": B * n_gpus * steps / (ms * 1e-3), "unit": "images/s",
+           "n_gpus": n_gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": f"training step fwd + CombinedLoss(CE+Focal+Contrastive, class weights) + bwd + gradient all-reduce, "
+                                  f"batch {B}/GPU @ {SIZE}x{SIZE} (BASELINE.json configs[2]); optimizer step not included",
+                      "per_gpu_batch": B, "global_batch": B * n_gpus, "image_size": SIZE,
+                      "parallelism": f"dp{n_gpus} (batch sharded; flat fp32 gradient buffer all-reduced over NCCL in "
+                                     f"{len(model._reducer.buckets) if model._reducer else 1} reverse-topological buckets on a side stream, "
+                                     "each behind the CUDA event of its last backward unit)",
+                      "l2_policy": "activations exceed the 126 MB L2; no flush needed"},
+           "allreduce": None if world == 1 else {
+               "ms_alone": ar_ms, "bytes": model._last_flat_grad.numel() * 4, "ms_per_step_without_collective": ms_off / steps,
+               "exposed_ms_per_step": ms / steps - ms_off / steps, "buckets": len(model._reducer.buckets),
+               "note": "exposed = step time with the collective - the same loop with it switched off (max over ranks each)"},
+           "roofline": roofline, "cpu_baseline": None,
+           "e2e": {"value": B * n_gpus * steps / (e2e_ms * 1e-3), "unit": "images/s",
+                   "h2d_bytes_per_step": (host_u8.numel() + lm.numel() * 4 + y.numel() * 8) * n_gpus, "d2h_bytes_per_step": 4 * n_gpus,
+                   "ms_per_step": e2e_ms / steps, "note": "model(uint8 crops, landmarks) + CombinedLoss + backward, pinned host inputs, loss.item() every step"},
+           "gpu_launches": launches, "clocks": clk.summary(),
+           "memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
-                    help="infer = BASELINE.json configs[1] (the headline line); train = configs[2], fwd + CombinedLoss + bwd + "
-                         "gradient all-reduce at batch 64/GPU")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
-
-    config = {"workload": f"batch-{args.batch}/GPU bf16 eval forward @ {SIZE}x{SIZE}, folded BN, fused SE epilogues "
-                          "(BASELINE.json configs[1])",
-              "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "image_size": SIZE,
-              "parallelism": f"dp{max(world, 1)} (batch sharded, no collective)",
-              "l2_policy": "activations (>=0.9 GB per layer at batch 256) exceed the 126 MB L2; no flush needed"}
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        steps = min(args.steps, 8)
-        cb = cpu_reference_run(steps, min(warmup, 2))
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(warmup, 2), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return
-
+def infer_leg(c, args, warmup):
     import torch
     import torch.distributed as dist
-    import deepfake_vit_b200 as d
-    from deepfake_vit_b200 import _lib
-    MODEL_CONFIG = d.DEFAULT_MODEL_CONFIG         # the YAML `model:` mapping
-
-    assert torch.cuda.is_available(), "bench.py --impl b200 needs a B200"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    if args.mode == "train":
-        return train_bench(args, d, _lib, dev, rank, world, local, warmup)
-
+    d, _lib, dev, rank, world, local = c.d, c._lib, c.dev, c.rank, c.world, c.local
     torch.manual_seed(42)
-    model = d.DeepfakeDetectionModel(**MODEL_CONFIG).to(dev).eval().set_compute_dtype(torch.bfloat16)
+    model = d.DeepfakeDetectionModel(**d.DEFAULT_MODEL_CONFIG).to(dev).eval().set_compute_dtype(torch.bfloat16)
     B = args.batch
-    g = torch.Generator().manual_seed(1234 + rank)
-    host_x = [torch.randn(B, 3, SIZE, SIZE, generator=g).pin_memory() for _ in range(2)]
-    host_lm = [(torch.rand(B, 5, 2, generator=g) * SIZE).pin_memory() for _ in range(2)]
-    x, lm = host_x[0].to(dev), host_lm[0].to(dev)
+    bufs = synthetic_inputs(B, rank, 2)
+    host_u8 = [to_uint8_crops(b[0]).pin_memory() for b in bufs]
+    host_lm = [b[1].pin_memory() for b in bufs]
+    host_x0 = bufs[0][0].pin_memory()
+    x, lm = host_x0.to(dev), host_lm[0].to(dev)
+    del bufs
 
     def barrier():
         torch.cuda.synchronize()
@@ -322,11 +387,17 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident throughput
-    for _ in range(warmup):
+    # ---- device-resident throughput: the forward captured once into a CUDA graph, one replay per step
+    for _ in range(2):
         model(x, lm)
-    barrier()
+    torch.cuda.synchronize()
     _lib.lib.dfv_launch_count(1)
+    model(x, lm)
+    launches_per_forward = int(_lib.lib.dfv_launch_count(0))
+    graph = d.GraphedInference(model, x, lm)
+    for _ in range(warmup):
+        graph.replay()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gc.collect()
     gc.disable()        # no collector pause inside the timed region
@@ -334,12 +405,22 @@ def main():
         barrier()
         ev0.record()
         for _ in range(args.steps):
-            logits, _ = model(x, lm)
+            logits, _ = graph.replay()
         ev1.record()
         barrier()
-    gc.enable()
     ms = ev0.elapsed_time(ev1)
-    launches = int(_lib.lib.dfv_launch_count(0))
+    # the same steps launched eagerly (one C call enqueuing ~130 kernels per step)
+    for _ in range(3):
+        model(x, lm)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        model(x, lm)
+    g1.record()
+    barrier()
+    eager_ms = g0.elapsed_time(g1)
+    gc.enable()
 
     # ---- per-kernel CUDA-event profile on the same stream, same buffers (roofline leg)
     _lib.lib.dfv_profile_enable(1)
@@ -353,93 +434,166 @@ def main():
         per = len(recs) // prof_steps
         with open(os.environ["DFV_BENCH_DUMP"], "w") as f:
             json.dump([{"kind": k, "bytes": b, "flops": fl, "ms": m} for k, b, fl, m in recs[-per:]], f)
-    agg = {}
-    for kind, nbytes, flops, kms in recs:
-        a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
-        a[0] += nbytes; a[1] += flops; a[2] += kms; a[3] += 1
     pk = peaks()
-    kernels = {}
-    for kind, (nbytes, flops, kms, n) in agg.items():
-        kernels[kind] = {"launches_per_step": n // prof_steps, "ms_per_step": kms / prof_steps,
-                         "gbs": nbytes / (kms * 1e-3) / 1e9 if kms > 0 else None,
-                         "tflops": flops / (kms * 1e-3) / 1e12 if kms > 0 else None,
-                         "hbm_frac": nbytes / (kms * 1e-3) / 1e9 / pk["hbm_gbs"] if kms > 0 else None}
-    top = max(agg, key=lambda k: agg[k][2])
-    tb, tf, tms, tn = agg[top]
-    roofline = {"kernel": top, "bound": "hbm", "achieved": tb / (tms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": measured_traffic(top), "peak_source": pk["source"],
-                "launches": tn // prof_steps, "avg_launch_ms": tms / tn,
-                "algorithmic_bytes_per_launch": tb / tn, "kernels": kernels,
-                "note": "achieved = sum of algorithmic bytes of this kernel's launches / sum of their CUDA-event "
-                        "durations, measured on the launch stream in a profiled pass right after the timed region"}
+    roofline = kernel_table(recs, prof_steps, pk)
 
     # ---- end to end through the public API: pinned host inputs, double-buffered H2D, D2H of logits
-    copy_stream = torch.cuda.Stream(device=dev)
-    dev_x = [torch.empty_like(x) for _ in range(2)]
-    dev_lm = [torch.empty_like(lm) for _ in range(2)]
-    host_out = torch.empty(B, 2).pin_memory()
-    ready = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
+    def e2e(host_imgs, tag):
+        copy_stream = torch.cuda.Stream(device=dev)
+        dev_x = [torch.empty_like(h, device=dev) for h in host_imgs]
+        dev_lm = [torch.empty_like(lm) for _ in range(2)]
+        host_out = torch.empty(B, 2).pin_memory()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
-    def stage(i):
-        s = i & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done[s])          # buffer free (previous user finished)
-            dev_x[s].copy_(host_x[s], non_blocking=True)
-            dev_lm[s].copy_(host_lm[s], non_blocking=True)
-            ready[s].record(copy_stream)
-
-    def e2e_loop(n):
-        cur = torch.cuda.current_stream()
-        stage(0)
-        for i in range(n):
+        def stage(i):
             s = i & 1
-            if i + 1 < n:
-                stage(i + 1)
-            cur.wait_event(ready[s])
-            lo, _ = model(dev_x[s], dev_lm[s])
-            done[s].record(cur)
-            host_out.copy_(lo, non_blocking=True)
-        cur.synchronize()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[s])          # buffer free (previous user finished)
+                dev_x[s].copy_(host_imgs[s], non_blocking=True)
+                dev_lm[s].copy_(host_lm[s], non_blocking=True)
+                ready[s].record(copy_stream)
 
-    for s in range(2):
-        done[s].record(torch.cuda.current_stream())
-    e2e_loop(3)
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_loop(args.steps)
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e2e_ms, 0.0) if e2e_ms > 0 else wall_ms
+        def loop(n):
+            cur = torch.cuda.current_stream()
+            stage(0)
+            for i in range(n):
+                s = i & 1
+                if i + 1 < n:
+                    stage(i + 1)
+                cur.wait_event(ready[s])
+                lo, _ = model(dev_x[s], dev_lm[s])
+                done[s].record(cur)
+                host_out.copy_(lo, non_blocking=True)
+            cur.synchronize()
+
+        for s in range(2):
+            done[s].record(torch.cuda.current_stream())
+        loop(3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop(args.steps)
+        e1.record()
+        barrier()
+        t = e0.elapsed_time(e1)
+        h2d = host_imgs[0].numel() * host_imgs[0].element_size() + lm.numel() * 4
+        del dev_x
+        return t, h2d
+
+    e2e_ms, h2d_u8 = e2e(host_u8, "u8")
+    host_f32 = [host_x0, host_x0]
+    e2e32_ms, h2d_f32 = e2e(host_f32, "f32")
 
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, e2e32_ms, eager_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t[0].item(), t[1].item()
+        ms, e2e_ms, e2e32_ms, eager_ms = (t[i].item() for i in range(4))
     n_gpus = max(world, 1)
-    value = B * n_gpus * args.steps / (ms * 1e-3)
-    e2e_value = B * n_gpus * args.steps / (e2e_ms * 1e-3)
+    per = lambda t: B * n_gpus * args.steps / (t * 1e-3)
+    line = {"metric": METRIC, "value": per(ms), "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": c.config,
+            "roofline": roofline, "cpu_baseline": None,
+            "e2e": {"value": per(e2e_ms), "unit": "images/s",
+                    "h2d_bytes_per_step": h2d_u8 * n_gpus, "d2h_bytes_per_step": B * 2 * 4 * n_gpus, "ms_per_step": e2e_ms / args.steps,
+                    "note": "model(images_uint8, landmarks): pinned host RAW crops (uint8 HWC, normalised inside the stem kernel), "
+                            "double-buffered H2D on a copy stream, logits copied back every step",
+                    "fp32_nchw_input": {"value": per(e2e32_ms), "h2d_bytes_per_step": h2d_f32 * n_gpus, "ms_per_step": e2e32_ms / args.steps,
+                                        "note": "the same loop fed the reference's fp32 NCHW contract (4x the bytes)"}},
+            "eager": {"value": per(eager_ms), "ms_per_step": eager_ms / args.steps,
+                      "note": "the timed steps launched eagerly instead of replayed from the CUDA graph"},
+            "gpu_launches": launches_per_forward * args.steps,
+            "gpu_launches_note": f"{launches_per_forward} kernels per forward (counted by the library on an eager step), replayed from one CUDA graph per step",
+            "clocks": clk.summary(),
+            "end_to_end_roofline": {"algorithmic_bytes_per_image": 204.7e6, "bound_images_per_s_per_gpu": pk["hbm_gbs"] * 1e9 / 204.7e6,
+                                    "frac": per(ms) / n_gpus / (pk["hbm_gbs"] * 1e9 / 204.7e6)}}
+    del graph, model
+    torch.cuda.empty_cache()
+    return line
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (inference leg)")
+    ap.add_argument("--train-batch", type=int, default=64, help="images per GPU per step (training leg)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="both", choices=["both", "infer", "train"],
+                    help="both = the headline line (BASELINE.json configs[1]) with configs[2] under \"train_step\"; "
+                         "infer / train = one leg only")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    config = {"workload": f"batch-{args.batch}/GPU bf16 eval forward @ {SIZE}x{SIZE}, folded BN, fused SE epilogues "
+                          "(BASELINE.json configs[1])",
+              "per_gpu_batch": args.batch, "global_batch": args.batch * max(world, 1), "image_size": SIZE,
+              "parallelism": f"dp{max(world, 1)} (batch sharded, no collective)",
+              "launch": "one CUDA-graph replay per step (GraphedInference); eager timing under \"eager\"",
+              "l2_policy": "activations (>=0.9 GB per layer at batch 256) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 200))
+        wu = max(1, min(args.warmup, 20))
+        cb = cpu_reference_run(steps, wu)
+        ref_config = dict(config)
+        ref_config["workload"] = (f"reference CPU path: batch 8, fp32, eval forward @ {SIZE}x{SIZE} on the host cores "
+                                  f"({cb['cores']} threads) -- a bounded sample of the batch-{args.batch} workload of BASELINE.json configs[1]; "
+                                  "images/s is batch-size independent on the CPU")
+        ref_config["per_gpu_batch"] = ref_config["global_batch"] = 8
+        ref_config["parallelism"] = "none (one process, all host threads)"
+        ref_config.pop("launch", None)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": wu, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": ref_config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import deepfake_vit_b200 as d
+    from deepfake_vit_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a B200"
+    bind_to_gpu_numa_node(local)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    c = Ctx()
+    c.d, c._lib, c.dev, c.rank, c.world, c.local, c.config = d, _lib, dev, rank, world, local, config
+    c.train_batch = args.train_batch
+
+    line = None
+    if args.mode in ("both", "infer"):
+        line = infer_leg(c, args, warmup)
+    if args.mode in ("both", "train"):
+        tsteps = args.steps if args.mode == "train" else max(3, min(args.steps, 10))
+        tr = train_leg(c, tsteps, max(3, min(warmup, 5)))
+        if line is None:
+            line = tr
+        else:
+            tr.pop("cpu_baseline", None)
+            line["train_step"] = tr
     if rank == 0:
-        cpu = None
-        if n_gpus == 1 and not args.no_cpu_baseline:
+        if max(world, 1) == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(5, 2)
-            cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n_gpus, "steps": args.steps,
-                "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
-                "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": "images/s",
-                        "h2d_bytes_per_step": (x.numel() * 4 + lm.numel() * 4) * n_gpus,
-                        "d2h_bytes_per_step": B * 2 * 4 * n_gpus, "ms_per_step": e2e_ms / args.steps,
-                        "note": "model(images, landmarks) with pinned host inputs, double-buffered H2D on a copy stream"},
-                "gpu_launches": launches, "clocks": clk.summary(),
-                "end_to_end_roofline": {"algorithmic_bytes_per_image": 204.7e6, "bound_images_per_s_per_gpu": pk["hbm_gbs"] * 1e9 / 204.7e6,
-                                        "frac": value / n_gpus / (pk["hbm_gbs"] * 1e9 / 204.7e6)}}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                line["gpu_stock_baseline"] = gpu_stock_baseline(dev)
+            except Exception as e:       # a baseline leg must never take the product's number down with it
+                line["gpu_stock_baseline"] = {"unavailable": repr(e)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -38,7 +38,29 @@ class InferArgs(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("logits", C.c_void_p), ("features", C.c_void_p), ("heat", C.c_void_p),
         ("taps", C.POINTER(C.c_void_p)),
+        ("images_u8", C.c_void_p), ("u8_norm", C.c_float * 6),
     ]
+
+
+class GemmTuning(C.Structure):
+    _fields_ = [("weight_stationary", C.c_int32), ("bn", C.c_int32)]
+
+
+class DwconvTuning(C.Structure):
+    _fields_ = [("L", C.c_int32), ("TW", C.c_int32), ("TH", C.c_int32), ("CB", C.c_int32)]
+
+
+class PackArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("bn_eps", C.c_float), ("cls_bn_eps", C.c_float),
+        ("params", C.POINTER(C.c_void_p)), ("blob", C.c_void_p),
+        ("head_layers", C.c_int32), ("head_dims", C.POINTER(C.c_int32)),
+        ("head_w_t", C.POINTER(C.c_void_p)), ("head_b", C.POINTER(C.c_void_p)),
+        ("ca_hidden", C.c_int32), ("ca_w2_t", C.c_void_p),
+    ]
+
+
+GRAD_UNITS = 34     # include/dfvit.h DFV_GRAD_UNITS: classifier+attention+head conv, block 31 .. block 0, stem
 
 
 class TrainArgs(C.Structure):
@@ -55,6 +77,7 @@ class TrainArgs(C.Structure):
         ("arena", C.c_void_p), ("arena_bytes", C.c_size_t), ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
         ("logits", C.c_void_p), ("features", C.c_void_p), ("dlogits", C.c_void_p), ("dfeatures", C.c_void_p),
         ("taps", C.POINTER(C.c_void_p)),
+        ("freeze_bn", C.c_int32), ("grad_events", C.POINTER(C.c_void_p)),
     ]
 
 
@@ -76,9 +99,8 @@ def _load():
         "dfv_version": (C.c_int, []),
         "dfv_last_error": (C.c_char_p, []),
         "dfv_device_check": (C.c_int, []),
-        "dfv_debug_force_simt_gemm": (None, [i32]),
         "dfv_launch_count": (i64, [i32]),
-        "dfv_debug_last_timeout": (C.c_uint, []),
+        "dfv_last_timeout_word": (C.c_uint, []),
         "dfv_profile_enable": (C.c_int, [i32]),
         "dfv_profile_count": (C.c_int, []),
         "dfv_profile_get": (C.c_int, [i32, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -91,6 +113,12 @@ def _load():
         "dfv_blob_bytes": (sz, [i32]),
         "dfv_blob_slot": (C.c_int, [i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]),
         "dfv_stem_conv_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "dfv_stem_conv_u8_fwd": (C.c_int, [vp, C.POINTER(C.c_float), vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "dfv_u8_to_nchw_f32": (C.c_int, [vp, C.POINTER(C.c_float), vp, i32, i32, i32, vp]),
+        "dfv_pack_weights": (C.c_int, [C.POINTER(PackArgs), vp]),
+        "dfv_pw_gemm_fwd_tuned": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, C.POINTER(GemmTuning), vp]),
+        "dfv_dwconv_fwd_tuned": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [C.POINTER(DwconvTuning), vp]),
+        "dfv_dwconv_pool_parts_tuned": (C.c_int, [i32] * 9 + [C.POINTER(DwconvTuning)]),
         "dfv_dwconv_pool_parts": (C.c_int, [i32] * 9),
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
         "dfv_se_scratch_floats": (sz, [i32, i32, i32]),
@@ -100,13 +128,12 @@ def _load():
         "dfv_pw_fold_ws_bytes": (sz, [i32]),
         "dfv_dwconv_stats_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 9 + [vp]),
         "dfv_bn_stats_from_sums": (C.c_int, [vp, i32, C.c_double, f32, f32, vp, vp, vp, vp, vp]),
-        "dfv_debug_dwconv_plan": (C.c_int, [i32] * 9 + [C.POINTER(C.c_int)]),
-        "dfv_debug_gemm_plan": (C.c_int, [C.c_longlong, i32, i32, i32, C.POINTER(C.c_int)]),
-        "dfv_debug_dwconv_tc_probe": (C.c_int, [vp, vp, vp, i32, i32, i32, vp, vp]),
+        "dfv_dwconv_plan_info": (C.c_int, [i32] * 9 + [C.POINTER(C.c_int)]),
+        "dfv_gemm_plan_info": (C.c_int, [C.c_longlong, i32, i32, i32, C.POINTER(C.c_int)]),
         "dfv_clip_aggregate": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, f32, vp]),
         "dfv_global_avg_pool": (C.c_int, [vp, i32, vp, i32, i64, i32, vp]),
         "dfv_l2_normalize": (C.c_int, [vp, vp, i32, i32, f32, vp]),
-        "dfv_clip_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, vp] + [C.c_double] * 7 + [i64, vp, vp]),
+        "dfv_clip_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, vp] + [C.c_double] * 7 + [i64, vp, vp, vp]),
         "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
         "dfv_attention_scratch_floats": (sz, [i32] * 5),
         "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 9 + [i32] * 8 + [vp]),
@@ -161,7 +188,7 @@ lib, EXPORTS = _load()
 def check(rc: int):
     if rc != 0:
         raise DfvError(f"libdfvit error {rc}: {lib.dfv_last_error().decode(errors='replace')} "
-                       f"[timeout word 0x{lib.dfv_debug_last_timeout():08x}]")
+                       f"[timeout word 0x{lib.dfv_last_timeout_word():08x}]")
 
 
 PROFILE_KINDS = ("stem", "expand_gemm", "dwconv", "se_gate", "project_gemm", "heatmap", "attention", "mlp_head",

@@ -13,7 +13,6 @@ namespace dfv {
 
 static thread_local char g_error[512] = "";
 static thread_local long long g_launches = 0;
-static int g_force_simt = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,7 +21,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
-bool force_simt_gemm() { return g_force_simt != 0; }
+#ifdef DFV_DEBUG
 int debug_flags() {
   static int flags = -1;
   if (flags < 0) {
@@ -31,6 +30,7 @@ int debug_flags() {
   }
   return flags;
 }
+#endif
 
 static unsigned int* g_timeout_host = nullptr;
 static unsigned int* g_timeout_dev = nullptr;
@@ -272,17 +272,16 @@ using namespace dfv;
 
 extern "C" {
 
-int dfv_version(void) { return 100; }
+int dfv_version(void) { return 200; }
 const char* dfv_last_error(void) { return g_error; }
 int dfv_device_check(void) { return check_device(); }
-void dfv_debug_force_simt_gemm(int on) { g_force_simt = on; }
 long long dfv_launch_count(int reset) {
   long long v = g_launches;
   if (reset) g_launches = 0;
   return v;
 }
 
-unsigned int dfv_debug_last_timeout(void) { return g_timeout_host ? *g_timeout_host : 0; }
+unsigned int dfv_last_timeout_word(void) { return g_timeout_host ? *g_timeout_host : 0; }
 
 int dfv_profile_enable(int on) {
   for (auto& r : g_prof) {

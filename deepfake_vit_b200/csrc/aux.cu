@@ -110,13 +110,14 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
                                                         float* __restrict__ v, long long n, const double* __restrict__ sqnorm,
                                                         float max_norm, float grad_scale, float decay, float beta1, float omb1,
                                                         float beta2, float omb2, float eps, float step_size, float bc2_sqrt,
-                                                        float* __restrict__ total_norm_out) {
+                                                        float* __restrict__ total_norm_out, const unsigned char* __restrict__ frozen) {
   pdl_prologue();
   const float total = sqrtf((float)*sqnorm) * grad_scale;
   float coef = grad_scale;
   if (max_norm > 0.f) coef *= fminf(max_norm / (total + 1e-6f), 1.0f);
   if (total_norm_out && blockIdx.x == 0 && threadIdx.x == 0) *total_norm_out = total;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (frozen && frozen[i >> 6]) continue;    // a parameter the optimizer must not touch (requires_grad False / no gradient)
     const float gi = g[i] * coef;
     float pi = p[i];
     pi *= decay;                                           // param.mul_(1 - lr * weight_decay)
@@ -171,7 +172,7 @@ int dfv_l2_normalize(const float* x, float* y, int B, int D, float eps, dfv_stre
  * sqnorm_ws: one double of device scratch.  total_norm_out: optional device float (the value clip_grad_norm_ returns). */
 int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, double* sqnorm_ws,
                         double max_norm, double grad_scale, double lr, double beta1, double beta2, double eps, double weight_decay,
-                        long long step, float* total_norm_out, dfv_stream_t stream) {
+                        long long step, float* total_norm_out, const unsigned char* frozen_chunks, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(params && grads && exp_avg && exp_avg_sq && sqnorm_ws && n > 0 && step >= 1, "dfv_clip_adamw_step: bad arguments");
   cudaStream_t st = as_stream(stream);
@@ -183,7 +184,7 @@ int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float
   const double bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
   DFV_PDL((clip_adamw_kernel), blocks, 256, 0, st, params, grads, exp_avg, exp_avg_sq, n, sqnorm_ws, (float)max_norm, (float)grad_scale,
                                            (float)(1.0 - lr * weight_decay), (float)beta1, (float)(1.0 - beta1), (float)beta2,
-                                           (float)(1.0 - beta2), (float)eps, (float)(lr / bc1), (float)std::sqrt(bc2), total_norm_out);
+                                           (float)(1.0 - beta2), (float)eps, (float)(lr / bc1), (float)std::sqrt(bc2), total_norm_out, frozen_chunks);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

@@ -15,8 +15,14 @@ void set_error(const char* fmt, ...);
 int check_device();                       // DFV_OK or DFV_ERR_DEVICE (cached per device)
 int num_sms();
 void count_launch(int n = 1);
-bool force_simt_gemm();
-int debug_flags();   // DFV_DEBUG_FLAGS env: bisecting aid (1 skip dwconv, 2 skip se, 4 skip stem, 8 simt project, 16 simt expand)
+// Bisecting aid of DEBUG builds only (make DEBUG=1 -> -DDFV_DEBUG): DFV_DEBUG_FLAGS env (1 skip dwconv, 2 skip se,
+// 4 skip stem, 8 simt project, 16 simt expand, 32 sync after tc GEMMs).  The product build has no environment
+// switches and no process-global modes: the function is a compile-time 0.
+#ifdef DFV_DEBUG
+int debug_flags();
+#else
+constexpr int debug_flags() { return 0; }
+#endif
 
 #define DFV_REQUIRE(cond, ...)                    \
   do {                                            \
@@ -177,7 +183,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) after ~2 s instead of hanging the GPU, after
-// leaving a tag in host-mapped memory (dfv_debug_last_timeout()) that says which wait starved.
+// leaving a tag in host-mapped memory (dfv_last_timeout_word()) that says which wait starved.
 static __device__ unsigned int* g_timeout_word = nullptr;   // one copy per translation unit (no -rdc)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;

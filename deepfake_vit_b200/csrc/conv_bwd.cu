@@ -475,7 +475,7 @@ int dfv_pw_wgrad(const void* g, const void* a, const void* a_scale, int rows_per
   dim3 grid((unsigned)nt, (unsigned)kt, (unsigned)splits);
   const double es = (double)dtype_size(dtype);
   ProfScope prof(PK_WGRAD, es * ((double)M * K + (double)M * N) + 4.0 * N * K, 2.0 * (double)M * K * N, st);
-  if (dtype == DFV_BF16 && K % 8 == 0 && N % 8 == 0 && !force_simt_gemm())
+  if (dtype == DFV_BF16 && K % 8 == 0 && N % 8 == 0)
     return launch_wgrad_tc(g, a, a_scale, rows_per_image, dw, M, K, N, st);
   if (dtype == DFV_BF16)
     pw_wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, (const __nv_bfloat16*)a_scale,

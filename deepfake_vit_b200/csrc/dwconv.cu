@@ -339,7 +339,8 @@ struct DwPlan {
 // Tile plan: search (channel chunk, strip length, tile width / height) for the configuration that keeps the most
 // threads busy (<= 256 per CTA, two CTAs per SM), wastes the fewest tile cells on the image edge and re-reads the
 // smallest halo.  Every candidate is a valid launch; the score only ranks them.
-static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, int pad_lo, int pad_hi) {
+static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, int pad_lo, int pad_hi,
+                     const dfv_dwconv_tuning* tuning = nullptr) {
   DwParams& p = pl->p;
   p.C = C;
   p.Ho = (H + pad_lo + pad_hi - K) / S + 1;
@@ -352,9 +353,8 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
   const int* Ls = S == 1 ? Ls1 : Ls2;
   const int nL = S == 1 ? 3 : 1;
   double best = -1.0;
-  // tuning aid: DFV_DW_FORCE="L,TW,TH,CB" (0 = free) restricts the search for stride-1 layers
-  int fL = 0, fTW = 0, fTH = 0, fCB = 0;
-  if (const char* e = getenv("DFV_DW_FORCE")) sscanf(e, "%d,%d,%d,%d", &fL, &fTW, &fTH, &fCB);
+  // a caller-supplied dfv_dwconv_tuning (0 = free) restricts the search for stride-1 layers
+  int fL = tuning ? tuning->L : 0, fTW = tuning ? tuning->TW : 0, fTH = tuning ? tuning->TH : 0, fCB = tuning ? tuning->CB : 0;
   if (S != 1) fL = fTW = fTH = fCB = 0;
   for (int cb = 8; cb <= cb_cap; cb += 8) {
     if (fCB && cb != fCB) continue;
@@ -486,8 +486,13 @@ static int dispatch(int K, int S, int L, int act, const CUtensorMap& tm, const f
 using namespace dfv;
 
 extern "C" int dfv_dwconv_pool_parts(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi) {
+  return dfv_dwconv_pool_parts_tuned(dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, nullptr);
+}
+
+extern "C" int dfv_dwconv_pool_parts_tuned(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi,
+                                           const dfv_dwconv_tuning* tuning) {
   DwPlan pl;
-  if (!valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) {
+  if (!valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi, tuning) != DFV_OK) {
     set_error("dfv_dwconv_pool_parts: bad shape");
     return DFV_ERR_INVALID;
   }
@@ -495,12 +500,12 @@ extern "C" int dfv_dwconv_pool_parts(int dtype, int B, int H, int W, int C, int 
   return pl.p.parts;
 }
 
-/* Debug / documentation aid (host only): the tile plan chosen for a layer.
+/* Plan introspection (host only): the tile plan chosen for a layer.
  * out[0..9] = CB, L, TW, TH, threads, smem bytes, tiles_w, tiles_h, parts, grid. */
-extern "C" int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out) {
+extern "C" int dfv_dwconv_plan_info(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out) {
   DwPlan pl;
   if (!out || !valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) {
-    set_error("dfv_debug_dwconv_plan: bad shape");
+    set_error("dfv_dwconv_plan_info: bad shape");
     return DFV_ERR_INVALID;
   }
   plan_grid(pl, B);
@@ -510,7 +515,8 @@ extern "C" int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int 
 }
 
 static int dwconv_entry(const void* x, const float* w, const float* bias, void* y, float* pool_partial, double* stats, int dtype,
-                        int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act, dfv_stream_t stream) {
+                        int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act, dfv_stream_t stream,
+                        const dfv_dwconv_tuning* tuning = nullptr) {
   DFV_TRY(check_device());
   DFV_REQUIRE(x && w && bias && y, "dfv_dwconv_fwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype), "dfv_dwconv_fwd: bad dtype %d", dtype);
@@ -520,7 +526,7 @@ static int dwconv_entry(const void* x, const float* w, const float* bias, void* 
   DFV_REQUIRE(pad_lo >= 0 && pad_hi >= 0 && pad_lo < kernel && pad_hi < kernel, "dfv_dwconv_fwd: bad pad");
   if (debug_flags() & 1) return DFV_OK;
   DwPlan pl;
-  DFV_REQUIRE(make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) == DFV_OK,
+  DFV_REQUIRE(make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi, tuning) == DFV_OK,
               "dfv_dwconv_fwd: cannot tile H=%d W=%d C=%d k=%d s=%d", H, W, C, kernel, stride);
   pl.p.act = act;
   const size_t es = dtype_size(dtype);
@@ -540,6 +546,12 @@ extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, 
                               int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act,
                               dfv_stream_t stream) {
   return dwconv_entry(x, w, bias, y, pool_partial, nullptr, dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, act, stream);
+}
+
+extern "C" int dfv_dwconv_fwd_tuned(const void* x, const float* w, const float* bias, void* y, float* pool_partial, int dtype,
+                                    int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act,
+                                    const dfv_dwconv_tuning* tuning, dfv_stream_t stream) {
+  return dwconv_entry(x, w, bias, y, pool_partial, nullptr, dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, act, stream, tuning);
 }
 
 /* Training forward: raw depthwise conv (no activation) that also ADDS the per-channel sum and sum of squares of its

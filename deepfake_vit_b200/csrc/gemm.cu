@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 // Tile plan of one GEMM: N tile, streaming vs weight-stationary, pipeline depth, grid.
-static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int K, int N, bool scaled, int rows_per_image, int act) {
+static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int K, int N, bool scaled, int rows_per_image, int act,
+                   const dfv_gemm_tuning* tuning = nullptr) {
   p.M = M;
   p.K = K;
   p.N = N;
@@ -489,7 +490,7 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   // Weight-stationary candidates: the CTA keeps one N tile of the weight (all of K) in shared memory and streams A
   // only.  The streaming scheme re-fetches the weight tile for every 128 rows, and on many of these layers that
   // L2 -> SM traffic (not HBM) sets the pace: e.g. 272 -> 1632 at 12x12 moved 496 MB through the crossbar for 21 MB of
-  // A and 0.9 MB of weight.  Estimated crossbar bytes decide; DFV_GEMM_FORCE="b_res,BN" overrides (tuning aid).
+  // A and 0.9 MB of weight.  Estimated crossbar bytes decide; a caller-supplied dfv_gemm_tuning restricts the choice.
   const long long n_tm = (M + kBM - 1) / kBM;
   const int k_blocks = (K + kBK - 1) / kBK;
   const size_t budget = 226 * 1024;   // of the 227 KB a CTA may opt in to
@@ -501,8 +502,7 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   p.m_splits = 1;
   p.tiles_per_cta = 1;
   {
-    int force_res = -1, force_bn = 0;
-    if (const char* f = getenv("DFV_GEMM_FORCE")) sscanf(f, "%d,%d", &force_res, &force_bn);
+    const int force_res = tuning ? tuning->weight_stationary : -1, force_bn = tuning ? tuning->bn : 0;
     if (force_res == 0 && force_bn > 0) {
       for (int ci = 0; ci < 6; ++ci)
         if (parts * cws[ci] == force_bn) { p.BN = force_bn; p.cw = cws[ci]; }
@@ -573,12 +573,12 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
 
 /* Debug / documentation aid (host only): the tile plan of a bf16 tensor-core GEMM.
  * out[0..7] = BN, weight-stationary flag, pipeline stages, staging buffers, grid, tiles per CTA, smem bytes, N tiles. */
-extern "C" int dfv_debug_gemm_plan(long long M, int K, int N, int scaled, int* out) {
+extern "C" int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* out) {
   TcParams p;
   size_t smem = 0;
   long long grid = 0;
   if (!out || M <= 0 || K <= 0 || N <= 0 || K % 8 || N % 8) {
-    set_error("dfv_debug_gemm_plan: bad shape");
+    set_error("dfv_gemm_plan_info: bad shape");
     return DFV_ERR_INVALID;
   }
   DFV_TRY(plan_tc(p, smem, grid, M, K, N, scaled != 0, 1, 0));
@@ -588,11 +588,12 @@ extern "C" int dfv_debug_gemm_plan(long long M, int K, int N, int scaled, int* o
 }
 
 static int launch_tc(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
-                     const void* residual, void* out, long long M, int K, int N, int act, cudaStream_t st) {
+                     const void* residual, void* out, long long M, int K, int N, int act, const dfv_gemm_tuning* tuning,
+                     cudaStream_t st) {
   TcParams p;
   size_t smem = 0;
   long long grid = 0;
-  DFV_TRY(plan_tc(p, smem, grid, M, K, N, a_scale != nullptr, rows_per_image, act));
+  DFV_TRY(plan_tc(p, smem, grid, M, K, N, a_scale != nullptr, rows_per_image, act, tuning));
 
   CUtensorMap tm_a, tm_b, tm_out, tm_res;
   {
@@ -683,7 +684,7 @@ __global__ void tile_gate_kernel(const T* __restrict__ g, T* __restrict__ gf, in
 constexpr int kFoldWElems = 64 * 1024, kFoldBias = 1024, kFoldGate = 256;
 
 static int pick_fold(int dtype, long long M, int K, int N, int rows_per_image, bool gated, int B) {
-  if (dtype != DFV_BF16 || K > 48 || force_simt_gemm()) return 1;
+  if (dtype != DFV_BF16 || K > 48) return 1;
   for (int f = 4; f >= 2; f >>= 1) {
     if (M % f || (gated && rows_per_image % f)) continue;
     // folded width: one N tile, or (f = 4) an exact multiple of the 192-column tile (e.g. 24 -> 144: 576 = 3 x 192)
@@ -702,6 +703,12 @@ using namespace dfv;
 extern "C" int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
                                const void* residual, void* out, int dtype, long long M, int K, int N, int act,
                                dfv_stream_t stream) {
+  return dfv_pw_gemm_fwd_tuned(a, w, bias, a_scale, rows_per_image, residual, out, dtype, M, K, N, act, nullptr, stream);
+}
+
+extern "C" int dfv_pw_gemm_fwd_tuned(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
+                                     const void* residual, void* out, int dtype, long long M, int K, int N, int act,
+                                     const dfv_gemm_tuning* tuning, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(a && w && bias && out, "dfv_pw_gemm_fwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype), "dfv_pw_gemm_fwd: bad dtype %d", dtype);
@@ -711,13 +718,13 @@ extern "C" int dfv_pw_gemm_fwd(const void* a, const void* w, const float* bias, 
   DFV_REQUIRE(act == DFV_ACT_NONE || act == DFV_ACT_SILU, "dfv_pw_gemm_fwd: bad act %d", act);
   cudaStream_t st = as_stream(stream);
   const int dbg = debug_flags();
-  const bool tc = dtype == DFV_BF16 && !force_simt_gemm() && !((dbg & 8) && a_scale) && !((dbg & 16) && !a_scale);
+  const bool tc = dtype == DFV_BF16 && !((dbg & 8) && a_scale) && !((dbg & 16) && !a_scale);
   // algorithmic bytes: A read once, out written once, residual read once, weights once
   const double es = (double)dtype_size(dtype);
   ProfScope prof(tc ? (a_scale ? PK_PROJECT_GEMM : PK_EXPAND_GEMM) : PK_GEMM_SIMT,
                  es * ((double)M * K + (double)M * N + (residual ? (double)M * N : 0.0) + (double)N * K), 2.0 * (double)M * K * N, st);
   if (tc)
-    return launch_tc(a, w, bias, a_scale, rows_per_image, residual, out, M, K, N, act, st);
+    return launch_tc(a, w, bias, a_scale, rows_per_image, residual, out, M, K, N, act, tuning, st);
   dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
   if (dtype == DFV_BF16)
     pw_gemm_simt_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)w, bias,

@@ -120,7 +120,7 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
   DFV_REQUIRE(a != nullptr, "dfv_infer_fwd: null args");
   DFV_REQUIRE(valid_dtype(a->dtype), "dfv_infer_fwd: bad dtype %d", a->dtype);
   DFV_REQUIRE(a->B > 0 && a->H >= 32 && a->W >= 32, "dfv_infer_fwd: bad shape B=%d H=%d W=%d", a->B, a->H, a->W);
-  DFV_REQUIRE(a->blob && a->images_nchw && a->workspace && a->logits && a->features, "dfv_infer_fwd: null pointer");
+  DFV_REQUIRE(a->blob && (a->images_nchw || a->images_u8) && a->workspace && a->logits && a->features, "dfv_infer_fwd: null pointer");
   DFV_REQUIRE(a->head_w_t && a->head_b && a->head_dims && a->head_layers >= 1, "dfv_infer_fwd: classifier head missing");
   const int dtype = a->dtype, B = a->B;
   Shapes s;
@@ -143,8 +143,12 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
   };
 
   int cur = 0;
-  DFV_TRY(dfv_stem_conv_fwd(a->images_nchw, (const float*)W_(-1, DFV_W_STEM), (const float*)W_(-1, DFV_W_STEM_BIAS),
-                            ws.act[cur], dtype, B, a->H, a->W, stem_c, DFV_ACT_SILU, stream));
+  if (a->images_u8)     // raw uint8 HWC crops: the reference's input normalisation runs inside the stem's operand load
+    DFV_TRY(dfv_stem_conv_u8_fwd(a->images_u8, a->u8_norm, (const float*)W_(-1, DFV_W_STEM), (const float*)W_(-1, DFV_W_STEM_BIAS),
+                                 ws.act[cur], dtype, B, a->H, a->W, stem_c, DFV_ACT_SILU, stream));
+  else
+    DFV_TRY(dfv_stem_conv_fwd(a->images_nchw, (const float*)W_(-1, DFV_W_STEM), (const float*)W_(-1, DFV_W_STEM_BIAS),
+                              ws.act[cur], dtype, B, a->H, a->W, stem_c, DFV_ACT_SILU, stream));
   DFV_TRY(tap(0, ws.act[cur], (size_t)B * s.Hs * s.Ws * stem_c));
 
   for (int i = 0; i < n; ++i) {

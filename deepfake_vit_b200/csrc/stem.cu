@@ -10,6 +10,29 @@ namespace dfv {
 
 constexpr int kStemC = 48;
 
+// Input contract of the reference (src/data/dataset.py:82-116): NCHW fp32, already normalised -- or, with kU8, the raw
+// crop: uint8 RGB in HWC order, normalised here on the operand path with the reference's own arithmetic
+//   v = (u8 / 255 - mean[c]) / std[c]        (fp32, IEEE division; dataset.py:95-98, task.ipynb:386)
+// Only 3 x 256 values exist, so every CTA tabulates them once (exact, op for op) and the conv reads the table.
+struct StemNorm {
+  float mean[3], std[3];
+};
+__device__ __forceinline__ void stem_build_lut(float* lut, const StemNorm& nm) {
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    const int c = i >> 8;
+    lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), nm.mean[c]), nm.std[c]);
+  }
+}
+template <bool kU8>
+__device__ __forceinline__ float stem_load(const void* x, const float* lut, int b, int ci, int hi, int wi, int H, int W) {
+  if constexpr (kU8) {
+    const unsigned char u = __ldg(reinterpret_cast<const unsigned char*>(x) + (((size_t)b * H + hi) * W + wi) * 3 + ci);
+    return lut[ci * 256 + u];
+  } else {
+    return __ldg(reinterpret_cast<const float*>(x) + (((size_t)b * 3 + ci) * H + hi) * W + wi);
+  }
+}
+
 // Register blocking: each thread computes 4 adjacent output pixels x 12 channels, so every
 // 16-byte weight read from shared memory feeds 16 FMAs (the 1 pixel x 48 channel version was
 // bound by shared-memory weight broadcasts).  Four threads (channel quarters) share each pixel quad.
@@ -26,14 +49,16 @@ __device__ __forceinline__ void stem_store12(float* p, const float o[12]) {
   q[2] = make_float4(o[8], o[9], o[10], o[11]);
 }
 
-template <typename T, bool kFast>
-__global__ void __launch_bounds__(256, 3) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <typename T, bool kFast, bool kU8>
+__global__ void __launch_bounds__(256, 3) stem_kernel(const void* __restrict__ x, const StemNorm nm, const float* __restrict__ w,
                                                   const float* __restrict__ bias, T* __restrict__ y, int B, int H,
                                                   int W, int Ho, int Wo, int act) {
   __shared__ __align__(16) float ws[27 * kStemC];
   __shared__ __align__(16) float bs[kStemC];
+  __shared__ float lut[kU8 ? 768 : 1];
   for (int i = threadIdx.x; i < 27 * kStemC; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < kStemC) bs[threadIdx.x] = bias[threadIdx.x];
+  if constexpr (kU8) stem_build_lut(lut, nm);
   __syncthreads();
 
   const int quads_w = (Wo + 3) / 4;
@@ -53,16 +78,14 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 12; ++i) acc[pxl][i] = 0.f;
 
-  const float* xb = x + (size_t)b * 3 * H * W;
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int hi = 2 * ho + kh;
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
       float in[9];
-      const float* xr = xb + ((size_t)ci * H + hi) * W + 2 * wo0;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) in[i] = (hi < H && 2 * wo0 + i < W) ? __ldg(xr + i) : 0.f;
+      for (int i = 0; i < 9; ++i) in[i] = (hi < H && 2 * wo0 + i < W) ? stem_load<kU8>(x, lut, b, ci, hi, 2 * wo0 + i, H, W) : 0.f;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const float4* wr = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * 3 + ci) * kStemC + cq * 12);
@@ -118,9 +141,9 @@ __device__ __forceinline__ uint64_t stem_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <bool kAct>
+template <bool kAct, bool kU8>
 __global__ void __launch_bounds__(kStemTcThreads, 2)
-    stem_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    stem_tc_kernel(const void* __restrict__ x, const StemNorm nm, const float* __restrict__ w, const float* __restrict__ bias,
                    __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, long long tiles_per_cta) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -129,6 +152,8 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
   unsigned char* staging = b_tile + 8192;                  // 2 x 12 KB
   float* bias_sm = reinterpret_cast<float*>(staging + 2 * 12288);
   StemBars* bars = reinterpret_cast<StemBars*>(bias_sm + 64);
+  float* lut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + ((sizeof(StemBars) + 15) / 16) * 16);   // [3][256], kU8 only
+  if constexpr (kU8) stem_build_lut(lut, nm);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = (long long)B * Ho * Wo;
@@ -179,16 +204,14 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
         const int wo = (int)(p % Wo);
         const long long r = p / Wo;
         const int ho = (int)(r % Ho), b = (int)(r / Ho);
-        const float* xb = x + (size_t)b * 3 * H * W;
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const int hi = 2 * ho + kh;
-            const float* xr = xb + ((size_t)ci * H + hi) * W + 2 * wo;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
-              if (hi < H && 2 * wo + kw < W) v[(kh * 3 + kw) * 3 + ci] = __ldg(xr + kw);
+              if (hi < H && 2 * wo + kw < W) v[(kh * 3 + kw) * 3 + ci] = stem_load<kU8>(x, lut, b, ci, hi, 2 * wo + kw, H, W);
           }
       }
       mbar_wait(&bars->a_empty[s], ph ^ 1, 31);
@@ -294,25 +317,70 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
   }
 }
 
-static int launch_stem_tc(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Ho, int Wo, int act,
-                          cudaStream_t st) {
+template <bool kU8>
+static int launch_stem_tc(const void* x, const StemNorm& nm, const float* w, const float* bias, void* y, int B, int H, int W, int Ho, int Wo,
+                          int act, cudaStream_t st) {
   const long long total = (long long)B * Ho * Wo;
   const long long n_tiles = (total + kStemTile - 1) / kStemTile;
   long long grid = std::min<long long>(n_tiles, 2LL * num_sms());
   const long long tpc = (n_tiles + grid - 1) / grid;
   grid = (n_tiles + tpc - 1) / tpc;
-  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 1024;
+  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 16 + (kU8 ? 768 * 4 : 0) + 1024;
   DFV_TRY(init_timeout_word_tu());
   static thread_local bool configured = false;
   if (!configured) {
-    DFV_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    DFV_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true, kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false, kU8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
   if (act)
-    stem_tc_kernel<true><<<(unsigned)grid, kStemTcThreads, smem, st>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, tpc);
+    stem_tc_kernel<true, kU8><<<(unsigned)grid, kStemTcThreads, smem, st>>>(x, nm, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, tpc);
   else
-    stem_tc_kernel<false><<<(unsigned)grid, kStemTcThreads, smem, st>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, tpc);
+    stem_tc_kernel<false, kU8><<<(unsigned)grid, kStemTcThreads, smem, st>>>(x, nm, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, tpc);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+// uint8 HWC -> normalised fp32 NCHW (the reference's input contract), same table as the fused stem
+__global__ void __launch_bounds__(256) u8_to_nchw_kernel(const unsigned char* __restrict__ x, const StemNorm nm, float* __restrict__ y,
+                                                        int B, int H, int W) {
+  __shared__ float lut[768];
+  stem_build_lut(lut, nm);
+  __syncthreads();
+  const long long total = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const long long b = p / ((long long)H * W), hw = p % ((long long)H * W);
+    const unsigned char* px = x + p * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[((size_t)b * 3 + c) * H * W + hw] = lut[c * 256 + px[c]];
+  }
+}
+
+template <bool kU8>
+static int stem_entry(const void* x, const float* norm6, const float* w, const float* bias, void* y, int dtype, int B, int H, int W, int C,
+                      int act, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(x && w && bias && y && (!kU8 || norm6), "dfv_stem_conv_fwd: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype), "dfv_stem_conv_fwd: bad dtype %d", dtype);
+  DFV_REQUIRE(C == kStemC, "dfv_stem_conv_fwd: C must be %d (EfficientNet-B4 stem), got %d", kStemC, C);
+  DFV_REQUIRE(B > 0 && H >= 3 && W >= 3, "dfv_stem_conv_fwd: bad shape B=%d H=%d W=%d", B, H, W);
+  if (debug_flags() & 4) return DFV_OK;
+  StemNorm nm = {{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  if (kU8) {
+    for (int c = 0; c < 3; ++c) {
+      nm.mean[c] = norm6[c];
+      nm.std[c] = norm6[3 + c];
+      DFV_REQUIRE(nm.std[c] > 0.f, "dfv_stem_conv_u8_fwd: std[%d] must be positive", c);
+    }
+  }
+  const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo;
+  const long long threads = (long long)B * Ho * ((Wo + 3) / 4) * 4;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  ProfScope prof(PK_STEM, (double)B * 3 * H * W * (kU8 ? 1 : 4) + (double)total * kStemC * dtype_size(dtype),
+                 2.0 * 27 * kStemC * (double)total, as_stream(stream));
+  if (dtype == DFV_BF16) return launch_stem_tc<kU8>(x, nm, w, bias, y, B, H, W, Ho, Wo, act, as_stream(stream));
+  stem_kernel<float, false, kU8><<<grid, 256, 0, as_stream(stream)>>>(x, nm, w, bias, (float*)y, B, H, W, Ho, Wo, act);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -323,23 +391,26 @@ using namespace dfv;
 
 extern "C" int dfv_stem_conv_fwd(const float* x, const float* w, const float* bias, void* y, int dtype, int B, int H,
                                  int W, int C, int act, dfv_stream_t stream) {
+  return stem_entry<false>(x, nullptr, w, bias, y, dtype, B, H, W, C, act, stream);
+}
+
+extern "C" int dfv_stem_conv_u8_fwd(const uint8_t* x, const float* norm6, const float* w, const float* bias, void* y, int dtype,
+                                    int B, int H, int W, int C, int act, dfv_stream_t stream) {
+  return stem_entry<true>(x, norm6, w, bias, y, dtype, B, H, W, C, act, stream);
+}
+
+extern "C" int dfv_u8_to_nchw_f32(const uint8_t* x, const float* norm6, float* y, int B, int H, int W, dfv_stream_t stream) {
   DFV_TRY(check_device());
-  DFV_REQUIRE(x && w && bias && y, "dfv_stem_conv_fwd: null pointer");
-  DFV_REQUIRE(valid_dtype(dtype), "dfv_stem_conv_fwd: bad dtype %d", dtype);
-  DFV_REQUIRE(C == kStemC, "dfv_stem_conv_fwd: C must be %d (EfficientNet-B4 stem), got %d", kStemC, C);
-  DFV_REQUIRE(B > 0 && H >= 3 && W >= 3, "dfv_stem_conv_fwd: bad shape B=%d H=%d W=%d", B, H, W);
-  if (debug_flags() & 4) return DFV_OK;
-  const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
-  const long long total = (long long)B * Ho * Wo;
-  const long long threads = (long long)B * Ho * ((Wo + 3) / 4) * 4;
-  const unsigned grid = (unsigned)((threads + 255) / 256);
-  ProfScope prof(PK_STEM, (double)B * 3 * H * W * 4 + (double)total * kStemC * dtype_size(dtype),
-                 2.0 * 27 * kStemC * (double)total, as_stream(stream));
-  if (dtype == DFV_BF16 && !force_simt_gemm()) return launch_stem_tc(x, w, bias, y, B, H, W, Ho, Wo, act, as_stream(stream));
-  if (dtype == DFV_BF16)
-    stem_kernel<__nv_bfloat16, true><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Ho, Wo, act);
-  else
-    stem_kernel<float, false><<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, (float*)y, B, H, W, Ho, Wo, act);
+  DFV_REQUIRE(x && norm6 && y && B > 0 && H > 0 && W > 0, "dfv_u8_to_nchw_f32: bad arguments");
+  StemNorm nm;
+  for (int c = 0; c < 3; ++c) {
+    nm.mean[c] = norm6[c];
+    nm.std[c] = norm6[3 + c];
+    DFV_REQUIRE(nm.std[c] > 0.f, "dfv_u8_to_nchw_f32: std[%d] must be positive", c);
+  }
+  const long long total = (long long)B * H * W;
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+  u8_to_nchw_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, nm, y, B, H, W);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

@@ -260,6 +260,23 @@ __global__ void stem_weight_pack_kernel(const float* __restrict__ src, float* __
   dst[i] = src[(size_t)co * 27 + ci * 9 + kh * 3 + kw];
 }
 
+// freeze_bn: eval-mode BatchNorm inside the training step -- "statistics" are the running ones, nothing is updated
+__global__ void bn_frozen_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float eps, float* __restrict__ mean,
+                                       float* __restrict__ invstd, int C) {
+  pdl_prologue();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  invstd[c] = 1.0f / sqrtf(rv[c] + eps);
+}
+
+static int bn_frozen_stats(const float* rm, const float* rv, float eps, float* mean, float* invstd, int C, cudaStream_t st) {
+  DFV_REQUIRE(rm && rv, "dfv_train_fwd: freeze_bn needs the running statistics");
+  DFV_PDL((bn_frozen_stats_kernel), (C + 127) / 128, 128, 0, st, rm, rv, eps, mean, invstd, C);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
 }  // namespace dfv
 
 using namespace dfv;
@@ -335,8 +352,13 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
   DFV_PDL((stem_weight_pack_kernel), (27 * stem_c + 255) / 256, 256, 0, st, P(-1, DFV_TG_STEM_W), ar.stem_w, stem_c);
   DFV_LAUNCH_CHECK();
   DFV_TRY(dfv_stem_conv_fwd(a->images_nchw, ar.stem_w, ar.zero_bias, ar.s_raw, dtype, B, a->H, a->W, stem_c, DFV_ACT_NONE, stream));
-  DFV_TRY(dfv_bn_stats_fwd(ar.s_raw, dtype, B, (long long)s.Hs * s.Ws, stem_c, eps, mom, ar.sm, ar.si, PW(-1, DFV_TG_STEM_RM),
-                           PW(-1, DFV_TG_STEM_RV), ar.bn_ws, stream));
+  const bool frozen = a->freeze_bn != 0;
+  // batch statistics (+ running-statistics update), or -- freeze_bn -- the running statistics themselves
+  auto bn_stats = [&](const void* raw, long long rows, int C, float* mean, float* invstd, float* rm, float* rv) -> int {
+    if (frozen) return bn_frozen_stats(rm, rv, eps, mean, invstd, C, st);
+    return dfv_bn_stats_fwd(raw, dtype, B, rows, C, eps, mom, mean, invstd, rm, rv, ar.bn_ws, stream);
+  };
+  DFV_TRY(bn_stats(ar.s_raw, (long long)s.Hs * s.Ws, stem_c, ar.sm, ar.si, PW(-1, DFV_TG_STEM_RM), PW(-1, DFV_TG_STEM_RV)));
   DFV_TRY(dfv_bn_act_fwd(ar.s_raw, ar.sm, ar.si, P(-1, DFV_TG_STEM_G), P(-1, DFV_TG_STEM_B), DFV_ACT_SILU, nullptr, nullptr, nullptr,
                          ar.a0, nullptr, dtype, B, (long long)s.Hs * s.Ws, stem_c, stream));
   DFV_TRY(tap(0, ar.a0, (size_t)B * s.Hs * s.Ws * stem_c));
@@ -355,7 +377,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
       DFV_TRY(dfv_cast_weight(P(i, DFV_T_EXPAND_W), ba.wEt, dtype, b.c_in, b.c_mid, 1, stream));
       DFV_TRY(dfv_pw_conv_fwd(x, ba.wE, ar.zero_bias, nullptr, (int)hw_in, nullptr, ba.e_raw, dtype, B, B * hw_in, b.c_in, b.c_mid, DFV_ACT_NONE,
                               ar.fold_ws, stream));
-      DFV_TRY(dfv_bn_stats_fwd(ba.e_raw, dtype, B, hw_in, b.c_mid, eps, mom, ba.m0, ba.i0, PW(i, DFV_T_BN0_RM), PW(i, DFV_T_BN0_RV), ar.bn_ws, stream));
+      DFV_TRY(bn_stats(ba.e_raw, hw_in, b.c_mid, ba.m0, ba.i0, PW(i, DFV_T_BN0_RM), PW(i, DFV_T_BN0_RV)));
       DFV_TRY(dfv_bn_act_fwd(ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ba.e,
                              nullptr, dtype, B, hw_in, b.c_mid, stream));
       dw_in = ba.e;
@@ -364,11 +386,17 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_dw_weight_pack(P(i, DFV_T_DW_W), ba.wDf, b.c_mid, b.kernel, 1, stream));
     // depthwise conv with the BatchNorm batch statistics accumulated in its epilogue (no separate pass over d_raw)
     DFV_REQUIRE(b.c_mid <= 4096, "dfv_train_fwd: c_mid %d > 4096", b.c_mid);
-    DFV_CUDA(cudaMemsetAsync(ar.bn_acc, 0, sizeof(double) * 2 * (size_t)b.c_mid, st));
-    DFV_TRY(dfv_dwconv_stats_fwd(dw_in, ba.wD, ar.zero_bias, ba.d_raw, ar.bn_acc, dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo,
-                                 b.pad_hi, stream));
-    DFV_TRY(dfv_bn_stats_from_sums(ar.bn_acc, b.c_mid, (double)B * (double)hw_out, eps, mom, ba.m1, ba.i1, PW(i, DFV_T_BN1_RM),
-                                   PW(i, DFV_T_BN1_RV), stream));
+    if (frozen) {
+      DFV_TRY(dfv_dwconv_fwd(dw_in, ba.wD, ar.zero_bias, ba.d_raw, nullptr, dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi,
+                             DFV_ACT_NONE, stream));
+      DFV_TRY(bn_frozen_stats(PW(i, DFV_T_BN1_RM), PW(i, DFV_T_BN1_RV), eps, ba.m1, ba.i1, b.c_mid, st));
+    } else {
+      DFV_CUDA(cudaMemsetAsync(ar.bn_acc, 0, sizeof(double) * 2 * (size_t)b.c_mid, st));
+      DFV_TRY(dfv_dwconv_stats_fwd(dw_in, ba.wD, ar.zero_bias, ba.d_raw, ar.bn_acc, dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo,
+                                   b.pad_hi, stream));
+      DFV_TRY(dfv_bn_stats_from_sums(ar.bn_acc, b.c_mid, (double)B * (double)hw_out, eps, mom, ba.m1, ba.i1, PW(i, DFV_T_BN1_RM),
+                                     PW(i, DFV_T_BN1_RV), stream));
+    }
     DFV_TRY(dfv_bn_act_fwd(ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ba.d,
                            ar.pool_ws, dtype, B, hw_out, b.c_mid, stream));
     DFV_TRY(dfv_se_train_fwd(ar.pool_ws, dfv_rows_chunks(B, hw_out), 1.0f / (float)hw_out, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_R_B),
@@ -377,7 +405,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_cast_weight(P(i, DFV_T_PROJ_W), ba.wPt, dtype, b.c_mid, b.c_out, 1, stream));
     DFV_TRY(dfv_pw_conv_fwd(ba.d, ba.wP, ar.zero_bias, ba.gate, (int)hw_out, nullptr, ba.p_raw, dtype, B, B * hw_out, b.c_mid, b.c_out, DFV_ACT_NONE,
                             ar.fold_ws, stream));
-    DFV_TRY(dfv_bn_stats_fwd(ba.p_raw, dtype, B, hw_out, b.c_out, eps, mom, ba.m2, ba.i2, PW(i, DFV_T_BN2_RM), PW(i, DFV_T_BN2_RV), ar.bn_ws, stream));
+    DFV_TRY(bn_stats(ba.p_raw, hw_out, b.c_out, ba.m2, ba.i2, PW(i, DFV_T_BN2_RM), PW(i, DFV_T_BN2_RV)));
     const float rate = a->drop_connect_rate * (float)i / (float)n;
     const float* rowscale = nullptr;
     if (b.has_skip && rate > 0.f) {
@@ -397,7 +425,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
   DFV_TRY(dfv_cast_weight(P(-1, DFV_TG_HEAD_W), ar.wH, dtype, head_c, c_last, 0, stream));
   DFV_TRY(dfv_cast_weight(P(-1, DFV_TG_HEAD_W), ar.wHt, dtype, c_last, head_c, 1, stream));
   DFV_TRY(dfv_pw_gemm_fwd(x, ar.wH, ar.zero_bias, nullptr, 0, nullptr, ar.h_raw, dtype, B * hw_f, c_last, head_c, DFV_ACT_NONE, stream));
-  DFV_TRY(dfv_bn_stats_fwd(ar.h_raw, dtype, B, hw_f, head_c, eps, mom, ar.hm, ar.hi, PW(-1, DFV_TG_HEAD_RM), PW(-1, DFV_TG_HEAD_RV), ar.bn_ws, stream));
+  DFV_TRY(bn_stats(ar.h_raw, hw_f, head_c, ar.hm, ar.hi, PW(-1, DFV_TG_HEAD_RM), PW(-1, DFV_TG_HEAD_RV)));
   DFV_TRY(dfv_bn_act_fwd(ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, nullptr, ar.h, nullptr,
                          dtype, B, hw_f, head_c, stream));
   DFV_TRY(tap(1 + n, ar.h, (size_t)B * hw_f * head_c));
@@ -469,6 +497,19 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
   const int stem_c = topo_stem_c(), head_c = topo_head_c();
   auto P = [&](int block, int kind) -> const float* { return a->params[dfv_train_index(block, kind)]; };
   auto G = [&](int block, int kind) -> float* { return a->grads[dfv_train_index(block, kind)]; };
+  const bool frozen = a->freeze_bn != 0;
+  // freeze_bn: eval-mode BatchNorm has no batch-statistics terms in its input gradient (d raw = gamma * invstd * du)
+  // and no gamma / beta gradients: run the same two kernels with the two coefficient means zeroed in between.
+  auto bn_grad = [&](float* g_ptr) -> float* { return frozen ? nullptr : g_ptr; };
+  auto bn_apply = [&](const void* du, const void* raw, const float* mean, const float* invstd, const float* gamma, void* draw, long long M,
+                      int C) -> int {
+    if (frozen) DFV_CUDA(cudaMemsetAsync(sc.coef, 0, sizeof(float) * 2 * (size_t)C, st));
+    return dfv_bn_bwd_apply(du, raw, mean, invstd, gamma, sc.coef, draw, dtype, M, C, stream);
+  };
+  auto unit_done = [&](int unit) -> int {
+    if (a->grad_events && a->grad_events[unit]) DFV_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->grad_events[unit]), st));
+    return DFV_OK;
+  };
 
   // ---- classifier
   const float* g = a->dlogits;
@@ -509,11 +550,12 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_landmark_heatmap_bwd(a->landmarks, P(-1, DFV_TG_LM_W), ar.heat_raw, ar.heat_max, sc.dheat, G(-1, DFV_TG_LM_W), B, s.Hf, s.Wf,
                                      a->landmark_ref_size > 0.f ? a->landmark_ref_size : 224.0f, 1.5f, a->heat_group, stream));
   DFV_TRY(dfv_act_bn_bwd(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr,
-                         nullptr, sc.gE, G(-1, DFV_TG_HEAD_G), G(-1, DFV_TG_HEAD_B), sc.coef, sc.bn_ws, dtype, B, hw_f, head_c, stream));
-  DFV_TRY(dfv_bn_bwd_apply(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), sc.coef, sc.gE, dtype, B * hw_f, head_c, stream));
+                         nullptr, sc.gE, bn_grad(G(-1, DFV_TG_HEAD_G)), bn_grad(G(-1, DFV_TG_HEAD_B)), sc.coef, sc.bn_ws, dtype, B, hw_f, head_c, stream));
+  DFV_TRY(bn_apply(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), sc.gE, B * hw_f, head_c));
   DFV_TRY(dfv_pw_wgrad(sc.gE, ar.blk[n - 1].out, nullptr, 0, G(-1, DFV_TG_HEAD_W), dtype, B * hw_f, c_last, head_c, stream));
   int gc = 0;
   DFV_TRY(dfv_pw_gemm_fwd(sc.gE, ar.wHt, ar.zero_bias, nullptr, 0, nullptr, sc.gout[gc], dtype, B * hw_f, head_c, c_last, DFV_ACT_NONE, stream));
+  DFV_TRY(unit_done(0));
 
   // ---- blocks, last to first.  sc.gout[gc] = gradient wrt the block's output.
   for (int i = n - 1; i >= 0; --i) {
@@ -527,8 +569,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     const float* rowscale = (b.has_skip && rate > 0.f) ? ba.dc : nullptr;
     // bn2 (no activation); the skip branch keeps gy
     DFV_TRY(dfv_act_bn_bwd(gy, ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), P(i, DFV_T_BN2_B), DFV_ACT_NONE, nullptr, nullptr, 0.f, rowscale, nullptr,
-                           sc.gP, G(i, DFV_T_BN2_G), G(i, DFV_T_BN2_B), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_out, stream));
-    DFV_TRY(dfv_bn_bwd_apply(sc.gP, ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), sc.coef, sc.gP, dtype, B * hw_out, b.c_out, stream));
+                           sc.gP, bn_grad(G(i, DFV_T_BN2_G)), bn_grad(G(i, DFV_T_BN2_B)), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_out, stream));
+    DFV_TRY(bn_apply(sc.gP, ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), sc.gP, B * hw_out, b.c_out));
     // project conv
     DFV_TRY(dfv_pw_wgrad(sc.gP, ba.d, ba.gate, (int)hw_out, G(i, DFV_T_PROJ_W), dtype, B * hw_out, b.c_mid, b.c_out, stream));
     DFV_TRY(dfv_pw_conv_fwd(sc.gP, ba.wPt, ar.zero_bias, nullptr, (int)hw_out, nullptr, sc.gA, dtype, B, B * hw_out, b.c_out, b.c_mid, DFV_ACT_NONE,
@@ -538,8 +580,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
                        G(i, DFV_T_SE_R_B), G(i, DFV_T_SE_E_W), G(i, DFV_T_SE_E_B), sc.se_ws, B, hw_out, b.c_mid, b.se_squeeze, stream));
     // gate, swish, bn1
     DFV_TRY(dfv_act_bn_bwd(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool, 1.0f / (float)hw_out,
-                           nullptr, nullptr, sc.gA, G(i, DFV_T_BN1_G), G(i, DFV_T_BN1_B), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_mid, stream));
-    DFV_TRY(dfv_bn_bwd_apply(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), sc.coef, sc.gA, dtype, B * hw_out, b.c_mid, stream));
+                           nullptr, nullptr, sc.gA, bn_grad(G(i, DFV_T_BN1_G)), bn_grad(G(i, DFV_T_BN1_B)), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_mid, stream));
+    DFV_TRY(bn_apply(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), sc.gA, B * hw_out, b.c_mid));
     // depthwise conv
     const void* dw_in = b.has_expand ? (const void*)ba.e : x;
     const int kk = b.kernel * b.kernel;
@@ -555,8 +597,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     void* gx = sc.gout[gc ^ 1];
     if (b.has_expand) {
       DFV_TRY(dfv_act_bn_bwd(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr, nullptr,
-                             sc.gE, G(i, DFV_T_BN0_G), G(i, DFV_T_BN0_B), sc.coef, sc.bn_ws, dtype, B, hw_in, b.c_mid, stream));
-      DFV_TRY(dfv_bn_bwd_apply(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), sc.coef, sc.gE, dtype, B * hw_in, b.c_mid, stream));
+                             sc.gE, bn_grad(G(i, DFV_T_BN0_G)), bn_grad(G(i, DFV_T_BN0_B)), sc.coef, sc.bn_ws, dtype, B, hw_in, b.c_mid, stream));
+      DFV_TRY(bn_apply(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), sc.gE, B * hw_in, b.c_mid));
       DFV_TRY(dfv_pw_wgrad(sc.gE, x, nullptr, 0, G(i, DFV_T_EXPAND_W), dtype, B * hw_in, b.c_in, b.c_mid, stream));
       DFV_TRY(dfv_pw_conv_fwd(sc.gE, ba.wEt, ar.zero_bias, nullptr, (int)hw_in, b.has_skip ? gy : nullptr, gx, dtype, B, B * hw_in, b.c_mid, b.c_in,
                               DFV_ACT_NONE, sc.fold_ws, stream));
@@ -566,13 +608,15 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
                              B, hw_in, b.c_in, stream));
     }
     gc ^= 1;
+    DFV_TRY(unit_done(1 + (n - 1 - i)));
   }
 
   // ---- stem
   DFV_TRY(dfv_act_bn_bwd(sc.gout[gc], ar.s_raw, ar.sm, ar.si, P(-1, DFV_TG_STEM_G), P(-1, DFV_TG_STEM_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr,
-                         nullptr, sc.gout[gc], G(-1, DFV_TG_STEM_G), G(-1, DFV_TG_STEM_B), sc.coef, sc.bn_ws, dtype, B, (long long)s.Hs * s.Ws, stem_c, stream));
-  DFV_TRY(dfv_bn_bwd_apply(sc.gout[gc], ar.s_raw, ar.sm, ar.si, P(-1, DFV_TG_STEM_G), sc.coef, sc.gout[gc], dtype, (long long)B * s.Hs * s.Ws, stem_c, stream));
+                         nullptr, sc.gout[gc], bn_grad(G(-1, DFV_TG_STEM_G)), bn_grad(G(-1, DFV_TG_STEM_B)), sc.coef, sc.bn_ws, dtype, B, (long long)s.Hs * s.Ws, stem_c, stream));
+  DFV_TRY(bn_apply(sc.gout[gc], ar.s_raw, ar.sm, ar.si, P(-1, DFV_TG_STEM_G), sc.gout[gc], (long long)B * s.Hs * s.Ws, stem_c));
   DFV_TRY(dfv_stem_wgrad(sc.gout[gc], a->images_nchw, G(-1, DFV_TG_STEM_W), dtype, B, a->H, a->W, stream));
+  DFV_TRY(unit_done(DFV_GRAD_UNITS - 1));
   return DFV_OK;
 }
 

@@ -2,8 +2,13 @@
 
 The forward is ~140 kernel launches of fixed shapes; a replay removes their launch gaps (14.10 -> 13.92 ms per batch of
 256 on a B200, logits bit-identical) and, more importantly for a serving loop, takes the host out of the loop: one launch
-per batch.  Inputs are copied into the graph's static buffers; the returned tensors are the graph's static outputs and
-stay valid until the next call.
+per batch.  Inputs are copied into the graph's static buffers (or written there directly: `gi.images` / `gi.landmarks`
+are the H2D targets of a serving loop); the returned tensors are the graph's static outputs and stay valid until the
+next call.
+
+The graph holds raw device pointers, so this object keeps alive everything it captured -- the model's inference
+workspace for this shape (pinned: eager calls at other shapes no longer evict it) and the packed weight blob -- and
+re-captures when the model's weights change (load_state_dict, an optimizer step, a train-mode forward).
 """
 import torch
 
@@ -14,15 +19,40 @@ class GraphedInference:
         self.model, self.return_features = model, return_features
         self.images = images.detach().clone()
         self.landmarks = None if landmarks is None else landmarks.detach().clone()
-        side = torch.cuda.Stream(device=images.device)
-        side.wait_stream(torch.cuda.current_stream(images.device))
-        with torch.cuda.stream(side), torch.no_grad():          # warm-up off the capture stream (allocator, one-off setup)
+        self._capture()
+
+    def _capture(self):
+        from . import ops
+        model, dev = self.model, self.images.device
+        if self.images.dtype == torch.uint8:
+            B, H, W = self.images.shape[0], self.images.shape[1], self.images.shape[2]
+        else:
+            B, H, W = self.images.shape[0], self.images.shape[2], self.images.shape[3]
+        self._ws_key = (ops.dtype_code(model.compute_dtype), B, H, W, str(dev))
+        model._pinned_ws.add(self._ws_key)                     # _ws() never evicts a pinned shape
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():          # warm-up off the capture stream (allocator, weight packing)
             for _ in range(2):
-                model(self.images, self.landmarks, return_features=return_features)
-        torch.cuda.current_stream(images.device).wait_stream(side)
+                model(self.images, self.landmarks, return_features=self.return_features)
+        torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
-            self.outputs = model(self.images, self.landmarks, return_features=return_features)
+            self.outputs = model(self.images, self.landmarks, return_features=self.return_features)
+        # what the captured kernels read and write: owned here for the lifetime of the graph
+        self._version = model._version_key()
+        self._dtype = model.compute_dtype
+        self._keep = (model._workspace[self._ws_key], model._packed[(model.compute_dtype, str(dev))])
+        self._blob = self._keep[1].blob
+
+    def replay(self):
+        """Replay on the static buffers (fill `self.images` / `self.landmarks` first)."""
+        m = self.model
+        if m._version_key() != self._version or m.compute_dtype != self._dtype or m.training:
+            assert not m.training, "the captured forward is the eval forward"
+            self._capture()                                     # weights changed: fold again and capture again
+        self.graph.replay()
+        return self.outputs
 
     def __call__(self, images, landmarks=None):
         if images.shape != self.images.shape or images.dtype != self.images.dtype:
@@ -32,5 +62,4 @@ class GraphedInference:
         self.images.copy_(images, non_blocking=True)
         if landmarks is not None:
             self.landmarks.copy_(landmarks, non_blocking=True)
-        self.graph.replay()
-        return self.outputs
+        return self.replay()

@@ -22,10 +22,11 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .parallel import allreduce_gradients, flat_offsets
+from .parallel import BucketedAllReduce, flat_offsets
 from ._lib import check, lib
 
 BN_EPS, BN_MOM = 1e-3, 0.01   # efficientnet-pytorch global params for B4
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)   # src/data/dataset.py:59-60, task.ipynb:364-365
 
 
 def _holder(cls):
@@ -104,6 +105,36 @@ class EfficientNetB4Backbone(nn.Module):
             self._freeze_bn_layers()
         return self
 
+    def _model(self):
+        owner = getattr(self, "_owner", None)
+        m = owner() if owner is not None else None
+        if m is None:
+            raise RuntimeError("EfficientNetB4Backbone is a parameter holder; use it through DeepfakeDetectionModel")
+        return m
+
+    def forward(self, x, return_intermediate: bool = False):
+        """-> (features (B, 1792), {'reduction_2' | 'reduction_4' | 'reduction_5': NCHW maps of blocks 5 / 10 / 21} | None)
+        (efficientnet.py:122-151): backbone maps -> global average pool -> dropout, no attention.  Computed by the owning
+        model's libdfvit forward with the attention stage switched off."""
+        m = self._model()
+        if m.training:
+            feats, taps = m._train_features(x, None, attention=False, want_taps=return_intermediate)
+        else:
+            _, feats, _, taps = m._infer(x, None, taps=return_intermediate, attention=False)
+        inter = None
+        if return_intermediate:
+            inter = {name: taps[1 + blk].permute(0, 3, 1, 2).float()
+                     for name, blk in (("reduction_2", 5), ("reduction_4", 10), ("reduction_5", 21))}
+            self.intermediate_features = inter
+        return feats, inter
+
+    def get_feature_maps(self, x):
+        """(B, 1792, h, w) final feature maps (efficientnet.py:153-163), eval mode."""
+        m = self._model()
+        assert not m.training, "get_feature_maps is the eval-mode side API"
+        _, _, _, taps = m._infer(x, None, taps=True, attention=False)
+        return taps[-1].permute(0, 3, 1, 2).float()
+
 
 class LandmarkAttention(nn.Module):
     def __init__(self, feature_size=(7, 7), sigma=1.5, learnable=True):
@@ -180,13 +211,16 @@ class DeepfakeFeatureExtractor(nn.Module):
         """-> (features (B, 1792), attention_map (B, 1, 7, 7) | None)  (feature_extractor.py:74-117; the reference
         renders the returned map on a hard-coded 7x7 grid whatever the real feature size is, :100-103)."""
         m = self._model()
-        assert not m.training, "feature_extractor(...) is the eval-mode side API; train through DeepfakeDetectionModel.forward"
-        _, feats, _, _ = m._infer(images, landmarks)
+        if m.training:      # train mode: the same autograd node as model.forward, without the classifier's logits
+            feats, _ = m._train_features(images, landmarks)
+        else:
+            _, feats, _, _ = m._infer(images, landmarks)
         amap = None
         if return_attention and landmarks is not None and self.use_attention and self.attention is not None \
                 and getattr(self.attention, "use_landmark", False):
-            amap = self.attention.landmark_attn._create_attention_map(landmarks, (7, 7), images.device,
-                                                                      group=int(m.landmark_max_group))
+            with torch.no_grad():
+                amap = self.attention.landmark_attn._create_attention_map(landmarks, (7, 7), images.device,
+                                                                          group=int(m.landmark_max_group))
         return feats, amap
 
     def extract_multi_scale_features(self, images, landmarks=None):
@@ -205,39 +239,29 @@ class DeepfakeFeatureExtractor(nn.Module):
         return ops.l2_normalize(feats.contiguous()) if normalize else feats
 
 
-class _TrainState:
-    """What one train-mode forward leaves behind for its backward (arena = saved activations)."""
-
-    def __init__(self):
-        self.arena = None
-        self.key = None
-        self.in_flight = False
-
-
 class _TrainFn(torch.autograd.Function):
     """forward = dfv_train_fwd, backward = dfv_train_bwd (+ the data-parallel all-reduce)."""
 
     @staticmethod
-    def forward(ctx, model, images, landmarks, *params):
-        logits, feats, run = model._train_fwd(images, landmarks)
+    def forward(ctx, model, images, landmarks, opts, *params):
+        logits, feats, run = model._train_fwd(images, landmarks, **opts)
         ctx.model, ctx.run = model, run
-        ctx.n_params = len(params)
         return logits, feats
 
     @staticmethod
     def backward(ctx, dlogits, dfeats):
         grads = ctx.model._train_bwd(ctx.run, dlogits, dfeats)
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 class _Packed:
-    """Folded, device-resident weights for one (dtype, device) pair."""
+    """Folded, device-resident weights for one (dtype, device) pair (written by dfv_pack_weights)."""
 
     def __init__(self):
         self.key = None
         self.blob = None
         self.head: Optional[ops.HeadPack] = None
-        self.lm_w = self.ca_w1 = self.ca_w2_t = self.sa_w = None
+        self.ca_w2_t = None
 
 
 class DeepfakeDetectionModel(nn.Module):
@@ -250,7 +274,9 @@ class DeepfakeDetectionModel(nn.Module):
         if feature_extractor_config is None:   # top-level `pretrained` ignored otherwise (:210-218)
             feature_extractor_config = {"pretrained": pretrained, "use_attention": True}
         self.feature_extractor = DeepfakeFeatureExtractor(**feature_extractor_config)
-        object.__setattr__(self.feature_extractor, "_owner", weakref.ref(self))   # side APIs run this model's forward
+        # the side APIs of the parameter-holder sub-modules run this model's forward
+        object.__setattr__(self.feature_extractor, "_owner", weakref.ref(self))
+        object.__setattr__(self.feature_extractor.backbone, "_owner", weakref.ref(self))
         layers, d = [], self.feature_extractor.feature_dim
         for h in classifier_hidden_dims:
             layers += [_Linear(d, h), _BN1d(h), nn.ReLU(inplace=True), nn.Dropout(dropout_rate)]
@@ -262,92 +288,86 @@ class DeepfakeDetectionModel(nn.Module):
         self.compute_dtype = torch.bfloat16     # or torch.float32 (parity mode)
         self.landmark_max_group = 0             # images per heat-map max group; 0 = whole call (reference)
         self.ddp_allreduce = True               # average gradients over torch.distributed ranks inside backward
+        self.ddp_bucket_floats = 4 << 20        # ~16 MB gradient buckets, all-reduced while the backward still runs
+        # uint8 (B, H, W, 3) RGB crops are normalised inside the stem: (u8 / 255 - mean) / std (dataset.py:95-98)
+        self.input_mean, self.input_std = IMAGENET_MEAN, IMAGENET_STD
         self._packed: Dict[Tuple, _Packed] = {}
         self._workspace: Dict[Tuple, torch.Tensor] = {}
-        self._train_state = _TrainState()
+        self._pinned_ws = set()                 # workspace keys a live CUDA graph replays from: never evicted
+        self._arena_pool: Dict[Tuple, List[torch.Tensor]] = {}
         self._train_scratch = None
+        self._flat_grad = None
+        self._reducer: Optional[BucketedAllReduce] = None
+        self._epoch = 0                         # bumped by everything that rewrites weights behind autograd's back
+        self._state_list = None
+        self._bn_list = None
         self._want_taps = False                 # debug: keep NHWC copies of every stage output of a train forward
         self._last_taps = None
         self._last_flat_grad = None
 
     # ------------------------------------------------------------------ packing
-    def _version_key(self):
-        return sum(t._version for t in self.state_dict(keep_vars=True).values())
+    def invalidate_packed(self):
+        """Tell the model its weights changed through a path torch's version counters do not see (`p.data` writes, raw
+        pointer writes by a fused optimizer, a broadcast into `.data`).  FusedAdamW.step, parallel.broadcast_parameters
+        and the train-mode forward (running statistics) call it."""
+        self._epoch += 1
 
-    @staticmethod
-    def _fold(bn):
-        scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
-        return scale, bn.bias.float() - bn.running_mean.float() * scale
+    def _version_key(self):
+        if self._state_list is None:
+            self._state_list = list(self.parameters()) + list(self.buffers())
+        return (self._epoch, sum(t._version for t in self._state_list), sum(t.data_ptr() & 0xFFFFFF for t in self._state_list[:4]))
+
+    def _apply(self, fn, *a, **k):      # .to() / .cuda() / .float(): new storages
+        self._state_list = None
+        self._epoch += 1
+        return super()._apply(fn, *a, **k)
+
+    def _head_spec(self):
+        dims, p_drop, i = [self.feature_extractor.feature_dim], 0.0, 0
+        mods = list(self.classifier)
+        while i < len(mods):
+            dims.append(mods[i].out_features)
+            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
+                p_drop = mods[i + 3].p
+                i += 4
+            else:
+                i += 1
+        return dims, p_drop
 
     @torch.no_grad()
     def _pack(self, dtype: torch.dtype, device) -> _Packed:
+        """Fold BatchNorm and lay the weights out for the inference kernels -- dfv_pack_weights, a handful of launches
+        over the module's own parameter storage (no host-framework arithmetic)."""
         key = (dtype, str(device))
         pk = self._packed.setdefault(key, _Packed())
         ver = self._version_key()
         if pk.key == ver:
             return pk
         code = ops.dtype_code(dtype)
-        blob = torch.zeros(lib.dfv_blob_bytes(code), dtype=torch.uint8, device=device)
-
-        def put(block, kind, t, as_dtype=torch.float32):
-            off, n = _lib.blob_slot(code, block, kind)
-            t = t.to(device=device, dtype=as_dtype).contiguous()
-            assert t.numel() == n, (block, kind, t.shape, n)
-            blob[off:off + n * t.element_size()].copy_(t.view(-1).view(torch.uint8))
-
-        bb = self.feature_extractor.backbone.backbone
-        s, b = self._fold(bb._bn0)
-        put(-1, _lib.W_STEM, bb._conv_stem.weight.float().permute(2, 3, 1, 0) * s)     # [kh][kw][ci][co]
-        put(-1, _lib.W_STEM_BIAS, b)
-        for i, blk in enumerate(bb._blocks):
-            info = blk.info
-            cmid = info["c_mid"]
-            if info["has_expand"]:
-                s, b = self._fold(blk._bn0)
-                put(i, _lib.W_EXPAND, blk._expand_conv.weight.float().view(cmid, -1) * s[:, None], dtype)
-                put(i, _lib.W_EXPAND_BIAS, b)
-            s, b = self._fold(blk._bn1)
-            kk = info["kernel"] ** 2
-            put(i, _lib.W_DW, (blk._depthwise_conv.weight.float().view(cmid, kk) * s[:, None]).t())   # [k*k][C]
-            put(i, _lib.W_DW_BIAS, b)
-            put(i, _lib.W_SE_REDUCE, blk._se_reduce.weight.float().view(-1, cmid))                   # [sq][C]
-            put(i, _lib.W_SE_REDUCE_BIAS, blk._se_reduce.bias.float())
-            put(i, _lib.W_SE_EXPAND, blk._se_expand.weight.float().view(cmid, -1).t())               # [sq][C]
-            put(i, _lib.W_SE_EXPAND_BIAS, blk._se_expand.bias.float())
-            s, b = self._fold(blk._bn2)
-            put(i, _lib.W_PROJECT, blk._project_conv.weight.float().view(info["c_out"], cmid) * s[:, None], dtype)
-            put(i, _lib.W_PROJECT_BIAS, b)
-        s, b = self._fold(bb._bn1)
-        put(-1, _lib.W_HEAD, bb._conv_head.weight.float().view(bb.head_channels, -1) * s[:, None], dtype)
-        put(-1, _lib.W_HEAD_BIAS, b)
-        pk.blob = blob
-
-        att = self.feature_extractor.attention
+        T, dims, _ = self._train_tensors()
+        for t in T:
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "parameters must be contiguous fp32 CUDA tensors"
         f32 = dict(device=device, dtype=torch.float32)
-        if att is not None and att.use_landmark:
-            pk.lm_w = att.landmark_attn.attention_weights.detach().to(**f32).contiguous()
-        if att is not None and att.use_channel:
-            pk.ca_w1 = att.channel_attn.fc[0].weight.detach().to(**f32).contiguous()
-            pk.ca_w2_t = att.channel_attn.fc[2].weight.detach().to(**f32).t().contiguous()
-        if att is not None and att.use_spatial:
-            pk.sa_w = att.spatial_attn.conv.weight.detach().to(**f32).reshape(-1).contiguous()
-
-        w_t, bs = [], []
-        mods = list(self.classifier)
-        i = 0
-        while i < len(mods):
-            lin = mods[i]
-            w, bias = lin.weight.float(), lin.bias.float()
-            if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
-                s, sh = self._fold(mods[i + 1])
-                w, bias = w * s[:, None], bias * s + sh
-                i += 4          # Linear, BN, ReLU, Dropout
-            else:
-                i += 1
-            w_t.append(w.t().to(**f32).contiguous())
-            bs.append(bias.to(**f32).contiguous())
-        pk.head = ops.HeadPack(w_t, bs)
-        pk.key = ver
+        blob = torch.empty(lib.dfv_blob_bytes(code), dtype=torch.uint8, device=device)
+        w_t = [torch.empty(dims[l], dims[l + 1], **f32) for l in range(len(dims) - 1)]
+        bs = [torch.empty(dims[l + 1], **f32) for l in range(len(dims) - 1)]
+        head = ops.HeadPack(w_t, bs)
+        att = self.feature_extractor.attention
+        use_c = bool(self.feature_extractor.use_attention and att is not None and att.use_channel)
+        ca_hidden = att.channel_attn.fc[0].out_features if use_c else 0
+        ca_w2_t = torch.empty(ca_hidden, self.feature_extractor.feature_dim, **f32) if use_c else None
+        bn1d = [m for m in self.classifier if isinstance(m, nn.BatchNorm1d)]
+        a = _lib.PackArgs()
+        a.dtype, a.bn_eps = code, self.feature_extractor.backbone.backbone._bn0.eps
+        a.cls_bn_eps = bn1d[0].eps if bn1d else 1e-5
+        a.params = (C.c_void_p * len(T))(*[t.data_ptr() if t is not None else None for t in T])
+        a.blob = blob.data_ptr()
+        a.head_layers, a.head_dims = head.n, C.cast(head.dims, C.POINTER(C.c_int32))
+        a.head_w_t, a.head_b = head.wp, head.bp
+        a.ca_hidden, a.ca_w2_t = ca_hidden, (ca_w2_t.data_ptr() if use_c else None)
+        check(lib.dfv_pack_weights(C.byref(a), torch.cuda.current_stream().cuda_stream))
+        pk.blob, pk.head, pk.ca_w2_t, pk.key = blob, head, ca_w2_t, ver
         return pk
 
     def _ws(self, code, B, H, W, device):
@@ -357,27 +377,52 @@ class DeepfakeDetectionModel(nn.Module):
             n = lib.dfv_infer_workspace_bytes(code, B, H, W)
             if n == 0:
                 check(-1)
-            self._workspace = {key: torch.empty(n, dtype=torch.uint8, device=device)}   # keep one shape resident
-            ws = self._workspace[key]
+            # keep one eager shape resident, plus every shape a live CUDA graph was captured on
+            self._workspace = {k: v for k, v in self._workspace.items() if k in self._pinned_ws}
+            ws = self._workspace[key] = torch.empty(n, dtype=torch.uint8, device=device)
         return ws
 
-    # ------------------------------------------------------------------ inference
-    @torch.no_grad()
-    def _infer(self, images, landmarks, want_heat=False, taps=False):
+    def _images(self, images):
+        """-> (fp32 NCHW tensor | None, uint8 HWC tensor | None, B, H, W)."""
         if not images.is_cuda:
             raise RuntimeError("deepfake_vit_b200 runs on sm_100 CUDA devices only (no CPU path); move the "
                                "model and inputs to cuda")
         check(lib.dfv_device_check())
+        if images.dtype == torch.uint8:
+            assert images.dim() == 4 and images.shape[3] == 3, "uint8 images must be (B, H, W, 3) RGB crops"
+            u8 = images.detach().contiguous()
+            return None, u8, u8.shape[0], u8.shape[1], u8.shape[2]
+        x = images.detach().to(torch.float32).contiguous()
+        assert x.dim() == 4 and x.shape[1] == 3, "images must be (B, 3, H, W)"
+        return x, None, x.shape[0], x.shape[2], x.shape[3]
+
+    def _norm6(self):
+        return (C.c_float * 6)(*self.input_mean, *self.input_std)
+
+    def _check_modes(self):
+        """Only the top-level mode selects the path; a sub-module left in the other mode would be silently ignored."""
+        if self._bn_list is None:
+            inside = {id(x) for x in self.feature_extractor.backbone.backbone.modules()}
+            self._bn_list = [(n, m, id(m) in inside) for n, m in self.named_modules() if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d))]
+        frozen = self.feature_extractor.backbone.freeze_bn
+        for name, m, in_backbone in self._bn_list:
+            if m.training != self.training:
+                if frozen and self.training and in_backbone:
+                    continue        # freeze_bn: backbone BatchNorm stays in eval mode by construction
+                raise RuntimeError(f"{name}.training = {m.training} but the model is in {'train' if self.training else 'eval'} "
+                                   "mode: per-sub-module modes are not supported (use freeze_bn=True to freeze the backbone BatchNorm)")
+
+    # ------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def _infer(self, images, landmarks, want_heat=False, taps=False, attention=True):
+        x, u8, B, H, W = self._images(images)
         dev = images.device
-        images = images.detach().to(torch.float32).contiguous()
-        B, Cin, H, W = images.shape
-        assert Cin == 3, "images must be (B, 3, H, W)"
         dtype = self.compute_dtype
         code = ops.dtype_code(dtype)
         pk = self._pack(dtype, dev)
         ws = self._ws(code, B, H, W, dev)
         att = self.feature_extractor.attention
-        use_att = bool(self.feature_extractor.use_attention and att is not None)
+        use_att = bool(attention and self.feature_extractor.use_attention and att is not None)
         ho, wo = C.c_int(), C.c_int()
         check(lib.dfv_b4_output_hw(H, W, C.byref(ho), C.byref(wo)))
         Hf, Wf = ho.value, wo.value
@@ -403,13 +448,19 @@ class DeepfakeDetectionModel(nn.Module):
         a.heat_group = int(self.landmark_max_group)
         a.landmark_ref_size = 224.0
         a.blob = pk.blob.data_ptr()
-        a.images_nchw = images.data_ptr()
+        a.images_nchw = x.data_ptr() if x is not None else None
+        if u8 is not None:
+            a.images_u8, a.u8_norm = u8.data_ptr(), self._norm6()
         a.landmarks = lm.data_ptr() if lm is not None else None
-        a.lm_weights = pk.lm_w.data_ptr() if pk.lm_w is not None else None
-        a.ca_w1 = pk.ca_w1.data_ptr() if pk.ca_w1 is not None else None
-        a.ca_w2_t = pk.ca_w2_t.data_ptr() if pk.ca_w2_t is not None else None
-        a.ca_hidden = pk.ca_w1.shape[0] if pk.ca_w1 is not None else 0
-        a.sa_w = pk.sa_w.data_ptr() if pk.sa_w is not None else None
+        # small attention tensors are read from the parameters themselves (fp32, contiguous, on the device)
+        if use_att and att.use_landmark:
+            a.lm_weights = att.landmark_attn.attention_weights.data_ptr()
+        if use_att and att.use_channel:
+            a.ca_w1 = att.channel_attn.fc[0].weight.data_ptr()
+            a.ca_w2_t = pk.ca_w2_t.data_ptr()
+            a.ca_hidden = att.channel_attn.fc[0].out_features
+        if use_att and att.use_spatial:
+            a.sa_w = att.spatial_attn.conv.weight.data_ptr()
         a.head_w_t, a.head_b = pk.head.wp, pk.head.bp
         a.head_dims, a.head_layers = C.cast(pk.head.dims, C.POINTER(C.c_int32)), pk.head.n
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -453,26 +504,23 @@ class DeepfakeDetectionModel(nn.Module):
             if att.use_channel:
                 T[ix(-1, _lib.TG_CA_W1)] = att.channel_attn.fc[0].weight
                 T[ix(-1, _lib.TG_CA_W2)] = att.channel_attn.fc[2].weight
-        mods, layer, dims, i = list(self.classifier), 0, [self.feature_extractor.feature_dim], 0
-        p_drop = 0.0
+        mods, layer, i = list(self.classifier), 0, 0
         while i < len(mods):
             lin = mods[i]
             T[cx(layer, 0)], T[cx(layer, 1)] = lin.weight, lin.bias
-            dims.append(lin.out_features)
             if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d):
                 b1 = mods[i + 1]
                 T[cx(layer, 2)], T[cx(layer, 3)], T[cx(layer, 4)], T[cx(layer, 5)] = b1.weight, b1.bias, b1.running_mean, b1.running_var
-                p_drop = mods[i + 3].p
                 i += 4
             else:
                 i += 1
             layer += 1
+        dims, p_drop = self._head_spec()
         return T, dims, p_drop
 
-    def _train_args(self, images, landmarks, T, dims, p_drop):
-        dev = images.device
+    def _train_args(self, images, landmarks, T, dims, p_drop, attention=True):
         att = self.feature_extractor.attention
-        use_att = bool(self.feature_extractor.use_attention and att is not None)
+        use_att = bool(attention and self.feature_extractor.use_attention and att is not None)
         a = _lib.TrainArgs()
         a.dtype = ops.dtype_code(self.compute_dtype)
         a.B, _, a.H, a.W = images.shape
@@ -489,6 +537,7 @@ class DeepfakeDetectionModel(nn.Module):
         a.drop_connect_rate = float(bb.drop_connect_rate)
         a.feat_dropout = float(self.feature_extractor.backbone.dropout.p)
         a.cls_dropout = float(p_drop)
+        a.freeze_bn = int(bool(self.feature_extractor.backbone.freeze_bn))
         for t in T:
             if t is not None:
                 assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "parameters must be contiguous fp32 CUDA tensors"
@@ -500,65 +549,78 @@ class DeepfakeDetectionModel(nn.Module):
         a.head_dims, a.head_layers = hd, len(dims) - 1
         return a, hd
 
-    def _train_fwd(self, images, landmarks):
-        if not images.is_cuda:
-            raise RuntimeError("deepfake_vit_b200 runs on sm_100 CUDA devices only (no CPU path)")
-        if self.feature_extractor.backbone.freeze_bn:
-            raise NotImplementedError("freeze_bn=True training (eval-mode backbone BatchNorm inside train mode) is not built")
-        check(lib.dfv_device_check())
+    def _train_fwd(self, images, landmarks, needs_bwd=True, attention=True, want_taps=False):
+        x, u8, B, H, W = self._images(images)
         dev = images.device
-        images = images.detach().to(torch.float32).contiguous()
-        B, Cin, H, W = images.shape
-        assert Cin == 3, "images must be (B, 3, H, W)"
+        if u8 is not None:      # the stem's weight gradient reads the fp32 image: normalise once, same arithmetic as the fused stem
+            x = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
+            check(lib.dfv_u8_to_nchw_f32(u8.data_ptr(), self._norm6(), x.data_ptr(), B, H, W, torch.cuda.current_stream().cuda_stream))
         att = self.feature_extractor.attention
         lm = None
-        if landmarks is not None and self.feature_extractor.use_attention and att is not None and att.use_landmark:
+        if landmarks is not None and attention and self.feature_extractor.use_attention and att is not None and att.use_landmark:
             lm = landmarks.detach().to(device=dev, dtype=torch.float32).contiguous()
             assert lm.shape == (B, 5, 2), "landmarks must be (B, 5, 2)"
         T, dims, p_drop = self._train_tensors()
-        a, hd = self._train_args(images, lm, T, dims, p_drop)
-        key = (a.dtype, B, H, W, str(dev))
-        st = self._train_state
-        if st.in_flight or st.key != key or st.arena is None:
+        a, hd = self._train_args(x, lm, T, dims, p_drop, attention)
+        key = (a.dtype, B, H, W, str(dev), a.ca_hidden)
+        # every forward that will be differentiated OWNS its arena until its backward has run (two forwards before a
+        # backward, siamese losses); finished arenas go back to a per-shape pool
+        pool = self._arena_pool.setdefault(key, [])
+        if pool:
+            arena = pool.pop()
+        else:
             n = lib.dfv_train_arena_bytes(a.dtype, B, H, W, hd, a.head_layers, a.ca_hidden)
             if n == 0:
                 check(-1)
-            if st.in_flight:          # an earlier forward still awaits its backward: do not reuse its arena
-                st = _TrainState()
-            else:
-                self._train_state = st
-            st.arena, st.key = torch.empty(n, dtype=torch.uint8, device=dev), key
-        st.in_flight = torch.is_grad_enabled()
-        a.arena, a.arena_bytes = st.arena.data_ptr(), st.arena.numel()
+            for k in [k for k in self._arena_pool if k != key]:      # another shape: drop its idle arenas
+                del self._arena_pool[k]
+            pool = self._arena_pool.setdefault(key, [])
+            arena = torch.empty(n, dtype=torch.uint8, device=dev)
+        a.arena, a.arena_bytes = arena.data_ptr(), arena.numel()
         logits = torch.empty(B, dims[-1], device=dev, dtype=torch.float32)
         feats = torch.empty(B, dims[0], device=dev, dtype=torch.float32)
         a.logits, a.features = logits.data_ptr(), feats.data_ptr()
-        a.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        # dropout / drop-connect masks are a function of (seed, position); the seed comes from torch's CPU generator
+        # (so torch.manual_seed reproduces a run) mixed with the data-parallel rank (ranks draw different masks)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        a.seed = (seed ^ (_rank() * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
         taps = None
-        if self._want_taps:
+        if self._want_taps or want_taps:
             taps = self._tap_tensors(B, H, W, dev, self.compute_dtype)
             a.taps = (C.c_void_p * len(taps))(*[t.data_ptr() for t in taps])
         check(lib.dfv_train_fwd(C.byref(a), torch.cuda.current_stream().cuda_stream))
-        nbt = [m.num_batches_tracked for m in self.modules() if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d))]
+        frozen = self.feature_extractor.backbone.freeze_bn
+        bb = self.feature_extractor.backbone.backbone
+        nbt = [m.num_batches_tracked for m in self.modules() if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)) and m.training]
+        if not frozen:
+            assert len(nbt) > 0
         torch._foreach_add_(nbt, 1)
-        run = dict(args=a, keep=(hd, images, lm, T, st, feats), taps=taps, state=st)
+        self.invalidate_packed()          # running statistics were updated through raw pointers
+        run = dict(args=a, keep=(hd, x, lm, T, feats), taps=taps, arena=arena, pool_key=key)
+        if not needs_bwd:                 # nothing will come back for this arena: stream order makes it reusable at once
+            pool.append(arena)
+            run["arena"] = None
         self._last_taps = taps
         return logits, feats, run
 
-    def _train_bwd(self, run, dlogits, dfeats):
-        a, st = run["args"], run["state"]
-        hd, images, lm, T, _, feats = run["keep"]
-        dev = images.device
+    def _flat_layout(self):
         params = [p for _, p in self.named_parameters()]
         starts, total = flat_offsets([p.numel() for p in params])
+        return params, starts, total
+
+    def _train_bwd(self, run, dlogits, dfeats):
+        a = run["args"]
+        if run["arena"] is None:
+            raise RuntimeError("backward through a train-mode forward that ran under torch.no_grad()")
+        hd, images, lm, T, feats = run["keep"]
+        dev = images.device
+        params, starts, total = self._flat_layout()
         offs = {id(p): o for p, o in zip(params, starts)}
+        # ONE flat fp32 gradient buffer per step (the all-reduce and the fused optimizer read it in place).  A fresh
+        # zeroed allocation per backward: autograd hands these views out as .grad, so the previous step's buffer
+        # may still be referenced by the caller (gradient accumulation adds into it).
         flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        gp = []
-        for t in T:
-            if t is not None and id(t) in offs:
-                gp.append(flat.data_ptr() + 4 * offs[id(t)])
-            else:
-                gp.append(None)
+        gp = [flat.data_ptr() + 4 * offs[id(t)] if (t is not None and id(t) in offs) else None for t in T]
         a.grads = (C.c_void_p * len(T))(*gp)
         key = (a.dtype, a.B, a.H, a.W, str(dev))
         if self._train_scratch is None or self._train_scratch[0] != key:
@@ -572,12 +634,52 @@ class DeepfakeDetectionModel(nn.Module):
         df = dfeats.detach().to(torch.float32).contiguous() if dfeats is not None else None
         a.dlogits = dl.data_ptr()
         a.dfeatures = df.data_ptr() if df is not None else None
+        reducer = None
+        if self.ddp_allreduce and BucketedAllReduce.active():
+            if self._reducer is None or self._reducer.total != total or self._reducer.bucket_floats != self.ddp_bucket_floats:
+                self._reducer = BucketedAllReduce(self._unit_ranges(params, starts, total), total, self.ddp_bucket_floats, dev)
+            reducer = self._reducer
+            a.grad_events = reducer.event_table()
         check(lib.dfv_train_bwd(C.byref(a), torch.cuda.current_stream().cuda_stream))
-        st.in_flight = False
-        if self.ddp_allreduce:
-            allreduce_gradients(flat)
+        if reducer is not None:
+            reducer.reduce(flat)          # bucket by bucket on a side stream, behind the events dfv_train_bwd recorded
+        self._arena_pool.setdefault(run["pool_key"], []).append(run["arena"])
+        run["arena"] = None
+        for p, o in zip(params, starts):      # parameters the caller froze: no gradient leaves this function for them
+            if not p.requires_grad:
+                flat[o:o + p.numel()].zero_()
         self._last_flat_grad = flat
         return [flat[offs[id(p)]:offs[id(p)] + p.numel()].view_as(p) if p.requires_grad else None for p in params]
+
+    def _unit_ranges(self, params, starts, total):
+        """Flat-buffer range [lo, hi) of every gradient unit of dfv_train_bwd, in completion order (include/dfvit.h
+        grad_events): unit 0 = head conv + attention + classifier, unit 1 + j = block 31 - j, unit 33 = stem."""
+        names = [n for n, _ in self.named_parameters()]
+        first = {}
+        for n, o in zip(names, starts):
+            if "._blocks." in n:
+                blk = int(n.split("._blocks.")[1].split(".")[0])
+                first.setdefault(("block", blk), o)
+            elif "_conv_head" in n:
+                first.setdefault(("head",), o)
+        nblk = lib.dfv_b4_num_blocks()
+        bounds = [first[("block", i)] for i in range(nblk)] + [first[("head",)]]
+        units = [(bounds[nblk], total)]
+        for j in range(nblk):
+            i = nblk - 1 - j
+            units.append((bounds[i], bounds[i + 1]))
+        units.append((0, bounds[0]))
+        assert len(units) == _lib.GRAD_UNITS
+        return units
+
+    def _train_features(self, images, landmarks, attention=True, want_taps=False):
+        """Train-mode features through the same autograd node as forward() (used by the sub-modules' side APIs)."""
+        self._check_modes()
+        needs_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        params = [p for _, p in self.named_parameters()]
+        opts = dict(needs_bwd=needs_bwd, attention=attention, want_taps=want_taps)
+        _, feats = _TrainFn.apply(self, images, landmarks, opts, *params)
+        return feats, self._last_taps
 
     def _tap_tensors(self, B, H, W, dev, dtype):
         bb = self.feature_extractor.backbone.backbone
@@ -594,16 +696,22 @@ class DeepfakeDetectionModel(nn.Module):
     # ------------------------------------------------------------------ reference API
     def forward(self, images: torch.Tensor, landmarks: Optional[torch.Tensor] = None,
                 return_features: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """images: (B, 3, H, W) fp32 normalised crops (the reference's contract, src/data/dataset.py:82-116) or
+        (B, H, W, 3) uint8 RGB crops, normalised inside the stem kernel."""
+        self._check_modes()
         if self.training:
+            # grad mode is read HERE: inside autograd.Function.forward it is always off
+            needs_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
             params = [p for _, p in self.named_parameters()]
-            logits, feats = _TrainFn.apply(self, images, landmarks, *params)
+            logits, feats = _TrainFn.apply(self, images, landmarks, dict(needs_bwd=needs_bwd), *params)
             return (logits, feats) if return_features else (logits, None)
         logits, feats, _, _ = self._infer(images, landmarks)
         return (logits, feats) if return_features else (logits, None)
 
     def predict(self, images, landmarks=None, return_probs=True):
-        logits, _ = self.forward(images, landmarks)
-        return torch.softmax(logits, dim=1) if return_probs else logits
+        with torch.no_grad():       # feature_extractor.py:287
+            logits, _ = self.forward(images, landmarks)
+            return torch.softmax(logits, dim=1) if return_probs else logits
 
     @torch.no_grad()
     def score_clips(self, images, landmarks=None, frames_per_clip: int = 32, threshold: float = 0.5):
@@ -632,3 +740,8 @@ class DeepfakeDetectionModel(nn.Module):
         ops.dtype_code(dtype)
         self.compute_dtype = dtype
         return self
+
+
+def _rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0

@@ -44,21 +44,42 @@ def stem_conv(x_nchw, w_khwc, bias, out_dtype, act=DFV_ACT_SILU):
     return y
 
 
-def dwconv(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, act=DFV_ACT_SILU, want_pool=True):
-    """x: [B,H,W,C].  Returns (y [B,Ho,Wo,C], pool_partial [B,parts,C] fp32 or None)."""
+def stem_conv_u8(x_hwc, mean, std, w_khwc, bias, out_dtype, act=DFV_ACT_SILU):
+    """x_hwc: [B,H,W,3] uint8 RGB crops; normalised (u8 / 255 - mean) / std inside the kernel."""
+    B, H, W, _ = x_hwc.shape
+    C_ = bias.numel()
+    Ho, Wo = (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1
+    y = torch.empty(B, Ho, Wo, C_, device=x_hwc.device, dtype=out_dtype)
+    assert x_hwc.dtype == torch.uint8
+    norm = (C.c_float * 6)(*mean, *std)
+    check(lib.dfv_stem_conv_u8_fwd(_ptr(x_hwc), norm, _f32(w_khwc), _f32(bias), _ptr(y), dtype_code(out_dtype), B, H, W, C_, act, _stream()))
+    return y
+
+
+def u8_to_nchw(x_hwc, mean, std):
+    B, H, W, _ = x_hwc.shape
+    y = torch.empty(B, 3, H, W, device=x_hwc.device, dtype=torch.float32)
+    check(lib.dfv_u8_to_nchw_f32(_ptr(x_hwc), (C.c_float * 6)(*mean, *std), _f32(y), B, H, W, _stream()))
+    return y
+
+
+def dwconv(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, act=DFV_ACT_SILU, want_pool=True, tuning=None):
+    """x: [B,H,W,C].  Returns (y [B,Ho,Wo,C], pool_partial [B,parts,C] fp32 or None).
+    tuning: optional (L, TW, TH, CB) restriction of the tile plan (0 = free)."""
     B, H, W, C_ = x.shape
     dt = dtype_code(x.dtype)
     Ho = (H + pad_lo + pad_hi - kernel) // stride + 1
     Wo = (W + pad_lo + pad_hi - kernel) // stride + 1
     y = torch.empty(B, Ho, Wo, C_, device=x.device, dtype=x.dtype)
     pool = None
+    tn = C.byref(_lib.DwconvTuning(*tuning)) if tuning is not None else None
     if want_pool:
-        parts = lib.dfv_dwconv_pool_parts(dt, B, H, W, C_, kernel, stride, pad_lo, pad_hi)
+        parts = lib.dfv_dwconv_pool_parts_tuned(dt, B, H, W, C_, kernel, stride, pad_lo, pad_hi, tn)
         if parts <= 0:
             check(parts)
         pool = torch.empty(B, parts, C_, device=x.device, dtype=torch.float32)
-    check(lib.dfv_dwconv_fwd(_ptr(x), _f32(w_kkc), _f32(bias), _ptr(y), _ptr(pool), dt, B, H, W, C_, kernel, stride,
-                             pad_lo, pad_hi, act, _stream()))
+    check(lib.dfv_dwconv_fwd_tuned(_ptr(x), _f32(w_kkc), _f32(bias), _ptr(y), _ptr(pool), dt, B, H, W, C_, kernel, stride,
+                                   pad_lo, pad_hi, act, tn, _stream()))
     return y, pool
 
 
@@ -72,16 +93,18 @@ def se_gate(pool_partial, hw, w_reduce, b_reduce, w_expand_t, b_expand, gate_dty
     return gate
 
 
-def pw_gemm(a, w, bias, act=DFV_ACT_NONE, a_scale=None, rows_per_image=0, residual=None):
-    """a: [..., K] (NHWC activations), w: [N, K].  Returns [..., N]."""
+def pw_gemm(a, w, bias, act=DFV_ACT_NONE, a_scale=None, rows_per_image=0, residual=None, tuning=None):
+    """a: [..., K] (NHWC activations), w: [N, K].  Returns [..., N].
+    tuning: optional (weight_stationary in {-1, 0, 1}, N tile) restriction of the tile plan."""
     K = a.shape[-1]
     N = w.shape[0]
     M = a.numel() // K
     assert w.shape[1] == K and w.dtype == a.dtype
     assert a_scale is None or a_scale.dtype == a.dtype, "the SE gate has the activation dtype"
     out = torch.empty(*a.shape[:-1], N, device=a.device, dtype=a.dtype)
-    check(lib.dfv_pw_gemm_fwd(_ptr(a), _ptr(w), _f32(bias), _ptr(a_scale), rows_per_image, _ptr(residual), _ptr(out),
-                              dtype_code(a.dtype), M, K, N, act, _stream()))
+    tn = C.byref(_lib.GemmTuning(*tuning)) if tuning is not None else None
+    check(lib.dfv_pw_gemm_fwd_tuned(_ptr(a), _ptr(w), _f32(bias), _ptr(a_scale), rows_per_image, _ptr(residual), _ptr(out),
+                                    dtype_code(a.dtype), M, K, N, act, tn, _stream()))
     return out
 
 

@@ -45,7 +45,24 @@ class FusedAdamW(torch.optim.Optimizer):
                 self._flat_p[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self._flat_p[off:off + k].view_as(p)
         self._step = 0
+        self._frozen_key, self._frozen_chunks = None, None
         self._bind_state()
+        if grad_source is not None and hasattr(grad_source, "invalidate_packed"):
+            grad_source.invalidate_packed()       # the parameters moved into the flat buffer
+
+    def _frozen_mask(self, grads_present):
+        """One byte per 64-element chunk of the flat buffers: 1 = the optimizer must not touch it.  torch.optim.AdamW
+        skips parameters whose .grad is None (requires_grad False, freeze_bn): no update, no weight decay."""
+        key = tuple(grads_present)
+        if all(key):
+            return None
+        if self._frozen_key != key:
+            mask = torch.zeros(self._n // 64, dtype=torch.uint8)
+            for p, off, ok in zip(self._params, self._offsets, key):
+                if not ok:
+                    mask[off // 64:(off + p.numel() + 63) // 64] = 1
+            self._frozen_key, self._frozen_chunks = key, mask.to(self._flat_p.device)
+        return self._frozen_chunks
 
     def _bind_state(self):
         for p, off in zip(self._params, self._offsets):
@@ -71,16 +88,25 @@ class FusedAdamW(torch.optim.Optimizer):
         """One clip + AdamW step.  Returns the pre-clip global gradient norm (a 1-element device tensor: no
         host synchronisation), the value `clip_grad_norm_` returns in the reference loop."""
         loss = closure() if closure is not None else None
+        lo, hi = self._flat_p.data_ptr(), self._flat_p.data_ptr() + 4 * self._n
+        for p in self._params:
+            assert lo <= p.data_ptr() < hi, ("a parameter is no longer a view of FusedAdamW's flat buffer (model.to(...) / "
+                                             ".float() after the optimizer was built): rebuild the optimizer")
+        present = [p.grad is not None and p.requires_grad for p in self._params]
         g = self._grad_flat_checked()
+        frozen = self._frozen_mask(present)
         grp = self.param_groups[0]
         self._step += 1
         b1, b2 = grp["betas"]
         check(lib.dfv_clip_adamw_step(self._flat_p.data_ptr(), g.data_ptr(), self._flat_m.data_ptr(), self._flat_v.data_ptr(),
                                       self._n, self._norm_ws.data_ptr(), self.max_grad_norm, float(grad_scale), float(grp["lr"]),
                                       float(b1), float(b2), float(grp["eps"]), float(grp["weight_decay"]), self._step,
-                                      self._total_norm.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                                      self._total_norm.data_ptr(), frozen.data_ptr() if frozen is not None else None,
+                                      torch.cuda.current_stream().cuda_stream))
         for p in self._params:
             self.state[p]["step"].fill_(float(self._step))
+        if self._grad_source is not None and hasattr(self._grad_source, "invalidate_packed"):
+            self._grad_source.invalidate_packed()     # weights were rewritten through raw pointers
         return self._total_norm if loss is None else loss
 
     def _grad_flat_checked(self):

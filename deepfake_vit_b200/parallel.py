@@ -80,5 +80,65 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src, group=group)
+    with torch.no_grad():       # in-place on the tensors themselves: version counters see it
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=group)
+    if hasattr(module, "invalidate_packed"):
+        module.invalidate_packed()
+
+
+def merge_units(unit_ranges, bucket_floats: int):
+    """Gradient buckets from the backward pass's completion units.  `unit_ranges[u] = (lo, hi)` is the flat-buffer range
+    whose gradients are complete after unit u (completion order = reverse registration order, so consecutive units are
+    adjacent ranges going DOWN the buffer).  Consecutive units are merged until a bucket holds >= bucket_floats elements.
+    Returns [(lo, hi, last_unit)] in completion order; the buckets tile [0, total) exactly."""
+    buckets, lo, hi = [], None, None
+    for u, (a, b) in enumerate(unit_ranges):
+        if lo is None:
+            lo, hi = a, b
+        else:
+            assert b == lo, "units must be adjacent, descending"
+            lo = a
+        if hi - lo >= bucket_floats or u == len(unit_ranges) - 1:
+            buckets.append((lo, hi, u))
+            lo = hi = None
+    return buckets
+
+
+class BucketedAllReduce:
+    """Gradient all-reduce overlapped with the backward pass: dfv_train_bwd records one CUDA event per
+    gradient unit on the compute stream; each bucket's NCCL all-reduce is issued on a side stream behind the event of
+    its last unit, so it runs while the remaining (earlier-layer) backward kernels execute.  The compute stream joins
+    the side stream once, after the last bucket."""
+
+    def __init__(self, unit_ranges, total: int, bucket_floats: int, device):
+        import ctypes as C
+        self.total, self.bucket_floats = total, bucket_floats
+        self.buckets = merge_units(unit_ranges, bucket_floats)
+        self.stream = torch.cuda.Stream(device=device)
+        self.events = {}
+        table = [None] * len(unit_ranges)
+        cur = torch.cuda.current_stream(device)
+        for _, _, unit in self.buckets:
+            ev = torch.cuda.Event()
+            ev.record(cur)                      # torch creates the CUDA event lazily, on its first record
+            self.events[unit] = ev
+            table[unit] = ev.cuda_event
+        self._table = (C.c_void_p * len(table))(*table)
+
+    @staticmethod
+    def active(group=None) -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def event_table(self):
+        return self._table
+
+    def reduce(self, flat: torch.Tensor, group=None):
+        cur = torch.cuda.current_stream(flat.device)
+        with torch.cuda.stream(self.stream):
+            for lo, hi, unit in self.buckets:
+                self.stream.wait_event(self.events[unit])
+                allreduce_gradients(flat[lo:hi], group)
+        flat.record_stream(self.stream)
+        cur.wait_stream(self.stream)

@@ -51,12 +51,10 @@ int dfv_version(void);
 const char* dfv_last_error(void);
 /* DFV_OK if the current CUDA device can run the kernels (compute capability 10.x). */
 int dfv_device_check(void);
-/* Debug/localisation switch: route bf16 1x1 convolutions through the SIMT kernel that the
- * fp32 mode uses instead of tcgen05.  Tests only; default 0. */
-void dfv_debug_force_simt_gemm(int on);
-/* Debug: nonzero if a bounded in-kernel barrier wait starved (the kernel then traps): bit 31 set,
- * bits 24-30 = which wait, bits 0-23 = block index.  Readable after a launch failure. */
-unsigned int dfv_debug_last_timeout(void);
+/* Diagnostics: nonzero if a bounded in-kernel barrier wait starved (the kernel then traps): bit 31 set,
+ * bits 24-30 = which wait, bits 0-23 = block index.  Readable after a launch failure (appended to the
+ * Python wrapper's error message). */
+unsigned int dfv_last_timeout_word(void);
 /* Number of kernels launched by this thread since the last reset (bench.py's gpu_launches). */
 long long dfv_launch_count(int reset);
 
@@ -126,6 +124,19 @@ int dfv_blob_slot(int dtype, int block, int kind, size_t* offset, size_t* elems)
  * (src/data/dataset.py:82-116): NCHW fp32.  y: NHWC [B][Ho][Wo][C]. */
 int dfv_stem_conv_fwd(const float* x_nchw, const float* w_khwc, const float* bias, void* y, int dtype,
                       int B, int H, int W, int C, int act, dfv_stream_t stream);
+
+/* The same stem fed by the RAW crop: uint8 RGB, HWC ([B][H][W][3], what cv2.imread + cvtColor gives before the
+ * reference's `image.transpose(2,0,1)`), with the input normalisation of the reference's data path fused into
+ * the operand load: v = (u8 / 255 - mean[c]) / std[c] in fp32 with IEEE division, exactly the op order of
+ * PreprocessedFaceDataset.__getitem__ (src/data/dataset.py:92-98; constants :59-60; task.ipynb:386 does the same
+ * on the device).  The 3 x 256 possible values are tabulated per CTA, so the fp32 path is bit-identical to
+ * feeding dfv_stem_conv_fwd the normalised NCHW fp32 tensor.  norm6: HOST float[6] = mean[3], std[3].
+ * 4x fewer input bytes from HBM and over PCIe than the fp32 NCHW contract. */
+int dfv_stem_conv_u8_fwd(const uint8_t* x_hwc, const float* norm6, const float* w_khwc, const float* bias, void* y,
+                         int dtype, int B, int H, int W, int C, int act, dfv_stream_t stream);
+/* The normalisation alone: uint8 HWC -> fp32 NCHW (the reference's input contract), same arithmetic.  Used by the
+ * training path, whose stem weight gradient reads the fp32 image. */
+int dfv_u8_to_nchw_f32(const uint8_t* x_hwc, const float* norm6, float* y_nchw, int B, int H, int W, dfv_stream_t stream);
 
 /* Depthwise k x k conv (k in {3,5}, stride in {1,2}) with the static asymmetric pad
  * applied by TMA out-of-bounds zero fill (no padded copy), folded BN, swish, and the SE
@@ -232,7 +243,7 @@ typedef struct {
   int32_t heat_group;            /* images per heat-map max group; 0 = whole batch */
   float landmark_ref_size;       /* 224.0 (landmark_attention.py:97-98) */
   const void* blob;              /* folded backbone weights, dfv_blob_* layout */
-  const float* images_nchw;      /* [B][3][H][W] fp32 */
+  const float* images_nchw;      /* [B][3][H][W] fp32 (NULL when images_u8 is given) */
   const float* landmarks;        /* [B][5][2] fp32 or NULL */
   const float* lm_weights;       /* [5] */
   const float* ca_w1;            /* [hidden][1792] */
@@ -251,6 +262,9 @@ typedef struct {
   void* const* taps;             /* optional: host array of 34 device pointers (stem, block0..31,
                                     head) receiving NHWC copies of each stage output; entries may
                                     be NULL; NULL array = no taps */
+  const uint8_t* images_u8;      /* optional: [B][H][W][3] uint8 RGB crops; normalised inside the stem
+                                    (dfv_stem_conv_u8_fwd) with u8_norm = mean[3], std[3] */
+  float u8_norm[6];
 } dfv_infer_args;
 
 size_t dfv_infer_workspace_bytes(int dtype, int B, int H, int W);
@@ -392,7 +406,17 @@ typedef struct {
   const float* dfeatures;          /* bwd in  [B][1792] or NULL */
   void* const* taps;               /* optional debug: host array of 34 device pointers (stem, block0..31, head)
                                       receiving NHWC copies of each stage output (fwd) */
+  int32_t freeze_bn;               /* 1: backbone BatchNorm2d layers run in EVAL mode inside the training step (running
+                                      statistics, not updated; no gamma / beta gradients) -- EfficientNetB4Backbone
+                                      freeze_bn=True (src/feature_extraction/efficientnet.py:84-90,165-170).  The
+                                      classifier's BatchNorm1d layers stay in train mode, as in the reference. */
+  void* const* grad_events;        /* bwd, optional: host array of DFV_GRAD_UNITS cudaEvent_t handles (entries may be
+                                      NULL).  Event u is recorded on the stream once every gradient of unit u is
+                                      complete: unit 0 = classifier + attention + head conv, unit 1 + j = block 31 - j,
+                                      unit 33 = stem.  Lets the caller start the data-parallel all-reduce of a
+                                      finished gradient bucket on a side stream while the rest of the backward runs. */
 } dfv_train_args;
+#define DFV_GRAD_UNITS 34
 
 size_t dfv_train_arena_bytes(int dtype, int B, int H, int W, const int32_t* head_dims, int head_layers, int ca_hidden);
 size_t dfv_train_scratch_bytes(int dtype, int B, int H, int W, const int32_t* head_dims, int head_layers, int ca_hidden);
@@ -428,23 +452,65 @@ int dfv_l2_normalize(const float* x, float* y, int B, int D, float eps, dfv_stre
  * torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.AdamW, over FLAT fp32 buffers of n
  * elements (parameters, gradients, exp_avg, exp_avg_sq).  grad_scale multiplies the gradients first (1/N of a
  * summed all-reduce, or a loss-scale inverse); max_norm <= 0 disables clipping; step is 1-based.
- * sqnorm_ws: one double of device scratch; total_norm_out: optional device float (pre-clip global norm). */
+ * sqnorm_ws: one double of device scratch; total_norm_out: optional device float (pre-clip global norm).
+ * frozen_chunks: optional device bytes, one per 64-element chunk of the flat buffers (tensors start on 64-element
+ * boundaries): nonzero = leave the chunk's parameters and moments untouched, as torch.optim.AdamW skips parameters
+ * without a gradient (freeze_bn, requires_grad = False). */
 int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                         double* sqnorm_ws, double max_norm, double grad_scale, double lr, double beta1, double beta2,
-                        double eps, double weight_decay, long long step, float* total_norm_out, dfv_stream_t stream);
+                        double eps, double weight_decay, long long step, float* total_norm_out,
+                        const unsigned char* frozen_chunks, dfv_stream_t stream);
 
-/* Debug / documentation aid (host only): the depthwise tile plan chosen for a layer.
+/* Plan introspection (host only, pure functions of the shape): the depthwise tile plan chosen for a layer.
  * out[0..9] = CB, L, TW, TH, threads, smem bytes, tiles_w, tiles_h, pool parts, grid. */
-int dfv_debug_dwconv_plan(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out);
+int dfv_dwconv_plan_info(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out);
 /* Tile plan of a bf16 tensor-core 1x1-conv GEMM (host only): out[0..7] = N tile, weight-stationary flag, pipeline
  * stages, staging buffers, grid, tiles per CTA, shared-memory bytes, N tiles. */
-int dfv_debug_gemm_plan(long long M, int K, int N, int scaled, int* out);
-/* Probe for the planned tensor-core depthwise kernel (csrc/dw_tc_probe.cu; not on the product path):
- * out[p][c] = sum_t x[p + offs[t]][c] * w[t][c] for 128 pixels x 64 channels with tcgen05.mma on a TMA-written SWIZZLE_128B
- * tile viewed from arbitrary pixel-row offsets.  x [P][64] bf16, w [taps][64] bf16, offs DEVICE int[taps], out [128][64] fp32;
- * mode 0 / 1 = A descriptor without / with the matrix-base-offset field. */
-int dfv_debug_dwconv_tc_probe(const void* x, const void* w, const int* offs, int taps, int P, int mode, float* out,
-                              dfv_stream_t stream);
+int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* out);
+
+/* Tuning entry points: the same operators with the tile plan restricted by the CALLER (a per-call argument: no
+ * process state, no environment variables).  Fields left 0 (-1 for weight_stationary) are chosen by the planner.
+ * Used by the kernel-sweep scripts and by the tests that exercise every plan family at full size. */
+typedef struct {
+  int32_t weight_stationary;   /* -1 auto, 0 streaming, 1 weight-stationary */
+  int32_t bn;                  /* N tile (0 = auto) */
+} dfv_gemm_tuning;
+int dfv_pw_gemm_fwd_tuned(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
+                          const void* residual, void* out, int dtype, long long M, int K, int N, int act,
+                          const dfv_gemm_tuning* tuning, dfv_stream_t stream);
+typedef struct {
+  int32_t L, TW, TH, CB;       /* strip length, tile width / height, channel chunk (0 = auto); stride-1 layers only */
+} dfv_dwconv_tuning;
+int dfv_dwconv_fwd_tuned(const void* x, const float* w_kkc, const float* bias, void* y, float* pool_partial, int dtype,
+                         int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act,
+                         const dfv_dwconv_tuning* tuning, dfv_stream_t stream);
+int dfv_dwconv_pool_parts_tuned(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi,
+                                const dfv_dwconv_tuning* tuning);
+
+/* ------------------------------------------------------------------------------------
+ * Weight packing for inference, from the module's own parameter storage: `params` is the same host table of
+ * device pointers to fp32 torch-layout tensors as dfv_train_args.params (dfv_train_index / dfv_train_cls_index,
+ * running statistics included).  Folds eval-mode BatchNorm (w' = w * gamma / sqrt(var + eps),
+ * b' = beta - mean * scale [+ bias * scale]) and writes
+ *   blob        the dfv_blob_* slots (GEMM weights in `dtype`, the rest fp32)
+ *   head_w_t[l] fp32 [dims[l]][dims[l+1]]  transposed folded classifier weights, head_b[l] fp32 [dims[l+1]]
+ *   ca_w2_t     fp32 [ca_hidden][1792]     channel_attn.fc.2.weight transposed (NULL: no channel attention)
+ * in a handful of launches -- no arithmetic of the path is left to the host framework.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dtype;
+  float bn_eps;                    /* backbone BatchNorm2d eps (1e-3) */
+  float cls_bn_eps;                /* classifier BatchNorm1d eps (1e-5) */
+  const float* const* params;      /* host table, dfv_train_table_size() entries */
+  void* blob;                      /* dfv_blob_bytes(dtype) bytes */
+  int32_t head_layers;
+  const int32_t* head_dims;        /* host int[head_layers + 1] */
+  float* const* head_w_t;          /* host array of device pointers (out) */
+  float* const* head_b;
+  int32_t ca_hidden;
+  float* ca_w2_t;
+} dfv_pack_args;
+int dfv_pack_weights(const dfv_pack_args* args, dfv_stream_t stream);
 
 
 #ifdef __cplusplus

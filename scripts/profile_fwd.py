@@ -20,6 +20,6 @@ try:
     torch.cuda.synchronize()
 except Exception as e:
     print("FAILED at iteration", i, "after", round(time.time() - t0, 2), "s:", str(e)[:300])
-    print("timeout word: 0x%08x" % d._lib.lib.dfv_debug_last_timeout())
+    print("timeout word: 0x%08x" % d._lib.lib.dfv_last_timeout_word())
     sys.exit(1)
 print("ok", out[0].shape, d._lib.lib.dfv_launch_count(0))

@@ -7,5 +7,5 @@ layers = [(48,190,3,1,1,1),(24,190,3,1,1,1),(144,190,3,2,0,1),(192,95,3,1,1,1),(
 out = (C.c_int * 10)()
 print("    C   H k s | CB  L TW TH thr   smem tw th parts grid")
 for (c, h, k, s, pl, ph) in layers:
-    rc = lib.dfv_debug_dwconv_plan(1, B, h, h, c, k, s, pl, ph, out)
+    rc = lib.dfv_dwconv_plan_info(1, B, h, h, c, k, s, pl, ph, out)
     print(f"{c:5d} {h:3d} {k} {s} |", rc, " ".join(f"{v:3d}" for v in out))

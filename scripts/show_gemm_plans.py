@@ -24,5 +24,5 @@ for name, H, K, N, g in layers:
     M = B * H * H
     f = fold(M, K, N, bool(g), H * H)
     Mf, Kf, Nf = M // f, K * f, N * f
-    rc = lib.dfv_debug_gemm_plan(C.c_longlong(Mf), Kf, Nf, g, out)
+    rc = lib.dfv_gemm_plan_info(C.c_longlong(Mf), Kf, Nf, g, out)
     print(f"{name:12s} {Mf:9d} {Kf:5d} {Nf:5d} {g} {f} |", rc, " ".join(f"{v:4d}" for v in out))

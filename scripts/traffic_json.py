@@ -1,5 +1,5 @@
 """gpurun_out/traffic.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum) ->
-profiles/r01_traffic.json: per kernel family, DRAM bytes per launch averaged over the launches of one forward."""
+profiles/r02_traffic.json: per kernel family, DRAM bytes per launch averaged over the launches of one forward."""
 import csv, json, collections, sys
 src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/traffic.csv"
 rows = [r for r in csv.reader(open(src)) if len(r) > 10 and r[0].isdigit()]
@@ -22,5 +22,5 @@ for k, d in acc.items():
     out[k] = {"launches": int(n), "dram_bytes_per_launch": (d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"]) / n,
               "dram_read_bytes_total": d["dram__bytes_read.sum"], "dram_write_bytes_total": d["dram__bytes_write.sum"],
               "ncu_time_us_total": d["gpu__time_duration.sum"], "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, one batch-256 forward"}
-json.dump(out, open("profiles/r01_traffic.json", "w"), indent=1)
+json.dump(out, open("profiles/r02_traffic.json", "w"), indent=1)
 print(json.dumps(out, indent=1))

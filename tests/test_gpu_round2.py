@@ -1,0 +1,382 @@
+"""B200 only: boundary pieces added in round 2.
+
+  * uint8 HWC front end fused into the stem (src/data/dataset.py:92-98, task.ipynb:386): BIT-identical to feeding the
+    normalised fp32 NCHW tensor, in fp32 and bf16, eval and train
+  * dfv_pack_weights (BatchNorm folding + layout packing inside the library) against the folding formula in torch
+  * freeze_bn=True training (src/feature_extraction/efficientnet.py:84-90,165-170) against the oracle
+  * EfficientNetB4Backbone.forward / train-mode feature_extractor(...) / checkpoint FILES in the layout of
+    src/training/trainer.py:299-306 and src/utils/io_utils.py:185-229
+  * lifetime / staleness regressions: two train forwards before a backward, CUDA-graph replay after an eager call at
+    another shape and after a weight update, `.data` writes + invalidate_packed(), frozen parameters in FusedAdamW
+"""
+import copy
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LOSS_W = {"ce": 1.0, "focal": 0.5, "contrastive": 0.2}
+MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _no_stochastic(model, oracle_side):
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+    bb = model.feature_extractor.backbone.backbone
+    if oracle_side:
+        bb._global_params = bb._global_params._replace(drop_connect_rate=0.0)
+    else:
+        bb.drop_connect_rate = 0.0
+
+
+def _pair(size=96, config=None, stochastic=False):
+    import deepfake_vit_b200 as d
+    from oracle import calibrate, refmodel
+    ns = refmodel.get_oracle()
+    if config is None:
+        om = calibrate.build(ns, "calibrated", calib_size=size, calib_batches=2)
+        config = refmodel.MODEL_CONFIG
+    else:
+        torch.manual_seed(42)
+        from oracle.load_reference import quiet
+        with quiet():
+            om = ns.DeepfakeDetectionModel(**config)
+        g = torch.Generator().manual_seed(43)
+        with torch.no_grad():      # non-trivial BatchNorm state: randomised affine + statistics
+            for mod in om.modules():
+                if isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm1d)):
+                    mod.weight.copy_(0.8 + 0.4 * torch.rand(mod.weight.shape, generator=g))
+                    mod.bias.copy_(0.1 * torch.randn(mod.bias.shape, generator=g))
+                    mod.running_mean.copy_(0.1 * torch.randn(mod.running_mean.shape, generator=g))
+                    mod.running_var.copy_(0.5 + torch.rand(mod.running_var.shape, generator=g))
+    m = d.DeepfakeDetectionModel(**config)
+    m.load_state_dict(om.state_dict(), strict=True)
+    m = m.to(DEV)
+    if not stochastic:
+        _no_stochastic(om, True)
+        _no_stochastic(m, False)
+    return om, m, d, refmodel
+
+
+def _normalise_cpu(u8):
+    """The reference's own input arithmetic (dataset.py:92-98), on CPU."""
+    img = u8.permute(0, 3, 1, 2).float()
+    img = img / 255.0
+    return (img - torch.tensor(MEAN).view(1, 3, 1, 1)) / torch.tensor(STD).view(1, 3, 1, 1)
+
+
+# ------------------------------------------------------------------------------------------------ uint8 front end
+@pytest.mark.parametrize("shape", [(3, 380, 380), (2, 129, 161)])
+def test_uint8_front_end_is_bit_identical_to_the_normalised_fp32_input(shape):
+    om, m, d, _ = _pair(128)
+    B, H, W = shape
+    g = torch.Generator().manual_seed(21)
+    u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    lm = torch.rand(B, 5, 2, generator=g) * min(H, W)
+    x = _normalise_cpu(u8)
+    assert torch.equal(d.ops.u8_to_nchw(u8.to(DEV), MEAN, STD).cpu(), x)        # the normalisation itself, bit for bit
+    m.eval()
+    for dtype in (torch.float32, torch.bfloat16):
+        m.set_compute_dtype(dtype)
+        lo_f, fe_f, _, taps_f = m.forward_with_taps(x.to(DEV), lm.to(DEV))
+        lo_u, fe_u, _, taps_u = m.forward_with_taps(u8.to(DEV), lm.to(DEV))
+        assert torch.equal(taps_u[0], taps_f[0]), dtype                           # stem output
+        assert torch.equal(lo_u, lo_f) and torch.equal(fe_u, fe_f), dtype
+    m.set_compute_dtype(torch.float32)
+    with torch.no_grad():
+        ref, _ = om.eval()(x, lm)
+    out, _ = m(u8.to(DEV), lm.to(DEV))
+    assert rel(out, ref) < 1e-4 and torch.equal(out.argmax(1).cpu(), ref.argmax(1))
+
+
+def test_uint8_input_in_train_mode():
+    om, m, d, refmodel = _pair(96)
+    g = torch.Generator().manual_seed(22)
+    u8 = torch.randint(0, 256, (4, 96, 96, 3), generator=g, dtype=torch.uint8)
+    lm = torch.rand(4, 5, 2, generator=g) * 96
+    y = torch.tensor([0, 1, 1, 0])
+    x = _normalise_cpu(u8)
+    om.train()
+    lo, fe = om(x, lm, return_features=True)
+    refmodel.CombinedLoss(LOSS_W, None)(lo, y, fe)["total"].backward()
+    m.train().set_compute_dtype(torch.float32)
+    lo2, fe2 = m(u8.to(DEV), lm.to(DEV), return_features=True)
+    d.CombinedLoss(LOSS_W, None)(lo2, y.to(DEV), fe2)["total"].backward()
+    assert rel(lo2, lo) < 1e-4
+    ref = dict(om.named_parameters())
+    for name in ("feature_extractor.backbone.backbone._conv_stem.weight", "feature_extractor.backbone.backbone._blocks.3._project_conv.weight"):
+        assert rel(dict(m.named_parameters())[name].grad, ref[name].grad) < 5e-3, name
+
+
+# ------------------------------------------------------------------------------------------------ weight packing
+def test_pack_weights_kernel_matches_the_folding_formula():
+    """dfv_pack_weights folds BatchNorm inside the library; compare every blob slot and the classifier / attention
+    matrices with w * gamma / sqrt(var + eps), beta - mean * scale computed by torch."""
+    om, m, d, _ = _pair(96)
+    m.eval()
+    L = d._lib
+    for dtype, code, tol in ((torch.float32, 0, 1e-6), (torch.bfloat16, 1, 4e-3)):
+        pk = m._pack(dtype, torch.device(DEV, torch.cuda.current_device()))
+        torch.cuda.synchronize()
+
+        def slot(block, kind, dt):
+            off, n = L.blob_slot(code, block, kind)
+            es = 2 if dt == torch.bfloat16 else 4
+            return pk.blob[off:off + n * es].view(dt).float().cpu()
+
+        def fold(bn):
+            s = bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps)
+            return s, bn.bias.detach().float() - bn.running_mean.float() * s
+
+        bb = om.feature_extractor.backbone.backbone
+        s, b = fold(bb._bn0)
+        assert rel(slot(-1, L.W_STEM, torch.float32), (bb._conv_stem.weight.detach().permute(2, 3, 1, 0) * s).reshape(-1)) < 1e-6
+        assert rel(slot(-1, L.W_STEM_BIAS, torch.float32), b) < 1e-6
+        for i in (0, 2, 6, 17, 22, 31):
+            blk = bb._blocks[i]
+            cmid = blk._depthwise_conv.weight.shape[0]
+            if hasattr(blk, "_expand_conv") and i > 1:
+                s, b = fold(blk._bn0)
+                assert rel(slot(i, L.W_EXPAND, dtype), (blk._expand_conv.weight.detach().view(cmid, -1) * s[:, None]).reshape(-1)) < tol, i
+                assert rel(slot(i, L.W_EXPAND_BIAS, torch.float32), b) < 1e-6
+            s, b = fold(blk._bn1)
+            kk = blk._depthwise_conv.weight.shape[-1] ** 2
+            assert rel(slot(i, L.W_DW, torch.float32), (blk._depthwise_conv.weight.detach().view(cmid, kk) * s[:, None]).t().reshape(-1)) < 1e-6, i
+            assert rel(slot(i, L.W_DW_BIAS, torch.float32), b) < 1e-6
+            assert torch.equal(slot(i, L.W_SE_REDUCE, torch.float32), blk._se_reduce.weight.detach().view(-1, cmid).reshape(-1))
+            assert torch.equal(slot(i, L.W_SE_REDUCE_BIAS, torch.float32), blk._se_reduce.bias.detach())
+            assert torch.equal(slot(i, L.W_SE_EXPAND, torch.float32), blk._se_expand.weight.detach().view(cmid, -1).t().reshape(-1))
+            assert torch.equal(slot(i, L.W_SE_EXPAND_BIAS, torch.float32), blk._se_expand.bias.detach())
+            s, b = fold(blk._bn2)
+            cout = blk._project_conv.weight.shape[0]
+            assert rel(slot(i, L.W_PROJECT, dtype), (blk._project_conv.weight.detach().view(cout, cmid) * s[:, None]).reshape(-1)) < tol, i
+            assert rel(slot(i, L.W_PROJECT_BIAS, torch.float32), b) < 1e-6
+        s, b = fold(bb._bn1)
+        assert rel(slot(-1, L.W_HEAD, dtype), (bb._conv_head.weight.detach().view(1792, -1) * s[:, None]).reshape(-1)) < tol
+        mods = list(om.classifier)
+        for l, i in enumerate((0, 4, 8, 12)):
+            w, bias = mods[i].weight.detach().float(), mods[i].bias.detach().float()
+            if i < 12:
+                s, sh = fold(mods[i + 1])
+                w, bias = w * s[:, None], bias * s + sh
+            assert rel(pk.head.w_t[l], w.t()) < 1e-6 and rel(pk.head.b[l], bias) < 1e-6, l
+        assert torch.equal(pk.ca_w2_t.cpu(), om.feature_extractor.attention.channel_attn.fc[2].weight.detach().t().contiguous())
+
+
+def test_data_writes_need_invalidate_packed():
+    """Writes through `.data` are invisible to torch's version counters: invalidate_packed() is the documented hook
+    (FusedAdamW.step, broadcast_parameters and the train forward call it themselves)."""
+    _, m, _, _ = _pair(96)
+    m.eval().set_compute_dtype(torch.float32)
+    x = torch.randn(2, 3, 96, 96, device=DEV)
+    a, _ = m(x, None)
+    m.classifier[12].bias.data.add_(1.0)
+    m.invalidate_packed()
+    b, _ = m(x, None)
+    assert torch.allclose(b, a + 1.0, atol=1e-5)
+    with torch.no_grad():
+        m.classifier[12].bias.add_(1.0)          # a tracked in-place write needs nothing
+    c, _ = m(x, None)
+    assert torch.allclose(c, a + 2.0, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ freeze_bn
+def test_freeze_bn_training_step_matches_the_oracle():
+    from oracle import calibrate, refmodel
+    cfg = copy.deepcopy(refmodel.MODEL_CONFIG)
+    cfg["feature_extractor_config"]["freeze_bn"] = True
+    om, m, d, _ = _pair(96, config=cfg)
+    x, lm, _ = calibrate.synthetic_batch(4, 96)
+    y = torch.tensor([0, 1, 1, 1])
+    cw = torch.tensor([1.0, 1.5])
+    om.train()
+    sd0 = copy.deepcopy(om.state_dict())
+    lo, fe = om(x, lm, return_features=True)
+    ref_loss = refmodel.CombinedLoss(LOSS_W, cw)(lo, y, fe)
+    ref_loss["total"].backward()
+    m.train().set_compute_dtype(torch.float32)
+    lo2, fe2 = m(x.to(DEV), lm.to(DEV), return_features=True)
+    loss = d.CombinedLoss(LOSS_W, cw.to(DEV))(lo2, y.to(DEV), fe2)
+    loss["total"].backward()
+    assert rel(fe2, fe) < 1e-4 and rel(lo2, lo) < 1e-4
+    assert abs(loss["total"].item() - ref_loss["total"].item()) < 1e-4
+    ref = dict(om.named_parameters())
+    norms = sorted(float(p.grad.norm()) for p in ref.values() if p.grad is not None)
+    typical = norms[len(norms) // 2]
+    n_frozen = 0
+    for name, p in m.named_parameters():
+        r = ref[name]
+        assert p.requires_grad == r.requires_grad, name
+        if r.grad is None:
+            n_frozen += 1
+            assert p.grad is None, name
+            continue
+        e = float((p.grad.double().cpu() - r.grad.double()).norm()) / max(float(r.grad.norm()), 1e-3 * typical)
+        assert e < 5e-3, (name, e)
+    assert n_frozen == 2 * (1 + 30 + 32 + 32 + 1)        # every backbone BatchNorm weight and bias
+    sd, ref_sd = m.state_dict(), om.state_dict()
+    for k, v in ref_sd.items():
+        if "backbone" in k and ("running" in k or "num_batches" in k):
+            assert torch.equal(sd[k].cpu(), sd0[k]), k           # frozen: untouched
+        elif k.endswith(("running_mean", "running_var")):
+            assert rel(sd[k], v) < 1e-4, k                       # classifier BatchNorm1d trains as usual
+        elif k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+    # the stock-format optimizer leaves frozen parameters alone (no update, no weight decay), like torch.optim.AdamW
+    opt = d.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=1e-2, max_grad_norm=1.0, grad_source=m)
+    ref_opt = torch.optim.AdamW(om.parameters(), lr=1e-3, weight_decay=1e-2)
+    m.zero_grad(set_to_none=True)
+    lo2, fe2 = m(x.to(DEV), lm.to(DEV), return_features=True)
+    d.CombinedLoss(LOSS_W, cw.to(DEV))(lo2, y.to(DEV), fe2)["total"].backward()
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    opt.step()
+    torch.nn.utils.clip_grad_norm_(om.parameters(), 1.0)
+    ref_opt.step()
+    for n, p in m.named_parameters():
+        if not p.requires_grad:
+            assert torch.equal(p.detach(), before[n]), n
+    name = "feature_extractor.backbone.backbone._blocks.5._project_conv.weight"
+    assert rel(dict(m.named_parameters())[name].detach(), ref[name].detach()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ sub-module APIs
+def test_backbone_forward_and_train_mode_feature_extractor():
+    from oracle import calibrate, refmodel
+    om, m, d, _ = _pair(128)
+    x, lm, y = calibrate.synthetic_batch(4, 128)
+    m.set_compute_dtype(torch.float32)
+    om.eval(); m.eval()
+    with torch.no_grad():
+        f_ref, inter_ref = om.feature_extractor.backbone(x, return_intermediate=True)
+        maps_ref = om.feature_extractor.backbone.get_feature_maps(x)
+    f, inter = m.feature_extractor.backbone(x.to(DEV), return_intermediate=True)
+    assert rel(f, f_ref) < 1e-4 and set(inter) == set(inter_ref)
+    for k in inter_ref:
+        assert inter[k].shape == inter_ref[k].shape and rel(inter[k], inter_ref[k]) < 1e-4, k
+    assert m.feature_extractor.backbone(x.to(DEV))[1] is None
+    assert rel(m.feature_extractor.backbone.get_feature_maps(x.to(DEV)), maps_ref) < 1e-4
+    # train mode: features with autograd through the library (the reference's Trainer never calls this, its users may)
+    om.train(); m.train()
+    f_ref, _ = om.feature_extractor(x, lm)
+    f_ref.square().sum().backward()
+    f, amap = m.feature_extractor(x.to(DEV), lm.to(DEV), return_attention=True)
+    f.square().sum().backward()
+    assert rel(f, f_ref) < 1e-4 and amap.shape == (4, 1, 7, 7)
+    ref = dict(om.named_parameters())
+    for name in ("feature_extractor.backbone.backbone._conv_stem.weight", "feature_extractor.attention.channel_attn.fc.0.weight",
+                 "feature_extractor.backbone.backbone._blocks.20._se_expand.weight"):
+        assert rel(dict(m.named_parameters())[name].grad, ref[name].grad) < 5e-3, name
+    fb_ref, _ = om.feature_extractor.backbone(x)
+    fb, _ = m.feature_extractor.backbone(x.to(DEV))
+    assert rel(fb, fb_ref) < 1e-4
+
+
+def test_checkpoint_files_round_trip_with_the_reference_layout(tmp_path):
+    """Files in the dict layout of Trainer._save_checkpoint (trainer.py:299-306) / io_utils.save_checkpoint
+    (io_utils.py:135-182): written by either side, loaded by the other with strict load_state_dict."""
+    from oracle import calibrate, refmodel
+    om, m, d, _ = _pair(96)
+    x, lm, _ = calibrate.synthetic_batch(2, 96)
+    m.eval().set_compute_dtype(torch.float32)
+    # reference -> ours
+    ref_opt = torch.optim.AdamW(om.parameters(), lr=1e-4, weight_decay=1e-4)
+    path = os.path.join(tmp_path, "best_model.pth")
+    torch.save({"epoch": 3, "model_state_dict": om.state_dict(), "optimizer_state_dict": ref_opt.state_dict(),
+                "scheduler_state_dict": None, "metrics_history": {"val_loss": [0.5]}, "config": {"seed": 42}}, path)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    m2 = d.DeepfakeDetectionModel(**refmodel.MODEL_CONFIG)
+    m2.load_state_dict(ck["model_state_dict"])               # default strict=True, as io_utils.py:215 / task.ipynb:358
+    m2 = m2.to(DEV).eval().set_compute_dtype(torch.float32)
+    with torch.no_grad():
+        ref, _ = om.eval()(x, lm)
+    assert rel(m2(x.to(DEV), lm.to(DEV))[0], ref) < 1e-4
+    opt = d.FusedAdamW(m2.parameters(), lr=1e-4, weight_decay=1e-4)
+    opt.load_state_dict(ck["optimizer_state_dict"])
+    # ours -> reference
+    path2 = os.path.join(tmp_path, "checkpoint_epoch_4.pth")
+    torch.save({"epoch": 4, "model_state_dict": m2.state_dict(), "optimizer_state_dict": opt.state_dict()}, path2)
+    ck2 = torch.load(path2, map_location="cpu", weights_only=False)
+    om2 = refmodel.DeepfakeDetectionModel(**refmodel.MODEL_CONFIG)
+    om2.load_state_dict(ck2["model_state_dict"])
+    with torch.no_grad():
+        assert torch.equal(om2.eval()(x, lm)[0], ref)
+    torch.optim.AdamW(om2.parameters(), lr=1e-4).load_state_dict(ck2["optimizer_state_dict"])
+
+
+# ------------------------------------------------------------------------------------------------ lifetimes
+def test_two_train_forwards_before_their_backwards():
+    """Each differentiated forward owns its saved-activation arena until its own backward ran (siamese / two-view
+    losses); different shapes in flight at once included."""
+    from oracle import calibrate, refmodel
+    om, m, d, _ = _pair(96)
+    om.train(); m.train().set_compute_dtype(torch.float32)
+    xa, lma, _ = calibrate.synthetic_batch(4, 96, seed=1)
+    xb, lmb, _ = calibrate.synthetic_batch(2, 64, seed=2)
+    la, _ = om(xa, lma)
+    lb, _ = om(xb, lmb)
+    (la.square().sum() + 2.0 * lb.square().sum()).backward()
+    oa, _ = m(xa.to(DEV), lma.to(DEV))
+    with torch.no_grad():
+        m(xb.to(DEV), lmb.to(DEV))                      # a no-grad train forward in between must not disturb anything
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    ob, _ = m(xb.to(DEV), lmb.to(DEV))
+    (oa.square().sum() + 2.0 * ob.square().sum()).backward()
+    assert rel(oa, la) < 1e-4
+    ref = dict(om.named_parameters())
+    norms = sorted(float(p.grad.norm()) for p in ref.values())
+    typical = norms[len(norms) // 2]
+    for name, p in m.named_parameters():
+        e = float((p.grad.double().cpu() - ref[name].grad.double()).norm()) / max(float(ref[name].grad.norm()), 1e-3 * typical)
+        assert e < 5e-3, (name, e)
+    del sd
+
+
+def test_graphed_inference_survives_other_shapes_and_weight_updates():
+    import deepfake_vit_b200 as d
+    torch.manual_seed(3)
+    m = d.DeepfakeDetectionModel(**d.DEFAULT_MODEL_CONFIG).to(DEV).eval().set_compute_dtype(torch.bfloat16)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(8, 3, 160, 160, device=DEV, generator=g)
+    lm = torch.rand(8, 5, 2, device=DEV, generator=g) * 160
+    gi = d.GraphedInference(m, x, lm)
+    want = m(x, lm)[0].clone()
+    # an eager call at another shape (the tail batch of a serving loop) used to free the captured workspace
+    tail = m(torch.randn(3, 3, 224, 224, device=DEV, generator=g), None)[0]
+    junk = [torch.randn(1 << 22, device=DEV) for _ in range(8)]      # reuse whatever the allocator got back
+    assert torch.isfinite(tail).all()
+    assert torch.equal(gi(x, lm)[0], want)
+    # a weight update re-captures instead of replaying stale folded weights
+    with torch.no_grad():
+        m.classifier[12].bias.add_(1.0)
+    got = gi(x, lm)[0]
+    assert torch.allclose(got, want + 1.0, atol=1e-5)
+    del junk
+    # uint8 static input buffer
+    u8 = torch.randint(0, 256, (4, 128, 128, 3), device=DEV, dtype=torch.uint8, generator=g)
+    gu = d.GraphedInference(m, u8, None)
+    assert torch.equal(gu(u8)[0], m(u8, None)[0])
+
+
+def test_predict_runs_without_autograd_state_and_modes_are_checked():
+    _, m, d, _ = _pair(64)
+    m.train().set_compute_dtype(torch.float32)
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    p = m.predict(x)
+    assert not p.requires_grad and torch.allclose(p.sum(1), torch.ones(4, device=DEV), atol=1e-6)
+    m.feature_extractor.backbone.backbone._blocks[3]._bn1.eval()       # a sub-module in another mode is an error, not ignored
+    with pytest.raises(RuntimeError, match="per-sub-module modes"):
+        m(x)
+    m.train()
+    with pytest.raises(Exception):                                       # train-mode BatchNorm needs more than one sample
+        m(x[:1])
+    out, _ = m(x)
+    assert torch.isfinite(out).all()

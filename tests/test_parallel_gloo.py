@@ -98,3 +98,23 @@ def test_flat_offsets_shared_by_gradient_buffer_and_optimizer():
     offs, total = flat_offsets([1296, 48, 7, 64, 65])
     assert offs == [0, 1344, 1408, 1472, 1536] and total == 1664
     assert all(o % FLAT_ALIGN == 0 for o in offs)
+
+
+def test_gradient_buckets_tile_the_flat_buffer_in_completion_order():
+    """The backward's gradient units (head+attention+classifier, block 31..0, stem) merged into all-reduce buckets:
+    every bucket is one contiguous flat range, buckets follow completion order and tile [0, total) exactly."""
+    import deepfake_vit_b200 as d
+    from deepfake_vit_b200.parallel import merge_units
+    m = d.DeepfakeDetectionModel(**d.DEFAULT_MODEL_CONFIG)
+    params, starts, total = m._flat_layout()
+    units = m._unit_ranges(params, starts, total)
+    assert len(units) == d._lib.GRAD_UNITS and units[0][1] == total and units[-1][0] == 0
+    names = [n for n, _ in m.named_parameters()]
+    lo31 = starts[names.index("feature_extractor.backbone.backbone._blocks.31._expand_conv.weight")]
+    assert units[1][0] == lo31 and units[0][0] == starts[names.index("feature_extractor.backbone.backbone._conv_head.weight")]
+    for bucket_floats in (1 << 18, 4 << 20, 1 << 30):
+        buckets = merge_units(units, bucket_floats)
+        assert buckets[0][1] == total and buckets[-1][0] == 0 and buckets[-1][2] == len(units) - 1
+        assert all(buckets[i][0] == buckets[i + 1][1] for i in range(len(buckets) - 1))
+        assert all(hi - lo >= bucket_floats for lo, hi, _ in buckets[:-1])
+    assert len(merge_units(units, 1 << 30)) == 1 and 3 <= len(merge_units(units, 4 << 20)) <= 8
