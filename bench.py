@@ -438,13 +438,21 @@ def infer_leg(c, args, warmup):
     roofline = kernel_table(recs, prof_steps, pk)
 
     # ---- end to end through the public API: pinned host inputs, double-buffered H2D, D2H of logits
-    def e2e(host_imgs, tag):
+    def e2e(host_imgs, graphed):
+        """graphed: the serving call -- d.GraphedInference, one per input buffer; the H2D copy lands directly in the graph's
+        static input.  Otherwise the plain nn.Module call model(images, landmarks) on double-buffered device tensors."""
         copy_stream = torch.cuda.Stream(device=dev)
-        dev_x = [torch.empty_like(h, device=dev) for h in host_imgs]
-        dev_lm = [torch.empty_like(lm) for _ in range(2)]
         host_out = torch.empty(B, 2).pin_memory()
         ready = [torch.cuda.Event() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
+        if graphed:
+            gis = [d.GraphedInference(model, host_imgs[s].to(dev), host_lm[s].to(dev)) for s in range(2)]
+            dev_x, dev_lm = [g.images for g in gis], [g.landmarks for g in gis]
+            call = lambda s: gis[s].replay()
+        else:
+            dev_x = [torch.empty_like(h, device=dev) for h in host_imgs]
+            dev_lm = [torch.empty_like(lm) for _ in range(2)]
+            call = lambda s: model(dev_x[s], dev_lm[s])
 
         def stage(i):
             s = i & 1
@@ -462,7 +470,7 @@ def infer_leg(c, args, warmup):
                 if i + 1 < n:
                     stage(i + 1)
                 cur.wait_event(ready[s])
-                lo, _ = model(dev_x[s], dev_lm[s])
+                lo, _ = call(s)
                 done[s].record(cur)
                 host_out.copy_(lo, non_blocking=True)
             cur.synchronize()
@@ -478,12 +486,10 @@ def infer_leg(c, args, warmup):
         barrier()
         t = e0.elapsed_time(e1)
         h2d = host_imgs[0].numel() * host_imgs[0].element_size() + lm.numel() * 4
-        del dev_x
         return t, h2d
 
-    e2e_ms, h2d_u8 = e2e(host_u8, "u8")
-    host_f32 = [host_x0, host_x0]
-    e2e32_ms, h2d_f32 = e2e(host_f32, "f32")
+    e2e_ms, h2d_u8 = e2e(host_u8, True)
+    e2e32_ms, h2d_f32 = e2e([host_x0, host_x0], False)
 
     if world > 1:
         t = torch.tensor([ms, e2e_ms, e2e32_ms, eager_ms], device=dev, dtype=torch.float64)
@@ -497,10 +503,11 @@ def infer_leg(c, args, warmup):
             "roofline": roofline, "cpu_baseline": None,
             "e2e": {"value": per(e2e_ms), "unit": "images/s",
                     "h2d_bytes_per_step": h2d_u8 * n_gpus, "d2h_bytes_per_step": B * 2 * 4 * n_gpus, "ms_per_step": e2e_ms / args.steps,
-                    "note": "model(images_uint8, landmarks): pinned host RAW crops (uint8 HWC, normalised inside the stem kernel), "
-                            "double-buffered H2D on a copy stream, logits copied back every step",
+                    "note": "GraphedInference(model)(images_uint8, landmarks), the package's serving call: pinned host RAW crops "
+                            "(uint8 HWC, normalised inside the stem kernel) copied straight into the graph's static input, "
+                            "double-buffered H2D on a copy stream, one graph replay per step, logits copied back every step",
                     "fp32_nchw_input": {"value": per(e2e32_ms), "h2d_bytes_per_step": h2d_f32 * n_gpus, "ms_per_step": e2e32_ms / args.steps,
-                                        "note": "the same loop fed the reference's fp32 NCHW contract (4x the bytes)"}},
+                                        "note": "the plain eager call model(images, landmarks) fed the reference's fp32 NCHW contract (4x the bytes)"}},
             "eager": {"value": per(eager_ms), "ms_per_step": eager_ms / args.steps,
                       "note": "the timed steps launched eagerly instead of replayed from the CUDA graph"},
             "gpu_launches": launches_per_forward * args.steps,

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -12,7 +13,7 @@
 namespace dfv {
 
 static thread_local char g_error[512] = "";
-static thread_local long long g_launches = 0;
+static std::atomic<long long> g_launches{0};   // process-wide: the backward pass runs on autograd's worker thread
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -276,9 +277,7 @@ int dfv_version(void) { return 200; }
 const char* dfv_last_error(void) { return g_error; }
 int dfv_device_check(void) { return check_device(); }
 long long dfv_launch_count(int reset) {
-  long long v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 unsigned int dfv_last_timeout_word(void) { return g_timeout_host ? *g_timeout_host : 0; }

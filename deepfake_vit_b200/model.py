@@ -552,17 +552,18 @@ class DeepfakeDetectionModel(nn.Module):
     def _train_fwd(self, images, landmarks, needs_bwd=True, attention=True, want_taps=False):
         x, u8, B, H, W = self._images(images)
         dev = images.device
-        if u8 is not None:      # the stem's weight gradient reads the fp32 image: normalise once, same arithmetic as the fused stem
-            x = torch.empty(B, 3, H, W, device=dev, dtype=torch.float32)
-            check(lib.dfv_u8_to_nchw_f32(u8.data_ptr(), self._norm6(), x.data_ptr(), B, H, W, torch.cuda.current_stream().cuda_stream))
         att = self.feature_extractor.attention
         lm = None
         if landmarks is not None and attention and self.feature_extractor.use_attention and att is not None and att.use_landmark:
             lm = landmarks.detach().to(device=dev, dtype=torch.float32).contiguous()
             assert lm.shape == (B, 5, 2), "landmarks must be (B, 5, 2)"
         T, dims, p_drop = self._train_tensors()
-        a, hd = self._train_args(x, lm, T, dims, p_drop, attention)
-        key = (a.dtype, B, H, W, str(dev), a.ca_hidden)
+        a, hd = self._train_args(images if x is None else x, lm, T, dims, p_drop, attention)
+        a.B, a.H, a.W = B, H, W
+        # uint8 crops: the stem's weight gradient reads the fp32 image, so it is normalised once into the tail of this
+        # forward's own arena (same arithmetic as the fused stem; no per-step allocation)
+        stage_bytes = B * 3 * H * W * 4 if u8 is not None else 0
+        key = (a.dtype, B, H, W, str(dev), a.ca_hidden, stage_bytes)
         # every forward that will be differentiated OWNS its arena until its backward has run (two forwards before a
         # backward, siamese losses); finished arenas go back to a per-shape pool
         pool = self._arena_pool.setdefault(key, [])
@@ -575,8 +576,12 @@ class DeepfakeDetectionModel(nn.Module):
             for k in [k for k in self._arena_pool if k != key]:      # another shape: drop its idle arenas
                 del self._arena_pool[k]
             pool = self._arena_pool.setdefault(key, [])
-            arena = torch.empty(n, dtype=torch.uint8, device=dev)
-        a.arena, a.arena_bytes = arena.data_ptr(), arena.numel()
+            arena = torch.empty((n + 255) // 256 * 256 + stage_bytes, dtype=torch.uint8, device=dev)
+        a.arena, a.arena_bytes = arena.data_ptr(), arena.numel() - stage_bytes
+        if u8 is not None:
+            x = arena[arena.numel() - stage_bytes:].view(torch.float32).view(B, 3, H, W)
+            check(lib.dfv_u8_to_nchw_f32(u8.data_ptr(), self._norm6(), x.data_ptr(), B, H, W, torch.cuda.current_stream().cuda_stream))
+            a.images_nchw = x.data_ptr()
         logits = torch.empty(B, dims[-1], device=dev, dtype=torch.float32)
         feats = torch.empty(B, dims[0], device=dev, dtype=torch.float32)
         a.logits, a.features = logits.data_ptr(), feats.data_ptr()

@@ -55,7 +55,7 @@ int dfv_device_check(void);
  * bits 24-30 = which wait, bits 0-23 = block index.  Readable after a launch failure (appended to the
  * Python wrapper's error message). */
 unsigned int dfv_last_timeout_word(void);
-/* Number of kernels launched by this thread since the last reset (bench.py's gpu_launches). */
+/* Number of kernels launched by this process since the last reset (bench.py's gpu_launches). */
 long long dfv_launch_count(int reset);
 
 /* Per-launch profiler (CUDA events on the launching stream around every operator launch), used

@@ -49,6 +49,17 @@ def _oracle_cpu(weight_set):
     return calibrate.build(refmodel.get_oracle(), weight_set)
 
 
+def _oracle_gpu(sd):
+    """A fresh oracle module on the GPU with the given state (deepcopy of a used oracle drags along the activations its
+    forward hooks stashed)."""
+    from oracle import refmodel
+    from oracle.load_reference import quiet
+    with quiet():
+        om = refmodel.get_oracle().DeepfakeDetectionModel(**refmodel.MODEL_CONFIG)
+    om.load_state_dict(sd, strict=True)
+    return om.to(DEV)
+
+
 def _ours(om_cpu, dtype):
     import deepfake_vit_b200 as d
     from oracle import refmodel
@@ -79,7 +90,7 @@ def test_config1_batch256_bf16_vs_oracle(golden_dir):
     om_cpu = _oracle_cpu("calibrated")
     x, lm, _ = calibrate.synthetic_batch(B, size)                 # == the first input buffer of bench.py
     xd, lmd = x.to(DEV), lm.to(DEV)
-    om = copy.deepcopy(om_cpu).to(DEV).eval()
+    om = _oracle_gpu(om_cpu.state_dict()).eval()
 
     # 1. the GPU-run oracle IS the reference: pinned to the CPU goldens of the real reference import
     lo32, fe32, taps32 = _taps_forward(om, xd, lmd)
@@ -175,7 +186,7 @@ def train64(golden_dir):
     x, lm, y = calibrate.synthetic_batch(B, size)
     xd, lmd, yd = x.to(DEV), lm.to(DEV), y.to(DEV)
     ns = refmodel.get_oracle()
-    om = copy.deepcopy(om_cpu).to(DEV)
+    om = _oracle_gpu(sd0)
     mg.no_stochastic(om)
     om.train()
     lo, fe, losses = mg.train_step(ns, om, xd, lmd, yd, mg.CLASS_W)
@@ -190,8 +201,13 @@ def train64(golden_dir):
     assert names == [n for n, _ in om.named_parameters()]
     typical = float(np.median(g["grad_norm"]))
     for i, n in enumerate(names):
-        floor = max(float(g["grad_norm"][i]), 1e-3 * typical)
         nrm, sig = mg.fingerprint(ref_grads[n])
+        if g["grad_norm"][i] < 1e-4 * typical:
+            # analytically zero gradient (a BatchNorm bias feeding a conv + batch-stat BatchNorm is a no-op shift):
+            # rounding noise on every platform -- only its size can be compared
+            assert nrm < 1e-3 * typical, (n, nrm)
+            continue
+        floor = max(float(g["grad_norm"][i]), 1e-3 * typical)
         assert abs(nrm - g["grad_norm"][i]) < 5e-3 * floor, (n, nrm, g["grad_norm"][i])
         assert abs(sig - g["grad_signature"][i]) < 2e-2 * floor, (n, sig, g["grad_signature"][i])
     for n in mg.FULL_GRADS:
@@ -228,6 +244,9 @@ def test_config2_train_step_fp32_every_parameter(train64):
     bad, worst = [], 0.0
     for n, p in m.named_parameters():
         r = t["grads"][n]
+        if float(r.norm()) < 1e-4 * t["typical"]:        # analytically zero: rounding noise on both sides
+            assert float(p.grad.norm()) < 1e-3 * t["typical"], n
+            continue
         e = float((p.grad.double() - r.double()).norm()) / max(float(r.norm()), 1e-3 * t["typical"])
         worst = max(worst, e)
         if e > 5e-3:
@@ -247,8 +266,7 @@ def test_config2_train_step_bf16_group_norms(train64):
     mg, ns = t["mg"], t["ns"]
     xd, lmd, yd = t["data"]
     # yardstick: the oracle under torch.autocast(bf16) on the same step
-    om = copy.deepcopy(t["om_cpu"]).to(DEV)
-    om.load_state_dict(t["sd0"])
+    om = _oracle_gpu(t["sd0"])
     mg.no_stochastic(om)
     om.train()
     undo = mg.checkpoint_blocks(om)      # non-reentrant checkpoints replay the autocast state in the recomputation
