@@ -38,6 +38,23 @@ struct DwParams {
   int red_parts;   // second-stage partials of the pool reduction
 };
 
+// Squeeze-excite, first half, fused into the depthwise kernel's tail (inference): every CTA turns the pool sums of ITS
+// channel chunk and ITS images into partial hidden sums  hpart[b][slot][j] = sum_{c in chunk} w1[j][c] * mean[b][c]
+// (the squeeze layer is linear, so partial channel sums are enough), takes a ticket per image, and the CTA that arrives
+// LAST for an image adds the partials in fixed order (+ bias) into hid[b][:].  Wait-free: nobody spins on anybody, so
+// there is no co-residency requirement.  What is left of the gate is one small launch (the excite layer, se.cu) instead
+// of three dependent ones.
+struct SeFuse {
+  const float* w1;        // [sq][C] squeeze weight; nullptr = not fused
+  const float* b1;        // [sq]
+  float* hpart;           // [B][chunks * parts][sq] scratch
+  float* hid;             // [B][sq] out: hidden pre-activations (bias added, swish NOT applied)
+  unsigned int* tickets;  // [B], zero on entry; left zero on exit
+  int sq;
+  float inv_hw;
+};
+constexpr int kSeGroup = 16;   // images per tail round (bounds the tail's shared memory)
+
 // 8 channels of activations / weights as they sit in shared memory.
 template <typename T> struct Vec8;
 template <> struct Vec8<__nv_bfloat16> { uint4 r; };
@@ -138,7 +155,7 @@ template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool 
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        T* __restrict__ y, float* __restrict__ pool_partial,
-                                                       double* __restrict__ stats, DwParams p) {
+                                                       double* __restrict__ stats, DwParams p, SeFuse se) {
   constexpr bool kHalf = kFast && kAct && sizeof(T) == 2;
   const int CB = kCB ? kCB : p.CB;     // compile-time for the full-width chunk: shared-memory offsets become immediates
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -297,6 +314,67 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
     th_i = nth_i;
     b = nb;
   }
+  if constexpr (kAct && !kStats) {
+    if (se.w1 != nullptr && t_begin < t_end) {
+      // ---- fused squeeze (see SeFuse).  The tile buffers are free now: [ws: sq x (CB+1)] [ps: kSeGroup x CB] [flags]
+      __syncthreads();
+      const int sq = se.sq, WP = CB + 1;
+      float* ws = reinterpret_cast<float*>(smem_raw);
+      float* ps = ws + (size_t)sq * WP;
+      int* last_flag = reinterpret_cast<int*>(ps + kSeGroup * CB);
+      for (int i = tid; i < sq * CB; i += nth) {
+        const int jj = i / CB, o = i % CB;
+        ws[jj * WP + o] = (c0 + o < p.C) ? __ldg(se.w1 + (size_t)jj * p.C + c0 + o) : 0.f;
+      }
+      const int b_first = (int)(t_begin / n_tiles), b_last = (int)((t_end - 1) / n_tiles);
+      const int nslots = p.chunks * p.parts;
+      for (int g0 = b_first; g0 <= b_last; g0 += kSeGroup) {
+        const int ng = min(kSeGroup, b_last - g0 + 1);
+        for (int i = tid; i < ng * CB; i += nth) {       // this CTA's own pool sums (written above, visible after the barrier)
+          const int li = i / CB, o = i % CB, bb = g0 + li;
+          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
+          ps[i] = (c0 + o < p.C) ? pool_partial[((size_t)bb * p.parts + (size_t)(slot - first_cta)) * p.C + c0 + o] * se.inv_hw : 0.f;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < ng * sq; idx += nth) {
+          const int li = idx / sq, jj = idx % sq, bb = g0 + li;
+          const float* wr = ws + jj * WP;
+          const float* pr = ps + li * CB;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int o = 0; o < CB; ++o) acc = fmaf(wr[o], pr[o], acc);
+          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
+          se.hpart[((size_t)bb * nslots + (size_t)chunk * p.parts + (size_t)(slot - first_cta)) * sq + jj] = acc;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid < ng) {
+          const int bb = g0 + tid;
+          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
+          const long long last_cta = ((long long)(bb + 1) * n_tiles - 1) / p.tiles_per_cta;
+          const unsigned expected = (unsigned)(p.chunks * (last_cta - first_cta + 1));
+          last_flag[tid] = atomicAdd(se.tickets + bb, 1u) == expected - 1u;
+        }
+        __syncthreads();
+        for (int li = 0; li < ng; ++li) {
+          if (!last_flag[li]) continue;                  // CTA-uniform
+          const int bb = g0 + li;
+          __threadfence();
+          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
+          const long long last_cta = ((long long)(bb + 1) * n_tiles - 1) / p.tiles_per_cta;
+          const int ns = (int)(last_cta - first_cta + 1);
+          for (int jj = tid; jj < sq; jj += nth) {
+            float s = se.b1[jj];
+            for (int ch = 0; ch < p.chunks; ++ch)
+              for (int q = 0; q < ns; ++q) s += __ldcg(se.hpart + ((size_t)bb * nslots + (size_t)ch * p.parts + q) * sq + jj);
+            se.hid[(size_t)bb * sq + jj] = s;
+          }
+          if (tid == 0) se.tickets[bb] = 0u;             // ready for the next launch
+        }
+        __syncthreads();
+      }
+    }
+  }
   if constexpr (kStats) {
     // CTA reduction of the two statistics (same two-stage scheme as the pool flush), one double atomic per channel
     const int R = p.red_parts;
@@ -443,9 +521,19 @@ static void plan_grid(DwPlan& pl, int B) {
   pl.p.parts = (int)((n + tpc - 2) / tpc + 1);
 }
 
+// The fused squeeze tail reuses the two tile buffers: [sq x (CB+1)] weights + [kSeGroup x CB] pool means + flags.
+static bool se_tail_fits(const DwPlan& pl, int sq) {
+  const size_t ts_bytes = pl.smem;     // >= 2 tile buffers + the rest; recompute the tile part exactly as the kernel does
+  (void)ts_bytes;
+  const size_t tile_bytes_f32 = (size_t)pl.p.THI * pl.p.TWI * pl.p.CB;   // elements
+  const size_t two_tiles_min = 2 * ((tile_bytes_f32 * 2 + 127) / 128) * 128;    // bf16 (the smaller of the two dtypes)
+  const size_t need = ((size_t)sq * (pl.p.CB + 1) + (size_t)kSeGroup * pl.p.CB + kSeGroup) * sizeof(float);
+  return sq > 0 && sq <= 256 && need <= two_tiles_min;
+}
+
 template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats>
 static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, double* stats, DwPlan& pl, int B,
-                  cudaStream_t st) {
+                  cudaStream_t st, const SeFuse& se) {
   auto kern = dwconv_kernel<T, K, S, L, kFast, kAct, kCB, kStats>;
   static thread_local bool configured = false;
   if (!configured) {
@@ -456,23 +544,23 @@ static int launch(const CUtensorMap& tm, const float* w, const float* bias, void
   DFV_TRY(init_timeout_word_tu());
   plan_grid(pl, B);
   const unsigned grid = (unsigned)((long long)pl.p.ctas_per_chunk * pl.chunks);
-  kern<<<grid, pl.p.nthreads, pl.smem, st>>>(tm, w, bias, (T*)y, pool, stats, pl.p);
+  kern<<<grid, pl.p.nthreads, pl.smem, st>>>(tm, w, bias, (T*)y, pool, stats, pl.p, se);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
 
 template <typename T, bool kFast>
 static int dispatch(int K, int S, int L, int act, const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool,
-                    double* stats, DwPlan& pl, int B, cudaStream_t st) {
+                    double* stats, DwPlan& pl, int B, cudaStream_t st, const SeFuse& se) {
 #define DW_CASE(k, s, l)                                                                          \
   if (K == k && S == s && L == l) {                                                               \
-    if (stats) return launch<T, k, s, l, kFast, false, 0, true>(tm, w, bias, y, pool, stats, pl, B, st);    \
+    if (stats) return launch<T, k, s, l, kFast, false, 0, true>(tm, w, bias, y, pool, stats, pl, B, st, se);    \
     if (sizeof(T) == 2 && pl.p.CB == 64) {                                                                  \
-      if (act) return launch<T, k, s, l, kFast, true, 64, false>(tm, w, bias, y, pool, stats, pl, B, st);   \
-      return launch<T, k, s, l, kFast, false, 64, false>(tm, w, bias, y, pool, stats, pl, B, st);           \
+      if (act) return launch<T, k, s, l, kFast, true, 64, false>(tm, w, bias, y, pool, stats, pl, B, st, se);   \
+      return launch<T, k, s, l, kFast, false, 64, false>(tm, w, bias, y, pool, stats, pl, B, st, se);           \
     }                                                                                                       \
-    if (act) return launch<T, k, s, l, kFast, true, 0, false>(tm, w, bias, y, pool, stats, pl, B, st);      \
-    return launch<T, k, s, l, kFast, false, 0, false>(tm, w, bias, y, pool, stats, pl, B, st);              \
+    if (act) return launch<T, k, s, l, kFast, true, 0, false>(tm, w, bias, y, pool, stats, pl, B, st, se);      \
+    return launch<T, k, s, l, kFast, false, 0, false>(tm, w, bias, y, pool, stats, pl, B, st, se);              \
   }
   DW_CASE(3, 1, 8) DW_CASE(3, 1, 6) DW_CASE(3, 1, 4) DW_CASE(5, 1, 8) DW_CASE(5, 1, 6) DW_CASE(5, 1, 4)
   DW_CASE(3, 2, 4) DW_CASE(5, 2, 4)
@@ -516,7 +604,7 @@ extern "C" int dfv_dwconv_plan_info(int dtype, int B, int H, int W, int C, int k
 
 static int dwconv_entry(const void* x, const float* w, const float* bias, void* y, float* pool_partial, double* stats, int dtype,
                         int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act, dfv_stream_t stream,
-                        const dfv_dwconv_tuning* tuning = nullptr) {
+                        const dfv_dwconv_tuning* tuning = nullptr, const SeFuse* se_in = nullptr) {
   DFV_TRY(check_device());
   DFV_REQUIRE(x && w && bias && y, "dfv_dwconv_fwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype), "dfv_dwconv_fwd: bad dtype %d", dtype);
@@ -537,9 +625,14 @@ static int dwconv_entry(const void* x, const float* w, const float* bias, void* 
   DFV_TRY(make_tensor_map(&tm, dtype, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE));
   ProfScope prof(PK_DWCONV, ((double)B * H * W * C + (double)B * pl.p.Ho * pl.p.Wo * C) * es,
                  2.0 * kernel * kernel * (double)B * pl.p.Ho * pl.p.Wo * C, as_stream(stream));
+  SeFuse se = {};
+  if (se_in) {
+    DFV_REQUIRE(act == DFV_ACT_SILU && pool_partial && !stats && se_tail_fits(pl, se_in->sq), "dfv_dwconv_se_fwd: layer cannot fuse the squeeze (see dfv_dwconv_se_supported)");
+    se = *se_in;
+  }
   if (dtype == DFV_BF16)
-    return dispatch<__nv_bfloat16, true>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, stats, pl, B, as_stream(stream));
-  return dispatch<float, false>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, stats, pl, B, as_stream(stream));
+    return dispatch<__nv_bfloat16, true>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, stats, pl, B, as_stream(stream), se);
+  return dispatch<float, false>(kernel, stride, pl.L, act, tm, w, bias, y, pool_partial, stats, pl, B, as_stream(stream), se);
 }
 
 extern "C" int dfv_dwconv_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, int dtype,
@@ -552,6 +645,33 @@ extern "C" int dfv_dwconv_fwd_tuned(const void* x, const float* w, const float* 
                                     int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int act,
                                     const dfv_dwconv_tuning* tuning, dfv_stream_t stream) {
   return dwconv_entry(x, w, bias, y, pool_partial, nullptr, dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, act, stream, tuning);
+}
+
+/* Depthwise conv (+ folded BN + swish + SE pool sums) with the squeeze layer of the SE block fused into the kernel's tail:
+ * hid[b][j] = b_reduce[j] + sum_c w_reduce[j][c] * mean_hw(y[b][..][c])  (pre-swish hidden vector of the gate).
+ * hpart: dfv_dwconv_se_scratch_floats() floats of scratch; tickets: uint32 [B], ZERO on entry (left zero on exit). */
+extern "C" int dfv_dwconv_se_supported(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze) {
+  DwPlan pl;
+  if (!valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) return 0;
+  return se_tail_fits(pl, squeeze) ? 1 : 0;
+}
+
+extern "C" size_t dfv_dwconv_se_scratch_floats(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze) {
+  DwPlan pl;
+  if (!valid_dtype(dtype) || B <= 0 || squeeze <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) return 0;
+  plan_grid(pl, B);
+  return (size_t)B * pl.chunks * pl.p.parts * squeeze;
+}
+
+extern "C" int dfv_dwconv_se_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, const float* w_reduce,
+                                 const float* b_reduce, float* hpart, float* hid, unsigned int* tickets, int squeeze, int dtype, int B,
+                                 int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream) {
+  DFV_REQUIRE(w_reduce && b_reduce && hpart && hid && tickets && squeeze > 0 && pool_partial, "dfv_dwconv_se_fwd: null pointer");
+  const int Ho = (H + pad_lo + pad_hi - kernel) / stride + 1, Wo = (W + pad_lo + pad_hi - kernel) / stride + 1;
+  SeFuse se;
+  se.w1 = w_reduce; se.b1 = b_reduce; se.hpart = hpart; se.hid = hid; se.tickets = tickets; se.sq = squeeze;
+  se.inv_hw = 1.0f / (float)((long long)Ho * Wo);
+  return dwconv_entry(x, w, bias, y, pool_partial, nullptr, dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, DFV_ACT_SILU, stream, nullptr, &se);
 }
 
 /* Training forward: raw depthwise conv (no activation) that also ADDS the per-channel sum and sum of squares of its

@@ -72,6 +72,35 @@ extern "C" int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_h
                           nullptr, nullptr, nullptr, scratch, as_stream(stream));
 }
 
+/* Second half of the gate when the squeeze layer ran inside the depthwise kernel (dfv_dwconv_se_fwd):
+ * gate[b][c] = sigmoid(b_expand[c] + sum_j w_expand_t[j][c] * swish(hid[b][j])). */
+extern "C" int dfv_se_excite_fwd(const float* hid, const float* w_expand_t, const float* b_expand, void* gate, int gate_dtype, int B, int C,
+                                 int squeeze, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(hid && w_expand_t && b_expand && gate, "dfv_se_excite_fwd: null pointer");
+  DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && valid_dtype(gate_dtype), "dfv_se_excite_fwd: bad shape / dtype");
+  if (debug_flags() & 2) return DFV_OK;
+  cudaStream_t st = as_stream(stream);
+  const size_t smem_b = sl_kmajor_smem(squeeze);
+  DFV_REQUIRE(smem_b <= 100 * 1024, "dfv_se_excite_fwd: squeeze width %d too large", squeeze);
+  static thread_local bool configured = false;
+  if (!configured) {
+    DFV_CUDA(cudaFuncSetAttribute(sl_kmajor_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(sl_kmajor_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * squeeze + (double)C * squeeze) + (double)dtype_size(gate_dtype) * B * C, 2.0 * B * (double)C * squeeze, st);
+  const dim3 grid_b((unsigned)((C + kSlCols - 1) / kSlCols), (unsigned)((B + kSlRows - 1) / kSlRows));
+  if (gate_dtype == DFV_BF16)
+    DFV_PDL((sl_kmajor_kernel<__nv_bfloat16, false>), grid_b, kSlThreads, smem_b, st, hid, w_expand_t, b_expand, (__nv_bfloat16*)gate,
+            (float*)nullptr, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID);
+  else
+    DFV_PDL((sl_kmajor_kernel<float, false>), grid_b, kSlThreads, smem_b, st, hid, w_expand_t, b_expand, (float*)gate, (float*)nullptr,
+            (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
 /* Training variant (declared in dfvit.h next to the other training entry points): torch-layout weights, saves pooled / h1 /
  * fp32 gate for dfv_se_bwd. */
 extern "C" int dfv_se_train_fwd(const float* pool_partial, int parts, float inv_hw, const float* w_reduce, const float* b_reduce,

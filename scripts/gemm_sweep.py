@@ -1,52 +1,67 @@
-"""Time the tensor-core 1x1-conv GEMM for the B4 layer shapes under forced tile plans and check every plan against a
-torch fp32 matmul (DFV_GEMM_FORCE="weight_stationary,BN" is read per call)."""
-import os, sys
+"""Measured tile-plan search for the tcgen05 1x1-conv GEMM: every distinct expand / project / head GEMM of B4 at batch 256
+under the planner's choice and under restricted plans (per-call dfv_gemm_tuning: weight-stationary flag, N tile)."""
+import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import deepfake_vit_b200 as d
-ops = d.ops
-B = 256
-# (name, M, K, N, gated, rows_per_image, act, residual) after row folding
-L = [("b1 project", 2310400, 96, 96, 1, 9025, 0, 1), ("b2 expand", 2310400, 96, 576, 0, 0, 1, 0), ("b3 expand", 1155200, 64, 384, 0, 0, 1, 0),
-     ("b3 project", 2310400, 192, 32, 1, 9025, 0, 1), ("b7 expand", 589824, 56, 336, 0, 0, 1, 0), ("b7 project", 589824, 336, 56, 1, 2304, 0, 1),
-     ("b11 expand", 147456, 112, 672, 0, 0, 1, 0), ("b11 project", 147456, 672, 112, 1, 576, 0, 1), ("b17 expand", 147456, 160, 960, 0, 0, 1, 0),
-     ("b17 project", 147456, 960, 160, 1, 576, 0, 1), ("b23 expand", 36864, 272, 1632, 0, 0, 1, 0), ("b23 project", 36864, 1632, 272, 1, 144, 0, 1),
-     ("b31 expand", 36864, 448, 2688, 0, 0, 1, 0), ("b31 project", 36864, 2688, 448, 1, 144, 0, 1), ("head", 36864, 448, 1792, 0, 0, 1, 0)]
-only = sys.argv[1:]
-for (name, M, K, N, g, rpi, act, res) in L:
-    if only and not any(o in name for o in only): continue
-    torch.manual_seed(0)
-    a = torch.randn(M, K, device="cuda").bfloat16()
-    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
-    bias = torch.randn(N, device="cuda") * 0.1
-    sc = torch.rand(M // rpi, K, device="cuda").bfloat16() if g else None
-    r = torch.randn(M, N, device="cuda").bfloat16() if res else None
-    # reference on a row sample
-    idx = torch.cat([torch.arange(0, min(M, 300), device="cuda"), torch.randint(0, M, (1500,), device="cuda"), torch.arange(M - 300, M, device="cuda")])
-    av = a[idx].float()
-    if g: av = (a[idx] * sc[idx // rpi]).float()
-    ref = av @ w.float().t() + bias
-    if act: ref = ref * torch.sigmoid(ref)
-    if res: ref = ref + r[idx].float()
-    parts = 2 if g else 4
-    bns = [parts * c for c in (16, 32, 48, 64, 96, 128) if parts * c <= 256]
-    out = []
-    os.environ["DFV_GEMM_FORCE"] = "-1,0"
-    for _ in range(10): ops.pw_gemm(a, w, bias, act=act, a_scale=sc, rows_per_image=rpi, residual=r)     # clocks up
-    for cfg in ["-1,0"] + [f"0,{bn}" for bn in bns] + [f"1,{bn}" for bn in bns]:
-        os.environ["DFV_GEMM_FORCE"] = cfg
-        try:
-            y = ops.pw_gemm(a, w, bias, act=act, a_scale=sc, rows_per_image=rpi, residual=r)
-            err = ((y[idx].float() - ref).abs() / (ref.abs() + 1.0)).max().item()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5): ops.pw_gemm(a, w, bias, act=act, a_scale=sc, rows_per_image=rpi, residual=r)
-            e1.record(); torch.cuda.synchronize()
-            out.append((e0.elapsed_time(e1) / 5 * 1000, cfg, err))
-        except Exception as ex:
-            if "fit" not in str(ex): print("   ", cfg, "failed:", str(ex)[:120])
-    auto = out[0]
-    out.sort()
-    bad = [(c, round(e, 4)) for t, c, e in out if e > 2e-2]
-    print(f"{name:12s} M={M} K={K} N={N}: auto {auto[0]:.0f} us; best:", [(round(t), c) for t, c, e in out[:5]], "BAD" if bad else "ok", bad)
+
+ops, lib, DEV = d.ops, d._lib.lib, "cuda"
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+shapes, seen, h = [], set(), 190
+for b in d._lib.b4_blocks():
+    ho = (h + b.pad_lo + b.pad_hi - b.kernel) // b.stride + 1
+    cand = []
+    if b.has_expand:
+        cand.append((B * h * h, b.c_in, b.c_mid, False, h * h))
+    cand.append((B * ho * ho, b.c_mid, b.c_out, True, ho * ho))
+    for c in cand:
+        if c not in seen and c[1] > 48:          # thin layers run row-folded (another plan family)
+            seen.add(c); shapes.append(c)
+    h = ho
+shapes.append((B * 144, 448, 1792, False, 144))
+
+
+def timed(fn, iters=5):
+    for _ in range(2):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+g = torch.Generator(device=DEV).manual_seed(0)
+report = {}
+for (M, K, N, gated, rpi) in shapes:
+    a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    sc = torch.rand(M // rpi, K, device=DEV, generator=g).bfloat16() if gated else None
+    act = 0 if gated else 1
+    run = lambda tn=None: ops.pw_gemm(a, w, bias, act, sc, rpi if gated else 0, None, tuning=tn)
+    ref = run()
+    info = (C.c_int * 8)()
+    lib.dfv_gemm_plan_info(C.c_longlong(M), K, N, int(gated), info)
+    base = timed(run)
+    res = []
+    for ws in ((0,) if gated else (0, 1)):
+        for bn in ((32, 64, 96, 128, 192, 256) if gated else (64, 128, 192, 256)):
+            try:
+                y = run((ws, bn))
+            except Exception:
+                continue
+            chk = (C.c_int * 8)()
+            if not torch.equal(y, ref) and (y.float() - ref.float()).abs().max().item() > 0.05:
+                print("MISMATCH", (M, K, N, gated), (ws, bn), flush=True)
+                continue
+            res.append((timed(lambda: run((ws, bn)), 3), (ws, bn)))
+    res.sort()
+    nbytes = 2.0 * (M * K + M * N + N * K)
+    key = f"M{M} K{K} N{N} {'gated' if gated else 'silu'}"
+    report[key] = dict(planner=dict(bn=info[0], ws=info[1], us=base * 1e3, gbs=nbytes / base / 1e6, tflops=2.0 * M * K * N / base / 1e9),
+                       best=[dict(plan=p, us=ms * 1e3) for ms, p in res[:4]])
+    print(f"{key}: planner bn={info[0]} ws={info[1]} {base*1e3:.0f} us | " + ", ".join(f"{p} {ms*1e3:.0f}" for ms, p in res[:4]), flush=True)
+    del a, ref
+print(json.dumps(report))

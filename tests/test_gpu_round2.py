@@ -380,3 +380,43 @@ def test_predict_runs_without_autograd_state_and_modes_are_checked():
         m(x[:1])
     out, _ = m(x)
     assert torch.isfinite(out).all()
+
+
+# ------------------------------------------------------------------------------------------------ fused squeeze
+@pytest.mark.parametrize("cfg", [(256, 1632, 12, 5, 1, 2, 2, 68), (64, 336, 48, 5, 1, 2, 2, 14), (8, 48, 190, 3, 1, 1, 1, 12),
+                                 (3, 144, 190, 3, 2, 0, 1, 6), (37, 960, 24, 5, 2, 1, 2, 40), (256, 2688, 12, 3, 1, 1, 1, 112),
+                                 (5, 672, 24, 3, 1, 1, 1, 28)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_depthwise_kernel_with_fused_squeeze(cfg, dtype):
+    """dfv_dwconv_se_fwd: same y / pool sums as the plain kernel (bit for bit), hid = b1 + W1 . mean(y) against torch,
+    tickets back to zero, identical results on a second launch (fixed summation order); then the one-launch excite
+    against the three-launch gate."""
+    import deepfake_vit_b200 as d
+    ops = d.ops
+    B, C_, H, k, s, pl, ph, sq = cfg
+    if dtype == torch.float32 and B * C_ * H * H > 3e8:
+        B = 16
+    g = torch.Generator(device=DEV).manual_seed(31)
+    x = torch.randn(B, H, H, C_, device=DEV, generator=g).to(dtype)
+    w = torch.randn(k * k, C_, device=DEV, generator=g) * 0.2
+    bias = torch.randn(C_, device=DEV, generator=g) * 0.1
+    w1 = torch.randn(sq, C_, device=DEV, generator=g) / C_ ** 0.5
+    b1 = torch.randn(sq, device=DEV, generator=g) * 0.1
+    w2t = torch.randn(sq, C_, device=DEV, generator=g) / sq ** 0.5
+    b2 = torch.randn(C_, device=DEV, generator=g) * 0.1
+    y_ref, pool_ref = ops.dwconv(x, w, bias, k, s, pl, ph)
+    y, pool, hid, tickets = ops.dwconv_se(x, w, bias, k, s, pl, ph, w1, b1)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref) and torch.equal(pool, pool_ref)
+    assert int(tickets.abs().sum()) == 0
+    hw = y.shape[1] * y.shape[2]
+    mean = pool_ref.double().sum(1) / hw
+    want = b1.double() + mean @ w1.double().t()
+    assert rel(hid, want) < 2e-6, rel(hid, want)
+    y2, pool2, hid2, _ = ops.dwconv_se(x, w, bias, k, s, pl, ph, w1, b1)
+    assert torch.equal(hid2, hid)
+    gate = ops.se_excite(hid, w2t, b2, dtype)
+    gate_ref = ops.se_gate(pool_ref, hw, w1, b1, w2t, b2, dtype)
+    assert (gate.float() - gate_ref.float()).abs().max().item() < (8e-3 if dtype == torch.bfloat16 else 1e-5)
+    hsw = want * torch.sigmoid(want)
+    assert rel(gate.float(), torch.sigmoid(b2.double() + hsw @ w2t.double())) < (4e-3 if dtype == torch.bfloat16 else 1e-5)
