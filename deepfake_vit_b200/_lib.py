@@ -122,9 +122,8 @@ def _load():
         "dfv_dwconv_pool_parts": (C.c_int, [i32] * 9),
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
         "dfv_dwconv_se_supported": (C.c_int, [i32] * 10),
-        "dfv_dwconv_se_scratch_floats": (sz, [i32] * 10),
-        "dfv_dwconv_se_fwd": (C.c_int, [vp] * 10 + [i32] * 11 + [vp]),
-        "dfv_se_excite_fwd": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+        "dfv_dwconv_se_fwd": (C.c_int, [vp] * 8 + [i64] + [i32] * 10 + [vp]),
+        "dfv_se_excite_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "dfv_se_scratch_floats": (sz, [i32, i32, i32]),
         "dfv_se_gate_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp]),
         "dfv_pw_gemm_fwd": (C.c_int, [vp, vp, vp, vp, i32, vp, vp, i32, i64, i32, i32, i32, vp]),

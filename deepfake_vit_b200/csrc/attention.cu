@@ -306,7 +306,7 @@ static int launch_attention(const T* fmap, const float* heat, const float* ca_w1
             (const float*)part_m, ks, (const float*)nullptr, hid, B, hidden, 1);
     const dim3 grid_b((unsigned)((C + kSlCols - 1) / kSlCols), (unsigned)((B + kSlRows - 1) / kSlRows));
     DFV_PDL((sl_kmajor_kernel<float, false>), grid_b, kSlThreads, sl_kmajor_smem(hidden), st, (const float*)hid, ca_w2_t, (const float*)nullptr,
-            gate_c, (float*)nullptr, (float*)nullptr, B, C, hidden, hidden, 0, SL_OUT_SIGMOID);
+            gate_c, (float*)nullptr, (float*)nullptr, B, C, hidden, hidden, 0, SL_OUT_SIGMOID, (const long long*)nullptr, (const float*)nullptr, 1.0f);
     count_launch(4);
   }
   const float* gc = use_channel ? gate_c : nullptr;

@@ -39,21 +39,22 @@ struct DwParams {
 };
 
 // Squeeze-excite, first half, fused into the depthwise kernel's tail (inference): every CTA turns the pool sums of ITS
-// channel chunk and ITS images into partial hidden sums  hpart[b][slot][j] = sum_{c in chunk} w1[j][c] * mean[b][c]
-// (the squeeze layer is linear, so partial channel sums are enough), takes a ticket per image, and the CTA that arrives
-// LAST for an image adds the partials in fixed order (+ bias) into hid[b][:].  Wait-free: nobody spins on anybody, so
-// there is no co-residency requirement.  What is left of the gate is one small launch (the excite layer, se.cu) instead
-// of three dependent ones.
+// channel chunk and ITS images into partial hidden sums  sum_{c in chunk} w1[j][c] * mean[b][c]  (the squeeze layer is
+// linear, so partial channel sums are enough) and ADDS them into hid[b][j] with 64-bit FIXED-POINT atomics (2^-30
+// resolution): integer addition is associative, so the result does not depend on the order in which CTAs arrive --
+// bit-reproducible without tickets, finalize passes or any CTA waiting on another.  What is left of the gate is one
+// small launch (the excite layer, se.cu) instead of three dependent ones.  The accumulator of the NEXT layer is zeroed
+// in this kernel's prologue (two buffers alternate; nobody reads the other one while this kernel runs).
 struct SeFuse {
-  const float* w1;        // [sq][C] squeeze weight; nullptr = not fused
-  const float* b1;        // [sq]
-  float* hpart;           // [B][chunks * parts][sq] scratch
-  float* hid;             // [B][sq] out: hidden pre-activations (bias added, swish NOT applied)
-  unsigned int* tickets;  // [B], zero on entry; left zero on exit
+  const float* w1;          // [sq][C] squeeze weight; nullptr = not fused
+  long long* hid_fix;       // [B][sq] fixed-point accumulators, zero on entry
+  long long* zero_next;     // buffer to zero for the next fused layer (zero_count entries), may be nullptr
+  long long zero_count;
   int sq;
   float inv_hw;
 };
-constexpr int kSeGroup = 16;   // images per tail round (bounds the tail's shared memory)
+constexpr int kSeGroup = 16;             // images per tail round (bounds the tail's shared memory)
+constexpr float kSeFixScale = 1073741824.0f;   // 2^30
 
 // 8 channels of activations / weights as they sit in shared memory.
 template <typename T> struct Vec8;
@@ -197,6 +198,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
     if constexpr (sizeof(T) == 2) wsm[i] = __float2bfloat16_rn(v); else wsm[i] = v;
   }
   for (int i = tid; i < CB; i += blockDim.x) bsm[i] = (c0 + i < p.C) ? fold * bias[c0 + i] : 0.f;
+  if constexpr (kAct && !kStats) {
+    if (se.zero_next != nullptr)
+      for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < se.zero_count; i += (long long)gridDim.x * blockDim.x) se.zero_next[i] = 0;
+  }
   __syncthreads();
 
   // fixed per-thread role
@@ -316,18 +321,16 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   }
   if constexpr (kAct && !kStats) {
     if (se.w1 != nullptr && t_begin < t_end) {
-      // ---- fused squeeze (see SeFuse).  The tile buffers are free now: [ws: sq x (CB+1)] [ps: kSeGroup x CB] [flags]
+      // ---- fused squeeze (see SeFuse).  The tile buffers are free now: [ws: sq x (CB+1)] [ps: kSeGroup x CB]
       __syncthreads();
       const int sq = se.sq, WP = CB + 1;
       float* ws = reinterpret_cast<float*>(smem_raw);
       float* ps = ws + (size_t)sq * WP;
-      int* last_flag = reinterpret_cast<int*>(ps + kSeGroup * CB);
       for (int i = tid; i < sq * CB; i += nth) {
         const int jj = i / CB, o = i % CB;
         ws[jj * WP + o] = (c0 + o < p.C) ? __ldg(se.w1 + (size_t)jj * p.C + c0 + o) : 0.f;
       }
       const int b_first = (int)(t_begin / n_tiles), b_last = (int)((t_end - 1) / n_tiles);
-      const int nslots = p.chunks * p.parts;
       for (int g0 = b_first; g0 <= b_last; g0 += kSeGroup) {
         const int ng = min(kSeGroup, b_last - g0 + 1);
         for (int i = tid; i < ng * CB; i += nth) {       // this CTA's own pool sums (written above, visible after the barrier)
@@ -337,39 +340,17 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
         }
         __syncthreads();
         for (int idx = tid; idx < ng * sq; idx += nth) {
-          const int li = idx / sq, jj = idx % sq, bb = g0 + li;
+          const int li = idx / sq, jj = idx % sq;
           const float* wr = ws + jj * WP;
           const float* pr = ps + li * CB;
-          float acc = 0.f;
-#pragma unroll 8
-          for (int o = 0; o < CB; ++o) acc = fmaf(wr[o], pr[o], acc);
-          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
-          se.hpart[((size_t)bb * nslots + (size_t)chunk * p.parts + (size_t)(slot - first_cta)) * sq + jj] = acc;
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid < ng) {
-          const int bb = g0 + tid;
-          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
-          const long long last_cta = ((long long)(bb + 1) * n_tiles - 1) / p.tiles_per_cta;
-          const unsigned expected = (unsigned)(p.chunks * (last_cta - first_cta + 1));
-          last_flag[tid] = atomicAdd(se.tickets + bb, 1u) == expected - 1u;
-        }
-        __syncthreads();
-        for (int li = 0; li < ng; ++li) {
-          if (!last_flag[li]) continue;                  // CTA-uniform
-          const int bb = g0 + li;
-          __threadfence();
-          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
-          const long long last_cta = ((long long)(bb + 1) * n_tiles - 1) / p.tiles_per_cta;
-          const int ns = (int)(last_cta - first_cta + 1);
-          for (int jj = tid; jj < sq; jj += nth) {
-            float s = se.b1[jj];
-            for (int ch = 0; ch < p.chunks; ++ch)
-              for (int q = 0; q < ns; ++q) s += __ldcg(se.hpart + ((size_t)bb * nslots + (size_t)ch * p.parts + q) * sq + jj);
-            se.hid[(size_t)bb * sq + jj] = s;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          for (int o = 0; o < CB; o += 4) {
+            a0 = fmaf(wr[o], pr[o], a0); a1 = fmaf(wr[o + 1], pr[o + 1], a1);
+            a2 = fmaf(wr[o + 2], pr[o + 2], a2); a3 = fmaf(wr[o + 3], pr[o + 3], a3);
           }
-          if (tid == 0) se.tickets[bb] = 0u;             // ready for the next launch
+          const float acc = (a0 + a1) + (a2 + a3);
+          atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + li) * sq + jj),
+                    (unsigned long long)__float2ll_rn(acc * kSeFixScale));
         }
         __syncthreads();
       }
@@ -527,7 +508,7 @@ static bool se_tail_fits(const DwPlan& pl, int sq) {
   (void)ts_bytes;
   const size_t tile_bytes_f32 = (size_t)pl.p.THI * pl.p.TWI * pl.p.CB;   // elements
   const size_t two_tiles_min = 2 * ((tile_bytes_f32 * 2 + 127) / 128) * 128;    // bf16 (the smaller of the two dtypes)
-  const size_t need = ((size_t)sq * (pl.p.CB + 1) + (size_t)kSeGroup * pl.p.CB + kSeGroup) * sizeof(float);
+  const size_t need = ((size_t)sq * (pl.p.CB + 1) + (size_t)kSeGroup * pl.p.CB) * sizeof(float);
   return sq > 0 && sq <= 256 && need <= two_tiles_min;
 }
 
@@ -648,28 +629,22 @@ extern "C" int dfv_dwconv_fwd_tuned(const void* x, const float* w, const float* 
 }
 
 /* Depthwise conv (+ folded BN + swish + SE pool sums) with the squeeze layer of the SE block fused into the kernel's tail:
- * hid[b][j] = b_reduce[j] + sum_c w_reduce[j][c] * mean_hw(y[b][..][c])  (pre-swish hidden vector of the gate).
- * hpart: dfv_dwconv_se_scratch_floats() floats of scratch; tickets: uint32 [B], ZERO on entry (left zero on exit). */
+ * hid_fix[b][j] += round(2^30 * sum_c w_reduce[j][c] * mean_hw(y[b][..][c]))  (64-bit fixed-point accumulators, zero on entry;
+ * the bias is added by dfv_se_excite_fwd).  zero_next / zero_count: a buffer this launch zeroes for the next fused layer. */
 extern "C" int dfv_dwconv_se_supported(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze) {
   DwPlan pl;
   if (!valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) return 0;
   return se_tail_fits(pl, squeeze) ? 1 : 0;
 }
 
-extern "C" size_t dfv_dwconv_se_scratch_floats(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze) {
-  DwPlan pl;
-  if (!valid_dtype(dtype) || B <= 0 || squeeze <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) return 0;
-  plan_grid(pl, B);
-  return (size_t)B * pl.chunks * pl.p.parts * squeeze;
-}
-
 extern "C" int dfv_dwconv_se_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, const float* w_reduce,
-                                 const float* b_reduce, float* hpart, float* hid, unsigned int* tickets, int squeeze, int dtype, int B,
-                                 int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream) {
-  DFV_REQUIRE(w_reduce && b_reduce && hpart && hid && tickets && squeeze > 0 && pool_partial, "dfv_dwconv_se_fwd: null pointer");
+                                 long long* hid_fix, long long* zero_next, long long zero_count, int squeeze, int dtype, int B, int H, int W,
+                                 int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream) {
+  DFV_REQUIRE(w_reduce && hid_fix && squeeze > 0 && pool_partial, "dfv_dwconv_se_fwd: null pointer");
+  DFV_REQUIRE(zero_next != hid_fix && zero_count >= 0, "dfv_dwconv_se_fwd: the buffer to zero must not be the live accumulator");
   const int Ho = (H + pad_lo + pad_hi - kernel) / stride + 1, Wo = (W + pad_lo + pad_hi - kernel) / stride + 1;
   SeFuse se;
-  se.w1 = w_reduce; se.b1 = b_reduce; se.hpart = hpart; se.hid = hid; se.tickets = tickets; se.sq = squeeze;
+  se.w1 = w_reduce; se.hid_fix = hid_fix; se.zero_next = zero_next; se.zero_count = zero_next ? zero_count : 0; se.sq = squeeze;
   se.inv_hw = 1.0f / (float)((long long)Ho * Wo);
   return dwconv_entry(x, w, bias, y, pool_partial, nullptr, dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, DFV_ACT_SILU, stream, nullptr, &se);
 }

@@ -59,7 +59,7 @@ extern "C" int dfv_mlp_head_fwd(const float* features, const float* const* w_t, 
     const dim3 grid((unsigned)((dout + kSlCols - 1) / kSlCols), (unsigned)((B + kSlRows - 1) / kSlRows), (unsigned)ks);
     // one K slice: bias and ReLU in the kernel; several: raw partial sums, finished by the combine pass
     DFV_PDL((sl_kmajor_kernel<float, false>), grid, kSlThreads, sl_kmajor_smem(kc), st, in, w_t[l], b[l], out, (float*)nullptr, part, B, dout,
-            din, kc, 0, last ? 0 : SL_OUT_RELU);
+            din, kc, 0, last ? 0 : SL_OUT_RELU, (const long long*)nullptr, (const float*)nullptr, 1.0f);
     DFV_LAUNCH_CHECK();
     if (ks > 1) {
       DFV_PDL(sl_combine_kernel, (unsigned)(((size_t)B * dout + kSlThreads - 1) / kSlThreads), kSlThreads, 0, st, (const float*)part,

@@ -18,7 +18,6 @@ struct Shapes {
   size_t pool_floats;         // per image: max parts * c_mid
   int max_cmid;
   size_t se_scratch_floats;   // whole batch: max over blocks of dfv_se_scratch_floats
-  size_t se_hpart_floats;     // whole batch: max over blocks of dfv_dwconv_se_scratch_floats (fused squeeze)
   int max_sq;
   bool se_fused[64];          // block runs the squeeze layer inside its depthwise kernel
 };
@@ -33,7 +32,6 @@ static int compute_shapes(Shapes* s, int dtype, int B, int H, int W) {
   s->exp_elems = s->dw_elems = s->pool_floats = 0;
   s->max_cmid = 0;
   s->se_scratch_floats = 0;
-  s->se_hpart_floats = 0;
   s->max_sq = 1;
   for (int i = 0; i < n; ++i) {
     const dfv_block_info& b = blk[i];
@@ -53,8 +51,6 @@ static int compute_shapes(Shapes* s, int dtype, int B, int H, int W) {
     s->max_cmid = std::max(s->max_cmid, b.c_mid);
     s->se_scratch_floats = std::max(s->se_scratch_floats, dfv_se_scratch_floats(B, b.c_mid, b.se_squeeze));
     s->se_fused[i] = dfv_dwconv_se_supported(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, b.se_squeeze) != 0;
-    if (s->se_fused[i])
-      s->se_hpart_floats = std::max(s->se_hpart_floats, dfv_dwconv_se_scratch_floats(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, b.se_squeeze));
     s->max_sq = std::max(s->max_sq, b.se_squeeze);
     h = ho;
     w = wo;
@@ -72,9 +68,7 @@ struct Workspace {
   float* pool;
   void* gate;
   float* se_scratch;       // squeeze partial sums between the two SE kernels
-  float* se_hpart;         // fused squeeze: per-CTA partial hidden sums
-  float* se_hid;           // fused squeeze: hidden pre-activations [B][squeeze]
-  unsigned int* se_tickets;   // fused squeeze: one arrival counter per image (zero between launches)
+  long long* se_hid[2];    // fused squeeze: fixed-point hidden accumulators [B][squeeze], two buffers alternating by layer
   float* heat;
   float* heat_raw;
   uint32_t* heat_max;
@@ -103,9 +97,8 @@ static void carve(Workspace* ws, char* base, const Shapes& s, int dtype, int B) 
   ws->pool = (float*)take((size_t)B * s.pool_floats * 4);
   ws->gate = take((size_t)B * s.max_cmid * 4);
   ws->se_scratch = (float*)take(s.se_scratch_floats * 4);
-  ws->se_hpart = (float*)take(s.se_hpart_floats * 4);
-  ws->se_hid = (float*)take((size_t)B * s.max_sq * 4);
-  ws->se_tickets = (unsigned int*)take((size_t)B * 4);
+  ws->se_hid[0] = (long long*)take((size_t)B * s.max_sq * 8);
+  ws->se_hid[1] = (long long*)take((size_t)B * s.max_sq * 8);
   ws->heat = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_raw = (float*)take((size_t)B * s.Hf * s.Wf * 4);
   ws->heat_max = (uint32_t*)take((size_t)B * 4);
@@ -157,8 +150,10 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
     return DFV_OK;
   };
 
-  // arrival counters of the fused squeeze: zero on entry (the kernels leave them zero; a faulted launch might not)
-  DFV_CUDA(cudaMemsetAsync(ws.se_tickets, 0, sizeof(unsigned int) * (size_t)B, st));
+  // fixed-point accumulators of the fused squeeze: the first layer's buffer is zeroed here, every later one by the
+  // depthwise kernel of the layer before it
+  DFV_CUDA(cudaMemsetAsync(ws.se_hid[0], 0, sizeof(long long) * (size_t)B * s.max_sq, st));
+  int se_buf = 0;
   int cur = 0;
   if (a->images_u8)     // raw uint8 HWC crops: the reference's input normalisation runs inside the stem's operand load
     DFV_TRY(dfv_stem_conv_u8_fwd(a->images_u8, a->u8_norm, (const float*)W_(-1, DFV_W_STEM), (const float*)W_(-1, DFV_W_STEM_BIAS),
@@ -181,10 +176,11 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
     const int parts = dfv_dwconv_pool_parts(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi);
     if (s.se_fused[i]) {      // squeeze layer in the depthwise kernel's tail; one launch left for the gate
       DFV_TRY(dfv_dwconv_se_fwd(dw_in, (const float*)W_(i, DFV_W_DW), (const float*)W_(i, DFV_W_DW_BIAS), ws.dw, ws.pool,
-                                (const float*)W_(i, DFV_W_SE_REDUCE), (const float*)W_(i, DFV_W_SE_REDUCE_BIAS), ws.se_hpart, ws.se_hid,
-                                ws.se_tickets, b.se_squeeze, dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, stream));
-      DFV_TRY(dfv_se_excite_fwd(ws.se_hid, (const float*)W_(i, DFV_W_SE_EXPAND), (const float*)W_(i, DFV_W_SE_EXPAND_BIAS), ws.gate, dtype, B,
-                                b.c_mid, b.se_squeeze, stream));
+                                (const float*)W_(i, DFV_W_SE_REDUCE), ws.se_hid[se_buf], ws.se_hid[se_buf ^ 1], (long long)B * s.max_sq,
+                                b.se_squeeze, dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, stream));
+      DFV_TRY(dfv_se_excite_fwd(ws.se_hid[se_buf], (const float*)W_(i, DFV_W_SE_REDUCE_BIAS), (const float*)W_(i, DFV_W_SE_EXPAND),
+                                (const float*)W_(i, DFV_W_SE_EXPAND_BIAS), ws.gate, dtype, B, b.c_mid, b.se_squeeze, stream));
+      se_buf ^= 1;
     } else {
       DFV_TRY(dfv_dwconv_fwd(dw_in, (const float*)W_(i, DFV_W_DW), (const float*)W_(i, DFV_W_DW_BIAS), ws.dw, ws.pool, dtype, B, h,
                              w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, DFV_ACT_SILU, stream));

@@ -42,10 +42,10 @@ static int launch_se(const float* pool_partial, int parts, float inv_hw, const f
           (const float*)nullptr, ksplit, b_reduce, hid, B, squeeze, 0);
   if (gate_dtype == DFV_BF16)
     DFV_PDL((sl_kmajor_kernel<__nv_bfloat16, kTrain>), grid_b, kSlThreads, smem_b, st, (const float*)hid, w_expand, b_expand,
-            (__nv_bfloat16*)gate, gate_f32, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID);
+            (__nv_bfloat16*)gate, gate_f32, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID, (const long long*)nullptr, (const float*)nullptr, 1.0f);
   else
     DFV_PDL((sl_kmajor_kernel<float, kTrain>), grid_b, kSlThreads, smem_b, st, (const float*)hid, w_expand, b_expand, (float*)gate,
-            gate_f32, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID);
+            gate_f32, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID, (const long long*)nullptr, (const float*)nullptr, 1.0f);
   count_launch(2);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
@@ -73,11 +73,11 @@ extern "C" int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_h
 }
 
 /* Second half of the gate when the squeeze layer ran inside the depthwise kernel (dfv_dwconv_se_fwd):
- * gate[b][c] = sigmoid(b_expand[c] + sum_j w_expand_t[j][c] * swish(hid[b][j])). */
-extern "C" int dfv_se_excite_fwd(const float* hid, const float* w_expand_t, const float* b_expand, void* gate, int gate_dtype, int B, int C,
-                                 int squeeze, dfv_stream_t stream) {
+ * hid = b_reduce + 2^-30 * hid_fix;  gate[b][c] = sigmoid(b_expand[c] + sum_j w_expand_t[j][c] * swish(hid[b][j])). */
+extern "C" int dfv_se_excite_fwd(const long long* hid_fix, const float* b_reduce, const float* w_expand_t, const float* b_expand, void* gate,
+                                 int gate_dtype, int B, int C, int squeeze, dfv_stream_t stream) {
   DFV_TRY(check_device());
-  DFV_REQUIRE(hid && w_expand_t && b_expand && gate, "dfv_se_excite_fwd: null pointer");
+  DFV_REQUIRE(hid_fix && b_reduce && w_expand_t && b_expand && gate, "dfv_se_excite_fwd: null pointer");
   DFV_REQUIRE(B > 0 && C > 0 && squeeze > 0 && valid_dtype(gate_dtype), "dfv_se_excite_fwd: bad shape / dtype");
   if (debug_flags() & 2) return DFV_OK;
   cudaStream_t st = as_stream(stream);
@@ -89,14 +89,15 @@ extern "C" int dfv_se_excite_fwd(const float* hid, const float* w_expand_t, cons
     DFV_CUDA(cudaFuncSetAttribute(sl_kmajor_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
-  ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * squeeze + (double)C * squeeze) + (double)dtype_size(gate_dtype) * B * C, 2.0 * B * (double)C * squeeze, st);
+  ProfScope prof(PK_SE_GATE, 8.0 * B * squeeze + 4.0 * (double)C * squeeze + (double)dtype_size(gate_dtype) * B * C, 2.0 * B * (double)C * squeeze, st);
   const dim3 grid_b((unsigned)((C + kSlCols - 1) / kSlCols), (unsigned)((B + kSlRows - 1) / kSlRows));
+  const float inv_scale = 1.0f / 1073741824.0f;    // dwconv.cu kSeFixScale
   if (gate_dtype == DFV_BF16)
-    DFV_PDL((sl_kmajor_kernel<__nv_bfloat16, false>), grid_b, kSlThreads, smem_b, st, hid, w_expand_t, b_expand, (__nv_bfloat16*)gate,
-            (float*)nullptr, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID);
+    DFV_PDL((sl_kmajor_kernel<__nv_bfloat16, false>), grid_b, kSlThreads, smem_b, st, (const float*)nullptr, w_expand_t, b_expand,
+            (__nv_bfloat16*)gate, (float*)nullptr, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID, hid_fix, b_reduce, inv_scale);
   else
-    DFV_PDL((sl_kmajor_kernel<float, false>), grid_b, kSlThreads, smem_b, st, hid, w_expand_t, b_expand, (float*)gate, (float*)nullptr,
-            (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID);
+    DFV_PDL((sl_kmajor_kernel<float, false>), grid_b, kSlThreads, smem_b, st, (const float*)nullptr, w_expand_t, b_expand, (float*)gate,
+            (float*)nullptr, (float*)nullptr, B, C, squeeze, squeeze, SL_IN_SWISH, SL_OUT_SIGMOID, hid_fix, b_reduce, inv_scale);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

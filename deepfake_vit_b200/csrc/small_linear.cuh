@@ -179,7 +179,8 @@ template <typename GT, bool kTrain>
 __global__ void __launch_bounds__(kSlThreads)
     sl_kmajor_kernel(const float* __restrict__ h1, const float* __restrict__ w2, const float* __restrict__ b2,
                      GT* __restrict__ gate, float* __restrict__ gate_f32, float* __restrict__ part_out, int B, int C, int sq, int kc,
-                     int in_act, int out_act) {
+                     int in_act, int out_act, const long long* __restrict__ h_fix = nullptr, const float* __restrict__ h_bias = nullptr,
+                     float h_fix_scale = 1.0f) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) float sm[];
   float* hs = sm;                               // [kc][kSlRows]       iact(h), row-minor
@@ -223,7 +224,10 @@ __global__ void __launch_bounds__(kSlThreads)
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int i = base + u * kSlThreads, im = i / nk, jj = i % nk;        // consecutive threads -> consecutive k (coalesced)
-      v[u] = i < nk * kSlRows && im < nimg ? h1[(size_t)(b0 + im) * sq + k0 + jj] : 0.f;
+      if (h_fix != nullptr)      // fixed-point accumulators of the fused squeeze (dwconv.cu SeFuse) + the squeeze bias
+        v[u] = i < nk * kSlRows && im < nimg ? (float)((double)h_fix[(size_t)(b0 + im) * sq + k0 + jj] * (double)h_fix_scale) + h_bias[k0 + jj] : 0.f;
+      else
+        v[u] = i < nk * kSlRows && im < nimg ? h1[(size_t)(b0 + im) * sq + k0 + jj] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {

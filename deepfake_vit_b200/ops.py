@@ -83,12 +83,12 @@ def dwconv(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, act=DFV_ACT_SILU, wan
     return y, pool
 
 
-def dwconv_se(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, w_reduce, b_reduce):
+def dwconv_se(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, w_reduce, zero_next=None):
     """Depthwise conv + folded BN + swish with the SE squeeze layer fused into the kernel's tail.
-    Returns (y, pool_partial, hid [B, squeeze] fp32 = hidden pre-activations of the gate)."""
+    Returns (y, pool_partial, hid_fix [B, squeeze] int64 fixed-point hidden sums, 2^-30 resolution, bias not added)."""
     B, H, W, C_ = x.shape
     dt = dtype_code(x.dtype)
-    sq = b_reduce.numel()
+    sq = w_reduce.shape[0]
     args = (dt, B, H, W, C_, kernel, stride, pad_lo, pad_hi)
     if not lib.dfv_dwconv_se_supported(*args, sq):
         raise _lib.DfvError("this layer's tile plan cannot host the fused squeeze")
@@ -96,19 +96,19 @@ def dwconv_se(x, w_kkc, bias, kernel, stride, pad_lo, pad_hi, w_reduce, b_reduce
     Wo = (W + pad_lo + pad_hi - kernel) // stride + 1
     y = torch.empty(B, Ho, Wo, C_, device=x.device, dtype=x.dtype)
     pool = torch.empty(B, lib.dfv_dwconv_pool_parts(*args), C_, device=x.device, dtype=torch.float32)
-    hpart = _f32buf(lib.dfv_dwconv_se_scratch_floats(*args, sq), x.device)
-    hid = torch.empty(B, sq, device=x.device, dtype=torch.float32)
-    tickets = torch.zeros(B, device=x.device, dtype=torch.int32)
-    check(lib.dfv_dwconv_se_fwd(_ptr(x), _f32(w_kkc), _f32(bias), _ptr(y), _f32(pool), _f32(w_reduce), _f32(b_reduce), _f32(hpart),
-                                _f32(hid), _ptr(tickets), sq, dt, B, H, W, C_, kernel, stride, pad_lo, pad_hi, _stream()))
-    return y, pool, hid, tickets
+    hid = torch.zeros(B, sq, device=x.device, dtype=torch.int64)
+    check(lib.dfv_dwconv_se_fwd(_ptr(x), _f32(w_kkc), _f32(bias), _ptr(y), _f32(pool), _f32(w_reduce), _ptr(hid), _ptr(zero_next),
+                                zero_next.numel() if zero_next is not None else 0, sq, dt, B, H, W, C_, kernel, stride, pad_lo, pad_hi,
+                                _stream()))
+    return y, pool, hid
 
 
-def se_excite(hid, w_expand_t, b_expand, gate_dtype=torch.float32):
-    B, sq = hid.shape
+def se_excite(hid_fix, b_reduce, w_expand_t, b_expand, gate_dtype=torch.float32):
+    B, sq = hid_fix.shape
     C_ = b_expand.numel()
-    gate = torch.empty(B, C_, device=hid.device, dtype=gate_dtype)
-    check(lib.dfv_se_excite_fwd(_f32(hid), _f32(w_expand_t), _f32(b_expand), _ptr(gate), dtype_code(gate_dtype), B, C_, sq, _stream()))
+    gate = torch.empty(B, C_, device=hid_fix.device, dtype=gate_dtype)
+    check(lib.dfv_se_excite_fwd(_ptr(hid_fix), _f32(b_reduce), _f32(w_expand_t), _f32(b_expand), _ptr(gate), dtype_code(gate_dtype), B, C_,
+                                sq, _stream()))
     return gate
 
 

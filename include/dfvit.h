@@ -163,21 +163,21 @@ int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_hw, const fl
 
 /* The same depthwise convolution with the SQUEEZE layer of the SE block fused into its tail, and the excite layer as the
  * one remaining launch (three dependent launches -> one; replaces the same MBConvBlock lines as the two entries above):
- *   dfv_dwconv_se_fwd   y as dfv_dwconv_fwd (swish), pool_partial as there, and
- *                       hid[b][j] = b_reduce[j] + sum_c w_reduce[j][c] * mean_hw(y[b][.][c])     fp32 [B][squeeze]
- *                       (every CTA reduces its channel chunk of its images to partial hidden sums in `hpart`; a ticket
- *                       per image (`tickets`, uint32 [B], ZERO on entry, left zero on exit) lets the CTA that arrives
- *                       last add them in fixed order -- wait-free, no co-residency requirement)
- *   dfv_se_excite_fwd   gate[b][c] = sigmoid(b_expand[c] + sum_j w_expand_t[j][c] * swish(hid[b][j]))
- * dfv_dwconv_se_supported() says whether the layer's tile plan leaves room for the tail (else use the three-launch
- * path); hpart needs dfv_dwconv_se_scratch_floats() floats. */
+ *   dfv_dwconv_se_fwd   y and pool_partial as dfv_dwconv_fwd (swish), and every CTA adds the partial hidden sums of its
+ *                       channel chunk and images into 64-bit FIXED-POINT accumulators (2^-30 resolution)
+ *                         hid_fix[b][j] += round(2^30 * sum_{c in chunk} w_reduce[j][c] * mean_hw(y[b][.][c]))
+ *                       Integer addition is associative: the sums are bit-reproducible whatever the CTA arrival order,
+ *                       without tickets or waiting.  hid_fix: int64 [B][squeeze], ZERO on entry.  zero_next (optional,
+ *                       != hid_fix): zero_count int64 entries this launch zeroes for the NEXT fused layer (two buffers
+ *                       alternate through the network, so no per-layer memset is needed).
+ *   dfv_se_excite_fwd   hid = b_reduce + 2^-30 * hid_fix;  gate[b][c] = sigmoid(b_expand[c] + sum_j w_expand_t[j][c] * swish(hid[b][j]))
+ * dfv_dwconv_se_supported() says whether the layer's tile plan leaves room for the tail (else use the three-launch path). */
 int dfv_dwconv_se_supported(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze);
-size_t dfv_dwconv_se_scratch_floats(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze);
 int dfv_dwconv_se_fwd(const void* x, const float* w_kkc, const float* bias, void* y, float* pool_partial, const float* w_reduce,
-                      const float* b_reduce, float* hpart, float* hid, unsigned int* tickets, int squeeze, int dtype, int B,
-                      int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream);
-int dfv_se_excite_fwd(const float* hid, const float* w_expand_t, const float* b_expand, void* gate, int gate_dtype, int B, int C,
-                      int squeeze, dfv_stream_t stream);
+                      long long* hid_fix, long long* zero_next, long long zero_count, int squeeze, int dtype, int B, int H, int W,
+                      int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream);
+int dfv_se_excite_fwd(const long long* hid_fix, const float* b_reduce, const float* w_expand_t, const float* b_expand, void* gate,
+                      int gate_dtype, int B, int C, int squeeze, dfv_stream_t stream);
 
 /* Pointwise (1x1) convolution as a GEMM  out[M][N] = act((a[M][K] * a_scale) . w[N][K]^T + bias) + residual.
  * M = B*H*W rows.  a_scale: [M / rows_per_image][K] per-image channel scale (SE gate) of the

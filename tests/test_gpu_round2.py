@@ -67,6 +67,13 @@ def _pair(size=96, config=None, stochastic=False):
     return om, m, d, refmodel
 
 
+def _random_crops(B, H, W, g):
+    """uint8 crops whose normalised values look like the N(0, 1) inputs the weight sets were calibrated on."""
+    x = torch.randn(B, 3, H, W, generator=g)
+    u8 = ((x * torch.tensor(STD).view(1, 3, 1, 1) + torch.tensor(MEAN).view(1, 3, 1, 1)) * 255.0).round().clamp(0, 255)
+    return u8.to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
 def _normalise_cpu(u8):
     """The reference's own input arithmetic (dataset.py:92-98), on CPU."""
     img = u8.permute(0, 3, 1, 2).float()
@@ -80,7 +87,8 @@ def test_uint8_front_end_is_bit_identical_to_the_normalised_fp32_input(shape):
     om, m, d, _ = _pair(128)
     B, H, W = shape
     g = torch.Generator().manual_seed(21)
-    u8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    u8 = _random_crops(B, H, W, g)
+    assert int(u8.min()) == 0 and int(u8.max()) == 255
     lm = torch.rand(B, 5, 2, generator=g) * min(H, W)
     x = _normalise_cpu(u8)
     assert torch.equal(d.ops.u8_to_nchw(u8.to(DEV), MEAN, STD).cpu(), x)        # the normalisation itself, bit for bit
@@ -101,7 +109,7 @@ def test_uint8_front_end_is_bit_identical_to_the_normalised_fp32_input(shape):
 def test_uint8_input_in_train_mode():
     om, m, d, refmodel = _pair(96)
     g = torch.Generator().manual_seed(22)
-    u8 = torch.randint(0, 256, (4, 96, 96, 3), generator=g, dtype=torch.uint8)
+    u8 = _random_crops(4, 96, 96, g)
     lm = torch.rand(4, 5, 2, generator=g) * 96
     y = torch.tensor([0, 1, 1, 0])
     x = _normalise_cpu(u8)
@@ -389,8 +397,8 @@ def test_predict_runs_without_autograd_state_and_modes_are_checked():
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
 def test_depthwise_kernel_with_fused_squeeze(cfg, dtype):
     """dfv_dwconv_se_fwd: same y / pool sums as the plain kernel (bit for bit), hid = b1 + W1 . mean(y) against torch,
-    tickets back to zero, identical results on a second launch (fixed summation order); then the one-launch excite
-    against the three-launch gate."""
+    bit-identical on a second launch (fixed-point integer atomics), the next layer's buffer zeroed; then the one-launch
+    excite against the three-launch gate."""
     import deepfake_vit_b200 as d
     ops = d.ops
     B, C_, H, k, s, pl, ph, sq = cfg
@@ -405,17 +413,19 @@ def test_depthwise_kernel_with_fused_squeeze(cfg, dtype):
     w2t = torch.randn(sq, C_, device=DEV, generator=g) / sq ** 0.5
     b2 = torch.randn(C_, device=DEV, generator=g) * 0.1
     y_ref, pool_ref = ops.dwconv(x, w, bias, k, s, pl, ph)
-    y, pool, hid, tickets = ops.dwconv_se(x, w, bias, k, s, pl, ph, w1, b1)
+    nxt = torch.full((B * sq + 7,), 123, device=DEV, dtype=torch.int64)
+    y, pool, hid = ops.dwconv_se(x, w, bias, k, s, pl, ph, w1, zero_next=nxt)
     torch.cuda.synchronize()
     assert torch.equal(y, y_ref) and torch.equal(pool, pool_ref)
-    assert int(tickets.abs().sum()) == 0
+    assert int(nxt.abs().sum()) == 0                      # the next layer's accumulators were zeroed by this launch
     hw = y.shape[1] * y.shape[2]
     mean = pool_ref.double().sum(1) / hw
     want = b1.double() + mean @ w1.double().t()
-    assert rel(hid, want) < 2e-6, rel(hid, want)
-    y2, pool2, hid2, _ = ops.dwconv_se(x, w, bias, k, s, pl, ph, w1, b1)
-    assert torch.equal(hid2, hid)
-    gate = ops.se_excite(hid, w2t, b2, dtype)
+    got = b1.double() + hid.double() / 2 ** 30
+    assert rel(got, want) < 2e-6, rel(got, want)
+    _, _, hid2 = ops.dwconv_se(x, w, bias, k, s, pl, ph, w1)
+    assert torch.equal(hid2, hid)                         # integer accumulation: bit-reproducible whatever the arrival order
+    gate = ops.se_excite(hid, b1, w2t, b2, dtype)
     gate_ref = ops.se_gate(pool_ref, hw, w1, b1, w2t, b2, dtype)
     assert (gate.float() - gate_ref.float()).abs().max().item() < (8e-3 if dtype == torch.bfloat16 else 1e-5)
     hsw = want * torch.sigmoid(want)
