@@ -53,7 +53,7 @@ struct SeFuse {
   int sq;
   float inv_hw;
 };
-constexpr int kSeGroup = 16;             // images per tail round (bounds the tail's shared memory)
+constexpr int kSeGroup = 32;             // images per tail round (bounds the tail's shared memory)
 constexpr float kSeFixScale = 1073741824.0f;   // 2^30
 
 // 8 channels of activations / weights as they sit in shared memory.
@@ -201,6 +201,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   if constexpr (kAct && !kStats) {
     if (se.zero_next != nullptr)
       for (long long i = (long long)blockIdx.x * blockDim.x + tid; i < se.zero_count; i += (long long)gridDim.x * blockDim.x) se.zero_next[i] = 0;
+    if (se.w1 != nullptr) {      // the squeeze weights of this chunk are HBM-cold: pull them into L2 now, the tail reads them
+      for (int i = tid; i < se.sq * ((CB * 4 + 127) / 128); i += blockDim.x) {
+        const int jj = i / ((CB * 4 + 127) / 128), l = i % ((CB * 4 + 127) / 128);
+        if (c0 + l * 32 < p.C) asm volatile("prefetch.global.L2 [%0];" ::"l"(se.w1 + (size_t)jj * p.C + c0 + l * 32));
+      }
+    }
   }
   __syncthreads();
 
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
       __syncthreads();
       const int sq = se.sq, WP = CB + 1;
       float* ws = reinterpret_cast<float*>(smem_raw);
-      float* ps = ws + (size_t)sq * WP;
+      float* ps = ws + (((size_t)sq * WP + 3) & ~(size_t)3);      // 16-byte aligned: read as float4
       for (int i = tid; i < sq * CB; i += nth) {
         const int jj = i / CB, o = i % CB;
         ws[jj * WP + o] = (c0 + o < p.C) ? __ldg(se.w1 + (size_t)jj * p.C + c0 + o) : 0.f;
@@ -339,18 +345,28 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
           ps[i] = (c0 + o < p.C) ? pool_partial[((size_t)bb * p.parts + (size_t)(slot - first_cta)) * p.C + c0 + o] * se.inv_hw : 0.f;
         }
         __syncthreads();
-        for (int idx = tid; idx < ng * sq; idx += nth) {
-          const int li = idx / sq, jj = idx % sq;
+        // thread = (squeeze row jj, image pair): the weight row is read once for two images; the pool means are
+        // 16-byte broadcast reads
+        const int npair = (ng + 1) >> 1;
+        for (int idx = tid; idx < npair * sq; idx += nth) {
+          const int lp = idx / sq, jj = idx - lp * sq;
+          const int l0 = 2 * lp, l1 = min(2 * lp + 1, ng - 1);
           const float* wr = ws + jj * WP;
-          const float* pr = ps + li * CB;
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          const float4* p0 = reinterpret_cast<const float4*>(ps + l0 * CB);
+          const float4* p1 = reinterpret_cast<const float4*>(ps + l1 * CB);
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 4
           for (int o = 0; o < CB; o += 4) {
-            a0 = fmaf(wr[o], pr[o], a0); a1 = fmaf(wr[o + 1], pr[o + 1], a1);
-            a2 = fmaf(wr[o + 2], pr[o + 2], a2); a3 = fmaf(wr[o + 3], pr[o + 3], a3);
+            const float4 u = p0[o >> 2], v = p1[o >> 2];
+            const float w0 = wr[o], w1 = wr[o + 1], w2 = wr[o + 2], w3 = wr[o + 3];
+            a0 = fmaf(w0, u.x, a0); a1 = fmaf(w1, u.y, a1); a0 = fmaf(w2, u.z, a0); a1 = fmaf(w3, u.w, a1);
+            b0 = fmaf(w0, v.x, b0); b1 = fmaf(w1, v.y, b1); b0 = fmaf(w2, v.z, b0); b1 = fmaf(w3, v.w, b1);
           }
-          const float acc = (a0 + a1) + (a2 + a3);
-          atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + li) * sq + jj),
-                    (unsigned long long)__float2ll_rn(acc * kSeFixScale));
+          atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + l0) * sq + jj),
+                    (unsigned long long)__float2ll_rn((a0 + a1) * kSeFixScale));
+          if (l1 != l0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + l1) * sq + jj),
+                      (unsigned long long)__float2ll_rn((b0 + b1) * kSeFixScale));
         }
         __syncthreads();
       }
@@ -508,8 +524,10 @@ static bool se_tail_fits(const DwPlan& pl, int sq) {
   (void)ts_bytes;
   const size_t tile_bytes_f32 = (size_t)pl.p.THI * pl.p.TWI * pl.p.CB;   // elements
   const size_t two_tiles_min = 2 * ((tile_bytes_f32 * 2 + 127) / 128) * 128;    // bf16 (the smaller of the two dtypes)
-  const size_t need = ((size_t)sq * (pl.p.CB + 1) + (size_t)kSeGroup * pl.p.CB) * sizeof(float);
-  return sq > 0 && sq <= 256 && need <= two_tiles_min;
+  const size_t need = ((size_t)sq * (pl.p.CB + 1) + 4 + (size_t)kSeGroup * pl.p.CB) * sizeof(float);
+  // measured (round 2, batch 256): the tail pays for itself up to C x squeeze ~ 20k (blocks 0-16: -2 .. -30 us per layer
+  // net of the two launches it saves); beyond that the three-launch gate is faster
+  return sq > 0 && sq <= 256 && need <= two_tiles_min && (long long)pl.p.C * sq <= 20000;
 }
 
 template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats>

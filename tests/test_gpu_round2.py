@@ -228,6 +228,12 @@ def test_freeze_bn_training_step_matches_the_oracle():
             n_frozen += 1
             assert p.grad is None, name
             continue
+        if name in ("classifier.0.bias", "classifier.4.bias", "classifier.8.bias"):
+            # a Linear bias in front of a batch-statistics BatchNorm1d is a no-op shift: its gradient is analytically
+            # zero and rounding noise on both sides -- only its size (against the layer's weight gradient) is checked
+            wn = float(ref[name.replace("bias", "weight")].grad.norm())
+            assert float(p.grad.norm()) < 1e-3 * wn and float(r.grad.norm()) < 1e-3 * wn, name
+            continue
         e = float((p.grad.double().cpu() - r.grad.double()).norm()) / max(float(r.grad.norm()), 1e-3 * typical)
         assert e < 5e-3, (name, e)
     assert n_frozen == 2 * (1 + 30 + 32 + 32 + 1)        # every backbone BatchNorm weight and bias
