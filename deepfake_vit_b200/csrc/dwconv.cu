@@ -143,6 +143,73 @@ __device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4],
   }
 }
 
+// The fused squeeze tail (see SeFuse), deliberately NOT inlined: it recomputes the CTA's tile range from blockIdx so that
+// none of its state is live across the depthwise main loop (inlined, it cost that loop 7-8 % in spills).
+// The tile buffers are free when it runs: [ws: sq x (CB+1)] [ps: kSeGroup x CB].
+struct SeTailArgs {       // passed BY VALUE (scalars only): taking the kernel parameter structs' addresses would move them to local memory
+  const float* w1;
+  long long* hid_fix;
+  const float* pool_partial;
+  long long tiles_per_cta, per_chunk;
+  int sq, C, chunks, parts, n_tiles, CB;
+  float inv_hw;
+};
+__device__ __noinline__ void se_tail(unsigned char* smem_raw, const SeTailArgs a) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int CB = a.CB;
+  const int chunk = blockIdx.x % a.chunks, slot = blockIdx.x / a.chunks;
+  const int c0 = chunk * CB;
+  const int n_tiles = a.n_tiles;
+  const long long t_begin = (long long)slot * a.tiles_per_cta;
+  const long long t_end = min(t_begin + a.tiles_per_cta, a.per_chunk);
+  if (t_begin >= t_end) return;
+  __syncthreads();
+  const float* __restrict__ pool_partial = a.pool_partial;
+  struct { const float* w1; long long* hid_fix; int sq; float inv_hw; } se = {a.w1, a.hid_fix, a.sq, a.inv_hw};
+  struct { int C, parts; long long tiles_per_cta; } p = {a.C, a.parts, a.tiles_per_cta};
+  const int sq = se.sq, WP = CB + 1;
+  float* ws = reinterpret_cast<float*>(smem_raw);
+  float* ps = ws + (((size_t)sq * WP + 3) & ~(size_t)3);      // 16-byte aligned: read as float4
+  for (int i = tid; i < sq * CB; i += nth) {
+    const int jj = i / CB, o = i % CB;
+    ws[jj * WP + o] = (c0 + o < p.C) ? __ldg(se.w1 + (size_t)jj * p.C + c0 + o) : 0.f;
+  }
+  const int b_first = (int)(t_begin / n_tiles), b_last = (int)((t_end - 1) / n_tiles);
+  for (int g0 = b_first; g0 <= b_last; g0 += kSeGroup) {
+    const int ng = min(kSeGroup, b_last - g0 + 1);
+    for (int i = tid; i < ng * CB; i += nth) {       // this CTA's own pool sums (written by the main loop, visible after the barrier)
+      const int li = i / CB, o = i % CB, bb = g0 + li;
+      const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
+      ps[i] = (c0 + o < p.C) ? pool_partial[((size_t)bb * p.parts + (size_t)(slot - first_cta)) * p.C + c0 + o] * se.inv_hw : 0.f;
+    }
+    __syncthreads();
+    // thread = (squeeze row jj, image pair): the weight row is read once for two images; the pool means are
+    // 16-byte broadcast reads
+    const int npair = (ng + 1) >> 1;
+    for (int idx = tid; idx < npair * sq; idx += nth) {
+      const int lp = idx / sq, jj = idx - lp * sq;
+      const int l0 = 2 * lp, l1 = min(2 * lp + 1, ng - 1);
+      const float* wr = ws + jj * WP;
+      const float4* p0 = reinterpret_cast<const float4*>(ps + l0 * CB);
+      const float4* p1 = reinterpret_cast<const float4*>(ps + l1 * CB);
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 4
+      for (int o = 0; o < CB; o += 4) {
+        const float4 u = p0[o >> 2], v = p1[o >> 2];
+        const float w0 = wr[o], w1 = wr[o + 1], w2 = wr[o + 2], w3 = wr[o + 3];
+        a0 = fmaf(w0, u.x, a0); a1 = fmaf(w1, u.y, a1); a0 = fmaf(w2, u.z, a0); a1 = fmaf(w3, u.w, a1);
+        b0 = fmaf(w0, v.x, b0); b1 = fmaf(w1, v.y, b1); b0 = fmaf(w2, v.z, b0); b1 = fmaf(w3, v.w, b1);
+      }
+      atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + l0) * sq + jj),
+                (unsigned long long)__float2ll_rn((a0 + a1) * kSeFixScale));
+      if (l1 != l0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + l1) * sq + jj),
+                  (unsigned long long)__float2ll_rn((b0 + b1) * kSeFixScale));
+    }
+    __syncthreads();
+  }
+}
+
 // Persistent CTA: a CONTIGUOUS range of the (image, tile row, tile column) tiles of ONE channel chunk, with a
 // 2-deep TMA pipeline: the tile for step i+1 is in flight while step i is computed.  A thread keeps its
 // (channel group, strip, first row) for the whole kernel; consecutive tiles belong to the same image for long
@@ -326,50 +393,11 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
     b = nb;
   }
   if constexpr (kAct && !kStats) {
-    if (se.w1 != nullptr && t_begin < t_end) {
-      // ---- fused squeeze (see SeFuse).  The tile buffers are free now: [ws: sq x (CB+1)] [ps: kSeGroup x CB]
-      __syncthreads();
-      const int sq = se.sq, WP = CB + 1;
-      float* ws = reinterpret_cast<float*>(smem_raw);
-      float* ps = ws + (((size_t)sq * WP + 3) & ~(size_t)3);      // 16-byte aligned: read as float4
-      for (int i = tid; i < sq * CB; i += nth) {
-        const int jj = i / CB, o = i % CB;
-        ws[jj * WP + o] = (c0 + o < p.C) ? __ldg(se.w1 + (size_t)jj * p.C + c0 + o) : 0.f;
-      }
-      const int b_first = (int)(t_begin / n_tiles), b_last = (int)((t_end - 1) / n_tiles);
-      for (int g0 = b_first; g0 <= b_last; g0 += kSeGroup) {
-        const int ng = min(kSeGroup, b_last - g0 + 1);
-        for (int i = tid; i < ng * CB; i += nth) {       // this CTA's own pool sums (written above, visible after the barrier)
-          const int li = i / CB, o = i % CB, bb = g0 + li;
-          const long long first_cta = ((long long)bb * n_tiles) / p.tiles_per_cta;
-          ps[i] = (c0 + o < p.C) ? pool_partial[((size_t)bb * p.parts + (size_t)(slot - first_cta)) * p.C + c0 + o] * se.inv_hw : 0.f;
-        }
-        __syncthreads();
-        // thread = (squeeze row jj, image pair): the weight row is read once for two images; the pool means are
-        // 16-byte broadcast reads
-        const int npair = (ng + 1) >> 1;
-        for (int idx = tid; idx < npair * sq; idx += nth) {
-          const int lp = idx / sq, jj = idx - lp * sq;
-          const int l0 = 2 * lp, l1 = min(2 * lp + 1, ng - 1);
-          const float* wr = ws + jj * WP;
-          const float4* p0 = reinterpret_cast<const float4*>(ps + l0 * CB);
-          const float4* p1 = reinterpret_cast<const float4*>(ps + l1 * CB);
-          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll 4
-          for (int o = 0; o < CB; o += 4) {
-            const float4 u = p0[o >> 2], v = p1[o >> 2];
-            const float w0 = wr[o], w1 = wr[o + 1], w2 = wr[o + 2], w3 = wr[o + 3];
-            a0 = fmaf(w0, u.x, a0); a1 = fmaf(w1, u.y, a1); a0 = fmaf(w2, u.z, a0); a1 = fmaf(w3, u.w, a1);
-            b0 = fmaf(w0, v.x, b0); b1 = fmaf(w1, v.y, b1); b0 = fmaf(w2, v.z, b0); b1 = fmaf(w3, v.w, b1);
-          }
-          atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + l0) * sq + jj),
-                    (unsigned long long)__float2ll_rn((a0 + a1) * kSeFixScale));
-          if (l1 != l0)
-            atomicAdd(reinterpret_cast<unsigned long long*>(se.hid_fix + (size_t)(g0 + l1) * sq + jj),
-                      (unsigned long long)__float2ll_rn((b0 + b1) * kSeFixScale));
-        }
-        __syncthreads();
-      }
+    if (se.w1 != nullptr) {      // out of line: nothing of it lives in the main loop's registers
+      SeTailArgs ta;
+      ta.w1 = se.w1; ta.hid_fix = se.hid_fix; ta.pool_partial = pool_partial; ta.tiles_per_cta = p.tiles_per_cta; ta.per_chunk = p.per_chunk;
+      ta.sq = se.sq; ta.C = p.C; ta.chunks = p.chunks; ta.parts = p.parts; ta.n_tiles = p.tiles_w * p.tiles_h; ta.CB = CB; ta.inv_hw = se.inv_hw;
+      se_tail(smem_raw, ta);
     }
   }
   if constexpr (kStats) {

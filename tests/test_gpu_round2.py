@@ -334,7 +334,7 @@ def test_two_train_forwards_before_their_backwards():
     om, m, d, _ = _pair(96)
     om.train(); m.train().set_compute_dtype(torch.float32)
     xa, lma, _ = calibrate.synthetic_batch(4, 96, seed=1)
-    xb, lmb, _ = calibrate.synthetic_batch(2, 64, seed=2)
+    xb, lmb, _ = calibrate.synthetic_batch(4, 128, seed=2)      # another shape in flight at the same time
     la, _ = om(xa, lma)
     lb, _ = om(xb, lmb)
     (la.square().sum() + 2.0 * lb.square().sum()).backward()
