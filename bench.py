@@ -296,18 +296,32 @@ def train_leg(c, steps, warmup):
         step(x, lm, y)
     barrier()
     _lib.lib.dfv_launch_count(1)
+    step(x, lm, y)
+    torch.cuda.synchronize()
+    launches_per_step = int(_lib.lib.dfv_launch_count(0))
     gc.collect()
-    gc.disable()        # a collector pause inside a ~3000-launch step drains the launch queue (seen as sporadic 33-38 ms steps)
+    gc.disable()        # a collector pause inside a ~3500-launch step drains the launch queue (seen as sporadic 33-38 ms steps)
+    eager_ms = timed(steps, lambda: step(x, lm, y))
+    # the headline: the same step captured once into a CUDA graph (GraphedTrainStep) and replayed -- the eager step needs
+    # ~28 ms of host time to enqueue ~30 ms of GPU work
+    graphed = d.GraphedTrainStep(model, crit, x, lm, y)
+    for _ in range(2):
+        graphed.replay()
     with ClockSampler(local) as clk:
-        ms = timed(steps, lambda: step(x, lm, y))
-    launches = int(_lib.lib.dfv_launch_count(0))
+        ms = timed(steps, graphed.replay)
+    launches = launches_per_step * steps
+    model.zero_grad(set_to_none=True)
     # the collective's cost: the same loop with it switched off, and the all-reduce alone
     ms_off, ar_ms = None, None
     if world > 1:
         model.ddp_allreduce = False
-        step(x, lm, y)
-        ms_off = timed(steps, lambda: step(x, lm, y))
+        g_off = d.GraphedTrainStep(model, crit, x, lm, y)
+        g_off.replay()
+        ms_off = timed(steps, g_off.replay)
+        del g_off
         model.ddp_allreduce = True
+        model.zero_grad(set_to_none=True)
+        step(x, lm, y)
         flat = model._last_flat_grad
         ar_ms = timed(5, lambda: d.parallel.allreduce_gradients(flat)) / 5
     gc.enable()
@@ -327,20 +341,21 @@ def train_leg(c, steps, warmup):
     roofline = kernel_table(recs, prof_steps, pk)
 
     # end to end: pinned host batch (raw uint8 crops) -> device every step, loss read back every step
-    du8, dl, dy = torch.empty_like(host_u8, device=dev), torch.empty_like(lm), torch.empty_like(y)
+    model.zero_grad(set_to_none=True)
+    g_u8 = d.GraphedTrainStep(model, crit, host_u8.to(dev), lm, y)
 
     def e2e_step():
-        du8.copy_(host_u8, non_blocking=True)
-        dl.copy_(host_lm, non_blocking=True)
-        dy.copy_(host_y, non_blocking=True)
-        return step(du8, dl, dy).item()
+        g_u8.images.copy_(host_u8, non_blocking=True)
+        g_u8.landmarks.copy_(host_lm, non_blocking=True)
+        g_u8.targets.copy_(host_y, non_blocking=True)
+        return g_u8.replay()["total"].item()
 
     e2e_step()
     e2e_ms = timed(steps, e2e_step)
     if world > 1:
-        t = torch.tensor([ms, e2e_ms, ms_off], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms, ms_off, eager_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, ms_off = t[0].item(), t[1].item(), t[2].item()
+        ms, e2e_ms, ms_off, eager_ms = (t[i].item() for i in range(4))
     n_gpus = max(world, 1)
     out = {"metric": "images/sec @380x380 train-step (bf16)", "value": B * n_gpus * steps / (ms * 1e-3), "unit": "images/s",
            "n_gpus": n_gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
@@ -351,15 +366,18 @@ def train_leg(c, steps, warmup):
                       "parallelism": f"dp{n_gpus} (batch sharded; flat fp32 gradient buffer all-reduced over NCCL in "
                                      f"{len(model._reducer.buckets) if model._reducer else 1} reverse-topological buckets on a side stream, "
                                      "each behind the CUDA event of its last backward unit)",
+                      "launch": "one CUDA-graph replay per step (GraphedTrainStep: fwd + loss + bwd + bucketed all-reduce captured once); eager timing under \"eager\"",
                       "l2_policy": "activations exceed the 126 MB L2; no flush needed"},
            "allreduce": None if world == 1 else {
                "ms_alone": ar_ms, "bytes": model._last_flat_grad.numel() * 4, "ms_per_step_without_collective": ms_off / steps,
                "exposed_ms_per_step": ms / steps - ms_off / steps, "buckets": len(model._reducer.buckets),
                "note": "exposed = step time with the collective - the same loop with it switched off (max over ranks each)"},
            "roofline": roofline, "cpu_baseline": None,
+           "eager": {"value": B * n_gpus * steps / (eager_ms * 1e-3), "ms_per_step": eager_ms / steps,
+                     "note": "the same steps launched eagerly (model(...), criterion(...), loss.backward()) instead of replayed from the CUDA graph"},
            "e2e": {"value": B * n_gpus * steps / (e2e_ms * 1e-3), "unit": "images/s",
                    "h2d_bytes_per_step": (host_u8.numel() + lm.numel() * 4 + y.numel() * 8) * n_gpus, "d2h_bytes_per_step": 4 * n_gpus,
-                   "ms_per_step": e2e_ms / steps, "note": "model(uint8 crops, landmarks) + CombinedLoss + backward, pinned host inputs, loss.item() every step"},
+                   "ms_per_step": e2e_ms / steps, "note": "GraphedTrainStep on uint8 crops: pinned host inputs copied into the graph's static buffers, one replay, loss.item() every step"},
            "gpu_launches": launches, "clocks": clk.summary(),
            "memory_gb": torch.cuda.max_memory_allocated() / 1e9}
     del model

@@ -8,7 +8,7 @@ forward signatures, same state_dict layout; all arithmetic runs in hand-written 
 from . import _lib, ops, parallel  # noqa: F401  (raises if libdfvit.so is missing)
 from .losses import CombinedLoss
 from .optim import FusedAdamW
-from .graphed import GraphedInference
+from .graphed import GraphedInference, GraphedTrainStep
 from .model import (ChannelAttention, DeepfakeDetectionModel, DeepfakeFeatureExtractor, EfficientNetB4Backbone,
                     HybridAttention, LandmarkAttention, SpatialAttention)
 
@@ -26,5 +26,5 @@ DEFAULT_MODEL_CONFIG = {
     "dropout_rate": 0.4,
 }
 
-__all__ = ["FusedAdamW", "GraphedInference", "DEFAULT_MODEL_CONFIG", "DeepfakeDetectionModel", "DeepfakeFeatureExtractor", "EfficientNetB4Backbone", "HybridAttention",
+__all__ = ["FusedAdamW", "GraphedInference", "GraphedTrainStep", "DEFAULT_MODEL_CONFIG", "DeepfakeDetectionModel", "DeepfakeFeatureExtractor", "EfficientNetB4Backbone", "HybridAttention",
            "LandmarkAttention", "SpatialAttention", "ChannelAttention", "CombinedLoss", "ops"]

@@ -77,7 +77,7 @@ class TrainArgs(C.Structure):
         ("arena", C.c_void_p), ("arena_bytes", C.c_size_t), ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t),
         ("logits", C.c_void_p), ("features", C.c_void_p), ("dlogits", C.c_void_p), ("dfeatures", C.c_void_p),
         ("taps", C.POINTER(C.c_void_p)),
-        ("freeze_bn", C.c_int32), ("grad_events", C.POINTER(C.c_void_p)),
+        ("freeze_bn", C.c_int32), ("grad_events", C.POINTER(C.c_void_p)), ("seed_dev", C.c_void_p),
     ]
 
 
@@ -122,6 +122,7 @@ def _load():
         "dfv_dwconv_pool_parts": (C.c_int, [i32] * 9),
         "dfv_dwconv_fwd": (C.c_int, [vp, vp, vp, vp, vp] + [i32] * 10 + [vp]),
         "dfv_dwconv_se_supported": (C.c_int, [i32] * 10),
+        "dfv_dwconv_se_profitable": (C.c_int, [i32] * 10),
         "dfv_dwconv_se_fwd": (C.c_int, [vp] * 8 + [i64] + [i32] * 10 + [vp]),
         "dfv_se_excite_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "dfv_se_scratch_floats": (sz, [i32, i32, i32]),
@@ -166,6 +167,7 @@ def _load():
         "dfv_dw_weight_pack": (C.c_int, [vp, vp, i32, i32, i32, vp]),
         "dfv_dw_weight_unpack": (C.c_int, [vp, vp, i32, i32, vp]),
         "dfv_dropout_mask": (C.c_int, [vp, i64, f32, C.c_uint64, vp]),
+        "dfv_dropout_mask_dev": (C.c_int, [vp, i64, f32, C.c_uint64, vp, vp]),
         "dfv_colsum": (C.c_int, [vp, i32, i32, vp, vp]),
         "dfv_add_mul": (C.c_int, [vp, vp, vp, vp, i64, vp]),
         "dfv_convert": (C.c_int, [vp, i32, vp, i32, i64, vp]),

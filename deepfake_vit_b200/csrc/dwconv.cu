@@ -553,9 +553,7 @@ static bool se_tail_fits(const DwPlan& pl, int sq) {
   const size_t tile_bytes_f32 = (size_t)pl.p.THI * pl.p.TWI * pl.p.CB;   // elements
   const size_t two_tiles_min = 2 * ((tile_bytes_f32 * 2 + 127) / 128) * 128;    // bf16 (the smaller of the two dtypes)
   const size_t need = ((size_t)sq * (pl.p.CB + 1) + 4 + (size_t)kSeGroup * pl.p.CB) * sizeof(float);
-  // measured (round 2, batch 256): the tail pays for itself up to C x squeeze ~ 20k (blocks 0-16: -2 .. -30 us per layer
-  // net of the two launches it saves); beyond that the three-launch gate is faster
-  return sq > 0 && sq <= 256 && need <= two_tiles_min && (long long)pl.p.C * sq <= 20000;
+  return sq > 0 && sq <= 256 && need <= two_tiles_min;
 }
 
 template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats>
@@ -681,6 +679,12 @@ extern "C" int dfv_dwconv_se_supported(int dtype, int B, int H, int W, int C, in
   DwPlan pl;
   if (!valid_dtype(dtype) || B <= 0 || make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi) != DFV_OK) return 0;
   return se_tail_fits(pl, squeeze) ? 1 : 0;
+}
+
+/* Policy, measured on a B200 at batch 256 (round 2, isolated launches): the tail costs 2-4 us up to C = 960 and 12 us at
+ * C = 1632 (squeeze 68), the gate drops from 18 / 30 us (three launches) to 9 / 13 us (one): profitable on every B4 layer. */
+extern "C" int dfv_dwconv_se_profitable(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze) {
+  return dfv_dwconv_se_supported(dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, squeeze);
 }
 
 extern "C" int dfv_dwconv_se_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, const float* w_reduce,

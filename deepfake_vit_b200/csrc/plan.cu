@@ -50,7 +50,7 @@ static int compute_shapes(Shapes* s, int dtype, int B, int H, int W) {
     s->act_elems = std::max(s->act_elems, (size_t)ho * wo * b.c_out);
     s->max_cmid = std::max(s->max_cmid, b.c_mid);
     s->se_scratch_floats = std::max(s->se_scratch_floats, dfv_se_scratch_floats(B, b.c_mid, b.se_squeeze));
-    s->se_fused[i] = dfv_dwconv_se_supported(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, b.se_squeeze) != 0;
+    s->se_fused[i] = dfv_dwconv_se_profitable(dtype, B, h, w, b.c_mid, b.kernel, b.stride, b.pad_lo, b.pad_hi, b.se_squeeze) != 0;
     s->max_sq = std::max(s->max_sq, b.se_squeeze);
     h = ho;
     w = wo;

@@ -409,7 +409,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
     const float rate = a->drop_connect_rate * (float)i / (float)n;
     const float* rowscale = nullptr;
     if (b.has_skip && rate > 0.f) {
-      DFV_TRY(dfv_dropout_mask(ba.dc, B, rate, a->seed + 1000 + (unsigned long long)i, stream));
+      DFV_TRY(dfv_dropout_mask_dev(ba.dc, B, rate, a->seed + 1000 + (unsigned long long)i, a->seed_dev, stream));
       rowscale = ba.dc;
     }
     DFV_TRY(dfv_bn_act_fwd(ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), P(i, DFV_T_BN2_B), DFV_ACT_NONE, rowscale, b.has_skip ? x : nullptr, nullptr,
@@ -442,7 +442,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
   DFV_TRY(dfv_hybrid_attention_train_fwd(ar.h, heat, P(-1, DFV_TG_CA_W1), P(-1, DFV_TG_CA_W2), P(-1, DFV_TG_SA_W), ar.feat_pre, ar.attn_saved,
                                          dtype, B, s.Hf, s.Wf, head_c, use_c ? a->ca_hidden : 0, use_c, use_s, stream));
   if (a->feat_dropout > 0.f) {
-    DFV_TRY(dfv_dropout_mask(ar.mask_f, (long long)B * head_c, a->feat_dropout, a->seed + 1, stream));
+    DFV_TRY(dfv_dropout_mask_dev(ar.mask_f, (long long)B * head_c, a->feat_dropout, a->seed + 1, a->seed_dev, stream));
     DFV_TRY(dfv_bn_act_fwd(ar.feat_pre, nullptr, nullptr, nullptr, nullptr, DFV_ACT_NONE, nullptr, nullptr, ar.mask_f, a->features, nullptr,
                            DFV_F32, B, 1, head_c, stream));
   } else {
@@ -466,7 +466,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
                                ar.bn_ws, stream));
       const float* mask = nullptr;
       if (a->cls_dropout > 0.f) {
-        DFV_TRY(dfv_dropout_mask(ca.mask, (long long)B * dout, a->cls_dropout, a->seed + 2000 + (unsigned long long)l, stream));
+        DFV_TRY(dfv_dropout_mask_dev(ca.mask, (long long)B * dout, a->cls_dropout, a->seed + 2000 + (unsigned long long)l, a->seed_dev, stream));
         mask = ca.mask;
       }
       DFV_TRY(dfv_bn_act_fwd(ca.lin, ca.mean, ca.invstd, a->params[dfv_train_cls_index(l, 2)], a->params[dfv_train_cls_index(l, 3)], DFV_ACT_RELU,

@@ -791,8 +791,12 @@ __global__ void dw_weight_unpack_kernel(const float* __restrict__ src, float* __
 }
 
 // Counter-based uniform hash (splitmix64 finaliser): out[i] = u(seed, i) >= p ? 1 / (1 - p) : 0.
-__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float p, unsigned long long seed) {
+// seed_dev (optional): a device word ADDED to the seed -- the launch arguments of a captured CUDA graph are frozen, a device
+// word is not, so a replayed training step still draws fresh masks.
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float p, unsigned long long seed,
+                                    const unsigned long long* __restrict__ seed_dev) {
   pdl_prologue();
+  if (seed_dev) seed += *seed_dev;
   const float scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
@@ -1061,10 +1065,14 @@ int dfv_dw_weight_unpack(const float* src_kkc, float* dst_ckk, int C, int kernel
 }
 
 int dfv_dropout_mask(float* out, long long n, float p, unsigned long long seed, dfv_stream_t stream) {
+  return dfv_dropout_mask_dev(out, n, p, seed, nullptr, stream);
+}
+
+int dfv_dropout_mask_dev(float* out, long long n, float p, unsigned long long seed, const unsigned long long* seed_dev, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(out && n > 0 && p >= 0.f && p <= 1.f, "dfv_dropout_mask: bad arguments");
   const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 4LL * num_sms());
-  DFV_PDL(dropout_mask_kernel, blocks, 256, 0, as_stream(stream), out, n, p, seed);
+  DFV_PDL(dropout_mask_kernel, blocks, 256, 0, as_stream(stream), out, n, p, seed, seed_dev);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

@@ -301,6 +301,7 @@ class DeepfakeDetectionModel(nn.Module):
         self._epoch = 0                         # bumped by everything that rewrites weights behind autograd's back
         self._state_list = None
         self._bn_list = None
+        self._seed_dev = None                   # GraphedTrainStep: device word holding the dropout seed of a captured step
         self._want_taps = False                 # debug: keep NHWC copies of every stage output of a train forward
         self._last_taps = None
         self._last_flat_grad = None
@@ -587,8 +588,10 @@ class DeepfakeDetectionModel(nn.Module):
         a.logits, a.features = logits.data_ptr(), feats.data_ptr()
         # dropout / drop-connect masks are a function of (seed, position); the seed comes from torch's CPU generator
         # (so torch.manual_seed reproduces a run) mixed with the data-parallel rank (ranks draw different masks)
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        a.seed = (seed ^ (_rank() * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
+        if self._seed_dev is not None:     # a captured step (GraphedTrainStep): the seed lives in a device word set before each replay
+            a.seed, a.seed_dev = 0, self._seed_dev.data_ptr()
+        else:
+            a.seed = _mix_seed(int(torch.randint(0, 2 ** 62, (1,)).item()))
         taps = None
         if self._want_taps or want_taps:
             taps = self._tap_tensors(B, H, W, dev, self.compute_dtype)
@@ -745,6 +748,10 @@ class DeepfakeDetectionModel(nn.Module):
         ops.dtype_code(dtype)
         self.compute_dtype = dtype
         return self
+
+
+def _mix_seed(seed: int) -> int:
+    return (seed ^ (_rank() * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
 
 
 def _rank() -> int:

@@ -140,5 +140,6 @@ class BucketedAllReduce:
             for lo, hi, unit in self.buckets:
                 self.stream.wait_event(self.events[unit])
                 allreduce_gradients(flat[lo:hi], group)
-        flat.record_stream(self.stream)
+        if not torch.cuda.is_current_stream_capturing():
+            flat.record_stream(self.stream)
         cur.wait_stream(self.stream)

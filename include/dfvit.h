@@ -171,8 +171,10 @@ int dfv_se_gate_fwd(const float* pool_partial, int parts, float inv_hw, const fl
  *                       != hid_fix): zero_count int64 entries this launch zeroes for the NEXT fused layer (two buffers
  *                       alternate through the network, so no per-layer memset is needed).
  *   dfv_se_excite_fwd   hid = b_reduce + 2^-30 * hid_fix;  gate[b][c] = sigmoid(b_expand[c] + sum_j w_expand_t[j][c] * swish(hid[b][j]))
- * dfv_dwconv_se_supported() says whether the layer's tile plan leaves room for the tail (else use the three-launch path). */
+ * dfv_dwconv_se_supported() says whether the layer's tile plan leaves room for the tail (else use the three-launch path);
+ * dfv_dwconv_se_profitable() is the measured policy dfv_infer_fwd follows. */
 int dfv_dwconv_se_supported(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze);
+int dfv_dwconv_se_profitable(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze);
 int dfv_dwconv_se_fwd(const void* x, const float* w_kkc, const float* bias, void* y, float* pool_partial, const float* w_reduce,
                       long long* hid_fix, long long* zero_next, long long zero_count, int squeeze, int dtype, int B, int H, int W,
                       int C, int kernel, int stride, int pad_lo, int pad_hi, dfv_stream_t stream);
@@ -362,6 +364,10 @@ int dfv_cast_weight(const float* src, void* dst, int dtype, int rows, int cols, 
 int dfv_dw_weight_pack(const float* src_ckk, float* dst_kkc, int C, int kernel, int flip, dfv_stream_t stream);
 int dfv_dw_weight_unpack(const float* src_kkc, float* dst_ckk, int C, int kernel, dfv_stream_t stream);
 int dfv_dropout_mask(float* out, long long n, float p, unsigned long long seed, dfv_stream_t stream);
+/* The same with a DEVICE word added to the seed (may be NULL): launch arguments are frozen inside a captured CUDA graph, a
+ * device word is not. */
+int dfv_dropout_mask_dev(float* out, long long n, float p, unsigned long long seed, const unsigned long long* seed_dev,
+                         dfv_stream_t stream);
 int dfv_colsum(const float* a, int rows, int C, float* out, dfv_stream_t stream);
 int dfv_add_mul(const float* a, const float* b, const float* mask, float* out, long long n, dfv_stream_t stream);
 int dfv_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, dfv_stream_t stream);
@@ -433,6 +439,8 @@ typedef struct {
                                       complete: unit 0 = classifier + attention + head conv, unit 1 + j = block 31 - j,
                                       unit 33 = stem.  Lets the caller start the data-parallel all-reduce of a
                                       finished gradient bucket on a side stream while the rest of the backward runs. */
+  const unsigned long long* seed_dev; /* optional device word added to `seed` by every mask kernel: lets a CUDA-graph replay of
+                                      the step (GraphedTrainStep) draw fresh dropout / drop-connect masks */
 } dfv_train_args;
 #define DFV_GRAD_UNITS 34
 

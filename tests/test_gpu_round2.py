@@ -436,3 +436,62 @@ def test_depthwise_kernel_with_fused_squeeze(cfg, dtype):
     assert (gate.float() - gate_ref.float()).abs().max().item() < (8e-3 if dtype == torch.bfloat16 else 1e-5)
     hsw = want * torch.sigmoid(want)
     assert rel(gate.float(), torch.sigmoid(b2.double() + hsw @ w2t.double())) < (4e-3 if dtype == torch.bfloat16 else 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ captured training step
+def test_graphed_train_step_replays_the_eager_step():
+    """GraphedTrainStep: fwd + CombinedLoss + bwd in one CUDA-graph replay.  With the stochastic parts off a replay must
+    reproduce the eager step bit for bit (same kernels, same order); with them on, every replay draws fresh masks from
+    the device-side seed; gradients survive zero_grad(set_to_none=True); the fused optimizer steps from them."""
+    import deepfake_vit_b200 as d
+    from oracle import calibrate
+    _, m, _, _ = _pair(96)
+    m.train().set_compute_dtype(torch.bfloat16)
+    crit = d.CombinedLoss(LOSS_W, torch.tensor([1.0, 1.5], device=DEV))
+    x, lm, y = calibrate.synthetic_batch(8, 96)
+    x, lm, y = x.to(DEV), lm.to(DEV), y.to(DEV)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m.zero_grad(set_to_none=True)
+    lo, fe = m(x, lm, return_features=True)
+    ref_loss = crit(lo, y, fe)
+    ref_loss["total"].backward()
+    ref_grads = [p.grad.clone() for p in m.parameters()]
+    ref_rm = m.feature_extractor.backbone.backbone._bn0.running_mean.clone()
+    m.load_state_dict(sd0)
+    step = d.GraphedTrainStep(m, crit, x, lm, y)
+    m.load_state_dict(sd0)                                   # capture and warm-up moved the running statistics
+    x2, lm2, y2 = calibrate.synthetic_batch(8, 96, seed=77)
+    step(x2.to(DEV), lm2.to(DEV), y2.to(DEV))                # other data first: the static buffers really are inputs
+    m.load_state_dict(sd0)
+    m.zero_grad(set_to_none=True)
+    losses = step(x, lm, y)
+    torch.cuda.synchronize()
+    assert torch.equal(losses["total"], ref_loss["total"].detach())
+    for p, r in zip(m.parameters(), ref_grads):
+        assert p.grad is not None and torch.equal(p.grad, r)
+    assert torch.equal(m.feature_extractor.backbone.backbone._bn0.running_mean, ref_rm)
+    assert int(m.feature_extractor.backbone.backbone._bn0.num_batches_tracked) == int(sd0["feature_extractor.backbone.backbone._bn0.num_batches_tracked"]) + 1
+    opt = d.FusedAdamW(m.parameters(), lr=1e-3, weight_decay=1e-4, max_grad_norm=1.0, grad_source=m)
+    step2 = d.GraphedTrainStep(m, crit, x, lm, y)            # parameters moved into the optimizer's flat buffer: capture again
+    before = m.classifier[0].weight.detach().clone()
+    first = None
+    for i in range(4):
+        out = step2(x, lm, y)
+        opt.step()
+        first = first if first is not None else out["total"].item()
+    assert not torch.equal(m.classifier[0].weight.detach(), before)
+    assert out["total"].item() < first
+    # eval after replayed steps sees the new weights / statistics (invalidate_packed inside replay)
+    m.eval()
+    a, _ = m(x, lm)
+    m.train()
+    # stochastic parts on: two replays of the same batch differ (fresh masks from the device-side seed)
+    _, m3, _, _ = _pair(96, stochastic=True)
+    m3.train().set_compute_dtype(torch.float32)
+    step3 = d.GraphedTrainStep(m3, crit, x, lm, y)
+    sd3 = {k: v.clone() for k, v in m3.state_dict().items()}
+    g1 = [step3(x, lm, y)["total"].item(), m3._last_flat_grad.clone()]
+    m3.load_state_dict(sd3)
+    g2 = [step3(x, lm, y)["total"].item(), m3._last_flat_grad.clone()]
+    assert g1[0] != g2[0] and not torch.equal(g1[1], g2[1])
+    assert torch.isfinite(g2[1]).all() and torch.isfinite(a).all()
