@@ -152,6 +152,7 @@ def _load():
         "dfv_act_bn_bwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i64,
                                      i32, vp]),
         "dfv_bn_bwd_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]),
+        "dfv_act_bn_bwd_apply": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp, vp, f32, vp, vp, vp, vp, i32, i32, i64, i32, vp]),
         "dfv_se_train_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
         "dfv_se_bwd_ws_floats": (sz, [i32, i64, i32, i32]),
         "dfv_se_bwd": (C.c_int, [vp, vp, i32] + [vp] * 11 + [i32, i64, i32, i32, vp]),

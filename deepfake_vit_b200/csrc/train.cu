@@ -501,10 +501,17 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
   // freeze_bn: eval-mode BatchNorm has no batch-statistics terms in its input gradient (d raw = gamma * invstd * du)
   // and no gamma / beta gradients: run the same two kernels with the two coefficient means zeroed in between.
   auto bn_grad = [&](float* g_ptr) -> float* { return frozen ? nullptr : g_ptr; };
-  auto bn_apply = [&](const void* du, const void* raw, const float* mean, const float* invstd, const float* gamma, void* draw, long long M,
-                      int C) -> int {
+  // Backward through [mask, rowscale, SE gate] -> activation -> BatchNorm of one backbone layer, two streaming passes over
+  // (g, raw): the reduction (dgamma, dbeta, the two coefficient means; du is NOT written) and the apply pass, which
+  // recomputes du and writes d raw into `out` (may alias g).
+  auto bn_backward = [&](const void* gin, const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta, int act,
+                         const void* gate, const float* dpool, float inv_hw, const float* rowscale, void* out, float* dgamma, float* dbeta,
+                         long long rows, int C) -> int {
+    DFV_TRY(dfv_act_bn_bwd(gin, raw, mean, invstd, gamma, beta, act, gate, dpool, inv_hw, rowscale, nullptr, nullptr, bn_grad(dgamma), bn_grad(dbeta),
+                           sc.coef, sc.bn_ws, dtype, B, rows, C, stream));
     if (frozen) DFV_CUDA(cudaMemsetAsync(sc.coef, 0, sizeof(float) * 2 * (size_t)C, st));
-    return dfv_bn_bwd_apply(du, raw, mean, invstd, gamma, sc.coef, draw, dtype, M, C, stream);
+    return dfv_act_bn_bwd_apply(gin, raw, mean, invstd, gamma, beta, act, gate, dpool, inv_hw, rowscale, nullptr, sc.coef, out, dtype, B, rows, C,
+                                stream);
   };
   auto unit_done = [&](int unit) -> int {
     if (a->grad_events && a->grad_events[unit]) DFV_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->grad_events[unit]), st));
@@ -549,9 +556,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
   if (has_heat && G(-1, DFV_TG_LM_W))
     DFV_TRY(dfv_landmark_heatmap_bwd(a->landmarks, P(-1, DFV_TG_LM_W), ar.heat_raw, ar.heat_max, sc.dheat, G(-1, DFV_TG_LM_W), B, s.Hf, s.Wf,
                                      a->landmark_ref_size > 0.f ? a->landmark_ref_size : 224.0f, 1.5f, a->heat_group, stream));
-  DFV_TRY(dfv_act_bn_bwd(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr,
-                         nullptr, sc.gE, bn_grad(G(-1, DFV_TG_HEAD_G)), bn_grad(G(-1, DFV_TG_HEAD_B)), sc.coef, sc.bn_ws, dtype, B, hw_f, head_c, stream));
-  DFV_TRY(bn_apply(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), sc.gE, B * hw_f, head_c));
+  DFV_TRY(bn_backward(sc.gE, ar.h_raw, ar.hm, ar.hi, P(-1, DFV_TG_HEAD_G), P(-1, DFV_TG_HEAD_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr, sc.gE,
+                      G(-1, DFV_TG_HEAD_G), G(-1, DFV_TG_HEAD_B), hw_f, head_c));
   DFV_TRY(dfv_pw_wgrad(sc.gE, ar.blk[n - 1].out, nullptr, 0, G(-1, DFV_TG_HEAD_W), dtype, B * hw_f, c_last, head_c, stream));
   int gc = 0;
   DFV_TRY(dfv_pw_gemm_fwd(sc.gE, ar.wHt, ar.zero_bias, nullptr, 0, nullptr, sc.gout[gc], dtype, B * hw_f, head_c, c_last, DFV_ACT_NONE, stream));
@@ -568,9 +574,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     const float rate = a->drop_connect_rate * (float)i / (float)n;
     const float* rowscale = (b.has_skip && rate > 0.f) ? ba.dc : nullptr;
     // bn2 (no activation); the skip branch keeps gy
-    DFV_TRY(dfv_act_bn_bwd(gy, ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), P(i, DFV_T_BN2_B), DFV_ACT_NONE, nullptr, nullptr, 0.f, rowscale, nullptr,
-                           sc.gP, bn_grad(G(i, DFV_T_BN2_G)), bn_grad(G(i, DFV_T_BN2_B)), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_out, stream));
-    DFV_TRY(bn_apply(sc.gP, ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), sc.gP, B * hw_out, b.c_out));
+    DFV_TRY(bn_backward(gy, ba.p_raw, ba.m2, ba.i2, P(i, DFV_T_BN2_G), P(i, DFV_T_BN2_B), DFV_ACT_NONE, nullptr, nullptr, 0.f, rowscale, sc.gP,
+                        G(i, DFV_T_BN2_G), G(i, DFV_T_BN2_B), hw_out, b.c_out));
     // project conv
     DFV_TRY(dfv_pw_wgrad(sc.gP, ba.d, ba.gate, (int)hw_out, G(i, DFV_T_PROJ_W), dtype, B * hw_out, b.c_mid, b.c_out, stream));
     DFV_TRY(dfv_pw_conv_fwd(sc.gP, ba.wPt, ar.zero_bias, nullptr, (int)hw_out, nullptr, sc.gA, dtype, B, B * hw_out, b.c_out, b.c_mid, DFV_ACT_NONE,
@@ -579,9 +584,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_se_bwd(sc.gA, ba.d, dtype, ba.gate_f32, ba.pooled, ba.h1, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_E_W), sc.dpool, G(i, DFV_T_SE_R_W),
                        G(i, DFV_T_SE_R_B), G(i, DFV_T_SE_E_W), G(i, DFV_T_SE_E_B), sc.se_ws, B, hw_out, b.c_mid, b.se_squeeze, stream));
     // gate, swish, bn1
-    DFV_TRY(dfv_act_bn_bwd(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool, 1.0f / (float)hw_out,
-                           nullptr, nullptr, sc.gA, bn_grad(G(i, DFV_T_BN1_G)), bn_grad(G(i, DFV_T_BN1_B)), sc.coef, sc.bn_ws, dtype, B, hw_out, b.c_mid, stream));
-    DFV_TRY(bn_apply(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), sc.gA, B * hw_out, b.c_mid));
+    DFV_TRY(bn_backward(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool, 1.0f / (float)hw_out,
+                        nullptr, sc.gA, G(i, DFV_T_BN1_G), G(i, DFV_T_BN1_B), hw_out, b.c_mid));
     // depthwise conv
     const void* dw_in = b.has_expand ? (const void*)ba.e : x;
     const int kk = b.kernel * b.kernel;
@@ -596,9 +600,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     }
     void* gx = sc.gout[gc ^ 1];
     if (b.has_expand) {
-      DFV_TRY(dfv_act_bn_bwd(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr, nullptr,
-                             sc.gE, bn_grad(G(i, DFV_T_BN0_G)), bn_grad(G(i, DFV_T_BN0_B)), sc.coef, sc.bn_ws, dtype, B, hw_in, b.c_mid, stream));
-      DFV_TRY(bn_apply(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), sc.gE, B * hw_in, b.c_mid));
+      DFV_TRY(bn_backward(sc.gE, ba.e_raw, ba.m0, ba.i0, P(i, DFV_T_BN0_G), P(i, DFV_T_BN0_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr, sc.gE,
+                          G(i, DFV_T_BN0_G), G(i, DFV_T_BN0_B), hw_in, b.c_mid));
       DFV_TRY(dfv_pw_wgrad(sc.gE, x, nullptr, 0, G(i, DFV_T_EXPAND_W), dtype, B * hw_in, b.c_in, b.c_mid, stream));
       DFV_TRY(dfv_pw_conv_fwd(sc.gE, ba.wEt, ar.zero_bias, nullptr, (int)hw_in, b.has_skip ? gy : nullptr, gx, dtype, B, B * hw_in, b.c_mid, b.c_in,
                               DFV_ACT_NONE, sc.fold_ws, stream));
@@ -612,9 +615,8 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
   }
 
   // ---- stem
-  DFV_TRY(dfv_act_bn_bwd(sc.gout[gc], ar.s_raw, ar.sm, ar.si, P(-1, DFV_TG_STEM_G), P(-1, DFV_TG_STEM_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr,
-                         nullptr, sc.gout[gc], bn_grad(G(-1, DFV_TG_STEM_G)), bn_grad(G(-1, DFV_TG_STEM_B)), sc.coef, sc.bn_ws, dtype, B, (long long)s.Hs * s.Ws, stem_c, stream));
-  DFV_TRY(bn_apply(sc.gout[gc], ar.s_raw, ar.sm, ar.si, P(-1, DFV_TG_STEM_G), sc.gout[gc], (long long)B * s.Hs * s.Ws, stem_c));
+  DFV_TRY(bn_backward(sc.gout[gc], ar.s_raw, ar.sm, ar.si, P(-1, DFV_TG_STEM_G), P(-1, DFV_TG_STEM_B), DFV_ACT_SILU, nullptr, nullptr, 0.f, nullptr,
+                      sc.gout[gc], G(-1, DFV_TG_STEM_G), G(-1, DFV_TG_STEM_B), (long long)s.Hs * s.Ws, stem_c));
   DFV_TRY(dfv_stem_wgrad(sc.gout[gc], a->images_nchw, G(-1, DFV_TG_STEM_W), dtype, B, a->H, a->W, stream));
   DFV_TRY(unit_done(DFV_GRAD_UNITS - 1));
   return DFV_OK;

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
           acc[e] += d;
           acc[8 + e] = fmaf(d, xh, acc[8 + e]);
         }
-        store8(du + off, gv);
+        if (du) store8(du + off, gv);      // du = NULL: reduction only (dfv_act_bn_bwd_apply recomputes du in the apply pass)
       };
       if constexpr (sizeof(T) == 2) {
         extern __shared__ uint4 stage[];   // [2 buffers][kPipeU rows][2 tensors][kNT threads]
@@ -540,6 +540,91 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__
 #pragma unroll
           for (int e = 0; e < 8; ++e) d[e] = fmaf(gi[e], d[e], -fmaf(gk[e], x[e], k0[e]));
           store8(draw + (size_t)ri * C + cv * 8, d);
+        }
+      }
+    }
+  }
+}
+
+// act_bn_bwd + bn_bwd_apply in ONE streaming pass over (g, raw): recomputes du = gin * act'(u) from the same inputs the
+// reduction pass read, so du is never written to / re-read from HBM (the reduction pass then runs with du = NULL):
+//   d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])
+// One write pass less per BatchNorm backward (6 -> 5 tensor passes), and du stays fp32 between the two halves.
+template <typename T, bool kGate>
+__global__ void __launch_bounds__(kNT) act_bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ raw,
+                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int act, const T* __restrict__ gate, const float* __restrict__ dpool,
+                                                              float inv_hw, const float* __restrict__ rowscale,
+                                                              const float* __restrict__ mask, const float* __restrict__ coef,
+                                                              T* __restrict__ draw, long long rows_per_image, int C,
+                                                              long long rows_per_chunk) {
+  pdl_prologue();
+  constexpr int U = Unroll<T>::U;
+  const ColMap m(C);
+  const int b = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
+  const size_t img = (size_t)b * rows_per_image * C;
+  const float rs = rowscale ? rowscale[b] : 1.f;
+  if (m.row_l >= m.rpp) return;
+  for (int cb = 0; cb < m.CV; cb += m.cpp) {
+    const int cv = cb + m.col_l;
+    if (cv >= m.CV) continue;
+    float is[8], nm[8], ga[8], be[8], gt[8], dp[8], gis[8], c1[8], c2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cv * 8 + e;
+      is[e] = invstd ? invstd[c] : 1.f;
+      nm[e] = -(mean ? mean[c] : 0.f) * is[e];
+      ga[e] = gamma ? gamma[c] : 1.f;
+      be[e] = beta ? beta[c] : 0.f;
+      gis[e] = ga[e] * is[e];
+      c1[e] = coef[c];
+      c2[e] = coef[C + c];
+      if constexpr (kGate) dp[e] = dpool ? dpool[(size_t)b * C + c] * inv_hw * rs : 0.f;
+    }
+    if constexpr (kGate) {
+      if (gate) load8(gate + (size_t)b * C + cv * 8, gt);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gt[e] = 1.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gt[e] *= rs;
+    }
+    for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
+      Raw8<T> gx[U], xx[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const long long ri = r + (long long)i * m.rpp;
+        if (ri < r1) {
+          const size_t off = img + (size_t)ri * C + cv * 8;
+          gx[i].load(g + off);
+          xx[i].load(raw + off);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const long long ri = r + (long long)i * m.rpp;
+        if (ri < r1) {
+          const size_t off = img + (size_t)ri * C + cv * 8;
+          float gv[8], x[8], mk[8];
+          gx[i].unpack(gv);
+          xx[i].unpack(x);
+          if (mask) load8(mask + off, mk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float gi;
+            if constexpr (kGate) gi = fmaf(gv[e], gt[e], dp[e]);
+            else gi = gv[e] * rs;
+            if (mask) gi *= mk[e];
+            const float xh = fmaf(x[e], is[e], nm[e]);
+            const float u = fmaf(xh, ga[e], be[e]);
+            const float d = gi * act_grad<sizeof(T) == 2>(u, act);
+            gv[e] = gis[e] * (d - fmaf(xh, c2[e], c1[e]));
+          }
+          store8(draw + off, gv);
         }
       }
     }
@@ -933,13 +1018,13 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
                    const float* mask, void* du, float* dgamma, float* dbeta, float* coef, float* ws, int dtype, int B,
                    long long rows_per_image, int C, dfv_stream_t stream) {
   DFV_TRY(check_device());
-  DFV_REQUIRE(g && raw && du && coef && ws, "dfv_act_bn_bwd: null pointer");
+  DFV_REQUIRE(g && raw && coef && ws, "dfv_act_bn_bwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0, "dfv_act_bn_bwd: bad shape (C %% 8)");
   cudaStream_t st = as_stream(stream);
   const long long chunks = chunks_for(B, rows_per_image);
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
   dim3 grid((unsigned)chunks, (unsigned)B);
-  ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 12.0 * B * rows_per_image * C, st);
+  ProfScope prof(PK_BN, (du ? 3.0 : 2.0) * B * rows_per_image * C * dtype_size(dtype), 12.0 * B * rows_per_image * C, st);
   const bool gated = gate != nullptr || dpool != nullptr;
 #define ABB(T_, G_, U_, M_, SMEM_)                                                                                                   \
   do {                                                                                                                              \
@@ -980,6 +1065,32 @@ int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const f
                                                                         gamma, coef, (__nv_bfloat16*)draw, M, C, rpc);
   else
     DFV_PDL((bn_bwd_apply_kernel<float>), (unsigned)blocks, kNT, 0, st, (const float*)du, (const float*)raw, mean, invstd, gamma, coef, (float*)draw, M, C, rpc);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_act_bn_bwd_apply(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                         int act, const void* gate, const float* dpool, float inv_hw, const float* rowscale, const float* mask,
+                         const float* coef, void* draw, int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(g && raw && coef && draw, "dfv_act_bn_bwd_apply: null pointer");
+  DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0, "dfv_act_bn_bwd_apply: bad shape (C %% 8)");
+  cudaStream_t st = as_stream(stream);
+  long long chunks = std::max<long long>(1, std::min<long long>(rows_per_image, (8LL * num_sms() + B - 1) / B));
+  const long long rpc = (rows_per_image + chunks - 1) / chunks;
+  chunks = (rows_per_image + rpc - 1) / rpc;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 14.0 * B * rows_per_image * C, st);
+  const bool gated = gate != nullptr || dpool != nullptr;
+#define ABA(T_, G_)                                                                                                                    \
+  DFV_PDL((act_bn_bwd_apply_kernel<T_, G_>), grid, kNT, 0, st, (const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act, (const T_*)gate, \
+          dpool, inv_hw, rowscale, mask, coef, (T_*)draw, rows_per_image, C, rpc)
+  if (dtype == DFV_BF16) {
+    if (gated) ABA(__nv_bfloat16, true); else ABA(__nv_bfloat16, false);
+  } else {
+    if (gated) ABA(float, true); else ABA(float, false);
+  }
+#undef ABA
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

@@ -93,27 +93,35 @@ class GraphedTrainStep:
         model._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self._seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._new_seed()
+        self._params = [p for p in model.parameters()]
+        # Warm-up and capture run on ONE side stream, and the parameters are not autograd inputs of the captured step: its
+        # only differentiable leaf is an anchor created here, so no AccumulateGrad node of an earlier (default-stream)
+        # iteration can be pulled into the capture.  The step attaches the gradient views to p.grad itself.
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                           # warm-up off the capture stream: allocator, arenas, NCCL
-            for _ in range(warmup):
-                model.zero_grad(set_to_none=True)
-                self._step()
+        with torch.cuda.stream(side):
+            anchor = torch.zeros(1, device=dev, requires_grad=True)
+            model._detached_anchor = anchor
+            try:
+                for _ in range(warmup):                         # allocator, arenas, NCCL communicators
+                    self._step()
+                side.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    self.losses = self._step()
+            finally:
+                model._detached_anchor = None
         torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        model.zero_grad(set_to_none=True)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.losses = self._step()
-        self._params = [p for p in model.parameters()]
-        self._grads = [p.grad for p in self._params]            # views of the captured flat gradient buffer
+        self._grads = list(model._detached_grads)               # views of the captured flat gradient buffer
         self._flat = model._last_flat_grad
+        for p, g in zip(self._params, self._grads):
+            p.grad = g
 
     def _step(self):
         logits, feats = self.model(self.images, self.landmarks, return_features=True)
         losses = self.criterion(logits, self.targets, feats)
         losses["total"].backward()
-        return losses
+        return {k: v.detach() for k, v in losses.items()}
 
     def _new_seed(self):
         from .model import _mix_seed

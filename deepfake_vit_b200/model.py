@@ -244,13 +244,18 @@ class _TrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, images, landmarks, opts, *params):
+        opts = dict(opts)
+        ctx.detached = opts.pop("detached_params", False)
         logits, feats, run = model._train_fwd(images, landmarks, **opts)
-        ctx.model, ctx.run = model, run
+        ctx.model, ctx.run, ctx.n_inputs = model, run, len(params)
         return logits, feats
 
     @staticmethod
     def backward(ctx, dlogits, dfeats):
         grads = ctx.model._train_bwd(ctx.run, dlogits, dfeats)
+        if ctx.detached:      # captured step: the caller attaches the gradient views itself (no AccumulateGrad nodes in the graph)
+            ctx.model._detached_grads = grads
+            return (None, None, None, None) + (None,) * ctx.n_inputs
         return (None, None, None, None) + tuple(grads)
 
 
@@ -302,6 +307,8 @@ class DeepfakeDetectionModel(nn.Module):
         self._state_list = None
         self._bn_list = None
         self._seed_dev = None                   # GraphedTrainStep: device word holding the dropout seed of a captured step
+        self._detached_anchor = None            # GraphedTrainStep: the only differentiable input of a captured step
+        self._detached_grads = None
         self._want_taps = False                 # debug: keep NHWC copies of every stage output of a train forward
         self._last_taps = None
         self._last_flat_grad = None
@@ -710,8 +717,13 @@ class DeepfakeDetectionModel(nn.Module):
         if self.training:
             # grad mode is read HERE: inside autograd.Function.forward it is always off
             needs_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-            params = [p for _, p in self.named_parameters()]
-            logits, feats = _TrainFn.apply(self, images, landmarks, dict(needs_bwd=needs_bwd), *params)
+            if self._detached_anchor is not None and needs_bwd:
+                # inside GraphedTrainStep: the parameters are NOT autograd inputs (their AccumulateGrad nodes may live on another
+                # stream, which breaks stream capture); the step attaches the gradient views to p.grad itself
+                logits, feats = _TrainFn.apply(self, images, landmarks, dict(needs_bwd=True, detached_params=True), self._detached_anchor)
+            else:
+                params = [p for _, p in self.named_parameters()]
+                logits, feats = _TrainFn.apply(self, images, landmarks, dict(needs_bwd=needs_bwd), *params)
             return (logits, feats) if return_features else (logits, None)
         logits, feats, _, _ = self._infer(images, landmarks)
         return (logits, feats) if return_features else (logits, None)

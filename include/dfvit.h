@@ -316,11 +316,17 @@ int dfv_bn_act_fwd(const void* raw, const float* mean, const float* invstd, cons
                    int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream);
 /* Backward through [mask, rowscale, SE gate] -> activation -> BatchNorm, reduction half:
  *   gin = (g * gate[image][c] + dpool[image][c] * inv_hw) * rowscale[image] * mask;  du = gin * act'(u)
- * writes du (may alias g), dgamma = sum du * xhat, dbeta = sum du (may be NULL), coef [2][C] = the two means. */
+ * writes du (may alias g; NULL = do not write it), dgamma = sum du * xhat, dbeta = sum du (may be NULL), coef [2][C] = the two means. */
 int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma,
                    const float* beta, int act, const void* gate, const float* dpool, float inv_hw, const float* rowscale,
                    const float* mask, void* du, float* dgamma, float* dbeta, float* coef, float* ws, int dtype, int B,
                    long long rows_per_image, int C, dfv_stream_t stream);
+/* The two halves without the du round trip through HBM: call dfv_act_bn_bwd with du = NULL (reduction only: dgamma, dbeta,
+ * coef), then this -- it recomputes du from (g, raw) and writes  d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])
+ * (draw may alias g).  One write pass less per BatchNorm backward; du stays fp32 between the halves. */
+int dfv_act_bn_bwd_apply(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                         int act, const void* gate, const float* dpool, float inv_hw, const float* rowscale, const float* mask,
+                         const float* coef, void* draw, int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream);
 /* d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])   (draw may alias du) */
 int dfv_bn_bwd_apply(const void* du, const void* raw, const float* mean, const float* invstd, const float* gamma,
                      const float* coef, void* draw, int dtype, long long M, int C, dfv_stream_t stream);
