@@ -681,10 +681,12 @@ extern "C" int dfv_dwconv_se_supported(int dtype, int B, int H, int W, int C, in
   return se_tail_fits(pl, squeeze) ? 1 : 0;
 }
 
-/* Policy, measured on a B200 at batch 256 (round 2, isolated launches): the tail costs 2-4 us up to C = 960 and 12 us at
- * C = 1632 (squeeze 68), the gate drops from 18 / 30 us (three launches) to 9 / 13 us (one): profitable on every B4 layer. */
+/* Policy, measured on a B200 at batch 256 inside the forward (round 2): up to C x squeeze ~ 20k (blocks 0-16 of B4) the tail
+ * costs 2-3 us and the gate drops from 18 us (three launches) to 9 us (one).  Beyond that the tail (4 us at C = 960, 12 us at
+ * C = 1632) plus the HBM-cold excite launch cost as much as the three-launch gate: fusing every layer measured 0.09 ms
+ * SLOWER per forward than fusing blocks 0-16 only. */
 extern "C" int dfv_dwconv_se_profitable(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int squeeze) {
-  return dfv_dwconv_se_supported(dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, squeeze);
+  return dfv_dwconv_se_supported(dtype, B, H, W, C, kernel, stride, pad_lo, pad_hi, squeeze) && (long long)C * squeeze <= 20000 ? 1 : 0;
 }
 
 extern "C" int dfv_dwconv_se_fwd(const void* x, const float* w, const float* bias, void* y, float* pool_partial, const float* w_reduce,

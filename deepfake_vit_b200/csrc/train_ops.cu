@@ -351,7 +351,9 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
 }
 
 // ------------------------------------------------------------------------------------ act_bn_bwd
-template <typename T, bool kGate, int U, int MINB>
+// kApply: the SECOND pass of the pair (dfv_act_bn_bwd_apply): same pipelined loads of (g, raw), recomputes du and writes
+//   d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])  into `du` (may alias g); no sums.
+template <typename T, bool kGate, int U, int MINB, bool kApply = false>
 __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -359,9 +361,9 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
                                                            float inv_hw, const float* __restrict__ rowscale,
                                                            const float* __restrict__ mask, T* __restrict__ du,
                                                            float* __restrict__ partial, long long rows_per_image, int C,
-                                                           long long rows_per_chunk) {
+                                                           long long rows_per_chunk, const float* __restrict__ coef = nullptr) {
   pdl_prologue();
-  __shared__ float sm[kNT * 16];
+  __shared__ float sm[kApply ? 1 : kNT * 16];
   const ColMap m(C);
   const int b = blockIdx.y;
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     if (cv < m.CV && m.row_l < m.rpp) {
       // xhat = x * is + nm,  u = xhat * ga + be
-      float is[8], nm[8], ga[8], be[8], gt[8], dp[8];
+      float is[8], nm[8], ga[8], be[8], gt[8], dp[8], pq[kApply ? 8 : 1], pr[kApply ? 8 : 1];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int c = cv * 8 + e;
@@ -385,6 +387,11 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
         ga[e] = gamma ? gamma[c] : 1.f;
         be[e] = beta ? beta[c] : 0.f;
         if constexpr (kGate) dp[e] = dpool ? dpool[(size_t)b * C + c] * inv_hw * rs : 0.f;
+        if constexpr (kApply) {      // out = (ga * is) * d - pq * x - pr
+          const float pa = ga[e] * is[e];
+          pq[e] = pa * coef[C + c] * is[e];
+          pr[e] = pa * fmaf(coef[C + c], nm[e], coef[c]);
+        }
       }
       if constexpr (kGate) {
         if (gate) load8(gate + (size_t)b * C + cv * 8, gt);
@@ -410,11 +417,15 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
           const float xh = fmaf(x[e], is[e], nm[e]);
           const float u = fmaf(xh, ga[e], be[e]);
           const float d = gi * act_grad<sizeof(T) == 2>(u, act);
-          gv[e] = d;
-          acc[e] += d;
-          acc[8 + e] = fmaf(d, xh, acc[8 + e]);
+          if constexpr (kApply) {
+            gv[e] = fmaf(ga[e] * is[e], d, -fmaf(pq[e], x[e], pr[e]));
+          } else {
+            gv[e] = d;
+            acc[e] += d;
+            acc[8 + e] = fmaf(d, xh, acc[8 + e]);
+          }
         }
-        if (du) store8(du + off, gv);      // du = NULL: reduction only (dfv_act_bn_bwd_apply recomputes du in the apply pass)
+        if (kApply || du) store8(du + off, gv);      // du = NULL: reduction only (the apply pass recomputes du)
       };
       if constexpr (sizeof(T) == 2) {
         extern __shared__ uint4 stage[];   // [2 buffers][kPipeU rows][2 tensors][kNT threads]
@@ -468,6 +479,7 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
         }
       }
     }
+    if constexpr (kApply) continue;
     reduce_rows<16>(sm, m, acc);
     if (m.row_l == 0 && cv < m.CV) {
       *reinterpret_cast<float4*>(pout + cv * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -540,91 +552,6 @@ __global__ void __launch_bounds__(kNT) bn_bwd_apply_kernel(const T* __restrict__
 #pragma unroll
           for (int e = 0; e < 8; ++e) d[e] = fmaf(gi[e], d[e], -fmaf(gk[e], x[e], k0[e]));
           store8(draw + (size_t)ri * C + cv * 8, d);
-        }
-      }
-    }
-  }
-}
-
-// act_bn_bwd + bn_bwd_apply in ONE streaming pass over (g, raw): recomputes du = gin * act'(u) from the same inputs the
-// reduction pass read, so du is never written to / re-read from HBM (the reduction pass then runs with du = NULL):
-//   d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])
-// One write pass less per BatchNorm backward (6 -> 5 tensor passes), and du stays fp32 between the two halves.
-template <typename T, bool kGate>
-__global__ void __launch_bounds__(kNT) act_bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ raw,
-                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              int act, const T* __restrict__ gate, const float* __restrict__ dpool,
-                                                              float inv_hw, const float* __restrict__ rowscale,
-                                                              const float* __restrict__ mask, const float* __restrict__ coef,
-                                                              T* __restrict__ draw, long long rows_per_image, int C,
-                                                              long long rows_per_chunk) {
-  pdl_prologue();
-  constexpr int U = Unroll<T>::U;
-  const ColMap m(C);
-  const int b = blockIdx.y;
-  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
-  const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
-  const size_t img = (size_t)b * rows_per_image * C;
-  const float rs = rowscale ? rowscale[b] : 1.f;
-  if (m.row_l >= m.rpp) return;
-  for (int cb = 0; cb < m.CV; cb += m.cpp) {
-    const int cv = cb + m.col_l;
-    if (cv >= m.CV) continue;
-    float is[8], nm[8], ga[8], be[8], gt[8], dp[8], gis[8], c1[8], c2[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = cv * 8 + e;
-      is[e] = invstd ? invstd[c] : 1.f;
-      nm[e] = -(mean ? mean[c] : 0.f) * is[e];
-      ga[e] = gamma ? gamma[c] : 1.f;
-      be[e] = beta ? beta[c] : 0.f;
-      gis[e] = ga[e] * is[e];
-      c1[e] = coef[c];
-      c2[e] = coef[C + c];
-      if constexpr (kGate) dp[e] = dpool ? dpool[(size_t)b * C + c] * inv_hw * rs : 0.f;
-    }
-    if constexpr (kGate) {
-      if (gate) load8(gate + (size_t)b * C + cv * 8, gt);
-      else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) gt[e] = 1.f;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) gt[e] *= rs;
-    }
-    for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
-      Raw8<T> gx[U], xx[U];
-#pragma unroll
-      for (int i = 0; i < U; ++i) {
-        const long long ri = r + (long long)i * m.rpp;
-        if (ri < r1) {
-          const size_t off = img + (size_t)ri * C + cv * 8;
-          gx[i].load(g + off);
-          xx[i].load(raw + off);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < U; ++i) {
-        const long long ri = r + (long long)i * m.rpp;
-        if (ri < r1) {
-          const size_t off = img + (size_t)ri * C + cv * 8;
-          float gv[8], x[8], mk[8];
-          gx[i].unpack(gv);
-          xx[i].unpack(x);
-          if (mask) load8(mask + off, mk);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float gi;
-            if constexpr (kGate) gi = fmaf(gv[e], gt[e], dp[e]);
-            else gi = gv[e] * rs;
-            if (mask) gi *= mk[e];
-            const float xh = fmaf(x[e], is[e], nm[e]);
-            const float u = fmaf(xh, ga[e], be[e]);
-            const float d = gi * act_grad<sizeof(T) == 2>(u, act);
-            gv[e] = gis[e] * (d - fmaf(xh, c2[e], c1[e]));
-          }
-          store8(draw + off, gv);
         }
       }
     }
@@ -1035,7 +962,7 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
     }                                                                                                                               \
     DFV_PDL((act_bn_bwd_kernel<T_, G_, U_, M_>), grid, kNT, SMEM_, st, (const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act,       \
                                                                (const T_*)gate, dpool, inv_hw, rowscale, mask, (T_*)du, ws,        \
-                                                               rows_per_image, C, rpc);                                            \
+                                                               rows_per_image, C, rpc, (const float*)nullptr);                     \
   } while (0)
   constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;   // cp.async staging of the bf16 kernels
   if (dtype == DFV_BF16) {
@@ -1076,19 +1003,27 @@ int dfv_act_bn_bwd_apply(const void* g, const void* raw, const float* mean, cons
   DFV_REQUIRE(g && raw && coef && draw, "dfv_act_bn_bwd_apply: null pointer");
   DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0, "dfv_act_bn_bwd_apply: bad shape (C %% 8)");
   cudaStream_t st = as_stream(stream);
-  long long chunks = std::max<long long>(1, std::min<long long>(rows_per_image, (8LL * num_sms() + B - 1) / B));
+  const long long chunks = chunks_for(B, rows_per_image);
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
-  chunks = (rows_per_image + rpc - 1) / rpc;
   dim3 grid((unsigned)chunks, (unsigned)B);
   ProfScope prof(PK_BN, 3.0 * B * rows_per_image * C * dtype_size(dtype), 14.0 * B * rows_per_image * C, st);
   const bool gated = gate != nullptr || dpool != nullptr;
-#define ABA(T_, G_)                                                                                                                    \
-  DFV_PDL((act_bn_bwd_apply_kernel<T_, G_>), grid, kNT, 0, st, (const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act, (const T_*)gate, \
-          dpool, inv_hw, rowscale, mask, coef, (T_*)draw, rows_per_image, C, rpc)
+#define ABA(T_, G_, U_, M_, SMEM_)                                                                                                  \
+  do {                                                                                                                              \
+    static thread_local bool configured = false;                                                                                    \
+    if (SMEM_ > 0 && !configured) {                                                                                                 \
+      DFV_CUDA(cudaFuncSetAttribute(act_bn_bwd_kernel<T_, G_, U_, M_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_));  \
+      configured = true;                                                                                                            \
+    }                                                                                                                               \
+    DFV_PDL((act_bn_bwd_kernel<T_, G_, U_, M_, true>), grid, kNT, SMEM_, st, (const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act,  \
+                                                               (const T_*)gate, dpool, inv_hw, rowscale, mask, (T_*)draw, (float*)nullptr, \
+                                                               rows_per_image, C, rpc, coef);                                      \
+  } while (0)
+  constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;   // cp.async staging of the bf16 kernels
   if (dtype == DFV_BF16) {
-    if (gated) ABA(__nv_bfloat16, true); else ABA(__nv_bfloat16, false);
+    if (gated) ABA(__nv_bfloat16, true, 4, 2, kStageBytes); else ABA(__nv_bfloat16, false, 4, 2, kStageBytes);
   } else {
-    if (gated) ABA(float, true); else ABA(float, false);
+    if (gated) ABA(float, true, 2, 2, 0); else ABA(float, false, 2, 2, 0);
   }
 #undef ABA
   DFV_LAUNCH_CHECK();
