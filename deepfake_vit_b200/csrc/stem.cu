@@ -227,9 +227,12 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
               const int sh = 8 * (int)(off & 3);
               const uint64_t lo = ((((uint64_t)w1) << 32) | w0) >> sh;
               const uint64_t hi2 = ((((uint64_t)w2) << 32) | w1) >> sh;
+              // lo holds window bytes [s, s + 8 - s) of the first two words, hi2 the same of words 1-2 (s = off & 3 is 0 or 2):
+              // row bytes 0-3 come from lo, 4-8 from hi2
 #pragma unroll
-              for (int j = 0; j < 8; ++j) by[j] = (unsigned char)(lo >> (8 * j));
-              by[8] = (unsigned char)(hi2 >> 32);
+              for (int j = 0; j < 4; ++j) by[j] = (unsigned char)(lo >> (8 * j));
+#pragma unroll
+              for (int j = 4; j < 9; ++j) by[j] = (unsigned char)(hi2 >> (8 * (j - 4)));
             } else {
 #pragma unroll
               for (int j = 0; j < 9; ++j) by[j] = off + j < total_bytes ? __ldg(xb + off + j) : 0;
