@@ -152,12 +152,8 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
   unsigned char* staging = b_tile + 8192;                  // 2 x 12 KB
   float* bias_sm = reinterpret_cast<float*>(staging + 2 * 12288);
   StemBars* bars = reinterpret_cast<StemBars*>(bias_sm + 64);
-  float* lut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + ((sizeof(StemBars) + 15) / 16) * 16);   // [4 copies][3][256], kU8 only
-  if constexpr (kU8) {      // four copies (lane & 3 picks one): random byte values collide on fewer banks
-    stem_build_lut(lut, nm);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 768; i += blockDim.x) lut[768 + i] = lut[i % 768];
-  }
+  float* lut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + ((sizeof(StemBars) + 15) / 16) * 16);   // [3][256], kU8 only
+  if constexpr (kU8) stem_build_lut(lut, nm);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = (long long)B * Ho * Wo;
@@ -208,53 +204,15 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
         const int wo = (int)(p % Wo);
         const long long r = p / Wo;
         const int ho = (int)(r % Ho), b = (int)(r / Ho);
-        if constexpr (kU8) {
-          // one kernel row = 9 consecutive bytes (3 pixels x RGB) starting at an EVEN byte offset: three aligned 32-bit
-          // loads + shifts instead of nine byte loads; the normalised values come from this lane's copy of the table
-          const unsigned char* xb = reinterpret_cast<const unsigned char*>(x);
-          const float* mylut = lut + (tid & 3) * 768;
-          const size_t total_bytes = (size_t)B * H * W * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
             const int hi = 2 * ho + kh;
-            if (hi >= H) continue;
-            const size_t off = (((size_t)b * H + hi) * W + 2 * wo) * 3;
-            const size_t base = off & ~(size_t)3;
-            unsigned char by[9];
-            if (base + 12 <= total_bytes) {
-              const uint32_t* src = reinterpret_cast<const uint32_t*>(xb + base);
-              const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-              const int sh = 8 * (int)(off & 3);
-              const uint64_t lo = ((((uint64_t)w1) << 32) | w0) >> sh;
-              const uint64_t hi2 = ((((uint64_t)w2) << 32) | w1) >> sh;
-              // lo holds window bytes [s, s + 8 - s) of the first two words, hi2 the same of words 1-2 (s = off & 3 is 0 or 2):
-              // row bytes 0-3 come from lo, 4-8 from hi2
-#pragma unroll
-              for (int j = 0; j < 4; ++j) by[j] = (unsigned char)(lo >> (8 * j));
-#pragma unroll
-              for (int j = 4; j < 9; ++j) by[j] = (unsigned char)(hi2 >> (8 * (j - 4)));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 9; ++j) by[j] = off + j < total_bytes ? __ldg(xb + off + j) : 0;
-            }
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
-              if (2 * wo + kw < W) {
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) v[(kh * 3 + kw) * 3 + ci] = mylut[ci * 256 + by[kw * 3 + ci]];
-              }
+              if (hi < H && 2 * wo + kw < W) v[(kh * 3 + kw) * 3 + ci] = stem_load<kU8>(x, lut, b, ci, hi, 2 * wo + kw, H, W);
           }
-        } else {
-#pragma unroll
-          for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              const int hi = 2 * ho + kh;
-#pragma unroll
-              for (int kw = 0; kw < 3; ++kw)
-                if (hi < H && 2 * wo + kw < W) v[(kh * 3 + kw) * 3 + ci] = stem_load<kU8>(x, lut, b, ci, hi, 2 * wo + kw, H, W);
-            }
-        }
       }
       mbar_wait(&bars->a_empty[s], ph ^ 1, 31);
       unsigned char* arow = a_tiles + s * 16384 + tid * 128;
@@ -367,7 +325,7 @@ static int launch_stem_tc(const void* x, const StemNorm& nm, const float* w, con
   long long grid = std::min<long long>(n_tiles, 2LL * num_sms());
   const long long tpc = (n_tiles + grid - 1) / grid;
   grid = (n_tiles + tpc - 1) / tpc;
-  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 16 + (kU8 ? 4 * 768 * 4 : 0) + 1024;
+  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 16 + (kU8 ? 768 * 4 : 0) + 1024;
   DFV_TRY(init_timeout_word_tu());
   static thread_local bool configured = false;
   if (!configured) {

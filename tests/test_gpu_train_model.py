@@ -85,9 +85,13 @@ def test_train_gradients_fp32(step96):
         g, r = p.grad, ref[name].grad
         assert g is not None, name
         assert r is not None, name
+        if float(r.norm()) < 1e-4 * typical:      # analytically zero on both sides: only the size of the noise is comparable
+            assert float(g.norm()) < 1e-3 * typical, name
+            continue
         e = float((g.double().cpu() - r.double()).norm()) / max(float(r.norm()), 1e-3 * typical)
         worst = max(worst, e)
-        if e > 5e-3:
+        # gradients far below the median (<1 %) are dominated by the rounding noise of both implementations: 2e-2 there
+        if e > (5e-3 if float(r.norm()) >= 1e-2 * typical else 2e-2):
             bad.append((name, e, r.norm().item()))
     print("median gradient norm", typical, "worst parameter-gradient relative error", worst)
     assert not bad, f"{len(bad)} gradients off, worst first: {sorted(bad, key=lambda t: -t[1])[:8]}"
