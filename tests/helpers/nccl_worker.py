@@ -59,21 +59,45 @@ def main():
     want /= world
     assert not torch.equal(gathered[0], gathered[-1]), "ranks computed identical gradients: the batch was not sharded"
     for bucket_floats in (4 << 20, 1 << 18, 1 << 30):   # ~4 buckets, one bucket per unit, a single bucket
+        # (1) the whole step: backward + bucketed all-reduce behind the events dfv_train_bwd records.  The weight-gradient
+        # kernels reduce with fp32 atomics, so two runs of the same step agree to rounding (~1e-6), not bit for bit.
         got = step(True, bucket_floats)
         nb = len(m._reducer.buckets)
-        if world == 2:      # (a + b) / 2 is exact whichever way NCCL averages
-            assert torch.equal(got, want), f"rank {rank}: bucketed all-reduce ({nb} buckets) != mean of single-GPU gradients"
+        err = ((got - want).double().norm() / want.double().norm()).item()
+        assert err < 2e-5, (rank, nb, err)
+        # (2) the collective itself on a FIXED buffer: bitwise the mean for 2 ranks ((a + b) / 2 is exact however NCCL averages)
+        buf = local_flat.clone()
+        for ev in m._reducer.events.values():
+            ev.record()
+        m._reducer.reduce(buf)
+        torch.cuda.synchronize()
+        if world == 2:
+            assert torch.equal(buf, want), f"rank {rank}: bucketed all-reduce ({nb} buckets) != mean of the ranks' buffers"
         else:
-            err = ((got - want).double().norm() / want.double().norm()).item()
-            assert err < 1e-6, (rank, nb, err)
+            assert ((buf - want).double().norm() / want.double().norm()).item() < 1e-6
         if rank == 0:
-            print(f"nccl_worker: world {world}, {nb} buckets: flat gradient == mean of per-rank gradients", flush=True)
+            print(f"nccl_worker: world {world}, {nb} buckets: step gradient rel err {err:.1e}; all-reduce of a fixed buffer == mean, bitwise", flush=True)
     # parameter .grad views are the reduced values
     p = m.feature_extractor.backbone.backbone._conv_head.weight
     names = [n for n, _ in m.named_parameters()]
     params, starts, _ = m._flat_layout()
     off = starts[names.index("feature_extractor.backbone.backbone._conv_head.weight")]
-    assert torch.equal(p.grad.flatten(), want[off:off + p.numel()])
+    assert torch.equal(p.grad.flatten(), m._last_flat_grad[off:off + p.numel()])
+    assert float((p.grad.flatten() - want[off:off + p.numel()]).norm()) < 2e-5 * float(want[off:off + p.numel()].norm())
+    # the captured step (GraphedTrainStep) records the NCCL collectives and the cross-stream event edges into the graph
+    m.load_state_dict(sd0)
+    m.ddp_allreduce, m.ddp_bucket_floats = True, 4 << 20
+    gstep = d.GraphedTrainStep(m, crit, x, lm, y)
+    m.load_state_dict(sd0)
+    gstep.replay()
+    torch.cuda.synchronize()
+    gerr = ((m._last_flat_grad - want).double().norm() / want.double().norm()).item()
+    assert gerr < 2e-5, (rank, gerr)
+    if rank == 0:
+        print(f"nccl_worker: graph-replayed step over NCCL: gradient rel err {gerr:.1e}", flush=True)
+    m.load_state_dict(sd0)
+    m.zero_grad(set_to_none=True)
+    step(True, 4 << 20)
     # BatchNorm buffers are rank-local
     rm = m.feature_extractor.backbone.backbone._bn0.running_mean.clone()
     all_rm = [torch.empty_like(rm) for _ in range(world)]
