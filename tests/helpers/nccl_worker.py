@@ -115,9 +115,22 @@ def main():
     dist.all_gather(masks, (f == 0).float())
     assert not torch.equal(masks[0], masks[-1]), "every rank drew the same dropout mask"
     dist.barrier()
+    torch.cuda.synchronize()
     if rank == 0:
         print("nccl_worker: OK", flush=True)
-    dist.destroy_process_group()
+    # Tear-down: the captured graph holds NCCL kernels of this communicator -- drop it first.  destroy_process_group()
+    # blocked forever with the graph alive (seen on the 2-GPU box), so it also gets a bounded wait; everything asserted
+    # above has been checked and printed by now.
+    del gstep
+    import gc
+    import threading
+    gc.collect()
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(30)
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
