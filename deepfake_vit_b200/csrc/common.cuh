@@ -128,6 +128,22 @@ __device__ __forceinline__ void store8(float* p, const float v[8]) {
 
 // swish / SiLU.  EXACT: x / (1 + exp(-x)) with IEEE expf + division (fp32 parity mode).
 // FAST: one MUFU.TANH: silu(x) = h*tanh(h) + h, h = x/2 (max rel err ~2^-11, below bf16 ulp).
+// packed fp32 pair helpers (sm_100 FFMA2 / FADD2: two fp32 operations per issue slot)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
 template <bool kFast>
 __device__ __forceinline__ float silu(float x) {
   if constexpr (kFast) {
@@ -253,6 +269,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, with the 16 destination registers of a tmem_ld16 tied to it: code that reads them cannot be scheduled
+// above the wait (used where another tmem_ld16 is already in flight into a second register set).
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t v[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
 // A training step is ~3000 mostly small launches; stream-ordered launches pay the full launch latency and the previous

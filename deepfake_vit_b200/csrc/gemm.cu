@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->ready[s], 256);
+      mbar_init(&bars->ready[s], 8);
       mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         asm volatile("bar.sync 3, 256;" ::: "memory");
         cached_img = img_lo;
       }
-      const __nv_bfloat16* srow = smem_gate ? gate_sm + (size_t)(img - img_lo) * k_pad : a_scale + (size_t)img * p.K;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(&bars->full[stage], phase, 4);
         if (valid) {
@@ -309,12 +308,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           // reference where sigmoid(se) is a bf16 tensor; one rounding, no unpack / repack.
           // All loads first: a store between them would serialise (swizzled addresses alias).
           uint4 u[4], gt[4];
+          if (smem_gate) {       // explicit shared-space loads: through the generic `srow` they were LD.E (long scoreboard)
+            const uint32_t gaddr = smem_u32(gate_sm + (size_t)(img - img_lo) * k_pad + k0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = cbase + i;
-            if (c < nchunk) {
-              u[i] = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
-              gt[i] = *reinterpret_cast<const uint4*>(srow + k0 + c * 8);
+            for (int i = 0; i < 4; ++i) {
+              const int c = cbase + i;
+              if (c < nchunk) {
+                u[i] = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(gt[i].x), "=r"(gt[i].y), "=r"(gt[i].z), "=r"(gt[i].w) : "r"(gaddr + (uint32_t)c * 16u));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = cbase + i;
+              if (c < nchunk) {
+                u[i] = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+                gt[i] = __ldg(reinterpret_cast<const uint4*>(a_scale + (size_t)img * p.K + k0 + c * 8));
+              }
             }
           }
 #pragma unroll
@@ -330,8 +342,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         }
-        fence_proxy_async();
-        mbar_arrive(&bars->ready[stage]);
+        fence_proxy_async();      // every writer fences, then ONE arrival per warp (256 arrivals per stage serialised on the barrier word)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->ready[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -353,34 +366,43 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t xr = p.swz == 3 ? (uint32_t)(lane & 7) : (p.swz == 2 ? (uint32_t)((lane >> 1) & 3) : (p.swz == 1 ? (uint32_t)((lane >> 2) & 1) : 0u));
     const uint32_t box_bytes = 32u * pitch;
     unsigned char* my_stage = staging + (size_t)ew * p.nbuf * warp_stage_bytes;
-    // one 8-column group: +bias, swish, +residual, bf16, swizzled 16-byte store into the warp's staging slice
+    // one 8-column group: +bias, swish, +residual, bf16, swizzled 16-byte store into the warp's staging slice.
+    // Issue slots are what this epilogue runs out of on the write-dominated expand layers (6x more outputs than
+    // inputs: ~11 outputs per clock per SM at the HBM roofline), so the arithmetic is packed fp32 pairs (FFMA2 /
+    // FADD2: bit-identical to two scalar operations) and the staging address needs no division (a warp owns at most
+    // two store boxes).
     auto emit8 = [&](const uint32_t* v, int wcol, int n, unsigned char* stg) {
       const float4 b0 = *reinterpret_cast<const float4*>(bias_sm + n);
       const float4 b1 = *reinterpret_cast<const float4*>(bias_sm + n + 4);
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+      const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+      float2 o[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
         if constexpr (kAct == DFV_ACT_SILU) {
-          const float h = fmaf(__uint_as_float(v[j]), 0.5f, bb[j]);
-          float th;
-          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
-          o[j] = fmaf(h, th, h);
+          const float2 h = ffma2(a, make_float2(0.5f, 0.5f), bb[j]);
+          float2 th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(h.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(h.y));
+          o[j] = ffma2(h, th, h);
         } else {
-          o[j] = __uint_as_float(v[j]) + bb[j];
+          o[j] = fadd2(a, bb[j]);
         }
       }
-      const uint32_t box = (uint32_t)wcol / (uint32_t)p.bw, c8 = ((uint32_t)wcol % (uint32_t)p.bw) >> 3;
+      const uint32_t box = (uint32_t)wcol >= (uint32_t)p.bw ? 1u : 0u;
+      const uint32_t c8 = ((uint32_t)wcol - (box ? (uint32_t)p.bw : 0u)) >> 3;
       unsigned char* dst = stg + box * box_bytes + row_off + ((c8 ^ xr) << 4);
       if constexpr (kRes) {
         // the residual box was loaded by TMA into this very slot (same box shape and swizzle as the store): add in place
         const uint4 rres = *reinterpret_cast<const uint4*>(dst);
-        o[0] += bf16_lo(rres.x); o[1] += bf16_hi(rres.x); o[2] += bf16_lo(rres.y); o[3] += bf16_hi(rres.y);
-        o[4] += bf16_lo(rres.z); o[5] += bf16_hi(rres.z); o[6] += bf16_lo(rres.w); o[7] += bf16_hi(rres.w);
+        o[0] = fadd2(o[0], make_float2(bf16_lo(rres.x), bf16_hi(rres.x)));
+        o[1] = fadd2(o[1], make_float2(bf16_lo(rres.y), bf16_hi(rres.y)));
+        o[2] = fadd2(o[2], make_float2(bf16_lo(rres.z), bf16_hi(rres.z)));
+        o[3] = fadd2(o[3], make_float2(bf16_lo(rres.w), bf16_hi(rres.w)));
       }
       uint4 pk;
-      pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
-      pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+      pk.x = pack_bf16(o[0].x, o[0].y); pk.y = pack_bf16(o[1].x, o[1].y);
+      pk.z = pack_bf16(o[2].x, o[2].y); pk.w = pack_bf16(o[3].x, o[3].y);
       *reinterpret_cast<uint4*>(dst) = pk;
     };
     int it = 0;
@@ -415,18 +437,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256 + (uint32_t)col_lo;
       if (active) {
         if constexpr (kRes) mbar_wait(&bars->res_full[ew][buf], (uint32_t)((p.nbuf == 2 ? (n_stores >> 1) : n_stores) & 1), 7);
-        for (int cc = 0; cc < nchunk; cc += 2) {
+        // 16-column chunks, software-pipelined over two register sets: the tcgen05.ld of chunk c+1 is in flight while
+        // chunk c goes through bias / swish / pack / staging store (the load latency was exposed once per 32 columns)
+        int ncv = (p.N - n_lo + 15) >> 4;            // chunks of this warp that hold real columns
+        if (ncv > nchunk) ncv = nchunk;
+        uint32_t v0[16], v1[16];
+        __syncwarp();
+        tmem_ld16(tbase, v0);
+        for (int cc = 0; cc < ncv; cc += 2) {
           const int wcol = cc * 16, n0 = n_lo + wcol;
-          if (n0 >= p.N) break;
-          uint32_t v0[16], v1[16];
-          const bool two = cc + 1 < nchunk && n0 + 16 < p.N;
-          __syncwarp();
-          tmem_ld16(tbase + (uint32_t)wcol, v0);
-          if (two) tmem_ld16(tbase + (uint32_t)wcol + 16, v1);
-          tmem_ld_wait();
+          tmem_ld_wait16(v0);
+          if (cc + 1 < ncv) tmem_ld16(tbase + (uint32_t)wcol + 16, v1);
           emit8(v0, wcol, n0, stg);
           emit8(v0 + 8, wcol + 8, n0 + 8, stg);
-          if (two) {
+          if (cc + 1 < ncv) {
+            tmem_ld_wait16(v1);
+            if (cc + 2 < ncv) tmem_ld16(tbase + (uint32_t)wcol + 32, v0);
             emit8(v1, wcol + 16, n0 + 16, stg);
             emit8(v1 + 8, wcol + 24, n0 + 24, stg);
           }
