@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) pw_gemm_simt_kernel(const T* __restrict__
 // ------------------------------------------------------------------------------------
 constexpr int kBM = 128;        // UMMA M (cta_group::1)
 constexpr int kBK = 64;         // one 128-byte swizzle atom of bf16 along K
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kTcThreads = 576; // 18 warps
 constexpr int kFirstWorker = 2; // warps 2..17: 16 workers
 constexpr int kNumWorkers = 16;
@@ -162,8 +162,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the dynamic-smem base
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // weight-stationary plans are made for ungated GEMMs only: the gated variants (at the register cap) compile without it
-  const bool b_res = !kHasScale && p.b_res != 0;
+  const bool b_res = p.b_res != 0;
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
   const uint32_t stage_bytes = b_res ? a_bytes : a_bytes + b_bytes;        // weight-stationary: stages carry A only
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->ready[s], 8);
+      mbar_init(&bars->ready[s], 4);
       mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -268,23 +267,32 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
   } else if (kHasScale && warp < kFirstWorker + kNumXform) {
     // ------------------------------------------------------------- SE-gate transform
-    // 256 threads: thread t owns half of tile row (t & 127): four of its eight 16-byte chunks.
-    // Every thread waits on EVERY stage's full barrier (a waiter that skipped stages could fall
-    // two phases behind an mbarrier and mis-read its parity).
-    const int tx = (warp - kFirstWorker) * 32 + lane;    // 0..255
+    // Two groups of four warps take the even / the odd pipeline STAGES, so two stages are in transform at any time: one stage is a serial chain (barrier wait -> shared loads -> multiply ->
+    // stores -> proxy fence -> arrival) of several hundred cycles, and with all eight warps on every stage that chain
+    // -- not HBM -- paced the gated GEMMs.  Thread = one 128-byte tile row (eight 16-byte chunks, two halves of four).
+    // The split is by stage index, not by k-block counter: a group then sees EVERY phase of the barriers it waits on.
+    // (Alternating by counter with an odd stage count lets the other group consume the intermediate phase of a barrier;
+    // a parity wait two phases behind passes at once on the stale phase -- seen as a rare wrong tile.)
+    const int grp = (warp - kFirstWorker) >> 2;           // 0 / 1
+    const int tx = threadIdx.x - kFirstWorker * 32;       // 0..255: gate staging is done by all transform threads together
     const int row = tx & 127;
-    const int cbase = (tx >> 7) * 4;                      // chunks cbase .. cbase+3
     const bool smem_gate = p.rows_per_image >= kBM;       // a tile then touches at most two images
     const long long n_images = p.M / p.rows_per_image;
+    const uint32_t tiles_s = smem_u32(tiles), gate_s = smem_u32(gate_sm);
+    const uint32_t row_s = (uint32_t)row * 128u;
+    uint32_t sw[8];                                       // swizzled chunk offsets of this row (tile-invariant)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sw[c] = (uint32_t)((c ^ (row & 7)) << 4);
     long long cached_img = -1;
-    int stage = 0;
+    long long img_lo = t_begin < t_end ? (tile_m(t_begin) * kBM) / p.rows_per_image : 0;    // one division per CTA
+    int stage = 0;                                        // stage / phase of the running k-block (all tiles)
     uint32_t phase = 0;
     for (long long t = t_begin; t < t_end; ++t) {
       const long long m0 = tile_m(t) * kBM;
+      while (m0 >= (img_lo + 1) * p.rows_per_image) ++img_lo;   // tiles are visited in increasing m: at most a step or two
       const long long m = m0 + row;
       const bool valid = m < p.M;
-      const long long img_lo = m0 / p.rows_per_image;
-      const long long img = valid ? m / p.rows_per_image : img_lo;
+      const int second = (smem_gate && m >= (img_lo + 1) * p.rows_per_image) ? 1 : 0;      // this row lies in image img_lo + 1
       if (smem_gate && img_lo != cached_img) {
         // stage the gate rows of images img_lo, img_lo + 1 (bf16 [2][k_pad]); the barrier before keeps
         // slower transform threads of the previous tile from reading rows that are being replaced
@@ -298,51 +306,49 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         asm volatile("bar.sync 3, 256;" ::: "memory");
         cached_img = img_lo;
       }
+      const uint32_t grow_s = gate_s + (uint32_t)second * (uint32_t)k_pad * 2u;
+      const __nv_bfloat16* grow_g = smem_gate ? nullptr : a_scale + (size_t)(valid ? m / p.rows_per_image : 0) * p.K;
       for (int kb = 0; kb < p.k_blocks; ++kb) {
+        if ((stage & 1) != grp) {       // the other group's stage
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_wait(&bars->full[stage], phase, 4);
         if (valid) {
-          unsigned char* arow = tiles + (size_t)stage * stage_bytes + (size_t)row * 128;
+          const uint32_t arow = tiles_s + (uint32_t)stage * stage_bytes + row_s;
           const int k0 = kb * kBK;
           const int nchunk = min(8, (p.K - k0) >> 3);
           // x * gate in packed bf16 (HMUL2.BF16): both operands are bf16, as in the autocast
           // reference where sigmoid(se) is a bf16 tensor; one rounding, no unpack / repack.
-          // All loads first: a store between them would serialise (swizzled addresses alias).
-          uint4 u[4], gt[4];
-          if (smem_gate) {       // explicit shared-space loads: through the generic `srow` they were LD.E (long scoreboard)
-            const uint32_t gaddr = smem_u32(gate_sm + (size_t)(img - img_lo) * k_pad + k0);
+          // All loads of a half first: a store between them would serialise (swizzled addresses alias).
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h * 4 >= nchunk) break;
+            uint4 u[4], gt[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int c = cbase + i;
+              const int c = h * 4 + i;
               if (c < nchunk) {
-                u[i] = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(gt[i].x), "=r"(gt[i].y), "=r"(gt[i].z), "=r"(gt[i].w) : "r"(gaddr + (uint32_t)c * 16u));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[i].x), "=r"(u[i].y), "=r"(u[i].z), "=r"(u[i].w) : "r"(arow + sw[c]));
+                if (smem_gate)
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(gt[i].x), "=r"(gt[i].y), "=r"(gt[i].z), "=r"(gt[i].w) : "r"(grow_s + (uint32_t)(k0 + c * 8) * 2u));
+                else
+                  gt[i] = __ldg(reinterpret_cast<const uint4*>(grow_g + k0 + c * 8));
               }
             }
-          } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int c = cbase + i;
+              const int c = h * 4 + i;
               if (c < nchunk) {
-                u[i] = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
-                gt[i] = __ldg(reinterpret_cast<const uint4*>(a_scale + (size_t)img * p.K + k0 + c * 8));
+                const uint32_t vx = hmul2_bf16(u[i].x, gt[i].x), vy = hmul2_bf16(u[i].y, gt[i].y);
+                const uint32_t vz = hmul2_bf16(u[i].z, gt[i].z), vw = hmul2_bf16(u[i].w, gt[i].w);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(arow + sw[c]), "r"(vx), "r"(vy), "r"(vz), "r"(vw) : "memory");
               }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = cbase + i;
-            if (c < nchunk) {
-              uint4 v;
-              v.x = hmul2_bf16(u[i].x, gt[i].x);
-              v.y = hmul2_bf16(u[i].y, gt[i].y);
-              v.z = hmul2_bf16(u[i].z, gt[i].z);
-              v.w = hmul2_bf16(u[i].w, gt[i].w);
-              *reinterpret_cast<uint4*>(arow + ((c ^ (row & 7)) << 4)) = v;
             }
           }
         }
-        fence_proxy_async();      // every writer fences, then ONE arrival per warp (256 arrivals per stage serialised on the barrier word)
+        fence_proxy_async();      // every writer fences, then ONE arrival per warp
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->ready[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -535,10 +541,15 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
     }
     const int ntn0 = (N + p.BN - 1) / p.BN;
     const double stream_bytes = (double)n_tm * ((double)ntn0 * kBM * K * 2 + (double)N * K * 2);
-    double best = force_res == 1 ? 1e300 : stream_bytes * 0.8;      // must be clearly better than streaming
-    for (int ci = 0; ci < 6 && force_res != 0 && !scaled; ++ci) {
+    // must be clearly better than streaming; a gated GEMM is charged its padded columns on both sides (it gains the
+    // deeper A ring as well as the weight traffic)
+    double best = force_res == 1 ? 1e300 : stream_bytes * (scaled ? (double)ntn0 * p.BN / N : 0.8);
+    for (int ci = 0; ci < 6 && force_res != 0; ++ci) {
       const int bn = parts * cws[ci];
       if (bn > 256) continue;
+      // gated GEMMs: one N tile only (the gate transform of A would be repeated per N tile) and a weight that leaves
+      // room for a deep A ring -- their pace is set by stages in flight over the load + transform + MMA chain
+      if (scaled && ((N + bn - 1) / bn != 1 || (size_t)k_blocks * bn * kBK * 2 > 96 * 1024)) continue;
       if (force_res == 1 && force_bn > 0 && bn != force_bn) continue;
       const size_t fixed = (size_t)k_blocks * bn * kBK * 2 + (size_t)bn * 256 + tail_bytes(bn);
       // A alone is 16 KB per k-block: the pipeline needs depth (>= 5 stages) to cover the L2 latency, and a narrow tile
@@ -580,6 +591,9 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   const size_t staging = (size_t)p.BN * 256;            // all epilogue warps, one buffer each
   const size_t tail = tail_bytes(p.BN) + resident;
   p.nbuf = (2 * staging + (p.b_res ? 5 : 3) * stage_bytes + tail <= 222 * 1024) ? 2 : 1;     // (the measured plans' rule)
+  // gated GEMMs write little and wait long (load -> gate transform -> MMA per stage): a pipeline stage is worth more
+  // than a second staging buffer unless six stages fit anyway
+  if (scaled && p.nbuf == 2 && 2 * staging + 6 * stage_bytes + tail > budget) p.nbuf = 1;
   int stages = (int)((budget - tail - p.nbuf * staging) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   DFV_REQUIRE(stages >= 2, "dfv_pw_gemm_fwd: tile does not fit shared memory (N=%d)", N);
