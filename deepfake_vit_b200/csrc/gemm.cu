@@ -122,6 +122,8 @@ struct TcParams {
   int b_res;          // 1: weight-stationary -- the CTA keeps ONE N tile of the weight (all of K) in shared memory
   int m_splits;       //    and walks tiles_per_cta consecutive M tiles; blockIdx = n_tile * m_splits + m_split
   long long n_tiles_m;
+  int cl;             // streaming plans: CTAs per cluster (1 / 2 / 4).  The CTAs of a cluster take consecutive M tiles of the
+                      // SAME N tile and k-block in lockstep; each loads 1/cl of the weight tile and multicasts it to all
   int k_blocks;
   int stages;
   int rows_per_image;
@@ -178,10 +180,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(reinterpret_cast<unsigned char*>(gate_sm) + (kHasScale ? (size_t)2 * k_pad * 2 : 0));
   // contiguous tile range per CTA (m-major): consecutive tiles stay inside one image for rows_per_image / 128 tiles.
   // Weight-stationary mode: one N tile, tiles_per_cta consecutive M tiles.
-  const long long t_begin = b_res ? (long long)(blockIdx.x % p.m_splits) * p.tiles_per_cta : (long long)blockIdx.x * p.tiles_per_cta;
+  // Streaming plans with a cluster (p.cl > 1): the tile index counts CLUSTER tiles (cl consecutive M tiles x one N tile),
+  // every CTA of the cluster walks the same range, CTA rank r takes M tile (cluster tile row) * cl + r.
+  const int cl = b_res ? 1 : p.cl;
+  const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
+  const long long t_begin = b_res ? (long long)(blockIdx.x % p.m_splits) * p.tiles_per_cta : (long long)(blockIdx.x / cl) * p.tiles_per_cta;
   const long long t_end = min(t_begin + p.tiles_per_cta, b_res ? p.n_tiles_m : p.n_tiles);
   const int nt_res = b_res ? (int)(blockIdx.x / p.m_splits) : 0;
-  auto tile_m = [&](long long t) -> long long { return b_res ? t : t / p.n_tiles_n; };
+  auto tile_m = [&](long long t) -> long long { return b_res ? t : (t / p.n_tiles_n) * cl + crank; };
   auto tile_n = [&](long long t) -> int { return b_res ? nt_res : (int)(t % p.n_tiles_n); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->ready[s], 4);
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->empty[s], (uint32_t)cl);     // one MMA commit per CTA that reads (a copy of) this stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -230,7 +238,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           unsigned char* sa = tiles + (size_t)stage * stage_bytes;
           mbar_expect_tx(&bars->full[stage], stage_bytes);
           tma_load_2d(sa, &tm_a, &bars->full[stage], kb * kBK, (int)(mt * kBM));
-          if (!b_res) tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
+          if (!b_res) {
+            if (cl > 1) {     // this CTA's 1/cl of the weight tile's rows, to every CTA of the cluster (tm_b's box is BN / cl rows)
+              const int rows = p.BN / cl;
+              tma_load_2d_mc(sa + a_bytes + (size_t)crank * rows * 128, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN + (int)crank * rows, cmask);
+            } else {
+              tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
+            }
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -259,7 +274,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const int ksteps = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
           for (int k = 0; k < ksteps; ++k)
             umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          umma_commit(&bars->empty[stage]);
+          if (cl > 1) umma_commit_mc(&bars->empty[stage], cmask); else umma_commit(&bars->empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bars->tmem_full[as]);
@@ -321,30 +336,35 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           // x * gate in packed bf16 (HMUL2.BF16): both operands are bf16, as in the autocast
           // reference where sigmoid(se) is a bf16 tensor; one rounding, no unpack / repack.
           // All loads of a half first: a store between them would serialise (swizzled addresses alias).
+          if (nchunk == 8 && smem_gate) {
+            // the common case, branch-free: a full 64-column k-block, gate rows in shared memory
+            const uint32_t gk = grow_s + (uint32_t)k0 * 2u;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h * 4 >= nchunk) break;
-            uint4 u[4], gt[4];
+            for (int h = 0; h < 2; ++h) {
+              uint4 u[4], gt[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = h * 4 + i;
-              if (c < nchunk) {
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[i].x), "=r"(u[i].y), "=r"(u[i].z), "=r"(u[i].w) : "r"(arow + sw[c]));
-                if (smem_gate)
-                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                               : "=r"(gt[i].x), "=r"(gt[i].y), "=r"(gt[i].z), "=r"(gt[i].w) : "r"(grow_s + (uint32_t)(k0 + c * 8) * 2u));
-                else
-                  gt[i] = __ldg(reinterpret_cast<const uint4*>(grow_g + k0 + c * 8));
+              for (int i = 0; i < 4; ++i) {
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u[i].x), "=r"(u[i].y), "=r"(u[i].z), "=r"(u[i].w) : "r"(arow + sw[h * 4 + i]));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(gt[i].x), "=r"(gt[i].y), "=r"(gt[i].z), "=r"(gt[i].w) : "r"(gk + (uint32_t)(h * 4 + i) * 16u));
               }
-            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = h * 4 + i;
-              if (c < nchunk) {
+              for (int i = 0; i < 4; ++i) {
                 const uint32_t vx = hmul2_bf16(u[i].x, gt[i].x), vy = hmul2_bf16(u[i].y, gt[i].y);
                 const uint32_t vz = hmul2_bf16(u[i].z, gt[i].z), vw = hmul2_bf16(u[i].w, gt[i].w);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(arow + sw[c]), "r"(vx), "r"(vy), "r"(vz), "r"(vw) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(arow + sw[h * 4 + i]), "r"(vx), "r"(vy), "r"(vz), "r"(vw) : "memory");
               }
+            }
+          } else {
+            for (int c = 0; c < nchunk; ++c) {      // K tail / tiny images: one chunk at a time
+              uint4 u, gt;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(arow + (uint32_t)((c ^ (row & 7)) << 4)));
+              if (smem_gate)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gt.x), "=r"(gt.y), "=r"(gt.z), "=r"(gt.w) : "r"(grow_s + (uint32_t)(k0 + c * 8) * 2u));
+              else
+                gt = __ldg(reinterpret_cast<const uint4*>(grow_g + k0 + c * 8));
+              const uint32_t vx = hmul2_bf16(u.x, gt.x), vy = hmul2_bf16(u.y, gt.y), vz = hmul2_bf16(u.z, gt.z), vw = hmul2_bf16(u.w, gt.w);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)((c ^ (row & 7)) << 4)), "r"(vx), "r"(vy), "r"(vz), "r"(vw) : "memory");
             }
           }
         }
@@ -487,6 +507,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -496,7 +517,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
 // Tile plan of one GEMM: N tile, streaming vs weight-stationary, pipeline depth, grid.
 static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int K, int N, bool scaled, int rows_per_image, int act,
-                   const dfv_gemm_tuning* tuning = nullptr) {
+                   const dfv_gemm_tuning* tuning = nullptr, int max_clusters = 0) {
   p.M = M;
   p.K = K;
   p.N = N;
@@ -577,11 +598,23 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
     }
   }
   p.n_tiles_n = (N + p.BN - 1) / p.BN;
+  // Streaming plans re-fetch the weight tile from L2 for every 128 rows.  A cluster of `cl` CTAs on consecutive M tiles
+  // can share each weight stage by TMA multicast (every CTA loads 1 / cl of the rows, all receive all of them), which
+  // halves / quarters the L2 READS of the weight.  Measured on B200 (round 2, every streaming layer of the batch-256
+  // forward, cl = 2): no gain, 0-3 % slower (e.g. 1632 -> 272 at 12x12: 76 -> 78 us) -- these layers are paced by the
+  // bytes DELIVERED to each SM (~28 B/clk/SM of A + B stages), which multicast does not reduce, not by L2 reads.  So
+  // the planner does not choose it; dfv_gemm_tuning.cluster asks for it explicitly (tests/test_gpu_ops.py keeps it correct).
+  p.cl = 1;
+  if (!p.b_res) {
+    int want = tuning && tuning->cluster > 0 ? tuning->cluster : 1;
+    while (want > 1 && ((p.BN / want) % 8 != 0 || n_tm < 2 * want)) want >>= 1;
+    p.cl = want;
+  }
   p.nb = p.cw > 64 ? 2 : 1;
   p.bw = p.cw / p.nb;
   p.swz = p.bw == 64 ? 3 : (p.bw == 32 ? 2 : (p.bw == 16 ? 1 : 0));
   p.n_tiles_m = n_tm;
-  p.n_tiles = n_tm * p.n_tiles_n;
+  p.n_tiles = ((n_tm + p.cl - 1) / p.cl) * p.n_tiles_n;      // cluster tiles (= tiles when cl == 1)
   p.k_blocks = k_blocks;
   p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
   p.act = act;
@@ -604,15 +637,19 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   if (p.b_res) {
     grid = (long long)p.m_splits * p.n_tiles_n;
   } else {
-    grid = p.n_tiles < (long long)num_sms() ? p.n_tiles : (long long)num_sms();
-    p.tiles_per_cta = (p.n_tiles + grid - 1) / grid;
-    grid = (p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    long long slots = num_sms() / p.cl;                   // clusters that can be resident (refined by the launcher's occupancy query)
+    if (max_clusters > 0 && p.cl > 1 && max_clusters < slots) slots = max_clusters;
+    long long nc = p.n_tiles < slots ? p.n_tiles : slots;
+    p.tiles_per_cta = (p.n_tiles + nc - 1) / nc;
+    nc = (p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    grid = nc * p.cl;
   }
   return DFV_OK;
 }
 
 /* Debug / documentation aid (host only): the tile plan of a bf16 tensor-core GEMM.
- * out[0..7] = BN, weight-stationary flag, pipeline stages, staging buffers, grid, tiles per CTA, smem bytes, N tiles. */
+ * out[0..8] = BN, weight-stationary flag, pipeline stages, staging buffers, grid, tiles per CTA, smem bytes, N tiles,
+ * CTAs per cluster (weight-stage multicast; the grid is the planner's estimate before the launcher's occupancy query). */
 extern "C" int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* out) {
   TcParams p;
   size_t smem = 0;
@@ -623,8 +660,45 @@ extern "C" int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* ou
   }
   DFV_TRY(plan_tc(p, smem, grid, M, K, N, scaled != 0, 1, 0));
   out[0] = p.BN; out[1] = p.b_res; out[2] = p.stages; out[3] = p.nbuf; out[4] = (int)grid; out[5] = (int)p.tiles_per_cta;
-  out[6] = (int)smem; out[7] = p.n_tiles_n;
+  out[6] = (int)smem; out[7] = p.n_tiles_n; out[8] = p.cl;
   return DFV_OK;
+}
+
+// Resident-cluster capacity of the device for one kernel variant / cluster size at (about) this much shared memory;
+// queried once per (variant, cluster size) and cached.  0 = clusters of that size cannot be launched.
+static int max_active_clusters(int kidx, int cl, size_t smem) {
+  static int cache[8][5] = {};     // 0 = unknown, -1 = unsupported
+  if (cache[kidx][cl] != 0) return cache[kidx][cl] < 0 ? 0 : cache[kidx][cl];
+  const void* fn = nullptr;
+  switch (kidx) {
+    case 0: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_NONE, false>; break;
+    case 1: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_NONE, true>; break;
+    case 2: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_SILU, false>; break;
+    case 3: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_SILU, true>; break;
+    case 4: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_NONE, false>; break;
+    case 5: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_NONE, true>; break;
+    case 6: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_SILU, false>; break;
+    default: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_SILU, true>; break;
+  }
+  int n = 0;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_sms() / cl * cl));
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+  } else {
+    (void)cudaGetLastError();
+  }
+  cache[kidx][cl] = n > 0 ? n : -1;
+  return n > 0 ? n : 0;
 }
 
 static int launch_tc(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
@@ -634,6 +708,19 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   size_t smem = 0;
   long long grid = 0;
   DFV_TRY(plan_tc(p, smem, grid, M, K, N, a_scale != nullptr, rows_per_image, act, tuning));
+  if (p.cl > 1) {
+    // how many clusters of this shape the device can hold at once (GPCs with an odd SM count leave SMs unpaired): a
+    // persistent grid larger than that would run its last clusters as a second wave
+    const int kidx = (a_scale ? 4 : 0) + (act == DFV_ACT_SILU ? 2 : 0) + (residual ? 1 : 0);
+    const int mc = max_active_clusters(kidx, p.cl, smem);
+    if (mc <= 0) {
+      dfv_gemm_tuning t1 = tuning ? *tuning : dfv_gemm_tuning{-1, 0, 0};
+      t1.cluster = -1;
+      DFV_TRY(plan_tc(p, smem, grid, M, K, N, a_scale != nullptr, rows_per_image, act, &t1));
+    } else {
+      DFV_TRY(plan_tc(p, smem, grid, M, K, N, a_scale != nullptr, rows_per_image, act, tuning, mc));
+    }
+  }
 
   CUtensorMap tm_a, tm_b, tm_out, tm_res;
   {
@@ -645,7 +732,7 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)p.BN};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(p.b_res ? p.BN : p.BN / p.cl)};     // clustered: every CTA loads its share of the rows
     DFV_TRY(make_tensor_map(&tm_b, DFV_BF16, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
@@ -666,9 +753,20 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
       DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
       configured = true;                                                                                                        \
     }                                                                                                                           \
-    pw_gemm_tc_kernel<S_, A_, R_><<<(unsigned)grid, kTcThreads, smem, st>>>(tm_a, tm_b, tm_out, tm_res, bias,                   \
-                                                                          (const __nv_bfloat16*)a_scale,                       \
-                                                                          p);                                                  \
+    cudaLaunchConfig_t cfg = {};                                                                                                \
+    cfg.gridDim = dim3((unsigned)grid);                                                                                         \
+    cfg.blockDim = dim3(kTcThreads);                                                                                            \
+    cfg.dynamicSmemBytes = smem;                                                                                                \
+    cfg.stream = st;                                                                                                            \
+    cudaLaunchAttribute cattr[1];                                                                                               \
+    cattr[0].id = cudaLaunchAttributeClusterDimension;                                                                          \
+    cattr[0].val.clusterDim.x = (unsigned)p.cl;                                                                                 \
+    cattr[0].val.clusterDim.y = 1;                                                                                              \
+    cattr[0].val.clusterDim.z = 1;                                                                                              \
+    cfg.attrs = cattr;                                                                                                          \
+    cfg.numAttrs = p.cl > 1 ? 1 : 0;                                                                                            \
+    DFV_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<S_, A_, R_>, tm_a, tm_b, tm_out, tm_res, bias,                          \
+                                (const __nv_bfloat16*)a_scale, p));                                                             \
   } while (0)
   const bool silu_act = act == DFV_ACT_SILU;
   if (a_scale) {
