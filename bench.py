@@ -538,6 +538,15 @@ def infer_leg(c, args, warmup):
     return line
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    sys.stdout.flush()
+    text = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, text)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -582,7 +591,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     import torch
@@ -619,10 +628,15 @@ def main():
                 line["gpu_stock_baseline"] = gpu_stock_baseline(dev)
             except Exception as e:       # a baseline leg must never take the product's number down with it
                 line["gpu_stock_baseline"] = {"unavailable": repr(e)[:200]}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line (the JSON record): anything libraries print while the job runs (NCCL's version banner,
+    # warnings) is sent to stderr by pointing fd 1 at fd 2 for the duration; _emit() writes the record to the real stdout.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
