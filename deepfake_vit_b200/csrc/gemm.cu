@@ -122,8 +122,8 @@ struct TcParams {
   int b_res;          // 1: weight-stationary -- the CTA keeps ONE N tile of the weight (all of K) in shared memory
   int m_splits;       //    and walks tiles_per_cta consecutive M tiles; blockIdx = n_tile * m_splits + m_split
   long long n_tiles_m;
-  int cl;             // streaming plans: CTAs per cluster (1 / 2 / 4).  The CTAs of a cluster take consecutive M tiles of the
-                      // SAME N tile and k-block in lockstep; each loads 1/cl of the weight tile and multicasts it to all
+  int cl;             // streaming plans: 2 = CTA pair (cta_group::2).  The two CTAs of a cluster take consecutive M tiles of
+                      // the SAME N tile; each loads its A tile and HALF of the weight tile's rows, the leader issues M = 256 MMAs
   int k_blocks;
   int stages;
   int rows_per_image;
@@ -155,7 +155,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // Worker warps 2..17.  With an SE gate (project GEMMs) warps 2..9 are the operand transform
 // (two groups of four alternating k-block stages) and warps 10..17 the epilogue; without one
 // (expand / head GEMMs) all sixteen are epilogue warps.
-template <bool kHasScale, int kAct, bool kRes>
+// kPair: the CTA-pair (cta_group::2) variant -- a separate instantiation, because a kernel that contains cta_group::2
+// instructions can only be launched as a cluster of two (a plain launch fails with "cluster misconfiguration").
+template <bool kHasScale, int kAct, bool kRes, bool kPair>
 __global__ void __launch_bounds__(kTcThreads, 1)
     pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
@@ -166,7 +168,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const bool b_res = p.b_res != 0;
   const uint32_t a_bytes = kBM * kBK * 2;
-  const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
+  constexpr bool pair = kPair;                                             // CTA pair: this CTA stages half of the weight tile's rows
+  const uint32_t b_bytes = (uint32_t)(pair ? p.BN / 2 : p.BN) * kBK * 2;
   const uint32_t stage_bytes = b_res ? a_bytes : a_bytes + b_bytes;        // weight-stationary: stages carry A only
   unsigned char* tiles = smem;
   constexpr int kNumEpiW = kNumWorkers - (kHasScale ? 8 : 0);
@@ -180,11 +183,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(reinterpret_cast<unsigned char*>(gate_sm) + (kHasScale ? (size_t)2 * k_pad * 2 : 0));
   // contiguous tile range per CTA (m-major): consecutive tiles stay inside one image for rows_per_image / 128 tiles.
   // Weight-stationary mode: one N tile, tiles_per_cta consecutive M tiles.
-  // Streaming plans with a cluster (p.cl > 1): the tile index counts CLUSTER tiles (cl consecutive M tiles x one N tile),
-  // every CTA of the cluster walks the same range, CTA rank r takes M tile (cluster tile row) * cl + r.
-  const int cl = b_res ? 1 : p.cl;
-  const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
-  const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
+  // CTA-pair plans: the tile index counts PAIR tiles (two consecutive M tiles x one N tile), both CTAs walk the same
+  // range, CTA rank r takes M tile (pair tile row) * 2 + r.
+  const int cl = pair ? 2 : 1;
+  const uint32_t crank = pair ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
   const long long t_begin = b_res ? (long long)(blockIdx.x % p.m_splits) * p.tiles_per_cta : (long long)(blockIdx.x / cl) * p.tiles_per_cta;
   const long long t_end = min(t_begin + p.tiles_per_cta, b_res ? p.n_tiles_m : p.n_tiles);
   const int nt_res = b_res ? (int)(blockIdx.x / p.m_splits) : 0;
@@ -200,12 +203,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->ready[s], 4);
-      mbar_init(&bars->empty[s], (uint32_t)cl);     // one MMA commit per CTA that reads (a copy of) this stage
+      mbar_init(&bars->ready[s], pair ? 8 : 4);     // pair: the leader's MMA thread waits for both CTAs' transform groups
+      mbar_init(&bars->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars->tmem_full[s], 1);
-      mbar_init(&bars->tmem_empty[s], kNumEpi);
+      mbar_init(&bars->tmem_empty[s], pair ? 2 * kNumEpi : kNumEpi);     // pair: both CTAs' epilogue warps release the leader
     }
     mbar_init(&bars->b_full, 1);
     for (int e = 0; e < 16; ++e) { mbar_init(&bars->res_full[e][0], 1); mbar_init(&bars->res_full[e][1], 1); }
@@ -214,10 +217,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_out);
   }
-  if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+  if (warp == 1) {
+    if (pair) tmem_alloc_pair(&bars->tmem_base, kTmemCols); else tmem_alloc(&bars->tmem_base, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
-  if (cl > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts into them
+  if (pair) cluster_sync_all();     // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -236,25 +241,36 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1, 1);
           unsigned char* sa = tiles + (size_t)stage * stage_bytes;
+          if (pair) {
+            // this CTA's A tile and its half of the weight tile's rows (tm_b's box is BN / 2 rows).  Gated: the bytes are
+            // counted on THIS CTA's barrier (its transform warps wait there, then arrive at the leader); ungated: on the
+            // LEADER's barrier, which expects both CTAs' bytes and releases the MMA thread directly.
+            const int brow = nt * p.BN + (int)crank * (p.BN / 2);
+            if (kHasScale) {
+              mbar_expect_tx(&bars->full[stage], stage_bytes);
+              tma_load_2d(sa, &tm_a, &bars->full[stage], kb * kBK, (int)(mt * kBM));
+              tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, brow);
+            } else {
+              if (leader) mbar_expect_tx(&bars->full[stage], 2 * stage_bytes);
+              const uint32_t lbar = mapa_shared(&bars->full[stage], 0);
+              tma_load_2d_pair(sa, &tm_a, lbar, kb * kBK, (int)(mt * kBM));
+              tma_load_2d_pair(sa + a_bytes, &tm_b, lbar, kb * kBK, brow);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&bars->full[stage], stage_bytes);
           tma_load_2d(sa, &tm_a, &bars->full[stage], kb * kBK, (int)(mt * kBM));
-          if (!b_res) {
-            if (cl > 1) {     // this CTA's 1/cl of the weight tile's rows, to every CTA of the cluster (tm_b's box is BN / cl rows)
-              const int rows = p.BN / cl;
-              tma_load_2d_mc(sa + a_bytes + (size_t)crank * rows * 128, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN + (int)crank * rows, cmask);
-            } else {
-              tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
-            }
-          }
+          if (!b_res) tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    if (lane == 0 && leader) {      // CTA pair: the leader issues for both SMs
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128 (256 across a CTA pair)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((pair ? 2 * kBM : kBM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -272,12 +288,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(b_res ? smem_u32(bres + (size_t)kb * b_bytes) : sa + a_bytes);
           const int k_left = p.K - kb * kBK;
           const int ksteps = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          if (cl > 1) umma_commit_mc(&bars->empty[stage], cmask); else umma_commit(&bars->empty[stage]);
+          if (pair) {
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_commit_pair(&bars->empty[stage]);      // frees the stage in both CTAs
+          } else {
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_commit(&bars->empty[stage]);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->tmem_full[as]);
+        if (pair) umma_commit_pair(&bars->tmem_full[as]); else umma_commit(&bars->tmem_full[as]);
       }
     }
   } else if (kHasScale && warp < kFirstWorker + kNumXform) {
@@ -370,7 +392,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         fence_proxy_async();      // every writer fences, then ONE arrival per warp
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->ready[stage]);
+        if (lane == 0) {
+          if (pair) mbar_arrive_cluster(mapa_shared(&bars->ready[stage], 0));      // the leader's MMA thread waits for both CTAs
+          else mbar_arrive(&bars->ready[stage]);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -486,7 +511,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);     // TMEM stage drained
+      if (lane == 0) {                                       // TMEM stage drained (pair: tell the leader's MMA thread)
+        if (pair) mbar_arrive_cluster(mapa_shared(&bars->tmem_empty[as], 0)); else mbar_arrive(&bars->tmem_empty[as]);
+      }
       fence_proxy_async();                                   // staging writes -> visible to the TMA engine
       __syncwarp();
       if (lane == 0 && active) {
@@ -507,11 +534,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (cl > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it or signal its barriers
+  if (pair) cluster_sync_all();     // no CTA leaves (or frees TMEM) while the pair's MMAs or barrier signals may still touch it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (pair) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -598,16 +625,15 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
     }
   }
   p.n_tiles_n = (N + p.BN - 1) / p.BN;
-  // Streaming plans re-fetch the weight tile from L2 for every 128 rows.  A cluster of `cl` CTAs on consecutive M tiles
-  // can share each weight stage by TMA multicast (every CTA loads 1 / cl of the rows, all receive all of them), which
-  // halves / quarters the L2 READS of the weight.  Measured on B200 (round 2, every streaming layer of the batch-256
-  // forward, cl = 2): no gain, 0-3 % slower (e.g. 1632 -> 272 at 12x12: 76 -> 78 us) -- these layers are paced by the
-  // bytes DELIVERED to each SM (~28 B/clk/SM of A + B stages), which multicast does not reduce, not by L2 reads.  So
-  // the planner does not choose it; dfv_gemm_tuning.cluster asks for it explicitly (tests/test_gpu_ops.py keeps it correct).
+  // Streaming plans re-fetch the weight tile for every 128 rows, and on the wide-K layers the bytes DELIVERED to each SM
+  // (A + B stages, ~28 B/clk/SM measured), not HBM, set the pace.  A CTA pair (cta_group::2, M = 256 across two SMs)
+  // stages only HALF of the weight tile's rows per SM: (16 + BN/8) KB instead of (16 + BN/4) KB per k-block, and more
+  // stages fit.  (Sharing the weight stage by TMA multicast over a cluster instead -- every SM still receives the whole
+  // tile -- was measured first: no gain, 0-3 % slower; L2 reads are not the limit.)
   p.cl = 1;
   if (!p.b_res) {
-    int want = tuning && tuning->cluster > 0 ? tuning->cluster : 1;
-    while (want > 1 && ((p.BN / want) % 8 != 0 || n_tm < 2 * want)) want >>= 1;
+    int want = tuning && tuning->cluster != 0 ? tuning->cluster : ((size_t)p.BN * kBK * 2 >= (size_t)kBM * kBK && k_blocks >= 4 ? 2 : 1);
+    if (want != 2 || (p.BN / 2) % 8 != 0 || p.BN % 32 != 0 || n_tm < 4) want = 1;
     p.cl = want;
   }
   p.nb = p.cw > 64 ? 2 : 1;
@@ -619,7 +645,7 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
   p.act = act;
   const size_t a_stage = (size_t)kBM * kBK * 2;
-  const size_t stage_bytes = p.b_res ? a_stage : a_stage + (size_t)p.BN * kBK * 2;
+  const size_t stage_bytes = p.b_res ? a_stage : a_stage + (size_t)(p.cl == 2 ? p.BN / 2 : p.BN) * kBK * 2;
   const size_t resident = p.b_res ? (size_t)k_blocks * p.BN * kBK * 2 : 0;
   const size_t staging = (size_t)p.BN * 256;            // all epilogue warps, one buffer each
   const size_t tail = tail_bytes(p.BN) + resident;
@@ -649,7 +675,7 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
 
 /* Debug / documentation aid (host only): the tile plan of a bf16 tensor-core GEMM.
  * out[0..8] = BN, weight-stationary flag, pipeline stages, staging buffers, grid, tiles per CTA, smem bytes, N tiles,
- * CTAs per cluster (weight-stage multicast; the grid is the planner's estimate before the launcher's occupancy query). */
+ * CTAs per cluster (2 = CTA-pair plan; the grid is the planner's estimate before the launcher's occupancy query). */
 extern "C" int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* out) {
   TcParams p;
   size_t smem = 0;
@@ -671,14 +697,14 @@ static int max_active_clusters(int kidx, int cl, size_t smem) {
   if (cache[kidx][cl] != 0) return cache[kidx][cl] < 0 ? 0 : cache[kidx][cl];
   const void* fn = nullptr;
   switch (kidx) {
-    case 0: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_NONE, false>; break;
-    case 1: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_NONE, true>; break;
-    case 2: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_SILU, false>; break;
-    case 3: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_SILU, true>; break;
-    case 4: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_NONE, false>; break;
-    case 5: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_NONE, true>; break;
-    case 6: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_SILU, false>; break;
-    default: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_SILU, true>; break;
+    case 0: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_NONE, false, true>; break;
+    case 1: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_NONE, true, true>; break;
+    case 2: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_SILU, false, true>; break;
+    case 3: fn = (const void*)pw_gemm_tc_kernel<false, DFV_ACT_SILU, true, true>; break;
+    case 4: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_NONE, false, true>; break;
+    case 5: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_NONE, true, true>; break;
+    case 6: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_SILU, false, true>; break;
+    default: fn = (const void*)pw_gemm_tc_kernel<true, DFV_ACT_SILU, true, true>; break;
   }
   int n = 0;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess) {
@@ -732,7 +758,7 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(p.b_res ? p.BN : p.BN / p.cl)};     // clustered: every CTA loads its share of the rows
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(p.b_res ? p.BN : p.BN / p.cl)};     // CTA pair: every CTA loads its half of the rows
     DFV_TRY(make_tensor_map(&tm_b, DFV_BF16, 2, w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   {
@@ -750,7 +776,8 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
   do {                                                                                                                          \
     static thread_local bool configured = false;                                                                                \
     if (!configured) {                                                                                                          \
-      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
+      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
+      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
       configured = true;                                                                                                        \
     }                                                                                                                           \
     cudaLaunchConfig_t cfg = {};                                                                                                \
@@ -765,8 +792,12 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
     cattr[0].val.clusterDim.z = 1;                                                                                              \
     cfg.attrs = cattr;                                                                                                          \
     cfg.numAttrs = p.cl > 1 ? 1 : 0;                                                                                            \
-    DFV_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<S_, A_, R_>, tm_a, tm_b, tm_out, tm_res, bias,                          \
-                                (const __nv_bfloat16*)a_scale, p));                                                             \
+    if (p.cl == 2)                                                                                                              \
+      DFV_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<S_, A_, R_, true>, tm_a, tm_b, tm_out, tm_res, bias,                  \
+                                  (const __nv_bfloat16*)a_scale, p));                                                           \
+    else                                                                                                                        \
+      DFV_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<S_, A_, R_, false>, tm_a, tm_b, tm_out, tm_res, bias,                 \
+                                  (const __nv_bfloat16*)a_scale, p));                                                           \
   } while (0)
   const bool silu_act = act == DFV_ACT_SILU;
   if (a_scale) {

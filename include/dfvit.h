@@ -497,8 +497,8 @@ int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float
  * out[0..9] = CB, L, TW, TH, threads, smem bytes, tiles_w, tiles_h, pool parts, grid. */
 int dfv_dwconv_plan_info(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out);
 /* Tile plan of a bf16 tensor-core 1x1-conv GEMM (host only): out[0..8] = N tile, weight-stationary flag, pipeline
- * stages, staging buffers, grid, tiles per CTA, shared-memory bytes, N tiles, CTAs per cluster (streaming plans share each
- * weight stage by TMA multicast). */
+ * stages, staging buffers, grid, tiles per CTA, shared-memory bytes, N tiles, CTAs per cluster (2 = CTA-pair plan,
+ * cta_group::2). */
 int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* out);
 
 /* Tuning entry points: the same operators with the tile plan restricted by the CALLER (a per-call argument: no
@@ -507,7 +507,7 @@ int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* out);
 typedef struct {
   int32_t weight_stationary;   /* -1 auto, 0 streaming, 1 weight-stationary */
   int32_t bn;                  /* N tile (0 = auto) */
-  int32_t cluster;             /* streaming plans: CTAs per cluster sharing each weight stage by TMA multicast (0 = auto, -1 = none, 2, 4) */
+  int32_t cluster;             /* streaming plans: 2 = CTA pair (cta_group::2: M = 256 over two SMs, half of the weight tile per SM), -1 = single CTA, 0 = auto */
 } dfv_gemm_tuning;
 int dfv_pw_gemm_fwd_tuned(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
                           const void* residual, void* out, int dtype, long long M, int K, int N, int act,

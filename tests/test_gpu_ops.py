@@ -237,9 +237,9 @@ def test_pw_gemm_full_size_every_element(ops):
             r = av.float() @ w.float().t() + bias
             r = r * torch.sigmoid(r) if act else r
             ref[i:i + 65536] = r + res[i:i + 65536].float() if gated else r
-        # planner's choice, two forced streaming plans, then streaming with the weight stage shared by TMA multicast over
-        # clusters of 2 and 4 CTAs (ragged M: the last cluster has phantom tiles) -- per-call tuning argument
-        for forced in (None, (0, 192), (0, 128), (0, 128, 2), (0, 0, 4)):
+        # planner's choice, forced single-CTA streaming plans, forced CTA-pair plans (cta_group::2; ragged M: the last pair
+        # has a phantom tile) -- per-call tuning argument (weight_stationary, N tile, cluster)
+        for forced in (None, (0, 192, -1), (0, 128, -1), (0, 128, 2), (0, 0, 2)):
             for rep in range(3):
                 y = ops.pw_gemm(a, w, bias, act, sc, rpi, res, tuning=forced)
                 bad = ((y.float() - ref).abs() > 0.03 * (ref.abs() + 1.0)).sum().item()
