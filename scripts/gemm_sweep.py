@@ -1,5 +1,5 @@
 """Measured tile-plan search for the tcgen05 1x1-conv GEMM: every distinct expand / project / head GEMM of B4 at batch 256
-under the planner's choice and under restricted plans (per-call dfv_gemm_tuning: weight-stationary flag, N tile)."""
+under the planner's choice and under restricted plans (per-call dfv_gemm_tuning: weight-stationary flag, N tile, 2 = CTA pair)."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -46,22 +46,23 @@ for (M, K, N, gated, rpi) in shapes:
     lib.dfv_gemm_plan_info(C.c_longlong(M), K, N, int(gated), info)
     base = timed(run)
     res = []
-    for ws in ((0,) if gated else (0, 1)):
-        for bn in ((32, 64, 96, 128, 192, 256) if gated else (64, 128, 192, 256)):
+    plans = [(ws, bn, cl) for ws in (0, 1) for bn in ((32, 64, 96, 128, 192, 256) if gated else (64, 128, 192, 256)) for cl in ((-1, 2) if ws == 0 else (-1,))]
+    for (ws, bn, cl) in plans:
+        if True:
             try:
-                y = run((ws, bn))
+                y = run((ws, bn, cl))
             except Exception:
                 continue
             chk = (C.c_int * 8)()
             if not torch.equal(y, ref) and (y.float() - ref.float()).abs().max().item() > 0.05:
-                print("MISMATCH", (M, K, N, gated), (ws, bn), flush=True)
+                print("MISMATCH", (M, K, N, gated), (ws, bn, cl), flush=True)
                 continue
-            res.append((timed(lambda: run((ws, bn)), 3), (ws, bn)))
+            res.append((timed(lambda: run((ws, bn, cl)), 3), (ws, bn, cl)))
     res.sort()
     nbytes = 2.0 * (M * K + M * N + N * K)
     key = f"M{M} K{K} N{N} {'gated' if gated else 'silu'}"
-    report[key] = dict(planner=dict(bn=info[0], ws=info[1], us=base * 1e3, gbs=nbytes / base / 1e6, tflops=2.0 * M * K * N / base / 1e9),
+    report[key] = dict(planner=dict(bn=info[0], ws=info[1], cl=info[8], us=base * 1e3, gbs=nbytes / base / 1e6, tflops=2.0 * M * K * N / base / 1e9),
                        best=[dict(plan=p, us=ms * 1e3) for ms, p in res[:4]])
-    print(f"{key}: planner bn={info[0]} ws={info[1]} {base*1e3:.0f} us | " + ", ".join(f"{p} {ms*1e3:.0f}" for ms, p in res[:4]), flush=True)
+    print(f"{key}: planner bn={info[0]} ws={info[1]} cl={info[8]} {base*1e3:.0f} us | " + ", ".join(f"{p} {ms*1e3:.0f}" for ms, p in res[:4]), flush=True)
     del a, ref
 print(json.dumps(report))
