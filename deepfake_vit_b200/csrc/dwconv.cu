@@ -127,39 +127,6 @@ __device__ __forceinline__ void finish_pixel(const float acc[8], float2 psum[4],
   }
 }
 
-// ---- 4-channel x L-pixel strips on packed fp32 (FFMA2) -- the 5x5 stride-1 layers --------------------------------------
-// The 8-channel FHFMA strips above issue one FMA per lane per slot: 25 per output, and with loads and the epilogue the
-// 5x5 layers are ISSUE-bound at ~75 % issue-active / 60 % FMA pipe (profiles/r01_final_full_dw7.txt).  Here a thread owns 4
-// channels and 12 pixels: bf16 pairs are widened to fp32 pairs once per loaded vector (2 ALU-pipe ops per pair, reused by up
-// to 5 taps) and every multiply-add is an FFMA2 on two channels -- half the FMA issue slots, the freed slots absorb loads and
-// unpacks, so the FP32 pipe (the real limit: 25 MACs per output at 128 lanes/SM) stays busy.  A 16-pixel input window per
-// 12 outputs also re-reads 1.33x instead of 1.67x from shared memory.  Same products, same accumulation order (kernel row,
-// then tap, ascending) as the 8-channel strips: the two variants are bit-identical.
-__device__ __forceinline__ float2 widen_bf16x2(uint32_t v) {
-  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
-}
-
-template <bool kAct, bool kHalf>
-__device__ __forceinline__ void finish_pixel4(const float2 acc[2], float2 psum[2], __nv_bfloat16* out) {
-  uint2 pk;
-  uint32_t* pw = &pk.x;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    float2 o;
-    if constexpr (kAct && kHalf) {
-      const float2 t = make_float2(tanh_fast(acc[j].x), tanh_fast(acc[j].y));
-      o = ffma2(acc[j], t, acc[j]);
-    } else if constexpr (kAct) {
-      o = make_float2(silu<false>(acc[j].x), silu<false>(acc[j].y));
-    } else {
-      o = acc[j];
-    }
-    psum[j] = fadd2(psum[j], o);
-    pw[j] = pack_bf16(o.x, o.y);
-  }
-  *reinterpret_cast<uint2*>(out) = pk;
-}
-
 // The fused squeeze tail (see SeFuse), deliberately NOT inlined: it recomputes the CTA's tile range from blockIdx so that
 // none of its state is live across the depthwise main loop (inlined, it cost that loop 7-8 % in spills).
 // The tile buffers are free when it runs: [ws: sq x (CB+1)] [ps: kSeGroup x CB].
@@ -236,13 +203,12 @@ __device__ __noinline__ void se_tail(unsigned char* smem_raw, const SeTailArgs a
 // kStats (training, kAct = false): per-channel sum / sum of squares of the raw conv output, accumulated in registers
 // over the whole kernel and added (double atomics, one per channel per CTA) into stats[2C] -- the BatchNorm
 // batch statistics without a separate pass over the output.
-template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats, int CG = 8>
+template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats>
 __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ CUtensorMap tmap,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        T* __restrict__ y, float* __restrict__ pool_partial,
                                                        double* __restrict__ stats, DwParams p, SeFuse se) {
   constexpr bool kHalf = kFast && kAct && sizeof(T) == 2;
-  static_assert(CG == 8 || (CG == 4 && sizeof(T) == 2 && !kStats && S == 1), "4-channel strips: bf16, stride 1, no statistics");
   const int CB = kCB ? kCB : p.CB;     // compile-time for the full-width chunk: shared-memory offsets become immediates
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [tile0][tile1][weights: K*K*CB T][bias: CB f32][red: nthreads*8 f32][red2: 4*CB f32][mbar x2]
@@ -296,26 +262,20 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
   __syncthreads();
 
   // fixed per-thread role
-  const int G = CB / CG;
+  const int G = CB >> 3;
   const int g = tid % G;
   const int j = (tid / G) % p.strips;
   const int r0 = tid / (G * p.strips);
-  const int c = c0 + g * CG;
+  const int c = c0 + g * 8;
   const bool chan_ok = c < p.C;
-  const int in_off0 = ((r0 * S) * p.TWI + j * L * S) * CB + g * CG;
+  const int in_off0 = ((r0 * S) * p.TWI + j * L * S) * CB + g * 8;
   const int in_step = p.rpr * S * p.TWI * CB;
-  const int out_off0 = (r0 * p.Wo + j * L) * p.C + g * CG;
+  const int out_off0 = (r0 * p.Wo + j * L) * p.C + g * 8;
   const int out_step = p.rpr * p.Wo * p.C;
   const int row_stride = p.TWI * CB;
-  const T* wbase = wsm + g * CG;
+  const T* wbase = wsm + g * 8;
   float bv[8];
-  if constexpr (CG == 8) {
-    load8(bsm + g * 8, bv);
-  } else {
-    const float4 b4 = *reinterpret_cast<const float4*>(bsm + g * 4);
-    bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
-    bv[4] = bv[5] = bv[6] = bv[7] = 0.f;
-  }
+  load8(bsm + g * 8, bv);
   constexpr int NI = (L - 1) * S + K;  // input window per kernel row
   const int nth = blockDim.x;
 
@@ -341,81 +301,38 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
       int r = r0, in_off = in_off0, out_off = out_off0;
       for (int rr = 0; rr < p.rounds; ++rr, r += p.rpr, in_off += in_step, out_off += out_step) {
         if (r >= p.TH || r >= hrem) break;
-        if constexpr (CG == 4) {
-          float2 acc[L][2];
+        float acc[L][8];
 #pragma unroll
-          for (int l = 0; l < L; ++l) {
-            acc[l][0] = make_float2(bv[0], bv[1]);
-            acc[l][1] = make_float2(bv[2], bv[3]);
-          }
-          const __nv_bfloat16* in = tile + in_off;
+        for (int l = 0; l < L; ++l)
 #pragma unroll
-          for (int kh = 0; kh < K; ++kh) {
-            float2 wk[K][2];
+          for (int e = 0; e < 8; ++e) acc[l][e] = bv[e];
+
+        const T* in = tile + in_off;
 #pragma unroll
-            for (int kw = 0; kw < K; ++kw) {
-              const uint2 wv = *reinterpret_cast<const uint2*>(wbase + (kh * K + kw) * CB);
-              wk[kw][0] = widen_bf16x2(wv.x);
-              wk[kw][1] = widen_bf16x2(wv.y);
-            }
-            const __nv_bfloat16* row = in + kh * row_stride;
+        for (int kh = 0; kh < K; ++kh) {
+          Vec8<T> wk[K];
 #pragma unroll
-            for (int iw = 0; iw < NI; ++iw) {
-              const uint2 v = *reinterpret_cast<const uint2*>(row + iw * CB);
-              const float2 x0 = widen_bf16x2(v.x), x1 = widen_bf16x2(v.y);
+          for (int kw = 0; kw < K; ++kw) ldvec(wbase + (kh * K + kw) * CB, wk[kw]);
+          const T* row = in + kh * row_stride;
 #pragma unroll
-              for (int l = 0; l < L; ++l) {
-                const int kw = iw - l;
-                if (kw >= 0 && kw < K) {
-                  acc[l][0] = ffma2(x0, wk[kw][0], acc[l][0]);
-                  acc[l][1] = ffma2(x1, wk[kw][1], acc[l][1]);
-                }
-              }
+          for (int iw = 0; iw < NI; ++iw) {
+            Vec8<T> v;
+            ldvec(row + iw * CB, v);
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+              const int kw = iw - l * S;
+              if (kw >= 0 && kw < K) fma8(v, wk[kw], acc[l]);
             }
           }
-          __nv_bfloat16* out = out_tile + out_off;
-          if (wrem >= L) {
+        }
+        T* out = out_tile + out_off;
+        if (wrem >= L) {
 #pragma unroll
-            for (int l = 0; l < L; ++l) finish_pixel4<kAct, kHalf>(acc[l], psum, out + (size_t)l * p.C);
-          } else {
-#pragma unroll
-            for (int l = 0; l < L; ++l)
-              if (l < wrem) finish_pixel4<kAct, kHalf>(acc[l], psum, out + (size_t)l * p.C);
-          }
+          for (int l = 0; l < L; ++l) finish_pixel<T, kAct, kHalf, kStats>(acc[l], psum, psq, out + (size_t)l * p.C);
         } else {
-          float acc[L][8];
 #pragma unroll
           for (int l = 0; l < L; ++l)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[l][e] = bv[e];
-
-          const T* in = tile + in_off;
-#pragma unroll
-          for (int kh = 0; kh < K; ++kh) {
-            Vec8<T> wk[K];
-#pragma unroll
-            for (int kw = 0; kw < K; ++kw) ldvec(wbase + (kh * K + kw) * CB, wk[kw]);
-            const T* row = in + kh * row_stride;
-#pragma unroll
-            for (int iw = 0; iw < NI; ++iw) {
-              Vec8<T> v;
-              ldvec(row + iw * CB, v);
-#pragma unroll
-              for (int l = 0; l < L; ++l) {
-                const int kw = iw - l * S;
-                if (kw >= 0 && kw < K) fma8(v, wk[kw], acc[l]);
-              }
-            }
-          }
-          T* out = out_tile + out_off;
-          if (wrem >= L) {
-#pragma unroll
-            for (int l = 0; l < L; ++l) finish_pixel<T, kAct, kHalf, kStats>(acc[l], psum, psq, out + (size_t)l * p.C);
-          } else {
-#pragma unroll
-            for (int l = 0; l < L; ++l)
-              if (l < wrem) finish_pixel<T, kAct, kHalf, kStats>(acc[l], psum, psq, out + (size_t)l * p.C);
-          }
+            if (l < wrem) finish_pixel<T, kAct, kHalf, kStats>(acc[l], psum, psq, out + (size_t)l * p.C);
         }
       }
     }
@@ -424,18 +341,18 @@ __global__ void __launch_bounds__(256, 2) dwconv_kernel(const __grid_constant__ 
     if (flush) {
       // deterministic two-stage CTA reduction over the threads that share a channel group (tid = g + G*i)
 #pragma unroll
-      for (int e = 0; e < CG / 2; ++e) {
-        red[tid * CG + 2 * e] = psum[e].x;
-        red[tid * CG + 2 * e + 1] = psum[e].y;
+      for (int e = 0; e < 4; ++e) {
+        red[tid * 8 + 2 * e] = psum[e].x;
+        red[tid * 8 + 2 * e + 1] = psum[e].y;
         psum[e] = make_float2(0.f, 0.f);
       }
       __syncthreads();   // also: everyone is done with tile[buf] before it is refilled
       const int R = p.red_parts;
       for (int idx = tid; idx < CB * R; idx += nth) {
         const int o = idx % CB, q = idx / CB;
-        const int gg = o / CG, e = o % CG;
+        const int gg = o >> 3, e = o & 7;
         float s = 0.f;
-        for (int u = gg + G * q; u < nth; u += G * R) s += red[u * CG + e];
+        for (int u = gg + G * q; u < nth; u += G * R) s += red[u * 8 + e];
         red2[idx] = s;
       }
       __syncthreads();
@@ -510,7 +427,7 @@ struct DwPlan {
 // threads busy (<= 256 per CTA, two CTAs per SM), wastes the fewest tile cells on the image edge and re-reads the
 // smallest halo.  Every candidate is a valid launch; the score only ranks them.
 static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, int pad_lo, int pad_hi,
-                     const dfv_dwconv_tuning* tuning = nullptr, bool allow_pk = true) {
+                     const dfv_dwconv_tuning* tuning = nullptr) {
   DwParams& p = pl->p;
   p.C = C;
   p.Ho = (H + pad_lo + pad_hi - K) / S + 1;
@@ -519,11 +436,9 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
   p.pad = pad_lo;
   const size_t ts = dtype_size(dtype);
   const int cb_cap = dtype == DFV_BF16 ? 64 : 32;
-  // strip variants: L = 12 is the 4-channel packed-fp32 strip (5x5 stride-1 bf16 layers with full-width chunks only)
-  const bool pk_ok = allow_pk && dtype == DFV_BF16 && K == 5 && S == 1 && C >= cb_cap;
-  const int Ls1[4] = {12, 8, 6, 4}, Ls2[1] = {4};
+  const int Ls1[3] = {8, 6, 4}, Ls2[1] = {4};
   const int* Ls = S == 1 ? Ls1 : Ls2;
-  const int nL = S == 1 ? 4 : 1;
+  const int nL = S == 1 ? 3 : 1;
   double best = -1.0;
   // a caller-supplied dfv_dwconv_tuning (0 = free) restricts the search for stride-1 layers
   int fL = tuning ? tuning->L : 0, fTW = tuning ? tuning->TW : 0, fTH = tuning ? tuning->TH : 0, fCB = tuning ? tuning->CB : 0;
@@ -534,13 +449,12 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
     // channels of the last chunk; its threads are masked): 8 channel groups = one 128-byte shared-memory row per
     // pixel, the only width whose quarter-warp vector loads never collide on a bank
     if (C % cb && !(cb == cb_cap && C > cb)) continue;
+    const int G = cb / 8;
     const double waste = (double)C / ((double)((C + cb - 1) / cb) * cb);
     const double banks = (cb * ts == 128) ? 1.0 : (cb * ts > 64 ? 0.8 : 0.65);
     for (int li = 0; li < nL; ++li) {
       const int L = Ls[li];
       if (fL && L != fL) continue;
-      if (L == 12 && !(pk_ok && cb == cb_cap)) continue;
-      const int G = cb / (L == 12 ? 4 : 8);
       for (int strips = 1; strips * L <= 48; ++strips) {
         const int TW = strips * L;
         if (fTW && TW != fTW) continue;
@@ -569,9 +483,7 @@ static int make_plan(DwPlan* pl, int dtype, int H, int W, int C, int K, int S, i
           const double busy = (double)TH / (rounds * rpr);              // rows actually computed per round slot
           const double threads = std::min(1.0, nt / 256.0) * ((nt % 32 == 0) ? 1.0 : (double)nt / ((nt + 31) / 32 * 32));
           const double halo = (double)(TH * S) * (TW * S) / ((double)THI * TWI);
-          // 8-channel strips, L = 8: 64 accumulators + a row of weight vectors = 128 registers, spills.  4-channel packed-fp32
-          // strips: half the FMA issue slots and a 16/12 instead of 10/6 input window -- measured 1.25-1.4x on the 5x5 layers
-          const double regs = L == 8 ? 0.9 : (L == 12 ? 1.3 : 1.0);
+          const double regs = L == 8 ? 0.9 : 1.0;                      // 64 accumulators + a row of weight vectors: 128 registers, spills
           const double per_tile = (double)TH * TW / (TH * TW + 24.0);  // fixed per-tile cost (barrier, TMA issue)
           const double seg = std::min(1.0, (double)cb * ts / 128.0);   // contiguous bytes per pixel the TMA box fetches
           const double score = cover * busy * threads * (0.6 + 0.4 * halo) * regs * per_tile * (0.3 + 0.7 * seg) * waste * banks;
@@ -628,10 +540,10 @@ static bool se_tail_fits(const DwPlan& pl, int sq) {
   return sq > 0 && sq <= 256 && need <= two_tiles_min;
 }
 
-template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats, int CG = 8>
+template <typename T, int K, int S, int L, bool kFast, bool kAct, int kCB, bool kStats>
 static int launch(const CUtensorMap& tm, const float* w, const float* bias, void* y, float* pool, double* stats, DwPlan& pl, int B,
                   cudaStream_t st, const SeFuse& se) {
-  auto kern = dwconv_kernel<T, K, S, L, kFast, kAct, kCB, kStats, CG>;
+  auto kern = dwconv_kernel<T, K, S, L, kFast, kAct, kCB, kStats>;
   static thread_local bool configured = false;
   if (!configured) {
     DFV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -658,12 +570,6 @@ static int dispatch(int K, int S, int L, int act, const CUtensorMap& tm, const f
     }                                                                                                       \
     if (act) return launch<T, k, s, l, kFast, true, 0, false>(tm, w, bias, y, pool, stats, pl, B, st, se);      \
     return launch<T, k, s, l, kFast, false, 0, false>(tm, w, bias, y, pool, stats, pl, B, st, se);              \
-  }
-  if constexpr (sizeof(T) == 2) {
-    if (K == 5 && S == 1 && L == 12 && !stats && pl.p.CB == 64) {
-      if (act) return launch<T, 5, 1, 12, kFast, true, 64, false, 4>(tm, w, bias, y, pool, stats, pl, B, st, se);
-      return launch<T, 5, 1, 12, kFast, false, 64, false, 4>(tm, w, bias, y, pool, stats, pl, B, st, se);
-    }
   }
   DW_CASE(3, 1, 8) DW_CASE(3, 1, 6) DW_CASE(3, 1, 4) DW_CASE(5, 1, 8) DW_CASE(5, 1, 6) DW_CASE(5, 1, 4)
   DW_CASE(3, 2, 4) DW_CASE(5, 2, 4)
@@ -717,7 +623,7 @@ static int dwconv_entry(const void* x, const float* w, const float* bias, void* 
   DFV_REQUIRE(pad_lo >= 0 && pad_hi >= 0 && pad_lo < kernel && pad_hi < kernel, "dfv_dwconv_fwd: bad pad");
   if (debug_flags() & 1) return DFV_OK;
   DwPlan pl;
-  DFV_REQUIRE(make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi, tuning, stats == nullptr) == DFV_OK,
+  DFV_REQUIRE(make_plan(&pl, dtype, H, W, C, kernel, stride, pad_lo, pad_hi, tuning) == DFV_OK,
               "dfv_dwconv_fwd: cannot tile H=%d W=%d C=%d k=%d s=%d", H, W, C, kernel, stride);
   pl.p.act = act;
   const size_t es = dtype_size(dtype);

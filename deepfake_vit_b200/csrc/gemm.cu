@@ -124,6 +124,9 @@ struct TcParams {
   long long n_tiles_m;
   int cl;             // streaming plans: 2 = CTA pair (cta_group::2).  The two CTAs of a cluster take consecutive M tiles of
                       // the SAME N tile; each loads its A tile and HALF of the weight tile's rows, the leader issues M = 256 MMAs
+  int nsub;           // streaming plans with exactly two N tiles: 2 = both N tiles of an M tile share ONE A stage -- the stage carries A and the
+                      // weight rows of both tiles, the MMA thread accumulates into the two TMEM buffers side by side, the A operand (and its
+                      // gate transform) is fetched once instead of once per N tile.  The price: no accumulator double-buffering across tiles
   int k_blocks;
   int stages;
   int rows_per_image;
@@ -170,7 +173,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t a_bytes = kBM * kBK * 2;
   constexpr bool pair = kPair;                                             // CTA pair: this CTA stages half of the weight tile's rows
   const uint32_t b_bytes = (uint32_t)(pair ? p.BN / 2 : p.BN) * kBK * 2;
-  const uint32_t stage_bytes = b_res ? a_bytes : a_bytes + b_bytes;        // weight-stationary: stages carry A only
+  const bool dual = p.nsub == 2;                                           // both N tiles of an M tile ride on one A stage
+  const uint32_t stage_bytes = b_res ? a_bytes : a_bytes + (dual ? 2 : 1) * b_bytes;        // weight-stationary: stages carry A only
   unsigned char* tiles = smem;
   constexpr int kNumEpiW = kNumWorkers - (kHasScale ? 8 : 0);
   unsigned char* bres = smem + (size_t)p.stages * stage_bytes;               // [k_blocks][BN x 64] resident weight tile
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (long long t = t_begin; t < t_end; ++t) {
         const long long mt = tile_m(t);
         const int nt = tile_n(t);
+        if (dual && nt != 0) continue;      // its operands arrived with the first N tile of this M tile
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1, 1);
           unsigned char* sa = tiles + (size_t)stage * stage_bytes;
@@ -250,11 +255,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               mbar_expect_tx(&bars->full[stage], stage_bytes);
               tma_load_2d(sa, &tm_a, &bars->full[stage], kb * kBK, (int)(mt * kBM));
               tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, brow);
+              if (dual) tma_load_2d(sa + a_bytes + b_bytes, &tm_b, &bars->full[stage], kb * kBK, brow + p.BN);
             } else {
               if (leader) mbar_expect_tx(&bars->full[stage], 2 * stage_bytes);
               const uint32_t lbar = mapa_shared(&bars->full[stage], 0);
               tma_load_2d_pair(sa, &tm_a, lbar, kb * kBK, (int)(mt * kBM));
               tma_load_2d_pair(sa + a_bytes, &tm_b, lbar, kb * kBK, brow);
+              if (dual) tma_load_2d_pair(sa + a_bytes + b_bytes, &tm_b, lbar, kb * kBK, brow + p.BN);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             continue;
@@ -262,6 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           mbar_expect_tx(&bars->full[stage], stage_bytes);
           tma_load_2d(sa, &tm_a, &bars->full[stage], kb * kBK, (int)(mt * kBM));
           if (!b_res) tma_load_2d(sa + a_bytes, &tm_b, &bars->full[stage], kb * kBK, nt * p.BN);
+          if (dual) tma_load_2d(sa + a_bytes + b_bytes, &tm_b, &bars->full[stage], kb * kBK, (nt + 1) * p.BN);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -278,7 +286,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (long long t = t_begin; t < t_end; ++t, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        if (dual && as != 0) continue;      // second N tile of the M tile: accumulated together with the first (a CTA's range holds whole M tiles)
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1, 2);
+        if (dual) mbar_wait(&bars->tmem_empty[1], aphase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -286,20 +296,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
           const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(b_res ? smem_u32(bres + (size_t)kb * b_bytes) : sa + a_bytes);
+          const uint64_t db2 = make_sw128_desc(sa + a_bytes + b_bytes);
           const int k_left = p.K - kb * kBK;
           const int ksteps = k_left >= kBK ? kBK / 16 : (k_left + 15) / 16;
           if (pair) {
-            for (int k = 0; k < ksteps; ++k)
+            for (int k = 0; k < ksteps; ++k) {
               umma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              if (dual) umma_bf16_pair(d_tmem + 256, da + (uint64_t)(k * 2), db2 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
             umma_commit_pair(&bars->empty[stage]);      // frees the stage in both CTAs
           } else {
-            for (int k = 0; k < ksteps; ++k)
+            for (int k = 0; k < ksteps; ++k) {
               umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              if (dual) umma_bf16(d_tmem + 256, da + (uint64_t)(k * 2), db2 + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
             umma_commit(&bars->empty[stage]);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (pair) umma_commit_pair(&bars->tmem_full[as]); else umma_commit(&bars->tmem_full[as]);
+        if (dual) { if (pair) umma_commit_pair(&bars->tmem_full[1]); else umma_commit(&bars->tmem_full[1]); }
       }
     }
   } else if (kHasScale && warp < kFirstWorker + kNumXform) {
@@ -325,6 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     int stage = 0;                                        // stage / phase of the running k-block (all tiles)
     uint32_t phase = 0;
     for (long long t = t_begin; t < t_end; ++t) {
+      if (dual && tile_n(t) != 0) continue;                      // the A stages of this M tile were transformed with its first N tile
       const long long m0 = tile_m(t) * kBM;
       while (m0 >= (img_lo + 1) * p.rows_per_image) ++img_lo;   // tiles are visited in increasing m: at most a step or two
       const long long m = m0 + row;
@@ -636,6 +653,18 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
     if (want != 2 || (p.BN / 2) % 8 != 0 || p.BN % 32 != 0 || n_tm < 4) want = 1;
     p.cl = want;
   }
+  // Shared-A plans: a streaming GEMM with exactly two N tiles fetches (and, gated, transforms) every A stage twice.  What
+  // paces the wide-K project GEMMs of the 12x12 stage is the byte rate INTO the SMs (L2 -> SM: 16 KB of A + the weight rows
+  // per k-block and N tile; ~7-8 TB/s over the chip whether the bytes come from HBM or L2), so both N tiles ride on one A
+  // stage and accumulate side by side in the two TMEM buffers: per k-block 16 + 2 x BN/8 KB instead of 2 x (16 + BN/8) KB.
+  // Gated GEMMs only: their epilogue (bias + residual, no activation) is short, and without accumulator double-buffering
+  // it is exposed once per M tile.
+  p.nsub = 1;
+  {
+    const int want = tuning ? tuning->share_a : 0;
+    const bool ok = !p.b_res && p.n_tiles_n == 2 && 2 * p.BN <= (int)kTmemCols;
+    if (ok && (want == 1 || (want == 0 && scaled && k_blocks >= 8))) p.nsub = 2;
+  }
   p.nb = p.cw > 64 ? 2 : 1;
   p.bw = p.cw / p.nb;
   p.swz = p.bw == 64 ? 3 : (p.bw == 32 ? 2 : (p.bw == 16 ? 1 : 0));
@@ -645,15 +674,21 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   p.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
   p.act = act;
   const size_t a_stage = (size_t)kBM * kBK * 2;
-  const size_t stage_bytes = p.b_res ? a_stage : a_stage + (size_t)(p.cl == 2 ? p.BN / 2 : p.BN) * kBK * 2;
   const size_t resident = p.b_res ? (size_t)k_blocks * p.BN * kBK * 2 : 0;
   const size_t staging = (size_t)p.BN * 256;            // all epilogue warps, one buffer each
   const size_t tail = tail_bytes(p.BN) + resident;
-  p.nbuf = (2 * staging + (p.b_res ? 5 : 3) * stage_bytes + tail <= 222 * 1024) ? 2 : 1;     // (the measured plans' rule)
-  // gated GEMMs write little and wait long (load -> gate transform -> MMA per stage): a pipeline stage is worth more
-  // than a second staging buffer unless six stages fit anyway
-  if (scaled && p.nbuf == 2 && 2 * staging + 6 * stage_bytes + tail > budget) p.nbuf = 1;
-  int stages = (int)((budget - tail - p.nbuf * staging) / stage_bytes);
+  size_t stage_bytes = 0;
+  int stages = 0;
+  for (;;) {
+    stage_bytes = p.b_res ? a_stage : a_stage + (size_t)p.nsub * (size_t)(p.cl == 2 ? p.BN / 2 : p.BN) * kBK * 2;
+    p.nbuf = (2 * staging + (p.b_res ? 5 : 3) * stage_bytes + tail <= 222 * 1024) ? 2 : 1;     // (the measured plans' rule)
+    // gated GEMMs write little and wait long (load -> gate transform -> MMA per stage): a pipeline stage is worth more
+    // than a second staging buffer unless six stages fit anyway
+    if (scaled && p.nbuf == 2 && 2 * staging + 6 * stage_bytes + tail > budget) p.nbuf = 1;
+    stages = (int)((budget - tail - p.nbuf * staging) / stage_bytes);
+    if (p.nsub == 2 && stages < 3) { p.nsub = 1; continue; }      // a shared-A stage is up to 80 KB: without three of them, do not share
+    break;
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   DFV_REQUIRE(stages >= 2, "dfv_pw_gemm_fwd: tile does not fit shared memory (N=%d)", N);
   p.stages = stages;
@@ -667,6 +702,7 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
     if (max_clusters > 0 && p.cl > 1 && max_clusters < slots) slots = max_clusters;
     long long nc = p.n_tiles < slots ? p.n_tiles : slots;
     p.tiles_per_cta = (p.n_tiles + nc - 1) / nc;
+    if (p.nsub == 2) p.tiles_per_cta += p.tiles_per_cta & 1;      // whole M tiles (both N tiles) per CTA
     nc = (p.n_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     grid = nc * p.cl;
   }
@@ -686,7 +722,7 @@ extern "C" int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* ou
   }
   DFV_TRY(plan_tc(p, smem, grid, M, K, N, scaled != 0, 1, 0));
   out[0] = p.BN; out[1] = p.b_res; out[2] = p.stages; out[3] = p.nbuf; out[4] = (int)grid; out[5] = (int)p.tiles_per_cta;
-  out[6] = (int)smem; out[7] = p.n_tiles_n; out[8] = p.cl;
+  out[6] = (int)smem; out[7] = p.n_tiles_n; out[8] = p.cl; out[9] = p.nsub;
   return DFV_OK;
 }
 

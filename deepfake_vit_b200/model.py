@@ -712,7 +712,19 @@ class DeepfakeDetectionModel(nn.Module):
     def forward(self, images: torch.Tensor, landmarks: Optional[torch.Tensor] = None,
                 return_features: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """images: (B, 3, H, W) fp32 normalised crops (the reference's contract, src/data/dataset.py:82-116) or
-        (B, H, W, 3) uint8 RGB crops, normalised inside the stem kernel."""
+        (B, H, W, 3) uint8 RGB crops, normalised inside the stem kernel.
+
+        Mixed precision (trainer.py:137-141 runs the model under `torch.cuda.amp.autocast()`): inside an autocast region
+        the call computes on the bf16 tensor-core path whatever `set_compute_dtype` says -- bf16 is this library's reduced
+        precision (fp16's range is why the reference needs its GradScaler; the scaler protocol is honoured all the same:
+        the scale arrives through the loss gradient, `unscale_` / `clip_grad_norm_` / `scaler.step` see ordinary fp32
+        `.grad` tensors).  Logits and features are fp32 either way."""
+        if torch.is_autocast_enabled("cuda") and self.compute_dtype != torch.bfloat16:
+            prev, self.compute_dtype = self.compute_dtype, torch.bfloat16
+            try:
+                return self.forward(images, landmarks, return_features)
+            finally:
+                self.compute_dtype = prev
         self._check_modes()
         if self.training:
             # grad mode is read HERE: inside autograd.Function.forward it is always off

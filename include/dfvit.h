@@ -496,9 +496,9 @@ int dfv_clip_adamw_step(float* params, const float* grads, float* exp_avg, float
 /* Plan introspection (host only, pure functions of the shape): the depthwise tile plan chosen for a layer.
  * out[0..9] = CB, L, TW, TH, threads, smem bytes, tiles_w, tiles_h, pool parts, grid. */
 int dfv_dwconv_plan_info(int dtype, int B, int H, int W, int C, int kernel, int stride, int pad_lo, int pad_hi, int* out);
-/* Tile plan of a bf16 tensor-core 1x1-conv GEMM (host only): out[0..8] = N tile, weight-stationary flag, pipeline
+/* Tile plan of a bf16 tensor-core 1x1-conv GEMM (host only): out[0..9] = N tile, weight-stationary flag, pipeline
  * stages, staging buffers, grid, tiles per CTA, shared-memory bytes, N tiles, CTAs per cluster (2 = CTA-pair plan,
- * cta_group::2). */
+ * cta_group::2), N tiles per A stage (2 = shared-A plan: both N tiles of an M tile accumulate from one A stage). */
 int dfv_gemm_plan_info(long long M, int K, int N, int scaled, int* out);
 
 /* Tuning entry points: the same operators with the tile plan restricted by the CALLER (a per-call argument: no
@@ -508,6 +508,7 @@ typedef struct {
   int32_t weight_stationary;   /* -1 auto, 0 streaming, 1 weight-stationary */
   int32_t bn;                  /* N tile (0 = auto) */
   int32_t cluster;             /* streaming plans: 2 = CTA pair (cta_group::2: M = 256 over two SMs, half of the weight tile per SM), -1 = single CTA, 0 = auto */
+  int32_t share_a;             /* streaming plans with two N tiles: 1 = both N tiles share each A stage (two accumulators side by side in TMEM), -1 = off, 0 = auto */
 } dfv_gemm_tuning;
 int dfv_pw_gemm_fwd_tuned(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
                           const void* residual, void* out, int dtype, long long M, int K, int N, int act,

@@ -42,7 +42,7 @@ for (M, K, N, gated, rpi) in shapes:
     act = 0 if gated else 1
     run = lambda tn=None: ops.pw_gemm(a, w, bias, act, sc, rpi if gated else 0, None, tuning=tn)
     ref = run()
-    info = (C.c_int * 9)()
+    info = (C.c_int * 10)()
     lib.dfv_gemm_plan_info(C.c_longlong(M), K, N, int(gated), info)
     base = timed(run)
     res = []

@@ -18,7 +18,7 @@ layers = [("b0 project", 190, 48, 24, 1), ("b1 project", 190, 24, 24, 1), ("b2 e
           ("b16 project", 24, 672, 160, 1), ("b17 expand", 24, 160, 960, 0), ("b17 project", 24, 960, 160, 1), ("b22 project", 12, 960, 272, 1),
           ("b23 expand", 12, 272, 1632, 0), ("b23 project", 12, 1632, 272, 1), ("b30 project", 12, 1632, 448, 1), ("b31 expand", 12, 448, 2688, 0),
           ("b31 project", 12, 2688, 448, 1), ("head", 12, 448, 1792, 0)]
-out = (C.c_int * 9)()
+out = (C.c_int * 10)()
 print(f"{'layer':12s} {'M':>9s} {'K':>5s} {'N':>5s} g f |  BN res stg nbuf grid t/cta   smem ntn  cl")
 for name, H, K, N, g in layers:
     M = B * H * H

@@ -499,3 +499,78 @@ def test_graphed_train_step_replays_the_eager_step():
     g2 = [step3(x, lm, y)["total"].item(), m3._last_flat_grad.clone()]
     assert g1[0] != g2[0] and not torch.equal(g1[1], g2[1])
     assert torch.isfinite(g2[1]).all() and torch.isfinite(a).all()
+
+
+def test_amp_branch_of_the_reference_trainer():
+    """trainer.py:137-167 verbatim -- autocast + GradScaler + gradient accumulation + unscale_ + clip_grad_norm_ +
+    scaler.step / update / zero_grad -- against the plain branch (trainer.py:168-189) on a twin model: inside autocast the
+    model computes in bf16 (its reduced precision), the loss scale (a power of two) passes through CombinedLoss and the
+    backward kernels and cancels exactly in unscale_, so both branches must land on the same weights; an overflowing step is
+    skipped and halves the scale."""
+    import deepfake_vit_b200 as d
+    from oracle import calibrate
+    _, m_amp, _, _ = _pair(96, stochastic=True)
+    m_std = copy.deepcopy(m_amp)
+    m_std.set_compute_dtype(torch.bfloat16)
+    m_amp.set_compute_dtype(torch.float32)            # autocast must override this
+    crit = d.CombinedLoss(LOSS_W, torch.tensor([1.0, 1.5]))
+    cfg = dict(accumulation_steps=2, gradient_clip=1.0)
+    batches = [calibrate.synthetic_batch(4, 96, seed=70 + i) for i in range(4)]
+
+    def run(model, use_amp):
+        model.train()
+        opt = d.FusedAdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, grad_source=model)
+        scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 12) if use_amp else None
+        seen = []                                      # the clipped gradients every optimizer step consumed
+        for batch_idx, (x, lm, y) in enumerate(batches):
+            torch.manual_seed(1000 + batch_idx)        # same dropout / drop-connect masks in both branches
+            images, landmarks, labels = x.to(DEV), lm.to(DEV), y.to(DEV)
+            if use_amp:
+                with torch.autocast("cuda"):
+                    logits, features = model(images, landmarks, return_features=True)
+                    loss = crit(logits, labels, features)["total"]
+                    loss = loss / cfg["accumulation_steps"]
+                assert logits.dtype == torch.float32
+                scaler.scale(loss).backward()
+                if (batch_idx + 1) % cfg["accumulation_steps"] == 0:
+                    scaler.unscale_(opt)
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), cfg["gradient_clip"])
+                    seen.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone())
+                    scaler.step(opt)
+                    scaler.update()
+                    opt.zero_grad()
+            else:
+                logits, features = model(images, landmarks, return_features=True)
+                loss = crit(logits, labels, features)["total"] / cfg["accumulation_steps"]
+                loss.backward()
+                if (batch_idx + 1) % cfg["accumulation_steps"] == 0:
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), cfg["gradient_clip"])
+                    seen.append(torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone())
+                    opt.step()
+                    opt.zero_grad()
+        return opt, scaler, seen
+
+    opt_amp, scaler, g_amp = run(m_amp, True)
+    _, _, g_std = run(m_std, False)
+    # first optimizer step: identical weights on both sides, so the accumulated, unscaled, clipped gradients must agree to the
+    # rounding of the atomic weight-gradient reductions.  (Adam turns rounding-level differences of near-zero gradients into
+    # +-lr steps, so from the second step on the weights -- and the gradients -- only agree loosely.)
+    r1, r2 = rel(g_amp[0], g_std[0]), rel(g_amp[1], g_std[1])
+    moved = max(rel(a, b) for a, b in zip(m_amp.parameters(), m_std.parameters()))
+    print(f"AMP branch vs plain branch: gradient of step 1 rel diff {r1:.2e}, step 2 {r2:.2e}; worst parameter rel diff {moved:.2e}")
+    assert r1 < 2e-5 and r2 < 0.2 and moved < 0.1, (r1, r2, moved)
+    assert m_amp.compute_dtype == torch.float32 and scaler.get_scale() == 2.0 ** 12
+
+    # an overflowing step: skipped, scale halved (GradScaler's contract)
+    before = [p.detach().clone() for p in m_amp.parameters()]
+    x, lm, y = batches[0]
+    with torch.autocast("cuda"):
+        logits, features = m_amp(x.to(DEV), lm.to(DEV), return_features=True)
+        loss = crit(logits, y.to(DEV), features)["total"] * 3e38
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt_amp)
+    scaler.step(opt_amp)
+    scaler.update()
+    opt_amp.zero_grad()
+    assert scaler.get_scale() == 2.0 ** 11
+    assert all(torch.equal(a, b) for a, b in zip(before, m_amp.parameters()))
