@@ -43,7 +43,7 @@ class InferArgs(C.Structure):
 
 
 class GemmTuning(C.Structure):
-    _fields_ = [("weight_stationary", C.c_int32), ("bn", C.c_int32), ("cluster", C.c_int32), ("share_a", C.c_int32)]
+    _fields_ = [("weight_stationary", C.c_int32), ("bn", C.c_int32), ("cluster", C.c_int32), ("share_a", C.c_int32), ("rotate", C.c_int32)]
 
 
 class DwconvTuning(C.Structure):

@@ -127,6 +127,7 @@ struct TcParams {
   int nsub;           // streaming plans with exactly two N tiles: 2 = both N tiles of an M tile share ONE A stage -- the stage carries A and the
                       // weight rows of both tiles, the MMA thread accumulates into the two TMEM buffers side by side, the A operand (and its
                       // gate transform) is fetched once instead of once per N tile.  The price: no accumulator double-buffering across tiles
+  int rotate;         // streaming plans: 1 = every cluster starts its walk over the N tiles at a different tile (see tile_n)
   int k_blocks;
   int stages;
   int rows_per_image;
@@ -160,7 +161,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // (expand / head GEMMs) all sixteen are epilogue warps.
 // kPair: the CTA-pair (cta_group::2) variant -- a separate instantiation, because a kernel that contains cta_group::2
 // instructions can only be launched as a cluster of two (a plain launch fails with "cluster misconfiguration").
-template <bool kHasScale, int kAct, bool kRes, bool kPair>
+template <bool kHasScale, int kAct, bool kRes, bool kPair, bool kDual = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
     pw_gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
@@ -173,11 +174,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const uint32_t a_bytes = kBM * kBK * 2;
   constexpr bool pair = kPair;                                             // CTA pair: this CTA stages half of the weight tile's rows
   const uint32_t b_bytes = (uint32_t)(pair ? p.BN / 2 : p.BN) * kBK * 2;
-  const bool dual = p.nsub == 2;                                           // both N tiles of an M tile ride on one A stage
+  constexpr bool dual = kDual;                                             // both N tiles of an M tile ride on one A stage (p.nsub == 2)
   const uint32_t stage_bytes = b_res ? a_bytes : a_bytes + (dual ? 2 : 1) * b_bytes;        // weight-stationary: stages carry A only
   unsigned char* tiles = smem;
   constexpr int kNumEpiW = kNumWorkers - (kHasScale ? 8 : 0);
-  unsigned char* bres = smem + (size_t)p.stages * stage_bytes;               // [k_blocks][BN x 64] resident weight tile
+  unsigned char* bres = tiles + (size_t)p.stages * stage_bytes;              // [k_blocks][BN x 64] resident weight tile
   unsigned char* staging = bres + (b_res ? (size_t)p.k_blocks * b_bytes : 0);   // [epilogue warp][nbuf][nb][32 rows x bw]
   const uint32_t warp_stage_bytes = (uint32_t)p.cw * 64;                     // 32 rows x cw columns x 2 B
   float* bias_sm = reinterpret_cast<float*>(staging + (size_t)kNumEpiW * p.nbuf * warp_stage_bytes);
@@ -196,7 +197,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const long long t_end = min(t_begin + p.tiles_per_cta, b_res ? p.n_tiles_m : p.n_tiles);
   const int nt_res = b_res ? (int)(blockIdx.x / p.m_splits) : 0;
   auto tile_m = [&](long long t) -> long long { return b_res ? t : (t / p.n_tiles_n) * cl + crank; };
-  auto tile_n = [&](long long t) -> int { return b_res ? nt_res : (int)(t % p.n_tiles_n); };
+  // Streaming plans walk the N tiles of an M tile in an order ROTATED by the M tile's index: CTAs run in near lockstep on
+  // different M tiles, and without the rotation all of them fetch the same weight tile (the same few hundred L2 lines, i.e.
+  // the same few L2 slices) at the same moment while the other slices idle.  The rotation is a function of the M tile only, so
+  // the (M tile, N tile) pairs stay a bijection however the tile range is cut into CTAs.
+  const bool rotate = !b_res && !dual && p.rotate != 0 && p.n_tiles_n > 1;
+  auto tile_n = [&](long long t) -> int {
+    if (b_res) return nt_res;
+    const long long row = t / p.n_tiles_n;
+    const int n0 = (int)(t - row * p.n_tiles_n);
+    if (!rotate) return n0;
+    const int n = n0 + (int)((uint32_t)row % (uint32_t)p.n_tiles_n);
+    return n >= p.n_tiles_n ? n - p.n_tiles_n : n;
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kNumXform = kHasScale ? 8 : 0;
@@ -653,6 +666,7 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
     if (want != 2 || (p.BN / 2) % 8 != 0 || p.BN % 32 != 0 || n_tm < 4) want = 1;
     p.cl = want;
   }
+  p.rotate = (tuning && tuning->rotate < 0) ? 0 : 1;
   // Shared-A plans: a streaming GEMM with exactly two N tiles fetches (and, gated, transforms) every A stage twice.  What
   // paces the wide-K project GEMMs of the 12x12 stage is the byte rate INTO the SMs (L2 -> SM: 16 KB of A + the weight rows
   // per k-block and N tile; ~7-8 TB/s over the chip whether the bytes come from HBM or L2), so both N tiles ride on one A
@@ -662,8 +676,8 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   p.nsub = 1;
   {
     const int want = tuning ? tuning->share_a : 0;
-    const bool ok = !p.b_res && p.n_tiles_n == 2 && 2 * p.BN <= (int)kTmemCols;
-    if (ok && (want == 1 || (want == 0 && scaled && k_blocks >= 8))) p.nsub = 2;
+    const bool ok = !p.b_res && scaled && p.cl == 2 && p.n_tiles_n == 2 && 2 * p.BN <= (int)kTmemCols;      // (the kernel variant exists for gated CTA-pair plans)
+    if (ok && (want == 1 || (want == 0 && k_blocks >= 8))) p.nsub = 2;
   }
   p.nb = p.cw > 64 ? 2 : 1;
   p.bw = p.cw / p.nb;
@@ -680,7 +694,8 @@ static int plan_tc(TcParams& p, size_t& smem, long long& grid, long long M, int 
   size_t stage_bytes = 0;
   int stages = 0;
   for (;;) {
-    stage_bytes = p.b_res ? a_stage : a_stage + (size_t)p.nsub * (size_t)(p.cl == 2 ? p.BN / 2 : p.BN) * kBK * 2;
+    const size_t b_stage = (size_t)(p.cl == 2 ? p.BN / 2 : p.BN) * kBK * 2;
+    stage_bytes = p.b_res ? a_stage : a_stage + (size_t)p.nsub * b_stage;
     p.nbuf = (2 * staging + (p.b_res ? 5 : 3) * stage_bytes + tail <= 222 * 1024) ? 2 : 1;     // (the measured plans' rule)
     // gated GEMMs write little and wait long (load -> gate transform -> MMA per stage): a pipeline stage is worth more
     // than a second staging buffer unless six stages fit anyway
@@ -814,6 +829,7 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
     if (!configured) {                                                                                                          \
       DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
       DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
+      DFV_CUDA(cudaFuncSetAttribute(pw_gemm_tc_kernel<S_, A_, R_, true, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   \
       configured = true;                                                                                                        \
     }                                                                                                                           \
     cudaLaunchConfig_t cfg = {};                                                                                                \
@@ -828,7 +844,10 @@ static int launch_tc(const void* a, const void* w, const float* bias, const void
     cattr[0].val.clusterDim.z = 1;                                                                                              \
     cfg.attrs = cattr;                                                                                                          \
     cfg.numAttrs = p.cl > 1 ? 1 : 0;                                                                                            \
-    if (p.cl == 2)                                                                                                              \
+    if (p.cl == 2 && p.nsub == 2)                                                                                               \
+      DFV_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<S_, A_, R_, true, S_>, tm_a, tm_b, tm_out, tm_res, bias,              \
+                                  (const __nv_bfloat16*)a_scale, p));                                                           \
+    else if (p.cl == 2)                                                                                                         \
       DFV_CUDA(cudaLaunchKernelEx(&cfg, pw_gemm_tc_kernel<S_, A_, R_, true>, tm_a, tm_b, tm_out, tm_res, bias,                  \
                                   (const __nv_bfloat16*)a_scale, p));                                                           \
     else                                                                                                                        \

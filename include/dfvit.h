@@ -508,7 +508,8 @@ typedef struct {
   int32_t weight_stationary;   /* -1 auto, 0 streaming, 1 weight-stationary */
   int32_t bn;                  /* N tile (0 = auto) */
   int32_t cluster;             /* streaming plans: 2 = CTA pair (cta_group::2: M = 256 over two SMs, half of the weight tile per SM), -1 = single CTA, 0 = auto */
-  int32_t share_a;             /* streaming plans with two N tiles: 1 = both N tiles share each A stage (two accumulators side by side in TMEM), -1 = off, 0 = auto */
+  int32_t share_a;             /* gated CTA-pair plans with two N tiles: 1 = both N tiles share each A stage (two accumulators side by side in TMEM), -1 = off, 0 = auto */
+  int32_t rotate;              /* streaming plans: -1 = every CTA walks the N tiles in the same order (off), 0 / 1 = order rotated by the cluster index */
 } dfv_gemm_tuning;
 int dfv_pw_gemm_fwd_tuned(const void* a, const void* w, const float* bias, const void* a_scale, int rows_per_image,
                           const void* residual, void* out, int dtype, long long M, int K, int N, int act,

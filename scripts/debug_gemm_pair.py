@@ -6,7 +6,7 @@ import torch
 import deepfake_vit_b200 as d
 ops, lib, DEV = d.ops, d._lib.lib, "cuda"
 shapes = [(396, 672, 112, 0, 0), (396, 1632, 272, 1, 36), (36864, 1632, 272, 1, 144), (36864, 272, 1632, 0, 0), (147456, 672, 112, 1, 576),
-          (147461, 960, 160, 1, 147461), (36864, 448, 1792, 0, 0), (36864, 2688, 448, 1, 144), (36864, 1632, 448, 1, 144), (36864, 960, 272, 1, 144)]
+          (147461, 960, 160, 1, 147461), (36864, 448, 1792, 0, 0), (36864, 2688, 448, 1, 144), (36864, 1632, 448, 1, 144), (36864, 960, 272, 1, 144), (36864, 448, 2688, 0, 0), (147456, 160, 960, 0, 0)]
 if len(sys.argv) > 1:      # comma-separated shape indices; argv[2] = timing iterations (0: one call per plan, for ncu)
     shapes = [shapes[int(i)] for i in sys.argv[1].split(",")]
 ITERS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
@@ -25,7 +25,7 @@ for (M, K, N, gated, rpi) in shapes:
     ref = ref * torch.sigmoid(ref) if not gated else ref + res.float()
     lib.dfv_gemm_plan_info(C.c_longlong(M), K, N, gated, info)
     print(f"M={M} K={K} N={N} gated={gated}: planner {list(info)}", flush=True)
-    for tn in ((0, 0, -1, -1), (0, 0, 2, -1), (0, 0, -1, 1), (0, 0, 2, 1)):
+    for tn in ((0, 0, 2, -1, -1), (0, 0, 2, -1, 1), (0, 0, 2, 1, 1), (0, 0, -1, -1, -1), (0, 0, -1, -1, 1)):     # (ws, bn, cluster, share_a, rotate)
         try:
             run = lambda: ops.pw_gemm(a, w, bias, 0 if gated else 1, sc, rpi, res, tuning=tn)
             y = run(); torch.cuda.synchronize()

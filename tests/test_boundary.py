@@ -136,7 +136,7 @@ def test_tile_planners_stay_within_the_sm(d):
                 assert 16 <= bn <= 256 and bn % 16 == 0 and ntn * bn >= N
                 assert stages >= 2 and nbuf in (1, 2) and 0 < smem <= 227 * 1024
                 assert 1 <= grid <= 148 and tpc >= 1 and grid * tpc * (1 if res else 1) >= 1
-                assert nsub in (1, 2) and (nsub == 1 or (ntn == 2 and not res and 2 * bn <= 512 and tpc % 2 == 0 and stages >= 3))
+                assert nsub in (1, 2) and (nsub == 1 or (ntn == 2 and not res and gated and cl == 2 and 2 * bn <= 512 and tpc % 2 == 0 and stages >= 3))
                 assert cl in (1, 2, 4) and grid % cl == 0 and (bn // cl) % 8 == 0 and not (res and cl > 1)
                 if res:     # the resident weight tile leaves room for the activation ring (gated: one N tile, <= 96 KB)
                     assert ((K + 63) // 64) * 64 * bn * 2 <= (96 if gated else 160) * 1024 and (not gated or ntn == 1)

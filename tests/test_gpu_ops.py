@@ -224,7 +224,8 @@ def test_pw_gemm_full_size_every_element(ops):
     for (M, K, N, act, gated, rpi) in ((589824, 56, 336, 1, False, 0), (147456, 160, 960, 1, False, 0),
                                        (36864, 1632, 272, 0, True, 144), (2310400 // 4, 96, 576, 1, False, 0),
                                        (577600, 96, 96, 0, True, 9025 // 1), (147461, 672, 112, 0, True, 147461),
-                                       (145 * 255, 2688, 448, 0, True, 145), (73728, 272, 448, 1, False, 0)):
+                                       (145 * 255, 2688, 448, 0, True, 145), (73728, 272, 448, 1, False, 0), (36864 + 40, 272, 1632, 1, False, 0),
+                                       (36864, 448, 1792, 1, False, 0)):
         a = torch.randn(M, K, device=DEV, generator=g).bfloat16()
         w = (torch.randn(N, K, device=DEV, generator=g) / math.sqrt(K)).bfloat16()
         bias = torch.randn(N, device=DEV, generator=g) * 0.1
@@ -240,9 +241,9 @@ def test_pw_gemm_full_size_every_element(ops):
             ref[i:i + 65536] = r + res[i:i + 65536].float() if gated else r
         # planner's choice, forced single-CTA streaming plans, forced CTA-pair plans (cta_group::2; ragged M: the last pair
         # has a phantom tile) -- per-call tuning argument (weight_stationary, N tile, cluster)
-        # ... and shared-A plans (two N tiles accumulate from one A stage, 4th field) where the shape has exactly two N tiles,
-        # on single CTAs and on CTA pairs, against the same plans without sharing
-        for forced in (None, (0, 192, -1), (0, 128, -1), (0, 128, 2), (0, 0, 2), (0, 0, -1, 1), (0, 0, 2, 1), (0, 0, 2, -1), (0, 192, 2, 1)):
+        # ... and shared-A plans (two N tiles accumulate from one A stage, 4th field) where a gated shape has exactly two N
+        # tiles, against the same CTA-pair plans without sharing
+        for forced in (None, (0, 192, -1), (0, 128, -1), (0, 128, 2), (0, 0, 2), (0, 0, 2, 1), (0, 0, 2, -1), (0, 192, 2, 1), (0, 0, 0, 0, -1), (0, 0, -1, 0, -1)):     # 5th field -1: N tiles walked in the same order by every CTA
             for rep in range(3):
                 y = ops.pw_gemm(a, w, bias, act, sc, rpi, res, tuning=forced)
                 bad = ((y.float() - ref).abs() > 0.03 * (ref.abs() + 1.0)).sum().item()
