@@ -39,6 +39,7 @@ class InferArgs(C.Structure):
         ("logits", C.c_void_p), ("features", C.c_void_p), ("heat", C.c_void_p),
         ("taps", C.POINTER(C.c_void_p)),
         ("images_u8", C.c_void_p), ("u8_norm", C.c_float * 6),
+        ("heat_max_floor", C.c_void_p),
     ]
 
 
@@ -139,12 +140,16 @@ def _load():
         "dfv_l2_normalize": (C.c_int, [vp, vp, i32, i32, f32, vp]),
         "dfv_clip_adamw_step": (C.c_int, [vp, vp, vp, vp, i64, vp] + [C.c_double] * 7 + [i64, vp, vp, vp]),
         "dfv_landmark_heatmap_fwd": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp]),
+        "dfv_landmark_heatmap_fwd_ex": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp, vp]),
+        "dfv_class_weight_sum": (C.c_int, [vp, vp, vp, i32, i32, vp]),
         "dfv_attention_scratch_floats": (sz, [i32] * 5),
         "dfv_hybrid_attention_fwd": (C.c_int, [vp] * 9 + [i32] * 8 + [vp]),
         "dfv_mlp_head_fwd": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), i32, vp, vp, i32, vp]),
         "dfv_mlp_head_scratch_floats": (sz, [C.POINTER(C.c_int), i32, i32]),
         "dfv_combined_loss_fwd_bwd": (C.c_int, [vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, i32, i32, i32,
                                                 C.POINTER(C.c_int), vp]),
+        "dfv_combined_loss_fwd_bwd_ex": (C.c_int, [vp, vp, vp, vp, f32, f32, f32, vp, vp, vp, i32, i32, i32,
+                                                   C.POINTER(C.c_int), vp, vp]),
         "dfv_rows_chunks": (C.c_int, [i32, i64]),
         "dfv_bn_ws_floats": (sz, [i32, i64, i32]),
         "dfv_bn_stats_fwd": (C.c_int, [vp, i32, i32, i64, i32, f32, f32, vp, vp, vp, vp, vp, vp]),

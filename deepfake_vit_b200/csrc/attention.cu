@@ -58,11 +58,12 @@ __global__ void heat_raw_kernel(const float* __restrict__ lm, const float* __res
 }
 
 __global__ void heat_norm_kernel(const float* __restrict__ raw, const uint32_t* __restrict__ gmax,
-                                 float* __restrict__ heat, int B, int HW, int group) {
+                                 float* __restrict__ heat, int B, int HW, int group, const uint32_t* __restrict__ floor_key) {
   pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * HW) return;
   uint32_t key = gmax[(idx / HW) / group];
+  if (floor_key != nullptr) key = max(key, floor_key[0]);      // keys are order-preserving: the larger key is the larger float
   key = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
   const float mx = __uint_as_float(key);
   float v = __fdiv_rn(raw[idx], __fadd_rn(mx, 1e-8f));
@@ -328,10 +329,17 @@ using namespace dfv;
 extern "C" int dfv_landmark_heatmap_fwd(const float* landmarks, const float* weights5, float* heat, float* raw_ws,
                                         uint32_t* max_ws, float* scaled_xy, int B, int H, int W, float ref_size,
                                         float sigma, int group, dfv_stream_t stream) {
+  return dfv_landmark_heatmap_fwd_ex(landmarks, weights5, heat, raw_ws, max_ws, scaled_xy, B, H, W, ref_size, sigma, group, nullptr, stream);
+}
+
+extern "C" int dfv_landmark_heatmap_fwd_ex(const float* landmarks, const float* weights5, float* heat, float* raw_ws,
+                                           uint32_t* max_ws, float* scaled_xy, int B, int H, int W, float ref_size,
+                                           float sigma, int group, const uint32_t* max_floor, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(landmarks && weights5 && heat && raw_ws && max_ws, "dfv_landmark_heatmap_fwd: null pointer");
   DFV_REQUIRE(B > 0 && H > 0 && W > 0 && ref_size > 0.f && sigma > 0.f, "dfv_landmark_heatmap_fwd: bad shape");
   if (group <= 0 || group > B) group = B;
+  DFV_REQUIRE(max_floor == nullptr || group == B, "dfv_landmark_heatmap_fwd_ex: a maximum floor needs the whole-call group");
   const int n_groups = (B + group - 1) / group;
   cudaStream_t st = as_stream(stream);
   DFV_CUDA(cudaMemsetAsync(max_ws, 0, sizeof(uint32_t) * n_groups, st));
@@ -343,7 +351,7 @@ extern "C" int dfv_landmark_heatmap_fwd(const float* landmarks, const float* wei
   DFV_PDL((heat_raw_kernel), (total + 255) / 256, 256, 0, st, landmarks, weights5, raw_ws, max_ws, scaled_xy, B, H, W, sx, sy,
                                                       denom, group);
   DFV_LAUNCH_CHECK();
-  DFV_PDL((heat_norm_kernel), (total + 255) / 256, 256, 0, st, raw_ws, max_ws, heat, B, H * W, group);
+  DFV_PDL((heat_norm_kernel), (total + 255) / 256, 256, 0, st, raw_ws, max_ws, heat, B, H * W, group, max_floor);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }

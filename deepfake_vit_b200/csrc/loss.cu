@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) combined_loss_kernel(const float* __restr
                                                            const float* __restrict__ cw, float w_ce, float w_focal,
                                                            float w_con, float* __restrict__ losses,
                                                            float* __restrict__ dlogits, float* __restrict__ dfeat,
-                                                           int B, int C, int D) {
+                                                           int B, int C, int D, const float* __restrict__ ce_norm) {
   pdl_prologue();
   __shared__ float red[3][8];
   __shared__ float s_wsum, s_ce_num, s_focal;
@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256) combined_loss_kernel(const float* __restr
     s_wsum = a; s_ce_num = b2; s_focal = c2 / (float)B;
   }
   __syncthreads();
-  const float inv_wsum = 1.f / s_wsum;
+  // the weighted mean's normaliser: the local sum of w[y_i], or the caller's (data-parallel exact form)
+  const float inv_wsum = 1.f / (ce_norm != nullptr ? ce_norm[0] : s_wsum);
 
   // ---- gradient wrt logits
   if (dlogits) {
@@ -119,14 +120,40 @@ __global__ void __launch_bounds__(256) combined_loss_kernel(const float* __restr
   }
 }
 
+// sum_i w[y_i] by ONE warp in a fixed order (the normaliser every rank contributes to the global weighted CE)
+__global__ void __launch_bounds__(32) class_weight_sum_kernel(const long long* __restrict__ targets, const float* __restrict__ cw,
+                                                             float* __restrict__ out, int B) {
+  pdl_prologue();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B; i += 32) s += cw ? cw[(int)targets[i]] : 1.f;
+  s = warp_sum(s);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
 }  // namespace dfv
 
 using namespace dfv;
+
+extern "C" int dfv_class_weight_sum(const int64_t* targets, const float* class_weights, float* out, int B, int C, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(targets && out && B > 0 && C > 1, "dfv_class_weight_sum: bad arguments");
+  DFV_PDL((class_weight_sum_kernel), 1, 32, 0, as_stream(stream), (const long long*)targets, class_weights, out, B);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
 
 extern "C" int dfv_combined_loss_fwd_bwd(const float* logits, const int64_t* targets, const float* features,
                                          const float* class_weights, float w_ce, float w_focal, float w_contrastive,
                                          float* losses, float* dlogits, float* dfeatures, int B, int C, int D,
                                          int* has_contrastive, dfv_stream_t stream) {
+  return dfv_combined_loss_fwd_bwd_ex(logits, targets, features, class_weights, w_ce, w_focal, w_contrastive, losses, dlogits, dfeatures,
+                                      B, C, D, has_contrastive, nullptr, stream);
+}
+
+extern "C" int dfv_combined_loss_fwd_bwd_ex(const float* logits, const int64_t* targets, const float* features,
+                                            const float* class_weights, float w_ce, float w_focal, float w_contrastive,
+                                            float* losses, float* dlogits, float* dfeatures, int B, int C, int D,
+                                            int* has_contrastive, const float* ce_norm, dfv_stream_t stream) {
   DFV_TRY(check_device());
   DFV_REQUIRE(logits && targets && losses, "dfv_combined_loss_fwd_bwd: null pointer");
   DFV_REQUIRE(B > 0 && C > 1 && (features == nullptr || D > 0), "dfv_combined_loss_fwd_bwd: bad shape");
@@ -137,7 +164,7 @@ extern "C" int dfv_combined_loss_fwd_bwd(const float* logits, const int64_t* tar
   DFV_PDL((combined_loss_kernel), 1, 256, 0, as_stream(stream), logits, (const long long*)targets, con ? features : nullptr,
                                                         class_weights, w_ce > 0.f ? w_ce : 0.f,
                                                         w_focal > 0.f ? w_focal : 0.f, con ? w_contrastive : 0.f, losses,
-                                                        dlogits, con ? dfeatures : nullptr, B, C, D);
+                                                        dlogits, con ? dfeatures : nullptr, B, C, D, ce_norm);
   DFV_LAUNCH_CHECK();
   if (!con && dfeatures && features)
     DFV_CUDA(cudaMemsetAsync(dfeatures, 0, sizeof(float) * (size_t)B * D, as_stream(stream)));

@@ -203,8 +203,9 @@ extern "C" int dfv_infer_fwd(const dfv_infer_args* a, dfv_stream_t stream) {
   const float* heat = nullptr;
   if (a->use_attention && a->use_landmark && a->landmarks != nullptr) {
     DFV_REQUIRE(a->lm_weights, "dfv_infer_fwd: landmark attention weights missing");
-    DFV_TRY(dfv_landmark_heatmap_fwd(a->landmarks, a->lm_weights, ws.heat, ws.heat_raw, ws.heat_max, nullptr, B, s.Hf, s.Wf,
-                                     a->landmark_ref_size > 0.f ? a->landmark_ref_size : 224.0f, 1.5f, a->heat_group, stream));
+    DFV_TRY(dfv_landmark_heatmap_fwd_ex(a->landmarks, a->lm_weights, ws.heat, ws.heat_raw, ws.heat_max, nullptr, B, s.Hf, s.Wf,
+                                        a->landmark_ref_size > 0.f ? a->landmark_ref_size : 224.0f, 1.5f, a->heat_group, a->heat_max_floor,
+                                        stream));
     heat = ws.heat;
     if (a->heat) DFV_CUDA(cudaMemcpyAsync(a->heat, ws.heat, sizeof(float) * (size_t)B * s.Hf * s.Wf, cudaMemcpyDeviceToDevice, st));
   }

@@ -292,6 +292,9 @@ class DeepfakeDetectionModel(nn.Module):
         # ---- knobs that are not part of the reference API
         self.compute_dtype = torch.bfloat16     # or torch.float32 (parity mode)
         self.landmark_max_group = 0             # images per heat-map max group; 0 = whole call (reference)
+        self.landmark_max_scope = "rank"        # "rank": the maximum over this call's batch (= the reference run on this shard);
+                                                # "global" (eval, torch.distributed): the maximum over ALL ranks' batches, one 4-byte
+                                                # all-reduce(MAX) -- bit-equal to one GPU scoring the concatenated batch
         self.ddp_allreduce = True               # average gradients over torch.distributed ranks inside backward
         self.ddp_bucket_floats = 4 << 20        # ~16 MB gradient buckets, all-reduced while the backward still runs
         # uint8 (B, H, W, 3) RGB crops are normalised inside the stem: (u8 / 255 - mean) / std (dataset.py:95-98)
@@ -455,6 +458,13 @@ class DeepfakeDetectionModel(nn.Module):
         a.use_spatial = int(use_att and att.use_spatial)
         a.heat_group = int(self.landmark_max_group)
         a.landmark_ref_size = 224.0
+        floor_key = None
+        if lm is not None and self.landmark_max_scope == "global":
+            from . import parallel
+            assert int(self.landmark_max_group) in (0, B), "the global normaliser is the whole-call maximum of every rank"
+            floor_key = parallel.allreduce_max_key(ops.landmark_max_key(lm, att.landmark_attn.attention_weights.detach(), Hf, Wf,
+                                                                        224.0, att.landmark_attn.sigma))
+            a.heat_max_floor = floor_key.data_ptr()
         a.blob = pk.blob.data_ptr()
         a.images_nchw = x.data_ptr() if x is not None else None
         if u8 is not None:
@@ -537,6 +547,9 @@ class DeepfakeDetectionModel(nn.Module):
         a.use_channel = int(use_att and att.use_channel)
         a.use_spatial = int(use_att and att.use_spatial)
         a.heat_group = int(self.landmark_max_group)
+        if self.landmark_max_scope != "rank":
+            raise RuntimeError("landmark_max_scope='global' is an inference mode: in training the maximum's gradient would have to "
+                               "cross ranks; train with the per-rank normaliser (what DDP over the reference does)")
         a.landmark_ref_size = 224.0
         bb = self.feature_extractor.backbone.backbone
         a.bn_eps, a.bn_momentum = bb._bn0.eps, bb._bn0.momentum

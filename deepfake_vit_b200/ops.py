@@ -137,16 +137,30 @@ def pw_gemm(a, w, bias, act=DFV_ACT_NONE, a_scale=None, rows_per_image=0, residu
     return out
 
 
-def landmark_heatmap(landmarks, weights5, H, W, ref_size=224.0, sigma=1.5, group=0, return_scaled=False):
+def landmark_heatmap(landmarks, weights5, H, W, ref_size=224.0, sigma=1.5, group=0, return_scaled=False, max_floor=None,
+                     return_max_key=False):
+    """max_floor: optional int32 tensor holding ONE order-preserving key (see landmark_max_key) the group maximum is raised
+    to -- the data-parallel `global` normaliser.  return_max_key: also return this call's own key(s) [groups] int32."""
     B = landmarks.shape[0]
     dev = landmarks.device
     heat = torch.empty(B, H, W, device=dev, dtype=torch.float32)
     raw = torch.empty(B * H * W, device=dev, dtype=torch.float32)
     mx = torch.empty(B, device=dev, dtype=torch.int32)
     scaled = torch.empty(B, 5, 2, device=dev, dtype=torch.float32) if return_scaled else None
-    check(lib.dfv_landmark_heatmap_fwd(_f32(landmarks), _f32(weights5), _f32(heat), _f32(raw), _ptr(mx), _ptr(scaled),
-                                       B, H, W, ref_size, sigma, group, _stream()))
-    return (heat, scaled) if return_scaled else heat
+    check(lib.dfv_landmark_heatmap_fwd_ex(_f32(landmarks), _f32(weights5), _f32(heat), _f32(raw), _ptr(mx), _ptr(scaled),
+                                          B, H, W, ref_size, sigma, group, _ptr(max_floor), _stream()))
+    out = (heat, scaled) if return_scaled else heat
+    if return_max_key:
+        g = B if group <= 0 or group > B else group
+        return out, mx[:(B + g - 1) // g]
+    return out
+
+
+def landmark_max_key(landmarks, weights5, H, W, ref_size=224.0, sigma=1.5):
+    """The whole-call heat-map maximum of this batch as an order-preserving key (int32 storage of the library's uint32 key:
+    UNSIGNED order == float order).  parallel.allreduce_max_key() turns every rank's key into the global one."""
+    _, key = landmark_heatmap(landmarks, weights5, H, W, ref_size, sigma, 0, return_max_key=True)
+    return key[:1]
 
 
 def hybrid_attention(fmap, heat, ca_w1, ca_w2_t, sa_w, use_channel=True, use_spatial=True, return_gates=False):
@@ -185,8 +199,17 @@ def mlp_head(features, pack: HeadPack):
     return logits
 
 
-def combined_loss(logits, targets, features, class_weights, w_ce, w_focal, w_con, want_grad=True):
-    """Returns (losses[4] = ce, focal, contrastive, total; has_contrastive; dlogits; dfeatures)."""
+def class_weight_sum(targets, class_weights, n_classes):
+    """sum_i class_weights[targets[i]] (B when class_weights is None) as a 1-element fp32 device tensor."""
+    out = torch.empty(1, device=targets.device, dtype=torch.float32)
+    assert targets.dtype == torch.int64
+    check(lib.dfv_class_weight_sum(_ptr(targets), _ptr(class_weights), _f32(out), targets.numel(), n_classes, _stream()))
+    return out
+
+
+def combined_loss(logits, targets, features, class_weights, w_ce, w_focal, w_con, want_grad=True, ce_norm=None):
+    """Returns (losses[4] = ce, focal, contrastive, total; has_contrastive; dlogits; dfeatures).
+    ce_norm: optional 1-element fp32 device tensor replacing the weighted CE's local normaliser."""
     B, Cn = logits.shape
     D = features.shape[1] if features is not None else 0
     dev = logits.device
@@ -195,9 +218,9 @@ def combined_loss(logits, targets, features, class_weights, w_ce, w_focal, w_con
     dfeat = torch.empty_like(features) if (want_grad and features is not None) else None
     has = C.c_int(0)
     assert targets.dtype == torch.int64
-    check(lib.dfv_combined_loss_fwd_bwd(_f32(logits), _ptr(targets), _ptr(features), _ptr(class_weights), w_ce, w_focal,
-                                        w_con, _f32(losses), _ptr(dlogits), _ptr(dfeat), B, Cn, D, C.byref(has),
-                                        _stream()))
+    check(lib.dfv_combined_loss_fwd_bwd_ex(_f32(logits), _ptr(targets), _ptr(features), _ptr(class_weights), w_ce, w_focal,
+                                           w_con, _f32(losses), _ptr(dlogits), _ptr(dfeat), B, Cn, D, C.byref(has),
+                                           _ptr(ce_norm), _stream()))
     return losses, bool(has.value), dlogits, dfeat
 
 

@@ -47,6 +47,23 @@ def allreduce_gradients(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+def allreduce_mean_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place mean over ranks of a small tensor (the weighted-CE normaliser of the exact data-parallel loss)."""
+    return allreduce_gradients(t, group)
+
+
+def allreduce_max_key(key: torch.Tensor, group=None) -> torch.Tensor:
+    """Element-wise maximum over ranks of order-preserving heat-map keys (ops.landmark_max_key): int32 storage of uint32
+    keys whose UNSIGNED order is the float order.  Collectives compare int32 as signed, so the sign bit is flipped for
+    the exchange (unsigned order -> signed order) and flipped back.  Returns a new tensor; one 4-byte all-reduce(MAX)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return key
+    k = key ^ (-2 ** 31)
+    dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+    return k ^ (-2 ** 31)
+
+
 FLAT_ALIGN = 64   # floats: every tensor starts on a 256-byte boundary inside a flat buffer, like a torch allocation
                   # (the kernels read parameters with 16-byte vector loads)
 

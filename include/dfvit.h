@@ -212,6 +212,14 @@ int dfv_pw_conv_fwd(const void* a, const void* w, const float* bias, const void*
 int dfv_landmark_heatmap_fwd(const float* landmarks, const float* weights5, float* heat, float* raw_ws,
                              uint32_t* max_ws, float* scaled_xy, int B, int H, int W, float ref_size,
                              float sigma, int group, dfv_stream_t stream);
+/* The same with a floor on the maximum: the `global` normaliser mode of data-parallel runs (SURVEY.md 8(e) caveat 1).
+ * max_ws holds ORDER-PRESERVING uint32 keys of the group maxima (unsigned order == float order); max_floor (device, one
+ * key, may be NULL) is the element-wise maximum of every rank's max_ws[0] (a 1-word all-reduce(MAX) run by the host
+ * between two calls): the map is divided by max(local maximum, floor) -- for the global maximum that IS the value a
+ * single-GPU run over the concatenated batch divides by (landmark_attention.py:125).  Whole-call group only. */
+int dfv_landmark_heatmap_fwd_ex(const float* landmarks, const float* weights5, float* heat, float* raw_ws,
+                                uint32_t* max_ws, float* scaled_xy, int B, int H, int W, float ref_size,
+                                float sigma, int group, const uint32_t* max_floor, dfv_stream_t stream);
 
 /* HybridAttention (landmark -> channel -> spatial, landmark_attention.py:283-310) fused
  * with the global average pool of DeepfakeFeatureExtractor.forward
@@ -250,6 +258,17 @@ int dfv_combined_loss_fwd_bwd(const float* logits, const int64_t* targets, const
                               const float* class_weights, float w_ce, float w_focal, float w_contrastive,
                               float* losses, float* dlogits, float* dfeatures, int B, int C, int D,
                               int* has_contrastive, dfv_stream_t stream);
+/* The same with the weighted cross-entropy's normaliser supplied by the caller: ce_norm (device, one float, may be NULL
+ * = the local sum of w[y_i], nn.CrossEntropyLoss(weight), losses.py:188,217).  Data-parallel exact form (SURVEY.md 8(e)
+ * caveat 3): every rank passes the MEAN over ranks of its dfv_class_weight_sum -- then the mean over ranks of the
+ * returned ce (and of its gradient, which the gradient all-reduce forms) is the weighted CE of the global batch. */
+int dfv_combined_loss_fwd_bwd_ex(const float* logits, const int64_t* targets, const float* features,
+                                 const float* class_weights, float w_ce, float w_focal, float w_contrastive,
+                                 float* losses, float* dlogits, float* dfeatures, int B, int C, int D,
+                                 int* has_contrastive, const float* ce_norm, dfv_stream_t stream);
+/* out[0] = sum_i class_weights[targets[i]] (B if class_weights is NULL): fixed summation order. */
+int dfv_class_weight_sum(const int64_t* targets, const float* class_weights, float* out, int B, int C,
+                         dfv_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Whole-path inference: DeepfakeDetectionModel.forward in eval mode
@@ -285,6 +304,7 @@ typedef struct {
   const uint8_t* images_u8;      /* optional: [B][H][W][3] uint8 RGB crops; normalised inside the stem
                                     (dfv_stem_conv_u8_fwd) with u8_norm = mean[3], std[3] */
   float u8_norm[6];
+  const uint32_t* heat_max_floor; /* optional (device, one key): floor of the heat-map maximum, see dfv_landmark_heatmap_fwd_ex */
 } dfv_infer_args;
 
 size_t dfv_infer_workspace_bytes(int dtype, int B, int H, int W);

@@ -54,7 +54,22 @@ def _worker(rank, world, port, out):
         wg2 = wgt.detach().clone().requires_grad_(True)
         sum((x[a:b] @ wg2).pow(2).mean() for a, b in [parallel.shard_bounds(4, world, r) for r in range(world)]).div(world).backward()
         ok_ddp = bool(torch.allclose(g, wg2.grad, atol=1e-6))
-        out[rank] = (ok_mean, ok_shard, ok_even, ok_bcast, ok_ddp)
+        # 5. the optional `global` modes' exchanges (SURVEY 8(e) caveats 1 and 3): the heat-map maximum travels as an
+        #    order-preserving key (uint32 order == float order, int32 storage), the weighted-CE normaliser as a mean
+        import struct
+
+        def key_of(v):      # the library's key: non-negative floats get the sign bit set, negative ones are inverted
+            u = struct.unpack("<I", struct.pack("<f", v))[0]
+            u = (~u & 0xFFFFFFFF) if (u & 0x80000000) else (u | 0x80000000)
+            return u - (1 << 32) if u >= (1 << 31) else u
+        vals = [[0.75, -0.5], [1.25, -0.25]]        # rank 1 holds the larger maximum in both cases
+        ok_key = True
+        for j in range(2):
+            got = parallel.allreduce_max_key(torch.tensor([key_of(vals[rank][j])], dtype=torch.int32))
+            ok_key = ok_key and int(got[0]) == key_of(max(vals[0][j], vals[1][j]))
+        norm = parallel.allreduce_mean_(torch.tensor([10.0 + 4.0 * rank]))
+        ok_norm = abs(float(norm[0]) - 12.0) < 1e-6
+        out[rank] = (ok_mean, ok_shard, ok_even, ok_bcast, ok_ddp, ok_key, ok_norm)
     finally:
         dist.destroy_process_group()
 
