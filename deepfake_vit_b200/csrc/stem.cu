@@ -3,6 +3,7 @@
 // HBM-bound by bytes (1.7 MB in / 3.5 MB out per image at 380 in bf16) but carries
 // 1296 FMA per output pixel, so it sits near the FP32-pipe / HBM crossover.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -22,6 +23,7 @@ __device__ __forceinline__ void stem_build_lut(float* lut, const StemNorm& nm) {
     const int c = i >> 8;
     lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), nm.mean[c]), nm.std[c]);
   }
+  if (threadIdx.x == 0) lut[768] = 0.f;      // pad taps of the tensor-core stem index this entry
 }
 template <bool kU8>
 __device__ __forceinline__ float stem_load(const void* x, const float* lut, int b, int ci, int hi, int wi, int H, int W) {
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const void* __restrict__ x
                                                   int W, int Ho, int Wo, int act) {
   __shared__ __align__(16) float ws[27 * kStemC];
   __shared__ __align__(16) float bs[kStemC];
-  __shared__ float lut[kU8 ? 768 : 1];
+  __shared__ float lut[kU8 ? 772 : 1];
   for (int i = threadIdx.x; i < 27 * kStemC; i += blockDim.x) ws[i] = w[i];
   if (threadIdx.x < kStemC) bs[threadIdx.x] = bias[threadIdx.x];
   if constexpr (kU8) stem_build_lut(lut, nm);
@@ -192,14 +194,16 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
 
   if (warp < 4) {
     // ------------------------------------------------------------- im2col builders
-    int it = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+    // One thread per output pixel: 27 gathered taps -> one 64-byte (32 x bf16, taps 27..31 zero) swizzled A row.
+    // The gather of tile t+1 is ISSUED before tile t is packed (two register sets, loop unrolled by two): with the loads
+    // and the pack in sequence the builders sat on the load latency for ~40 % of all samples (long_scoreboard at the
+    // first use) and the kernel ran at 0.41 of the HBM roofline.  uint8 input: the registers hold LUT indices
+    // (ci * 256 + u, or 768 = the zero entry for pad taps); the look-up happens at pack time.
+    using RawT = typename std::conditional<kU8, uint32_t, float>::type;
+    auto gather = [&](long long t, RawT (&v)[27]) {
       const long long p = t * kStemTile + tid;
-      float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      for (int i = 0; i < 27; ++i) v[i] = kU8 ? (RawT)768 : (RawT)0;
       if (p < total) {
         const int wo = (int)(p % Wo);
         const long long r = p / Wo;
@@ -211,22 +215,48 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
             const int hi = 2 * ho + kh;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
-              if (hi < H && 2 * wo + kw < W) v[(kh * 3 + kw) * 3 + ci] = stem_load<kU8>(x, lut, b, ci, hi, 2 * wo + kw, H, W);
+              if (hi < H && 2 * wo + kw < W) {
+                if constexpr (kU8)
+                  v[(kh * 3 + kw) * 3 + ci] = (RawT)(ci * 256) + (RawT)__ldg(reinterpret_cast<const unsigned char*>(x) + (((size_t)b * H + hi) * W + 2 * wo + kw) * 3 + ci);
+                else
+                  v[(kh * 3 + kw) * 3 + ci] = __ldg(reinterpret_cast<const float*>(x) + (((size_t)b * 3 + ci) * H + hi) * W + 2 * wo + kw);
+              }
           }
       }
+    };
+    auto emit = [&](int it, const RawT (&v)[27]) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
       mbar_wait(&bars->a_empty[s], ph ^ 1, 31);
       unsigned char* arow = a_tiles + s * 16384 + tid * 128;
+      auto val = [&](int k) -> float {
+        if (k >= 27) return 0.f;
+        if constexpr (kU8) return lut[v[k < 27 ? k : 0]]; else return v[k < 27 ? k : 0];
+      };
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 pk;
-        pk.x = pack_bf16(v[c * 8 + 0], v[c * 8 + 1]);
-        pk.y = pack_bf16(v[c * 8 + 2], v[c * 8 + 3]);
-        pk.z = pack_bf16(v[c * 8 + 4], v[c * 8 + 5]);
-        pk.w = pack_bf16(v[c * 8 + 6], v[c * 8 + 7]);
+        pk.x = pack_bf16(val(c * 8 + 0), val(c * 8 + 1));
+        pk.y = pack_bf16(val(c * 8 + 2), val(c * 8 + 3));
+        pk.z = pack_bf16(val(c * 8 + 4), val(c * 8 + 5));
+        pk.w = pack_bf16(val(c * 8 + 6), val(c * 8 + 7));
         *reinterpret_cast<uint4*>(arow + ((c ^ (tid & 7)) << 4)) = pk;
       }
       fence_proxy_async();
       mbar_arrive(&bars->a_full[s]);
+    };
+    RawT va[27], vb[27];
+    long long t = t_begin;
+    int it = 0;
+    if (t < t_end) gather(t, va);
+    while (t < t_end) {
+      if (t + 1 < t_end) gather(t + 1, vb);
+      emit(it, va);
+      ++t; ++it;
+      if (t >= t_end) break;
+      if (t + 1 < t_end) gather(t + 1, va);
+      emit(it, vb);
+      ++t; ++it;
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------- MMA issuer
@@ -325,7 +355,7 @@ static int launch_stem_tc(const void* x, const StemNorm& nm, const float* w, con
   long long grid = std::min<long long>(n_tiles, 2LL * num_sms());
   const long long tpc = (n_tiles + grid - 1) / grid;
   grid = (n_tiles + tpc - 1) / tpc;
-  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 16 + (kU8 ? 768 * 4 : 0) + 1024;
+  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 16 + (kU8 ? 772 * 4 : 0) + 1024;
   DFV_TRY(init_timeout_word_tu());
   static thread_local bool configured = false;
   if (!configured) {
@@ -345,7 +375,7 @@ static int launch_stem_tc(const void* x, const StemNorm& nm, const float* w, con
 // Thread = 4 consecutive pixels of one image: three 32-bit loads (12 bytes), three float4 stores (one per channel plane).
 __global__ void __launch_bounds__(256) u8_to_nchw_kernel(const unsigned char* __restrict__ x, const StemNorm nm, float* __restrict__ y,
                                                         int B, int H, int W) {
-  __shared__ float lut[768];
+  __shared__ float lut[772];
   stem_build_lut(lut, nm);
   __syncthreads();
   const long long hw = (long long)H * W;
