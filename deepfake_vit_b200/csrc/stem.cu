@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256, 3) stem_kernel(const void* __restrict__ x
 constexpr int kStemTcThreads = 288;
 constexpr int kStemTile = 128;
 constexpr uint32_t kStemTmemCols = 128;
+constexpr int kLutPitch = 264;
 
 struct __align__(8) StemBars {
   uint64_t a_full[2], a_empty[2], t_full[2], t_empty[2];
@@ -155,7 +156,14 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
   float* bias_sm = reinterpret_cast<float*>(staging + 2 * 12288);
   StemBars* bars = reinterpret_cast<StemBars*>(bias_sm + 64);
   float* lut = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + ((sizeof(StemBars) + 15) / 16) * 16);   // [3][256], kU8 only
-  if constexpr (kU8) stem_build_lut(lut, nm);
+  // [3][kLutPitch]: entries 0..255 the normalised values of channel c, entry 256 = 0 for pad taps -- the builders keep the raw
+  // byte (or 256) in a register and the channel offset rides in the load's immediate
+  if constexpr (kU8) {
+    for (int i = threadIdx.x; i < 3 * kLutPitch; i += blockDim.x) {
+      const int c = i / kLutPitch, u = i % kLutPitch;
+      lut[i] = u < 256 ? __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), nm.mean[c]), nm.std[c]) : 0.f;
+    }
+  }
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total = (long long)B * Ho * Wo;
@@ -197,8 +205,8 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
     // One thread per output pixel: 27 gathered taps -> one 64-byte (32 x bf16, taps 27..31 zero) swizzled A row.
     // The gather of tile t+1 is ISSUED before tile t is packed (two register sets, loop unrolled by two): with the loads
     // and the pack in sequence the builders sat on the load latency for ~40 % of all samples (long_scoreboard at the
-    // first use) and the kernel ran at 0.41 of the HBM roofline.  uint8 input: the registers hold LUT indices
-    // (ci * 256 + u, or 768 = the zero entry for pad taps); the look-up happens at pack time.
+    // first use) and the kernel ran at 0.41 of the HBM roofline.  uint8 input: the registers hold the raw bytes
+    // (256 = the zero entry, for pad taps); the look-up happens at pack time.
     using RawT = typename std::conditional<kU8, uint32_t, float>::type;
     // (b, ho, wo) of this thread's pixel in the tile about to be gathered: ONE 64-bit division at the start, then advanced
     // by 128 pixels per tile (the four 64-bit divisions per pixel and tile were ~250 of the builders' ~400 instructions,
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
     auto gather = [&](long long t, RawT (&v)[27]) {
       const long long p = t * kStemTile + tid;
 #pragma unroll
-      for (int i = 0; i < 27; ++i) v[i] = kU8 ? (RawT)768 : (RawT)0;
+      for (int i = 0; i < 27; ++i) v[i] = kU8 ? (RawT)256 : (RawT)0;
       const int wo = g_wo, ho = g_ho, b = g_b;
       g_wo += kStemTile;                                // the next tile's pixel
       while (g_wo >= Wo) {
@@ -223,20 +231,46 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
         if (++g_ho == Ho) { g_ho = 0; ++g_b; }
       }
       if (p < total) {
+        if (2 * ho + 2 < H && 2 * wo + 2 < W) {
+          // interior pixel (all but the last output row / column): no bounds checks, one row pointer per (channel, kernel row)
+          // and immediate offsets for the taps -- the per-tap 64-bit address arithmetic and predicates were ~130 of the ~260
+          // instructions a builder thread spent per tile
+          if constexpr (kU8) {
+            const unsigned char* p0 = reinterpret_cast<const unsigned char*>(x) + (((size_t)b * H + 2 * ho) * W + 2 * wo) * 3;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+            for (int kh = 0; kh < 3; ++kh) {
+              const unsigned char* pr = p0 + (size_t)kh * W * 3;
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
-            const int hi = 2 * ho + kh;
+              for (int j = 0; j < 9; ++j) v[kh * 9 + j] = (RawT)__ldg(pr + j);      // j = kw * 3 + ci
+            }
+          } else {
+            const size_t plane = (size_t)H * W;
+            const float* p0 = reinterpret_cast<const float*>(x) + ((size_t)b * 3 * H + 2 * ho) * W + 2 * wo;
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              if (hi < H && 2 * wo + kw < W) {
-                if constexpr (kU8)
-                  v[(kh * 3 + kw) * 3 + ci] = (RawT)(ci * 256) + (RawT)__ldg(reinterpret_cast<const unsigned char*>(x) + (((size_t)b * H + hi) * W + 2 * wo + kw) * 3 + ci);
-                else
-                  v[(kh * 3 + kw) * 3 + ci] = __ldg(reinterpret_cast<const float*>(x) + (((size_t)b * 3 + ci) * H + hi) * W + 2 * wo + kw);
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                const float* pr = p0 + ci * plane + (size_t)kh * W;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) v[(kh * 3 + kw) * 3 + ci] = __ldg(pr + kw);
               }
           }
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              const int hi = 2 * ho + kh;
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw)
+                if (hi < H && 2 * wo + kw < W) {
+                  if constexpr (kU8)
+                    v[(kh * 3 + kw) * 3 + ci] = (RawT)__ldg(reinterpret_cast<const unsigned char*>(x) + (((size_t)b * H + hi) * W + 2 * wo + kw) * 3 + ci);
+                  else
+                    v[(kh * 3 + kw) * 3 + ci] = __ldg(reinterpret_cast<const float*>(x) + (((size_t)b * 3 + ci) * H + hi) * W + 2 * wo + kw);
+                }
+            }
+        }
       }
     };
     auto emit = [&](int it, const RawT (&v)[27]) {
@@ -246,7 +280,7 @@ __global__ void __launch_bounds__(kStemTcThreads, 2)
       unsigned char* arow = a_tiles + s * 16384 + tid * 128;
       auto val = [&](int k) -> float {
         if (k >= 27) return 0.f;
-        if constexpr (kU8) return lut[v[k < 27 ? k : 0]]; else return v[k < 27 ? k : 0];
+        if constexpr (kU8) return lut[(k % 3) * kLutPitch + v[k < 27 ? k : 0]]; else return v[k < 27 ? k : 0];
       };
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -370,7 +404,7 @@ static int launch_stem_tc(const void* x, const StemNorm& nm, const float* w, con
   long long grid = std::min<long long>(n_tiles, 2LL * num_sms());
   const long long tpc = (n_tiles + grid - 1) / grid;
   grid = (n_tiles + tpc - 1) / tpc;
-  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 16 + (kU8 ? 772 * 4 : 0) + 1024;
+  const size_t smem = 2 * 16384 + 8192 + 2 * 12288 + 256 + sizeof(StemBars) + 16 + (kU8 ? 3 * kLutPitch * 4 : 0) + 1024;
   DFV_TRY(init_timeout_word_tu());
   static thread_local bool configured = false;
   if (!configured) {
