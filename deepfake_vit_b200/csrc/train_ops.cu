@@ -8,6 +8,7 @@
 // All HBM-bound streaming kernels: 16-byte vectors of 8 channels, fixed channel group per thread,
 // fp32 accumulation, per-CTA partials finished by a tiny second kernel (deterministic).
 #include <algorithm>
+#include <type_traits>
 
 #include <cooperative_groups.h>
 
@@ -96,6 +97,7 @@ template <> struct Raw8<float> {
   }
 };
 template <typename T> struct Unroll { static constexpr int U = sizeof(T) == 2 ? 4 : 2; };
+template <typename T> struct UnrollStats { static constexpr int U = sizeof(T) == 2 ? 8 : 2; };   // read-only stream: deeper
 
 // cp.async (LDGSTS) staging for the compute-heavy streams: every thread owns private 16-byte shared-memory slots
 // that it fills for the NEXT round while it computes the current one, so the memory system always has
@@ -114,7 +116,7 @@ template <typename T>
 __global__ void __launch_bounds__(kNT) bn_stats_kernel(const T* __restrict__ raw, long long rows_per_image, int C,
                                                       long long rows_per_chunk, float* __restrict__ partial) {
   pdl_prologue();
-  constexpr int U = Unroll<T>::U;
+  constexpr int U = UnrollStats<T>::U;
   __shared__ float sm[kNT * 16];
   const ColMap m(C);
   const long long r0 = (long long)blockIdx.x * rows_per_chunk;
@@ -231,15 +233,21 @@ __global__ void __launch_bounds__(256) bn_stats_from_sums_kernel(const double* _
 }
 
 // ------------------------------------------------------------------------------------ bn_act
-template <typename T, bool kFast>
+// kSpec: the backbone's expanded tensors -- swish, no mask, no row scale, no residual -- with those four run-time switches
+// folded at compile time (these streams co-limit on issue slots: ~20 instructions per element beside one MUFU)
+template <typename T, bool kFast, bool kSpec = false>
 __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, const float* __restrict__ mean,
                                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                    const float* __restrict__ beta, int act,
-                                                    const float* __restrict__ rowscale, const T* __restrict__ residual,
-                                                    const float* __restrict__ mask, T* __restrict__ out,
+                                                    const float* __restrict__ beta, int act_rt,
+                                                    const float* __restrict__ rowscale_rt, const T* __restrict__ residual_rt,
+                                                    const float* __restrict__ mask_rt, T* __restrict__ out,
                                                     float* __restrict__ pool_partial, long long rows_per_image, int C,
                                                     long long rows_per_chunk) {
   pdl_prologue();
+  const int act = kSpec ? (int)DFV_ACT_SILU : act_rt;
+  const float* rowscale = kSpec ? nullptr : rowscale_rt;
+  const T* residual = kSpec ? nullptr : residual_rt;
+  const float* mask = kSpec ? nullptr : mask_rt;
   constexpr int U = Unroll<T>::U;
   __shared__ float sm[kNT * 8];
   const ColMap m(C);
@@ -288,37 +296,47 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
         store8(out + off, v);
       };
       if constexpr (sizeof(T) == 2) {
-        extern __shared__ uint4 stage[];   // [2 buffers][kPipeU rows][2 tensors][kNT threads]
-        auto slot = [&](int buf, int i, int t) { return stage + ((buf * kPipeU + i) * 2 + t) * kNT + threadIdx.x; };
-        auto prefetch = [&](long long r, int buf) {
+        // [2 buffers][U rows][1 or 2 tensors][kNT threads] = 16 slots per thread either way: without a residual (every
+        // layer but the block outputs) the residual's slots carry four more rows of `raw` -- with 4 x 16 bytes per thread in
+        // flight the one-input forward streams ran at 3.8-4.8 TB/s (28.63 -> 28.08 ms per training step with 8 x 16)
+        extern __shared__ uint4 stage[];
+        auto stream_rows = [&](auto u_c, auto res_c) {
+          constexpr int U = decltype(u_c)::value;
+          constexpr bool kRes = decltype(res_c)::value;
+          constexpr int NTen = kRes ? 2 : 1;
+          auto slot = [&](int buf, int i, int t) { return stage + ((buf * U + i) * NTen + t) * kNT + threadIdx.x; };
+          auto prefetch = [&](long long r, int buf) {
 #pragma unroll
-          for (int i = 0; i < kPipeU; ++i) {
-            const long long ri = r + (long long)i * m.rpp;
-            if (ri < r1) {
-              const size_t off = img + (size_t)ri * C + cv * 8;
-              cp_async16(slot(buf, i, 0), raw + off);
-              if (residual) cp_async16(slot(buf, i, 1), residual + off);
+            for (int i = 0; i < U; ++i) {
+              const long long ri = r + (long long)i * m.rpp;
+              if (ri < r1) {
+                const size_t off = img + (size_t)ri * C + cv * 8;
+                cp_async16(slot(buf, i, 0), raw + off);
+                if constexpr (kRes) cp_async16(slot(buf, i, 1), residual + off);
+              }
+            }
+            cp_async_commit();
+          };
+          long long r = r0 + m.row_l;
+          int buf = 0;
+          prefetch(r, 0);
+          for (; r < r1; r += (long long)U * m.rpp, buf ^= 1) {
+            prefetch(r + (long long)U * m.rpp, buf ^ 1);
+            cp_async_wait1();
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+              const long long ri = r + (long long)i * m.rpp;
+              if (ri < r1) {
+                Raw8<T> xi, qi;
+                xi.r = *slot(buf, i, 0);
+                if constexpr (kRes) qi.r = *slot(buf, i, 1); else qi.zero();
+                body(xi, qi, img + (size_t)ri * C + cv * 8);
+              }
             }
           }
-          cp_async_commit();
         };
-        long long r = r0 + m.row_l;
-        int buf = 0;
-        prefetch(r, 0);
-        for (; r < r1; r += (long long)kPipeU * m.rpp, buf ^= 1) {
-          prefetch(r + (long long)kPipeU * m.rpp, buf ^ 1);
-          cp_async_wait1();
-#pragma unroll
-          for (int i = 0; i < kPipeU; ++i) {
-            const long long ri = r + (long long)i * m.rpp;
-            if (ri < r1) {
-              Raw8<T> xi, qi;
-              xi.r = *slot(buf, i, 0);
-              if (residual) qi.r = *slot(buf, i, 1); else qi.zero();
-              body(xi, qi, img + (size_t)ri * C + cv * 8);
-            }
-          }
-        }
+        if (residual) stream_rows(std::integral_constant<int, kPipeU>{}, std::true_type{});
+        else stream_rows(std::integral_constant<int, 2 * kPipeU>{}, std::false_type{});
       } else {
         for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
           Raw8<T> x[U], rr[U];
@@ -353,16 +371,20 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
 // ------------------------------------------------------------------------------------ act_bn_bwd
 // kApply: the SECOND pass of the pair (dfv_act_bn_bwd_apply): same pipelined loads of (g, raw), recomputes du and writes
 //   d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])  into `du` (may alias g); no sums.
-template <typename T, bool kGate, int U, int MINB, bool kApply = false>
+template <typename T, bool kGate, int U, int MINB, bool kApply = false, bool kSpec = false>
 __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           int act, const T* __restrict__ gate, const float* __restrict__ dpool,
-                                                           float inv_hw, const float* __restrict__ rowscale,
-                                                           const float* __restrict__ mask, T* __restrict__ du,
+                                                           int act_rt, const T* __restrict__ gate, const float* __restrict__ dpool,
+                                                           float inv_hw, const float* __restrict__ rowscale_rt,
+                                                           const float* __restrict__ mask_rt, T* __restrict__ du,
                                                            float* __restrict__ partial, long long rows_per_image, int C,
                                                            long long rows_per_chunk, const float* __restrict__ coef = nullptr) {
   pdl_prologue();
+  // kSpec: swish, no dropout mask, no drop-connect row scale (the backbone's expanded tensors) folded at compile time
+  const int act = kSpec ? (int)DFV_ACT_SILU : act_rt;
+  const float* rowscale = kSpec ? nullptr : rowscale_rt;
+  const float* mask = kSpec ? nullptr : mask_rt;
   __shared__ float sm[kApply ? 1 : kNT * 16];
   const ColMap m(C);
   const int b = blockIdx.y;
@@ -929,9 +951,20 @@ int dfv_bn_act_fwd(const void* raw, const float* mean, const float* invstd, cons
       DFV_CUDA(cudaFuncSetAttribute(bn_act_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStage));
       configured = true;
     }
-    DFV_PDL((bn_act_kernel<__nv_bfloat16, true>), grid, kNT, kStage, st, (const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act, rowscale,
-                                                                (const __nv_bfloat16*)residual, mask, (__nv_bfloat16*)out,
-                                                                pool_partial, rows_per_image, C, rpc);
+    if (act == DFV_ACT_SILU && !rowscale && !residual && !mask) {
+      static thread_local bool configured_s = false;
+      if (!configured_s) {
+        DFV_CUDA(cudaFuncSetAttribute(bn_act_kernel<__nv_bfloat16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStage));
+        configured_s = true;
+      }
+      DFV_PDL((bn_act_kernel<__nv_bfloat16, true, true>), grid, kNT, kStage, st, (const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act,
+                                                                        rowscale, (const __nv_bfloat16*)residual, mask, (__nv_bfloat16*)out,
+                                                                        pool_partial, rows_per_image, C, rpc);
+    } else {
+      DFV_PDL((bn_act_kernel<__nv_bfloat16, true>), grid, kNT, kStage, st, (const __nv_bfloat16*)raw, mean, invstd, gamma, beta, act, rowscale,
+                                                                  (const __nv_bfloat16*)residual, mask, (__nv_bfloat16*)out,
+                                                                  pool_partial, rows_per_image, C, rpc);
+    }
   } else {
     DFV_PDL((bn_act_kernel<float, false>), grid, kNT, 0, st, (const float*)raw, mean, invstd, gamma, beta, act, rowscale,
                                                     (const float*)residual, mask, (float*)out, pool_partial, rows_per_image, C, rpc);
@@ -964,13 +997,27 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
                                                                (const T_*)gate, dpool, inv_hw, rowscale, mask, (T_*)du, ws,        \
                                                                rows_per_image, C, rpc, (const float*)nullptr);                     \
   } while (0)
+#define ABB_SPEC(G_, SMEM_)                                                                                                          \
+  do {                                                                                                                              \
+    static thread_local bool configured = false;                                                                                    \
+    if (!configured) {                                                                                                              \
+      DFV_CUDA(cudaFuncSetAttribute(act_bn_bwd_kernel<__nv_bfloat16, G_, 4, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_)); \
+      configured = true;                                                                                                            \
+    }                                                                                                                               \
+    DFV_PDL((act_bn_bwd_kernel<__nv_bfloat16, G_, 4, 2, false, true>), grid, kNT, SMEM_, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)raw, mean, \
+            invstd, gamma, beta, act, (const __nv_bfloat16*)gate, dpool, inv_hw, rowscale, mask, (__nv_bfloat16*)du, ws, rows_per_image, C, rpc,     \
+            (const float*)nullptr);                                                                                                 \
+  } while (0)
   constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;   // cp.async staging of the bf16 kernels
+  const bool spec = act == DFV_ACT_SILU && !rowscale && !mask;
   if (dtype == DFV_BF16) {
-    if (gated) ABB(__nv_bfloat16, true, 4, 2, kStageBytes); else ABB(__nv_bfloat16, false, 4, 2, kStageBytes);
+    if (spec) { if (gated) ABB_SPEC(true, kStageBytes); else ABB_SPEC(false, kStageBytes); }
+    else if (gated) ABB(__nv_bfloat16, true, 4, 2, kStageBytes); else ABB(__nv_bfloat16, false, 4, 2, kStageBytes);
   } else {
     if (gated) ABB(float, true, 2, 2, 0); else ABB(float, false, 2, 2, 0);
   }
 #undef ABB
+#undef ABB_SPEC
   DFV_LAUNCH_CHECK();
   DFV_PDL(bn_bwd_finalize_kernel, (C + 31) / 32, kFinLanes * 32, 0, st, ws, (int)(chunks * B), C, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
   DFV_LAUNCH_CHECK();
@@ -1020,12 +1067,26 @@ int dfv_act_bn_bwd_apply(const void* g, const void* raw, const float* mean, cons
                                                                rows_per_image, C, rpc, coef);                                      \
   } while (0)
   constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;   // cp.async staging of the bf16 kernels
+#define ABA_SPEC(G_, SMEM_)                                                                                                          \
+  do {                                                                                                                              \
+    static thread_local bool configured = false;                                                                                    \
+    if (!configured) {                                                                                                              \
+      DFV_CUDA(cudaFuncSetAttribute(act_bn_bwd_kernel<__nv_bfloat16, G_, 4, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_)); \
+      configured = true;                                                                                                            \
+    }                                                                                                                               \
+    DFV_PDL((act_bn_bwd_kernel<__nv_bfloat16, G_, 4, 2, true, true>), grid, kNT, SMEM_, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)raw, mean, \
+            invstd, gamma, beta, act, (const __nv_bfloat16*)gate, dpool, inv_hw, rowscale, mask, (__nv_bfloat16*)draw, (float*)nullptr,             \
+            rows_per_image, C, rpc, coef);                                                                                          \
+  } while (0)
+  const bool spec = act == DFV_ACT_SILU && !rowscale && !mask;
   if (dtype == DFV_BF16) {
-    if (gated) ABA(__nv_bfloat16, true, 4, 2, kStageBytes); else ABA(__nv_bfloat16, false, 4, 2, kStageBytes);
+    if (spec) { if (gated) ABA_SPEC(true, kStageBytes); else ABA_SPEC(false, kStageBytes); }
+    else if (gated) ABA(__nv_bfloat16, true, 4, 2, kStageBytes); else ABA(__nv_bfloat16, false, 4, 2, kStageBytes);
   } else {
     if (gated) ABA(float, true, 2, 2, 0); else ABA(float, false, 2, 2, 0);
   }
 #undef ABA
+#undef ABA_SPEC
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
