@@ -108,10 +108,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def measured_traffic(kernel):
+def measured_traffic(kernel, train=False):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over this kernel's launches of one
-    step) from the committed ncu pass (profiles/r02_traffic.json, else round 1's); None if absent."""
-    for name in ("r02_traffic.json", "r01_traffic.json"):
+    step) from the committed ncu pass (profiles/r02_traffic.json, else round 1's; the training step:
+    profiles/r02_train_traffic.json); None if absent."""
+    for name in (("r02_train_traffic.json",) if train else ("r02_traffic.json", "r01_traffic.json")):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 v = json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
@@ -226,7 +227,7 @@ def gpu_stock_baseline(dev):
     return out
 
 
-def kernel_table(recs, prof_steps, pk):
+def kernel_table(recs, prof_steps, pk, train=False):
     agg = {}
     for kind, nbytes, flops, kms in recs:
         a = agg.setdefault(kind, [0.0, 0.0, 0.0, 0])
@@ -240,7 +241,7 @@ def kernel_table(recs, prof_steps, pk):
     top = max(agg, key=lambda k: agg[k][2])
     tb, tf, tms, tn = agg[top]
     roofline = {"kernel": top, "bound": "hbm", "achieved": tb / (tms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": measured_traffic(top), "peak_source": pk["source"],
+                "frac": tb / (tms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": measured_traffic(top, train), "peak_source": pk["source"],
                 "launches": tn // prof_steps, "avg_launch_ms": tms / tn, "algorithmic_bytes_per_launch": tb / tn, "kernels": kernels,
                 "note": "achieved = sum of algorithmic bytes of this kernel's launches / sum of their CUDA-event "
                         "durations, measured on the launch stream in a profiled pass right after the timed region"}
@@ -338,7 +339,7 @@ def train_leg(c, steps, warmup):
         with open(os.environ["DFV_BENCH_DUMP"] + ".train", "w") as f:
             json.dump([{"kind": k, "bytes": b, "flops": fl, "ms": m} for k, b, fl, m in recs[-per:]], f)
     pk = peaks()
-    roofline = kernel_table(recs, prof_steps, pk)
+    roofline = kernel_table(recs, prof_steps, pk, train=True)
 
     # end to end: pinned host batch (raw uint8 crops) -> device every step, loss read back every step
     model.zero_grad(set_to_none=True)
