@@ -299,6 +299,31 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
         // [2 buffers][U rows][1 or 2 tensors][kNT threads] = 16 slots per thread either way: without a residual (every
         // layer but the block outputs) the residual's slots carry four more rows of `raw` -- with 4 x 16 bytes per thread in
         // flight the one-input forward streams ran at 3.8-4.8 TB/s (28.63 -> 28.08 ms per training step with 8 x 16)
+        // kSpec: swish on channel PAIRS with packed fp32 instructions (h = u / 2 = x * sc / 2 + sh / 2, y = h tanh(h) + h)
+        float2 sch[4], shh[4], ps2[4];
+        if constexpr (kSpec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sch[j] = make_float2(0.5f * sc[2 * j], 0.5f * sc[2 * j + 1]);
+            shh[j] = make_float2(0.5f * sh[2 * j], 0.5f * sh[2 * j + 1]);
+            ps2[j] = make_float2(0.f, 0.f);
+          }
+        }
+        auto body2 = [&](const uint4& xr, size_t off) {
+          const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 h = ffma2(make_float2(bf16_lo(xw[j]), bf16_hi(xw[j])), sch[j], shh[j]);
+            float2 t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+            const float2 y = ffma2(h, t, h);
+            ps2[j] = fadd2(ps2[j], y);
+            ow[j] = pack_bf16(y.x, y.y);
+          }
+          *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        };
         extern __shared__ uint4 stage[];
         auto stream_rows = [&](auto u_c, auto res_c) {
           constexpr int U = decltype(u_c)::value;
@@ -327,16 +352,24 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
             for (int i = 0; i < U; ++i) {
               const long long ri = r + (long long)i * m.rpp;
               if (ri < r1) {
-                Raw8<T> xi, qi;
-                xi.r = *slot(buf, i, 0);
-                if constexpr (kRes) qi.r = *slot(buf, i, 1); else qi.zero();
-                body(xi, qi, img + (size_t)ri * C + cv * 8);
+                if constexpr (kSpec) {
+                  body2(*slot(buf, i, 0), img + (size_t)ri * C + cv * 8);
+                } else {
+                  Raw8<T> xi, qi;
+                  xi.r = *slot(buf, i, 0);
+                  if constexpr (kRes) qi.r = *slot(buf, i, 1); else qi.zero();
+                  body(xi, qi, img + (size_t)ri * C + cv * 8);
+                }
               }
             }
           }
         };
         if (residual) stream_rows(std::integral_constant<int, kPipeU>{}, std::true_type{});
         else stream_rows(std::integral_constant<int, 2 * kPipeU>{}, std::false_type{});
+        if constexpr (kSpec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { ps[2 * j] = ps2[j].x; ps[2 * j + 1] = ps2[j].y; }
+        }
       } else {
         for (long long r = r0 + m.row_l; r < r1; r += (long long)U * m.rpp) {
           Raw8<T> x[U], rr[U];
@@ -450,6 +483,58 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
         if (kApply || du) store8(du + off, gv);      // du = NULL: reduction only (the apply pass recomputes du)
       };
       if constexpr (sizeof(T) == 2) {
+        // kSpec (swish, bf16): the same arithmetic on PAIRS of channels with packed fp32 instructions (FFMA2 / FMUL2 / FADD2
+        // take one issue slot for two lanes' operations; these streams co-limit on issue slots, ~16 scalar instructions per
+        // element beside the MUFU).  With h = u / 2 = x * c1 + c2, t = tanh(h), s = sigma(u) = t / 2 + 1 / 2:
+        //   act'(u) = s + u s (1 - s) = s - h (t^2 - 1) / 2
+        float2 c1p[4], c2p[4], isp[4], nmp[4], gtp[kGate ? 4 : 1], dpp[kGate ? 4 : 1], pap[kApply ? 4 : 1], npq[kApply ? 4 : 1],
+            npr[kApply ? 4 : 1], accd[4], accx[4];
+        if constexpr (kSpec) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e0 = 2 * j, e1 = 2 * j + 1;
+            c1p[j] = make_float2(0.5f * is[e0] * ga[e0], 0.5f * is[e1] * ga[e1]);
+            c2p[j] = make_float2(0.5f * fmaf(nm[e0], ga[e0], be[e0]), 0.5f * fmaf(nm[e1], ga[e1], be[e1]));
+            isp[j] = make_float2(is[e0], is[e1]);
+            nmp[j] = make_float2(nm[e0], nm[e1]);
+            accd[j] = accx[j] = make_float2(0.f, 0.f);
+            if constexpr (kGate) { gtp[j] = make_float2(gt[e0], gt[e1]); dpp[j] = make_float2(dp[e0], dp[e1]); }
+            if constexpr (kApply) {
+              pap[j] = make_float2(ga[e0] * is[e0], ga[e1] * is[e1]);
+              npq[j] = make_float2(-pq[e0], -pq[e1]);
+              npr[j] = make_float2(-pr[e0], -pr[e1]);
+            }
+          }
+        }
+        auto body2 = [&](const uint4& gr, const uint4& xr, size_t off) {
+          const uint32_t gw[4] = {gr.x, gr.y, gr.z, gr.w}, xw[4] = {xr.x, xr.y, xr.z, xr.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 g2 = make_float2(bf16_lo(gw[j]), bf16_hi(gw[j])), x2 = make_float2(bf16_lo(xw[j]), bf16_hi(xw[j]));
+            float2 gi;
+            if constexpr (kGate) gi = ffma2(g2, gtp[j], dpp[j]); else gi = g2;
+            const float2 h = ffma2(x2, c1p[j], c2p[j]);
+            float2 t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+            const float2 sg = ffma2(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+            const float2 w = ffma2(t, t, make_float2(-1.f, -1.f));
+            const float2 z = fmul2(h, w);
+            const float2 gr2 = ffma2(z, make_float2(-0.5f, -0.5f), sg);
+            const float2 d = fmul2(gi, gr2);
+            if constexpr (kApply) {
+              const float2 o = ffma2(pap[j], d, ffma2(npq[j], x2, npr[j]));
+              ow[j] = pack_bf16(o.x, o.y);
+            } else {
+              const float2 xh = ffma2(x2, isp[j], nmp[j]);
+              accd[j] = fadd2(accd[j], d);
+              accx[j] = ffma2(d, xh, accx[j]);
+              if (du) ow[j] = pack_bf16(d.x, d.y);
+            }
+          }
+          if (kApply || du) *reinterpret_cast<uint4*>(du + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        };
         extern __shared__ uint4 stage[];   // [2 buffers][kPipeU rows][2 tensors][kNT threads]
         auto slot = [&](int buf, int i, int t) { return stage + ((buf * kPipeU + i) * 2 + t) * kNT + threadIdx.x; };
         auto prefetch = [&](long long r, int buf) {
@@ -474,11 +559,22 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
           for (int i = 0; i < kPipeU; ++i) {
             const long long ri = r + (long long)i * m.rpp;
             if (ri < r1) {
-              Raw8<T> gxi, xxi;
-              gxi.r = *slot(buf, i, 0);
-              xxi.r = *slot(buf, i, 1);
-              body(gxi, xxi, img + (size_t)ri * C + cv * 8);
+              if constexpr (kSpec) {
+                body2(*slot(buf, i, 0), *slot(buf, i, 1), img + (size_t)ri * C + cv * 8);
+              } else {
+                Raw8<T> gxi, xxi;
+                gxi.r = *slot(buf, i, 0);
+                xxi.r = *slot(buf, i, 1);
+                body(gxi, xxi, img + (size_t)ri * C + cv * 8);
+              }
             }
+          }
+        }
+        if constexpr (kSpec && !kApply) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] = accd[j].x; acc[2 * j + 1] = accd[j].y;
+            acc[8 + 2 * j] = accx[j].x; acc[8 + 2 * j + 1] = accx[j].y;
           }
         }
       } else {
