@@ -580,12 +580,28 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     DFV_TRY(dfv_pw_wgrad(sc.gP, ba.d, ba.gate, (int)hw_out, G(i, DFV_T_PROJ_W), dtype, B * hw_out, b.c_mid, b.c_out, stream));
     DFV_TRY(dfv_pw_conv_fwd(sc.gP, ba.wPt, ar.zero_bias, nullptr, (int)hw_out, nullptr, sc.gA, dtype, B, B * hw_out, b.c_out, b.c_mid, DFV_ACT_NONE,
                             sc.fold_ws, stream));
-    // squeeze-excite
-    DFV_TRY(dfv_se_bwd(sc.gA, ba.d, dtype, ba.gate_f32, ba.pooled, ba.h1, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_E_W), sc.dpool, G(i, DFV_T_SE_R_W),
-                       G(i, DFV_T_SE_R_B), G(i, DFV_T_SE_E_W), G(i, DFV_T_SE_E_B), sc.se_ws, B, hw_out, b.c_mid, b.se_squeeze, stream));
-    // gate, swish, bn1
-    DFV_TRY(bn_backward(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool, 1.0f / (float)hw_out,
-                        nullptr, sc.gA, G(i, DFV_T_BN1_G), G(i, DFV_T_BN1_B), hw_out, b.c_mid));
+    if (dtype == DFV_BF16) {
+      // squeeze-excite + the reduction half of [gate, swish, bn1] in ONE pass over (gA, d_raw): the reduction is linear in
+      // (gate, dpool) per image, so it runs before the SE backward (which it also feeds: sum_hw gA * swish(u)) and is
+      // combined with gate / dpool afterwards (dfv_act_bn_bwd_gated_reduce).  Saves the SE backward's own pass over (gA, d).
+      DFV_TRY(dfv_act_bn_bwd_gated_reduce(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), sc.bn_ws, sc.se_ws, dtype, B, hw_out,
+                                          b.c_mid, stream));
+      DFV_TRY(dfv_se_bwd_from_partials(ba.gate_f32, ba.pooled, ba.h1, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_E_W), sc.dpool, G(i, DFV_T_SE_R_W),
+                                       G(i, DFV_T_SE_R_B), G(i, DFV_T_SE_E_W), G(i, DFV_T_SE_E_B), sc.se_ws, B, hw_out, b.c_mid, b.se_squeeze,
+                                       stream));
+      DFV_TRY(dfv_bn_bwd_gated_finalize(sc.bn_ws, ba.gate, sc.dpool, 1.0f / (float)hw_out, ba.m1, ba.i1, bn_grad(G(i, DFV_T_BN1_G)),
+                                        bn_grad(G(i, DFV_T_BN1_B)), sc.coef, dtype, B, hw_out, b.c_mid, stream));
+      if (frozen) DFV_CUDA(cudaMemsetAsync(sc.coef, 0, sizeof(float) * 2 * (size_t)b.c_mid, st));
+      DFV_TRY(dfv_act_bn_bwd_apply(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool,
+                                   1.0f / (float)hw_out, nullptr, nullptr, sc.coef, sc.gA, dtype, B, hw_out, b.c_mid, stream));
+    } else {
+      // squeeze-excite
+      DFV_TRY(dfv_se_bwd(sc.gA, ba.d, dtype, ba.gate_f32, ba.pooled, ba.h1, P(i, DFV_T_SE_R_W), P(i, DFV_T_SE_E_W), sc.dpool, G(i, DFV_T_SE_R_W),
+                         G(i, DFV_T_SE_R_B), G(i, DFV_T_SE_E_W), G(i, DFV_T_SE_E_B), sc.se_ws, B, hw_out, b.c_mid, b.se_squeeze, stream));
+      // gate, swish, bn1
+      DFV_TRY(bn_backward(sc.gA, ba.d_raw, ba.m1, ba.i1, P(i, DFV_T_BN1_G), P(i, DFV_T_BN1_B), DFV_ACT_SILU, ba.gate, sc.dpool, 1.0f / (float)hw_out,
+                          nullptr, sc.gA, G(i, DFV_T_BN1_G), G(i, DFV_T_BN1_B), hw_out, b.c_mid));
+    }
     // depthwise conv
     const void* dw_in = b.has_expand ? (const void*)ba.e : x;
     const int kk = b.kernel * b.kernel;

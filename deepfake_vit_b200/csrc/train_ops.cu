@@ -404,7 +404,13 @@ __global__ void __launch_bounds__(kNT) bn_act_kernel(const T* __restrict__ raw, 
 // ------------------------------------------------------------------------------------ act_bn_bwd
 // kApply: the SECOND pass of the pair (dfv_act_bn_bwd_apply): same pipelined loads of (g, raw), recomputes du and writes
 //   d raw = gamma * invstd * (du - coef[0] - xhat * coef[1])  into `du` (may alias g); no sums.
-template <typename T, bool kGate, int U, int MINB, bool kApply = false, bool kSpec = false>
+// kDefer (gated swish layers, bf16, reduction pass only): the SE backward needs sum_hw(g * d) BEFORE this layer's input gradient
+// exists (its dpool enters gi = g * gate + dpool / HW), which used to cost a separate pass over (g, d).  The reduction is
+// linear in (gate, dpool) per image, so this pass accumulates per (image, channel)
+//   S1 = sum g act'(u),  S2 = sum act'(u),  S3 = sum g act'(u) x,  S4 = sum act'(u) x,  D = sum g swish(u)
+// (swish(u) = d is recomputed from raw: one more FFMA2 per pair), the SE backward runs on D, and
+// bn_bwd_finalize_defer_kernel forms sum du = sum_b (gate S1 + dp S2), sum du xhat = is (sum_b (gate S3 + dp S4)) + nm sum du.
+template <typename T, bool kGate, int U, int MINB, bool kApply = false, bool kSpec = false, bool kDefer = false>
 __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restrict__ g, const T* __restrict__ raw,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -412,7 +418,9 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
                                                            float inv_hw, const float* __restrict__ rowscale_rt,
                                                            const float* __restrict__ mask_rt, T* __restrict__ du,
                                                            float* __restrict__ partial, long long rows_per_image, int C,
-                                                           long long rows_per_chunk, const float* __restrict__ coef = nullptr) {
+                                                           long long rows_per_chunk, const float* __restrict__ coef = nullptr,
+                                                           float* __restrict__ partial_d = nullptr) {
+  static_assert(!kDefer || (kGate && kSpec && !kApply && sizeof(T) == 2), "deferred gate: gated swish reduction pass, bf16");
   pdl_prologue();
   // kSpec: swish, no dropout mask, no drop-connect row scale (the backbone's expanded tensors) folded at compile time
   const int act = kSpec ? (int)DFV_ACT_SILU : act_rt;
@@ -425,12 +433,16 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
   const long long r1 = min(r0 + rows_per_chunk, rows_per_image);
   const size_t img = (size_t)b * rows_per_image * C;
   const float rs = rowscale ? rowscale[b] : 1.f;
-  float* pout = partial + ((size_t)b * gridDim.x + blockIdx.x) * 2 * C;
+  float* pout = partial + ((size_t)b * gridDim.x + blockIdx.x) * (kDefer ? 4 : 2) * C;
   for (int cb = 0; cb < m.CV; cb += m.cpp) {
     const int cv = cb + m.col_l;
-    float acc[16];
+    float acc[16], acc_b[kDefer ? 24 : 1];      // kDefer: acc = S1 | S2, acc_b = S3 | S4 | D
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+    if constexpr (kDefer) {
+#pragma unroll
+      for (int e = 0; e < 24; ++e) acc_b[e] = 0.f;
+    }
     if (cv < m.CV && m.row_l < m.rpp) {
       // xhat = x * is + nm,  u = xhat * ga + be
       float is[8], nm[8], ga[8], be[8], gt[8], dp[8], pq[kApply ? 8 : 1], pr[kApply ? 8 : 1];
@@ -488,7 +500,11 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
         // element beside the MUFU).  With h = u / 2 = x * c1 + c2, t = tanh(h), s = sigma(u) = t / 2 + 1 / 2:
         //   act'(u) = s + u s (1 - s) = s - h (t^2 - 1) / 2
         float2 c1p[4], c2p[4], isp[4], nmp[4], gtp[kGate ? 4 : 1], dpp[kGate ? 4 : 1], pap[kApply ? 4 : 1], npq[kApply ? 4 : 1],
-            npr[kApply ? 4 : 1], accd[4], accx[4];
+            npr[kApply ? 4 : 1], accd[4], accx[4], acc2[kDefer ? 4 : 1], acc4[kDefer ? 4 : 1], accg[kDefer ? 4 : 1];
+        if constexpr (kDefer) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc2[j] = acc4[j] = accg[j] = make_float2(0.f, 0.f);
+        }
         if constexpr (kSpec) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -513,7 +529,7 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
           for (int j = 0; j < 4; ++j) {
             const float2 g2 = make_float2(bf16_lo(gw[j]), bf16_hi(gw[j])), x2 = make_float2(bf16_lo(xw[j]), bf16_hi(xw[j]));
             float2 gi;
-            if constexpr (kGate) gi = ffma2(g2, gtp[j], dpp[j]); else gi = g2;
+            if constexpr (kGate && !kDefer) gi = ffma2(g2, gtp[j], dpp[j]); else gi = g2;
             const float2 h = ffma2(x2, c1p[j], c2p[j]);
             float2 t;
             asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
@@ -523,7 +539,13 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
             const float2 z = fmul2(h, w);
             const float2 gr2 = ffma2(z, make_float2(-0.5f, -0.5f), sg);
             const float2 d = fmul2(gi, gr2);
-            if constexpr (kApply) {
+            if constexpr (kDefer) {      // d = g act'(u) here; accd = S1, acc2 = S2, accx = S3, acc4 = S4, accg = D
+              accd[j] = fadd2(accd[j], d);
+              acc2[j] = fadd2(acc2[j], gr2);
+              accx[j] = ffma2(d, x2, accx[j]);
+              acc4[j] = ffma2(gr2, x2, acc4[j]);
+              accg[j] = ffma2(g2, ffma2(h, t, h), accg[j]);
+            } else if constexpr (kApply) {
               const float2 o = ffma2(pap[j], d, ffma2(npq[j], x2, npr[j]));
               ow[j] = pack_bf16(o.x, o.y);
             } else {
@@ -533,7 +555,9 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
               if (du) ow[j] = pack_bf16(d.x, d.y);
             }
           }
-          if (kApply || du) *reinterpret_cast<uint4*>(du + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          if constexpr (!kDefer) {
+            if (kApply || du) *reinterpret_cast<uint4*>(du + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          }
         };
         extern __shared__ uint4 stage[];   // [2 buffers][kPipeU rows][2 tensors][kNT threads]
         auto slot = [&](int buf, int i, int t) { return stage + ((buf * kPipeU + i) * 2 + t) * kNT + threadIdx.x; };
@@ -570,7 +594,16 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
             }
           }
         }
-        if constexpr (kSpec && !kApply) {
+        if constexpr (kDefer) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] = accd[j].x; acc[2 * j + 1] = accd[j].y;
+            acc[8 + 2 * j] = acc2[j].x; acc[8 + 2 * j + 1] = acc2[j].y;
+            acc_b[2 * j] = accx[j].x; acc_b[2 * j + 1] = accx[j].y;
+            acc_b[8 + 2 * j] = acc4[j].x; acc_b[8 + 2 * j + 1] = acc4[j].y;
+            acc_b[16 + 2 * j] = accg[j].x; acc_b[16 + 2 * j + 1] = accg[j].y;
+          }
+        } else if constexpr (kSpec && !kApply) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             acc[2 * j] = accd[j].x; acc[2 * j + 1] = accd[j].y;
@@ -605,7 +638,71 @@ __global__ void __launch_bounds__(kNT, MINB) act_bn_bwd_kernel(const T* __restri
       *reinterpret_cast<float4*>(pout + C + cv * 8) = make_float4(acc[8], acc[9], acc[10], acc[11]);
       *reinterpret_cast<float4*>(pout + C + cv * 8 + 4) = make_float4(acc[12], acc[13], acc[14], acc[15]);
     }
+    if constexpr (kDefer) {
+      reduce_rows<16>(sm, m, acc_b);
+      if (m.row_l == 0 && cv < m.CV) {
+        *reinterpret_cast<float4*>(pout + 2 * C + cv * 8) = make_float4(acc_b[0], acc_b[1], acc_b[2], acc_b[3]);
+        *reinterpret_cast<float4*>(pout + 2 * C + cv * 8 + 4) = make_float4(acc_b[4], acc_b[5], acc_b[6], acc_b[7]);
+        *reinterpret_cast<float4*>(pout + 3 * C + cv * 8) = make_float4(acc_b[8], acc_b[9], acc_b[10], acc_b[11]);
+        *reinterpret_cast<float4*>(pout + 3 * C + cv * 8 + 4) = make_float4(acc_b[12], acc_b[13], acc_b[14], acc_b[15]);
+      }
+      reduce_rows<8>(sm, m, acc_b + 16);
+      if (m.row_l == 0 && cv < m.CV) {
+        float* pd = partial_d + ((size_t)b * gridDim.x + blockIdx.x) * C + cv * 8;
+        *reinterpret_cast<float4*>(pd) = make_float4(acc_b[16], acc_b[17], acc_b[18], acc_b[19]);
+        *reinterpret_cast<float4*>(pd + 4) = make_float4(acc_b[20], acc_b[21], acc_b[22], acc_b[23]);
+      }
+    }
   }
+}
+
+// Deferred-gate finalize: sums the per-(image, chunk) rows [S1 | S2 | S3 | S4] of the kDefer reduction pass with the image's gate
+// and dpool (see act_bn_bwd_kernel), in double, CTA = 32 channels x 32 row lanes.
+template <typename GT>
+__global__ void __launch_bounds__(kFinLanes * 32) bn_bwd_finalize_defer_kernel(const float* __restrict__ partial, int chunks, int B, int C,
+                                                                   const GT* __restrict__ gate, const float* __restrict__ dpool,
+                                                                   float inv_hw, const float* __restrict__ mean,
+                                                                   const float* __restrict__ invstd, double count,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   float* __restrict__ coef) {
+  pdl_prologue();
+  __shared__ double sh[2][kFinLanes][32];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const int n = B * chunks;
+  double s1 = 0.0, sx = 0.0;
+  if (c < C) {
+    for (int i = lane; i < n; i += kFinLanes * 4) {
+      float v[4][4], gv[4], dv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = i + u * kFinLanes;
+        const bool ok = r < n;
+        const int bi = ok ? r / chunks : 0;
+        const float* row = partial + (size_t)(ok ? r : 0) * 4 * C + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[u][q] = ok ? row[(size_t)q * C] : 0.f;
+        gv[u] = ok ? (float)gate[(size_t)bi * C + c] : 0.f;
+        dv[u] = ok ? dpool[(size_t)bi * C + c] * inv_hw : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s1 += (double)gv[u] * (double)v[u][0] + (double)dv[u] * (double)v[u][1];
+        sx += (double)gv[u] * (double)v[u][2] + (double)dv[u] * (double)v[u][3];
+      }
+    }
+  }
+  sh[0][lane][cl] = s1;
+  sh[1][lane][cl] = sx;
+  __syncthreads();
+  if (lane != 0 || c >= C) return;
+  for (int l = 1; l < kFinLanes; ++l) { s1 += sh[0][l][cl]; sx += sh[1][l][cl]; }
+  const double is = (double)invstd[c], nm = -(double)mean[c] * is;
+  const double s2 = is * sx + nm * s1;              // sum du * xhat,  xhat = x * is + nm
+  if (dbeta) dbeta[c] = (float)s1;
+  if (dgamma) dgamma[c] = (float)s2;
+  coef[c] = (float)(s1 / count);
+  coef[C + c] = (float)(s2 / count);
 }
 
 __global__ void __launch_bounds__(kFinLanes * 32) bn_bwd_finalize_kernel(const float* __restrict__ partial, int n_partial, int C,
@@ -993,8 +1090,8 @@ int dfv_rows_chunks(int B, long long rows_per_image) {
 
 size_t dfv_bn_ws_floats(int B, long long rows_per_image, int C) {
   if (B <= 0 || rows_per_image <= 0 || C <= 0) return 0;
-  /* >= 2C doubles (the per-channel sum / sum-of-squares accumulators) */
-  return std::max<size_t>((size_t)B * chunks_for(B, rows_per_image) * 2 * C, 4 * (size_t)C + 16);
+  /* >= 2C doubles (the per-channel sum / sum-of-squares accumulators); 4C floats per partial row: dfv_act_bn_bwd_gated_reduce */
+  return std::max<size_t>((size_t)B * chunks_for(B, rows_per_image) * 4 * C, 4 * (size_t)C + 16);
 }
 
 int dfv_bn_stats_fwd(const void* raw, int dtype, int B, long long rows_per_image, int C, float eps, float momentum,
@@ -1091,7 +1188,7 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
     }                                                                                                                               \
     DFV_PDL((act_bn_bwd_kernel<T_, G_, U_, M_>), grid, kNT, SMEM_, st, (const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act,       \
                                                                (const T_*)gate, dpool, inv_hw, rowscale, mask, (T_*)du, ws,        \
-                                                               rows_per_image, C, rpc, (const float*)nullptr);                     \
+                                                               rows_per_image, C, rpc, (const float*)nullptr, (float*)nullptr);    \
   } while (0)
 #define ABB_SPEC(G_, SMEM_)                                                                                                          \
   do {                                                                                                                              \
@@ -1102,7 +1199,7 @@ int dfv_act_bn_bwd(const void* g, const void* raw, const float* mean, const floa
     }                                                                                                                               \
     DFV_PDL((act_bn_bwd_kernel<__nv_bfloat16, G_, 4, 2, false, true>), grid, kNT, SMEM_, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)raw, mean, \
             invstd, gamma, beta, act, (const __nv_bfloat16*)gate, dpool, inv_hw, rowscale, mask, (__nv_bfloat16*)du, ws, rows_per_image, C, rpc,     \
-            (const float*)nullptr);                                                                                                 \
+            (const float*)nullptr, (float*)nullptr);                                                                                \
   } while (0)
   constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;   // cp.async staging of the bf16 kernels
   const bool spec = act == DFV_ACT_SILU && !rowscale && !mask;
@@ -1160,7 +1257,7 @@ int dfv_act_bn_bwd_apply(const void* g, const void* raw, const float* mean, cons
     }                                                                                                                               \
     DFV_PDL((act_bn_bwd_kernel<T_, G_, U_, M_, true>), grid, kNT, SMEM_, st, (const T_*)g, (const T_*)raw, mean, invstd, gamma, beta, act,  \
                                                                (const T_*)gate, dpool, inv_hw, rowscale, mask, (T_*)draw, (float*)nullptr, \
-                                                               rows_per_image, C, rpc, coef);                                      \
+                                                               rows_per_image, C, rpc, coef, (float*)nullptr);                     \
   } while (0)
   constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;   // cp.async staging of the bf16 kernels
 #define ABA_SPEC(G_, SMEM_)                                                                                                          \
@@ -1172,7 +1269,7 @@ int dfv_act_bn_bwd_apply(const void* g, const void* raw, const float* mean, cons
     }                                                                                                                               \
     DFV_PDL((act_bn_bwd_kernel<__nv_bfloat16, G_, 4, 2, true, true>), grid, kNT, SMEM_, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)raw, mean, \
             invstd, gamma, beta, act, (const __nv_bfloat16*)gate, dpool, inv_hw, rowscale, mask, (__nv_bfloat16*)draw, (float*)nullptr,             \
-            rows_per_image, C, rpc, coef);                                                                                          \
+            rows_per_image, C, rpc, coef, (float*)nullptr);                                                                         \
   } while (0)
   const bool spec = act == DFV_ACT_SILU && !rowscale && !mask;
   if (dtype == DFV_BF16) {
@@ -1183,6 +1280,47 @@ int dfv_act_bn_bwd_apply(const void* g, const void* raw, const float* mean, cons
   }
 #undef ABA
 #undef ABA_SPEC
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+/* Gated swish layers (the depthwise output), bf16: the BatchNorm-backward reduction with the SE gate / dpool terms DEFERRED
+ * (act_bn_bwd_kernel kDefer).  One pass over (g, raw) writes ws4 [B][chunks][4][C] and the SE backward's dot partials
+ * partial_d [B][chunks][C]; after dfv_se_bwd_from_partials has produced dpool, dfv_bn_bwd_gated_finalize forms dgamma / dbeta /
+ * coef -- exactly what dfv_act_bn_bwd(gate, dpool) returns, without the separate pass over (g, d) of dfv_se_bwd. */
+int dfv_act_bn_bwd_gated_reduce(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                float* ws4, float* partial_d, int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(g && raw && mean && invstd && ws4 && partial_d, "dfv_act_bn_bwd_gated_reduce: null pointer");
+  DFV_REQUIRE(dtype == DFV_BF16 && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0, "dfv_act_bn_bwd_gated_reduce: bf16 tensors, C %% 8 == 0");
+  cudaStream_t st = as_stream(stream);
+  const long long chunks = chunks_for(B, rows_per_image);
+  const long long rpc = (rows_per_image + chunks - 1) / chunks;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  ProfScope prof(PK_BN, 2.0 * B * rows_per_image * C * dtype_size(dtype), 16.0 * B * rows_per_image * C, st);
+  constexpr int kStageBytes = 2 * kPipeU * 2 * kNT * 16;
+  static thread_local bool configured = false;
+  if (!configured) {
+    DFV_CUDA(cudaFuncSetAttribute(act_bn_bwd_kernel<__nv_bfloat16, true, 4, 2, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kStageBytes));
+    configured = true;
+  }
+  DFV_PDL((act_bn_bwd_kernel<__nv_bfloat16, true, 4, 2, false, true, true>), grid, kNT, kStageBytes, st, (const __nv_bfloat16*)g,
+          (const __nv_bfloat16*)raw, mean, invstd, gamma, beta, (int)DFV_ACT_SILU, (const __nv_bfloat16*)nullptr, (const float*)nullptr, 0.f,
+          (const float*)nullptr, (const float*)nullptr, (__nv_bfloat16*)nullptr, ws4, rows_per_image, C, rpc, (const float*)nullptr, partial_d);
+  DFV_LAUNCH_CHECK();
+  return DFV_OK;
+}
+
+int dfv_bn_bwd_gated_finalize(const float* ws4, const void* gate, const float* dpool, float inv_hw, const float* mean, const float* invstd,
+                              float* dgamma, float* dbeta, float* coef, int dtype, int B, long long rows_per_image, int C,
+                              dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(ws4 && gate && dpool && mean && invstd && coef, "dfv_bn_bwd_gated_finalize: null pointer");
+  DFV_REQUIRE(dtype == DFV_BF16 && B > 0 && rows_per_image > 0 && C > 0, "dfv_bn_bwd_gated_finalize: bad arguments");
+  const long long chunks = chunks_for(B, rows_per_image);
+  DFV_PDL((bn_bwd_finalize_defer_kernel<__nv_bfloat16>), (C + 31) / 32, kFinLanes * 32, 0, as_stream(stream), ws4, (int)chunks, B, C,
+          (const __nv_bfloat16*)gate, dpool, inv_hw, mean, invstd, (double)B * (double)rows_per_image, dgamma, dbeta, coef);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
@@ -1200,22 +1338,39 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
                float* dw_expand, float* db_expand, float* ws, int B, long long rows_per_image, int C, int squeeze,
                dfv_stream_t stream) {
   DFV_TRY(check_device());
-  DFV_REQUIRE(da && d && gate_f32 && pooled && h1 && w_reduce && w_expand && dpool && dw_reduce && db_reduce && dw_expand &&
-                  db_expand && ws, "dfv_se_bwd: null pointer");
+  DFV_REQUIRE(da && d && ws, "dfv_se_bwd: null pointer");
   DFV_REQUIRE(valid_dtype(dtype) && B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0 && squeeze > 0, "dfv_se_bwd: bad shape");
   cudaStream_t st = as_stream(stream);
   const long long chunks = chunks_for(B, rows_per_image);
   const long long rpc = (rows_per_image + chunks - 1) / chunks;
+  dim3 grid((unsigned)chunks, (unsigned)B);
+  {
+    ProfScope prof(PK_SE_GATE, 2.0 * B * rows_per_image * C * dtype_size(dtype), 2.0 * B * rows_per_image * C, st);
+    if (dtype == DFV_BF16)
+      DFV_PDL((dot_rows_kernel<__nv_bfloat16>), grid, kNT, 0, st, (const __nv_bfloat16*)da, (const __nv_bfloat16*)d, rows_per_image, C, rpc, ws);
+    else
+      DFV_PDL((dot_rows_kernel<float>), grid, kNT, 0, st, (const float*)da, (const float*)d, rows_per_image, C, rpc, ws);
+    DFV_LAUNCH_CHECK();
+  }
+  return dfv_se_bwd_from_partials(gate_f32, pooled, h1, w_reduce, w_expand, dpool, dw_reduce, db_reduce, dw_expand, db_expand, ws, B,
+                                  rows_per_image, C, squeeze, stream);
+}
+
+/* dfv_se_bwd without its streaming pass: ws[0 .. B * dfv_rows_chunks * C) already holds the per-(image, chunk) partial sums of
+ * da * d (written by dfv_act_bn_bwd_gated_reduce, which forms them while it reads the same tensors for the BatchNorm reduction). */
+int dfv_se_bwd_from_partials(const float* gate_f32, const float* pooled, const float* h1, const float* w_reduce, const float* w_expand,
+                             float* dpool, float* dw_reduce, float* db_reduce, float* dw_expand, float* db_expand, float* ws, int B,
+                             long long rows_per_image, int C, int squeeze, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(gate_f32 && pooled && h1 && w_reduce && w_expand && dpool && dw_reduce && db_reduce && dw_expand && db_expand && ws,
+              "dfv_se_bwd: null pointer");
+  DFV_REQUIRE(B > 0 && rows_per_image > 0 && C > 0 && C % 8 == 0 && squeeze > 0, "dfv_se_bwd: bad shape");
+  cudaStream_t st = as_stream(stream);
+  const long long chunks = chunks_for(B, rows_per_image);
   float* partial = ws;
   float* dz = partial + (size_t)B * chunks * C;
   float* dh1 = dz + (size_t)B * C;
-  dim3 grid((unsigned)chunks, (unsigned)B);
-  ProfScope prof(PK_SE_GATE, 2.0 * B * rows_per_image * C * dtype_size(dtype), 2.0 * B * rows_per_image * C, st);
-  if (dtype == DFV_BF16)
-    DFV_PDL((dot_rows_kernel<__nv_bfloat16>), grid, kNT, 0, st, (const __nv_bfloat16*)da, (const __nv_bfloat16*)d, rows_per_image, C, rpc, partial);
-  else
-    DFV_PDL((dot_rows_kernel<float>), grid, kNT, 0, st, (const float*)da, (const float*)d, rows_per_image, C, rpc, partial);
-  DFV_LAUNCH_CHECK();
+  ProfScope prof(PK_SE_GATE, 4.0 * ((double)B * chunks * C + 3.0 * B * C + 4.0 * C * squeeze), 6.0 * B * (double)C * squeeze, st);
   DFV_REQUIRE(squeeze <= 128, "dfv_se_bwd: squeeze width %d > 128", squeeze);
   {
     const int img = B >= 16 ? 4 : 1;

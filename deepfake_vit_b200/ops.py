@@ -355,6 +355,31 @@ def se_bwd(da, d, gate_f32, pooled, h1, w_reduce, w_expand):
     return dpool, dw1, db1, dw2, db2
 
 
+def gated_bn_se_bwd(da, raw, mean, invstd, gamma, beta, gate, gate_f32, pooled, h1, w_reduce, w_expand):
+    """The depthwise-output backward of a training block in ONE reduction pass over (da, raw) (bf16):
+    dfv_act_bn_bwd_gated_reduce -> dfv_se_bwd_from_partials -> dfv_bn_bwd_gated_finalize -> dfv_act_bn_bwd_apply.
+    Returns (d raw, dgamma, dbeta, dpool, dw_reduce, db_reduce, dw_expand, db_expand)."""
+    B, rows, C_ = _rows(raw)
+    sq, dev = h1.shape[1], raw.device
+    code = dtype_code(raw.dtype)
+    ws4 = _f32buf(lib.dfv_bn_ws_floats(B, rows, C_), dev)
+    se_ws = _f32buf(lib.dfv_se_bwd_ws_floats(B, rows, C_, sq), dev)
+    dpool = _f32buf(B * C_, dev).view(B, C_)
+    dw1, db1 = torch.zeros_like(w_reduce), _f32buf(sq, dev)
+    dw2, db2 = torch.zeros_like(w_expand), _f32buf(C_, dev)
+    dgamma, dbeta, coef = _f32buf(C_, dev), _f32buf(C_, dev), _f32buf(2 * C_, dev)
+    out = torch.empty_like(raw)
+    check(lib.dfv_act_bn_bwd_gated_reduce(_ptr(da), _ptr(raw), _f32(mean), _f32(invstd), _f32(gamma), _f32(beta), _f32(ws4), _f32(se_ws),
+                                          code, B, rows, C_, _stream()))
+    check(lib.dfv_se_bwd_from_partials(_f32(gate_f32), _f32(pooled), _f32(h1), _f32(w_reduce), _f32(w_expand), _f32(dpool), _f32(dw1),
+                                       _f32(db1), _f32(dw2), _f32(db2), _f32(se_ws), B, rows, C_, sq, _stream()))
+    check(lib.dfv_bn_bwd_gated_finalize(_f32(ws4), _ptr(gate), _f32(dpool), 1.0 / rows, _f32(mean), _f32(invstd), _f32(dgamma), _f32(dbeta),
+                                        _f32(coef), code, B, rows, C_, _stream()))
+    check(lib.dfv_act_bn_bwd_apply(_ptr(da), _ptr(raw), _f32(mean), _f32(invstd), _f32(gamma), _f32(beta), DFV_ACT_SILU, _ptr(gate),
+                                   _f32(dpool), 1.0 / rows, None, None, _f32(coef), _ptr(out), code, B, rows, C_, _stream()))
+    return out, dgamma, dbeta, dpool, dw1, db1, dw2, db2
+
+
 def hybrid_attention_train(fmap, heat, ca_w1, ca_w2, sa_w, use_channel=True, use_spatial=True):
     """Torch layouts (ca_w2 = fc.2.weight [C, hidden]).  Returns (features, saved)."""
     B, H, W, C_ = fmap.shape

@@ -362,6 +362,22 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
                float* dw_expand, float* db_expand, float* ws, int B, long long rows_per_image, int C, int squeeze,
                dfv_stream_t stream);
 
+/* The same backward with one streaming pass less (bf16 tensors, swish): the SE backward needs sum_hw(da * d) before the layer's
+ * input gradient exists (its dpool enters that gradient), but the BatchNorm reduction is LINEAR in (gate, dpool) per image.
+ * dfv_act_bn_bwd_gated_reduce reads (da, d_raw) once and writes per-(image, chunk) rows ws4 [B][chunks][4][C] (sums of da act'(u),
+ * act'(u), and both times x) plus the SE dot partials [B][chunks][C] at the start of se_ws (d = swish(u) recomputed from d_raw);
+ * dfv_se_bwd_from_partials is dfv_se_bwd without its own pass over (da, d); dfv_bn_bwd_gated_finalize combines the rows with
+ * the gate (activation dtype, as the forward applied it) and dpool into dgamma / dbeta (may be NULL) and coef [2][C] -- the values
+ * dfv_act_bn_bwd(gate, dpool) returns.  ws4: dfv_bn_ws_floats() floats. */
+int dfv_act_bn_bwd_gated_reduce(const void* g, const void* raw, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                float* ws4, float* partial_d, int dtype, int B, long long rows_per_image, int C, dfv_stream_t stream);
+int dfv_se_bwd_from_partials(const float* gate_f32, const float* pooled, const float* h1, const float* w_reduce, const float* w_expand,
+                             float* dpool, float* dw_reduce, float* db_reduce, float* dw_expand, float* db_expand, float* ws, int B,
+                             long long rows_per_image, int C, int squeeze, dfv_stream_t stream);
+int dfv_bn_bwd_gated_finalize(const float* ws4, const void* gate, const float* dpool, float inv_hw, const float* mean, const float* invstd,
+                              float* dgamma, float* dbeta, float* coef, int dtype, int B, long long rows_per_image, int C,
+                              dfv_stream_t stream);
+
 /* 1x1 conv weight gradient: dw[N][K] (fp32, torch layout, caller zeroes) += sum_m g[m][n] a[m][k] a_scale[m/rpi][k]. */
 int dfv_pw_wgrad(const void* g, const void* a, const void* a_scale, int rows_per_image, float* dw, int dtype, long long M,
                  int K, int N, dfv_stream_t stream);

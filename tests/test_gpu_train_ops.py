@@ -235,6 +235,46 @@ def test_se_train(ops, shape, dtype):
     assert rel(got, dd_ref) < 5e-5
 
 
+@pytest.mark.parametrize("shape", [(4, 12, 12, 1632, 68), (3, 24, 24, 672, 28), (2, 48, 47, 336, 14), (64, 5, 5, 48, 12)])
+def test_gated_bn_se_bwd_in_one_reduction_pass(ops, shape):
+    """bf16 training path of a block's depthwise output: BatchNorm(batch statistics) -> swish -> SE gate.  The fused sequence
+    (reduction with the gate / dpool terms deferred, SE backward on its dot partials, finalize, apply) against autograd in fp32 on
+    the same bf16 tensors -- d raw, gamma / beta gradients, dpool and the four SE parameter gradients."""
+    B, H, W, C, sq = shape
+    dtype = torch.bfloat16
+    x = (rnd(dtype, B, H, W, C, seed=1) * 1.3 + 0.2).to(dtype).float().requires_grad_(True)
+    gamma = (rnd(torch.float32, C, seed=2) * 0.3 + 1.0).requires_grad_(True)
+    beta = (rnd(torch.float32, C, seed=3) * 0.3).requires_grad_(True)
+    w1 = (rnd(torch.float32, sq, C, seed=4) * 0.2).requires_grad_(True)
+    b1 = (rnd(torch.float32, sq, seed=5) * 0.2).requires_grad_(True)
+    w2 = (rnd(torch.float32, C, sq, seed=6) * 0.2).requires_grad_(True)
+    b2 = (rnd(torch.float32, C, seed=7) * 0.2).requires_grad_(True)
+    da = rnd(dtype, B, H, W, C, seed=8)
+    d = silu(F.batch_norm(x.permute(0, 3, 1, 2), None, None, gamma, beta, True, 0.0, 1e-3)).permute(0, 2, 3, 1)
+    pooled = d.mean((1, 2))
+    gate = torch.sigmoid(F.linear(silu(F.linear(pooled, w1, b1)), w2, b2))
+    gate_used = gate + (gate.detach().to(dtype).float() - gate.detach())          # the forward applies the bf16-rounded gate
+    (d * gate_used.view(B, 1, 1, C)).backward(da)
+
+    xd = x.detach().to(DEV, dtype)
+    mean, invstd = ops.bn_stats(xd, 1e-3)
+    dk, pool = ops.bn_act(xd, mean, invstd, gamma.detach().to(DEV), beta.detach().to(DEV), act=1, want_pool=True)
+    g, pooled_k, h1, g32 = ops.se_train_fwd(pool, H * W, w1.detach().to(DEV), b1.detach().to(DEV), w2.detach().to(DEV), b2.detach().to(DEV), dtype)
+    dx, dgamma, dbeta, dpool, dw1, db1, dw2, db2 = ops.gated_bn_se_bwd(da.to(DEV, dtype), xd, mean, invstd, gamma.detach().to(DEV),
+                                                                     beta.detach().to(DEV), g, g32, pooled_k, h1, w1.detach().to(DEV),
+                                                                     w2.detach().to(DEV))
+    assert rel(dx, x.grad) < 2e-2
+    assert rel(dgamma, gamma.grad) < 1e-2 and rel(dbeta, beta.grad) < 1e-2
+    for got, want in ((dw1, w1.grad), (db1, b1.grad), (dw2, w2.grad), (db2, b2.grad)):
+        assert rel(got, want) < 1e-2          # d is bf16-rounded in the stored tensor, recomputed in fp32 here
+    # and against the two-pass path it replaces (the SE backward reading the stored bf16 d): same numbers to bf16 noise
+    dpool2, dw1b, db1b, dw2b, db2b = ops.se_bwd(da.to(DEV, dtype), dk, g32, pooled_k, h1, w1.detach().to(DEV), w2.detach().to(DEV))
+    dx2, dgamma2, dbeta2 = ops.act_bn_bwd(da.to(DEV, dtype), xd, mean, invstd, gamma.detach().to(DEV), beta.detach().to(DEV), act=1, gate=g,
+                                          dpool=dpool2, inv_hw=1.0 / (H * W))
+    assert rel(dpool, dpool2) < 5e-3 and rel(dw2, dw2b) < 5e-3 and rel(dw1, dw1b) < 5e-3
+    assert rel(dgamma, dgamma2) < 5e-3 and rel(dbeta, dbeta2) < 5e-3 and rel(dx, dx2) < 1e-2
+
+
 # ------------------------------------------------------------------------------- HybridAttention
 def _oracle_attention(C):
     from oracle import refmodel
