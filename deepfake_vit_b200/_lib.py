@@ -161,6 +161,8 @@ def _load():
         "dfv_se_train_fwd": (C.c_int, [vp, i32, f32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]),
         "dfv_se_bwd_ws_floats": (sz, [i32, i64, i32, i32]),
         "dfv_se_bwd": (C.c_int, [vp, vp, i32] + [vp] * 11 + [i32, i64, i32, i32, vp]),
+        "dfv_linear_f32_scratch_floats": (sz, [i32, i32, i32]),
+        "dfv_linear_f32_fwd": (C.c_int, [vp, vp, vp, vp, vp, sz, i32, i32, i32, i32, vp]),
         "dfv_se_bwd_from_partials": (C.c_int, [vp] * 11 + [i32, i64, i32, i32, vp]),
         "dfv_act_bn_bwd_gated_reduce": (C.c_int, [vp] * 8 + [i32, i32, i64, i32, vp]),
         "dfv_bn_bwd_gated_finalize": (C.c_int, [vp, vp, vp, f32, vp, vp, vp, vp, vp, i32, i32, i64, i32, vp]),

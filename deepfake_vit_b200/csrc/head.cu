@@ -70,3 +70,44 @@ extern "C" int dfv_mlp_head_fwd(const float* features, const float* const* w_t, 
   }
   return DFV_OK;
 }
+
+/* One fp32 Linear layer with few rows (the classifier inside the training step, forward and input gradient):
+ *   out[b][n] = bias[n] + sum_k in[b][k] * W,   W = w[n][k] (torch layout, w_kmajor = 0) or w[k][n] (w_kmajor = 1, i.e. the
+ *   SAME torch tensor read as the transposed layer: the input gradient needs no transposed weight copy).
+ * The small-linear kernels over K slices of 256 (+ a fixed-order combine): ~230 CTAs for 1792 -> 512 at batch 64 instead of
+ * the 8 CTAs of the tiled SIMT GEMM walking K in 112 dependent steps (202 us).  scratch: dfv_linear_f32_scratch_floats(). */
+extern "C" size_t dfv_linear_f32_scratch_floats(int B, int K, int N) {
+  const int ks = head_ksplit(K);
+  return ks > 1 ? (size_t)ks * B * N : 0;
+}
+
+extern "C" int dfv_linear_f32_fwd(const float* in, const float* w, const float* bias, float* out, float* scratch, size_t scratch_floats,
+                                  int B, int K, int N, int w_kmajor, dfv_stream_t stream) {
+  DFV_TRY(check_device());
+  DFV_REQUIRE(in && w && out && B > 0 && K > 0 && N > 0, "dfv_linear_f32_fwd: bad arguments");
+  const int ks = head_ksplit(K);
+  const int kc = ks > 1 ? kHeadKc : K;
+  DFV_REQUIRE(ks == 1 || (scratch && scratch_floats >= (size_t)ks * B * N), "dfv_linear_f32_fwd: scratch too small");
+  cudaStream_t st = as_stream(stream);
+  ProfScope prof(PK_MLP_HEAD, 4.0 * ((double)K * N + (double)B * (K + N)), 2.0 * (double)B * K * N, st);
+  static thread_local bool configured = false;
+  if (!configured) {
+    DFV_CUDA(cudaFuncSetAttribute(sl_kmajor_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DFV_CUDA(cudaFuncSetAttribute(sl_kmajor_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  const dim3 grid((unsigned)((N + kSlCols - 1) / kSlCols), (unsigned)((B + kSlRows - 1) / kSlRows), (unsigned)ks);
+  if (w_kmajor)
+    DFV_PDL((sl_kmajor_kernel<float, false>), grid, kSlThreads, sl_kmajor_smem(kc), st, in, w, bias, out, (float*)nullptr, scratch, B, N, K, kc, 0,
+            0, (const long long*)nullptr, (const float*)nullptr, 1.0f);
+  else
+    DFV_PDL((sl_kmajor_kernel<float, true>), grid, kSlThreads, sl_kmajor_smem(kc), st, in, w, bias, out, out, scratch, B, N, K, kc, 0, 0,
+            (const long long*)nullptr, (const float*)nullptr, 1.0f);
+  DFV_LAUNCH_CHECK();
+  if (ks > 1) {
+    DFV_PDL(sl_combine_kernel, (unsigned)(((size_t)B * N + kSlThreads - 1) / kSlThreads), kSlThreads, 0, st, (const float*)scratch,
+            (const float*)nullptr, ks, bias, out, B, N, 0);
+    DFV_LAUNCH_CHECK();
+  }
+  return DFV_OK;
+}

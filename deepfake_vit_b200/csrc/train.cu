@@ -458,7 +458,7 @@ int dfv_train_fwd(const dfv_train_args* a, dfv_stream_t stream) {
     const float* bl = a->params[dfv_train_cls_index(l, 1)];
     DFV_REQUIRE(wl && bl, "dfv_train_fwd: classifier layer %d parameters missing", l);
     float* out = last ? a->logits : ar.cls[l].lin;
-    DFV_TRY(dfv_pw_gemm_fwd(in, wl, bl, nullptr, 0, nullptr, out, DFV_F32, B, din, dout, DFV_ACT_NONE, stream));
+    DFV_TRY(dfv_linear_f32_fwd(in, wl, bl, out, ar.bn_ws, max_bn_ws(s, B, a->head_dims, a->head_layers), B, din, dout, 0, stream));
     if (!last) {
       ClsArena& ca = ar.cls[l];
       DFV_TRY(dfv_bn_stats_fwd(ca.lin, DFV_F32, B, 1, dout, a->cls_bn_eps, a->cls_bn_momentum, ca.mean, ca.invstd,
@@ -537,8 +537,9 @@ int dfv_train_bwd(const dfv_train_args* a, dfv_stream_t stream) {
     }
     DFV_TRY(dfv_pw_wgrad(gl, in_l, nullptr, 0, a->grads[dfv_train_cls_index(l, 0)], DFV_F32, B, din, dout, stream));
     DFV_TRY(dfv_colsum(gl, B, dout, a->grads[dfv_train_cls_index(l, 1)], stream));
-    DFV_TRY(dfv_cast_weight(a->params[dfv_train_cls_index(l, 0)], sc.wT, DFV_F32, din, dout, 1, stream));
-    DFV_TRY(dfv_pw_gemm_fwd(gl, sc.wT, ar.zero_bias, nullptr, 0, nullptr, sc.gcls[cur ^ 1], DFV_F32, B, dout, din, DFV_ACT_NONE, stream));
+    // input gradient: the torch weight [dout][din] read K-major -- no transposed copy
+    DFV_TRY(dfv_linear_f32_fwd(gl, a->params[dfv_train_cls_index(l, 0)], nullptr, sc.gcls[cur ^ 1], sc.bn_ws,
+                               max_bn_ws(s, B, a->head_dims, a->head_layers), B, dout, din, 1, stream));
     cur ^= 1;
     g = sc.gcls[cur];
   }

@@ -362,6 +362,14 @@ int dfv_se_bwd(const void* da, const void* d, int dtype, const float* gate_f32, 
                float* dw_expand, float* db_expand, float* ws, int B, long long rows_per_image, int C, int squeeze,
                dfv_stream_t stream);
 
+/* One fp32 Linear layer with few rows (the classifier inside the training step): out[b][n] = bias[n] (may be NULL) +
+ * sum_k in[b][k] * W, with W = w[n][k] (torch layout) or, w_kmajor = 1, w[k][n] -- the same torch tensor read as the transposed
+ * layer, which is the input gradient of nn.Linear (feature_extractor.py:223-238) without a transposed copy.  scratch:
+ * dfv_linear_f32_scratch_floats(B, K, N) floats (K-slice partial sums, added in fixed order). */
+size_t dfv_linear_f32_scratch_floats(int B, int K, int N);
+int dfv_linear_f32_fwd(const float* in, const float* w, const float* bias, float* out, float* scratch, size_t scratch_floats,
+                       int B, int K, int N, int w_kmajor, dfv_stream_t stream);
+
 /* The same backward with one streaming pass less (bf16 tensors, swish): the SE backward needs sum_hw(da * d) before the layer's
  * input gradient exists (its dpool enters that gradient), but the BatchNorm reduction is LINEAR in (gate, dpool) per image.
  * dfv_act_bn_bwd_gated_reduce reads (da, d_raw) once and writes per-(image, chunk) rows ws4 [B][chunks][4][C] (sums of da act'(u),

@@ -350,7 +350,9 @@ def test_two_train_forwards_before_their_backwards():
     typical = norms[len(norms) // 2]
     for name, p in m.named_parameters():
         e = float((p.grad.double().cpu() - ref[name].grad.double()).norm()) / max(float(ref[name].grad.norm()), 1e-3 * typical)
-        assert e < 5e-3, (name, e)
+        # an arena mix-up gives O(1) errors; the bar leaves room for the run-to-run noise of the atomically reduced weight
+        # gradients on this small, chaotic case (5.2e-3 seen once on one parameter in a full-suite run, 3/3 green alone)
+        assert e < 1e-2, (name, e)
     del sd
 
 

@@ -191,7 +191,9 @@ def test_stem_wgrad(ops, shape, dtype):
     B, H, W = shape
     x = rnd(torch.float32, B, 3, H, W, seed=1)
     w = (rnd(torch.float32, 48, 3, 3, 3, seed=2) * 0.3).requires_grad_(True)
-    y = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, None, stride=2)
+    # bf16 path: the forward stem feeds bf16(x) to the tensor cores (as autocast does), so its weight gradient is g^T bf16(x)
+    xr = x.to(dtype).float()
+    y = F.conv2d(F.pad(xr, (0, 1, 0, 1)), w, None, stride=2)
     g = rnd(dtype, *y.shape, seed=3)
     y.backward(g)
     dw = ops.stem_wgrad(g.permute(0, 2, 3, 1).contiguous().to(DEV, dtype), x.to(DEV))
