@@ -137,6 +137,48 @@ struct DwDgParams {
   int pad;
 };
 
+// One dx row of a thread's strip (4 pixels x 8 channels) with the tap parities known at COMPILE time: KH0 = (hi + pad) & 1 picks
+// the kernel rows, P = pad & 1 the kernel columns of every pixel (the strip starts at a multiple of 4).  Per kernel row the
+// (at most 5) g columns the strip touches are loaded ONCE into registers and every weight vector once; the first version
+// computed each tap's tile address and loaded g and w per (pixel, tap): ~27 instructions per 8 FMAs, 308 us for the 144-channel
+// 190 -> 95 layer at batch 64.
+template <typename T, int K, int KH0, int P>
+__device__ __forceinline__ void dw_dgrad_s2_row(const T* __restrict__ gt, const float* __restrict__ wrow0, int TWg, int CB, int ho_base,
+                                                int col_base, float (&acc)[4][8]) {
+  constexpr int OFF_LO = -((K - 1) / 2), NOFF = 2 - OFF_LO + 1;      // column offsets (l + P - kw) / 2, l < 4, kw < K
+#pragma unroll
+  for (int t = 0; t < (K + 1) / 2; ++t) {
+    constexpr int dummy = 0; (void)dummy;
+    const int kh = KH0 + 2 * t;
+    if (kh >= K) break;
+    // tile-local g row of this kernel row: ((hi + pad - kh) >> 1) - glo_h = ho_base - t
+    const T* grow = gt + ((size_t)(ho_base - t) * TWg + col_base) * CB;
+    float gv[NOFF][8];
+#pragma unroll
+    for (int o = 0; o < NOFF; ++o) {
+      bool used = false;
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) used = used || (((l + P - kw) & 1) == 0 && (l + P - kw) / 2 == OFF_LO + o && (l + P - kw) >= 2 * OFF_LO);
+      if (used) load8(grow + (OFF_LO + o) * CB, gv[o]);
+    }
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) {
+      float wv[8];
+      load8(wrow0 + (size_t)(kh * K + kw) * CB, wv);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        if (((l + P - kw) & 1) != 0) continue;
+        constexpr int unused = 0; (void)unused;
+        const int o = (l + P - kw + 2 * (K - 1)) / 2 - (K - 1) - OFF_LO;      // (l + P - kw) / 2 - OFF_LO without dividing a negative
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[l][e] = fmaf(gv[o][e], wv[e], acc[l][e]);
+      }
+    }
+  }
+}
+
 template <typename T, int K>
 __global__ void __launch_bounds__(256, 2) dw_dgrad_s2_kernel(const __grid_constant__ CUtensorMap tm_g, const float* __restrict__ w,
                                                             T* __restrict__ dx, DwDgParams p) {
@@ -193,31 +235,17 @@ __global__ void __launch_bounds__(256, 2) dw_dgrad_s2_kernel(const __grid_consta
       for (int l = 0; l < L; ++l)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[l][e] = 0.f;
-      const int kh0 = (hi + p.pad) & 1;          // taps with (hi + pad - kh) even
-#pragma unroll
-      for (int th2 = 0; th2 < (K + 1) / 2; ++th2) {
-        const int kh = kh0 + 2 * th2;
-        if (kh < K) {
-          const int ho_t = ((hi + p.pad - kh) >> 1) - glo_h;       // tile-local g row (the numerator is even)
-          const T* grow = gt + (size_t)ho_t * p.TWg * p.CB;
-#pragma unroll
-          for (int l = 0; l < L; ++l) {
-            const int wi = wi0 + l;
-            const int kw0 = (wi + p.pad) & 1;
-#pragma unroll
-            for (int tw2 = 0; tw2 < (K + 1) / 2; ++tw2) {
-              const int kw = kw0 + 2 * tw2;
-              if (kw < K) {
-                const int wo_t = ((wi + p.pad - kw) >> 1) - glo_w;
-                float gv[8], wv[8];
-                load8(grow + (size_t)wo_t * p.CB, gv);
-                load8(wsm + (size_t)(kh * K + kw) * p.CB + g * 8, wv);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[l][e] = fmaf(gv[e], wv[e], acc[l][e]);
-              }
-            }
-          }
-        }
+      // taps with (hi + pad - kh) even and (wi + pad - kw) even: both parities resolved at compile time (dw_dgrad_s2_row)
+      const int kh0 = (hi + p.pad) & 1, pw = p.pad & 1;
+      const int ho_base = ((hi + p.pad - kh0) >> 1) - glo_h;          // tile-local g row of kernel row kh0
+      const int col_base = ((wi0 + p.pad - pw) >> 1) - glo_w;         // tile-local g column of column offset 0 (wi0 is a multiple of 4)
+      const float* wrow0 = wsm + g * 8;
+      if (kh0 == 0) {
+        if (pw == 0) dw_dgrad_s2_row<T, K, 0, 0>(gt, wrow0, p.TWg, p.CB, ho_base, col_base, acc);
+        else dw_dgrad_s2_row<T, K, 0, 1>(gt, wrow0, p.TWg, p.CB, ho_base, col_base, acc);
+      } else {
+        if (pw == 0) dw_dgrad_s2_row<T, K, 1, 0>(gt, wrow0, p.TWg, p.CB, ho_base, col_base, acc);
+        else dw_dgrad_s2_row<T, K, 1, 1>(gt, wrow0, p.TWg, p.CB, ho_base, col_base, acc);
       }
       T* out = dx + (((size_t)b * p.H + hi) * p.W + wi0) * p.C + c0 + g * 8;
 #pragma unroll
