@@ -22,8 +22,13 @@ struct AttnSaved {
   float* gate_p;   // [B][P]
 };
 
+// One CTA of 1024 threads per image.  The first version ran 256 threads with one thread per 8-channel vector walking all
+// positions and one warp per row of W1: ~28 KB of map and 8 KB of weights in flight per SM, 226 us at batch 64 for 33 MB of
+// map (5 % of the HBM roofline).  Now kTrPhases threads share a vector and take every kTrPhases-th position (partials meet in
+// shared memory in a fixed order), 32 warps walk W1 / W2 with 14 / 4 rows x 128 B in flight each.
+constexpr int kTrPhases = 4;
 template <typename T>
-__global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
+__global__ void __launch_bounds__(1024) hybrid_attention_train_fwd_kernel(
     const T* __restrict__ fmap, const float* __restrict__ heat, const float* __restrict__ w1,
     const float* __restrict__ w2, const float* __restrict__ sa_w, float* __restrict__ features, AttnSaved sv, int H,
     int W, int C, int hidden, int use_channel, int use_spatial) {
@@ -38,51 +43,76 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
   float* sp_mean = hid + hidden;
   float* sp_max = sp_mean + HW;
   float* gate_p = sp_max + HW;
+  float* red = gate_p + HW;                                       // [kTrPhases - 1][3][C]: partial sum / max / argmax of a position phase
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const T* fb = fmap + (size_t)b * HW * C;
   const int CV = C >> 3;
   const float inv_hw = 1.0f / (float)HW;
+  const int nvec = blockDim.x / kTrPhases;                        // 8-channel vectors per sweep
+  const int ph = tid / nvec, lv = tid % nvec;
 
   for (int p = tid; p < HW; p += blockDim.x) a_lm[p] = heat ? heat[(size_t)b * HW + p] : 1.0f;
   __syncthreads();
 
   if (use_channel) {
-    for (int cv = tid; cv < CV; cv += blockDim.x) {
+    for (int cv0 = 0; cv0 < CV; cv0 += nvec) {
+      const int cv = cv0 + lv;
       float s[8], m[8];
       int mi[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { s[e] = 0.f; m[e] = -INFINITY; mi[e] = 0; }
-      #pragma unroll 8
-      for (int p = 0; p < HW; ++p) {
-        float v[8];
-        load8(fb + (size_t)p * C + cv * 8, v);
-        const float a = a_lm[p];
+      if (cv < CV) {
+#pragma unroll 4
+        for (int p = ph; p < HW; p += kTrPhases) {
+          float v[8];
+          load8(fb + (size_t)p * C + cv * 8, v);
+          const float a = a_lm[p];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float x = v[e] * a;
-          s[e] += x;
-          if (x > m[e]) { m[e] = x; mi[e] = p; }
+          for (int e = 0; e < 8; ++e) {
+            const float x = v[e] * a;
+            s[e] += x;
+            if (x > m[e]) { m[e] = x; mi[e] = p; }
+          }
+        }
+        if (ph > 0) {
+          float* r = red + (size_t)(ph - 1) * 3 * C + cv * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { r[e] = s[e]; r[C + e] = m[e]; r[2 * C + e] = __int_as_float(mi[e]); }
         }
       }
+      __syncthreads();
+      if (ph == 0 && cv < CV) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cv * 8 + e;
-        avg_c[c] = s[e] * inv_hw;
-        max_c[c] = m[e];
-        sv.avg[(size_t)b * C + c] = s[e] * inv_hw;
-        sv.mx[(size_t)b * C + c] = m[e];
-        sv.mx_idx[(size_t)b * C + c] = mi[e];
+        for (int q = 0; q < kTrPhases - 1; ++q) {                 // fixed order; the FIRST position of the maximum wins (torch's argmax)
+          const float* r = red + (size_t)q * 3 * C + cv * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            s[e] += r[e];
+            const float om = r[C + e];
+            const int oi = __float_as_int(r[2 * C + e]);
+            if (om > m[e] || (om == m[e] && oi < mi[e])) { m[e] = om; mi[e] = oi; }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = cv * 8 + e;
+          avg_c[c] = s[e] * inv_hw;
+          max_c[c] = m[e];
+          sv.avg[(size_t)b * C + c] = s[e] * inv_hw;
+          sv.mx[(size_t)b * C + c] = m[e];
+          sv.mx_idx[(size_t)b * C + c] = mi[e];
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
     for (int j = warp; j < hidden; j += nwarps) {
       const float* wr = w1 + (size_t)j * C;
       float sa = 0.f, sx = 0.f;
-      #pragma unroll 8
+#pragma unroll 14
       for (int c = lane; c < C; c += 32) {
-        const float wv = wr[c];
+        const float wv = __ldg(wr + c);
         sa = fmaf(wv, avg_c[c], sa);
         sx = fmaf(wv, max_c[c], sx);
       }
@@ -95,13 +125,22 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
       }
     }
     __syncthreads();
-    for (int c = tid; c < C; c += blockDim.x) {
-      float s = 0.f;
-      #pragma unroll 8
-      for (int j = 0; j < hidden; ++j) s = fmaf(w2[(size_t)c * hidden + j], hid[j], s);
-      const float g = sigmoid_exact(s);
-      gate_c[c] = g;
-      sv.gate_c[(size_t)b * C + c] = g;
+    // W2 [C][hidden]: one warp per group of four rows, lanes along the row (coalesced; a thread per row read 32 sectors per request)
+    for (int c0 = warp * 4; c0 < C; c0 += nwarps * 4) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = lane; j < hidden; j += 32) {
+        const float h = hid[j];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (c0 + u < C) s[u] = fmaf(__ldg(w2 + (size_t)(c0 + u) * hidden + j), h, s[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s[u] = warp_sum(s[u]);
+      if (lane < 4 && c0 + lane < C) {
+        const float g = sigmoid_exact(lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3]);
+        gate_c[c0 + lane] = g;
+        sv.gate_c[(size_t)b * C + c0 + lane] = g;
+      }
     }
   } else {
     for (int c = tid; c < C; c += blockDim.x) gate_c[c] = 1.0f;
@@ -162,20 +201,38 @@ __global__ void __launch_bounds__(256) hybrid_attention_train_fwd_kernel(
   }
   __syncthreads();
 
-  for (int cv = tid; cv < CV; cv += blockDim.x) {
-    float s[8], gc[8];
+  for (int cv0 = 0; cv0 < CV; cv0 += nvec) {
+    const int cv = cv0 + lv;
+    float s[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { s[e] = 0.f; gc[e] = gate_c[cv * 8 + e]; }
-    #pragma unroll 8
-    for (int p = 0; p < HW; ++p) {
-      float v[8];
-      load8(fb + (size_t)p * C + cv * 8, v);
-      const float a = a_lm[p], g = gate_p[p];
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    if (cv < CV) {
+      float gc[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] += ((v[e] * a) * gc[e]) * g;
+      for (int e = 0; e < 8; ++e) gc[e] = gate_c[cv * 8 + e];
+#pragma unroll 4
+      for (int p = ph; p < HW; p += kTrPhases) {
+        float v[8];
+        load8(fb + (size_t)p * C + cv * 8, v);
+        const float a = a_lm[p], g = gate_p[p];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += ((v[e] * a) * gc[e]) * g;
+      }
+      if (ph > 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[(size_t)(ph - 1) * C + cv * 8 + e] = s[e];
+      }
     }
+    __syncthreads();
+    if (ph == 0 && cv < CV) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) features[(size_t)b * C + cv * 8 + e] = s[e] * inv_hw;
+      for (int q = 0; q < kTrPhases - 1; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += red[(size_t)q * C + cv * 8 + e];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) features[(size_t)b * C + cv * 8 + e] = s[e] * inv_hw;
+    }
+    __syncthreads();
   }
 }
 
@@ -285,30 +342,46 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
 
   if (use_channel) {
     // S3: d gc[c] = sum_p dx2[p][c] * x1[p][c];  dz = dgc * gc (1 - gc)
-    for (int cv = tid; cv < CV; cv += blockDim.x) {
-      float s[8];
+    // two position phases per 8-channel vector (even / odd positions; the odd half's partial sums pass through `davg`, which S5
+    // overwrites afterwards): one thread per vector left half of the CTA idle with 28 KB in flight
+    {
+      constexpr int kPh = 2;
+      const int nvec = blockDim.x / kPh, ph = tid / nvec, lv = tid % nvec;
+      for (int cv0 = 0; cv0 < CV; cv0 += nvec) {
+        const int cv = cv0 + lv;
+        float s[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] = 0.f;
-      #pragma unroll 8
-      for (int p = 0; p < HW; ++p) {
-        float v[8];
-        load8(fb + (size_t)p * C + cv * 8, v);
-        const float a = a_lm[p], g = gate_p[p], dm = dsm[p] * inv_c, dxv = dsx[p];
-        const int si = sp_idx[p];
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        if (cv < CV) {
+          #pragma unroll 8
+          for (int p = ph; p < HW; p += kPh) {
+            float v[8];
+            load8(fb + (size_t)p * C + cv * 8, v);
+            const float a = a_lm[p], g = gate_p[p], dm = dsm[p] * inv_c, dxv = dsx[p];
+            const int si = sp_idx[p];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = cv * 8 + e;
-          const float dx2 = fmaf(dfc[c], g, dm) + (c == si ? dxv : 0.f);
-          s[e] = fmaf(dx2, v[e] * a, s[e]);
+            for (int e = 0; e < 8; ++e) {
+              const int c = cv * 8 + e;
+              const float dx2 = fmaf(dfc[c], g, dm) + (c == si ? dxv : 0.f);
+              s[e] = fmaf(dx2, v[e] * a, s[e]);
+            }
+          }
+          if (ph > 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) davg[cv * 8 + e] = s[e];
+          }
         }
-      }
+        __syncthreads();
+        if (ph == 0 && cv < CV) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = cv * 8 + e;
-        const float g = gate_c[c];
-        const float v = s[e] * g * (1.f - g);
-        dzs[c] = v;
-        dz_out[(size_t)b * C + c] = v;
+          for (int e = 0; e < 8; ++e) {
+            const int c = cv * 8 + e;
+            const float g = gate_c[c];
+            const float v = (s[e] + davg[c]) * g * (1.f - g);
+            dzs[c] = v;
+            dz_out[(size_t)b * C + c] = v;
+          }
+        }
       }
     }
     __syncthreads();
@@ -318,8 +391,8 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
       const int j = tid % hidden, qd = tid / hidden;
       const int c0 = (int)((long long)C * qd / nq), c1 = (int)((long long)C * (qd + 1) / nq);
       float s = 0.f;
-      #pragma unroll 8
-      for (int c = c0; c < c1; ++c) s = fmaf(dzs[c], w2[(size_t)c * hidden + j], s);
+      #pragma unroll 32
+      for (int c = c0; c < c1; ++c) s = fmaf(dzs[c], __ldg(w2 + (size_t)c * hidden + j), s);      // 32 rows in flight per thread (8: 14 KB per SM)
       part[qd * hidden + j] = s;
     }
     __syncthreads();
@@ -337,9 +410,9 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
     // S5: d avg[c], d max[c]
     for (int c = tid; c < C; c += blockDim.x) {
       float sa = 0.f, sx = 0.f;
-      #pragma unroll 8
+      #pragma unroll 28
       for (int j = 0; j < hidden; ++j) {
-        const float wv = w1[(size_t)j * C + c];
+        const float wv = __ldg(w1 + (size_t)j * C + c);
         sa = fmaf(dh[j], wv, sa);
         sx = fmaf(dh[hidden + j], wv, sx);
       }
@@ -521,7 +594,7 @@ int dfv_hybrid_attention_train_fwd(const void* fmap, const float* heat, const fl
   DFV_REQUIRE(!use_spatial || sa_w, "dfv_hybrid_attention_train_fwd: spatial attention needs weights");
   DFV_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "dfv_hybrid_attention_train_fwd: bad shape (C %% 8 == 0)");
   if (!use_channel) hidden = 0;
-  const size_t smem = sizeof(float) * ((size_t)4 * H * W + 3 * (size_t)C + (size_t)hidden);
+  const size_t smem = sizeof(float) * ((size_t)4 * H * W + 3 * (size_t)C + (size_t)hidden + (size_t)(kTrPhases - 1) * 3 * C);
   DFV_REQUIRE(smem <= 200 * 1024, "dfv_hybrid_attention_train_fwd: map too large for one CTA");
   cudaStream_t st = as_stream(stream);
   AttnSaved sv;
@@ -530,11 +603,11 @@ int dfv_hybrid_attention_train_fwd(const void* fmap, const float* heat, const fl
   if (dtype == DFV_BF16) {
     auto k = hybrid_attention_train_fwd_kernel<__nv_bfloat16>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DFV_PDL((k), B, 256, smem, st, (const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
+    DFV_PDL((k), B, 1024, smem, st, (const __nv_bfloat16*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
   } else {
     auto k = hybrid_attention_train_fwd_kernel<float>;
     if (smem > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DFV_PDL((k), B, 256, smem, st, (const float*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
+    DFV_PDL((k), B, 1024, smem, st, (const float*)fmap, heat, ca_w1, ca_w2, sa_w, features, sv, H, W, C, hidden, use_channel, use_spatial);
   }
   DFV_LAUNCH_CHECK();
   return DFV_OK;

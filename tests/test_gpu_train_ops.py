@@ -291,8 +291,18 @@ def _oracle_attention(C):
 @pytest.mark.parametrize("cfg", [(True, True, True), (False, True, True), (True, False, True), (True, True, False), (False, False, False)])
 @pytest.mark.parametrize("dtype", DT)
 def test_hybrid_attention_train_fwd_bwd(ops, cfg, dtype):
+    _attention_train_case(ops, cfg, dtype, 3, 6, 6, 256)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_hybrid_attention_train_head_shape(ops, dtype):
+    """The shape the training step runs (12 x 12 x 1792 map, hidden 112): every position phase / vector sweep of the 1024-thread
+    forward and the two-phase S3 of the backward carries work, and the argmax of a channel falls in any of the four phases."""
+    _attention_train_case(ops, (True, True, True), dtype, 5, 12, 12, 1792)
+
+
+def _attention_train_case(ops, cfg, dtype, B, H, W, C):
     use_lm, use_c, use_s = cfg
-    B, H, W, C = 3, 6, 6, 256
     att = _oracle_attention(C)
     att.use_channel, att.use_spatial = use_c, use_s
     x = (rnd(dtype, B, C, H, W, seed=1) * 0.8).to(dtype).float().requires_grad_(True)
