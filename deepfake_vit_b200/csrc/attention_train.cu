@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
   int* mx_idx = reinterpret_cast<int*>(dmx + C);    // [C]
   float* part = reinterpret_cast<float*>(mx_idx + C);   // [4][hidden]
   float* dh = part + 4 * hidden;    // [2][hidden]
+  float* pdA = dh + 2 * hidden;     // [warps][HW]  per-warp partial sums of dA (S6)
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
     spx[p] = use_spatial ? sv.sp_max[(size_t)b * HW + p] : 0.f;
     dt[p] = dsm[p] = dsx[p] = 0.f;
   }
+  for (int i = tid; i < nwarps * HW; i += blockDim.x) pdA[i] = 0.f;
   for (int c = tid; c < C; c += blockDim.x) {
     gate_c[c] = use_channel ? sv.gate_c[(size_t)b * C + c] : 1.0f;
     mx_idx[c] = use_channel ? sv.mx_idx[(size_t)b * C + c] : -1;
@@ -325,17 +327,19 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
       dsm[q] = s0;
       dsx[q] = s1;
     }
-    if (tid < 98) {
-      const int ch = tid / 49, ky = (tid % 49) / 7, kx = tid % 7;
+    // conv weight gradient: one warp per tap, lanes over positions (98 threads walking all positions one after the other kept the
+    // other 400 waiting for ~3 k dependent instructions)
+    for (int t = warp; t < 98; t += nwarps) {
+      const int ch = t / 49, ky = (t % 49) / 7, kx = t % 7;
       const float* in = ch ? spx : spm;
       float s = 0.f;
-      #pragma unroll 8
-      for (int p = 0; p < HW; ++p) {
+      for (int p = lane; p < HW; p += 32) {
         const int yy = p / W + ky - 3, xx = p % W + kx - 3;
         if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
         s = fmaf(dt[p], in[yy * W + xx], s);
       }
-      atomicAdd(dsa_w + tid, s);
+      s = warp_sum(s);
+      if (lane == 0) atomicAdd(dsa_w + t, s);
     }
     __syncthreads();
   }
@@ -423,27 +427,64 @@ __global__ void __launch_bounds__(512) hybrid_attention_bwd_kernel(
   }
 
   // S6: dx1 = dx2 * gc + davg / P + [p == argmax_c] dmax;  dx = dx1 * A;  dA[p] = sum_c dx1 * x
-  for (int p = warp; p < HW; p += nwarps) {
-    const float a = a_lm[p], g = gate_p[p], dm = dsm[p] * inv_c, dxv = dsx[p];
-    const int si = sp_idx[p];
-    float sA = 0.f;
-    #pragma unroll 8
-    for (int cv = lane; cv < CV; cv += 32) {
-      float v[8], o[8];
-      const size_t off = (size_t)p * C + cv * 8;
-      load8(fb + off, v);
+  // thread = (8-channel vector, position phase): the five per-channel terms live in registers for the whole walk over the
+  // positions and only the per-position scalars come from shared memory.  (One warp per position read five shared arrays per
+  // ELEMENT at an 8-word lane stride: 57 % of the kernel's stall samples sat on those two lines, ~140 of 247 us.)  The
+  // per-position sum over channels goes through one shuffle reduction per warp into pdA[warp][p], summed in a fixed order.
+  {
+    constexpr int kPh = 2, kPB = 4;
+    const int nvec = blockDim.x / kPh, ph = tid / nvec, lv = tid % nvec;      // nvec is a multiple of 32: a warp has one phase
+    T* dxb = dx + (size_t)b * HW * C;
+    for (int cv0 = 0; cv0 < CV; cv0 += nvec) {
+      const int cv = cv0 + lv;
+      const bool on = cv < CV;
+      float k_df[8], k_gc[8], k_da[8], k_dm[8];
+      int k_mi[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int c = cv * 8 + e;
-        const float dx2 = fmaf(dfc[c], g, dm) + (c == si ? dxv : 0.f);
-        const float dx1 = fmaf(dx2, gate_c[c], davg[c]) + (mx_idx[c] == p ? dmx[c] : 0.f);
-        sA = fmaf(dx1, v[e], sA);
-        o[e] = dx1 * a;
+        const int c = on ? cv * 8 + e : 0;
+        k_df[e] = dfc[c]; k_gc[e] = gate_c[c]; k_da[e] = davg[c]; k_dm[e] = dmx[c]; k_mi[e] = mx_idx[c];
       }
-      store8(dx + (size_t)b * HW * C + off, o);
+      for (int p0 = ph; p0 < HW; p0 += kPh * kPB) {
+        float v[kPB][8];
+#pragma unroll
+        for (int u = 0; u < kPB; ++u) {
+          const int p = p0 + u * kPh;
+          if (on && p < HW) load8(fb + (size_t)p * C + cv * 8, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kPB; ++u) {
+          const int p = p0 + u * kPh;
+          if (p < HW) {                      // warp-uniform
+            const float a = a_lm[p], g = gate_p[p], dm = dsm[p] * inv_c, dxv = dsx[p];
+            const int si = sp_idx[p];
+            float sA = 0.f;
+            if (on) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int c = cv * 8 + e;
+                const float dx2 = fmaf(k_df[e], g, dm) + (c == si ? dxv : 0.f);
+                const float dx1 = fmaf(dx2, k_gc[e], k_da[e]) + (k_mi[e] == p ? k_dm[e] : 0.f);
+                sA = fmaf(dx1, v[u][e], sA);
+                o[e] = dx1 * a;
+              }
+              store8(dxb + (size_t)p * C + cv * 8, o);
+            }
+            sA = warp_sum(sA);
+            if (lane == 0) pdA[warp * HW + p] += sA;
+          }
+        }
+      }
     }
-    sA = warp_sum(sA);
-    if (lane == 0 && dA) dA[(size_t)b * HW + p] = sA;
+    __syncthreads();
+    if (dA) {
+      for (int p = tid; p < HW; p += blockDim.x) {
+        float sA = 0.f;
+        for (int w = 0; w < nwarps; ++w) sA += pdA[w * HW + p];
+        dA[(size_t)b * HW + p] = sA;
+      }
+    }
   }
 }
 
@@ -630,7 +671,7 @@ int dfv_hybrid_attention_bwd(const void* fmap, const float* heat, const float* c
   DFV_REQUIRE(!heat || dheat, "dfv_hybrid_attention_bwd: dheat missing");
   if (!use_channel) hidden = 0;
   const int HW = H * W;
-  const size_t smem = sizeof(float) * ((size_t)8 * HW + 6 * (size_t)C + 6 * (size_t)hidden);
+  const size_t smem = sizeof(float) * ((size_t)(8 + 512 / 32) * HW + 6 * (size_t)C + 6 * (size_t)hidden);
   DFV_REQUIRE(smem <= 200 * 1024, "dfv_hybrid_attention_bwd: map too large for one CTA");
   cudaStream_t st = as_stream(stream);
   AttnSaved sv;

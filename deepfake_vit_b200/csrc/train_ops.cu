@@ -928,14 +928,20 @@ __global__ void __cluster_dims__(kSeBwdCluster, 1, 1) __launch_bounds__(256, 2)
   }
 }
 
-// Weight gradients, reduced over the batch.  grid = (ceil(C / 128), squeeze slices), thread = channel.
-__global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __restrict__ dz, const float* __restrict__ dh1,
-                                                            const float* __restrict__ pooled, const float* __restrict__ h1,
-                                                            float* __restrict__ dw1, float* __restrict__ db1,
-                                                            float* __restrict__ dw2, float* __restrict__ db2, int B, int C,
-                                                            int sq) {
+// Weight gradients, reduced over the batch.  grid = (ceil(C / 128), squeeze slices), thread = (channel, quarter of the batch):
+// the first version (thread = channel, 128 threads) walked the batch in four dependent groups of 16 load pairs, with the db2
+// column sum as four more in front of them on the first slice -- 33 us per layer at batch 64 for 1 MB of operands (ncu:
+// 20 warps waiting on long_scoreboard per issue).  Now every thread's 2 x B/4 loads are in flight at once, db2 rides the same
+// loads, and the four quarters meet in shared memory in a fixed order.
+constexpr int kSeWgQ = 4;
+__global__ void __launch_bounds__(128 * kSeWgQ) se_bwd_weights_kernel(const float* __restrict__ dz, const float* __restrict__ dh1,
+                                                                     const float* __restrict__ pooled, const float* __restrict__ h1,
+                                                                     float* __restrict__ dw1, float* __restrict__ db1,
+                                                                     float* __restrict__ dw2, float* __restrict__ db2, int B, int C,
+                                                                     int sq) {
   pdl_prologue();
   extern __shared__ float sm[];   // hidden [B][jn], dh1 [B][jn] of this slice
+  __shared__ float red[kSeWgQ - 1][9][128];
   const int j0 = (int)((long long)sq * blockIdx.y / gridDim.y), j1 = (int)((long long)sq * (blockIdx.y + 1) / gridDim.y);
   const int jn = j1 - j0;
   float* hid = sm;
@@ -947,19 +953,16 @@ __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __rest
     dh[i] = dh1[(size_t)b * sq + j];
   }
   __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    if (blockIdx.y == 0) {
-      float sb = 0.f;
+  const int cl = threadIdx.x & 127, q = threadIdx.x >> 7;
+  const int c = blockIdx.x * 128 + cl;
+  const int b0 = (int)((long long)B * q / kSeWgQ), b1 = (int)((long long)B * (q + 1) / kSeWgQ);
+  for (int jj = 0; jj < jn; jj += 4) {
+    float s2[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, sb = 0.f;
+    if (c < C) {
 #pragma unroll 16
-      for (int b = 0; b < B; ++b) sb += dz[(size_t)b * C + c];
-      db2[c] = sb;
-    }
-    for (int jj = 0; jj < jn; jj += 4) {
-      float s2[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 16      // sixteen batch rows' loads in flight (the plain loop was a chain of 64 dependent load pairs: 17 us)
-      for (int b = 0; b < B; ++b) {
-        const float z = dz[(size_t)b * C + c], pv = pooled[(size_t)b * C + c];
+      for (int b = b0; b < b1; ++b) {
+        const float z = __ldg(dz + (size_t)b * C + c), pv = __ldg(pooled + (size_t)b * C + c);
+        sb += z;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (jj + u < jn) {
@@ -968,6 +971,20 @@ __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __rest
           }
         }
       }
+    }
+    if (q > 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { red[q - 1][u][cl] = s2[u]; red[q - 1][4 + u][cl] = s1[u]; }
+      red[q - 1][8][cl] = sb;
+    }
+    __syncthreads();
+    if (q == 0 && c < C) {
+#pragma unroll
+      for (int r = 0; r < kSeWgQ - 1; ++r) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s2[u] += red[r][u][cl]; s1[u] += red[r][4 + u][cl]; }
+        sb += red[r][8][cl];
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (jj + u < jn) {
@@ -975,7 +992,9 @@ __global__ void __launch_bounds__(128) se_bwd_weights_kernel(const float* __rest
           dw1[(size_t)(j0 + jj + u) * C + c] = s1[u];
         }
       }
+      if (blockIdx.y == 0 && jj == 0) db2[c] = sb;
     }
+    __syncthreads();
   }
   if (blockIdx.x == 0) {
     for (int j = threadIdx.x; j < jn; j += blockDim.x) {
@@ -1388,7 +1407,7 @@ int dfv_se_bwd_from_partials(const float* gate_f32, const float* pooled, const f
   const size_t smem2 = (size_t)2 * B * jn_max * sizeof(float);
   DFV_REQUIRE(smem2 <= 160 * 1024, "dfv_se_bwd: batch too large for the weight-gradient kernel (B * squeeze slice = %d)", B * jn_max);
   if (smem2 > 48 * 1024) DFV_CUDA(cudaFuncSetAttribute(se_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  DFV_PDL(se_bwd_weights_kernel, dim3((C + 127) / 128, slices), 128, smem2, st, dz, dh1, pooled, h1, dw_reduce, db_reduce, dw_expand, db_expand, B, C, squeeze);
+  DFV_PDL(se_bwd_weights_kernel, dim3((C + 127) / 128, slices), 128 * kSeWgQ, smem2, st, dz, dh1, pooled, h1, dw_reduce, db_reduce, dw_expand, db_expand, B, C, squeeze);
   DFV_LAUNCH_CHECK();
   return DFV_OK;
 }
