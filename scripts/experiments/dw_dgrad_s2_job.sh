@@ -1,5 +1,7 @@
 #!/bin/bash
 # Same-box A/B of the stride-2 depthwise dgrad (previous build vs this build), then the GPU suite and the bench line on this build.
+# scripts/experiments/_ab/libdfvit_prev.so = the build to compare against (git stash / checkout the older sources, make, copy the .so there;
+# *.so is git-ignored but travels to the GPU box).
 mkdir -p gpurun_out
 cp deepfake_vit_b200/libdfvit.so /tmp/libdfvit_new.so
 cp scripts/experiments/_ab/libdfvit_prev.so deepfake_vit_b200/libdfvit.so
